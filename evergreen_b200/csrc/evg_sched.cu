@@ -1,0 +1,1214 @@
+// evg_sched.cu -- libevgsched.so: CUDA kernels (sm_100a) + the C-ABI of
+// include/evg_sched.h.  See DESIGN.md for the data layout and the kernel list.
+//
+// General path (any distro size), one tick = all distros concatenated:
+//   k_mark_dependents   dependency edges -> "has in-queue dependents" byte     (planner.go:449-456)
+//   k_task              per task: queue-info reduction (scheduler.go:56-159),
+//                       unit membership links (planner.go:431-447), score of
+//                       single-task units (planner.go:209-337)
+//   k_unit              per (unit, member) pair: Unit.info reduction, score,
+//                       canonical tie data, rank inside the unit (planner.go:302-405)
+//   k_best              per task: first unit it is emitted from (planner.go:467-477)
+//   k_sort_*            per-distro segmented LSD radix sort (TaskPlan.Export, planner.go:462-481)
+//   k_emit              ranked queue + TotalValue (+ full breakdown on request)
+//   k_finalize_info     DistroQueueInfo / TaskGroupInfo scalars (scheduler.go:144-158)
+//   k_alloc             utilization host allocator (utilization_based_host_allocator.go:26-409)
+// No CPU fallback exists in this file: without a device every entry point fails.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "evg_score.cuh"
+
+using namespace evg;
+
+// --------------------------------------------------------------------------
+// host-side helpers
+// --------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(e_ == cudaErrorMemoryAllocation ? EVG_ERR_NOMEM : EVG_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return e;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int kTile = 2048;        // sort tile: 64 warp-chunks of 32
+constexpr int kChunks = kTile / 32;
+constexpr int kMaxPass = 16;       // 8 tie bytes + 8 value bytes
+constexpr uint32_t kInactive = 0xFFFFFFFFu;  // next[]: pair not linked / head[]: empty list
+constexpr uint32_t kEnd = 0xFFFFFFFEu;       // next[]: end of list
+constexpr uint32_t kNoAnchor = 0xFFFFFFFFu;
+
+}  // namespace
+
+// --------------------------------------------------------------------------
+// device-side views
+// --------------------------------------------------------------------------
+struct DTasks {
+  int64_t n, n_edges;
+  const int32_t* priority;
+  const int64_t* expected;
+  const int64_t* qbasis;
+  const int64_t* wbasis;
+  const int32_t* numdep;
+  const int32_t* tgo;
+  const int32_t* gid;
+  const int32_t* vid;
+  const uint32_t* flags;
+  const int64_t* dep_off;
+  const int32_t* dep_idx;
+};
+
+struct DDistros {
+  int32_t n;
+  const int64_t* task_off;
+  const int64_t* group_off;
+  const evg_distro_cfg* cfg;
+  const int32_t* gmax;
+  const int64_t* unit_base;  // n+1: first unit slot of each distro
+};
+
+struct SortBuf {
+  uint64_t* key_s;
+  uint64_t* key_v;
+  uint32_t* idx;
+};
+
+struct DWork {
+  uint8_t* has_dep;      // [T]
+  uint32_t* head;        // [unit slots]
+  uint32_t* next;        // [2T+E]
+  uint32_t* pair_slot;   // [2T+E]
+  uint32_t* edge_task;   // [E]
+  int64_t* cand_v;       // [2T+E]
+  uint32_t* cand_m;      // [2T+E]
+  uint32_t* cand_a;      // [2T+E]
+  uint32_t* cand_rk;     // [2T+E]
+  uint32_t* best_pair;   // [T]
+  SortBuf buf[2];
+  unsigned long long* bits;  // [D*4]: orS, andS, orV, andV
+  int32_t* npass;        // [D]
+  uint8_t* sched;        // [D*16]
+  int32_t* maxpass;      // [1]
+  const int32_t* tile_distro;  // [NT]
+  const int64_t* tile_start;   // [NT]
+  const int64_t* dtile_off;    // [D+1]
+  uint32_t* tile_hist;   // [NT*256]
+  evg_queue_info* qinfo; // [D]
+  evg_group_info* ginfo; // [G]
+};
+
+struct DHosts {
+  int64_t n;
+  const uint32_t* flags;
+  const int32_t* gid;
+  const int64_t* expected;
+  const int64_t* stddev;
+  const int64_t* start;
+  const int64_t* host_off;
+  const evg_alloc_cfg* cfg;
+};
+
+// --------------------------------------------------------------------------
+// device helpers
+// --------------------------------------------------------------------------
+__device__ __forceinline__ int find_distro(const int64_t* __restrict__ off, int lo, int hi, int64_t t) {
+  // largest d in [lo, hi] with off[d] <= t  (off[lo] <= t guaranteed)
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (__ldg(off + mid) <= t) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// Block-cooperative distro lookup: thread 0 / last thread bracket the block's
+// range, then each thread searches only inside the bracket.
+__device__ __forceinline__ int block_find_distro(const int64_t* __restrict__ off, int n_distros, int64_t t,
+                                                 int64_t n_items) {
+  __shared__ int s_lo, s_hi;
+  int64_t first = int64_t(blockIdx.x) * blockDim.x;
+  if (threadIdx.x == 0) s_lo = find_distro(off, 0, n_distros - 1, first);
+  if (threadIdx.x == blockDim.x - 1) {
+    int64_t last = first + blockDim.x - 1;
+    if (last >= n_items) last = n_items - 1;
+    s_hi = find_distro(off, 0, n_distros - 1, last);
+  }
+  __syncthreads();
+  if (t >= n_items) return -1;
+  return find_distro(off, s_lo, s_hi, t);
+}
+
+__device__ __forceinline__ int64_t warp_sum64(int64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint64_t warp_or64(uint64_t v) {
+  uint32_t lo = __reduce_or_sync(0xffffffffu, uint32_t(v));
+  uint32_t hi = __reduce_or_sync(0xffffffffu, uint32_t(v >> 32));
+  return (uint64_t(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t warp_and64(uint64_t v) {
+  uint32_t lo = __reduce_and_sync(0xffffffffu, uint32_t(v));
+  uint32_t hi = __reduce_and_sync(0xffffffffu, uint32_t(v >> 32));
+  return (uint64_t(hi) << 32) | lo;
+}
+__device__ __forceinline__ void atomic_add64(int64_t* p, int64_t v) {
+  if (v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+
+// Record which key bits vary inside a distro (drives the radix pass schedule).
+__device__ __forceinline__ void note_key_bits(unsigned long long* bits, int d, bool valid, bool uniform, uint64_t ks,
+                                              uint64_t kv) {
+  if (uniform) {
+    uint64_t os = warp_or64(ks), as = warp_and64(ks), ov = warp_or64(kv), av = warp_and64(kv);
+    if ((threadIdx.x & 31) == 0) {
+      atomicOr(bits + 4 * d + 0, os);
+      atomicAnd(bits + 4 * d + 1, as);
+      atomicOr(bits + 4 * d + 2, ov);
+      atomicAnd(bits + 4 * d + 3, av);
+    }
+  } else if (valid) {
+    atomicOr(bits + 4 * d + 0, ks);
+    atomicAnd(bits + 4 * d + 1, ks);
+    atomicOr(bits + 4 * d + 2, kv);
+    atomicAnd(bits + 4 * d + 3, kv);
+  }
+}
+
+// unit slot (distro-local) a task is filed under by its id key (planner.go:434-445)
+__device__ __forceinline__ uint32_t own_slot_local(int32_t gid, int32_t vid, uint32_t local_idx, uint32_t n_groups,
+                                                   bool group_versions) {
+  if (gid >= 0) return uint32_t(gid);
+  return n_groups + (group_versions ? uint32_t(vid) : local_idx);
+}
+
+__device__ __forceinline__ void link_pair(DWork& W, uint32_t pair, uint32_t slot) {
+  W.pair_slot[pair] = slot;
+  uint32_t prev = atomicExch(W.head + slot, pair);
+  W.next[pair] = (prev == kInactive) ? kEnd : prev;
+}
+
+// --------------------------------------------------------------------------
+// kernels
+// --------------------------------------------------------------------------
+
+// planner.go:449-456 (pass 2): mark every task some in-queue task depends on.
+__global__ void k_mark_dependents(DTasks T, DDistros D, DWork W) {
+  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  int d = block_find_distro(D.task_off, D.n, t, T.n);
+  if (d < 0) return;
+  int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
+  int64_t base = D.task_off[d];
+  for (int64_t e = e0; e < e1; e++) W.has_dep[base + T.dep_idx[e]] = 1;
+}
+
+// Per task: queue info (scheduler.go:56-159), unit links (planner.go:431-456),
+// and the score of units that are provably {this task} (planner.go:209-337).
+__global__ void __launch_bounds__(256) k_task(DTasks T, DDistros D, DWork W, int64_t now, int any_complex) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int d = block_find_distro(D.task_off, D.n, t, T.n);
+  const bool valid = d >= 0;
+  const unsigned full = 0xffffffffu;
+  const int d0 = __shfl_sync(full, d, 0);
+  const bool uniform = __all_sync(full, d == d0) && valid;
+
+  int32_t prio = 0, nd = 0, gid = -1, vid = 0;
+  int64_t exp_ns = 0, qb = EVG_TIME_ZERO, wb = EVG_TIME_ZERO;
+  uint32_t fl = 0;
+  evg_distro_cfg cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  int64_t base = 0;
+  if (valid) {
+    prio = T.priority[t]; exp_ns = T.expected[t]; qb = T.qbasis[t]; wb = T.wbasis[t];
+    nd = T.numdep[t]; gid = T.gid[t]; vid = T.vid[t]; fl = T.flags[t];
+    cfg = D.cfg[d];
+    base = D.task_off[d];
+  }
+
+  // ---- GetDistroQueueInfo contributions (scheduler.go:66-138) ----
+  const bool dm = valid && (fl & EVG_TF_DEPS_MET);
+  const bool counted = valid && (!cfg.includes_dependencies || dm);
+  const int64_t threshold = cfg.target_time_ns;
+  const bool over = counted && exp_ns > threshold;
+  const bool wait_over = counted && dm && since(now, wb) > threshold;
+  const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
+  const bool sec = valid && (fl & EVG_TF_OTHER_DISTRO);
+  const bool ung = valid && gid < 0;
+  if (valid) {
+    if (uniform) {
+      // five 6-bit counters per word (a warp adds at most 32 to each)
+      uint32_t w0 = uint32_t(dm) | (uint32_t(mq_dm) << 6) | (uint32_t(over) << 12) | (uint32_t(wait_over) << 18) |
+                    (uint32_t(sec) << 24);
+      uint32_t w1 = uint32_t(ung) | (uint32_t(ung && counted) << 6) | (uint32_t(ung && over) << 12) |
+                    (uint32_t(ung && wait_over) << 18) | (uint32_t(ung && mq_dm) << 24);
+      w0 = __reduce_add_sync(full, w0);
+      w1 = __reduce_add_sync(full, w1);
+      int64_t s_exp = warp_sum64(counted ? exp_ns : 0);
+      int64_t s_over = warp_sum64(over ? exp_ns : 0);
+      int64_t s_uexp = warp_sum64(ung && counted ? exp_ns : 0);
+      int64_t s_uover = warp_sum64(ung && over ? exp_ns : 0);
+      if ((threadIdx.x & 31) == 0) {
+        evg_queue_info* q = W.qinfo + d;
+        atomic_add64(&q->length_with_dependencies_met, w0 & 63);
+        atomic_add64(&q->count_dep_filled_merge_queue_tasks, (w0 >> 6) & 63);
+        atomic_add64(&q->count_duration_over_threshold, (w0 >> 12) & 63);
+        atomic_add64(&q->count_wait_over_threshold, (w0 >> 18) & 63);
+        atomic_add64(&q->secondary_queue, (w0 >> 24) & 63);
+        atomic_add64(&q->expected_duration, s_exp);
+        atomic_add64(&q->duration_over_threshold, s_over);
+        atomic_add64(&q->has_ungrouped, w1 & 63);
+        atomic_add64(&q->ungrouped.count, (w1 >> 6) & 63);
+        atomic_add64(&q->ungrouped.count_duration_over_threshold, (w1 >> 12) & 63);
+        atomic_add64(&q->ungrouped.count_wait_over_threshold, (w1 >> 18) & 63);
+        atomic_add64(&q->ungrouped.count_dep_filled_merge_queue_tasks, (w1 >> 24) & 63);
+        atomic_add64(&q->ungrouped.expected_duration, s_uexp);
+        atomic_add64(&q->ungrouped.duration_over_threshold, s_uover);
+      }
+    } else {
+      evg_queue_info* q = W.qinfo + d;
+      atomic_add64(&q->length_with_dependencies_met, dm);
+      atomic_add64(&q->count_dep_filled_merge_queue_tasks, mq_dm);
+      atomic_add64(&q->count_duration_over_threshold, over);
+      atomic_add64(&q->count_wait_over_threshold, wait_over);
+      atomic_add64(&q->secondary_queue, sec);
+      atomic_add64(&q->expected_duration, counted ? exp_ns : 0);
+      atomic_add64(&q->duration_over_threshold, over ? exp_ns : 0);
+      if (ung) {
+        atomic_add64(&q->has_ungrouped, 1);
+        atomic_add64(&q->ungrouped.count, counted);
+        atomic_add64(&q->ungrouped.count_duration_over_threshold, over);
+        atomic_add64(&q->ungrouped.count_wait_over_threshold, wait_over);
+        atomic_add64(&q->ungrouped.count_dep_filled_merge_queue_tasks, mq_dm);
+        atomic_add64(&q->ungrouped.expected_duration, counted ? exp_ns : 0);
+        atomic_add64(&q->ungrouped.duration_over_threshold, over ? exp_ns : 0);
+      }
+    }
+    if (gid >= 0) {
+      evg_group_info* g = W.ginfo + D.group_off[d] + gid;
+      atomic_add64(&g->count, counted);
+      atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
+      atomic_add64(&g->count_duration_over_threshold, over);
+      atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
+      atomic_add64(&g->count_wait_over_threshold, wait_over);
+      atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
+    }
+  }
+
+  // ---- units ----
+  uint64_t key_s = 0, key_v = 0;
+  if (valid) {
+    const uint32_t li = uint32_t(t - base);
+    const bool gv = cfg.group_versions != 0;
+    const uint32_t ng = uint32_t(D.group_off[d + 1] - D.group_off[d]);
+    bool own_complex = false;
+    if (any_complex) {
+      own_complex = gid >= 0 || gv || W.has_dep[t] != 0;
+      const uint32_t ub = uint32_t(D.unit_base[d]);
+      const uint32_t s_own = own_slot_local(gid, vid, li, ng, gv);
+      const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
+      if (own_complex) link_pair(W, uint32_t(t), ub + s_own);
+      if (s_ver != kInactive) link_pair(W, uint32_t(T.n + t), ub + s_ver);  // planner.go:439
+      if (T.n_edges > 0) {
+        const int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
+        for (int64_t e = e0; e < e1; e++) {
+          const uint32_t dl = uint32_t(T.dep_idx[e]);
+          const uint32_t s = own_slot_local(T.gid[base + dl], T.vid[base + dl], dl, ng, gv);
+          // Unit.Add is keyed by task id (planner.go:131): join each unit once.
+          bool dup = (s == s_own) || (s == s_ver);
+          for (int64_t f = e0; f < e && !dup; f++) {
+            const uint32_t fl2 = uint32_t(T.dep_idx[f]);
+            dup = own_slot_local(T.gid[base + fl2], T.vid[base + fl2], fl2, ng, gv) == s;
+          }
+          W.edge_task[e] = uint32_t(t);
+          if (!dup) link_pair(W, uint32_t(2 * T.n + e), ub + s);
+        }
+      }
+    }
+    if (!own_complex) {
+      UnitAcc a;
+      acc_init(a);
+      acc_add(a, now, prio, exp_ns, qb, nd, gid, fl);
+      const int64_t v = unit_value(a, cfg, nullptr);
+      if (any_complex) W.cand_v[t] = v;  // read back by k_best
+      key_v = enc_value(v);
+      key_s = enc_tie(li, li, 0);
+    }
+    if (!any_complex) {
+      W.buf[0].key_s[t] = key_s;
+      W.buf[0].key_v[t] = key_v;
+      W.buf[0].idx[t] = li;
+    }
+  }
+  if (!any_complex) note_key_bits(W.bits, valid ? d : 0, valid, uniform, key_s, key_v);
+}
+
+__device__ __forceinline__ uint32_t pair_task(const DTasks& T, const DWork& W, uint32_t p) {
+  if (p < uint32_t(T.n)) return p;
+  if (p < uint32_t(2 * T.n)) return p - uint32_t(T.n);
+  return W.edge_task[p - uint32_t(2 * T.n)];
+}
+
+// Per linked (unit, member) pair: Unit.info over the unit's member list, the
+// unit's score, its canonical tie data and this member's rank inside the unit.
+__global__ void __launch_bounds__(256) k_unit(DTasks T, DDistros D, DWork W, int64_t now, int64_t n_pairs) {
+  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  if (W.next[p] == kInactive) return;
+  const uint32_t t = pair_task(T, W, uint32_t(p));
+  const int d = find_distro(D.task_off, 0, D.n - 1, int64_t(t));
+  const int64_t base = D.task_off[d];
+  const uint32_t slot = W.pair_slot[p];
+  const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
+  const int64_t my_ex = T.expected[t];
+  const uint32_t my_li = uint32_t(t - base);
+  UnitAcc a;
+  acc_init(a);
+  uint32_t min_member = 0xFFFFFFFFu, anchor = kNoAnchor, rk = 0;
+  for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
+    const uint32_t tq = pair_task(T, W, q);
+    const uint32_t lq = uint32_t(tq - base);
+    const int32_t q_pr = T.priority[tq], q_nd = T.numdep[tq], q_tgo = T.tgo[tq];
+    const int64_t q_ex = T.expected[tq];
+    acc_add(a, now, q_pr, q_ex, T.qbasis[tq], q_nd, T.gid[tq], T.flags[tq]);
+    min_member = min(min_member, lq);
+    if (q < uint32_t(T.n)) anchor = min(anchor, lq);  // own-key pairs are the SetDistro members (planner.go:446)
+    if (in_unit_less(q_tgo, q_nd, q_pr, q_ex, lq, my_tgo, my_nd, my_pr, my_ex, my_li)) rk++;
+  }
+  W.cand_v[p] = unit_value(a, D.cfg[d], nullptr);
+  W.cand_m[p] = min_member;
+  W.cand_a[p] = anchor;  // kNoAnchor: unit never got a distro -> not exported (planner.go:81-83)
+  W.cand_rk[p] = rk;
+}
+
+// Per task: the unit it is emitted from = best of its memberships under the
+// canonical unit order (TaskPlan.Export first-occurrence rule, planner.go:467-477).
+__global__ void __launch_bounds__(256) k_best(DTasks T, DDistros D, DWork W) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int d = block_find_distro(D.task_off, D.n, t, T.n);
+  const bool valid = d >= 0;
+  const unsigned full = 0xffffffffu;
+  const int d0 = __shfl_sync(full, d, 0);
+  const bool uniform = __all_sync(full, d == d0) && valid;
+  uint64_t key_s = 0, key_v = 0;
+  if (valid) {
+    const uint32_t li = uint32_t(t - D.task_off[d]);
+    bool have = false;
+    int64_t bv = 0;
+    uint32_t bm = 0, ba = 0, brk = 0, bp = kInactive;
+    auto consider = [&](int64_t v, uint32_t m, uint32_t a, uint32_t rk, uint32_t pair) {
+      if (a == kNoAnchor) return;
+      bool better = !have || v > bv || (v == bv && (m < bm || (m == bm && a < ba)));
+      if (better) { have = true; bv = v; bm = m; ba = a; brk = rk; bp = pair; }
+    };
+    if (W.next[t] == kInactive) consider(W.cand_v[t], li, li, 0, kInactive);  // single-task unit scored by k_task
+    else consider(W.cand_v[t], W.cand_m[t], W.cand_a[t], W.cand_rk[t], uint32_t(t));
+    const int64_t pv = T.n + t;
+    if (W.next[pv] != kInactive) consider(W.cand_v[pv], W.cand_m[pv], W.cand_a[pv], W.cand_rk[pv], uint32_t(pv));
+    if (T.n_edges > 0) {
+      for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) {
+        const int64_t pe = 2 * T.n + e;
+        if (W.next[pe] != kInactive) consider(W.cand_v[pe], W.cand_m[pe], W.cand_a[pe], W.cand_rk[pe], uint32_t(pe));
+      }
+    }
+    key_v = enc_value(bv);
+    key_s = enc_tie(bm, ba, brk);
+    W.best_pair[t] = bp;
+    W.buf[0].key_s[t] = key_s;
+    W.buf[0].key_v[t] = key_v;
+    W.buf[0].idx[t] = li;
+  }
+  note_key_bits(W.bits, valid ? d : 0, valid, uniform, key_s, key_v);
+}
+
+// bits[]: or-words start at 0, and-words at all ones
+__global__ void k_init_bits(unsigned long long* bits, int n) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n) return;
+  bits[4 * d + 0] = 0ull;
+  bits[4 * d + 1] = ~0ull;
+  bits[4 * d + 2] = 0ull;
+  bits[4 * d + 3] = ~0ull;
+}
+
+// Radix pass schedule per distro: the key bytes that actually vary.
+__global__ void k_sched(DDistros D, DWork W, int use_tie) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D.n) return;
+  int n = 0;
+  if (D.task_off[d + 1] - D.task_off[d] > 1) {
+    uint64_t vs = W.bits[4 * d + 0] & ~W.bits[4 * d + 1];
+    uint64_t vv = W.bits[4 * d + 2] & ~W.bits[4 * d + 3];
+    if (use_tie)
+      for (int b = 0; b < 8; b++) if ((vs >> (8 * b)) & 0xff) W.sched[d * kMaxPass + n++] = uint8_t(b);
+    for (int b = 0; b < 8; b++) if ((vv >> (8 * b)) & 0xff) W.sched[d * kMaxPass + n++] = uint8_t(8 + b);
+  }
+  W.npass[d] = n;
+  if (n > 0) atomicMax(W.maxpass, n);
+}
+
+__device__ __forceinline__ uint32_t key_byte(uint64_t ks, uint64_t kv, int b) {
+  return uint32_t(((b < 8) ? (ks >> (8 * b)) : (kv >> (8 * (b - 8)))) & 0xffu);
+}
+
+__global__ void __launch_bounds__(256) k_sort_hist(int j, DDistros D, DWork W) {
+  if (j >= *W.maxpass) return;
+  const int tile = blockIdx.x;
+  const int d = W.tile_distro[tile];
+  if (j >= W.npass[d]) return;
+  const int b = W.sched[d * kMaxPass + j];
+  const SortBuf src = W.buf[j & 1];
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t start = W.tile_start[tile];
+  const int64_t end = D.task_off[d + 1];
+  const int cnt = int((end - start) < int64_t(kTile) ? (end - start) : int64_t(kTile));
+  for (int i = threadIdx.x; i < cnt; i += 256) atomicAdd(&h[key_byte(src.key_s[start + i], src.key_v[start + i], b)], 1u);
+  __syncthreads();
+  W.tile_hist[int64_t(tile) * 256 + threadIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) k_sort_scan(int j, DDistros D, DWork W) {
+  if (j >= *W.maxpass) return;
+  const int d = blockIdx.x;
+  if (j >= W.npass[d]) return;
+  const int64_t t0 = W.dtile_off[d], t1 = W.dtile_off[d + 1];
+  uint32_t run = 0;
+  for (int64_t tile = t0; tile < t1; tile++) {
+    uint32_t x = W.tile_hist[tile * 256 + threadIdx.x];
+    W.tile_hist[tile * 256 + threadIdx.x] = run;
+    run += x;
+  }
+  __shared__ uint32_t s[256];
+  s[threadIdx.x] = run;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    uint32_t v = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+    __syncthreads();
+    s[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const uint32_t basev = s[threadIdx.x] - run;
+  for (int64_t tile = t0; tile < t1; tile++) W.tile_hist[tile * 256 + threadIdx.x] += basev;
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(int j, DDistros D, DWork W) {
+  if (j >= *W.maxpass) return;
+  const int tile = blockIdx.x;
+  const int d = W.tile_distro[tile];
+  if (j >= W.npass[d]) return;
+  const int b = W.sched[d * kMaxPass + j];
+  const SortBuf src = W.buf[j & 1];
+  const SortBuf dst = W.buf[(j + 1) & 1];
+  __shared__ uint16_t ch[kChunks][256];
+  for (int i = threadIdx.x; i < kChunks * 256 / 2; i += 256) reinterpret_cast<uint32_t*>(&ch[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t start = W.tile_start[tile];
+  const int64_t seg = D.task_off[d];
+  const int64_t rem = D.task_off[d + 1] - start;
+  const int cnt = int(rem < int64_t(kTile) ? rem : int64_t(kTile));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  uint64_t ks[8], kv[8];
+  uint32_t ix[8], dg[8], rk[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int c = warp * 8 + k;
+    const int i = c * 32 + lane;
+    const bool ok = i < cnt;
+    if (ok) { ks[k] = src.key_s[start + i]; kv[k] = src.key_v[start + i]; ix[k] = src.idx[start + i]; }
+    else { ks[k] = 0; kv[k] = 0; ix[k] = 0; }
+    dg[k] = ok ? key_byte(ks[k], kv[k], b) : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, dg[k]);
+    rk[k] = __popc(peers & lt);
+    if (ok && rk[k] == 0) ch[c][dg[k]] = uint16_t(__popc(peers));
+  }
+  __syncthreads();
+  {
+    uint32_t run = 0;
+    for (int c = 0; c < kChunks; c++) {
+      uint32_t x = ch[c][threadIdx.x];
+      ch[c][threadIdx.x] = uint16_t(run);
+      run += x;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    if (dg[k] < 256u) {
+      const int c = warp * 8 + k;
+      const int64_t pos = seg + W.tile_hist[int64_t(tile) * 256 + dg[k]] + ch[c][dg[k]] + rk[k];
+      dst.key_s[pos] = ks[k];
+      dst.key_v[pos] = kv[k];
+      dst.idx[pos] = ix[k];
+    }
+  }
+}
+
+// Ranked queue out: order[], TotalValue and (optionally) the 13-field breakdown
+// of the unit each task was emitted from (planner.go:467-477, task.go:3990-4038).
+__global__ void __launch_bounds__(256) k_emit(DTasks T, DDistros D, DWork W, int64_t now, int any_complex,
+                                              int32_t* order, int64_t* total_value, int64_t* breakdown) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int d = block_find_distro(D.task_off, D.n, t, T.n);
+  if (d < 0) return;
+  const SortBuf src = W.buf[W.npass[d] & 1];
+  const uint32_t li = src.idx[t];
+  order[t] = int32_t(li);
+  const int64_t v = dec_value(src.key_v[t]);
+  total_value[t] = v;
+  if (breakdown) {
+    const int64_t base = D.task_off[d];
+    const int64_t g = base + li;
+    UnitAcc a;
+    acc_init(a);
+    const uint32_t bp = any_complex ? W.best_pair[g] : kInactive;
+    if (bp == kInactive) {
+      acc_add(a, now, T.priority[g], T.expected[g], T.qbasis[g], T.numdep[g], T.gid[g], T.flags[g]);
+    } else {
+      for (uint32_t q = W.head[W.pair_slot[bp]]; q < kEnd; q = W.next[q]) {
+        const uint32_t tq = pair_task(T, W, q);
+        acc_add(a, now, T.priority[tq], T.expected[tq], T.qbasis[tq], T.numdep[tq], T.gid[tq], T.flags[tq]);
+      }
+    }
+    int64_t bd[EVG_BD_N];
+    unit_value(a, D.cfg[d], bd);
+    for (int k = 0; k < EVG_BD_N; k++) breakdown[t * EVG_BD_N + k] = bd[k];
+  }
+}
+
+// scheduler.go:144-158: scalars of DistroQueueInfo / TaskGroupInfo that are not sums.
+__global__ void k_finalize_info(DDistros D, DWork W, int64_t n_groups_total) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < D.n) {
+    evg_queue_info* q = W.qinfo + i;
+    q->length = D.task_off[i + 1] - D.task_off[i];
+    q->max_duration_threshold = D.cfg[i].target_time_ns;
+    q->secondary_queue = q->secondary_queue != 0;
+    q->has_ungrouped = q->has_ungrouped != 0;
+  }
+  if (i < n_groups_total) W.ginfo[i].max_hosts = D.gmax[i];
+}
+
+// UtilizationBasedHostAllocator for one distro per thread
+// (utilization_based_host_allocator.go:26-130 and the helpers it calls).
+// FP64 sums run in host-index order (the canonical order; the reference's
+// channel order is nondeterministic, allocator.go:381-391).
+struct GroupScratch {
+  int32_t n_hosts;
+  int32_t n_free;
+  double soon;
+};
+
+__device__ int eval_group(const evg_alloc_cfg& c, const evg_group_info& info, int64_t threshold, int64_t max_hosts,
+                          int64_t n_hosts, int64_t n_free, double soon, int64_t* out_new, int64_t* out_free) {
+  // evalHostUtilization allocator.go:135-220
+  *out_new = 0;
+  *out_free = 0;
+  if (c.provider == EVG_PROVIDER_STATIC) return EVG_ALLOC_OK;
+  if (c.has_pool) {
+    if (!c.parent_found) return EVG_ALLOC_ERR_PARENT_MISSING;
+    max_hosts = int64_t(c.parent_maximum_hosts) * int64_t(c.pool_max_containers);
+  }
+  if (c.future_host_fraction > 1.0) return EVG_ALLOC_ERR_FUTURE_FRACTION;
+  const int64_t exp_free = n_free + d2i_floor(soon);  // allocator.go:317
+  const int64_t overdue = c.waits_over_thresh_feedback ? info.count_wait_over_threshold : 0;
+  const int64_t short_ns = wsub(info.expected_duration, info.duration_over_threshold);
+  int64_t n = calc_new_hosts_needed(short_ns, threshold, exp_free, info.count_duration_over_threshold, overdue,
+                                    info.count_dep_filled_merge_queue_tasks, !c.round_up);
+  if (n > info.count) n = info.count;
+  if (is_max_hosts_capacity(max_hosts, c.has_pool != 0, c.pool_max_containers, n, n_hosts)) n = max_hosts - n_hosts;
+  if (n < 0) n = 0;
+  if (max_hosts < 1) return EVG_ALLOC_ERR_POOL_SIZE;
+  *out_new = n;
+  *out_free = exp_free;
+  return EVG_ALLOC_OK;
+}
+
+__global__ void k_alloc(DHosts H, int32_t n_distros, const int64_t* group_off, const evg_queue_info* qinfo,
+                        evg_group_info* ginfo, GroupScratch* gs, int64_t now, evg_alloc_result* result,
+                        int32_t* status) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_distros) return;
+  const evg_alloc_cfg c = H.cfg[d];
+  const evg_queue_info qi = qinfo[d];
+  const int64_t threshold = qi.max_duration_threshold;
+  const int64_t h0 = H.host_off[d], h1 = H.host_off[d + 1];
+  const int64_t g0 = group_off[d], g1 = group_off[d + 1];
+  const int64_t n_existing = h1 - h0;
+  // one ordered pass over the hosts: IsFree count (allocator.go:33-37), bucket
+  // sizes (groupByTaskGroup :223-260) and the soon-to-be-free sums (:324-394)
+  int64_t n_free_all = 0, u_hosts = 0, u_free = 0;
+  double u_soon = 0.0;
+  for (int64_t h = h0; h < h1; h++) {
+    const uint32_t f = H.flags[h];
+    const int32_t g = H.gid[h];
+    const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
+    n_free_all += is_free;
+    double term = 0.0;
+    const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
+    if (running) term = soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction);
+    if (g == EVG_HG_NONE) {
+      u_hosts++;
+      u_free += is_free;
+      if (running) u_soon = fadd64(u_soon, term);
+    } else if (g >= 0 && g < g1 - g0) {
+      GroupScratch* s = gs + g0 + g;
+      s->n_hosts++;
+      s->n_free += is_free;
+      if (running) s->soon = fadd64(s->soon, term);
+    }
+  }
+  int64_t deficit = qi.expected_duration;
+  int32_t st = EVG_ALLOC_OK;
+  int64_t n_new = 0, n_free_out = n_free_all;
+  if (c.provider != EVG_PROVIDER_DOCKER && n_existing >= c.maximum_hosts) {
+    n_new = 0;  // allocator.go:39-48
+  } else if (c.disabled) {
+    n_new = int64_t(c.minimum_hosts) - n_existing;
+    if (n_new < 0) n_new = 0;  // allocator.go:51-66
+  } else {
+    int64_t required = 0, free_approx = 0;
+    // "" bucket exists when there are standalone tasks queued or hosts bucketed under ""
+    if (qi.has_ungrouped || u_hosts > 0) {
+      int64_t n, f;
+      st = eval_group(c, qi.ungrouped, threshold, c.maximum_hosts, u_hosts, u_free, u_soon, &n, &f);
+      required += n;
+      free_approx += f;
+    }
+    for (int64_t g = g0; g < g1 && st == EVG_ALLOC_OK; g++) {
+      evg_group_info* gi = ginfo + g;
+      if (gi->count == 0) continue;  // allocator.go:84-86
+      int64_t n, f;
+      st = eval_group(c, *gi, threshold, gi->max_hosts, gs[g].n_hosts, gs[g].n_free, gs[g].soon, &n, &f);
+      if (st != EVG_ALLOC_OK) break;
+      required += n;
+      free_approx += f;
+      gi->count_free = f;       // allocator.go:107-110
+      gi->count_required = n;
+    }
+    if (st == EVG_ALLOC_OK) {
+      if (required + n_free_all > qi.length_with_dependencies_met) required = qi.length_with_dependencies_met - n_free_all;
+      if (required < 0) required = 0;
+      int64_t topup = 0;
+      if (n_existing + required < c.minimum_hosts) topup = c.minimum_hosts - (n_existing + required);
+      n_new = required + topup;
+      n_free_out = free_approx;
+    } else {
+      n_new = 0;  // (0, len(freeHosts), err) allocator.go:99-101
+      n_free_out = n_free_all;
+    }
+  }
+  deficit = wsub(deficit, wmul(n_free_out, threshold));
+  if (deficit < 0) deficit = 0;
+  result[d].new_hosts = int32_t(n_new);
+  result[d].free_hosts = int32_t(n_free_out);
+  result[d].deficit_ns = deficit;
+  status[d] = st;
+}
+
+// --------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------
+struct evg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev_begin = nullptr, ev_sort0 = nullptr, ev_sort1 = nullptr, ev_end = nullptr;
+  // resident inputs
+  bool have_tasks = false, have_hosts = false;
+  int64_t T = 0, E = 0, G = 0, H = 0, U = 0, NT = 0;
+  int32_t Dn = 0;
+  int any_complex = 0;
+  int64_t launches = 0;
+  bool timed = false;
+  DevBuf b_prio, b_exp, b_qb, b_wb, b_nd, b_tgo, b_gid, b_vid, b_flags, b_depoff, b_depidx;
+  DevBuf b_taskoff, b_groupoff, b_cfg, b_gmax, b_unitbase;
+  DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_cv, b_cm, b_ca, b_crk, b_bestpair;
+  DevBuf b_ks[2], b_kv[2], b_ix[2], b_bits, b_npass, b_sched, b_maxpass;
+  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist;
+  DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
+  DevBuf b_hflags, b_hgid, b_hexp, b_hstd, b_hstart, b_hostoff, b_acfg, b_gs, b_result, b_status;
+  bool bd_valid = false;
+};
+
+namespace {
+
+int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt) {
+  if (!t || !dt) return fail(EVG_ERR_INVALID, "null task table / distro table");
+  const int64_t T = t->n_tasks, E = t->n_edges;
+  const int32_t D = dt->n_distros;
+  if (T < 0 || E < 0 || D < 0) return fail(EVG_ERR_INVALID, "negative sizes");
+  if (T >= (int64_t(1) << 31) - 2) return fail(EVG_ERR_INVALID, "n_tasks %lld exceeds 2^31-2 per call", (long long)T);
+  if (2 * T + E >= int64_t(0xFFFFFFF0u)) return fail(EVG_ERR_INVALID, "2*n_tasks+n_edges exceeds the 32-bit pair id space");
+  if (D > 0 && (!dt->task_off || !dt->group_off || !dt->cfg)) return fail(EVG_ERR_INVALID, "null distro arrays");
+  if (T > 0 && (!t->priority || !t->expected_ns || !t->queue_basis_ns || !t->wait_basis_ns || !t->num_dependents ||
+                !t->task_group_order || !t->group_id || !t->version_id || !t->flags))
+    return fail(EVG_ERR_INVALID, "null task column");
+  if (E > 0 && (!t->dep_off || !t->dep_idx)) return fail(EVG_ERR_INVALID, "n_edges > 0 but dep_off/dep_idx null");
+  if (D == 0 && T != 0) return fail(EVG_ERR_INVALID, "tasks without distros");
+  std::vector<int64_t> unit_base(size_t(D) + 1, 0), dtile_off(size_t(D) + 1, 0);
+  std::vector<int32_t> tile_distro;
+  std::vector<int64_t> tile_start;
+  int any_complex = E > 0 ? 1 : 0;
+  for (int32_t d = 0; d < D; d++) {
+    const int64_t a = dt->task_off[d], b = dt->task_off[d + 1];
+    const int64_t ga = dt->group_off[d], gb = dt->group_off[d + 1];
+    if (d == 0 && (a != 0 || ga != 0)) return fail(EVG_ERR_INVALID, "offsets must start at 0");
+    if (b < a || gb < ga) return fail(EVG_ERR_INVALID, "offsets of distro %d decrease", d);
+    if (b - a > kMaxTasksPerDistro) return fail(EVG_ERR_INVALID, "distro %d holds %lld tasks (max %lld)", d, (long long)(b - a), (long long)kMaxTasksPerDistro);
+    const evg_distro_cfg& cf = dt->cfg[d];
+    if (cf.n_versions < 0) return fail(EVG_ERR_INVALID, "distro %d: negative n_versions", d);
+    if (gb > ga || cf.group_versions) any_complex = 1;
+    unit_base[d + 1] = unit_base[d] + (gb - ga) + (cf.group_versions ? int64_t(cf.n_versions) : (b - a));
+    for (int64_t s = a; s < b; s += kTile) { tile_distro.push_back(d); tile_start.push_back(s); }
+    dtile_off[d + 1] = int64_t(tile_distro.size());
+  }
+  if (D > 0 && dt->task_off[D] != T) return fail(EVG_ERR_INVALID, "task_off[n_distros] != n_tasks");
+  const int64_t G = D > 0 ? dt->group_off[D] : 0;
+  if (G > 0 && !dt->group_max_hosts) return fail(EVG_ERR_INVALID, "null group_max_hosts");
+  const int64_t U = unit_base[D];
+  if (U >= int64_t(0xFFFFFFF0u)) return fail(EVG_ERR_INVALID, "unit slot space exceeds 32 bits");
+  const int64_t NT = int64_t(tile_distro.size());
+  const int64_t P = 2 * T + E;
+  cudaStream_t s = c->stream;
+#define UP(buf, ptr, count, type)                                                                     \
+  do {                                                                                                \
+    CK((buf).ensure(sizeof(type) * size_t((count) > 0 ? (count) : 1)));                               \
+    if ((count) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(count), cudaMemcpyHostToDevice, s)); \
+  } while (0)
+  UP(c->b_prio, t->priority, T, int32_t);
+  UP(c->b_exp, t->expected_ns, T, int64_t);
+  UP(c->b_qb, t->queue_basis_ns, T, int64_t);
+  UP(c->b_wb, t->wait_basis_ns, T, int64_t);
+  UP(c->b_nd, t->num_dependents, T, int32_t);
+  UP(c->b_tgo, t->task_group_order, T, int32_t);
+  UP(c->b_gid, t->group_id, T, int32_t);
+  UP(c->b_vid, t->version_id, T, int32_t);
+  UP(c->b_flags, t->flags, T, uint32_t);
+  if (E > 0) {
+    UP(c->b_depoff, t->dep_off, T + 1, int64_t);
+    UP(c->b_depidx, t->dep_idx, E, int32_t);
+  }
+  UP(c->b_taskoff, dt->task_off, D + 1, int64_t);
+  UP(c->b_groupoff, dt->group_off, D + 1, int64_t);
+  UP(c->b_cfg, dt->cfg, D, evg_distro_cfg);
+  UP(c->b_gmax, dt->group_max_hosts, G, int32_t);
+  UP(c->b_unitbase, unit_base.data(), D + 1, int64_t);
+  UP(c->b_tiledistro, tile_distro.data(), NT, int32_t);
+  UP(c->b_tilestart, tile_start.data(), NT, int64_t);
+  UP(c->b_dtileoff, dtile_off.data(), D + 1, int64_t);
+  // the staging vectors above must outlive the async copies
+  CK(cudaStreamSynchronize(s));
+  // work buffers
+  if (any_complex) {
+    CK(c->b_hasdep.ensure(size_t(T) + 1));
+    CK(c->b_head.ensure(sizeof(uint32_t) * size_t(U + 1)));
+    CK(c->b_next.ensure(sizeof(uint32_t) * size_t(P + 1)));
+    CK(c->b_pslot.ensure(sizeof(uint32_t) * size_t(P + 1)));
+    CK(c->b_etask.ensure(sizeof(uint32_t) * size_t(E + 1)));
+    CK(c->b_cv.ensure(sizeof(int64_t) * size_t(P + 1)));
+    CK(c->b_cm.ensure(sizeof(uint32_t) * size_t(P + 1)));
+    CK(c->b_ca.ensure(sizeof(uint32_t) * size_t(P + 1)));
+    CK(c->b_crk.ensure(sizeof(uint32_t) * size_t(P + 1)));
+    CK(c->b_bestpair.ensure(sizeof(uint32_t) * size_t(T + 1)));
+  }
+  for (int k = 0; k < 2; k++) {
+    CK(c->b_ks[k].ensure(sizeof(uint64_t) * size_t(T + 1)));
+    CK(c->b_kv[k].ensure(sizeof(uint64_t) * size_t(T + 1)));
+    CK(c->b_ix[k].ensure(sizeof(uint32_t) * size_t(T + 1)));
+  }
+  CK(c->b_bits.ensure(sizeof(uint64_t) * 4 * size_t(D + 1)));
+  CK(c->b_npass.ensure(sizeof(int32_t) * size_t(D + 1)));
+  CK(c->b_sched.ensure(size_t(kMaxPass) * size_t(D + 1)));
+  CK(c->b_maxpass.ensure(sizeof(int32_t) * 4));
+  CK(c->b_tilehist.ensure(sizeof(uint32_t) * 256 * size_t(NT + 1)));
+  CK(c->b_qinfo.ensure(sizeof(evg_queue_info) * size_t(D + 1)));
+  CK(c->b_ginfo.ensure(sizeof(evg_group_info) * size_t(G + 1)));
+  CK(c->b_order.ensure(sizeof(int32_t) * size_t(T + 1)));
+  CK(c->b_tv.ensure(sizeof(int64_t) * size_t(T + 1)));
+  c->T = T; c->E = E; c->G = G; c->U = U; c->NT = NT; c->Dn = D;
+  c->any_complex = any_complex;
+  c->have_tasks = true;
+  c->have_hosts = false;
+  return EVG_OK;
+}
+
+int upload_hosts(evg_ctx* c, const evg_host_soa* h, const int64_t* host_off, const evg_alloc_cfg* acfg, int32_t D) {
+  if (!h || !acfg) return fail(EVG_ERR_INVALID, "null host table / allocator config");
+  const int64_t H = h->n_hosts;
+  if (H < 0) return fail(EVG_ERR_INVALID, "negative n_hosts");
+  if (D > 0 && !host_off) return fail(EVG_ERR_INVALID, "null host_off");
+  for (int32_t d = 0; d < D; d++)
+    if (host_off[d + 1] < host_off[d] || (d == 0 && host_off[0] != 0)) return fail(EVG_ERR_INVALID, "bad host_off at distro %d", d);
+  if (D > 0 && host_off[D] != H) return fail(EVG_ERR_INVALID, "host_off[n_distros] != n_hosts");
+  if (H > 0 && (!h->flags || !h->group_id || !h->expected_ns || !h->std_ns || !h->start_ns)) return fail(EVG_ERR_INVALID, "null host column");
+  cudaStream_t s = c->stream;
+  UP(c->b_hflags, h->flags, H, uint32_t);
+  UP(c->b_hgid, h->group_id, H, int32_t);
+  UP(c->b_hexp, h->expected_ns, H, int64_t);
+  UP(c->b_hstd, h->std_ns, H, int64_t);
+  UP(c->b_hstart, h->start_ns, H, int64_t);
+  UP(c->b_hostoff, host_off, D + 1, int64_t);
+  UP(c->b_acfg, acfg, D, evg_alloc_cfg);
+  CK(c->b_result.ensure(sizeof(evg_alloc_result) * size_t(D + 1)));
+  CK(c->b_status.ensure(sizeof(int32_t) * size_t(D + 1)));
+  c->H = H;
+  c->have_hosts = true;
+  return EVG_OK;
+}
+#undef UP
+
+DTasks dtasks(const evg_ctx* c) {
+  DTasks t;
+  t.n = c->T; t.n_edges = c->E;
+  t.priority = c->b_prio.as<int32_t>(); t.expected = c->b_exp.as<int64_t>();
+  t.qbasis = c->b_qb.as<int64_t>(); t.wbasis = c->b_wb.as<int64_t>();
+  t.numdep = c->b_nd.as<int32_t>(); t.tgo = c->b_tgo.as<int32_t>();
+  t.gid = c->b_gid.as<int32_t>(); t.vid = c->b_vid.as<int32_t>(); t.flags = c->b_flags.as<uint32_t>();
+  t.dep_off = c->b_depoff.as<int64_t>(); t.dep_idx = c->b_depidx.as<int32_t>();
+  return t;
+}
+DDistros ddistros(const evg_ctx* c) {
+  DDistros d;
+  d.n = c->Dn; d.task_off = c->b_taskoff.as<int64_t>(); d.group_off = c->b_groupoff.as<int64_t>();
+  d.cfg = c->b_cfg.as<evg_distro_cfg>(); d.gmax = c->b_gmax.as<int32_t>(); d.unit_base = c->b_unitbase.as<int64_t>();
+  return d;
+}
+DWork dwork(const evg_ctx* c) {
+  DWork w;
+  w.has_dep = c->b_hasdep.as<uint8_t>(); w.head = c->b_head.as<uint32_t>(); w.next = c->b_next.as<uint32_t>();
+  w.pair_slot = c->b_pslot.as<uint32_t>(); w.edge_task = c->b_etask.as<uint32_t>();
+  w.cand_v = c->b_cv.as<int64_t>(); w.cand_m = c->b_cm.as<uint32_t>(); w.cand_a = c->b_ca.as<uint32_t>();
+  w.cand_rk = c->b_crk.as<uint32_t>(); w.best_pair = c->b_bestpair.as<uint32_t>();
+  for (int k = 0; k < 2; k++) {
+    w.buf[k].key_s = c->b_ks[k].as<uint64_t>(); w.buf[k].key_v = c->b_kv[k].as<uint64_t>(); w.buf[k].idx = c->b_ix[k].as<uint32_t>();
+  }
+  w.bits = c->b_bits.as<unsigned long long>(); w.npass = c->b_npass.as<int32_t>(); w.sched = c->b_sched.as<uint8_t>();
+  w.maxpass = c->b_maxpass.as<int32_t>();
+  w.tile_distro = c->b_tiledistro.as<int32_t>(); w.tile_start = c->b_tilestart.as<int64_t>();
+  w.dtile_off = c->b_dtileoff.as<int64_t>(); w.tile_hist = c->b_tilehist.as<uint32_t>();
+  w.qinfo = c->b_qinfo.as<evg_queue_info>(); w.ginfo = c->b_ginfo.as<evg_group_info>();
+  return w;
+}
+
+inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1) / block); }
+
+#define LAUNCH(c, kernel, grid, block, ...)                                  \
+  do {                                                                       \
+    if ((grid) > 0) {                                                        \
+      kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);              \
+      (c)->launches++;                                                       \
+    }                                                                        \
+  } while (0)
+
+int run_alloc(evg_ctx* c, int64_t now) {
+  DHosts h;
+  h.n = c->H; h.flags = c->b_hflags.as<uint32_t>(); h.gid = c->b_hgid.as<int32_t>();
+  h.expected = c->b_hexp.as<int64_t>(); h.stddev = c->b_hstd.as<int64_t>(); h.start = c->b_hstart.as<int64_t>();
+  h.host_off = c->b_hostoff.as<int64_t>(); h.cfg = c->b_acfg.as<evg_alloc_cfg>();
+  CK(c->b_gs.ensure(sizeof(GroupScratch) * size_t(c->G + 1)));
+  CK(cudaMemsetAsync(c->b_gs.p, 0, sizeof(GroupScratch) * size_t(c->G + 1), c->stream));
+  LAUNCH(c, k_alloc, grid_for(c->Dn, 128), 128, h, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
+         c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->b_result.as<evg_alloc_result>(),
+         c->b_status.as<int32_t>());
+  CK(cudaGetLastError());
+  return EVG_OK;
+}
+
+int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
+  const int64_t T = c->T, E = c->E, P = 2 * T + E;
+  const int32_t D = c->Dn;
+  cudaStream_t s = c->stream;
+  DTasks dt = dtasks(c);
+  DDistros dd = ddistros(c);
+  DWork w = dwork(c);
+  int64_t* bd = nullptr;
+  c->bd_valid = false;
+  if (opts & EVG_OPT_BREAKDOWN) {
+    CK(c->b_bd.ensure(sizeof(int64_t) * EVG_BD_N * size_t(T + 1)));
+    bd = c->b_bd.as<int64_t>();
+    c->bd_valid = true;
+  }
+  CK(cudaMemsetAsync(c->b_qinfo.p, 0, sizeof(evg_queue_info) * size_t(D + 1), s));
+  CK(cudaMemsetAsync(c->b_ginfo.p, 0, sizeof(evg_group_info) * size_t(c->G + 1), s));
+  CK(cudaMemsetAsync(c->b_maxpass.p, 0, sizeof(int32_t) * 4, s));
+  if (D == 0 || T == 0) {
+    LAUNCH(c, k_finalize_info, grid_for(std::max<int64_t>(D, c->G), 256), 256, dd, w, c->G);
+    CK(cudaGetLastError());
+    return EVG_OK;
+  }
+  if (c->any_complex) {
+    CK(cudaMemsetAsync(c->b_hasdep.p, 0, size_t(T) + 1, s));
+    CK(cudaMemsetAsync(c->b_head.p, 0xFF, sizeof(uint32_t) * size_t(c->U + 1), s));
+    CK(cudaMemsetAsync(c->b_next.p, 0xFF, sizeof(uint32_t) * size_t(P + 1), s));
+    if (E > 0) LAUNCH(c, k_mark_dependents, grid_for(T, 256), 256, dt, dd, w);
+  }
+  LAUNCH(c, k_init_bits, grid_for(D, 256), 256, w.bits, D);
+  LAUNCH(c, k_task, grid_for(T, 256), 256, dt, dd, w, now, c->any_complex);
+  if (c->any_complex) {
+    LAUNCH(c, k_unit, grid_for(P, 256), 256, dt, dd, w, now, P);
+    LAUNCH(c, k_best, grid_for(T, 256), 256, dt, dd, w);
+  }
+  if (c->timed) CK(cudaEventRecord(c->ev_sort0, s));
+  LAUNCH(c, k_sched, grid_for(D, 128), 128, dd, w, c->any_complex);
+  const int passes = c->any_complex ? kMaxPass : 8;
+  for (int j = 0; j < passes; j++) {
+    LAUNCH(c, k_sort_hist, unsigned(c->NT), 256, j, dd, w);
+    LAUNCH(c, k_sort_scan, unsigned(D), 256, j, dd, w);
+    LAUNCH(c, k_sort_scatter, unsigned(c->NT), 256, j, dd, w);
+  }
+  if (c->timed) CK(cudaEventRecord(c->ev_sort1, s));
+  LAUNCH(c, k_emit, grid_for(T, 256), 256, dt, dd, w, now, c->any_complex, c->b_order.as<int32_t>(), c->b_tv.as<int64_t>(), bd);
+  LAUNCH(c, k_finalize_info, grid_for(std::max<int64_t>(D, c->G), 256), 256, dd, w, c->G);
+  CK(cudaGetLastError());
+  return EVG_OK;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------
+// C-ABI
+// --------------------------------------------------------------------------
+extern "C" {
+
+const char* evg_last_error(void) { return g_err.c_str(); }
+int evg_abi_version(void) { return EVG_ABI_VERSION; }
+
+int evg_init(int device, void* stream, evg_ctx** out) {
+  if (!out) return fail(EVG_ERR_INVALID, "evg_init: out is null");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(EVG_ERR_CUDA, "no CUDA device: %s (libevgsched has no CPU fallback)", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(EVG_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(EVG_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  evg_ctx* c = new evg_ctx();
+  c->device = device;
+  if (stream) { c->stream = reinterpret_cast<cudaStream_t>(stream); c->own_stream = false; }
+  else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CK(cudaEventCreate(&c->ev_begin)); CK(cudaEventCreate(&c->ev_sort0));
+  CK(cudaEventCreate(&c->ev_sort1)); CK(cudaEventCreate(&c->ev_end));
+  *out = c;
+  return EVG_OK;
+}
+
+void evg_shutdown(evg_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf* all[] = {&c->b_prio, &c->b_exp, &c->b_qb, &c->b_wb, &c->b_nd, &c->b_tgo, &c->b_gid, &c->b_vid, &c->b_flags,
+                   &c->b_depoff, &c->b_depidx, &c->b_taskoff, &c->b_groupoff, &c->b_cfg, &c->b_gmax, &c->b_unitbase,
+                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_cv, &c->b_cm, &c->b_ca, &c->b_crk,
+                   &c->b_bestpair, &c->b_ks[0], &c->b_ks[1], &c->b_kv[0], &c->b_kv[1], &c->b_ix[0], &c->b_ix[1], &c->b_bits,
+                   &c->b_npass, &c->b_sched, &c->b_maxpass, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
+                   &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
+                   &c->b_hstart, &c->b_hostoff, &c->b_acfg, &c->b_gs, &c->b_result, &c->b_status};
+  for (DevBuf* b : all) b->release();
+  cudaEventDestroy(c->ev_begin); cudaEventDestroy(c->ev_sort0); cudaEventDestroy(c->ev_sort1); cudaEventDestroy(c->ev_end);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int evg_upload(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* distros, const evg_host_soa* hosts,
+               const int64_t* host_off, const evg_alloc_cfg* acfg) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  int rc = upload_tasks(c, tasks, distros);
+  if (rc != EVG_OK) return rc;
+  if (hosts) {
+    rc = upload_hosts(c, hosts, host_off, acfg, distros->n_distros);
+    if (rc != EVG_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return EVG_OK;
+}
+
+int evg_run_resident(evg_ctx* c, int64_t now_ns, uint32_t opts) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  if (!c->have_tasks) return fail(EVG_ERR_STATE, "evg_run_resident before evg_upload");
+  CK(cudaSetDevice(c->device));
+  c->launches = 0;
+  c->timed = true;
+  CK(cudaEventRecord(c->ev_begin, c->stream));
+  int rc = run_plan(c, now_ns, opts);
+  if (rc != EVG_OK) return rc;
+  if (c->T == 0 || c->Dn == 0) { CK(cudaEventRecord(c->ev_sort0, c->stream)); CK(cudaEventRecord(c->ev_sort1, c->stream)); }
+  if (c->have_hosts) {
+    rc = run_alloc(c, now_ns);
+    if (rc != EVG_OK) return rc;
+  }
+  CK(cudaEventRecord(c->ev_end, c->stream));
+  return EVG_OK;
+}
+
+int evg_download(evg_ctx* c, evg_plan_out* po, evg_alloc_out* ao) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  if (!c->have_tasks) return fail(EVG_ERR_STATE, "evg_download before evg_upload");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  if (po) {
+    if (po->order && c->T) CK(cudaMemcpyAsync(po->order, c->b_order.p, sizeof(int32_t) * size_t(c->T), cudaMemcpyDeviceToHost, s));
+    if (po->total_value && c->T) CK(cudaMemcpyAsync(po->total_value, c->b_tv.p, sizeof(int64_t) * size_t(c->T), cudaMemcpyDeviceToHost, s));
+    if (po->breakdown && c->T) {
+      if (!c->bd_valid) return fail(EVG_ERR_STATE, "breakdown requested but the run did not set EVG_OPT_BREAKDOWN");
+      CK(cudaMemcpyAsync(po->breakdown, c->b_bd.p, sizeof(int64_t) * EVG_BD_N * size_t(c->T), cudaMemcpyDeviceToHost, s));
+    }
+    if (po->info && c->Dn) CK(cudaMemcpyAsync(po->info, c->b_qinfo.p, sizeof(evg_queue_info) * size_t(c->Dn), cudaMemcpyDeviceToHost, s));
+    if (po->group_info && c->G) CK(cudaMemcpyAsync(po->group_info, c->b_ginfo.p, sizeof(evg_group_info) * size_t(c->G), cudaMemcpyDeviceToHost, s));
+  }
+  if (ao) {
+    if (!c->have_hosts) return fail(EVG_ERR_STATE, "allocator results requested but no hosts were uploaded");
+    if (ao->result && c->Dn) CK(cudaMemcpyAsync(ao->result, c->b_result.p, sizeof(evg_alloc_result) * size_t(c->Dn), cudaMemcpyDeviceToHost, s));
+    if (ao->status && c->Dn) CK(cudaMemcpyAsync(ao->status, c->b_status.p, sizeof(int32_t) * size_t(c->Dn), cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return EVG_OK;
+}
+
+void* evg_device_result_ptr(evg_ctx* c) { return c ? c->b_result.p : nullptr; }
+int64_t evg_last_launch_count(evg_ctx* c) { return c ? c->launches : 0; }
+
+int evg_last_timing_ms(evg_ctx* c, float* total_ms, float* sort_ms) {
+  if (!c || !c->timed) return fail(EVG_ERR_STATE, "no timed run");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventSynchronize(c->ev_end));
+  if (total_ms) CK(cudaEventElapsedTime(total_ms, c->ev_begin, c->ev_end));
+  if (sort_ms) CK(cudaEventElapsedTime(sort_ms, c->ev_sort0, c->ev_sort1));
+  return EVG_OK;
+}
+
+int evg_plan_batch(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* distros, int64_t now_ns, uint32_t opts,
+                   evg_plan_out* out) {
+  int rc = evg_upload(c, tasks, distros, nullptr, nullptr, nullptr);
+  if (rc != EVG_OK) return rc;
+  rc = evg_run_resident(c, now_ns, opts);
+  if (rc != EVG_OK) return rc;
+  return evg_download(c, out, nullptr);
+}
+
+int evg_plan_and_alloc_batch(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* distros,
+                             const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg, int64_t now_ns,
+                             uint32_t opts, evg_plan_out* plan_out, evg_alloc_out* alloc_out) {
+  if (!hosts || !acfg) return fail(EVG_ERR_INVALID, "evg_plan_and_alloc_batch needs hosts and allocator config");
+  int rc = evg_upload(c, tasks, distros, hosts, host_off, acfg);
+  if (rc != EVG_OK) return rc;
+  rc = evg_run_resident(c, now_ns, opts);
+  if (rc != EVG_OK) return rc;
+  return evg_download(c, plan_out, alloc_out);
+}
+
+int evg_alloc_batch(evg_ctx* c, const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* cfg,
+                    const evg_queue_info* info, evg_group_info* groups, const int64_t* group_off, int32_t n_distros,
+                    int64_t now_ns, evg_alloc_out* out) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  if (n_distros < 0 || (n_distros > 0 && (!info || !group_off || !out))) return fail(EVG_ERR_INVALID, "evg_alloc_batch: null argument");
+  CK(cudaSetDevice(c->device));
+  const int64_t G = n_distros > 0 ? group_off[n_distros] : 0;
+  if (G > 0 && !groups) return fail(EVG_ERR_INVALID, "evg_alloc_batch: groups is null");
+  int rc = upload_hosts(c, hosts, host_off, cfg, n_distros);
+  if (rc != EVG_OK) return rc;
+  cudaStream_t s = c->stream;
+  CK(c->b_groupoff.ensure(sizeof(int64_t) * size_t(n_distros + 1)));
+  CK(c->b_qinfo.ensure(sizeof(evg_queue_info) * size_t(n_distros + 1)));
+  CK(c->b_ginfo.ensure(sizeof(evg_group_info) * size_t(G + 1)));
+  if (n_distros > 0) {
+    CK(cudaMemcpyAsync(c->b_groupoff.p, group_off, sizeof(int64_t) * size_t(n_distros + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->b_qinfo.p, info, sizeof(evg_queue_info) * size_t(n_distros), cudaMemcpyHostToDevice, s));
+  }
+  if (G > 0) CK(cudaMemcpyAsync(c->b_ginfo.p, groups, sizeof(evg_group_info) * size_t(G), cudaMemcpyHostToDevice, s));
+  c->Dn = n_distros;
+  c->G = G;
+  c->have_tasks = false;  // the resident planner inputs no longer match these tables
+  c->launches = 0;
+  rc = run_alloc(c, now_ns);
+  if (rc != EVG_OK) return rc;
+  if (out->result && n_distros) CK(cudaMemcpyAsync(out->result, c->b_result.p, sizeof(evg_alloc_result) * size_t(n_distros), cudaMemcpyDeviceToHost, s));
+  if (out->status && n_distros) CK(cudaMemcpyAsync(out->status, c->b_status.p, sizeof(int32_t) * size_t(n_distros), cudaMemcpyDeviceToHost, s));
+  if (G > 0) CK(cudaMemcpyAsync(groups, c->b_ginfo.p, sizeof(evg_group_info) * size_t(G), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return EVG_OK;
+}
+
+int evg_plan_distro(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_cfg* cfg, int32_t n_groups,
+                    const int32_t* group_max_hosts, int64_t now_ns, uint32_t opts, evg_plan_out* out) {
+  if (!tasks || !cfg) return fail(EVG_ERR_INVALID, "evg_plan_distro: null argument");
+  int64_t task_off[2] = {0, tasks->n_tasks};
+  int64_t group_off[2] = {0, n_groups};
+  evg_distro_table dt;
+  dt.n_distros = 1; dt._reserved = 0; dt.task_off = task_off; dt.group_off = group_off; dt.cfg = cfg;
+  dt.group_max_hosts = group_max_hosts;
+  return evg_plan_batch(c, tasks, &dt, now_ns, opts, out);
+}
+
+int evg_alloc_distro(evg_ctx* c, const evg_host_soa* hosts, const evg_alloc_cfg* cfg, const evg_queue_info* info,
+                     evg_group_info* groups, int32_t n_groups, int64_t now_ns, evg_alloc_result* result, int32_t* status) {
+  if (!hosts || !cfg || !info) return fail(EVG_ERR_INVALID, "evg_alloc_distro: null argument");
+  int64_t host_off[2] = {0, hosts->n_hosts};
+  int64_t group_off[2] = {0, n_groups};
+  evg_alloc_out ao;
+  ao.result = result; ao.status = status;
+  return evg_alloc_batch(c, hosts, host_off, cfg, info, groups, group_off, 1, now_ns, &ao);
+}
+
+void* evg_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    g_err = "cudaHostAlloc failed";
+    return nullptr;
+  }
+  return p;
+}
+void evg_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

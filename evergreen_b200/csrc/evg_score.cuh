@@ -1,0 +1,250 @@
+// evg_score.cuh -- scalar arithmetic of the scheduler hot path, shared by every
+// kernel.  Go semantics are reproduced exactly: int64 arithmetic wraps,
+// time.Since saturates, Duration.Minutes()/Hours() are the stdlib two-term
+// FP64 formulas, float->int conversions truncate (or floor where the reference
+// calls math.Floor).  All FP64 operations use explicit round-to-nearest
+// intrinsics on the device so nvcc cannot contract them into FMAs.
+//
+// Reference: scheduler/planner.go:209-337 (Unit.info, unitInfo.value,
+// computeRankValue, computePriority), model/distro/distro.go:353-408 (factor
+// getters), scheduler/utilization_based_host_allocator.go:268-296,324-409.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/evg_sched.h"
+
+#if defined(__CUDACC__)
+#define EVG_HD __host__ __device__ __forceinline__
+#else
+#define EVG_HD inline
+#include <cmath>
+#endif
+
+namespace evg {
+
+constexpr int64_t kSecond = 1000000000LL;
+constexpr int64_t kMinute = 60 * kSecond;
+constexpr int64_t kHour = 60 * kMinute;
+constexpr int64_t kWeek = 7 * 24 * kHour;
+constexpr int64_t kMaxDurationPerDistroHost = 30 * kMinute;  // globals.go:267
+constexpr int64_t kI64Max = 0x7fffffffffffffffLL;
+constexpr int64_t kI64Min = -kI64Max - 1;
+
+// ---- FP64 with fixed rounding, never contracted ----
+EVG_HD double fadd64(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  volatile double r = a + b;
+  return r;
+#endif
+}
+EVG_HD double fmul64(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  volatile double r = a * b;
+  return r;
+#endif
+}
+EVG_HD double fdiv64(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __ddiv_rn(a, b);
+#else
+  volatile double r = a / b;
+  return r;
+#endif
+}
+EVG_HD double i2d(int64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ll2double_rn(x);
+#else
+  return double(x);
+#endif
+}
+EVG_HD int64_t d2i_trunc(double x) {  // Go int64(x)
+#if defined(__CUDA_ARCH__)
+  return __double2ll_rz(x);
+#else
+  return int64_t(x);
+#endif
+}
+EVG_HD int64_t d2i_floor(double x) {  // Go int64(math.Floor(x))
+#if defined(__CUDA_ARCH__)
+  return __double2ll_rd(x);
+#else
+  return int64_t(std::floor(x));
+#endif
+}
+EVG_HD int64_t d2i_ceil(double x) {  // Go int(math.Ceil(x))
+#if defined(__CUDA_ARCH__)
+  return __double2ll_ru(x);
+#else
+  return int64_t(std::ceil(x));
+#endif
+}
+
+// ---- Go integer / time semantics ----
+EVG_HD int64_t wadd(int64_t a, int64_t b) { return int64_t(uint64_t(a) + uint64_t(b)); }
+EVG_HD int64_t wsub(int64_t a, int64_t b) { return int64_t(uint64_t(a) - uint64_t(b)); }
+EVG_HD int64_t wmul(int64_t a, int64_t b) { return int64_t(uint64_t(a) * uint64_t(b)); }
+
+// time.Since(t) with a frozen clock; saturates like time.Time.Sub.
+EVG_HD int64_t since(int64_t now, int64_t t) {
+  if (t == EVG_TIME_ZERO) return kI64Max;
+  if (t < 0 && now > kI64Max + t) return kI64Max;
+  if (t > 0 && now < kI64Min + t) return kI64Min;
+  return now - t;
+}
+// time.Duration.Minutes() / Hours()
+EVG_HD double dur_minutes(int64_t d) { return fadd64(i2d(d / kMinute), fdiv64(i2d(d % kMinute), 60.0 * 1e9)); }
+EVG_HD double dur_hours(int64_t d) { return fadd64(i2d(d / kHour), fdiv64(i2d(d % kHour), 60.0 * 60.0 * 1e9)); }
+
+EVG_HD int64_t factor(int64_t x) { return x <= 0 ? 1 : x; }       // distro.go:353-408
+EVG_HD double factor_d(double x) { return x <= 0.0 ? 1.0 : x; }  // distro.go:381-386
+
+// unitInfo flags (planner.go:174-201)
+enum : uint32_t {
+  UF_MERGE_QUEUE = 1u,  // ContainsInCommitQueue
+  UF_PATCH = 2u,        // ContainsInPatch
+  UF_NON_GROUP = 4u,    // ContainsNonGroupTasks
+  UF_GENERATE = 8u,     // ContainsGenerateTask
+  UF_STEPBACK = 16u     // ContainsStepbackTask
+};
+
+// The reduction Unit.info performs over a unit's member tasks (planner.go:302-337).
+struct UnitAcc {
+  int64_t tiq;     // TimeInQueue
+  int64_t rt;      // ExpectedRuntime
+  int64_t max_p;   // MaxPriority (starts at 0)
+  int64_t max_d;   // MaxNumDependents (starts at 0)
+  int64_t n;       // len(TaskIDs)
+  uint32_t flags;  // UF_*
+};
+
+EVG_HD void acc_init(UnitAcc& a) {
+  a.tiq = 0; a.rt = 0; a.max_p = 0; a.max_d = 0; a.n = 0; a.flags = 0;
+}
+
+// One member task's contribution (planner.go:307-334).
+EVG_HD void acc_add(UnitAcc& a, int64_t now, int32_t priority, int64_t expected_ns, int64_t queue_basis_ns,
+                    int32_t num_dependents, int32_t group_id, uint32_t tflags) {
+  uint32_t req = tflags & EVG_TF_REQ_MASK;
+  if (req == EVG_TF_REQ_MERGE_QUEUE) a.flags |= UF_MERGE_QUEUE;
+  else if (req == EVG_TF_REQ_PATCH) a.flags |= UF_PATCH;
+  if (group_id < 0) a.flags |= UF_NON_GROUP;
+  if (tflags & EVG_TF_GENERATE) a.flags |= UF_GENERATE;
+  if (tflags & EVG_TF_STEPBACK) a.flags |= UF_STEPBACK;
+  if (queue_basis_ns != EVG_TIME_ZERO) a.tiq = wadd(a.tiq, since(now, queue_basis_ns));
+  if (int64_t(priority) > a.max_p) a.max_p = priority;
+  a.rt = wadd(a.rt, expected_ns);
+  if (int64_t(num_dependents) > a.max_d) a.max_d = num_dependents;
+  a.n += 1;
+}
+
+// unitInfo.value (planner.go:209-300).  Returns TotalValue; when bd != nullptr
+// also writes the 13-field breakdown (EVG_BD_*), bookkeeping quirks included.
+EVG_HD int64_t unit_value(const UnitAcc& a, const evg_distro_cfg& c, int64_t* bd) {
+  const int64_t len = a.n;
+  const bool nongroup = (a.flags & UF_NON_GROUP) != 0;
+  const bool gen = (a.flags & UF_GENERATE) != 0;
+  const bool mq = (a.flags & UF_MERGE_QUEUE) != 0;
+  const bool pat = (a.flags & UF_PATCH) != 0;
+  // computePriority planner.go:271-300
+  int64_t p_initial = wadd(1, a.max_p), p_tg = 0, p_gen = 0, p_cq = 0;
+  int64_t prio = p_initial;
+  if (!nongroup) { p_tg = len; prio = wadd(prio, len); }
+  if (gen) {
+    const int64_t gf = factor(c.generate_task_factor);
+    const int64_t prev = prio;
+    prio = wmul(prio, gf);
+    p_gen = wsub(prio, prev);
+    if (!nongroup) { p_tg = wmul(p_tg, gf); p_gen = wsub(p_gen, wmul(len, gf)); }
+  }
+  if (mq) { p_cq = 200; prio = wadd(prio, 200); }
+  // computeRankValue planner.go:223-265
+  int64_t r_patch = 0, r_patch_wait = 0, r_cq = 0, r_main = 0, r_step = 0;
+  if (pat) {
+    r_patch = factor(c.patch_factor);
+    r_patch_wait = wmul(factor(c.patch_time_in_queue_factor), d2i_floor(fdiv64(dur_minutes(a.tiq), i2d(len))));
+  } else if (mq) {
+    r_cq = factor(c.commit_queue_factor);
+  } else {
+    const int64_t avg = a.tiq / len;
+    if (avg < kWeek) r_main = wmul(factor(c.mainline_time_in_queue_factor), d2i_trunc(dur_hours(kWeek - avg)));
+    if (a.flags & UF_STEPBACK) r_step = factor(c.stepback_task_factor);
+  }
+  const int64_t r_deps = d2i_trunc(fmul64(factor_d(c.num_dependents_factor), i2d(a.max_d)));
+  const int64_t r_rt = wmul(factor(c.expected_runtime_factor), d2i_floor(fdiv64(dur_minutes(a.rt), i2d(len))));
+  int64_t rank = 1;
+  rank = wadd(rank, r_patch); rank = wadd(rank, r_patch_wait); rank = wadd(rank, r_main);
+  rank = wadd(rank, r_cq); rank = wadd(rank, r_step); rank = wadd(rank, r_deps); rank = wadd(rank, r_rt);
+  const int64_t total = wadd(wmul(prio, rank), len);
+  if (bd) {
+    bd[EVG_BD_TASK_GROUP_LENGTH] = len; bd[EVG_BD_TOTAL_VALUE] = total;
+    bd[EVG_BD_P_INITIAL] = p_initial; bd[EVG_BD_P_TASK_GROUP] = p_tg;
+    bd[EVG_BD_P_GENERATOR] = p_gen; bd[EVG_BD_P_COMMIT_QUEUE] = p_cq;
+    bd[EVG_BD_R_COMMIT_QUEUE] = r_cq; bd[EVG_BD_R_NUM_DEPENDENTS] = r_deps;
+    bd[EVG_BD_R_ESTIMATED_RUNTIME] = r_rt; bd[EVG_BD_R_MAINLINE_WAIT] = r_main;
+    bd[EVG_BD_R_STEPBACK] = r_step; bd[EVG_BD_R_PATCH] = r_patch; bd[EVG_BD_R_PATCH_WAIT] = r_patch_wait;
+  }
+  return total;
+}
+
+// Sort-key encoding: ascending unsigned order of enc_value(v) == descending v.
+EVG_HD uint64_t enc_value(int64_t v) { return ~(uint64_t(v) ^ 0x8000000000000000ULL); }
+EVG_HD int64_t dec_value(uint64_t k) { return int64_t((~k) ^ 0x8000000000000000ULL); }
+
+// Canonical tie word: smallest member index, anchor (smallest primary member
+// index), rank inside the unit; 21 bits each (distros hold < 2^21 tasks).
+constexpr int kIdxBits = 21;
+constexpr int64_t kMaxTasksPerDistro = (int64_t(1) << kIdxBits) - 1;
+EVG_HD uint64_t enc_tie(uint32_t min_member, uint32_t anchor, uint32_t rank_in_unit) {
+  return (uint64_t(min_member) << (2 * kIdxBits)) | (uint64_t(anchor) << kIdxBits) | uint64_t(rank_in_unit);
+}
+
+// TaskList.Less (planner.go:387-405) extended by input index: true when task x
+// sorts strictly before task y inside a unit.
+EVG_HD bool in_unit_less(int32_t tgo_x, int32_t nd_x, int32_t pr_x, int64_t ex_x, uint32_t ix,
+                         int32_t tgo_y, int32_t nd_y, int32_t pr_y, int64_t ex_y, uint32_t iy) {
+  if (tgo_x != tgo_y) return tgo_x < tgo_y;
+  if (nd_x != nd_y) return nd_x > nd_y;
+  if (pr_x != pr_y) return pr_x > pr_y;
+  if (ex_x != ex_y) return ex_x > ex_y;
+  return ix < iy;
+}
+
+// calcNewHostsNeeded (utilization_based_host_allocator.go:268-296)
+EVG_HD int64_t calc_new_hosts_needed(int64_t short_ns, int64_t threshold, int64_t exp_free, int64_t n_long,
+                                     int64_t n_overdue, int64_t n_mq, bool round_down) {
+  double x = fdiv64(i2d(short_ns), i2d(threshold));
+  x = fadd64(x, -i2d(exp_free));
+  x = fadd64(x, i2d(n_long));
+  x = fadd64(x, i2d(n_overdue));
+  x = fadd64(x, i2d(n_mq));
+  if (exp_free < 1 && x > 0.0 && x < 1.0) return 1;
+  int64_t n = round_down ? d2i_floor(x) : d2i_ceil(x);
+  return n < 0 ? 0 : n;
+}
+
+// One running host's contribution to getSoonToBeFreeHosts (allocator.go:357-378),
+// already scaled by futureHostFraction.
+EVG_HD double soon_free_term(int64_t now, int64_t expected, int64_t stddev, int64_t start, int64_t threshold,
+                             double future_host_fraction) {
+  const int64_t elapsed = since(now, start);
+  const int64_t left = wsub(expected, elapsed);
+  double f;
+  if (elapsed > kMaxDurationPerDistroHost && stddev > 0 && elapsed > wadd(expected, wmul(3, stddev))) f = 0.0;
+  else f = fdiv64(i2d(wsub(threshold, left)), i2d(threshold));
+  if (f < 0.0) f = 0.0;
+  if (f > 1.0) f = 1.0;
+  return fmul64(future_host_fraction, f);
+}
+
+// isMaxHostsCapacity (allocator.go:397-409)
+EVG_HD bool is_max_hosts_capacity(int64_t max_hosts, bool pool, int64_t pool_max, int64_t n_new, int64_t n_existing) {
+  if (pool && n_new > max_hosts * pool_max - n_existing) return true;
+  return n_new + n_existing > max_hosts;
+}
+
+}  // namespace evg

@@ -1,0 +1,307 @@
+"""Host-side mirror of the reference `scheduler` package's plug points, backed by
+libevgsched.so (CUDA, sm_100a).  Same names, argument meaning and error
+behaviour as the Go interfaces this path sits behind:
+
+* ``PrioritizeTasks`` / ``TaskPlanner``      scheduler/scheduler.go:25-51
+* ``GetDistroQueueInfo``                      scheduler/scheduler.go:56-159
+* ``HostAllocator`` / ``GetHostAllocator``    scheduler/host_allocator.go:15-32
+* ``UtilizationBasedHostAllocator``           scheduler/utilization_based_host_allocator.go:26-130
+* ``PlanDistro`` (planner half, DB-free)      scheduler/wrapper.go:30-130
+
+plus the batched entry the GPU wants (one call per 15 s tick instead of one
+amboy job per distro, units/crons.go:303-332).  Nothing here computes scores,
+orders or host counts on the CPU; the host code only marshals and un-marshals.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from . import model as M
+from . import soa as S
+
+RUNNER_NAME = "scheduler"  # scheduler/scheduler.go:53
+# new plug names a maintainer registers next to the existing ones
+# (globals.go:1080-1100: ValidTaskPlannerVersions / ValidHostAllocators)
+PLANNER_VERSION_GPU_TUNABLE = "gpu-tunable"
+HOST_ALLOCATOR_GPU_UTILIZATION = "gpu-utilization"
+
+
+class AllocatorError(Exception):
+    """The `error` UtilizationBasedHostAllocator returns for data problems."""
+    MESSAGES = {
+        L.EVG_ALLOC_ERR_FUTURE_FRACTION: "future host factor cannot be greater than 1",   # allocator.go:302-304
+        L.EVG_ALLOC_ERR_POOL_SIZE: "unable to plan hosts for distro due to pool size",     # allocator.go:200-202
+        L.EVG_ALLOC_ERR_PARENT_MISSING: "error finding parent distros",                    # allocator.go:151-158
+    }
+
+    def __init__(self, status: int, distro_id: str = ""):
+        super().__init__(f"error calculating hosts for distro {distro_id}: {self.MESSAGES.get(status, status)}")
+        self.status = status
+
+
+class Engine:
+    """One evg_ctx: device buffers + stream.  Thread-compatible (one tick at a time)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = L.load()
+        h = C.c_void_p()
+        L.check(self.lib.evg_init(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.ctx = h
+        self._n_tasks = self._n_distros = self._n_groups = 0
+        self._has_hosts = False
+
+    def close(self) -> None:
+        if getattr(self, "ctx", None):
+            self.lib.evg_shutdown(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- resident API ------------------------------------------------------
+    def upload(self, tasks: S.TaskSoA, distros: S.DistroTable, hosts: Optional[S.HostSoA] = None) -> None:
+        ts, ds = tasks.struct(), distros.struct()
+        if hosts is not None:
+            hs = hosts.struct()
+            L.check(self.lib.evg_upload(self.ctx, C.byref(ts), C.byref(ds), C.byref(hs), L.ptr(hosts.host_off),
+                                        L.ptr(hosts.cfg) if hosts.cfg.shape[0] else None))
+        else:
+            L.check(self.lib.evg_upload(self.ctx, C.byref(ts), C.byref(ds), None, None, None))
+        self._n_tasks, self._n_distros, self._n_groups = tasks.n_tasks, distros.n_distros, distros.n_groups
+        self._has_hosts = hosts is not None
+
+    def run(self, now: int, opts: int = 0) -> None:
+        L.check(self.lib.evg_run_resident(self.ctx, int(now), int(opts)))
+
+    def download(self, want_breakdown: bool = False, want_alloc: Optional[bool] = None):
+        T, D, G = self._n_tasks, self._n_distros, self._n_groups
+        po = S.PlanOutput(np.empty(T, np.int32), np.empty(T, np.int64), np.zeros(D, L.QUEUE_INFO_DTYPE),
+                          np.zeros(G, L.GROUP_INFO_DTYPE),
+                          np.empty((T, L.EVG_BD_N), np.int64) if want_breakdown else None)
+        ps = L.PlanOutStruct(L.ptr(po.order), L.ptr(po.total_value),
+                             L.ptr(po.breakdown) if want_breakdown else None, L.ptr(po.info), L.ptr(po.group_info))
+        ao = None
+        if want_alloc is None:
+            want_alloc = self._has_hosts
+        if want_alloc:
+            ao = S.AllocOutput(np.zeros(D, L.ALLOC_RESULT_DTYPE), np.zeros(D, np.int32))
+            as_ = L.AllocOutStruct(L.ptr(ao.result), L.ptr(ao.status))
+            L.check(self.lib.evg_download(self.ctx, C.byref(ps), C.byref(as_)))
+        else:
+            L.check(self.lib.evg_download(self.ctx, C.byref(ps), None))
+        return po, ao
+
+    def device_result_ptr(self) -> int:
+        return int(self.lib.evg_device_result_ptr(self.ctx) or 0)
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.evg_last_launch_count(self.ctx))
+
+    def last_timing_ms(self) -> Tuple[float, float]:
+        a, b = C.c_float(), C.c_float()
+        L.check(self.lib.evg_last_timing_ms(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # -- one-shot batch API (host buffers in, host buffers out) ---------------
+    def plan_batch(self, tasks: S.TaskSoA, distros: S.DistroTable, now: int, breakdown: bool = False) -> S.PlanOutput:
+        T, D, G = tasks.n_tasks, distros.n_distros, distros.n_groups
+        po = S.PlanOutput(np.empty(T, np.int32), np.empty(T, np.int64), np.zeros(D, L.QUEUE_INFO_DTYPE),
+                          np.zeros(G, L.GROUP_INFO_DTYPE), np.empty((T, L.EVG_BD_N), np.int64) if breakdown else None)
+        ps = L.PlanOutStruct(L.ptr(po.order), L.ptr(po.total_value), L.ptr(po.breakdown) if breakdown else None,
+                             L.ptr(po.info), L.ptr(po.group_info))
+        ts, ds = tasks.struct(), distros.struct()
+        L.check(self.lib.evg_plan_batch(self.ctx, C.byref(ts), C.byref(ds), int(now),
+                                        L.EVG_OPT_BREAKDOWN if breakdown else 0, C.byref(ps)))
+        self._n_tasks, self._n_distros, self._n_groups, self._has_hosts = T, D, G, False
+        return po
+
+    def plan_and_alloc_batch(self, tasks: S.TaskSoA, distros: S.DistroTable, hosts: S.HostSoA, now: int,
+                             breakdown: bool = False):
+        T, D, G = tasks.n_tasks, distros.n_distros, distros.n_groups
+        po = S.PlanOutput(np.empty(T, np.int32), np.empty(T, np.int64), np.zeros(D, L.QUEUE_INFO_DTYPE),
+                          np.zeros(G, L.GROUP_INFO_DTYPE), np.empty((T, L.EVG_BD_N), np.int64) if breakdown else None)
+        ao = S.AllocOutput(np.zeros(D, L.ALLOC_RESULT_DTYPE), np.zeros(D, np.int32))
+        ps = L.PlanOutStruct(L.ptr(po.order), L.ptr(po.total_value), L.ptr(po.breakdown) if breakdown else None,
+                             L.ptr(po.info), L.ptr(po.group_info))
+        as_ = L.AllocOutStruct(L.ptr(ao.result), L.ptr(ao.status))
+        ts, ds, hs = tasks.struct(), distros.struct(), hosts.struct()
+        L.check(self.lib.evg_plan_and_alloc_batch(self.ctx, C.byref(ts), C.byref(ds), C.byref(hs), L.ptr(hosts.host_off),
+                                                  L.ptr(hosts.cfg) if hosts.cfg.shape[0] else None, int(now),
+                                                  L.EVG_OPT_BREAKDOWN if breakdown else 0, C.byref(ps), C.byref(as_)))
+        self._n_tasks, self._n_distros, self._n_groups, self._has_hosts = T, D, G, True
+        return po, ao
+
+    def alloc_batch(self, hosts: S.HostSoA, qinfo: np.ndarray, ginfo: np.ndarray, group_off: np.ndarray, now: int):
+        D = int(qinfo.shape[0])
+        ao = S.AllocOutput(np.zeros(D, L.ALLOC_RESULT_DTYPE), np.zeros(D, np.int32))
+        as_ = L.AllocOutStruct(L.ptr(ao.result), L.ptr(ao.status))
+        hs = hosts.struct()
+        qinfo = np.ascontiguousarray(qinfo, dtype=L.QUEUE_INFO_DTYPE)
+        ginfo = np.ascontiguousarray(ginfo, dtype=L.GROUP_INFO_DTYPE)
+        group_off = np.ascontiguousarray(group_off, dtype=np.int64)
+        L.check(self.lib.evg_alloc_batch(self.ctx, C.byref(hs), L.ptr(hosts.host_off),
+                                         L.ptr(hosts.cfg) if D else None, L.ptr(qinfo) if D else None,
+                                         L.ptr(ginfo) if ginfo.shape[0] else None, L.ptr(group_off), D, int(now),
+                                         C.byref(as_)))
+        return ao, ginfo
+
+
+_default_engine: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine
+
+
+# ---------------------------------------------------------------------------
+# reference-shaped API
+# ---------------------------------------------------------------------------
+
+@dataclass
+class TaskPlannerOptions:  # scheduler/scheduler.go:18-23
+    id: str = ""
+    is_secondary_queue: bool = False
+    includes_dependencies: bool = False
+    started_at: int = M.ZERO_TIME
+
+
+def _queue_info_from_rows(q, groups, names: Sequence[str]) -> M.DistroQueueInfo:
+    infos: List[M.TaskGroupInfo] = []
+    if int(q["has_ungrouped"]):
+        u = q["ungrouped"]
+        infos.append(M.TaskGroupInfo("", *[int(u[f]) for f in L.GROUP_INFO_FIELDS]))
+    for name, g in zip(names, groups):
+        infos.append(M.TaskGroupInfo(name, *[int(g[f]) for f in L.GROUP_INFO_FIELDS]))
+    return M.DistroQueueInfo(
+        length=int(q["length"]), length_with_dependencies_met=int(q["length_with_dependencies_met"]),
+        count_dep_filled_merge_queue_tasks=int(q["count_dep_filled_merge_queue_tasks"]),
+        expected_duration=int(q["expected_duration"]), max_duration_threshold=int(q["max_duration_threshold"]),
+        count_duration_over_threshold=int(q["count_duration_over_threshold"]),
+        duration_over_threshold=int(q["duration_over_threshold"]),
+        count_wait_over_threshold=int(q["count_wait_over_threshold"]), task_group_infos=infos,
+        secondary_queue=bool(q["secondary_queue"]))
+
+
+def plan_distros(batch: Sequence[Tuple[M.Distro, List[M.Task]]], now: int, *, engine: Optional[Engine] = None,
+                 dependency_db: Optional[Dict[str, M.Task]] = None, breakdown: bool = True,
+                 secondary: bool = False):
+    """Batched runTunablePlanner minus persistence (scheduler/scheduler.go:34-51):
+    returns, per distro, (ranked [Task] with SortingValueBreakdown stamped,
+    DistroQueueInfo)."""
+    eng = engine or default_engine()
+    soa, table, keys = S.marshal_tasks(batch, now, dependency_db)
+    po = eng.plan_batch(soa, table, now, breakdown=breakdown)
+    out = []
+    for d, (distro, tasks) in enumerate(batch):
+        a, b = int(table.task_off[d]), int(table.task_off[d + 1])
+        ga, gb = int(table.group_off[d]), int(table.group_off[d + 1])
+        ranked = []
+        for r in range(a, b):
+            t = tasks[int(po.order[r])]
+            if breakdown:
+                t.sorting_value_breakdown = M.SortingValueBreakdown.from_row(po.breakdown[r])  # planner.go:475
+            else:
+                t.sorting_value_breakdown = M.SortingValueBreakdown(total_value=int(po.total_value[r]))
+            ranked.append(t)
+        info = _queue_info_from_rows(po.info[d], po.group_info[ga:gb], keys[d].group_names)
+        info.secondary_queue = secondary  # scheduler.go:44
+        out.append((ranked, info))
+    return out
+
+
+def PrioritizeTasks(d: M.Distro, tasks: List[M.Task], opts: Optional[TaskPlannerOptions] = None, *, now: int,
+                    engine: Optional[Engine] = None, dependency_db: Optional[Dict[str, M.Task]] = None):
+    """scheduler.PrioritizeTasks (scheduler/scheduler.go:27-32) for one distro.
+    Returns (plan, DistroQueueInfo); the reference persists the info instead
+    of returning it (scheduler.go:43-48)."""
+    opts = opts or TaskPlannerOptions()
+    (plan, info), = plan_distros([(d, tasks)], now, engine=engine, dependency_db=dependency_db,
+                                 secondary=opts.is_secondary_queue)
+    info.plan_created_at = opts.started_at
+    return plan, info
+
+
+def GetDistroQueueInfo(distro: M.Distro, tasks: List[M.Task], max_duration_threshold: int,
+                       opts: Optional[TaskPlannerOptions] = None, *, now: int, engine: Optional[Engine] = None,
+                       dependency_db: Optional[Dict[str, M.Task]] = None) -> M.DistroQueueInfo:
+    """scheduler.GetDistroQueueInfo (scheduler/scheduler.go:56-159).  Every
+    quantity is a commutative sum, so the plan order does not matter."""
+    opts = opts or TaskPlannerOptions()
+    import copy
+    d = copy.deepcopy(distro)
+    d.planner_settings.target_time = max_duration_threshold
+    d.dispatcher_settings.version = (M.DISPATCHER_VERSION_REVISED_WITH_DEPENDENCIES
+                                     if opts.includes_dependencies else "")
+    eng = engine or default_engine()
+    soa, table, keys = S.marshal_tasks([(d, tasks)], now, dependency_db)
+    po = eng.plan_batch(soa, table, now)
+    info = _queue_info_from_rows(po.info[0], po.group_info, keys[0].group_names)
+    return info
+
+
+def allocate_distros(datas: Sequence[M.HostAllocatorData], now: int, *, engine: Optional[Engine] = None):
+    """Batched UtilizationBasedHostAllocator: [(new_hosts, free_hosts, status)].
+    Mutates each DistroQueueInfo.TaskGroupInfos[i].CountFree/CountRequired like
+    the reference (utilization_based_host_allocator.go:107-110)."""
+    eng = engine or default_engine()
+    qrows, grows, goff, names = S.queue_info_rows([d.distro_queue_info for d in datas])
+    hosts = S.marshal_hosts(datas, names)
+    ao, ginfo = eng.alloc_batch(hosts, qrows, grows, goff, now)
+    out = []
+    for i, data in enumerate(datas):
+        st = int(ao.status[i])
+        if st == L.EVG_ALLOC_OK:
+            lookup = {n: k for k, n in enumerate(names[i])}
+            for g in data.distro_queue_info.task_group_infos:
+                k = lookup.get(g.name)
+                if k is not None:
+                    row = ginfo[int(goff[i]) + k]
+                    g.count_free, g.count_required = int(row["count_free"]), int(row["count_required"])
+        out.append((int(ao.result[i]["new_hosts"]), int(ao.result[i]["free_hosts"]), st))
+    return out
+
+
+def UtilizationBasedHostAllocator(data: M.HostAllocatorData, *, now: int, engine: Optional[Engine] = None):
+    """HostAllocator (scheduler/host_allocator.go:15): (newHostsNeeded, estimatedFreeHosts) or raises."""
+    (n, f, st), = allocate_distros([data], now, engine=engine)
+    if st != L.EVG_ALLOC_OK:
+        raise AllocatorError(st, data.distro.id)
+    return n, f
+
+
+HostAllocator = Callable[..., Tuple[int, int]]
+
+
+def GetHostAllocator(name: str) -> HostAllocator:
+    """scheduler.GetHostAllocator (scheduler/host_allocator.go:25-32): every name resolves to the utilization allocator."""
+    return UtilizationBasedHostAllocator
+
+
+def plan_and_allocate(batch: Sequence[Tuple[M.Distro, List[M.Task], M.HostAllocatorData]], now: int, *,
+                      engine: Optional[Engine] = None, dependency_db: Optional[Dict[str, M.Task]] = None):
+    """The fused tick: distroSchedulerJob + hostAllocatorJob for every distro
+    (units/scheduler.go:57-87, units/host_allocator.go:76-196) in one call; the
+    queue info stays on the device between the two halves."""
+    eng = engine or default_engine()
+    soa, table, keys = S.marshal_tasks([(d, t) for d, t, _ in batch], now, dependency_db)
+    hosts = S.marshal_hosts([h for _, _, h in batch], [k.group_names for k in keys])
+    po, ao = eng.plan_and_alloc_batch(soa, table, hosts, now)
+    out = []
+    for i, (distro, tasks, _) in enumerate(batch):
+        a, b = int(table.task_off[i]), int(table.task_off[i + 1])
+        ga, gb = int(table.group_off[i]), int(table.group_off[i + 1])
+        ranked = [tasks[int(po.order[r])] for r in range(a, b)]
+        info = _queue_info_from_rows(po.info[i], po.group_info[ga:gb], keys[i].group_names)
+        out.append((ranked, info, int(ao.result[i]["new_hosts"]), int(ao.result[i]["free_hosts"]), int(ao.status[i])))
+    return out

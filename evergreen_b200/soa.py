@@ -1,0 +1,371 @@
+"""SoA tables (numpy) that cross the C-ABI, and the marshalling of
+reference-shaped structs (evergreen_b200.model) into them.
+
+This is what the Go shim does on the reference side of the boundary
+(INTEGRATION.md): intern the string keys the planner hashes
+(task-group string, version, task id -> dense distro-local ids), resolve the
+per-task inputs the reference fetches lazily (expected duration, dependency
+state) and lay everything out column-wise.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from . import model as M
+
+
+@dataclass
+class TaskSoA:
+    """evg_task_soa (include/evg_sched.h). 48 B per task."""
+    priority: np.ndarray
+    expected_ns: np.ndarray
+    queue_basis_ns: np.ndarray
+    wait_basis_ns: np.ndarray
+    num_dependents: np.ndarray
+    task_group_order: np.ndarray
+    group_id: np.ndarray
+    version_id: np.ndarray
+    flags: np.ndarray
+    dep_off: Optional[np.ndarray] = None
+    dep_idx: Optional[np.ndarray] = None
+
+    COLUMNS = (("priority", np.int32), ("expected_ns", np.int64), ("queue_basis_ns", np.int64),
+               ("wait_basis_ns", np.int64), ("num_dependents", np.int32), ("task_group_order", np.int32),
+               ("group_id", np.int32), ("version_id", np.int32), ("flags", np.uint32))
+
+    @property
+    def n_tasks(self) -> int:
+        return int(self.priority.shape[0])
+
+    @property
+    def n_edges(self) -> int:
+        return 0 if self.dep_idx is None else int(self.dep_idx.shape[0])
+
+    def normalize(self) -> "TaskSoA":
+        for name, dt in self.COLUMNS:
+            setattr(self, name, np.ascontiguousarray(getattr(self, name), dtype=dt))
+        if self.dep_idx is not None and self.dep_idx.shape[0] > 0:
+            self.dep_off = np.ascontiguousarray(self.dep_off, dtype=np.int64)
+            self.dep_idx = np.ascontiguousarray(self.dep_idx, dtype=np.int32)
+        else:
+            self.dep_off, self.dep_idx = None, None
+        return self
+
+    def struct(self) -> L.TaskSoAStruct:
+        s = L.TaskSoAStruct()
+        s.n_tasks, s.n_edges = self.n_tasks, self.n_edges
+        for name, _ in self.COLUMNS:
+            setattr(s, name, L.ptr(getattr(self, name)))
+        s.dep_off, s.dep_idx = L.ptr(self.dep_off), L.ptr(self.dep_idx)
+        return s
+
+    def nbytes(self) -> int:
+        n = sum(getattr(self, name).nbytes for name, _ in self.COLUMNS)
+        if self.dep_idx is not None:
+            n += self.dep_off.nbytes + self.dep_idx.nbytes
+        return n
+
+
+@dataclass
+class DistroTable:
+    """evg_distro_table."""
+    task_off: np.ndarray
+    group_off: np.ndarray
+    cfg: np.ndarray              # L.DISTRO_CFG_DTYPE
+    group_max_hosts: np.ndarray
+
+    @property
+    def n_distros(self) -> int:
+        return int(self.cfg.shape[0])
+
+    @property
+    def n_groups(self) -> int:
+        return int(self.group_off[-1]) if self.group_off.shape[0] else 0
+
+    def normalize(self) -> "DistroTable":
+        self.task_off = np.ascontiguousarray(self.task_off, dtype=np.int64)
+        self.group_off = np.ascontiguousarray(self.group_off, dtype=np.int64)
+        self.cfg = np.ascontiguousarray(self.cfg, dtype=L.DISTRO_CFG_DTYPE)
+        self.group_max_hosts = np.ascontiguousarray(self.group_max_hosts, dtype=np.int32)
+        return self
+
+    def struct(self) -> L.DistroTableStruct:
+        s = L.DistroTableStruct()
+        s.n_distros = self.n_distros
+        s.task_off, s.group_off = L.ptr(self.task_off), L.ptr(self.group_off)
+        s.cfg = L.ptr(self.cfg) if self.n_distros else None
+        s.group_max_hosts = L.ptr(self.group_max_hosts) if self.group_max_hosts.shape[0] else None
+        return s
+
+    def nbytes(self) -> int:
+        return self.task_off.nbytes + self.group_off.nbytes + self.cfg.nbytes + self.group_max_hosts.nbytes
+
+
+@dataclass
+class HostSoA:
+    """evg_host_soa + host_off + evg_alloc_cfg[]. 32 B per host."""
+    flags: np.ndarray
+    group_id: np.ndarray
+    expected_ns: np.ndarray
+    std_ns: np.ndarray
+    start_ns: np.ndarray
+    host_off: np.ndarray
+    cfg: np.ndarray              # L.ALLOC_CFG_DTYPE
+
+    COLUMNS = (("flags", np.uint32), ("group_id", np.int32), ("expected_ns", np.int64), ("std_ns", np.int64),
+               ("start_ns", np.int64))
+
+    @property
+    def n_hosts(self) -> int:
+        return int(self.flags.shape[0])
+
+    def normalize(self) -> "HostSoA":
+        for name, dt in self.COLUMNS:
+            setattr(self, name, np.ascontiguousarray(getattr(self, name), dtype=dt))
+        self.host_off = np.ascontiguousarray(self.host_off, dtype=np.int64)
+        self.cfg = np.ascontiguousarray(self.cfg, dtype=L.ALLOC_CFG_DTYPE)
+        return self
+
+    def struct(self) -> L.HostSoAStruct:
+        s = L.HostSoAStruct()
+        s.n_hosts = self.n_hosts
+        for name, _ in self.COLUMNS:
+            setattr(s, name, L.ptr(getattr(self, name)) if self.n_hosts else None)
+        return s
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, name).nbytes for name, _ in self.COLUMNS) + self.host_off.nbytes + self.cfg.nbytes
+
+
+@dataclass
+class PlanOutput:
+    order: np.ndarray          # int32 [T]
+    total_value: np.ndarray    # int64 [T]
+    info: np.ndarray           # QUEUE_INFO_DTYPE [D]
+    group_info: np.ndarray     # GROUP_INFO_DTYPE [G]
+    breakdown: Optional[np.ndarray] = None  # int64 [T, 13]
+
+    def nbytes(self) -> int:
+        n = self.order.nbytes + self.total_value.nbytes + self.info.nbytes + self.group_info.nbytes
+        return n + (self.breakdown.nbytes if self.breakdown is not None else 0)
+
+
+@dataclass
+class AllocOutput:
+    result: np.ndarray         # ALLOC_RESULT_DTYPE [D]
+    status: np.ndarray         # int32 [D]
+
+    def nbytes(self) -> int:
+        return self.result.nbytes + self.status.nbytes
+
+
+# ---------------------------------------------------------------------------
+# marshalling reference-shaped structs -> SoA
+# ---------------------------------------------------------------------------
+
+def planner_cfg_row(d: M.Distro, includes_dependencies: bool, n_versions: int) -> tuple:
+    ps = d.planner_settings
+    return (ps.patch_factor, ps.patch_time_in_queue_factor, ps.commit_queue_factor,
+            ps.mainline_time_in_queue_factor, ps.expected_runtime_factor, ps.generate_task_factor,
+            ps.stepback_task_factor, float(ps.num_dependents_factor), d.get_target_time(),
+            int(ps.should_group_versions()), int(includes_dependencies), n_versions, 0)
+
+
+def requester_class(r: str) -> int:
+    if M.is_github_merge_queue_requester(r):
+        return L.EVG_TF_REQ_MERGE_QUEUE
+    if M.is_patch_requester(r):
+        return L.EVG_TF_REQ_PATCH
+    return L.EVG_TF_REQ_OTHER
+
+
+def satisfies_dependency(dep: M.Dependency, dep_task: M.Task) -> bool:
+    """Task.SatisfiesDependency (model/task/task.go:529-543)."""
+    if dep.status in (M.TASK_SUCCEEDED, ""):
+        return dep_task.status == M.TASK_SUCCEEDED
+    if dep.status == M.TASK_FAILED:
+        return dep_task.status == M.TASK_FAILED
+    if dep.status == M.ALL_STATUSES:
+        return dep_task.status in (M.TASK_FAILED, M.TASK_SUCCEEDED) or dep_task.blocked()
+    return False
+
+
+def dependencies_met(t: M.Task, in_queue: Dict[str, M.Task], db: Optional[Dict[str, M.Task]]) -> bool:
+    """Task.DependenciesMet (model/task/task.go:632-671) against the in-queue
+    cache first, then `db` (the tasks collection lookup); a missing dependency
+    is the lookup error checkDependenciesMet turns into false (scheduler.go:161-168)."""
+    if t.has_dependencies_met():
+        return True
+    for dep in t.depends_on:
+        dep_task = in_queue.get(dep.task_id)
+        if dep_task is None and db is not None:
+            dep_task = db.get(dep.task_id)
+        if dep_task is None:
+            return False
+        if not satisfies_dependency(dep, dep_task):
+            return False
+    return True
+
+
+@dataclass
+class MarshalledDistro:
+    """Key tables the shim keeps to translate results back to strings."""
+    group_names: List[str] = field(default_factory=list)
+    versions: List[str] = field(default_factory=list)
+
+
+def marshal_tasks(batch: Sequence[tuple], now: int, dependency_db: Optional[Dict[str, M.Task]] = None,
+                  duration_history: Optional[dict] = None):
+    """[(Distro, [Task])] -> (TaskSoA, DistroTable, [MarshalledDistro]).
+
+    Per task this resolves what the reference computes lazily on the path:
+    FetchExpectedDuration (PopulateCaches, setup_funcs.go:20-67) and
+    DependenciesMet (scheduler.go:161-168)."""
+    cols = {name: [] for name, _ in TaskSoA.COLUMNS}
+    dep_off, dep_idx = [0], []
+    task_off, group_off, cfg_rows, gmax, keys = [0], [0], [], [], []
+    for d, tasks in batch:
+        if len(tasks) > L.MAX_TASKS_PER_DISTRO:
+            raise ValueError(f"distro {d.id!r}: {len(tasks)} tasks exceed {L.MAX_TASKS_PER_DISTRO}")
+        incl = d.dispatcher_settings.version == M.DISPATCHER_VERSION_REVISED_WITH_DEPENDENCIES  # scheduler.go:28
+        index = {t.id: i for i, t in enumerate(tasks)}
+        by_id = {t.id: t for t in tasks}
+        groups: Dict[str, int] = {}
+        versions: Dict[str, int] = {}
+        md = MarshalledDistro()
+        for t in tasks:
+            hist = None if duration_history is None else duration_history.get((t.project, t.build_variant, t.display_name))
+            avg, _ = M.fetch_expected_duration(t, now, hist)
+            gid = -1
+            if t.task_group != "":
+                name = t.get_task_group_string()
+                gid = groups.get(name)
+                if gid is None:
+                    gid = groups[name] = len(groups)
+                    md.group_names.append(name)
+                    gmax.append(t.task_group_max_hosts)
+            vid = versions.get(t.version)
+            if vid is None:
+                vid = versions[t.version] = len(versions)
+                md.versions.append(t.version)
+            qb = t.activated_time if t.activated_time != M.ZERO_TIME else t.ingest_time  # planner.go:318-322
+            wb = max(t.scheduled_time, t.dependencies_met_time)  # scheduler.go:119-122 (ZERO_TIME sorts first)
+            fl = requester_class(t.requester)
+            if t.generate_task:
+                fl |= L.EVG_TF_GENERATE
+            if t.activated_by == M.STEPBACK_TASK_ACTIVATOR:
+                fl |= L.EVG_TF_STEPBACK
+            if dependencies_met(t, by_id, dependency_db):
+                fl |= L.EVG_TF_DEPS_MET
+            if t.distro_id != d.id:
+                fl |= L.EVG_TF_OTHER_DISTRO
+            cols["priority"].append(max(-2 ** 31, min(2 ** 31 - 1, t.priority)))
+            cols["expected_ns"].append(avg)
+            cols["queue_basis_ns"].append(qb)
+            cols["wait_basis_ns"].append(wb)
+            cols["num_dependents"].append(t.num_dependents)
+            cols["task_group_order"].append(t.task_group_order)
+            cols["group_id"].append(gid)
+            cols["version_id"].append(vid)
+            cols["flags"].append(fl)
+            for dep in t.depends_on:  # only dependencies that are in this queue join units (planner.go:453)
+                j = index.get(dep.task_id)
+                if j is not None:
+                    dep_idx.append(j)
+            dep_off.append(len(dep_idx))
+        task_off.append(task_off[-1] + len(tasks))
+        group_off.append(group_off[-1] + len(groups))
+        cfg_rows.append(planner_cfg_row(d, incl, len(versions)))
+        keys.append(md)
+    soa = TaskSoA(**{name: np.array(cols[name], dtype=dt) for name, dt in TaskSoA.COLUMNS},
+                  dep_off=np.array(dep_off, dtype=np.int64), dep_idx=np.array(dep_idx, dtype=np.int32)).normalize()
+    table = DistroTable(np.array(task_off, dtype=np.int64), np.array(group_off, dtype=np.int64),
+                        np.array(cfg_rows, dtype=L.DISTRO_CFG_DTYPE), np.array(gmax, dtype=np.int32)).normalize()
+    return soa, table, keys
+
+
+def provider_class(provider: str) -> int:
+    if provider == M.PROVIDER_DOCKER:
+        return L.EVG_PROVIDER_DOCKER
+    if provider in M.PROVIDER_SPAWNABLE:
+        return L.EVG_PROVIDER_EPHEMERAL
+    return L.EVG_PROVIDER_STATIC
+
+
+def alloc_cfg_row(data: M.HostAllocatorData) -> tuple:
+    d = data.distro
+    hs = d.host_allocator_settings
+    pool = data.container_pool
+    return (float(hs.future_host_fraction), provider_class(d.provider), int(d.disabled), hs.minimum_hosts,
+            hs.maximum_hosts, int(hs.rounding_rule == M.HOST_ALLOCATOR_ROUND_UP),
+            int(hs.feedback_rule == M.HOST_ALLOCATOR_WAITS_OVER_THRESH_FEEDBACK),
+            int(pool is not None), pool.max_containers if pool else 0,
+            int(data.parent_distro_maximum_hosts is not None),
+            data.parent_distro_maximum_hosts if data.parent_distro_maximum_hosts is not None else 0)
+
+
+def marshal_hosts(datas: Sequence[M.HostAllocatorData], group_names: Sequence[Sequence[str]]) -> HostSoA:
+    """[HostAllocatorData] -> HostSoA.  `group_names[d]` is the distro's group
+    table (slot order of its TaskGroupInfos); hosts are bucketed like
+    groupByTaskGroup (utilization_based_host_allocator.go:223-260)."""
+    fl, gid, exp, std, start, off, rows = [], [], [], [], [], [0], []
+    for data, names in zip(datas, group_names):
+        lookup = {n: i for i, n in enumerate(names)}
+        for h in data.existing_hosts:
+            f = 0
+            g = L.EVG_HG_NONE
+            e = s = 0
+            st = M.ZERO_TIME
+            if h.running_task != "":
+                f |= L.EVG_HF_RUNNING
+                rt = data.running_tasks.get(h.running_task)
+                if rt is not None and rt.found:
+                    f |= L.EVG_HF_RT_FOUND
+                    e, s, st = rt.expected, rt.std_dev, rt.start_time
+                if h.running_task_group != "":
+                    g = lookup.get(h.get_task_group_string(), L.EVG_HG_UNQUEUED)
+            if h.task_group_teardown_start_time != M.ZERO_TIME:
+                f |= L.EVG_HF_TEARDOWN
+            fl.append(f); gid.append(g); exp.append(e); std.append(s); start.append(st)
+        off.append(len(fl))
+        rows.append(alloc_cfg_row(data))
+    return HostSoA(np.array(fl, dtype=np.uint32), np.array(gid, dtype=np.int32), np.array(exp, dtype=np.int64),
+                   np.array(std, dtype=np.int64), np.array(start, dtype=np.int64), np.array(off, dtype=np.int64),
+                   np.array(rows, dtype=L.ALLOC_CFG_DTYPE)).normalize()
+
+
+def queue_info_rows(infos: Sequence[M.DistroQueueInfo]):
+    """[DistroQueueInfo] -> (QUEUE_INFO rows, GROUP_INFO rows, group_off, names per distro).
+    Later duplicates of a name win, like the map built at allocator.go:243-246."""
+    qrows = np.zeros(len(infos), dtype=L.QUEUE_INFO_DTYPE)
+    grows, goff, names_all = [], [0], []
+    for i, qi in enumerate(infos):
+        q = qrows[i]
+        q["length"] = qi.length
+        q["length_with_dependencies_met"] = qi.length_with_dependencies_met
+        q["count_dep_filled_merge_queue_tasks"] = qi.count_dep_filled_merge_queue_tasks
+        q["expected_duration"] = qi.expected_duration
+        q["max_duration_threshold"] = qi.max_duration_threshold
+        q["count_duration_over_threshold"] = qi.count_duration_over_threshold
+        q["duration_over_threshold"] = qi.duration_over_threshold
+        q["count_wait_over_threshold"] = qi.count_wait_over_threshold
+        q["secondary_queue"] = int(qi.secondary_queue)
+        by_name = {}
+        for g in qi.task_group_infos:
+            by_name[g.name] = g
+        names = []
+        for name, g in by_name.items():
+            row = tuple(getattr(g, f) for f in L.GROUP_INFO_FIELDS)
+            if name == "":
+                q["has_ungrouped"] = 1
+                q["ungrouped"] = row
+            else:
+                names.append(name)
+                grows.append(row)
+        goff.append(len(grows))
+        names_all.append(names)
+    return qrows, np.array(grows, dtype=L.GROUP_INFO_DTYPE).reshape(-1), np.array(goff, dtype=np.int64), names_all

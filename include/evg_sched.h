@@ -1,0 +1,305 @@
+/*
+ * evg_sched.h -- C-ABI of libevgsched.so: the B200 (sm_100a) implementation of
+ * Evergreen's scheduler hot path (scheduler.PlanDistro: tunable planner +
+ * DistroQueueInfo + utilization host allocator), batched over distros.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch/CUDA types.
+ * A Go maintainer binds it with cgo from package `scheduler` (INTEGRATION.md
+ * shows the stub); the Python mirror in evergreen_b200/ binds it with ctypes.
+ * Every entry point cites the reference interface it replaces; paths are
+ * relative to the evergreen-ci/evergreen checkout.
+ *
+ * Layout: all distros of one scheduler tick are concatenated.  Distro d owns
+ * tasks  [task_off[d],  task_off[d+1]),  hosts [host_off[d], host_off[d+1]) and
+ * task-group slots [group_off[d], group_off[d+1]).  Indices inside a distro
+ * (dep_idx, group_id, version_id, order[]) are distro-local.
+ *
+ * Determinism: `now_ns` replaces every time.Now()/time.Since on the path
+ * (planner.go:318-322, scheduler.go:123, utilization_based_host_allocator.go:360).
+ * Ties the reference leaves to map order / unstable sort are broken by the
+ * canonical policy of DESIGN.md §3 (units: TotalValue desc, smallest member
+ * index asc, smallest primary-member index asc; tasks in a unit: the
+ * TaskList.Less chain, then input index asc).
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * EVG_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef EVG_SCHED_H
+#define EVG_SCHED_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVG_ABI_VERSION 1
+
+/* Go's zero time.Time (year 1).  0 is the Unix epoch, which time.Time.IsZero
+ * reports as NON-zero; other values are ns since the Unix epoch. */
+#define EVG_TIME_ZERO INT64_MIN
+
+/* library status codes (negative = failure; message via evg_last_error()) */
+enum {
+  EVG_OK = 0,
+  EVG_ERR_INVALID = -1, /* bad argument / inconsistent offsets */
+  EVG_ERR_CUDA = -2,    /* no usable sm_100 device, or a CUDA call failed */
+  EVG_ERR_NOMEM = -3,   /* device or pinned allocation failed */
+  EVG_ERR_STATE = -4    /* resident call without a prior evg_upload */
+};
+
+/* per-distro allocator status: the data errors UtilizationBasedHostAllocator
+ * returns as `error` (utilization_based_host_allocator.go:151-160,200-202,302-304) */
+enum {
+  EVG_ALLOC_OK = 0,
+  EVG_ALLOC_ERR_FUTURE_FRACTION = 1, /* "future host factor cannot be greater than 1" */
+  EVG_ALLOC_ERR_POOL_SIZE = 2,       /* "unable to plan hosts ... due to pool size" (maxHosts < 1) */
+  EVG_ALLOC_ERR_PARENT_MISSING = 3   /* container pool parent distro not found */
+};
+
+/* evg_task_soa.flags */
+#define EVG_TF_REQ_MASK 0x3u       /* requester class */
+#define EVG_TF_REQ_OTHER 0u        /*   anything else -> mainline branch (planner.go:234) */
+#define EVG_TF_REQ_PATCH 1u        /*   IsPatchRequester && !merge queue (globals.go:1179) */
+#define EVG_TF_REQ_MERGE_QUEUE 2u  /*   IsGithubMergeQueueRequester (globals.go:1195) */
+#define EVG_TF_GENERATE 0x4u       /* Task.GenerateTask */
+#define EVG_TF_STEPBACK 0x8u       /* Task.ActivatedBy == "stepback" (globals.go:219) */
+#define EVG_TF_DEPS_MET 0x10u      /* Task.DependenciesMet(...) (model/task/task.go:632) */
+#define EVG_TF_OTHER_DISTRO 0x20u  /* Task.DistroId != distro id (scheduler.go:75) */
+
+/* Task records, SoA (replaces []task.Task, model/task/task.go:83-350; the
+ * fields are those SURVEY.md §8a row A20 lists).  48 B per task. */
+typedef struct {
+  int64_t n_tasks;
+  int64_t n_edges;
+  const int32_t* priority;         /* Task.Priority (int64 in Go; the shim saturates to int32) */
+  const int64_t* expected_ns;      /* Task.FetchExpectedDuration(ctx).Average (task.go:3519) */
+  const int64_t* queue_basis_ns;   /* ActivatedTime if !IsZero, else IngestTime if !IsZero, else EVG_TIME_ZERO (planner.go:318-322) */
+  const int64_t* wait_basis_ns;    /* later of ScheduledTime, DependenciesMetTime (scheduler.go:119-122); EVG_TIME_ZERO if both zero */
+  const int32_t* num_dependents;   /* Task.NumDependents */
+  const int32_t* task_group_order; /* Task.TaskGroupOrder */
+  const int32_t* group_id;         /* distro-local dense id of Task.GetTaskGroupString() (task.go:417); -1 when TaskGroup == "" */
+  const int32_t* version_id;       /* distro-local dense id of Task.Version */
+  const uint32_t* flags;           /* EVG_TF_* */
+  /* Task.DependsOn restricted to dependencies that are themselves in this
+   * distro's queue (planner.go:449-456), CSR over tasks; NULL when n_edges==0 */
+  const int64_t* dep_off;          /* n_tasks + 1 */
+  const int32_t* dep_idx;          /* distro-local index of the dependency */
+} evg_task_soa;
+
+/* distro.PlannerSettings (model/distro/distro.go:286-300), raw: the <=0 -> 1
+ * clamp of the factor getters (distro.go:353-408) happens on the device. */
+typedef struct {
+  int64_t patch_factor;
+  int64_t patch_time_in_queue_factor;
+  int64_t commit_queue_factor;
+  int64_t mainline_time_in_queue_factor;
+  int64_t expected_runtime_factor;
+  int64_t generate_task_factor;
+  int64_t stepback_task_factor;
+  double num_dependents_factor;
+  int64_t target_time_ns;        /* d.GetTargetTime() (distro.go:434-440), resolved by the shim */
+  int32_t group_versions;        /* PlannerSettings.ShouldGroupVersions() */
+  int32_t includes_dependencies; /* DispatcherSettings.Version == "revised-with-dependencies" (scheduler.go:28) */
+  int32_t n_versions;            /* number of distinct version ids in this distro */
+  int32_t _reserved;
+} evg_distro_cfg;
+
+typedef struct {
+  int32_t n_distros;
+  int32_t _reserved;
+  const int64_t* task_off;        /* n_distros + 1 */
+  const int64_t* group_off;       /* n_distros + 1 */
+  const evg_distro_cfg* cfg;      /* n_distros */
+  const int32_t* group_max_hosts; /* per group slot: Task.TaskGroupMaxHosts of the group (scheduler.go:87-90) */
+} evg_distro_table;
+
+/* model.TaskGroupInfo without the name (model/task_queue.go:22-47); the name
+ * of slot group_off[d]+g is the shim's string for group id g. 72 B. */
+typedef struct {
+  int64_t count;
+  int64_t count_free;      /* written by the allocator (allocator.go:107-110) */
+  int64_t count_required;  /* written by the allocator */
+  int64_t max_hosts;
+  int64_t expected_duration;
+  int64_t count_duration_over_threshold;
+  int64_t count_wait_over_threshold;
+  int64_t count_dep_filled_merge_queue_tasks;
+  int64_t duration_over_threshold;
+} evg_group_info;
+
+/* model.DistroQueueInfo (model/task_queue.go:49-75).  `ungrouped` is the
+ * TaskGroupInfo named "" (standalone tasks); it exists in TaskGroupInfos only
+ * when has_ungrouped != 0. */
+typedef struct {
+  int64_t length;
+  int64_t length_with_dependencies_met;
+  int64_t count_dep_filled_merge_queue_tasks;
+  int64_t expected_duration;
+  int64_t max_duration_threshold;
+  int64_t count_duration_over_threshold;
+  int64_t duration_over_threshold;
+  int64_t count_wait_over_threshold;
+  int64_t secondary_queue; /* any task.DistroId != distro (scheduler.go:75-77); callers overwrite it (scheduler.go:44) */
+  int64_t has_ungrouped;
+  evg_group_info ungrouped;
+} evg_queue_info;
+
+/* task.SortingValueBreakdown flattened to 13 int64 (model/task/task.go:3990-4038) */
+enum {
+  EVG_BD_TASK_GROUP_LENGTH = 0, EVG_BD_TOTAL_VALUE,
+  EVG_BD_P_INITIAL, EVG_BD_P_TASK_GROUP, EVG_BD_P_GENERATOR, EVG_BD_P_COMMIT_QUEUE,
+  EVG_BD_R_COMMIT_QUEUE, EVG_BD_R_NUM_DEPENDENTS, EVG_BD_R_ESTIMATED_RUNTIME,
+  EVG_BD_R_MAINLINE_WAIT, EVG_BD_R_STEPBACK, EVG_BD_R_PATCH, EVG_BD_R_PATCH_WAIT,
+  EVG_BD_N
+};
+
+/* Planner outputs (replaces the []task.Task PrioritizeTasks returns,
+ * scheduler.go:27, and the DistroQueueInfo of scheduler.go:43). */
+typedef struct {
+  int32_t* order;             /* [n_tasks] slot task_off[d]+r = distro-local index of the task ranked r (TaskPlan.Export, planner.go:462-481) */
+  int64_t* total_value;       /* [n_tasks] SortingValueBreakdown.TotalValue of the unit the task was emitted from, rank order */
+  int64_t* breakdown;         /* [n_tasks * EVG_BD_N] full breakdown in rank order, or NULL */
+  evg_queue_info* info;       /* [n_distros] */
+  evg_group_info* group_info; /* [group_off[n_distros]] */
+} evg_plan_out;
+
+/* evg_host_soa.flags */
+#define EVG_HF_RUNNING 0x1u    /* Host.RunningTask != "" */
+#define EVG_HF_TEARDOWN 0x2u   /* !Host.TaskGroupTeardownStartTime.IsZero() (host.go:219-221) */
+#define EVG_HF_RT_FOUND 0x4u   /* the running task was returned by task.Find(ByIds) (allocator.go:337) */
+
+/* host bucket codes for evg_host_soa.group_id (groupByTaskGroup, allocator.go:223-260) */
+#define EVG_HG_NONE (-1)       /* name "" : no running task or no running task group */
+#define EVG_HG_UNQUEUED (-2)   /* a named group with no TaskGroupInfo in the queue */
+
+/* Existing hosts, SoA (replaces HostAllocatorData.ExistingHosts []host.Host,
+ * host_allocator.go:17-23, model/host/host.go:79-88).  32 B per host. */
+typedef struct {
+  int64_t n_hosts;
+  const uint32_t* flags;      /* EVG_HF_* */
+  const int32_t* group_id;    /* EVG_HG_* or the distro-local task-group id of Host.GetTaskGroupString() (host.go:663) */
+  const int64_t* expected_ns; /* running task FetchExpectedDuration().Average (allocator.go:357-358) */
+  const int64_t* std_ns;      /* ... .StdDev (allocator.go:359) */
+  const int64_t* start_ns;    /* running task StartTime (allocator.go:360), EVG_TIME_ZERO if unset */
+} evg_host_soa;
+
+enum { EVG_PROVIDER_STATIC = 0, /* not in evergreen.ProviderSpawnable (globals.go:723-728) */
+       EVG_PROVIDER_EPHEMERAL = 1, /* ec2-ondemand, ec2-fleet, mock */
+       EVG_PROVIDER_DOCKER = 2 };
+
+/* distro.HostAllocatorSettings + the rest of HostAllocatorData that is not
+ * hosts or queue info (model/distro/distro.go:267-280, host_allocator.go:17-23) */
+typedef struct {
+  double future_host_fraction;
+  int32_t provider;                   /* EVG_PROVIDER_* */
+  int32_t disabled;                   /* Distro.Disabled */
+  int32_t minimum_hosts;
+  int32_t maximum_hosts;
+  int32_t round_up;                   /* RoundingRule == "round-up" (allocator.go:174-177) */
+  int32_t waits_over_thresh_feedback; /* FeedbackRule == "waits-over-thresh-feedback" (allocator.go:179-182) */
+  int32_t has_pool;                   /* HostAllocatorData.ContainerPool != nil */
+  int32_t pool_max_containers;        /* ContainerPool.MaxContainers */
+  int32_t parent_found;               /* distro.FindOneId(pool.Distro) succeeded (allocator.go:151-158) */
+  int32_t parent_maximum_hosts;       /* parent HostAllocatorSettings.MaximumHosts (allocator.go:159) */
+} evg_alloc_cfg;
+
+/* Allocator outputs (replaces the (int, int, error) of HostAllocator,
+ * host_allocator.go:15).  `result` is the same data packed for the
+ * multi-GPU all-gather: 16 B per distro. */
+typedef struct {
+  int32_t new_hosts;   /* numNewHostsToRequest */
+  int32_t free_hosts;  /* numFreeApprox (or len(freeHosts) on the early returns) */
+  int64_t deficit_ns;  /* auxiliary: max(0, expected_duration - free_hosts*threshold), host-time the free pool cannot absorb */
+} evg_alloc_result;
+
+typedef struct {
+  evg_alloc_result* result; /* [n_distros] */
+  int32_t* status;          /* [n_distros] EVG_ALLOC_* */
+} evg_alloc_out;
+
+/* option bits */
+#define EVG_OPT_BREAKDOWN 0x1u /* materialise evg_plan_out.breakdown */
+
+typedef struct evg_ctx evg_ctx;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+/* Bind a context to CUDA device `device`.  `stream` is a cudaStream_t the
+ * kernels are launched on (e.g. the caller's torch stream) or NULL for a
+ * private stream.  Replaces nothing in the reference (process bootstrap). */
+int evg_init(int device, void* stream, evg_ctx** out);
+void evg_shutdown(evg_ctx* ctx);
+/* thread-local message for the last failing call on this thread */
+const char* evg_last_error(void);
+int evg_abi_version(void);
+
+/* Pinned host buffers for the SoA columns (the Go shim fills C-allocated
+ * memory so no Go pointer is retained across the call). */
+void* evg_host_alloc(uint64_t bytes);
+void evg_host_free(void* p);
+
+/* ---- one-shot batch entry points: HOST pointers, H2D + kernels + D2H ---- */
+
+/* Tunable planner + queue info for every distro of the tick.
+ * Replaces: scheduler.PrioritizeTasks / runTunablePlanner minus persistence
+ * (scheduler/scheduler.go:27-51): PrepareTasksForPlanning(...).Export
+ * (planner.go:431-481) and GetDistroQueueInfo (scheduler.go:56-159). */
+int evg_plan_batch(evg_ctx* ctx, const evg_task_soa* tasks, const evg_distro_table* distros,
+                   int64_t now_ns, uint32_t opts, evg_plan_out* out);
+
+/* Utilization host allocator for every distro, from queue infos the caller
+ * already has (the reference reads them back from MongoDB,
+ * units/host_allocator.go:152).  `groups` is in/out: count_free and
+ * count_required are written like the reference mutates TaskGroupInfos.
+ * Replaces: scheduler.UtilizationBasedHostAllocator
+ * (scheduler/utilization_based_host_allocator.go:26-130) behind the
+ * HostAllocator plug point (scheduler/host_allocator.go:15,25-32). */
+int evg_alloc_batch(evg_ctx* ctx, const evg_host_soa* hosts, const int64_t* host_off,
+                    const evg_alloc_cfg* cfg, const evg_queue_info* info, evg_group_info* groups,
+                    const int64_t* group_off, int32_t n_distros, int64_t now_ns, evg_alloc_out* out);
+
+/* Fused planner + allocator: the queue info never leaves the device.
+ * Replaces: distroSchedulerJob.Run + hostAllocatorJob.Run for all distros of
+ * one tick (units/scheduler.go:57-87, units/host_allocator.go:76-196). */
+int evg_plan_and_alloc_batch(evg_ctx* ctx, const evg_task_soa* tasks, const evg_distro_table* distros,
+                             const evg_host_soa* hosts, const int64_t* host_off,
+                             const evg_alloc_cfg* acfg, int64_t now_ns, uint32_t opts,
+                             evg_plan_out* plan_out, evg_alloc_out* alloc_out);
+
+/* ---- resident API: inputs stay in HBM between ticks --------------------- */
+
+/* Copy a tick's inputs into context-owned device buffers (hosts/host_off/acfg
+ * may be NULL for planner-only use). */
+int evg_upload(evg_ctx* ctx, const evg_task_soa* tasks, const evg_distro_table* distros,
+               const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg);
+/* Launch the fused path on the resident inputs; asynchronous on the context
+ * stream.  Safe to call repeatedly (each call recomputes from the inputs). */
+int evg_run_resident(evg_ctx* ctx, int64_t now_ns, uint32_t opts);
+/* Wait for the stream and copy results out; either pointer may be NULL. */
+int evg_download(evg_ctx* ctx, evg_plan_out* plan_out, evg_alloc_out* alloc_out);
+/* Device pointer to the resident evg_alloc_result[n_distros] vector, the
+ * send buffer of the per-distro all-gather. */
+void* evg_device_result_ptr(evg_ctx* ctx);
+/* Number of kernel launches issued by the last evg_run_resident. */
+int64_t evg_last_launch_count(evg_ctx* ctx);
+/* Device time of the planner's dominant kernel (segmented sort) and of the
+ * whole resident run in ms, measured with CUDA events on the context stream
+ * during the last evg_run_resident (valid after a sync / download). */
+int evg_last_timing_ms(evg_ctx* ctx, float* total_ms, float* sort_ms);
+
+/* ---- single-distro wrappers: the per-job drop-in ------------------------- */
+
+/* One distro: PrioritizeTasks for `d` (scheduler/scheduler.go:27). */
+int evg_plan_distro(evg_ctx* ctx, const evg_task_soa* tasks, const evg_distro_cfg* cfg,
+                    int32_t n_groups, const int32_t* group_max_hosts, int64_t now_ns, uint32_t opts,
+                    evg_plan_out* out);
+/* One distro: UtilizationBasedHostAllocator(ctx, &HostAllocatorData{...})
+ * (scheduler/utilization_based_host_allocator.go:26). */
+int evg_alloc_distro(evg_ctx* ctx, const evg_host_soa* hosts, const evg_alloc_cfg* cfg,
+                     const evg_queue_info* info, evg_group_info* groups, int32_t n_groups,
+                     int64_t now_ns, evg_alloc_result* result, int32_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVG_SCHED_H */
