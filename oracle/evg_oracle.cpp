@@ -652,7 +652,8 @@ void evo_fetch_expected_duration(int64_t pred_value, int64_t pred_std, int64_t p
 void evo_job_batch(const evo_tasks* t, const int64_t* task_off, const evo_hosts* h, const int64_t* host_off,
                    const evo_planner_settings* ps, const evo_alloc_settings* as, const char* const* distro_ids,
                    int64_t n_distros, int64_t now, int32_t n_threads, int32_t* out_order, int64_t* out_total_value,
-                   evo_queue_info* out_info, int64_t* out_new, int64_t* out_free, int32_t* out_status) {
+                   evo_queue_info* out_info, int64_t* out_new, int64_t* out_free, int32_t* out_status,
+                   evo_group_info* out_groups) {
   std::atomic<int64_t> next{0};
   auto worker = [&]() {
     for (;;) {
@@ -671,6 +672,8 @@ void evo_job_batch(const evo_tasks* t, const int64_t* task_off, const evo_hosts*
         HView hv{h, host_off[d], host_off[d + 1] - host_off[d]};
         out_status[d] = allocate(hv, as[d], q.info, q.groups.data(), q.names, now, &out_new[d], &out_free[d]);
       }
+      if (out_groups)  // distro d's groups start at slot task_off[d] + d (at most n_tasks + 1 of them)
+        for (size_t g = 0; g < q.groups.size(); g++) out_groups[task_off[d] + d + int64_t(g)] = q.groups[g];
     }
   };
   if (n_threads <= 1) { worker(); return; }

@@ -192,12 +192,14 @@ void evo_fetch_expected_duration(int64_t pred_value, int64_t pred_std, int64_t p
  * Distro d owns tasks [task_off[d], task_off[d+1]) and hosts [host_off[d], ..).
  * Runs plan -> queue info -> allocator per distro. Outputs: out_order (global
  * task slots, distro-local indices), out_total_value (per rank), out_info[d],
- * out_new/out_free/out_status[d]. Group infos are discarded. */
+ * out_new/out_free/out_status[d], and (optionally) the TaskGroupInfos after the
+ * allocator mutated them. */
 void evo_job_batch(const evo_tasks* t, const int64_t* task_off, const evo_hosts* h,
                    const int64_t* host_off, const evo_planner_settings* ps,
                    const evo_alloc_settings* as, const char* const* distro_ids, int64_t n_distros,
                    int64_t now, int32_t n_threads, int32_t* out_order, int64_t* out_total_value,
-                   evo_queue_info* out_info, int64_t* out_new, int64_t* out_free, int32_t* out_status);
+                   evo_queue_info* out_info, int64_t* out_new, int64_t* out_free, int32_t* out_status,
+                   evo_group_info* out_groups /* may be NULL; distro d's infos at slot task_off[d]+d.. */);
 
 #ifdef __cplusplus
 }

@@ -497,12 +497,23 @@ class SoAJob:
         free = np.zeros(max(D, 1), dtype=np.int64)
         st = np.zeros(max(D, 1), dtype=np.int32)
         have_hosts = self.hosts is not None
+        groups = np.zeros(n + D + 1, dtype=GROUP_DTYPE)
         lib().evo_job_batch(C.byref(self.tasks), C.c_void_p(self.task_off.ctypes.data),
                             C.byref(self.hosts) if have_hosts else None,
                             C.c_void_p(self.host_off.ctypes.data) if have_hosts else None,
                             self.ps, self.alloc if have_hosts else None, self.distro_ids, C.c_int64(D), C.c_int64(now),
                             C.c_int32(threads), C.c_void_p(order.ctypes.data), C.c_void_p(tv.ctypes.data),
                             C.c_void_p(info.ctypes.data), C.c_void_p(new.ctypes.data), C.c_void_p(free.ctypes.data),
-                            C.c_void_p(st.ctypes.data))
+                            C.c_void_p(st.ctypes.data), C.c_void_p(groups.ctypes.data))
         return {"order": order[:n], "total_value": tv[:n], "info": info[:D], "new_hosts": new[:D],
-                "free_hosts": free[:D], "status": st[:D], "task_off": self.task_off}
+                "free_hosts": free[:D], "status": st[:D], "task_off": self.task_off, "groups": groups}
+
+    def groups_by_id(self, result, j: int, soa_group_id: np.ndarray):
+        """TaskGroupInfos of selected distro j keyed by the SoA group id (-1 = the "" bucket)."""
+        a = int(self.task_off[j])
+        out = {}
+        for g in range(int(result["info"][j]["n_groups"])):
+            row = result["groups"][a + j + g]
+            nt = int(row["name_task"])
+            out[-1 if nt < 0 else int(soa_group_id[a + nt])] = row
+        return out

@@ -1,0 +1,271 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle: the committed
+golden vectors, seeded synthetic ticks in every BASELINE shape, edge cases, and
+size-independent properties at full size.  Integer / index work: bit-exact."""
+import copy
+
+import numpy as np
+import pytest
+
+import golden_loader as G
+import parity
+from evergreen_b200 import _lib as L
+from evergreen_b200 import model as M
+from evergreen_b200 import scheduler as S
+from evergreen_b200 import soa, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KATS = G.load("planner_kats.json")
+ALLOC = G.load("allocator_scenarios.json")
+NOW, EL = KATS["now"], KATS["elapsed_ns"]
+
+
+def run(engine, w, breakdown=False):
+    if w.hosts is not None:
+        return engine.plan_and_alloc_batch(w.tasks, w.distros, w.hosts, w.now, breakdown=breakdown)
+    return engine.plan_batch(w.tasks, w.distros, w.now, breakdown=breakdown), None
+
+
+# ---------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("case", KATS["unit_values"], ids=lambda c: c["name"])
+def test_unit_value_kats(engine, case):
+    """planner_test.go:199-406 through the product: the tasks of each unit are
+    queued so that they form exactly that unit (one version under GroupVersions,
+    or their task group), and the stamped breakdown is compared."""
+    case = dict(case)
+    tasks = [G.make_task(t, NOW, EL) for t in case["tasks"]]
+    if len(tasks) > 1 and not tasks[0].task_group:
+        case["group_versions"] = True
+        for t in tasks:
+            t.version = "v"
+    d = G.make_distro(case)
+    plan, _ = S.PrioritizeTasks(d, tasks, now=NOW, engine=engine)
+    b = plan[0].sorting_value_breakdown
+    want = O.unit_value(d, tasks, NOW)
+    assert b.row() == want.row()
+    if "total" in case:
+        assert b.total_value == case["total"], case["ref"]
+    for f, v in case.get("fields", {}).items():
+        assert getattr(b, f) == v
+
+
+@pytest.mark.parametrize("case", KATS["plans"] + [dict(c, group_versions=True, _one_version=True) for c in KATS["task_lists"]],
+                         ids=lambda c: c["name"])
+def test_plan_kats(engine, case):
+    tasks = [G.make_task(t, NOW, EL) for t in case["tasks"]]
+    if case.get("_one_version"):
+        for t in tasks:
+            t.version = "v"
+    d = G.make_distro(case)
+    opts = S.TaskPlannerOptions(is_secondary_queue=bool(case.get("secondary_queue")))
+    plan, info = S.PrioritizeTasks(d, tasks, opts, now=NOW, engine=engine)
+    ids = [t.id for t in plan]
+    order, bd, _ = O.plan(d, tasks, NOW)
+    assert ids == [tasks[i].id for i in order]
+    assert [t.sorting_value_breakdown.row() for t in plan] == bd.tolist()
+    if "order" in case:
+        assert ids == case["order"], case["ref"]
+    if "n_out" in case:
+        assert len(ids) == case["n_out"]
+    if "last" in case:
+        assert ids[-1] == case["last"]
+    if "head_set" in case:
+        assert set(ids[:len(case["head_set"])]) == set(case["head_set"])
+    if "head_task_groups" in case:
+        assert [t.task_group for t in plan[:2]] == case["head_task_groups"]
+    for a, b in case.get("before", []):
+        assert ids.index(a) < ids.index(b)
+    assert info.secondary_queue == bool(case.get("secondary_queue"))
+
+
+@pytest.mark.parametrize("case", KATS["queue_infos"], ids=lambda c: c["name"])
+def test_queue_info_kats(engine, case):
+    tasks = [G.make_task(t, NOW, EL) for t in case["tasks"]]
+    info = S.GetDistroQueueInfo(M.Distro(id=case["distro_id"]), tasks, case["threshold"], now=NOW, engine=engine)
+    assert (info.length, info.length_with_dependencies_met) == (case["length"], case["length_with_dependencies_met"])
+    assert info.expected_duration == sum(case["expected_durations"])
+    want = O.queue_info(case["distro_id"], [G.make_task(t, NOW, EL) for t in case["tasks"]], case["threshold"], False, NOW)
+    key = lambda g: g.name
+    assert sorted(info.task_group_infos, key=key) == sorted(want.task_group_infos, key=key)
+
+
+@pytest.mark.parametrize("s", ALLOC["scenarios"], ids=lambda s: s["test"])
+def test_allocator_scenarios(engine, s):
+    data = G.go_allocator_data(s, M.fetch_expected_duration)
+    odata = G.go_allocator_data(s, O.fetch_expected_duration)
+    n, f = S.UtilizationBasedHostAllocator(data, now=s["now"], engine=engine)
+    assert (n, f) == (s["expect_new_hosts"], s["expect_free_hosts"]), s["ref"]
+    O.allocate(odata, s["now"])
+    assert data.distro_queue_info.task_group_infos == odata.distro_queue_info.task_group_infos
+
+
+@pytest.mark.parametrize("v", [v for v in ALLOC["vectors"] if v["fn"] == "calcNewHostsNeeded"],
+                         ids=lambda v: "-".join(str(a) for a in v["args"]))
+def test_calc_new_hosts_needed(engine, v):
+    """utilization_based_host_allocator_test.go:160-170 reached through the allocator:
+    one "" bucket whose numbers are exactly the vector's arguments."""
+    short, thr, exp_free, n_long, overdue, mq, round_down = v["args"]
+    g = M.TaskGroupInfo("", count=10 ** 6, expected_duration=short, count_duration_over_threshold=n_long,
+                        count_wait_over_threshold=overdue, count_dep_filled_merge_queue_tasks=mq)
+    qi = M.DistroQueueInfo(length=10 ** 6, length_with_dependencies_met=10 ** 6, expected_duration=short,
+                           max_duration_threshold=thr, task_group_infos=[g])
+    d = M.Distro(id="d", provider=M.PROVIDER_EC2_FLEET, host_allocator_settings=M.HostAllocatorSettings(
+        maximum_hosts=10 ** 6, future_host_fraction=0.5,
+        rounding_rule=M.HOST_ALLOCATOR_ROUND_DOWN if round_down else M.HOST_ALLOCATOR_ROUND_UP,
+        feedback_rule=M.HOST_ALLOCATOR_WAITS_OVER_THRESH_FEEDBACK))
+    hosts = [M.Host(id=f"h{i}") for i in range(exp_free)]
+    n, f = S.UtilizationBasedHostAllocator(M.HostAllocatorData(d, hosts, qi), now=NOW, engine=engine)
+    assert (n, f) == (v["expect"], exp_free), v["ref"]
+
+
+def test_allocator_data_errors(engine):
+    s = next(x for x in ALLOC["scenarios"] if x["test"] == "TestNoExistingHosts")
+    for mutate, code in ((lambda d: setattr(d.distro.host_allocator_settings, "future_host_fraction", 1.5), 1),
+                         (lambda d: (setattr(d.distro, "provider", M.PROVIDER_DOCKER),
+                                     setattr(d.distro.host_allocator_settings, "maximum_hosts", 0)), 2),
+                         (lambda d: setattr(d, "container_pool", M.ContainerPool("p", "nowhere", 10)), 3)):
+        d = G.go_allocator_data(s, M.fetch_expected_duration)
+        mutate(d)
+        with pytest.raises(S.AllocatorError) as e:
+            S.UtilizationBasedHostAllocator(d, now=s["now"], engine=engine)
+        assert e.value.status == code
+        assert O.allocate(copy.deepcopy(d), s["now"])[2] == code
+
+
+# ---------------------------------------------------------------- synthetic ticks vs oracle
+@pytest.mark.parametrize("k,scale", [(1, 1), (2, 0.004), (3, 0.05), (4, 0.03), (5, 0.02)])
+def test_config_parity(engine, k, scale):
+    w = synth.config(k, scale)
+    po, ao = run(engine, w)
+    parity.check_against_oracle(w, po, ao)
+    parity.check_properties(w, po, ao)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_mixed_parity(engine, seed):
+    """Everything at once: task groups, GroupVersions on half the distros, met and unmet
+    in-queue dependencies, custom factors, ragged sizes incl. empty and single-task distros."""
+    rng = synth.Rng(1000 + seed)
+    sizes = np.concatenate([[0, 1, 2, 0, 3], rng.integers(40, 1, 400), [2049, 4097, 0]])
+    w = synth.make(sizes, 7000 + seed, zipf_priority=True, unmet_dep_frac=0.06, met_dep_frac=0.04, tg_frac=0.2,
+                   group_versions_frac=0.5, custom_factor_frac=0.5, includes_dependencies=bool(seed & 1),
+                   n_hosts=300, providers=(0.6, 0.2, 0.2))
+    po, ao = run(engine, w)
+    parity.check_against_oracle(w, po, ao)
+    parity.check_properties(w, po, ao)
+
+
+def test_breakdown_parity(engine):
+    w = synth.make(np.array([300, 7, 1, 900]), 99, zipf_priority=True, unmet_dep_frac=0.05, met_dep_frac=0.05,
+                   tg_frac=0.3, group_versions_frac=0.5, custom_factor_frac=1.0)
+    po, _ = run(engine, w, breakdown=True)
+    assert np.array_equal(po.breakdown[:, L.EVG_BD_TOTAL_VALUE], po.total_value)
+    b = po.breakdown
+    prio = b[:, 2] + b[:, 3] + b[:, 4] + b[:, 5]
+    rank = b[:, 6:].sum(axis=1)
+    assert np.array_equal(prio + b[:, 0] + rank * prio, b[:, 1])  # verifyRankBreakdown planner_test.go:563-576
+    parity.check_against_oracle(w, po, None)
+
+
+def test_large_distros_multi_tile(engine):
+    """Distros far larger than one sort tile, with heavy TotalValue ties."""
+    w = synth.make(np.array([70_000, 5, 33_000]), 5, tg_frac=0.1, unmet_dep_frac=0.02, includes_dependencies=True,
+                   n_hosts=50)
+    po, ao = run(engine, w)
+    parity.check_against_oracle(w, po, ao)
+
+
+def test_group_versions_big_units(engine):
+    """GroupVersions with ~50-task version units and task groups nested in them."""
+    w = synth.make(np.full(6, 1500), 11, tg_frac=0.15, group_versions_frac=1.0, met_dep_frac=0.03, unmet_dep_frac=0.03)
+    po, _ = run(engine, w)
+    parity.check_against_oracle(w, po, None)
+
+
+def test_dependency_fan(engine):
+    """One task everyone depends on (fan-in) and one task depending on everyone (fan-out)."""
+    n = 400
+    w = synth.make(np.array([n]), 3, tg_frac=0.0)
+    t = w.tasks
+    dep_off = np.zeros(n + 1, dtype=np.int64)
+    idx = []
+    for i in range(n):
+        if i == 7:
+            idx += [j for j in range(n) if j != 7]      # fan-out: task 7 depends on all
+        elif i % 3 == 0:
+            idx += [5]                                   # fan-in: a third of the tasks depend on 5
+        dep_off[i + 1] = len(idx)
+    t.dep_off, t.dep_idx = dep_off, np.array(idx, dtype=np.int32)
+    t.flags = t.flags | np.uint32(L.EVG_TF_DEPS_MET)
+    t.normalize()
+    po, _ = run(engine, w)
+    parity.check_against_oracle(w, po, None)
+
+
+def test_edge_inputs(engine):
+    # no distros at all
+    w = synth.make(np.zeros(0, dtype=np.int64), 1)
+    po, _ = run(engine, w)
+    assert po.order.shape == (0,) and po.info.shape == (0,)
+    # only empty distros
+    w = synth.make(np.zeros(3, dtype=np.int64), 1, n_hosts=0)
+    po, _ = run(engine, w)
+    assert np.all(po.info["length"] == 0) and np.all(po.info["has_ungrouped"] == 0)
+    # all keys equal: order must be the input order
+    w = synth.make(np.array([3000]), 2, tg_frac=0.0)
+    for col in ("expected_ns", "queue_basis_ns", "wait_basis_ns"):
+        getattr(w.tasks, col)[:] = getattr(w.tasks, col)[0]
+    w.tasks.num_dependents[:] = 0
+    w.tasks.flags[:] = L.EVG_TF_DEPS_MET
+    po, _ = run(engine, w)
+    assert np.array_equal(po.order, np.arange(3000))
+    # negative priority (disabled tasks are -1): MaxPriority floors at 0 (planner.go:325-327)
+    w = synth.make(np.array([50]), 4)
+    w.tasks.priority[:] = -1
+    po, _ = run(engine, w)
+    parity.check_against_oracle(w, po, None)
+    # Go-zero and Unix-epoch times
+    w = synth.make(np.array([64]), 6)
+    w.tasks.queue_basis_ns[::2] = M.ZERO_TIME
+    w.tasks.queue_basis_ns[1::4] = 0
+    w.tasks.wait_basis_ns[::3] = M.ZERO_TIME
+    po, _ = run(engine, w)
+    parity.check_against_oracle(w, po, None)
+
+
+def test_bad_arguments_are_errors(engine):
+    w = synth.make(np.array([10]), 1)
+    bad = copy.deepcopy(w)
+    bad.distros.task_off[-1] = 11
+    with pytest.raises(L.EvgError) as e:
+        engine.plan_batch(bad.tasks, bad.distros, w.now)
+    assert e.value.code == L.EVG_ERR_INVALID
+    big = soa.DistroTable(np.array([0, L.MAX_TASKS_PER_DISTRO + 1]), np.array([0, 0]),
+                          np.zeros(1, L.DISTRO_CFG_DTYPE), np.zeros(0, np.int32)).normalize()
+    t = w.tasks
+    with pytest.raises(L.EvgError):
+        engine.plan_batch(t, big, w.now)
+
+
+def test_resident_rerun_is_idempotent(engine):
+    w = synth.config(3, 0.02)
+    engine.upload(w.tasks, w.distros, w.hosts)
+    engine.run(w.now)
+    a_po, a_ao = engine.download()
+    engine.run(w.now)
+    engine.run(w.now)
+    b_po, b_ao = engine.download()
+    assert np.array_equal(a_po.order, b_po.order) and np.array_equal(a_po.info, b_po.info)
+    assert np.array_equal(a_ao.result, b_ao.result)
+    assert engine.last_launch_count() > 0
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_c2_full_size_properties(engine):
+    """BASELINE configs[1] at full size: 1000 distros x 10k tasks (1e7 tasks).  The oracle checks a
+    sample of distros bit-exactly; the rest is covered by the size-independent invariants."""
+    w = synth.config(2, 1.0)
+    po, ao = run(engine, w)
+    parity.check_properties(w, po, ao)
+    parity.check_against_oracle(w, po, ao, distros=[0, 1, 499, 998, 999])
