@@ -27,6 +27,9 @@ EVG_HG_NONE, EVG_HG_UNQUEUED = -1, -2
 EVG_PROVIDER_STATIC, EVG_PROVIDER_EPHEMERAL, EVG_PROVIDER_DOCKER = 0, 1, 2
 EVG_OPT_BREAKDOWN = 0x1
 EVG_BD_N = 13
+(EVG_BD_TASK_GROUP_LENGTH, EVG_BD_TOTAL_VALUE, EVG_BD_P_INITIAL, EVG_BD_P_TASK_GROUP, EVG_BD_P_GENERATOR,
+ EVG_BD_P_COMMIT_QUEUE, EVG_BD_R_COMMIT_QUEUE, EVG_BD_R_NUM_DEPENDENTS, EVG_BD_R_ESTIMATED_RUNTIME,
+ EVG_BD_R_MAINLINE_WAIT, EVG_BD_R_STEPBACK, EVG_BD_R_PATCH, EVG_BD_R_PATCH_WAIT) = range(13)
 MAX_TASKS_PER_DISTRO = (1 << 21) - 1
 
 # numpy mirrors of the POD structs (all naturally aligned, no padding)
@@ -103,6 +106,7 @@ SYMBOLS = {
     "evg_run_resident": (C.c_int, [_P, C.c_int64, C.c_uint32]),
     "evg_download": (C.c_int, [_P, _P, _P]),
     "evg_device_result_ptr": (_P, [_P]),
+    "evg_bind_result_buffer": (C.c_int, [_P, _P, C.c_int64]),
     "evg_last_launch_count": (C.c_int64, [_P]),
     "evg_last_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "evg_plan_distro": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, C.c_uint32, _P]),

@@ -775,6 +775,9 @@ struct evg_ctx {
   DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
   DevBuf b_hflags, b_hgid, b_hexp, b_hstd, b_hstart, b_hostoff, b_acfg, b_gs, b_result, b_status;
   bool bd_valid = false;
+  evg_alloc_result* ext_result = nullptr;  // caller-owned send buffer (evg_bind_result_buffer)
+  int64_t ext_capacity = 0;
+  evg_alloc_result* result_ptr() const { return ext_result ? ext_result : b_result.as<evg_alloc_result>(); }
 };
 
 namespace {
@@ -952,11 +955,11 @@ int run_alloc(evg_ctx* c, int64_t now) {
   h.n = c->H; h.flags = c->b_hflags.as<uint32_t>(); h.gid = c->b_hgid.as<int32_t>();
   h.expected = c->b_hexp.as<int64_t>(); h.stddev = c->b_hstd.as<int64_t>(); h.start = c->b_hstart.as<int64_t>();
   h.host_off = c->b_hostoff.as<int64_t>(); h.cfg = c->b_acfg.as<evg_alloc_cfg>();
+  if (c->ext_result && c->ext_capacity < c->Dn) return fail(EVG_ERR_INVALID, "bound result buffer holds %lld rows, need %d", (long long)c->ext_capacity, c->Dn);
   CK(c->b_gs.ensure(sizeof(GroupScratch) * size_t(c->G + 1)));
   CK(cudaMemsetAsync(c->b_gs.p, 0, sizeof(GroupScratch) * size_t(c->G + 1), c->stream));
   LAUNCH(c, k_alloc, grid_for(c->Dn, 128), 128, h, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
-         c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->b_result.as<evg_alloc_result>(),
-         c->b_status.as<int32_t>());
+         c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>());
   CK(cudaGetLastError());
   return EVG_OK;
 }
@@ -1107,14 +1110,21 @@ int evg_download(evg_ctx* c, evg_plan_out* po, evg_alloc_out* ao) {
   }
   if (ao) {
     if (!c->have_hosts) return fail(EVG_ERR_STATE, "allocator results requested but no hosts were uploaded");
-    if (ao->result && c->Dn) CK(cudaMemcpyAsync(ao->result, c->b_result.p, sizeof(evg_alloc_result) * size_t(c->Dn), cudaMemcpyDeviceToHost, s));
+    if (ao->result && c->Dn) CK(cudaMemcpyAsync(ao->result, c->result_ptr(), sizeof(evg_alloc_result) * size_t(c->Dn), cudaMemcpyDeviceToHost, s));
     if (ao->status && c->Dn) CK(cudaMemcpyAsync(ao->status, c->b_status.p, sizeof(int32_t) * size_t(c->Dn), cudaMemcpyDeviceToHost, s));
   }
   CK(cudaStreamSynchronize(s));
   return EVG_OK;
 }
 
-void* evg_device_result_ptr(evg_ctx* c) { return c ? c->b_result.p : nullptr; }
+void* evg_device_result_ptr(evg_ctx* c) { return c ? (void*)c->result_ptr() : nullptr; }
+int evg_bind_result_buffer(evg_ctx* c, void* device_ptr, int64_t capacity) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  if (device_ptr && capacity < 0) return fail(EVG_ERR_INVALID, "negative capacity");
+  c->ext_result = reinterpret_cast<evg_alloc_result*>(device_ptr);
+  c->ext_capacity = device_ptr ? capacity : 0;
+  return EVG_OK;
+}
 int64_t evg_last_launch_count(evg_ctx* c) { return c ? c->launches : 0; }
 
 int evg_last_timing_ms(evg_ctx* c, float* total_ms, float* sort_ms) {
@@ -1171,7 +1181,7 @@ int evg_alloc_batch(evg_ctx* c, const evg_host_soa* hosts, const int64_t* host_o
   c->launches = 0;
   rc = run_alloc(c, now_ns);
   if (rc != EVG_OK) return rc;
-  if (out->result && n_distros) CK(cudaMemcpyAsync(out->result, c->b_result.p, sizeof(evg_alloc_result) * size_t(n_distros), cudaMemcpyDeviceToHost, s));
+  if (out->result && n_distros) CK(cudaMemcpyAsync(out->result, c->result_ptr(), sizeof(evg_alloc_result) * size_t(n_distros), cudaMemcpyDeviceToHost, s));
   if (out->status && n_distros) CK(cudaMemcpyAsync(out->status, c->b_status.p, sizeof(int32_t) * size_t(n_distros), cudaMemcpyDeviceToHost, s));
   if (G > 0) CK(cudaMemcpyAsync(groups, c->b_ginfo.p, sizeof(evg_group_info) * size_t(G), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));

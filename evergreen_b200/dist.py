@@ -1,0 +1,84 @@
+"""Distro sharding across the GPUs of one box.
+
+Distros are independent in both the planner (one amboy job per distro,
+units/crons.go:303-332) and the allocator (units/crons.go:274-301), so the path
+shards by whole distros with no data-path exchange.  The only collective is one
+all-gather of the per-distro evg_alloc_result vector (16 B per distro) so every
+rank ends the tick holding every distro's (new_hosts, free_hosts, deficit).
+
+`torch.distributed` is plumbing here: NCCL over NVLink on the GPU box, gloo in
+the CPU tests.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+
+RESULT_BYTES = 16  # sizeof(evg_alloc_result)
+
+
+@dataclass
+class Shards:
+    world: int
+    owner: np.ndarray          # [D] rank owning each distro
+    slot: np.ndarray           # [D] position of the distro inside its rank's shard
+    members: List[np.ndarray]  # per rank: global distro ids in shard order
+    load: np.ndarray           # per rank: summed weight
+
+    @property
+    def max_shard(self) -> int:
+        return max((len(m) for m in self.members), default=0)
+
+
+def lpt_partition(weights: Sequence[int], world: int) -> Shards:
+    """Longest-processing-time bin packing of whole distros onto `world` ranks.
+    weight = tasks (+ hosts) of the distro; a distro never spans ranks because its
+    sort must not cross GPUs.  Deterministic: ties go to the lower distro id / rank."""
+    w = np.asarray(weights, dtype=np.int64)
+    D = int(w.shape[0])
+    order = np.lexsort((np.arange(D), -w))  # heaviest first, stable on id
+    load = np.zeros(world, dtype=np.int64)
+    owner = np.zeros(D, dtype=np.int64)
+    if D >= 4 * world and w.size and w.max() * world <= max(1, int(w.sum())) // 8:
+        # many comparable distros: round-robin over the sorted list is LPT-equivalent and O(D)
+        owner[order] = np.arange(D) % world
+        np.add.at(load, owner, w)
+    else:
+        import heapq
+        heap = [(0, r) for r in range(world)]
+        for d in order.tolist():
+            l, r = heapq.heappop(heap)
+            owner[d] = r
+            load[r] = l + int(w[d])
+            heapq.heappush(heap, (int(load[r]), r))
+    members = [np.nonzero(owner == r)[0] for r in range(world)]
+    slot = np.zeros(D, dtype=np.int64)
+    for m in members:
+        slot[m] = np.arange(len(m))
+    return Shards(world, owner, slot, members, load)
+
+
+def all_gather_results(local, shards: Shards, rank: int):
+    """One all-gather of the padded per-rank result vectors.
+
+    `local` is a uint8 torch tensor [max_shard * 16] on the rank's device (the
+    buffer the allocator kernel wrote; rows past this rank's shard are padding).
+    Returns a uint8 tensor [D * 16] in GLOBAL distro order on the same device."""
+    import torch
+    import torch.distributed as dist
+    pad = shards.max_shard * RESULT_BYTES
+    assert local.dtype == torch.uint8 and local.numel() == pad
+    gathered = torch.empty(shards.world * pad, dtype=torch.uint8, device=local.device)
+    dist.all_gather_into_tensor(gathered, local)
+    # un-pad into global distro order
+    idx = torch.as_tensor(shards.owner * shards.max_shard + shards.slot, device=local.device)
+    rows = gathered.view(shards.world * shards.max_shard, RESULT_BYTES)
+    return rows.index_select(0, idx).reshape(-1)
+
+
+def decode_results(buf) -> np.ndarray:
+    """uint8 tensor [D*16] -> numpy structured array (new_hosts, free_hosts, deficit_ns)."""
+    from . import _lib as L
+    return np.frombuffer(buf.cpu().numpy().tobytes(), dtype=L.ALLOC_RESULT_DTYPE)

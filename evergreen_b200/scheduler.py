@@ -99,6 +99,11 @@ class Engine:
             L.check(self.lib.evg_download(self.ctx, C.byref(ps), None))
         return po, ao
 
+    def bind_result_buffer(self, device_ptr: int, capacity_rows: int) -> None:
+        """The allocator kernel writes evg_alloc_result rows straight into this device buffer
+        (the all-gather send buffer, evergreen_b200.dist)."""
+        L.check(self.lib.evg_bind_result_buffer(self.ctx, C.c_void_p(device_ptr) if device_ptr else None, int(capacity_rows)))
+
     def device_result_ptr(self) -> int:
         return int(self.lib.evg_device_result_ptr(self.ctx) or 0)
 

@@ -280,6 +280,10 @@ int evg_download(evg_ctx* ctx, evg_plan_out* plan_out, evg_alloc_out* alloc_out)
 /* Device pointer to the resident evg_alloc_result[n_distros] vector, the
  * send buffer of the per-distro all-gather. */
 void* evg_device_result_ptr(evg_ctx* ctx);
+/* Make the allocator kernel write its evg_alloc_result[] rows straight into a
+ * caller-owned DEVICE buffer (e.g. the NCCL send buffer of the all-gather),
+ * `capacity` rows long; NULL restores the context-owned buffer. */
+int evg_bind_result_buffer(evg_ctx* ctx, void* device_ptr, int64_t capacity);
 /* Number of kernel launches issued by the last evg_run_resident. */
 int64_t evg_last_launch_count(evg_ctx* ctx);
 /* Device time of the planner's dominant kernel (segmented sort) and of the
