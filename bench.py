@@ -191,7 +191,10 @@ def main():
     w, shards = workload(rank, world, args.distros, args.tasks_per_distro)
     D_local = w.distros.n_distros
     D_total = world * args.distros
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) stream: kernels, NCCL and the timing events all live on it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng = scheduler.Engine(local_rank, stream.cuda_stream)
     # allocator results go straight into the all-gather send buffer
     send = torch.zeros(shards.max_shard * edist.RESULT_BYTES, dtype=torch.uint8, device=dev)

@@ -1,0 +1,469 @@
+// evg_plan_smem.cuh -- k_plan_smem: one CTA plans one distro entirely on-chip.
+//
+// For distros of up to THREADS*ITEMS tasks (12288 with <1024,12>) the whole
+// planner -- queue info, unit construction, scoring, first-occurrence choice,
+// the canonical pre-arrangement and the stable LSD radix sort -- runs in one
+// kernel with the distro's keys resident in shared memory, so HBM sees exactly
+// the compulsory traffic: 48 B/task read once, 12 B/task written once.
+//
+// Shared memory (cap = THREADS*ITEMS):
+//   key  [8*cap]  phases A-D: int64 V[cap] (TotalValue of the unit each task is emitted from)
+//                 sort      : uint32 key[2][cap] ping-pong (Vmax - V, ascending == TotalValue descending)
+//   idx  [4*cap]  uint16 idx[2][cap] ping-pong;  idx[1] doubles as the anchor histogram e[] before the sort
+//   aux  [4*cap]  uint16 anchor[cap], rank_in_unit[cap]
+//   wc   [W*256]  uint16 per-warp digit counters / running offsets
+//
+// Reference: scheduler/planner.go:209-481, scheduler/scheduler.go:56-159.
+#pragma once
+
+template <int THREADS, int ITEMS>
+struct PlanSmem {
+  static constexpr int kCap = THREADS * ITEMS;
+  static constexpr int kWarps = THREADS / 32;
+  static constexpr size_t kBytes = size_t(16) * kCap + size_t(kWarps) * 256 * 2 + 256 * 4 * 2 + (kCap / 8) * 2 + 512;
+};
+
+struct PlanShared {
+  int64_t base, dep0;
+  int32_t tn, ng, d, any_complex, gv, has_edges;
+  uint32_t ub;
+  unsigned long long vmax_enc, vmin_enc;   // encoded so that atomicMax / atomicMin work on unsigned
+  int32_t n_displaced;
+  // queue-info block accumulators
+  unsigned int c[10];
+  unsigned long long s[4];
+};
+
+__device__ __forceinline__ unsigned long long ord_i64(int64_t v) { return uint64_t(v) ^ 0x8000000000000000ULL; }
+__device__ __forceinline__ int64_t unord_i64(unsigned long long k) { return int64_t(k ^ 0x8000000000000000ULL); }
+
+// Unit.info + value + this member's rank for one linked (unit, member) pair:
+// shared by the general path (k_unit) and the on-chip path.
+__device__ __forceinline__ void eval_pair(const DTasks& T, const DWork& W, const evg_distro_cfg& cfg, int64_t now,
+                                          uint32_t p, uint32_t t, int64_t base) {
+  const uint32_t slot = W.pair_slot[p];
+  const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
+  const int64_t my_ex = T.expected[t];
+  const uint32_t my_li = uint32_t(t - base);
+  UnitAcc a;
+  acc_init(a);
+  uint32_t anchor = kNoAnchor, rk = 0;
+  for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
+    const uint32_t tq = pair_task(T, W, q);
+    const uint32_t lq = uint32_t(tq - base);
+    const int32_t q_pr = T.priority[tq], q_nd = T.numdep[tq], q_tgo = T.tgo[tq];
+    const int64_t q_ex = T.expected[tq];
+    acc_add(a, now, q_pr, q_ex, T.qbasis[tq], q_nd, T.gid[tq], T.flags[tq]);
+    if (q < uint32_t(T.n)) anchor = min(anchor, lq);  // own-key pairs are the SetDistro members (planner.go:446)
+    if (in_unit_less(q_tgo, q_nd, q_pr, q_ex, lq, my_tgo, my_nd, my_pr, my_ex, my_li)) rk++;
+  }
+  W.cand_v[p] = unit_value(a, cfg, nullptr);
+  W.cand_a[p] = anchor;  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
+  W.cand_rk[p] = rk;
+}
+
+template <int THREADS, int ITEMS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int64_t now, int want_best_pair,
+            int32_t* __restrict__ order, int64_t* __restrict__ total_value) {
+  constexpr int CAP = THREADS * ITEMS;
+  constexpr int NW = THREADS / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int64_t* sV = reinterpret_cast<int64_t*>(smem_raw);
+  uint32_t* sKey = reinterpret_cast<uint32_t*>(smem_raw);                 // [2][CAP]
+  uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem_raw + size_t(8) * CAP);  // [2][CAP]
+  uint16_t* sA = reinterpret_cast<uint16_t*>(smem_raw + size_t(12) * CAP);   // anchor
+  uint16_t* sRk = sA + CAP;                                               // rank in unit
+  uint16_t* sWc = reinterpret_cast<uint16_t*>(smem_raw + size_t(16) * CAP);  // [NW][256]
+  uint32_t* sTot = reinterpret_cast<uint32_t*>(sWc + NW * 256);          // [256]
+  uint32_t* sScan = sTot + 256;                                           // [256] scratch for block scans
+  uint32_t* sHasDep = sScan + 256;                                        // [CAP/32]
+  uint32_t* sDisp = sHasDep + CAP / 32;                                   // [CAP/32]
+  PlanShared* S = reinterpret_cast<PlanShared*>(sDisp + CAP / 32);
+  uint16_t* sE = sIdx + CAP;                                              // anchor histogram, aliases idx[1]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned full = 0xffffffffu;
+
+  // ---- phase 0: distro header ----
+  if (tid == 0) {
+    const int d = list[blockIdx.x];
+    S->d = d;
+    S->base = D.task_off[d];
+    S->tn = int32_t(D.task_off[d + 1] - D.task_off[d]);
+    S->ng = int32_t(D.group_off[d + 1] - D.group_off[d]);
+    S->ub = uint32_t(D.unit_base[d]);
+    S->gv = D.cfg[d].group_versions != 0;
+    int64_t e0 = 0, e1 = 0;
+    if (T.n_edges > 0) { e0 = T.dep_off[S->base]; e1 = T.dep_off[S->base + S->tn]; }
+    S->dep0 = e0;
+    S->has_edges = e1 > e0;
+    S->any_complex = (S->ng > 0) || S->gv || (e1 > e0);
+    S->vmax_enc = 0ull;
+    S->vmin_enc = ~0ull;
+    S->n_displaced = 0;
+    for (int k = 0; k < 10; k++) S->c[k] = 0;
+    for (int k = 0; k < 4; k++) S->s[k] = 0;
+  }
+  for (int i = tid; i < CAP / 32; i += THREADS) { sHasDep[i] = 0; sDisp[i] = 0; }
+  __syncthreads();
+  const int d = S->d;
+  const int64_t base = S->base;
+  const int tn = S->tn;
+  const uint32_t ng = uint32_t(S->ng), ub = S->ub;
+  const bool gv = S->gv != 0, any = S->any_complex != 0, has_edges = S->has_edges != 0;
+  const evg_distro_cfg cfg = D.cfg[d];
+
+  // ---- phase 1: dependents (planner.go:449-456) and empty unit lists ----
+  if (has_edges) {
+    for (int i = tid; i < tn; i += THREADS) {
+      const int64_t t = base + i;
+      for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) {
+        const uint32_t dl = uint32_t(T.dep_idx[e]);
+        atomicOr(&sHasDep[dl >> 5], 1u << (dl & 31));
+      }
+    }
+    __syncthreads();
+  }
+  if (any) {
+    const uint32_t nv = gv ? uint32_t(cfg.n_versions) : 0u;
+    for (uint32_t s = tid; s < ng + nv; s += THREADS) W.head[ub + s] = kInactive;
+    if (!gv && has_edges)
+      for (int i = tid; i < tn; i += THREADS)
+        if (sHasDep[i >> 5] & (1u << (i & 31))) W.head[ub + ng + i] = kInactive;
+    for (uint32_t g = tid; g < ng; g += THREADS) W.ginfo[D.group_off[d] + g].max_hosts = D.gmax[D.group_off[d] + g];
+    __syncthreads();
+  }
+
+  // ---- phase 2: per task -- queue info, unit links, score of single-task units ----
+  unsigned int c_dm = 0, c_mq = 0, c_over = 0, c_wait = 0, c_sec = 0, u_n = 0, u_cnt = 0, u_over = 0, u_wait = 0, u_mq = 0;
+  int64_t s_exp = 0, s_over = 0, s_uexp = 0, s_uover = 0;
+  const int64_t threshold = cfg.target_time_ns;
+  for (int i = tid; i < tn; i += THREADS) {
+    const int64_t t = base + i;
+    const int32_t prio = T.priority[t], nd = T.numdep[t], gid = T.gid[t], vid = T.vid[t];
+    const int64_t exp_ns = T.expected[t], qb = T.qbasis[t], wb = T.wbasis[t];
+    const uint32_t fl = T.flags[t];
+    // GetDistroQueueInfo (scheduler.go:66-138)
+    const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
+    const bool counted = !cfg.includes_dependencies || dm;
+    const bool over = counted && exp_ns > threshold;
+    const bool wait_over = counted && dm && since(now, wb) > threshold;
+    const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
+    c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += (fl & EVG_TF_OTHER_DISTRO) != 0;
+    if (counted) s_exp += exp_ns;
+    if (over) s_over += exp_ns;
+    if (gid < 0) {
+      u_n += 1; u_cnt += counted; u_over += over; u_wait += wait_over; u_mq += mq_dm;
+      if (counted) s_uexp += exp_ns;
+      if (over) s_uover += exp_ns;
+    } else {
+      evg_group_info* g = W.ginfo + D.group_off[d] + gid;
+      atomic_add64(&g->count, counted);
+      atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
+      atomic_add64(&g->count_duration_over_threshold, over);
+      atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
+      atomic_add64(&g->count_wait_over_threshold, wait_over);
+      atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
+    }
+    // units (planner.go:431-447)
+    const bool own_complex = any && (gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31))));
+    sA[i] = uint16_t(i);
+    sRk[i] = 0;
+    if (!own_complex) {
+      UnitAcc a;
+      acc_init(a);
+      acc_add(a, now, prio, exp_ns, qb, nd, gid, fl);
+      sV[i] = unit_value(a, cfg, nullptr);
+    }
+    if (any) {
+      const uint32_t s_own = own_slot_local(gid, vid, uint32_t(i), ng, gv);
+      const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
+      if (own_complex) link_pair(W, uint32_t(t), ub + s_own);
+      if (s_ver != kInactive) link_pair(W, uint32_t(T.n + t), ub + s_ver);
+      if (has_edges) {
+        const int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
+        for (int64_t e = e0; e < e1; e++) {
+          const uint32_t dl = uint32_t(T.dep_idx[e]);
+          const uint32_t s = own_slot_local(T.gid[base + dl], T.vid[base + dl], dl, ng, gv);
+          bool dup = (s == s_own) || (s == s_ver);  // Unit.Add is keyed by task id (planner.go:131)
+          for (int64_t f = e0; f < e && !dup; f++) {
+            const uint32_t fl2 = uint32_t(T.dep_idx[f]);
+            dup = own_slot_local(T.gid[base + fl2], T.vid[base + fl2], fl2, ng, gv) == s;
+          }
+          W.edge_task[e] = uint32_t(t);
+          W.edge_live[e] = dup ? 0 : 1;
+          if (!dup) link_pair(W, uint32_t(2 * T.n + e), ub + s);
+        }
+      }
+      if (want_best_pair) W.best_pair[t] = kInactive;
+    }
+  }
+  // fold the queue-info partials: warp shuffle, then shared atomics, then one writer
+  {
+    unsigned int cs[10] = {c_dm, c_mq, c_over, c_wait, c_sec, u_n, u_cnt, u_over, u_wait, u_mq};
+#pragma unroll
+    for (int k = 0; k < 10; k++) cs[k] = __reduce_add_sync(full, cs[k]);
+    int64_t ss[4] = {s_exp, s_over, s_uexp, s_uover};
+#pragma unroll
+    for (int k = 0; k < 4; k++) ss[k] = warp_sum64(ss[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 10; k++) if (cs[k]) atomicAdd(&S->c[k], cs[k]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (ss[k]) atomicAdd(&S->s[k], (unsigned long long)ss[k]);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    evg_queue_info q;
+    q.length = tn;
+    q.length_with_dependencies_met = S->c[0];
+    q.count_dep_filled_merge_queue_tasks = S->c[1];
+    q.expected_duration = int64_t(S->s[0]);
+    q.max_duration_threshold = threshold;
+    q.count_duration_over_threshold = S->c[2];
+    q.duration_over_threshold = int64_t(S->s[1]);
+    q.count_wait_over_threshold = S->c[3];
+    q.secondary_queue = S->c[4] != 0;
+    q.has_ungrouped = S->c[5] != 0;
+    q.ungrouped.count = S->c[6];
+    q.ungrouped.count_free = 0;
+    q.ungrouped.count_required = 0;
+    q.ungrouped.max_hosts = 0;
+    q.ungrouped.expected_duration = int64_t(S->s[2]);
+    q.ungrouped.count_duration_over_threshold = S->c[7];
+    q.ungrouped.count_wait_over_threshold = S->c[8];
+    q.ungrouped.count_dep_filled_merge_queue_tasks = S->c[9];
+    q.ungrouped.duration_over_threshold = int64_t(S->s[3]);
+    W.qinfo[d] = q;
+  }
+
+  // ---- phase 3/4: multi-member units (Unit.info, score, first-occurrence choice) ----
+  if (any) {
+    for (int i = tid; i < tn; i += THREADS) {
+      const int64_t t = base + i;
+      const int32_t gid = T.gid[t];
+      const bool own_complex = gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31)));
+      if (own_complex) eval_pair(T, W, cfg, now, uint32_t(t), uint32_t(t), base);
+      if (gid >= 0 && gv) eval_pair(T, W, cfg, now, uint32_t(T.n + t), uint32_t(t), base);
+      if (has_edges)
+        for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++)
+          if (W.edge_live[e]) eval_pair(T, W, cfg, now, uint32_t(2 * T.n + e), uint32_t(t), base);
+    }
+    __syncthreads();
+    for (int i = tid; i < tn; i += THREADS) {
+      const int64_t t = base + i;
+      const int32_t gid = T.gid[t];
+      const bool own_complex = gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31)));
+      const bool has_ver = gid >= 0 && gv;
+      const int64_t e0 = has_edges ? T.dep_off[t] : 0, e1 = has_edges ? T.dep_off[t + 1] : 0;
+      if (!own_complex && !has_ver && e1 == e0) continue;  // emitted from its own single-task unit
+      bool have = false;
+      int64_t bv = 0;
+      uint32_t ba = 0, brk = 0, bp = kInactive;
+      auto consider = [&](int64_t v, uint32_t a, uint32_t rk, uint32_t pair) {
+        if (a == kNoAnchor) return;
+        if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; brk = rk; bp = pair; }
+      };
+      if (!own_complex) consider(sV[i], uint32_t(i), 0, kInactive);
+      else consider(W.cand_v[t], W.cand_a[t], W.cand_rk[t], uint32_t(t));
+      if (has_ver) { const int64_t pv = T.n + t; consider(W.cand_v[pv], W.cand_a[pv], W.cand_rk[pv], uint32_t(pv)); }
+      for (int64_t e = e0; e < e1; e++)
+        if (W.edge_live[e]) { const int64_t pe = 2 * T.n + e; consider(W.cand_v[pe], W.cand_a[pe], W.cand_rk[pe], uint32_t(pe)); }
+      sV[i] = bv;
+      sA[i] = uint16_t(ba);
+      sRk[i] = uint16_t(brk);
+      W.best_pair[t] = bp;
+      if (!(ba == uint32_t(i) && brk == 0)) { atomicOr(&sDisp[i >> 5], 1u << (i & 31)); S->n_displaced = 1; }
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 5: value range ----
+  {
+    unsigned long long mx = 0ull, mn = ~0ull;
+    for (int i = tid; i < tn; i += THREADS) {
+      const unsigned long long k = ord_i64(sV[i]);
+      mx = max(mx, k);
+      mn = min(mn, k);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = max(mx, __shfl_xor_sync(full, mx, o));
+      mn = min(mn, __shfl_xor_sync(full, mn, o));
+    }
+    if (lane == 0) { atomicMax(&S->vmax_enc, mx); atomicMin(&S->vmin_enc, mn); }
+  }
+  // ---- phase 6: canonical pre-arrangement (ties: unit anchor asc, rank in unit asc) ----
+  const bool displaced = any && (S->n_displaced != 0);  // n_displaced was published by the barrier that closed phase 4
+  if (displaced) {
+    uint32_t* e32 = reinterpret_cast<uint32_t*>(sE);
+    for (int i = tid; i < CAP / 2; i += THREADS) e32[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < tn; i += THREADS) {
+      const uint32_t a = sA[i];
+      atomicAdd(&e32[a >> 1], 1u << (16 * (a & 1)));
+    }
+    __syncthreads();
+    // exclusive scan of e[0..CAP): ITEMS consecutive entries per thread
+    uint32_t loc[ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) { loc[k] = sE[tid * ITEMS + k]; sum += loc[k]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(full, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) sScan[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < NW ? sScan[lane] : 0, winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(full, winc, o); if (lane >= o) winc += v; }
+      if (lane < NW) sScan[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t run = sScan[warp] + inc - sum;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) { sE[tid * ITEMS + k] = uint16_t(run); run += loc[k]; }
+    __syncthreads();
+    for (int i = tid; i < tn; i += THREADS) {
+      const uint32_t a = sA[i];
+      uint32_t pos = sE[a];
+      if (sDisp[i >> 5] & (1u << (i & 31))) {
+        // offset among the tasks emitted from the same unit: members with the same best anchor and a smaller rank
+        const uint32_t myrk = sRk[i];
+        const uint32_t bp = W.best_pair[base + i];
+        for (uint32_t q = W.head[W.pair_slot[bp]]; q < kEnd; q = W.next[q]) {
+          const uint32_t lq = uint32_t(pair_task(T, W, q) - base);
+          if (sA[lq] == a && sRk[lq] < myrk) pos++;
+        }
+      }
+      sIdx[pos] = uint16_t(i);
+    }
+  } else {
+    for (int i = tid; i < tn; i += THREADS) sIdx[i] = uint16_t(i);
+  }
+  __syncthreads();
+
+  // ---- phase 7: compact keys: key = Vmax - V (ascending key == descending TotalValue) ----
+  const int64_t vmax = unord_i64(S->vmax_enc);
+  const uint64_t range = tn > 0 ? uint64_t(S->vmax_enc - S->vmin_enc) : 0;
+  int bits = 64 - __clzll((long long)(range | 1ull));
+  if (range == 0) bits = 0;
+  const bool wide = bits > 32;
+  {
+    uint32_t kreg[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+      const int p = tid + k * THREADS;
+      kreg[k] = 0;
+      if (p < tn) {
+        const uint32_t i = sIdx[p];
+        const uint64_t k64 = uint64_t(vmax) - uint64_t(sV[i]);
+        kreg[k] = uint32_t(k64);
+        if (wide) W.buf[0].key_v[base + i] = k64;  // high word is reloaded after the four low passes
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+      const int p = tid + k * THREADS;
+      if (p < tn) sKey[p] = kreg[k];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 8: stable LSD radix sort, 8-bit digits, warp-segmented ranking ----
+  int cur = 0;
+  const int seg = ((tn + NW - 1) / NW + 31) & ~31;  // elements per warp, multiple of 32
+  const int seg0 = warp * seg;
+  const int seg1 = min(seg0 + seg, tn);
+  const unsigned lt = (1u << lane) - 1u;
+  const int npass = (bits + 7) / 8;
+  for (int pass = 0; pass < npass; pass++) {
+    if (pass == 4) {  // wide keys: switch to the high word
+      uint32_t* kc = sKey + cur * CAP;
+      const uint16_t* ic = sIdx + cur * CAP;
+      for (int p = tid; p < tn; p += THREADS) kc[p] = uint32_t(W.buf[0].key_v[base + ic[p]] >> 32);
+      __syncthreads();
+    }
+    const int shift = 8 * (pass & 3);
+    const uint32_t* kc = sKey + cur * CAP;
+    const uint16_t* ic = sIdx + cur * CAP;
+    uint32_t* kn = sKey + (cur ^ 1) * CAP;
+    uint16_t* in_ = sIdx + (cur ^ 1) * CAP;
+    uint16_t* wc = sWc + warp * 256;
+    for (int k = lane; k < 256; k += 32) wc[k] = 0;
+    __syncwarp();
+    for (int s0 = seg0; s0 < seg1; s0 += 32) {
+      const int p = s0 + lane;
+      const uint32_t dg = p < seg1 ? ((kc[p] >> shift) & 255u) : 0xFFFFu;
+      const unsigned peers = __match_any_sync(full, dg);
+      if (dg != 0xFFFFu && (peers & lt) == 0) wc[dg] += uint16_t(__popc(peers));
+      __syncwarp();
+    }
+    __syncthreads();
+    if (tid < 256) {
+      uint32_t run = 0;
+      for (int w = 0; w < NW; w++) {
+        const uint32_t x = sWc[w * 256 + tid];
+        sWc[w * 256 + tid] = uint16_t(run);
+        run += x;
+      }
+      sTot[tid] = run;
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 256 digit totals
+      uint32_t v[8], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { v[k] = sTot[lane * 8 + k]; sum += v[k]; }
+      uint32_t inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(full, inc, o); if (lane >= o) inc += x; }
+      uint32_t run = inc - sum;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { sTot[lane * 8 + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    for (int s0 = seg0; s0 < seg1; s0 += 32) {
+      const int p = s0 + lane;
+      const bool ok = p < seg1;
+      const uint32_t kk = ok ? kc[p] : 0u;
+      const uint16_t ii = ok ? ic[p] : uint16_t(0);
+      const uint32_t dg = ok ? ((kk >> shift) & 255u) : 0xFFFFu;
+      const unsigned peers = __match_any_sync(full, dg);
+      const uint32_t r = __popc(peers & lt);
+      uint32_t off = 0;
+      if (ok) off = wc[dg];
+      __syncwarp();
+      if (ok && r == 0) wc[dg] = uint16_t(off + __popc(peers));
+      __syncwarp();
+      if (ok) {
+        const uint32_t pos = sTot[dg] + off + r;
+        kn[pos] = kk;
+        in_[pos] = ii;
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+
+  // ---- phase 9: ranked queue out (coalesced) ----
+  {
+    const uint32_t* kc = sKey + cur * CAP;
+    const uint16_t* ic = sIdx + cur * CAP;
+    if (!wide) {
+      for (int p = tid; p < tn; p += THREADS) {
+        order[base + p] = int32_t(ic[p]);
+        total_value[base + p] = int64_t(uint64_t(vmax) - uint64_t(kc[p]));
+      }
+    } else {
+      for (int p = tid; p < tn; p += THREADS) {
+        const uint32_t i = ic[p];
+        order[base + p] = int32_t(i);
+        total_value[base + p] = int64_t(uint64_t(vmax) - W.buf[0].key_v[base + i]);
+      }
+    }
+  }
+}

@@ -79,6 +79,8 @@ struct DevBuf {
 constexpr int kTile = 2048;        // sort tile: 64 warp-chunks of 32
 constexpr int kChunks = kTile / 32;
 constexpr int kMaxPass = 16;       // 8 tie bytes + 8 value bytes
+// on-chip planner classes <THREADS, ITEMS>: capacity = THREADS*ITEMS tasks per distro
+constexpr int kCapA = 128 * 8, kCapB = 256 * 16, kCapC = 1024 * 12;
 constexpr uint32_t kInactive = 0xFFFFFFFFu;  // next[]: pair not linked / head[]: empty list
 constexpr uint32_t kEnd = 0xFFFFFFFEu;       // next[]: end of list
 constexpr uint32_t kNoAnchor = 0xFFFFFFFFu;
@@ -124,8 +126,9 @@ struct DWork {
   uint32_t* next;        // [2T+E]
   uint32_t* pair_slot;   // [2T+E]
   uint32_t* edge_task;   // [E]
+  uint8_t* edge_live;    // [E] on-chip path: 1 = edge pair linked (not a duplicate membership)
+  const uint8_t* route;  // [D] 1 = distro planned by k_plan_smem (general kernels skip it)
   int64_t* cand_v;       // [2T+E]
-  uint32_t* cand_m;      // [2T+E]
   uint32_t* cand_a;      // [2T+E]
   uint32_t* cand_rk;     // [2T+E]
   uint32_t* best_pair;   // [T]
@@ -233,15 +236,23 @@ __device__ __forceinline__ void link_pair(DWork& W, uint32_t pair, uint32_t slot
   W.next[pair] = (prev == kInactive) ? kEnd : prev;
 }
 
+__device__ __forceinline__ uint32_t pair_task(const DTasks& T, const DWork& W, uint32_t p) {
+  if (p < uint32_t(T.n)) return p;
+  if (p < uint32_t(2 * T.n)) return p - uint32_t(T.n);
+  return W.edge_task[p - uint32_t(2 * T.n)];
+}
+
+#include "evg_plan_smem.cuh"
+
 // --------------------------------------------------------------------------
-// kernels
+// kernels (general path: any distro size)
 // --------------------------------------------------------------------------
 
 // planner.go:449-456 (pass 2): mark every task some in-queue task depends on.
 __global__ void k_mark_dependents(DTasks T, DDistros D, DWork W) {
   int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   int d = block_find_distro(D.task_off, D.n, t, T.n);
-  if (d < 0) return;
+  if (d < 0 || W.route[d]) return;
   int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
   int64_t base = D.task_off[d];
   for (int64_t e = e0; e < e1; e++) W.has_dep[base + T.dep_idx[e]] = 1;
@@ -252,7 +263,7 @@ __global__ void k_mark_dependents(DTasks T, DDistros D, DWork W) {
 __global__ void __launch_bounds__(256) k_task(DTasks T, DDistros D, DWork W, int64_t now, int any_complex) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int d = block_find_distro(D.task_off, D.n, t, T.n);
-  const bool valid = d >= 0;
+  const bool valid = d >= 0 && !W.route[d];
   const unsigned full = 0xffffffffu;
   const int d0 = __shfl_sync(full, d, 0);
   const bool uniform = __all_sync(full, d == d0) && valid;
@@ -376,7 +387,7 @@ __global__ void __launch_bounds__(256) k_task(DTasks T, DDistros D, DWork W, int
       const int64_t v = unit_value(a, cfg, nullptr);
       if (any_complex) W.cand_v[t] = v;  // read back by k_best
       key_v = enc_value(v);
-      key_s = enc_tie(li, li, 0);
+      key_s = enc_tie(li, 0);
     }
     if (!any_complex) {
       W.buf[0].key_s[t] = key_s;
@@ -387,42 +398,20 @@ __global__ void __launch_bounds__(256) k_task(DTasks T, DDistros D, DWork W, int
   if (!any_complex) note_key_bits(W.bits, valid ? d : 0, valid, uniform, key_s, key_v);
 }
 
-__device__ __forceinline__ uint32_t pair_task(const DTasks& T, const DWork& W, uint32_t p) {
-  if (p < uint32_t(T.n)) return p;
-  if (p < uint32_t(2 * T.n)) return p - uint32_t(T.n);
-  return W.edge_task[p - uint32_t(2 * T.n)];
-}
-
 // Per linked (unit, member) pair: Unit.info over the unit's member list, the
-// unit's score, its canonical tie data and this member's rank inside the unit.
+// unit's score, its anchor and this member's rank inside the unit.
 __global__ void __launch_bounds__(256) k_unit(DTasks T, DDistros D, DWork W, int64_t now, int64_t n_pairs) {
   const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
-  if (W.next[p] == kInactive) return;
-  const uint32_t t = pair_task(T, W, uint32_t(p));
+  // resolve the owning distro first: pairs of on-chip distros belong to k_plan_smem
+  uint32_t t;
+  if (p < T.n) t = uint32_t(p);
+  else if (p < 2 * T.n) t = uint32_t(p - T.n);
+  else t = W.edge_task[p - 2 * T.n];
   const int d = find_distro(D.task_off, 0, D.n - 1, int64_t(t));
-  const int64_t base = D.task_off[d];
-  const uint32_t slot = W.pair_slot[p];
-  const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
-  const int64_t my_ex = T.expected[t];
-  const uint32_t my_li = uint32_t(t - base);
-  UnitAcc a;
-  acc_init(a);
-  uint32_t min_member = 0xFFFFFFFFu, anchor = kNoAnchor, rk = 0;
-  for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
-    const uint32_t tq = pair_task(T, W, q);
-    const uint32_t lq = uint32_t(tq - base);
-    const int32_t q_pr = T.priority[tq], q_nd = T.numdep[tq], q_tgo = T.tgo[tq];
-    const int64_t q_ex = T.expected[tq];
-    acc_add(a, now, q_pr, q_ex, T.qbasis[tq], q_nd, T.gid[tq], T.flags[tq]);
-    min_member = min(min_member, lq);
-    if (q < uint32_t(T.n)) anchor = min(anchor, lq);  // own-key pairs are the SetDistro members (planner.go:446)
-    if (in_unit_less(q_tgo, q_nd, q_pr, q_ex, lq, my_tgo, my_nd, my_pr, my_ex, my_li)) rk++;
-  }
-  W.cand_v[p] = unit_value(a, D.cfg[d], nullptr);
-  W.cand_m[p] = min_member;
-  W.cand_a[p] = anchor;  // kNoAnchor: unit never got a distro -> not exported (planner.go:81-83)
-  W.cand_rk[p] = rk;
+  if (W.route[d]) return;
+  if (W.next[p] == kInactive) return;
+  eval_pair(T, W, D.cfg[d], now, uint32_t(p), t, D.task_off[d]);
 }
 
 // Per task: the unit it is emitted from = best of its memberships under the
@@ -430,7 +419,7 @@ __global__ void __launch_bounds__(256) k_unit(DTasks T, DDistros D, DWork W, int
 __global__ void __launch_bounds__(256) k_best(DTasks T, DDistros D, DWork W) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int d = block_find_distro(D.task_off, D.n, t, T.n);
-  const bool valid = d >= 0;
+  const bool valid = d >= 0 && !W.route[d];
   const unsigned full = 0xffffffffu;
   const int d0 = __shfl_sync(full, d, 0);
   const bool uniform = __all_sync(full, d == d0) && valid;
@@ -439,24 +428,24 @@ __global__ void __launch_bounds__(256) k_best(DTasks T, DDistros D, DWork W) {
     const uint32_t li = uint32_t(t - D.task_off[d]);
     bool have = false;
     int64_t bv = 0;
-    uint32_t bm = 0, ba = 0, brk = 0, bp = kInactive;
-    auto consider = [&](int64_t v, uint32_t m, uint32_t a, uint32_t rk, uint32_t pair) {
+    uint32_t ba = 0, brk = 0, bp = kInactive;
+    auto consider = [&](int64_t v, uint32_t a, uint32_t rk, uint32_t pair) {
       if (a == kNoAnchor) return;
-      bool better = !have || v > bv || (v == bv && (m < bm || (m == bm && a < ba)));
-      if (better) { have = true; bv = v; bm = m; ba = a; brk = rk; bp = pair; }
+      bool better = !have || v > bv || (v == bv && a < ba);
+      if (better) { have = true; bv = v; ba = a; brk = rk; bp = pair; }
     };
-    if (W.next[t] == kInactive) consider(W.cand_v[t], li, li, 0, kInactive);  // single-task unit scored by k_task
-    else consider(W.cand_v[t], W.cand_m[t], W.cand_a[t], W.cand_rk[t], uint32_t(t));
+    if (W.next[t] == kInactive) consider(W.cand_v[t], li, 0, kInactive);  // single-task unit scored by k_task
+    else consider(W.cand_v[t], W.cand_a[t], W.cand_rk[t], uint32_t(t));
     const int64_t pv = T.n + t;
-    if (W.next[pv] != kInactive) consider(W.cand_v[pv], W.cand_m[pv], W.cand_a[pv], W.cand_rk[pv], uint32_t(pv));
+    if (W.next[pv] != kInactive) consider(W.cand_v[pv], W.cand_a[pv], W.cand_rk[pv], uint32_t(pv));
     if (T.n_edges > 0) {
       for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) {
         const int64_t pe = 2 * T.n + e;
-        if (W.next[pe] != kInactive) consider(W.cand_v[pe], W.cand_m[pe], W.cand_a[pe], W.cand_rk[pe], uint32_t(pe));
+        if (W.next[pe] != kInactive) consider(W.cand_v[pe], W.cand_a[pe], W.cand_rk[pe], uint32_t(pe));
       }
     }
     key_v = enc_value(bv);
-    key_s = enc_tie(bm, ba, brk);
+    key_s = enc_tie(ba, brk);
     W.best_pair[t] = bp;
     W.buf[0].key_s[t] = key_s;
     W.buf[0].key_v[t] = key_v;
@@ -464,6 +453,8 @@ __global__ void __launch_bounds__(256) k_best(DTasks T, DDistros D, DWork W) {
   }
   note_key_bits(W.bits, valid ? d : 0, valid, uniform, key_s, key_v);
 }
+
+// bits[]: or-words start at 0, and-words at all ones
 
 // bits[]: or-words start at 0, and-words at all ones
 __global__ void k_init_bits(unsigned long long* bits, int n) {
@@ -480,7 +471,7 @@ __global__ void k_sched(DDistros D, DWork W, int use_tie) {
   int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D.n) return;
   int n = 0;
-  if (D.task_off[d + 1] - D.task_off[d] > 1) {
+  if (!W.route[d] && D.task_off[d + 1] - D.task_off[d] > 1) {
     uint64_t vs = W.bits[4 * d + 0] & ~W.bits[4 * d + 1];
     uint64_t vv = W.bits[4 * d + 2] & ~W.bits[4 * d + 3];
     if (use_tie)
@@ -590,36 +581,39 @@ __global__ void __launch_bounds__(256) k_sort_scatter(int j, DDistros D, DWork W
   }
 }
 
-// Ranked queue out: order[], TotalValue and (optionally) the 13-field breakdown
-// of the unit each task was emitted from (planner.go:467-477, task.go:3990-4038).
-__global__ void __launch_bounds__(256) k_emit(DTasks T, DDistros D, DWork W, int64_t now, int any_complex,
-                                              int32_t* order, int64_t* total_value, int64_t* breakdown) {
+// Ranked queue out (general path): order[] and TotalValue per rank (planner.go:467-477).
+__global__ void __launch_bounds__(256) k_emit(DTasks T, DDistros D, DWork W, int32_t* order, int64_t* total_value) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int d = block_find_distro(D.task_off, D.n, t, T.n);
+  if (d < 0 || W.route[d]) return;
+  const SortBuf src = W.buf[W.npass[d] & 1];
+  order[t] = int32_t(src.idx[t]);
+  total_value[t] = dec_value(src.key_v[t]);
+}
+
+// The 13-field SortingValueBreakdown of the unit each ranked task was emitted
+// from (planner.go:472-476, model/task/task.go:3990-4038); both paths.
+__global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W, int64_t now, int any_complex,
+                                                   const int32_t* order, int64_t* breakdown) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int d = block_find_distro(D.task_off, D.n, t, T.n);
   if (d < 0) return;
-  const SortBuf src = W.buf[W.npass[d] & 1];
-  const uint32_t li = src.idx[t];
-  order[t] = int32_t(li);
-  const int64_t v = dec_value(src.key_v[t]);
-  total_value[t] = v;
-  if (breakdown) {
-    const int64_t base = D.task_off[d];
-    const int64_t g = base + li;
-    UnitAcc a;
-    acc_init(a);
-    const uint32_t bp = any_complex ? W.best_pair[g] : kInactive;
-    if (bp == kInactive) {
-      acc_add(a, now, T.priority[g], T.expected[g], T.qbasis[g], T.numdep[g], T.gid[g], T.flags[g]);
-    } else {
-      for (uint32_t q = W.head[W.pair_slot[bp]]; q < kEnd; q = W.next[q]) {
-        const uint32_t tq = pair_task(T, W, q);
-        acc_add(a, now, T.priority[tq], T.expected[tq], T.qbasis[tq], T.numdep[tq], T.gid[tq], T.flags[tq]);
-      }
+  const int64_t base = D.task_off[d];
+  const int64_t g = base + order[t];
+  UnitAcc a;
+  acc_init(a);
+  const uint32_t bp = any_complex ? W.best_pair[g] : kInactive;
+  if (bp == kInactive) {
+    acc_add(a, now, T.priority[g], T.expected[g], T.qbasis[g], T.numdep[g], T.gid[g], T.flags[g]);
+  } else {
+    for (uint32_t q = W.head[W.pair_slot[bp]]; q < kEnd; q = W.next[q]) {
+      const uint32_t tq = pair_task(T, W, q);
+      acc_add(a, now, T.priority[tq], T.expected[tq], T.qbasis[tq], T.numdep[tq], T.gid[tq], T.flags[tq]);
     }
-    int64_t bd[EVG_BD_N];
-    unit_value(a, D.cfg[d], bd);
-    for (int k = 0; k < EVG_BD_N; k++) breakdown[t * EVG_BD_N + k] = bd[k];
   }
+  int64_t bd[EVG_BD_N];
+  unit_value(a, D.cfg[d], bd);
+  for (int k = 0; k < EVG_BD_N; k++) breakdown[t * EVG_BD_N + k] = bd[k];
 }
 
 // scheduler.go:144-158: scalars of DistroQueueInfo / TaskGroupInfo that are not sums.
@@ -769,7 +763,10 @@ struct evg_ctx {
   bool timed = false;
   DevBuf b_prio, b_exp, b_qb, b_wb, b_nd, b_tgo, b_gid, b_vid, b_flags, b_depoff, b_depidx;
   DevBuf b_taskoff, b_groupoff, b_cfg, b_gmax, b_unitbase;
-  DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_cv, b_cm, b_ca, b_crk, b_bestpair;
+  DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_cv, b_ca, b_crk, b_bestpair;
+  DevBuf b_route, b_listA, b_listB, b_listC;
+  int32_t nA = 0, nB = 0, nC = 0, n_general = 0;  // distros per on-chip class / general path
+  int general_complex = 0;
   DevBuf b_ks[2], b_kv[2], b_ix[2], b_bits, b_npass, b_sched, b_maxpass;
   DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist;
   DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
@@ -796,8 +793,11 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt) 
   if (E > 0 && (!t->dep_off || !t->dep_idx)) return fail(EVG_ERR_INVALID, "n_edges > 0 but dep_off/dep_idx null");
   if (D == 0 && T != 0) return fail(EVG_ERR_INVALID, "tasks without distros");
   std::vector<int64_t> unit_base(size_t(D) + 1, 0), dtile_off(size_t(D) + 1, 0);
-  std::vector<int32_t> tile_distro;
+  std::vector<int32_t> tile_distro, listA, listB, listC;
   std::vector<int64_t> tile_start;
+  std::vector<uint8_t> route(size_t(D) + 1, 0);
+  int32_t n_general = 0;
+  int general_complex = 0;
   int any_complex = E > 0 ? 1 : 0;
   for (int32_t d = 0; d < D; d++) {
     const int64_t a = dt->task_off[d], b = dt->task_off[d + 1];
@@ -809,7 +809,17 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt) 
     if (cf.n_versions < 0) return fail(EVG_ERR_INVALID, "distro %d: negative n_versions", d);
     if (gb > ga || cf.group_versions) any_complex = 1;
     unit_base[d + 1] = unit_base[d] + (gb - ga) + (cf.group_versions ? int64_t(cf.n_versions) : (b - a));
-    for (int64_t s = a; s < b; s += kTile) { tile_distro.push_back(d); tile_start.push_back(s); }
+    // route: small distros are planned on-chip by k_plan_smem, the rest by the general path
+    const int64_t n = b - a;
+    if (n <= kCapA) { listA.push_back(d); route[d] = 1; }
+    else if (n <= kCapB) { listB.push_back(d); route[d] = 1; }
+    else if (n <= kCapC) { listC.push_back(d); route[d] = 1; }
+    else {
+      n_general++;
+      const int64_t de = (E > 0) ? (t->dep_off[b] - t->dep_off[a]) : 0;
+      if (gb > ga || cf.group_versions || de > 0) general_complex = 1;
+      for (int64_t s = a; s < b; s += kTile) { tile_distro.push_back(d); tile_start.push_back(s); }
+    }
     dtile_off[d + 1] = int64_t(tile_distro.size());
   }
   if (D > 0 && dt->task_off[D] != T) return fail(EVG_ERR_INVALID, "task_off[n_distros] != n_tasks");
@@ -846,6 +856,10 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt) 
   UP(c->b_tiledistro, tile_distro.data(), NT, int32_t);
   UP(c->b_tilestart, tile_start.data(), NT, int64_t);
   UP(c->b_dtileoff, dtile_off.data(), D + 1, int64_t);
+  UP(c->b_route, route.data(), D + 1, uint8_t);
+  UP(c->b_listA, listA.data(), int64_t(listA.size()), int32_t);
+  UP(c->b_listB, listB.data(), int64_t(listB.size()), int32_t);
+  UP(c->b_listC, listC.data(), int64_t(listC.size()), int32_t);
   // the staging vectors above must outlive the async copies
   CK(cudaStreamSynchronize(s));
   // work buffers
@@ -855,8 +869,8 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt) 
     CK(c->b_next.ensure(sizeof(uint32_t) * size_t(P + 1)));
     CK(c->b_pslot.ensure(sizeof(uint32_t) * size_t(P + 1)));
     CK(c->b_etask.ensure(sizeof(uint32_t) * size_t(E + 1)));
+    CK(c->b_elive.ensure(size_t(E) + 1));
     CK(c->b_cv.ensure(sizeof(int64_t) * size_t(P + 1)));
-    CK(c->b_cm.ensure(sizeof(uint32_t) * size_t(P + 1)));
     CK(c->b_ca.ensure(sizeof(uint32_t) * size_t(P + 1)));
     CK(c->b_crk.ensure(sizeof(uint32_t) * size_t(P + 1)));
     CK(c->b_bestpair.ensure(sizeof(uint32_t) * size_t(T + 1)));
@@ -877,6 +891,9 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt) 
   CK(c->b_tv.ensure(sizeof(int64_t) * size_t(T + 1)));
   c->T = T; c->E = E; c->G = G; c->U = U; c->NT = NT; c->Dn = D;
   c->any_complex = any_complex;
+  c->nA = int32_t(listA.size()); c->nB = int32_t(listB.size()); c->nC = int32_t(listC.size());
+  c->n_general = n_general;
+  c->general_complex = general_complex;
   c->have_tasks = true;
   c->have_hosts = false;
   return EVG_OK;
@@ -927,7 +944,8 @@ DWork dwork(const evg_ctx* c) {
   DWork w;
   w.has_dep = c->b_hasdep.as<uint8_t>(); w.head = c->b_head.as<uint32_t>(); w.next = c->b_next.as<uint32_t>();
   w.pair_slot = c->b_pslot.as<uint32_t>(); w.edge_task = c->b_etask.as<uint32_t>();
-  w.cand_v = c->b_cv.as<int64_t>(); w.cand_m = c->b_cm.as<uint32_t>(); w.cand_a = c->b_ca.as<uint32_t>();
+  w.edge_live = c->b_elive.as<uint8_t>(); w.route = c->b_route.as<uint8_t>();
+  w.cand_v = c->b_cv.as<int64_t>(); w.cand_a = c->b_ca.as<uint32_t>();
   w.cand_rk = c->b_crk.as<uint32_t>(); w.best_pair = c->b_bestpair.as<uint32_t>();
   for (int k = 0; k < 2; k++) {
     w.buf[k].key_s = c->b_ks[k].as<uint64_t>(); w.buf[k].key_v = c->b_kv[k].as<uint64_t>(); w.buf[k].idx = c->b_ix[k].as<uint32_t>();
@@ -964,6 +982,18 @@ int run_alloc(evg_ctx* c, int64_t now) {
   return EVG_OK;
 }
 
+template <int THREADS, int ITEMS, int MIN_CTAS>
+int launch_smem(evg_ctx* c, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n, int64_t now,
+                int want_best_pair) {
+  if (n <= 0) return EVG_OK;
+  const size_t bytes = PlanSmem<THREADS, ITEMS>::kBytes;
+  CK(cudaFuncSetAttribute(k_plan_smem<THREADS, ITEMS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+  k_plan_smem<THREADS, ITEMS, MIN_CTAS><<<unsigned(n), THREADS, bytes, c->stream>>>(dt, dd, w, list, now, want_best_pair,
+                                                                          c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
+  c->launches++;
+  return EVG_OK;
+}
+
 int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
   const int64_t T = c->T, E = c->E, P = 2 * T + E;
   const int32_t D = c->Dn;
@@ -978,37 +1008,49 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
     bd = c->b_bd.as<int64_t>();
     c->bd_valid = true;
   }
-  CK(cudaMemsetAsync(c->b_qinfo.p, 0, sizeof(evg_queue_info) * size_t(D + 1), s));
+  const bool general = c->n_general > 0;
+  if (general) CK(cudaMemsetAsync(c->b_qinfo.p, 0, sizeof(evg_queue_info) * size_t(D + 1), s));
   CK(cudaMemsetAsync(c->b_ginfo.p, 0, sizeof(evg_group_info) * size_t(c->G + 1), s));
-  CK(cudaMemsetAsync(c->b_maxpass.p, 0, sizeof(int32_t) * 4, s));
-  if (D == 0 || T == 0) {
-    LAUNCH(c, k_finalize_info, grid_for(std::max<int64_t>(D, c->G), 256), 256, dd, w, c->G);
-    CK(cudaGetLastError());
+  if (c->timed) CK(cudaEventRecord(c->ev_sort0, s));
+  if (D == 0) {
+    if (c->timed) CK(cudaEventRecord(c->ev_sort1, s));
     return EVG_OK;
   }
-  if (c->any_complex) {
-    CK(cudaMemsetAsync(c->b_hasdep.p, 0, size_t(T) + 1, s));
-    CK(cudaMemsetAsync(c->b_head.p, 0xFF, sizeof(uint32_t) * size_t(c->U + 1), s));
-    CK(cudaMemsetAsync(c->b_next.p, 0xFF, sizeof(uint32_t) * size_t(P + 1), s));
-    if (E > 0) LAUNCH(c, k_mark_dependents, grid_for(T, 256), 256, dt, dd, w);
+  if (general) {
+    CK(cudaMemsetAsync(c->b_maxpass.p, 0, sizeof(int32_t) * 4, s));
+    if (c->general_complex) {
+      CK(cudaMemsetAsync(c->b_hasdep.p, 0, size_t(T) + 1, s));
+      CK(cudaMemsetAsync(c->b_head.p, 0xFF, sizeof(uint32_t) * size_t(c->U + 1), s));
+      CK(cudaMemsetAsync(c->b_next.p, 0xFF, sizeof(uint32_t) * size_t(P + 1), s));
+    }
   }
-  LAUNCH(c, k_init_bits, grid_for(D, 256), 256, w.bits, D);
-  LAUNCH(c, k_task, grid_for(T, 256), 256, dt, dd, w, now, c->any_complex);
-  if (c->any_complex) {
-    LAUNCH(c, k_unit, grid_for(P, 256), 256, dt, dd, w, now, P);
-    LAUNCH(c, k_best, grid_for(T, 256), 256, dt, dd, w);
-  }
-  if (c->timed) CK(cudaEventRecord(c->ev_sort0, s));
-  LAUNCH(c, k_sched, grid_for(D, 128), 128, dd, w, c->any_complex);
-  const int passes = c->any_complex ? kMaxPass : 8;
-  for (int j = 0; j < passes; j++) {
-    LAUNCH(c, k_sort_hist, unsigned(c->NT), 256, j, dd, w);
-    LAUNCH(c, k_sort_scan, unsigned(D), 256, j, dd, w);
-    LAUNCH(c, k_sort_scatter, unsigned(c->NT), 256, j, dd, w);
-  }
+  // on-chip planner: one CTA per distro, three capacity classes
+  const int wbp = bd ? 1 : 0;
+  int rc;
+  if ((rc = launch_smem<1024, 12, 1>(c, dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now, wbp)) != EVG_OK) return rc;
+  if ((rc = launch_smem<256, 16, 3>(c, dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now, wbp)) != EVG_OK) return rc;
+  if ((rc = launch_smem<128, 8, 8>(c, dt, dd, w, c->b_listA.as<int32_t>(), c->nA, now, wbp)) != EVG_OK) return rc;
   if (c->timed) CK(cudaEventRecord(c->ev_sort1, s));
-  LAUNCH(c, k_emit, grid_for(T, 256), 256, dt, dd, w, now, c->any_complex, c->b_order.as<int32_t>(), c->b_tv.as<int64_t>(), bd);
-  LAUNCH(c, k_finalize_info, grid_for(std::max<int64_t>(D, c->G), 256), 256, dd, w, c->G);
+  if (general) {
+    const int gc = c->general_complex;
+    if (gc && E > 0) LAUNCH(c, k_mark_dependents, grid_for(T, 256), 256, dt, dd, w);
+    LAUNCH(c, k_init_bits, grid_for(D, 256), 256, w.bits, D);
+    LAUNCH(c, k_task, grid_for(T, 256), 256, dt, dd, w, now, gc);
+    if (gc) {
+      LAUNCH(c, k_unit, grid_for(P, 256), 256, dt, dd, w, now, P);
+      LAUNCH(c, k_best, grid_for(T, 256), 256, dt, dd, w);
+    }
+    LAUNCH(c, k_sched, grid_for(D, 128), 128, dd, w, gc);
+    const int passes = gc ? kMaxPass : 8;
+    for (int j = 0; j < passes; j++) {
+      LAUNCH(c, k_sort_hist, unsigned(c->NT), 256, j, dd, w);
+      LAUNCH(c, k_sort_scan, unsigned(D), 256, j, dd, w);
+      LAUNCH(c, k_sort_scatter, unsigned(c->NT), 256, j, dd, w);
+    }
+    LAUNCH(c, k_emit, grid_for(T, 256), 256, dt, dd, w, c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
+    LAUNCH(c, k_finalize_info, grid_for(std::max<int64_t>(D, c->G), 256), 256, dd, w, c->G);
+  }
+  if (bd) LAUNCH(c, k_breakdown, grid_for(T, 256), 256, dt, dd, w, now, c->any_complex, c->b_order.as<int32_t>(), bd);
   CK(cudaGetLastError());
   return EVG_OK;
 }
@@ -1050,7 +1092,7 @@ void evg_shutdown(evg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->b_prio, &c->b_exp, &c->b_qb, &c->b_wb, &c->b_nd, &c->b_tgo, &c->b_gid, &c->b_vid, &c->b_flags,
                    &c->b_depoff, &c->b_depidx, &c->b_taskoff, &c->b_groupoff, &c->b_cfg, &c->b_gmax, &c->b_unitbase,
-                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_cv, &c->b_cm, &c->b_ca, &c->b_crk,
+                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_route, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_cv, &c->b_ca, &c->b_crk,
                    &c->b_bestpair, &c->b_ks[0], &c->b_ks[1], &c->b_kv[0], &c->b_kv[1], &c->b_ix[0], &c->b_ix[1], &c->b_bits,
                    &c->b_npass, &c->b_sched, &c->b_maxpass, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
@@ -1084,7 +1126,6 @@ int evg_run_resident(evg_ctx* c, int64_t now_ns, uint32_t opts) {
   CK(cudaEventRecord(c->ev_begin, c->stream));
   int rc = run_plan(c, now_ns, opts);
   if (rc != EVG_OK) return rc;
-  if (c->T == 0 || c->Dn == 0) { CK(cudaEventRecord(c->ev_sort0, c->stream)); CK(cudaEventRecord(c->ev_sort1, c->stream)); }
   if (c->have_hosts) {
     rc = run_alloc(c, now_ns);
     if (rc != EVG_OK) return rc;

@@ -195,12 +195,13 @@ EVG_HD int64_t unit_value(const UnitAcc& a, const evg_distro_cfg& c, int64_t* bd
 EVG_HD uint64_t enc_value(int64_t v) { return ~(uint64_t(v) ^ 0x8000000000000000ULL); }
 EVG_HD int64_t dec_value(uint64_t k) { return int64_t((~k) ^ 0x8000000000000000ULL); }
 
-// Canonical tie word: smallest member index, anchor (smallest primary member
-// index), rank inside the unit; 21 bits each (distros hold < 2^21 tasks).
+// Canonical tie word: anchor of the unit the task is emitted from (smallest
+// input index among the unit's primary members -- unique per unit), then the
+// task's rank inside that unit; 21 bits each (distros hold < 2^21 tasks).
 constexpr int kIdxBits = 21;
 constexpr int64_t kMaxTasksPerDistro = (int64_t(1) << kIdxBits) - 1;
-EVG_HD uint64_t enc_tie(uint32_t min_member, uint32_t anchor, uint32_t rank_in_unit) {
-  return (uint64_t(min_member) << (2 * kIdxBits)) | (uint64_t(anchor) << kIdxBits) | uint64_t(rank_in_unit);
+EVG_HD uint64_t enc_tie(uint32_t anchor, uint32_t rank_in_unit) {
+  return (uint64_t(anchor) << kIdxBits) | uint64_t(rank_in_unit);
 }
 
 // TaskList.Less (planner.go:387-405) extended by input index: true when task x

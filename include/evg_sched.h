@@ -17,9 +17,10 @@
  * Determinism: `now_ns` replaces every time.Now()/time.Since on the path
  * (planner.go:318-322, scheduler.go:123, utilization_based_host_allocator.go:360).
  * Ties the reference leaves to map order / unstable sort are broken by the
- * canonical policy of DESIGN.md §3 (units: TotalValue desc, smallest member
- * index asc, smallest primary-member index asc; tasks in a unit: the
- * TaskList.Less chain, then input index asc).
+ * canonical policy of DESIGN.md §3 (units: TotalValue desc, then the unit's
+ * anchor -- the smallest input index among the tasks whose own key the unit is
+ * filed under -- asc; tasks in a unit: the TaskList.Less chain, then input
+ * index asc).
  *
  * There is no CPU fallback: every compute entry point fails with
  * EVG_ERR_CUDA when no sm_100 device is usable.

@@ -254,14 +254,14 @@ PlanResult plan(const View& v, const evo_planner_settings& s, int64_t now) {
     r.units.push_back(std::move(pu));
   }
   // TaskPlan.Export planner.go:462-481 with the canonical tie policy:
-  // units: TotalValue desc, then smallest member input index asc, then anchor asc.
+  // units: TotalValue desc, then anchor asc (anchor = smallest input index among the
+  // tasks that SetDistro'd the unit; every task anchors exactly one unit, so this is total).
   std::vector<size_t> uo(r.units.size());
   for (size_t k = 0; k < uo.size(); k++) uo[k] = k;
   std::sort(uo.begin(), uo.end(), [&](size_t a, size_t b) {
     const PlannedUnit &A = r.units[a], &B = r.units[b];
     if (A.bd[EVO_BD_TOTAL_VALUE] != B.bd[EVO_BD_TOTAL_VALUE])
       return A.bd[EVO_BD_TOTAL_VALUE] > B.bd[EVO_BD_TOTAL_VALUE];
-    if (A.min_member != B.min_member) return A.min_member < B.min_member;
     return A.anchor < B.anchor;
   });
   std::vector<uint8_t> emitted(v.n, 0);
@@ -653,7 +653,7 @@ void evo_job_batch(const evo_tasks* t, const int64_t* task_off, const evo_hosts*
                    const evo_planner_settings* ps, const evo_alloc_settings* as, const char* const* distro_ids,
                    int64_t n_distros, int64_t now, int32_t n_threads, int32_t* out_order, int64_t* out_total_value,
                    evo_queue_info* out_info, int64_t* out_new, int64_t* out_free, int32_t* out_status,
-                   evo_group_info* out_groups) {
+                   evo_group_info* out_groups, int64_t* out_bd) {
   std::atomic<int64_t> next{0};
   auto worker = [&]() {
     for (;;) {
@@ -664,6 +664,7 @@ void evo_job_batch(const evo_tasks* t, const int64_t* task_off, const evo_hosts*
       for (size_t k = 0; k < r.order.size(); k++) {
         out_order[task_off[d] + k] = int32_t(r.order[k]);
         out_total_value[task_off[d] + k] = r.units[r.unit_of_rank[k]].bd[EVO_BD_TOTAL_VALUE];
+        if (out_bd) std::memcpy(out_bd + (task_off[d] + int64_t(k)) * EVO_BD_N, r.units[r.unit_of_rank[k]].bd, sizeof(int64_t) * EVO_BD_N);
       }
       QueueInfo q = queue_info(v, r.order.data(), int64_t(r.order.size()), distro_ids ? distro_ids[d] : "",
                                target_time(ps[d]), ps[d].includes_dependencies != 0, now);

@@ -199,7 +199,8 @@ void evo_job_batch(const evo_tasks* t, const int64_t* task_off, const evo_hosts*
                    const evo_alloc_settings* as, const char* const* distro_ids, int64_t n_distros,
                    int64_t now, int32_t n_threads, int32_t* out_order, int64_t* out_total_value,
                    evo_queue_info* out_info, int64_t* out_new, int64_t* out_free, int32_t* out_status,
-                   evo_group_info* out_groups /* may be NULL; distro d's infos at slot task_off[d]+d.. */);
+                   evo_group_info* out_groups /* may be NULL; distro d's infos at slot task_off[d]+d.. */,
+                   int64_t* out_bd /* may be NULL; EVO_BD_N values per ranked task */);
 
 #ifdef __cplusplus
 }

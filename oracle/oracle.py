@@ -498,15 +498,18 @@ class SoAJob:
         st = np.zeros(max(D, 1), dtype=np.int32)
         have_hosts = self.hosts is not None
         groups = np.zeros(n + D + 1, dtype=GROUP_DTYPE)
+        bd = np.zeros((max(n, 1), BD_N), dtype=np.int64)
         lib().evo_job_batch(C.byref(self.tasks), C.c_void_p(self.task_off.ctypes.data),
                             C.byref(self.hosts) if have_hosts else None,
                             C.c_void_p(self.host_off.ctypes.data) if have_hosts else None,
                             self.ps, self.alloc if have_hosts else None, self.distro_ids, C.c_int64(D), C.c_int64(now),
                             C.c_int32(threads), C.c_void_p(order.ctypes.data), C.c_void_p(tv.ctypes.data),
                             C.c_void_p(info.ctypes.data), C.c_void_p(new.ctypes.data), C.c_void_p(free.ctypes.data),
-                            C.c_void_p(st.ctypes.data), C.c_void_p(groups.ctypes.data))
+                            C.c_void_p(st.ctypes.data), C.c_void_p(groups.ctypes.data),
+                            C.c_void_p(bd.ctypes.data))
         return {"order": order[:n], "total_value": tv[:n], "info": info[:D], "new_hosts": new[:D],
-                "free_hosts": free[:D], "status": st[:D], "task_off": self.task_off, "groups": groups}
+                "free_hosts": free[:D], "status": st[:D], "task_off": self.task_off, "groups": groups,
+                "breakdown": bd[:n]}
 
     def groups_by_id(self, result, j: int, soa_group_id: np.ndarray):
         """TaskGroupInfos of selected distro j keyed by the SoA group id (-1 = the "" bucket)."""
