@@ -404,14 +404,14 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       __syncwarp();
     }
     __syncthreads();
-    if (tid < 256) {
+    for (int dgt = tid; dgt < 256; dgt += THREADS) {
       uint32_t run = 0;
       for (int w = 0; w < NW; w++) {
-        const uint32_t x = sWc[w * 256 + tid];
-        sWc[w * 256 + tid] = uint16_t(run);
+        const uint32_t x = sWc[w * 256 + dgt];
+        sWc[w * 256 + dgt] = uint16_t(run);
         run += x;
       }
-      sTot[tid] = run;
+      sTot[dgt] = run;
     }
     __syncthreads();
     if (warp == 0) {  // exclusive scan of the 256 digit totals

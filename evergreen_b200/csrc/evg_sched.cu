@@ -629,10 +629,9 @@ __global__ void k_finalize_info(DDistros D, DWork W, int64_t n_groups_total) {
   if (i < n_groups_total) W.ginfo[i].max_hosts = D.gmax[i];
 }
 
-// UtilizationBasedHostAllocator for one distro per thread
-// (utilization_based_host_allocator.go:26-130 and the helpers it calls).
-// FP64 sums run in host-index order (the canonical order; the reference's
-// channel order is nondeterministic, allocator.go:381-391).
+// UtilizationBasedHostAllocator (utilization_based_host_allocator.go:26-130 and
+// the helpers it calls).  FP64 sums run in host-index order (the canonical
+// order; the reference's channel order is nondeterministic, allocator.go:381-391).
 struct GroupScratch {
   int32_t n_hosts;
   int32_t n_free;
@@ -664,19 +663,25 @@ __device__ int eval_group(const evg_alloc_cfg& c, const evg_group_info& info, in
   return EVG_ALLOC_OK;
 }
 
-__global__ void k_alloc(DHosts H, int32_t n_distros, const int64_t* group_off, const evg_queue_info* qinfo,
-                        evg_group_info* ginfo, GroupScratch* gs, int64_t now, evg_alloc_result* result,
-                        int32_t* status) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= n_distros) return;
+// One warp per distro.  Hosts are walked in index order by the whole warp; the
+// lane that owns a bucket (lane 0 for "", lane g%32 for group g) does that
+// bucket's updates, so every bucket's FP64 sum is accumulated in host order
+// while buckets proceed in parallel.  Groups are then evaluated 32 at a time;
+// the per-group results are integers, so the warp reduction is exact.
+__global__ void __launch_bounds__(128) k_alloc(DHosts H, int32_t n_distros, const int64_t* group_off,
+                                               const evg_queue_info* qinfo, evg_group_info* ginfo, GroupScratch* gs,
+                                               int64_t now, evg_alloc_result* result, int32_t* status) {
+  const int d = int((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  if (d >= n_distros) return;  // warp-uniform
   const evg_alloc_cfg c = H.cfg[d];
   const evg_queue_info qi = qinfo[d];
   const int64_t threshold = qi.max_duration_threshold;
   const int64_t h0 = H.host_off[d], h1 = H.host_off[d + 1];
   const int64_t g0 = group_off[d], g1 = group_off[d + 1];
   const int64_t n_existing = h1 - h0;
-  // one ordered pass over the hosts: IsFree count (allocator.go:33-37), bucket
-  // sizes (groupByTaskGroup :223-260) and the soon-to-be-free sums (:324-394)
+  // IsFree count (allocator.go:33-37), bucket sizes (groupByTaskGroup :223-260), soon-to-be-free sums (:324-394)
   int64_t n_free_all = 0, u_hosts = 0, u_free = 0;
   double u_soon = 0.0;
   for (int64_t h = h0; h < h1; h++) {
@@ -684,48 +689,52 @@ __global__ void k_alloc(DHosts H, int32_t n_distros, const int64_t* group_off, c
     const int32_t g = H.gid[h];
     const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
     n_free_all += is_free;
-    double term = 0.0;
     const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
-    if (running) term = soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction);
     if (g == EVG_HG_NONE) {
-      u_hosts++;
-      u_free += is_free;
-      if (running) u_soon = fadd64(u_soon, term);
-    } else if (g >= 0 && g < g1 - g0) {
+      if (lane == 0) {
+        u_hosts++;
+        u_free += is_free;
+        if (running) u_soon = fadd64(u_soon, soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction));
+      }
+    } else if (g >= 0 && g < g1 - g0 && (g & 31) == lane) {
       GroupScratch* s = gs + g0 + g;
       s->n_hosts++;
       s->n_free += is_free;
-      if (running) s->soon = fadd64(s->soon, term);
+      if (running) s->soon = fadd64(s->soon, soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction));
     }
   }
-  int64_t deficit = qi.expected_duration;
+  __syncwarp();
   int32_t st = EVG_ALLOC_OK;
   int64_t n_new = 0, n_free_out = n_free_all;
   if (c.provider != EVG_PROVIDER_DOCKER && n_existing >= c.maximum_hosts) {
     n_new = 0;  // allocator.go:39-48
   } else if (c.disabled) {
-    n_new = int64_t(c.minimum_hosts) - n_existing;
-    if (n_new < 0) n_new = 0;  // allocator.go:51-66
+    n_new = int64_t(c.minimum_hosts) - n_existing;  // allocator.go:51-66
+    if (n_new < 0) n_new = 0;
   } else {
     int64_t required = 0, free_approx = 0;
-    // "" bucket exists when there are standalone tasks queued or hosts bucketed under ""
-    if (qi.has_ungrouped || u_hosts > 0) {
+    // "" bucket exists when standalone tasks are queued or hosts are bucketed under ""
+    if (lane == 0 && (qi.has_ungrouped || u_hosts > 0)) {
       int64_t n, f;
       st = eval_group(c, qi.ungrouped, threshold, c.maximum_hosts, u_hosts, u_free, u_soon, &n, &f);
       required += n;
       free_approx += f;
     }
-    for (int64_t g = g0; g < g1 && st == EVG_ALLOC_OK; g++) {
+    for (int64_t g = g0 + lane; g < g1; g += 32) {
       evg_group_info* gi = ginfo + g;
       if (gi->count == 0) continue;  // allocator.go:84-86
       int64_t n, f;
-      st = eval_group(c, *gi, threshold, gi->max_hosts, gs[g].n_hosts, gs[g].n_free, gs[g].soon, &n, &f);
-      if (st != EVG_ALLOC_OK) break;
+      const int e = eval_group(c, *gi, threshold, gi->max_hosts, gs[g].n_hosts, gs[g].n_free, gs[g].soon, &n, &f);
+      if (e != EVG_ALLOC_OK) { st = max(st, e); continue; }
       required += n;
       free_approx += f;
-      gi->count_free = f;       // allocator.go:107-110
+      gi->count_free = f;  // allocator.go:107-110
       gi->count_required = n;
     }
+    // a data error is distro-wide (fraction, parent) or the pool-size check of some group: any lane's error wins
+    st = __reduce_max_sync(full, st);
+    required = warp_sum64(required);
+    free_approx = warp_sum64(free_approx);
     if (st == EVG_ALLOC_OK) {
       if (required + n_free_all > qi.length_with_dependencies_met) required = qi.length_with_dependencies_met - n_free_all;
       if (required < 0) required = 0;
@@ -738,12 +747,14 @@ __global__ void k_alloc(DHosts H, int32_t n_distros, const int64_t* group_off, c
       n_free_out = n_free_all;
     }
   }
-  deficit = wsub(deficit, wmul(n_free_out, threshold));
-  if (deficit < 0) deficit = 0;
-  result[d].new_hosts = int32_t(n_new);
-  result[d].free_hosts = int32_t(n_free_out);
-  result[d].deficit_ns = deficit;
-  status[d] = st;
+  if (lane == 0) {
+    int64_t deficit = wsub(qi.expected_duration, wmul(n_free_out, threshold));
+    if (deficit < 0) deficit = 0;
+    result[d].new_hosts = int32_t(n_new);
+    result[d].free_hosts = int32_t(n_free_out);
+    result[d].deficit_ns = deficit;
+    status[d] = st;
+  }
 }
 
 // --------------------------------------------------------------------------
@@ -976,7 +987,7 @@ int run_alloc(evg_ctx* c, int64_t now) {
   if (c->ext_result && c->ext_capacity < c->Dn) return fail(EVG_ERR_INVALID, "bound result buffer holds %lld rows, need %d", (long long)c->ext_capacity, c->Dn);
   CK(c->b_gs.ensure(sizeof(GroupScratch) * size_t(c->G + 1)));
   CK(cudaMemsetAsync(c->b_gs.p, 0, sizeof(GroupScratch) * size_t(c->G + 1), c->stream));
-  LAUNCH(c, k_alloc, grid_for(c->Dn, 128), 128, h, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
+  LAUNCH(c, k_alloc, grid_for(int64_t(c->Dn) * 32, 128), 128, h, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
          c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>());
   CK(cudaGetLastError());
   return EVG_OK;
