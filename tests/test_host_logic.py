@@ -1,0 +1,148 @@
+"""Host-side logic of the shim mirror (no GPU): marshalling, dependency and
+duration restatements against the oracle, sharding, the synthetic generator."""
+import random
+
+import numpy as np
+import pytest
+
+from evergreen_b200 import _lib as L
+from evergreen_b200 import dist as edist
+from evergreen_b200 import model as M
+from evergreen_b200 import soa as S
+from evergreen_b200 import synth
+from oracle import oracle as O
+
+NOW = synth.NOW_NS
+
+
+def random_tasks(rng, n, n_ext=5):
+    tasks = []
+    for i in range(n):
+        t = M.Task(id=f"t{i}", version=f"v{rng.randrange(3)}", project="p", build_variant=f"bv{rng.randrange(2)}",
+                   priority=rng.choice([0, 0, 1, 50, -1]), requester=rng.choice(["gitter_request", "patch_request",
+                   "github_pull_request", "github_merge_request", "ad_hoc", "trigger_request"]),
+                   activated_by=rng.choice(["", "stepback", "user"]), generate_task=rng.random() < 0.1,
+                   num_dependents=rng.randrange(4), distro_id=rng.choice(["d", "d", "other"]),
+                   activated_time=rng.choice([M.ZERO_TIME, 0, NOW - rng.randrange(10 ** 13)]),
+                   ingest_time=rng.choice([M.ZERO_TIME, NOW - rng.randrange(10 ** 13)]),
+                   scheduled_time=rng.choice([M.ZERO_TIME, NOW - rng.randrange(10 ** 12)]),
+                   dependencies_met_time=rng.choice([M.ZERO_TIME, M.ZERO_TIME, 0, NOW - rng.randrange(10 ** 12)]),
+                   override_dependencies=rng.random() < 0.1)
+        if rng.random() < 0.3:
+            t.task_group, t.task_group_max_hosts, t.task_group_order = f"tg{rng.randrange(2)}", rng.randrange(1, 4), rng.randrange(5)
+        for _ in range(rng.choice([0, 0, 1, 2])):
+            target = rng.choice([f"t{rng.randrange(n)}", f"ext{rng.randrange(n_ext)}", "missing"])
+            t.depends_on.append(M.Dependency(target, status=rng.choice(["", "success", "failed", "*"]),
+                                             unattainable=rng.random() < 0.1))
+        tasks.append(t)
+    db = {f"ext{k}": M.Task(id=f"ext{k}", status=rng.choice(["success", "failed", "undispatched", "started"]),
+                            depends_on=[M.Dependency("x", unattainable=rng.random() < 0.5)]) for k in range(n_ext)}
+    return tasks, db
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_dependencies_met_restatement_matches_oracle(seed):
+    rng = random.Random(seed)
+    tasks, db = random_tasks(rng, 60)
+    by_id = {t.id: t for t in tasks}
+    mine = [S.dependencies_met(t, by_id, db) for t in tasks]
+    assert mine == O.deps_met(tasks, NOW, db).tolist()
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_marshal_tasks_columns(seed):
+    rng = random.Random(100 + seed)
+    tasks, db = random_tasks(rng, 50)
+    d = M.Distro(id="d", dispatcher_settings=M.DispatcherSettings(M.DISPATCHER_VERSION_REVISED_WITH_DEPENDENCIES))
+    soa, table, keys = S.marshal_tasks([(d, tasks)], NOW, db)
+    assert soa.n_tasks == 50 and table.n_distros == 1 and int(table.cfg[0]["includes_dependencies"]) == 1
+    names = keys[0].group_names
+    for i, t in enumerate(tasks):
+        g = int(soa.group_id[i])
+        assert (g == -1) == (t.task_group == "")
+        if g >= 0:
+            assert names[g] == t.get_task_group_string()
+            assert int(table.group_max_hosts[g]) == tasks[[x.get_task_group_string() if x.task_group else None for x in tasks].index(names[g])].task_group_max_hosts
+        assert keys[0].versions[int(soa.version_id[i])] == t.version
+        qb = t.activated_time if t.activated_time != M.ZERO_TIME else t.ingest_time
+        assert int(soa.queue_basis_ns[i]) == qb
+        assert int(soa.wait_basis_ns[i]) == max(t.scheduled_time, t.dependencies_met_time)
+        fl = int(soa.flags[i])
+        assert (fl & 3) == (2 if t.requester == "github_merge_request" else 1 if t.requester in ("patch_request", "github_pull_request") else 0)
+        assert bool(fl & L.EVG_TF_GENERATE) == t.generate_task
+        assert bool(fl & L.EVG_TF_STEPBACK) == (t.activated_by == "stepback")
+        assert bool(fl & L.EVG_TF_OTHER_DISTRO) == (t.distro_id != "d")
+        assert int(soa.expected_ns[i]) == M.DEFAULT_TASK_DURATION
+    # in-queue edges only, in DependsOn order
+    if soa.dep_idx is not None:
+        for i, t in enumerate(tasks):
+            want = [int(x.task_id[1:]) for x in t.depends_on if x.task_id.startswith("t")]
+            assert soa.dep_idx[int(soa.dep_off[i]):int(soa.dep_off[i + 1])].tolist() == want
+
+
+def test_fetch_expected_duration_restatement_matches_oracle():
+    rng = random.Random(3)
+    for _ in range(300):
+        t = M.Task(id="x", expected_duration=rng.choice([0, 0, 5 * M.MINUTE]), expected_duration_std_dev=rng.choice([0, M.MINUTE]),
+                   duration_prediction=M.CachedDurationValue(value=rng.choice([0, 7 * M.MINUTE]), std_dev=rng.choice([0, M.SECOND]),
+                                                             ttl=rng.choice([0, M.HOUR, 24 * M.HOUR]),
+                                                             collected_at=rng.choice([M.ZERO_TIME, NOW, NOW - 2 * M.HOUR, NOW - 9 * M.HOUR])))
+        hist = rng.choice([None, (0, 0), (13 * M.MINUTE, 2 * M.MINUTE)])
+        import copy
+        want = O.fetch_expected_duration(copy.deepcopy(t), NOW, hist)
+        assert M.fetch_expected_duration(t, NOW, hist) == want
+
+
+def test_marshal_hosts_buckets_like_group_by_task_group():
+    infos = [M.TaskGroupInfo("g1_bv_p_v", count=2), M.TaskGroupInfo("", count=1), M.TaskGroupInfo("g2_bv_p_v", count=1)]
+    hosts = [M.Host("h0"), M.Host("h1", running_task="a", running_task_group="g1", running_task_build_variant="bv",
+                                  running_task_project="p", running_task_version="v"),
+             M.Host("h2", running_task="b"), M.Host("h3", running_task_group="g1"),
+             M.Host("h4", running_task="c", running_task_group="gone"),
+             M.Host("h5", task_group_teardown_start_time=5)]
+    qi = M.DistroQueueInfo(task_group_infos=infos)
+    data = M.HostAllocatorData(M.Distro(id="d", provider="ec2-fleet"), hosts, qi,
+                               running_tasks={"a": M.RunningTaskStats(True, 10, 1, NOW - 5), "b": M.RunningTaskStats(False)})
+    q, g, goff, names = S.queue_info_rows([qi])
+    assert names == [["g1_bv_p_v", "g2_bv_p_v"]] and int(q[0]["has_ungrouped"]) == 1 and goff.tolist() == [0, 2]
+    h = S.marshal_hosts([data], names)
+    assert h.group_id.tolist() == [-1, 0, -1, -1, -2, -1]
+    assert h.flags.tolist() == [0, L.EVG_HF_RUNNING | L.EVG_HF_RT_FOUND, L.EVG_HF_RUNNING, 0, L.EVG_HF_RUNNING, L.EVG_HF_TEARDOWN]
+    buckets = O.group_by_task_group(hosts, infos)
+    assert sorted(buckets) == ["", "g1_bv_p_v", "g2_bv_p_v", "gone___"]
+    assert buckets["g1_bv_p_v"][0] == [1] and buckets[""][0] == [0, 2, 3, 5]
+
+
+def test_lpt_partition():
+    rng = synth.Rng(5)
+    sizes = synth.power_law_sizes(rng, 3000)
+    for world in (1, 2, 4, 8):
+        sh = edist.lpt_partition(sizes, world)
+        assert sorted(np.concatenate(sh.members).tolist()) == list(range(3000))
+        assert np.array_equal(sh.load, [int(sizes[m].sum()) for m in sh.members])
+        for r, m in enumerate(sh.members):
+            assert np.all(sh.owner[m] == r) and np.array_equal(sh.slot[m], np.arange(len(m)))
+        assert sh.load.max() <= max(sizes.max(), int(np.ceil(sizes.sum() / world)) + sizes.max())
+    sh = edist.lpt_partition(np.full(16, 10), 8)
+    assert sh.load.tolist() == [20] * 8
+    sh = edist.lpt_partition([100, 1, 1, 1], 2)
+    assert sorted(sh.load.tolist()) == [3, 100]
+
+
+def test_synth_is_deterministic_and_well_formed():
+    a, b = synth.config(5, 0.01), synth.config(5, 0.01)
+    for name, _ in a.tasks.COLUMNS:
+        assert np.array_equal(getattr(a.tasks, name), getattr(b.tasks, name))
+    t, d = a.tasks, a.distros
+    sizes = np.diff(d.task_off)
+    distro_of = np.repeat(np.arange(d.n_distros), sizes)
+    assert np.all(t.group_id < (d.group_off[1:] - d.group_off[:-1])[distro_of])
+    assert np.all(t.version_id < d.cfg["n_versions"][distro_of])
+    assert np.all(t.dep_idx < sizes[distro_of][np.repeat(np.arange(t.n_tasks), np.diff(t.dep_off))])
+    # a task group lives in one version
+    key = distro_of[t.group_id >= 0].astype(np.int64) * (1 << 32) + t.group_id[t.group_id >= 0]
+    ver = t.version_id[t.group_id >= 0]
+    order = np.argsort(key, kind="stable")
+    same = key[order][1:] == key[order][:-1]
+    assert np.all(ver[order][1:][same] == ver[order][:-1][same])
+    assert a.algorithmic_bytes() == 60 * t.n_tasks + 4 * t.n_edges + 28 * a.hosts.n_hosts + 96 * d.n_groups + 16 * d.n_distros
