@@ -239,19 +239,38 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     W.qinfo[d] = q;
   }
 
-  // ---- phase 3/4: multi-member units (Unit.info, score, first-occurrence choice) ----
+  // ---- phase 3: multi-member units (Unit.info + score once per unit, then each member's rank) ----
   if (any) {
+    // 3a: the pair at the head of a unit's list owns the unit: one walk for Unit.info / value / anchor
+    auto unit_head = [&](uint32_t p) {
+      const uint32_t slot = W.pair_slot[p];
+      if (W.head[slot] != p) return;
+      UnitAcc a;
+      acc_init(a);
+      uint32_t anchor = kNoAnchor;
+      for (uint32_t q = p; q < kEnd; q = W.next[q]) {
+        const uint32_t tq = pair_task(T, W, q);
+        acc_add(a, now, T.priority[tq], T.expected[tq], T.qbasis[tq], T.numdep[tq], T.gid[tq], T.flags[tq]);
+        if (q < uint32_t(T.n)) anchor = min(anchor, uint32_t(tq - base));  // own-key pairs are the SetDistro members (planner.go:446)
+      }
+      W.unit_v[slot] = unit_value(a, cfg, nullptr);
+      W.unit_a[slot] = anchor;  // kNoAnchor: never got a distro -> not exported (planner.go:81-83)
+      W.unit_n[slot] = uint32_t(a.n);
+      W.unit_mask[slot] = 0ull;
+    };
     for (int i = tid; i < tn; i += THREADS) {
       const int64_t t = base + i;
       const int32_t gid = T.gid[t];
       const bool own_complex = gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31)));
-      if (own_complex) eval_pair(T, W, cfg, now, uint32_t(t), uint32_t(t), base);
-      if (gid >= 0 && gv) eval_pair(T, W, cfg, now, uint32_t(T.n + t), uint32_t(t), base);
+      if (own_complex) unit_head(uint32_t(t));
+      if (gid >= 0 && gv) unit_head(uint32_t(T.n + t));
       if (has_edges)
         for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++)
-          if (W.edge_live[e]) eval_pair(T, W, cfg, now, uint32_t(2 * T.n + e), uint32_t(t), base);
+          if (W.edge_live[e]) unit_head(uint32_t(2 * T.n + e));
     }
     __syncthreads();
+    // 3b + 4: rank of the task inside each unit it belongs to (TaskList.Less), then the best unit
+    // (first occurrence in TaskPlan.Export, planner.go:467-477)
     for (int i = tid; i < tn; i += THREADS) {
       const int64_t t = base + i;
       const int32_t gid = T.gid[t];
@@ -259,18 +278,33 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       const bool has_ver = gid >= 0 && gv;
       const int64_t e0 = has_edges ? T.dep_off[t] : 0, e1 = has_edges ? T.dep_off[t + 1] : 0;
       if (!own_complex && !has_ver && e1 == e0) continue;  // emitted from its own single-task unit
+      const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
+      const int64_t my_ex = T.expected[t];
       bool have = false;
       int64_t bv = 0;
-      uint32_t ba = 0, brk = 0, bp = kInactive;
-      auto consider = [&](int64_t v, uint32_t a, uint32_t rk, uint32_t pair) {
+      uint32_t ba = 0, bslot = 0, bp = kInactive;
+      auto consider = [&](uint32_t p) {
+        const uint32_t slot = W.pair_slot[p];
+        const uint32_t a = W.unit_a[slot];
         if (a == kNoAnchor) return;
-        if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; brk = rk; bp = pair; }
+        const int64_t v = W.unit_v[slot];
+        if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; bslot = slot; bp = p; }
       };
-      if (!own_complex) consider(sV[i], uint32_t(i), 0, kInactive);
-      else consider(W.cand_v[t], W.cand_a[t], W.cand_rk[t], uint32_t(t));
-      if (has_ver) { const int64_t pv = T.n + t; consider(W.cand_v[pv], W.cand_a[pv], W.cand_rk[pv], uint32_t(pv)); }
+      if (!own_complex) { have = true; bv = sV[i]; ba = uint32_t(i); }
+      else consider(uint32_t(t));
+      if (has_ver) consider(uint32_t(T.n + t));
       for (int64_t e = e0; e < e1; e++)
-        if (W.edge_live[e]) { const int64_t pe = 2 * T.n + e; consider(W.cand_v[pe], W.cand_a[pe], W.cand_rk[pe], uint32_t(pe)); }
+        if (W.edge_live[e]) consider(uint32_t(2 * T.n + e));
+      uint32_t brk = 0;
+      if (bp != kInactive) {  // rank among ALL members of the chosen unit
+        for (uint32_t q = W.head[bslot]; q < kEnd; q = W.next[q]) {
+          const uint32_t tq = pair_task(T, W, q);
+          if (in_unit_less(T.tgo[tq], T.numdep[tq], T.priority[tq], T.expected[tq], uint32_t(tq - base),
+                           my_tgo, my_nd, my_pr, my_ex, uint32_t(i))) brk++;
+        }
+        // units of up to 64 members publish which ranks they emit, so phase 6 needs no second walk
+        if (W.unit_n[bslot] <= 64) atomicOr(&W.unit_mask[bslot], 1ull << brk);
+      }
       sV[i] = bv;
       sA[i] = uint16_t(ba);
       sRk[i] = uint16_t(brk);
@@ -333,10 +367,14 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       if (sDisp[i >> 5] & (1u << (i & 31))) {
         // offset among the tasks emitted from the same unit: members with the same best anchor and a smaller rank
         const uint32_t myrk = sRk[i];
-        const uint32_t bp = W.best_pair[base + i];
-        for (uint32_t q = W.head[W.pair_slot[bp]]; q < kEnd; q = W.next[q]) {
-          const uint32_t lq = uint32_t(pair_task(T, W, q) - base);
-          if (sA[lq] == a && sRk[lq] < myrk) pos++;
+        const uint32_t slot = W.pair_slot[W.best_pair[base + i]];
+        if (W.unit_n[slot] <= 64) {
+          pos += __popcll(W.unit_mask[slot] & ((1ull << myrk) - 1ull));
+        } else {
+          for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
+            const uint32_t lq = uint32_t(pair_task(T, W, q) - base);
+            if (sA[lq] == a && sRk[lq] < myrk) pos++;
+          }
         }
       }
       sIdx[pos] = uint16_t(i);

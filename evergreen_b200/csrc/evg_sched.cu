@@ -131,6 +131,10 @@ struct DWork {
   int64_t* cand_v;       // [2T+E]
   uint32_t* cand_a;      // [2T+E]
   uint32_t* cand_rk;     // [2T+E]
+  int64_t* unit_v;       // [unit slots] on-chip path: TotalValue of the unit
+  uint32_t* unit_a;      // [unit slots] anchor
+  uint32_t* unit_n;      // [unit slots] member count
+  unsigned long long* unit_mask;  // [unit slots] ranks emitted from the unit (units of <= 64 members)
   uint32_t* best_pair;   // [T]
   SortBuf buf[2];
   unsigned long long* bits;  // [D*4]: orS, andS, orV, andV
@@ -775,7 +779,7 @@ struct evg_ctx {
   DevBuf b_prio, b_exp, b_qb, b_wb, b_nd, b_tgo, b_gid, b_vid, b_flags, b_depoff, b_depidx;
   DevBuf b_taskoff, b_groupoff, b_cfg, b_gmax, b_unitbase;
   DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_cv, b_ca, b_crk, b_bestpair;
-  DevBuf b_route, b_listA, b_listB, b_listC;
+  DevBuf b_route, b_listA, b_listB, b_listC, b_unitv, b_unita, b_unitn, b_unitmask;
   int32_t nA = 0, nB = 0, nC = 0, n_general = 0;  // distros per on-chip class / general path
   int general_complex = 0;
   DevBuf b_ks[2], b_kv[2], b_ix[2], b_bits, b_npass, b_sched, b_maxpass;
@@ -881,6 +885,10 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt) 
     CK(c->b_pslot.ensure(sizeof(uint32_t) * size_t(P + 1)));
     CK(c->b_etask.ensure(sizeof(uint32_t) * size_t(E + 1)));
     CK(c->b_elive.ensure(size_t(E) + 1));
+    CK(c->b_unitv.ensure(sizeof(int64_t) * size_t(U + 1)));
+    CK(c->b_unita.ensure(sizeof(uint32_t) * size_t(U + 1)));
+    CK(c->b_unitn.ensure(sizeof(uint32_t) * size_t(U + 1)));
+    CK(c->b_unitmask.ensure(sizeof(uint64_t) * size_t(U + 1)));
     CK(c->b_cv.ensure(sizeof(int64_t) * size_t(P + 1)));
     CK(c->b_ca.ensure(sizeof(uint32_t) * size_t(P + 1)));
     CK(c->b_crk.ensure(sizeof(uint32_t) * size_t(P + 1)));
@@ -956,6 +964,8 @@ DWork dwork(const evg_ctx* c) {
   w.has_dep = c->b_hasdep.as<uint8_t>(); w.head = c->b_head.as<uint32_t>(); w.next = c->b_next.as<uint32_t>();
   w.pair_slot = c->b_pslot.as<uint32_t>(); w.edge_task = c->b_etask.as<uint32_t>();
   w.edge_live = c->b_elive.as<uint8_t>(); w.route = c->b_route.as<uint8_t>();
+  w.unit_v = c->b_unitv.as<int64_t>(); w.unit_a = c->b_unita.as<uint32_t>(); w.unit_n = c->b_unitn.as<uint32_t>();
+  w.unit_mask = c->b_unitmask.as<unsigned long long>();
   w.cand_v = c->b_cv.as<int64_t>(); w.cand_a = c->b_ca.as<uint32_t>();
   w.cand_rk = c->b_crk.as<uint32_t>(); w.best_pair = c->b_bestpair.as<uint32_t>();
   for (int k = 0; k < 2; k++) {
@@ -1103,7 +1113,7 @@ void evg_shutdown(evg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->b_prio, &c->b_exp, &c->b_qb, &c->b_wb, &c->b_nd, &c->b_tgo, &c->b_gid, &c->b_vid, &c->b_flags,
                    &c->b_depoff, &c->b_depidx, &c->b_taskoff, &c->b_groupoff, &c->b_cfg, &c->b_gmax, &c->b_unitbase,
-                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_route, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_cv, &c->b_ca, &c->b_crk,
+                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita, &c->b_unitn, &c->b_unitmask, &c->b_route, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_cv, &c->b_ca, &c->b_crk,
                    &c->b_bestpair, &c->b_ks[0], &c->b_ks[1], &c->b_kv[0], &c->b_kv[1], &c->b_ix[0], &c->b_ix[1], &c->b_bits,
                    &c->b_npass, &c->b_sched, &c->b_maxpass, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,

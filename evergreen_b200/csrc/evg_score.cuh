@@ -142,6 +142,22 @@ EVG_HD void acc_add(UnitAcc& a, int64_t now, int32_t priority, int64_t expected_
   a.n += 1;
 }
 
+// int64(math.Floor(d.Minutes() / float64(n))) and int64(d.Hours()) as the reference
+// computes them (planner.go:230,239,256).  For small non-negative d the FP64 expression
+// provably equals the integer quotient q: the fraction r/unit is at most 1 - 1/unit
+// (1 - 1.7e-11 for minutes, 1 - 2.8e-13 for hours); below 2^15 minutes doubles are spaced
+// 2^-38 = 3.6e-12 and below 2^10 hours 2^-43 = 1.1e-13, both finer than the gap to q + 1,
+// so fl(q + frac) < q + 1 and floor/trunc give q; x / 1.0 == x exactly.  Everything else
+// takes the literal FP64 path (tests/native/score_fastpath_check.cpp brute-forces this).
+EVG_HD int64_t floor_minutes_over(int64_t d, int64_t n) {
+  if (n == 1 && d >= 0 && d < (int64_t(1) << 15) * kMinute) return d / kMinute;
+  return d2i_floor(fdiv64(dur_minutes(d), i2d(n)));
+}
+EVG_HD int64_t trunc_hours(int64_t d) {
+  if (d >= 0 && d < (int64_t(1) << 10) * kHour) return d / kHour;
+  return d2i_trunc(dur_hours(d));
+}
+
 // unitInfo.value (planner.go:209-300).  Returns TotalValue; when bd != nullptr
 // also writes the 13-field breakdown (EVG_BD_*), bookkeeping quirks included.
 EVG_HD int64_t unit_value(const UnitAcc& a, const evg_distro_cfg& c, int64_t* bd) {
@@ -166,16 +182,16 @@ EVG_HD int64_t unit_value(const UnitAcc& a, const evg_distro_cfg& c, int64_t* bd
   int64_t r_patch = 0, r_patch_wait = 0, r_cq = 0, r_main = 0, r_step = 0;
   if (pat) {
     r_patch = factor(c.patch_factor);
-    r_patch_wait = wmul(factor(c.patch_time_in_queue_factor), d2i_floor(fdiv64(dur_minutes(a.tiq), i2d(len))));
+    r_patch_wait = wmul(factor(c.patch_time_in_queue_factor), floor_minutes_over(a.tiq, len));
   } else if (mq) {
     r_cq = factor(c.commit_queue_factor);
   } else {
-    const int64_t avg = a.tiq / len;
-    if (avg < kWeek) r_main = wmul(factor(c.mainline_time_in_queue_factor), d2i_trunc(dur_hours(kWeek - avg)));
+    const int64_t avg = len == 1 ? a.tiq : a.tiq / len;
+    if (avg < kWeek) r_main = wmul(factor(c.mainline_time_in_queue_factor), trunc_hours(kWeek - avg));
     if (a.flags & UF_STEPBACK) r_step = factor(c.stepback_task_factor);
   }
   const int64_t r_deps = d2i_trunc(fmul64(factor_d(c.num_dependents_factor), i2d(a.max_d)));
-  const int64_t r_rt = wmul(factor(c.expected_runtime_factor), d2i_floor(fdiv64(dur_minutes(a.rt), i2d(len))));
+  const int64_t r_rt = wmul(factor(c.expected_runtime_factor), floor_minutes_over(a.rt, len));
   int64_t rank = 1;
   rank = wadd(rank, r_patch); rank = wadd(rank, r_patch_wait); rank = wadd(rank, r_main);
   rank = wadd(rank, r_cq); rank = wadd(rank, r_step); rank = wadd(rank, r_deps); rank = wadd(rank, r_rt);

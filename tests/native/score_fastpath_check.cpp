@@ -1,0 +1,29 @@
+// Host check: the integer fast paths of evg_score.cuh equal the literal FP64 formulas.
+#include <cstdio>
+#include <initializer_list>
+#include <cstdlib>
+#include <cmath>
+#include "evergreen_b200/csrc/evg_score.cuh"
+using namespace evg;
+static int64_t ref_floor_minutes_over(int64_t d, int64_t n) { return int64_t(std::floor((double(d / kMinute) + double(d % kMinute) / (60.0 * 1e9)) / double(n))); }
+static int64_t ref_trunc_hours(int64_t d) { return int64_t(double(d / kHour) + double(d % kHour) / (3600.0 * 1e9)); }
+int main() {
+  uint64_t x = 88172645463325252ULL; long bad = 0; long n = 0;
+  auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  for (int it = 0; it < 20000000; it++) {
+    int64_t q = int64_t(rnd() % (uint64_t(1) << 15));
+    int64_t r; switch (rnd() % 4) { case 0: r = kMinute - 1 - int64_t(rnd() % 3); break; case 1: r = int64_t(rnd() % 3); break; default: r = int64_t(rnd() % uint64_t(kMinute)); }
+    int64_t d = q * kMinute + r;
+    if (floor_minutes_over(d, 1) != ref_floor_minutes_over(d, 1)) bad++;
+    int64_t rh; switch (rnd() % 4) { case 0: rh = kHour - 1 - int64_t(rnd() % 3); break; case 1: rh = int64_t(rnd() % 3); break; default: rh = int64_t(rnd() % uint64_t(kHour)); }
+    int64_t dh = (q % 2048) * kHour + rh;
+    if (trunc_hours(dh) != ref_trunc_hours(dh)) bad++;
+    n += 2;
+  }
+  // boundaries
+  for (int64_t q : {int64_t(0), int64_t(1), (int64_t(1) << 15) - 1}) for (int64_t r : {int64_t(0), kMinute - 1}) {
+    int64_t d = q * kMinute + r; if (floor_minutes_over(d, 1) != ref_floor_minutes_over(d, 1)) bad++;
+  }
+  printf("checked %ld, mismatches %ld\n", n, bad);
+  return bad != 0;
+}

@@ -146,3 +146,16 @@ def test_synth_is_deterministic_and_well_formed():
     same = key[order][1:] == key[order][:-1]
     assert np.all(ver[order][1:][same] == ver[order][:-1][same])
     assert a.algorithmic_bytes() == 60 * t.n_tasks + 4 * t.n_edges + 28 * a.hosts.n_hosts + 96 * d.n_groups + 16 * d.n_distros
+
+
+def test_score_fast_paths_equal_the_fp64_formulas(tmp_path):
+    """evg_score.cuh replaces Duration.Minutes()/Hours() FP64 arithmetic by integer quotients on a proven
+    range; brute-force the equivalence on the host (same header the kernels compile)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "check"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", root, "-o", str(exe),
+                           os.path.join(root, "tests", "native", "score_fastpath_check.cpp")])
+    out = subprocess.check_output([str(exe)]).decode()
+    assert "mismatches 0" in out, out
