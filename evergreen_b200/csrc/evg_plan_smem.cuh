@@ -29,6 +29,7 @@ struct PlanShared {
   uint32_t ub;
   unsigned long long vmax_enc, vmin_enc;   // encoded so that atomicMax / atomicMin work on unsigned
   int32_t n_displaced;
+  unsigned int n_list;
   // queue-info block accumulators
   unsigned int c[10];
   unsigned long long s[4];
@@ -64,7 +65,7 @@ __device__ __forceinline__ void eval_pair(const DTasks& T, const DWork& W, const
 
 template <int THREADS, int ITEMS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
-k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int64_t now, int want_best_pair,
+k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int64_t now,
             int32_t* __restrict__ order, int64_t* __restrict__ total_value) {
   constexpr int CAP = THREADS * ITEMS;
   constexpr int NW = THREADS / 32;
@@ -102,6 +103,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     S->vmax_enc = 0ull;
     S->vmin_enc = ~0ull;
     S->n_displaced = 0;
+    S->n_list = 0;
     for (int k = 0; k < 10; k++) S->c[k] = 0;
     for (int k = 0; k < 4; k++) S->s[k] = 0;
   }
@@ -135,68 +137,58 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     __syncthreads();
   }
 
-  // ---- phase 2: per task -- queue info, unit links, score of single-task units ----
+  // ---- phase 2: per task -- queue info, score of single-task units; tasks that touch a
+  // multi-member unit (task group, GroupVersions, in-queue dependency either way) are
+  // compacted into a work list so the list phases below run with full warps ----
+  uint16_t* sList = sWc;                      // free until the sort
+  constexpr int kListCap = NW * 256;
   unsigned int c_dm = 0, c_mq = 0, c_over = 0, c_wait = 0, c_sec = 0, u_n = 0, u_cnt = 0, u_over = 0, u_wait = 0, u_mq = 0;
   int64_t s_exp = 0, s_over = 0, s_uexp = 0, s_uover = 0;
   const int64_t threshold = cfg.target_time_ns;
-  for (int i = tid; i < tn; i += THREADS) {
-    const int64_t t = base + i;
-    const int32_t prio = T.priority[t], nd = T.numdep[t], gid = T.gid[t], vid = T.vid[t];
-    const int64_t exp_ns = T.expected[t], qb = T.qbasis[t], wb = T.wbasis[t];
-    const uint32_t fl = T.flags[t];
-    // GetDistroQueueInfo (scheduler.go:66-138)
-    const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
-    const bool counted = !cfg.includes_dependencies || dm;
-    const bool over = counted && exp_ns > threshold;
-    const bool wait_over = counted && dm && since(now, wb) > threshold;
-    const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
-    c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += (fl & EVG_TF_OTHER_DISTRO) != 0;
-    if (counted) s_exp += exp_ns;
-    if (over) s_over += exp_ns;
-    if (gid < 0) {
-      u_n += 1; u_cnt += counted; u_over += over; u_wait += wait_over; u_mq += mq_dm;
-      if (counted) s_uexp += exp_ns;
-      if (over) s_uover += exp_ns;
-    } else {
-      evg_group_info* g = W.ginfo + D.group_off[d] + gid;
-      atomic_add64(&g->count, counted);
-      atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
-      atomic_add64(&g->count_duration_over_threshold, over);
-      atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
-      atomic_add64(&g->count_wait_over_threshold, wait_over);
-      atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
+  for (int i0 = 0; i0 < tn; i0 += THREADS) {
+    const int i = i0 + tid;
+    bool complex_task = false;
+    if (i < tn) {
+      const int64_t t = base + i;
+      const int32_t prio = T.priority[t], nd = T.numdep[t], gid = T.gid[t];
+      const int64_t exp_ns = T.expected[t], qb = T.qbasis[t], wb = T.wbasis[t];
+      const uint32_t fl = T.flags[t];
+      // GetDistroQueueInfo (scheduler.go:66-138)
+      const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
+      const bool counted = !cfg.includes_dependencies || dm;
+      const bool over = counted && exp_ns > threshold;
+      const bool wait_over = counted && dm && since(now, wb) > threshold;
+      const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
+      c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += (fl & EVG_TF_OTHER_DISTRO) != 0;
+      if (counted) s_exp += exp_ns;
+      if (over) s_over += exp_ns;
+      if (gid < 0) {
+        u_n += 1; u_cnt += counted; u_over += over; u_wait += wait_over; u_mq += mq_dm;
+        if (counted) s_uexp += exp_ns;
+        if (over) s_uover += exp_ns;
+      }
+      const bool own_complex = any && (gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31))));
+      complex_task = own_complex || (has_edges && T.dep_off[t + 1] > T.dep_off[t]);
+      sA[i] = uint16_t(i);
+      sRk[i] = 0;
+      if (!own_complex) {  // unit == {this task}: planner.go:209-337 in registers
+        UnitAcc a;
+        acc_init(a);
+        acc_add(a, now, prio, exp_ns, qb, nd, gid, fl);
+        sV[i] = unit_value(a, cfg, nullptr);
+      }
     }
-    // units (planner.go:431-447)
-    const bool own_complex = any && (gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31))));
-    sA[i] = uint16_t(i);
-    sRk[i] = 0;
-    if (!own_complex) {
-      UnitAcc a;
-      acc_init(a);
-      acc_add(a, now, prio, exp_ns, qb, nd, gid, fl);
-      sV[i] = unit_value(a, cfg, nullptr);
-    }
-    if (any) {
-      const uint32_t s_own = own_slot_local(gid, vid, uint32_t(i), ng, gv);
-      const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
-      if (own_complex) link_pair(W, uint32_t(t), ub + s_own);
-      if (s_ver != kInactive) link_pair(W, uint32_t(T.n + t), ub + s_ver);
-      if (has_edges) {
-        const int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
-        for (int64_t e = e0; e < e1; e++) {
-          const uint32_t dl = uint32_t(T.dep_idx[e]);
-          const uint32_t s = own_slot_local(T.gid[base + dl], T.vid[base + dl], dl, ng, gv);
-          bool dup = (s == s_own) || (s == s_ver);  // Unit.Add is keyed by task id (planner.go:131)
-          for (int64_t f = e0; f < e && !dup; f++) {
-            const uint32_t fl2 = uint32_t(T.dep_idx[f]);
-            dup = own_slot_local(T.gid[base + fl2], T.vid[base + fl2], fl2, ng, gv) == s;
-          }
-          W.edge_task[e] = uint32_t(t);
-          W.edge_live[e] = dup ? 0 : 1;
-          if (!dup) link_pair(W, uint32_t(2 * T.n + e), ub + s);
+    if (any) {  // warp-aggregated append
+      const unsigned m = __ballot_sync(full, complex_task);
+      if (m) {
+        unsigned int pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(&S->n_list, (unsigned int)__popc(m));
+        pos0 = __shfl_sync(full, pos0, 0);
+        if (complex_task) {
+          const unsigned int pos = pos0 + __popc(m & ((1u << lane) - 1u));
+          if (pos < (unsigned)kListCap) sList[pos] = uint16_t(i);
         }
       }
-      if (want_best_pair) W.best_pair[t] = kInactive;
     }
   }
   // fold the queue-info partials: warp shuffle, then shared atomics, then one writer
@@ -239,9 +231,65 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     W.qinfo[d] = q;
   }
 
-  // ---- phase 3: multi-member units (Unit.info + score once per unit, then each member's rank) ----
+  // The list phases iterate the compacted work list (or, if it overflowed, every task with a filter).
+  const int n_list = int(S->n_list);
+  const bool use_list = n_list <= kListCap;
+  const int n_work = !any ? 0 : (use_list ? n_list : tn);
+  auto work_item = [&](int k) -> int {
+    if (use_list) return int(sList[k]);
+    const int64_t t = base + k;
+    const bool cx = T.gid[t] >= 0 || gv || (sHasDep[k >> 5] & (1u << (k & 31))) ||
+                    (has_edges && T.dep_off[t + 1] > T.dep_off[t]);
+    return cx ? k : -1;
+  };
+
   if (any) {
-    // 3a: the pair at the head of a unit's list owns the unit: one walk for Unit.info / value / anchor
+    // ---- phase 2b: task-group sums (scheduler.go:79-137) and unit membership links (planner.go:431-456) ----
+    for (int k = tid; k < n_work; k += THREADS) {
+      const int i = work_item(k);
+      if (i < 0) continue;
+      const int64_t t = base + i;
+      const int32_t gid = T.gid[t], vid = T.vid[t];
+      if (gid >= 0) {
+        const int64_t exp_ns = T.expected[t];
+        const uint32_t fl = T.flags[t];
+        const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
+        const bool counted = !cfg.includes_dependencies || dm;
+        const bool over = counted && exp_ns > threshold;
+        const bool wait_over = counted && dm && since(now, T.wbasis[t]) > threshold;
+        const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
+        evg_group_info* g = W.ginfo + D.group_off[d] + gid;
+        atomic_add64(&g->count, counted);
+        atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
+        atomic_add64(&g->count_duration_over_threshold, over);
+        atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
+        atomic_add64(&g->count_wait_over_threshold, wait_over);
+        atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
+      }
+      const bool own_complex = gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31)));
+      const uint32_t s_own = own_slot_local(gid, vid, uint32_t(i), ng, gv);
+      const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
+      if (own_complex) link_pair(W, uint32_t(t), ub + s_own);
+      if (s_ver != kInactive) link_pair(W, uint32_t(T.n + t), ub + s_ver);  // planner.go:439
+      if (has_edges) {
+        const int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
+        for (int64_t e = e0; e < e1; e++) {
+          const uint32_t dl = uint32_t(T.dep_idx[e]);
+          const uint32_t s = own_slot_local(T.gid[base + dl], T.vid[base + dl], dl, ng, gv);
+          bool dup = (s == s_own) || (s == s_ver);  // Unit.Add is keyed by task id (planner.go:131)
+          for (int64_t f = e0; f < e && !dup; f++) {
+            const uint32_t fl2 = uint32_t(T.dep_idx[f]);
+            dup = own_slot_local(T.gid[base + fl2], T.vid[base + fl2], fl2, ng, gv) == s;
+          }
+          W.edge_task[e] = uint32_t(t);
+          W.edge_live[e] = dup ? 0 : 1;
+          if (!dup) link_pair(W, uint32_t(2 * T.n + e), ub + s);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 3a: the pair at the head of a unit's list owns the unit: one walk for Unit.info / value / anchor ----
     auto unit_head = [&](uint32_t p) {
       const uint32_t slot = W.pair_slot[p];
       if (W.head[slot] != p) return;
@@ -258,7 +306,9 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       W.unit_n[slot] = uint32_t(a.n);
       W.unit_mask[slot] = 0ull;
     };
-    for (int i = tid; i < tn; i += THREADS) {
+    for (int k = tid; k < n_work; k += THREADS) {
+      const int i = work_item(k);
+      if (i < 0) continue;
       const int64_t t = base + i;
       const int32_t gid = T.gid[t];
       const bool own_complex = gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31)));
@@ -269,17 +319,17 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
           if (W.edge_live[e]) unit_head(uint32_t(2 * T.n + e));
     }
     __syncthreads();
-    // 3b + 4: rank of the task inside each unit it belongs to (TaskList.Less), then the best unit
-    // (first occurrence in TaskPlan.Export, planner.go:467-477)
-    for (int i = tid; i < tn; i += THREADS) {
+
+    // ---- phase 3b/4: the unit each task is emitted from (first occurrence in TaskPlan.Export,
+    // planner.go:467-477) and the task's rank inside it (TaskList.Less, planner.go:387-405) ----
+    for (int k = tid; k < n_work; k += THREADS) {
+      const int i = work_item(k);
+      if (i < 0) continue;
       const int64_t t = base + i;
       const int32_t gid = T.gid[t];
       const bool own_complex = gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31)));
       const bool has_ver = gid >= 0 && gv;
       const int64_t e0 = has_edges ? T.dep_off[t] : 0, e1 = has_edges ? T.dep_off[t + 1] : 0;
-      if (!own_complex && !has_ver && e1 == e0) continue;  // emitted from its own single-task unit
-      const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
-      const int64_t my_ex = T.expected[t];
       bool have = false;
       int64_t bv = 0;
       uint32_t ba = 0, bslot = 0, bp = kInactive;
@@ -297,6 +347,8 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
         if (W.edge_live[e]) consider(uint32_t(2 * T.n + e));
       uint32_t brk = 0;
       if (bp != kInactive) {  // rank among ALL members of the chosen unit
+        const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
+        const int64_t my_ex = T.expected[t];
         for (uint32_t q = W.head[bslot]; q < kEnd; q = W.next[q]) {
           const uint32_t tq = pair_task(T, W, q);
           if (in_unit_less(T.tgo[tq], T.numdep[tq], T.priority[tq], T.expected[tq], uint32_t(tq - base),
@@ -361,20 +413,22 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) { sE[tid * ITEMS + k] = uint16_t(run); run += loc[k]; }
     __syncthreads();
-    for (int i = tid; i < tn; i += THREADS) {
+    for (int i = tid; i < tn; i += THREADS)
+      if (!(sDisp[i >> 5] & (1u << (i & 31)))) sIdx[sE[sA[i]]] = uint16_t(i);  // rank 0 of its anchor
+    for (int k = tid; k < n_work; k += THREADS) {
+      const int i = work_item(k);
+      if (i < 0 || !(sDisp[i >> 5] & (1u << (i & 31)))) continue;
+      // offset among the tasks emitted from the same unit: members with the same best anchor and a smaller rank
       const uint32_t a = sA[i];
       uint32_t pos = sE[a];
-      if (sDisp[i >> 5] & (1u << (i & 31))) {
-        // offset among the tasks emitted from the same unit: members with the same best anchor and a smaller rank
-        const uint32_t myrk = sRk[i];
-        const uint32_t slot = W.pair_slot[W.best_pair[base + i]];
-        if (W.unit_n[slot] <= 64) {
-          pos += __popcll(W.unit_mask[slot] & ((1ull << myrk) - 1ull));
-        } else {
-          for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
-            const uint32_t lq = uint32_t(pair_task(T, W, q) - base);
-            if (sA[lq] == a && sRk[lq] < myrk) pos++;
-          }
+      const uint32_t myrk = sRk[i];
+      const uint32_t slot = W.pair_slot[W.best_pair[base + i]];
+      if (W.unit_n[slot] <= 64) {
+        pos += __popcll(W.unit_mask[slot] & ((1ull << myrk) - 1ull));
+      } else {
+        for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
+          const uint32_t lq = uint32_t(pair_task(T, W, q) - base);
+          if (sA[lq] == a && sRk[lq] < myrk) pos++;
         }
       }
       sIdx[pos] = uint16_t(i);

@@ -1004,12 +1004,11 @@ int run_alloc(evg_ctx* c, int64_t now) {
 }
 
 template <int THREADS, int ITEMS, int MIN_CTAS>
-int launch_smem(evg_ctx* c, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n, int64_t now,
-                int want_best_pair) {
+int launch_smem(evg_ctx* c, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n, int64_t now) {
   if (n <= 0) return EVG_OK;
   const size_t bytes = PlanSmem<THREADS, ITEMS>::kBytes;
   CK(cudaFuncSetAttribute(k_plan_smem<THREADS, ITEMS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
-  k_plan_smem<THREADS, ITEMS, MIN_CTAS><<<unsigned(n), THREADS, bytes, c->stream>>>(dt, dd, w, list, now, want_best_pair,
+  k_plan_smem<THREADS, ITEMS, MIN_CTAS><<<unsigned(n), THREADS, bytes, c->stream>>>(dt, dd, w, list, now,
                                                                           c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
   c->launches++;
   return EVG_OK;
@@ -1046,11 +1045,12 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
     }
   }
   // on-chip planner: one CTA per distro, three capacity classes
-  const int wbp = bd ? 1 : 0;
+  // breakdown mode reads best_pair for every task: tasks emitted from their own single-task unit keep kInactive
+  if (bd && c->any_complex) CK(cudaMemsetAsync(c->b_bestpair.p, 0xFF, sizeof(uint32_t) * size_t(T + 1), s));
   int rc;
-  if ((rc = launch_smem<1024, 12, 1>(c, dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now, wbp)) != EVG_OK) return rc;
-  if ((rc = launch_smem<256, 16, 3>(c, dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now, wbp)) != EVG_OK) return rc;
-  if ((rc = launch_smem<128, 8, 8>(c, dt, dd, w, c->b_listA.as<int32_t>(), c->nA, now, wbp)) != EVG_OK) return rc;
+  if ((rc = launch_smem<1024, 12, 1>(c, dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now)) != EVG_OK) return rc;
+  if ((rc = launch_smem<256, 16, 3>(c, dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now)) != EVG_OK) return rc;
+  if ((rc = launch_smem<128, 8, 8>(c, dt, dd, w, c->b_listA.as<int32_t>(), c->nA, now)) != EVG_OK) return rc;
   if (c->timed) CK(cudaEventRecord(c->ev_sort1, s));
   if (general) {
     const int gc = c->general_complex;

@@ -92,9 +92,10 @@ EVG_HD int64_t wmul(int64_t a, int64_t b) { return int64_t(uint64_t(a) * uint64_
 // time.Since(t) with a frozen clock; saturates like time.Time.Sub.
 EVG_HD int64_t since(int64_t now, int64_t t) {
   if (t == EVG_TIME_ZERO) return kI64Max;
-  if (t < 0 && now > kI64Max + t) return kI64Max;
-  if (t > 0 && now < kI64Min + t) return kI64Min;
-  return now - t;
+  const int64_t d = wsub(now, t);
+  // signed overflow of now - t: operands differ in sign and the result's sign differs from now's
+  if (((now ^ t) & (now ^ d)) < 0) return now < 0 ? kI64Min : kI64Max;
+  return d;
 }
 // time.Duration.Minutes() / Hours()
 EVG_HD double dur_minutes(int64_t d) { return fadd64(i2d(d / kMinute), fdiv64(i2d(d % kMinute), 60.0 * 1e9)); }

@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""Turn ncu artefacts brought back in gpurun_out/ into the committed summaries under profiles/.
+
+  python profiles/summarize.py launches gpurun_out/launches.csv  > profiles/rNN_launches.md
+  python profiles/summarize.py kernel   gpurun_out/prof.ncu-rep  > profiles/rNN_kernel.md
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    names = [(r["Kernel Name"].split("(")[0], float(r["Metric Value"].replace(",", ""))) for r in rows]
+    # one step = from one k_plan_smem/k_init_bits launch sequence start to the next k_alloc (inclusive)
+    ends = [i for i, (n, _) in enumerate(names) if n.startswith("k_alloc")]
+    print(f"# ncu launch list ({len(names)} launches; `--metrics gpu__time_duration.sum --clock-control none`)\n")
+    print("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n")
+    if len(ends) < 2:
+        seg = names
+    else:
+        seg = names[ends[-2] + 1: ends[-1] + 1]  # the last complete step
+    agg = collections.OrderedDict()
+    for n, v in seg:
+        a = agg.setdefault(n, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(v for _, v in agg.values())
+    print("| kernel | launches | time (us) | share |\n|---|---:|---:|---:|")
+    for n, (c, v) in agg.items():
+        print(f"| `{n}` | {c} | {v / 1e3:.1f} | {100 * v / tot:.1f}% |")
+    print(f"| **one tick** | {sum(c for c, _ in agg.values())} | {tot / 1e3:.1f} | 100% |")
+
+
+def kernel(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    keep = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.sum", "smsp__inst_executed.sum",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+            "launch__block_size", "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct",
+            "sm__inst_executed.avg.per_cycle_active", "smsp__issue_active.avg.pct"]
+    print(f"# ncu --set full: {m.get('Kernel Name', ('?', ''))[0][:90]}\n")
+    print("| metric | value | unit |\n|---|---:|---|")
+    for k in keep[1:]:
+        if k in m:
+            print(f"| `{k}` | {m[k][0]} | {m[k][1]} |")
+    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(src.splitlines()))
+    hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r]
+    if not hi:
+        return
+    hdr = rows[hi[0]]
+    ci, cs = hdr.index("Instructions Executed"), hdr.index("# Samples")
+    stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+    agg, cur = collections.OrderedDict(), None
+    for r in rows[hi[0] + 1:]:
+        if len(r) <= ci:
+            continue
+        if r[0] != "":
+            cur = (r[0], r[1].strip()[:95])
+            agg.setdefault(cur, [0, 0, collections.Counter()])
+            continue
+        if cur is None or r[2] in ("-", "..."):
+            continue
+        try:
+            ins, smp = int(r[ci]), int(r[cs])
+        except ValueError:
+            continue
+        agg[cur][0] += ins
+        agg[cur][1] += smp
+        for i, h in stall_cols:
+            try:
+                agg[cur][2][h] += int(r[i])
+            except ValueError:
+                pass
+    ti, ts = sum(v[0] for v in agg.values()), sum(v[1] for v in agg.values())
+    print(f"\nWarp-level instructions executed: {ti}; stall samples: {ts}\n")
+    print("Top source lines by stall samples:\n\n| line | samples | instr | top stalls | source |\n|---:|---:|---:|---|---|")
+    for (ln, s), (ins, smp, st) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+        tops = ", ".join(f"{k[6:]} {v}" for k, v in st.most_common(2))
+        print(f"| {ln} | {100 * smp / max(ts, 1):.1f}% | {100 * ins / max(ti, 1):.1f}% | {tops} | `{s.replace('|', '/')}` |")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])

@@ -24,6 +24,22 @@ int main() {
   for (int64_t q : {int64_t(0), int64_t(1), (int64_t(1) << 15) - 1}) for (int64_t r : {int64_t(0), kMinute - 1}) {
     int64_t d = q * kMinute + r; if (floor_minutes_over(d, 1) != ref_floor_minutes_over(d, 1)) bad++;
   }
+  // since(): saturating now - t against a 128-bit reference
+  auto ref_since = [](int64_t now, int64_t t) -> int64_t {
+    if (t == EVG_TIME_ZERO) return kI64Max;
+    __int128 d = (__int128)now - (__int128)t;
+    if (d > kI64Max) return kI64Max;
+    if (d < kI64Min) return kI64Min;
+    return int64_t(d);
+  };
+  const int64_t edges[] = {0, 1, -1, kI64Max, kI64Min, kI64Min + 1, kI64Max - 1, 1800000000000000000LL, -1800000000000000000LL};
+  for (int64_t a : edges) for (int64_t b : edges) { if (since(a, b) != ref_since(a, b)) bad++; n++; }
+  for (int it = 0; it < 2000000; it++) {
+    int64_t a = int64_t(rnd()), b = int64_t(rnd());
+    if (it & 1) { a >>= (rnd() % 40); b >>= (rnd() % 40); }
+    if (since(a, b) != ref_since(a, b)) bad++;
+    n++;
+  }
   printf("checked %ld, mismatches %ld\n", n, bad);
   return bad != 0;
 }

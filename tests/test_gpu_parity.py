@@ -190,7 +190,7 @@ def test_wide_value_range(engine):
     w = synth.make(np.array([9000, 700, 12000]), 31, zipf_priority=True, custom_factor_frac=1.0, tg_frac=0.1)
     for f in ("patch_time_in_queue_factor", "generate_task_factor", "expected_runtime_factor"):
         w.distros.cfg[f] = 100
-    w.tasks.priority[::7] = 100
+    w.tasks.priority[::7] = 1000
     po, _ = run(engine, w)
     assert int(po.total_value.max() - po.total_value.min()) > 2 ** 33
     parity.check_against_oracle(w, po, None)
