@@ -145,6 +145,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
   unsigned int c_dm = 0, c_mq = 0, c_over = 0, c_wait = 0, c_sec = 0, u_n = 0, u_cnt = 0, u_over = 0, u_wait = 0, u_mq = 0;
   int64_t s_exp = 0, s_over = 0, s_uexp = 0, s_uover = 0;
   const int64_t threshold = cfg.target_time_ns;
+  const PlannerFactors pf = clamp_factors(cfg);
   for (int i0 = 0; i0 < tn; i0 += THREADS) {
     const int i = i0 + tid;
     bool complex_task = false;
@@ -171,12 +172,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       complex_task = own_complex || (has_edges && T.dep_off[t + 1] > T.dep_off[t]);
       sA[i] = uint16_t(i);
       sRk[i] = 0;
-      if (!own_complex) {  // unit == {this task}: planner.go:209-337 in registers
-        UnitAcc a;
-        acc_init(a);
-        acc_add(a, now, prio, exp_ns, qb, nd, gid, fl);
-        sV[i] = unit_value(a, cfg, nullptr);
-      }
+      if (!own_complex) sV[i] = single_task_value(pf, now, prio, exp_ns, qb, nd, fl);  // unit == {this task}
     }
     if (any) {  // warp-aggregated append
       const unsigned m = __ballot_sync(full, complex_task);
@@ -488,12 +484,22 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     uint16_t* wc = sWc + warp * 256;
     for (int k = lane; k < 256; k += 32) wc[k] = 0;
     __syncwarp();
-    for (int s0 = seg0; s0 < seg1; s0 += 32) {
-      const int p = s0 + lane;
-      const uint32_t dg = p < seg1 ? ((kc[p] >> shift) & 255u) : 0xFFFFu;
-      const unsigned peers = __match_any_sync(full, dg);
-      if (dg != 0xFFFFu && (peers & lt) == 0) wc[dg] += uint16_t(__popc(peers));
-      __syncwarp();
+    // histogram of this warp's segment; 4 chunks of 32 in flight so the loads / MATCH overlap
+    for (int s0 = seg0; s0 < seg1; s0 += 128) {
+      uint32_t dg[4];
+      unsigned peers[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int p = s0 + u * 32 + lane;
+        dg[u] = p < seg1 ? ((kc[p] >> shift) & 255u) : 0xFFFFu;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) peers[u] = __match_any_sync(full, dg[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (dg[u] != 0xFFFFu && (peers[u] & lt) == 0) wc[dg[u]] += uint16_t(__popc(peers[u]));
+        __syncwarp();
+      }
     }
     __syncthreads();
     for (int dgt = tid; dgt < 256; dgt += THREADS) {
@@ -518,23 +524,33 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       for (int k = 0; k < 8; k++) { sTot[lane * 8 + k] = run; run += v[k]; }
     }
     __syncthreads();
-    for (int s0 = seg0; s0 < seg1; s0 += 32) {
-      const int p = s0 + lane;
-      const bool ok = p < seg1;
-      const uint32_t kk = ok ? kc[p] : 0u;
-      const uint16_t ii = ok ? ic[p] : uint16_t(0);
-      const uint32_t dg = ok ? ((kk >> shift) & 255u) : 0xFFFFu;
-      const unsigned peers = __match_any_sync(full, dg);
-      const uint32_t r = __popc(peers & lt);
-      uint32_t off = 0;
-      if (ok) off = wc[dg];
-      __syncwarp();
-      if (ok && r == 0) wc[dg] = uint16_t(off + __popc(peers));
-      __syncwarp();
-      if (ok) {
-        const uint32_t pos = sTot[dg] + off + r;
-        kn[pos] = kk;
-        in_[pos] = ii;
+    for (int s0 = seg0; s0 < seg1; s0 += 64) {
+      uint32_t kk[2], dg[2], r[2];
+      uint16_t ii[2];
+      unsigned peers[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int p = s0 + u * 32 + lane;
+        const bool ok = p < seg1;
+        kk[u] = ok ? kc[p] : 0u;
+        ii[u] = ok ? ic[p] : uint16_t(0);
+        dg[u] = ok ? ((kk[u] >> shift) & 255u) : 0xFFFFu;
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) { peers[u] = __match_any_sync(full, dg[u]); r[u] = __popc(peers[u] & lt); }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {  // chunks in order: stability
+        const bool ok = dg[u] != 0xFFFFu;
+        uint32_t off = 0;
+        if (ok) off = wc[dg[u]];
+        __syncwarp();
+        if (ok && r[u] == 0) wc[dg[u]] = uint16_t(off + __popc(peers[u]));
+        __syncwarp();
+        if (ok) {
+          const uint32_t pos = sTot[dg[u]] + off + r[u];
+          kn[pos] = kk[u];
+          in_[pos] = ii[u];
+        }
       }
     }
     __syncthreads();

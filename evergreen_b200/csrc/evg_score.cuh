@@ -151,11 +151,11 @@ EVG_HD void acc_add(UnitAcc& a, int64_t now, int32_t priority, int64_t expected_
 // so fl(q + frac) < q + 1 and floor/trunc give q; x / 1.0 == x exactly.  Everything else
 // takes the literal FP64 path (tests/native/score_fastpath_check.cpp brute-forces this).
 EVG_HD int64_t floor_minutes_over(int64_t d, int64_t n) {
-  if (n == 1 && d >= 0 && d < (int64_t(1) << 15) * kMinute) return d / kMinute;
+  if (n == 1 && d >= 0 && d < (int64_t(1) << 15) * kMinute) return int64_t(uint64_t(d) / uint64_t(kMinute));
   return d2i_floor(fdiv64(dur_minutes(d), i2d(n)));
 }
 EVG_HD int64_t trunc_hours(int64_t d) {
-  if (d >= 0 && d < (int64_t(1) << 10) * kHour) return d / kHour;
+  if (d >= 0 && d < (int64_t(1) << 10) * kHour) return int64_t(uint64_t(d) / uint64_t(kHour));
   return d2i_trunc(dur_hours(d));
 }
 
@@ -206,6 +206,51 @@ EVG_HD int64_t unit_value(const UnitAcc& a, const evg_distro_cfg& c, int64_t* bd
     bd[EVG_BD_R_STEPBACK] = r_step; bd[EVG_BD_R_PATCH] = r_patch; bd[EVG_BD_R_PATCH_WAIT] = r_patch_wait;
   }
   return total;
+}
+
+// Planner factors after the getters' "<= 0 -> 1" clamp (model/distro/distro.go:353-408),
+// hoisted out of the per-task path.
+struct PlannerFactors {
+  int64_t patch, patch_tiq, commit_queue, mainline_tiq, runtime, generate, stepback;
+  double num_dependents;
+};
+EVG_HD PlannerFactors clamp_factors(const evg_distro_cfg& c) {
+  PlannerFactors f;
+  f.patch = factor(c.patch_factor);
+  f.patch_tiq = factor(c.patch_time_in_queue_factor);
+  f.commit_queue = factor(c.commit_queue_factor);
+  f.mainline_tiq = factor(c.mainline_time_in_queue_factor);
+  f.runtime = factor(c.expected_runtime_factor);
+  f.generate = factor(c.generate_task_factor);
+  f.stepback = factor(c.stepback_task_factor);
+  f.num_dependents = factor_d(c.num_dependents_factor);
+  return f;
+}
+
+// unitInfo.value (planner.go:209-300) for the unit {one task that is not in a task group}:
+// the common case, with len == 1 and ContainsNonGroupTasks folded in.  Same arithmetic as
+// acc_add + unit_value; the parity tests compare both against the oracle.
+EVG_HD int64_t single_task_value(const PlannerFactors& f, int64_t now, int32_t priority, int64_t expected_ns,
+                                 int64_t queue_basis_ns, int32_t num_dependents, uint32_t tflags) {
+  const uint32_t req = tflags & EVG_TF_REQ_MASK;
+  const bool mq = req == EVG_TF_REQ_MERGE_QUEUE;
+  const int64_t tiq = queue_basis_ns == EVG_TIME_ZERO ? 0 : since(now, queue_basis_ns);
+  int64_t prio = wadd(1, priority > 0 ? int64_t(priority) : 0);
+  if (tflags & EVG_TF_GENERATE) prio = wmul(prio, f.generate);
+  if (mq) prio = wadd(prio, 200);
+  int64_t term;
+  if (req == EVG_TF_REQ_PATCH) {
+    term = wadd(f.patch, wmul(f.patch_tiq, floor_minutes_over(tiq, 1)));
+  } else if (mq) {
+    term = f.commit_queue;
+  } else {
+    term = tiq < kWeek ? wmul(f.mainline_tiq, trunc_hours(wsub(kWeek, tiq))) : 0;
+    if (tflags & EVG_TF_STEPBACK) term = wadd(term, f.stepback);
+  }
+  const int64_t r_deps = d2i_trunc(fmul64(f.num_dependents, i2d(num_dependents > 0 ? int64_t(num_dependents) : 0)));
+  const int64_t r_rt = wmul(f.runtime, floor_minutes_over(expected_ns, 1));
+  const int64_t rank = wadd(wadd(wadd(1, term), r_deps), r_rt);
+  return wadd(wmul(prio, rank), 1);
 }
 
 // Sort-key encoding: ascending unsigned order of enc_value(v) == descending v.

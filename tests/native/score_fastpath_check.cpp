@@ -40,6 +40,25 @@ int main() {
     if (since(a, b) != ref_since(a, b)) bad++;
     n++;
   }
+  // single_task_value == acc_add + unit_value for a lone non-task-group task
+  for (int it = 0; it < 3000000; it++) {
+    evg_distro_cfg c;
+    c.patch_factor = int64_t(rnd() % 120) - 10; c.patch_time_in_queue_factor = int64_t(rnd() % 120) - 10;
+    c.commit_queue_factor = int64_t(rnd() % 120) - 10; c.mainline_time_in_queue_factor = int64_t(rnd() % 120) - 10;
+    c.expected_runtime_factor = int64_t(rnd() % 120) - 10; c.generate_task_factor = int64_t(rnd() % 120) - 10;
+    c.stepback_task_factor = int64_t(rnd() % 120) - 10; c.num_dependents_factor = double(int64_t(rnd() % 1200) - 100) / 10.0;
+    c.target_time_ns = 0; c.group_versions = 0; c.includes_dependencies = 0; c.n_versions = 0; c._reserved = 0;
+    const int64_t now = 1800000000000000000LL;
+    int64_t qb;
+    switch (rnd() % 6) { case 0: qb = EVG_TIME_ZERO; break; case 1: qb = 0; break; case 2: qb = now + int64_t(rnd() % 1000000000000ULL); break;
+                         case 3: qb = now - int64_t(rnd() % (30ULL * 24 * 3600 * 1000000000ULL)); break; default: qb = now - int64_t(rnd() % (72ULL * 3600 * 1000000000ULL)); }
+    const int32_t prio = int32_t(rnd() % 1200) - 100, nd = int32_t(rnd() % 50) - 5;
+    const int64_t ex = (rnd() % 5 == 0) ? int64_t(rnd() % (1ULL << 58)) : int64_t(rnd() % (7200ULL * 1000000000ULL));
+    const uint32_t fl = uint32_t(rnd() % 3) | (rnd() % 8 == 0 ? EVG_TF_GENERATE : 0) | (rnd() % 8 == 0 ? EVG_TF_STEPBACK : 0);
+    UnitAcc a; acc_init(a); acc_add(a, now, prio, ex, qb, nd, -1, fl);
+    if (unit_value(a, c, nullptr) != single_task_value(clamp_factors(c), now, prio, ex, qb, nd, fl)) bad++;
+    n++;
+  }
   printf("checked %ld, mismatches %ld\n", n, bad);
   return bad != 0;
 }
