@@ -35,6 +35,15 @@ struct PlanShared {
   unsigned long long s[4];
 };
 
+// cp.async (LDGSTS): global -> shared without a register round trip
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long ord_i64(int64_t v) { return uint64_t(v) ^ 0x8000000000000000ULL; }
 __device__ __forceinline__ int64_t unord_i64(unsigned long long k) { return int64_t(k ^ 0x8000000000000000ULL); }
 
@@ -146,19 +155,55 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
   int64_t s_exp = 0, s_over = 0, s_uexp = 0, s_uover = 0;
   const int64_t threshold = cfg.target_time_ns;
   const PlannerFactors pf = clamp_factors(cfg);
+  // since(now, wb) > threshold  <=>  wb < now - threshold whenever 0 <= threshold <= now (no overflow on either
+  // side; the Go zero time is INT64_MIN and so always "waits"); other clocks take the literal saturating path.
+  const bool sane_clock = threshold >= 0 && now >= threshold;
+  const int64_t wait_cutoff = wsub(now, threshold);
+  // The next iteration's seven columns are staged into the (still idle) index region with cp.async while this
+  // iteration computes: 4 x 4 B + 3 x 8 B per thread, each thread reads back only what it copied itself.
+  constexpr bool kStage = size_t(4) * CAP >= size_t(THREADS) * 40;
+  uint32_t* st32 = reinterpret_cast<uint32_t*>(sIdx);                 // [4][THREADS] priority, num_dependents, group_id, flags
+  int64_t* st64 = reinterpret_cast<int64_t*>(st32 + 4 * THREADS);    // [3][THREADS] expected, queue_basis, wait_basis
+  auto prefetch = [&](int i0) {
+    const int i = i0 + tid;
+    if (i < tn) {
+      const int64_t t = base + i;
+      cp_async4(st32 + 0 * THREADS + tid, T.priority + t);
+      cp_async4(st32 + 1 * THREADS + tid, T.numdep + t);
+      cp_async4(st32 + 2 * THREADS + tid, T.gid + t);
+      cp_async4(st32 + 3 * THREADS + tid, T.flags + t);
+      cp_async8(st64 + 0 * THREADS + tid, T.expected + t);
+      cp_async8(st64 + 1 * THREADS + tid, T.qbasis + t);
+      cp_async8(st64 + 2 * THREADS + tid, T.wbasis + t);
+    }
+  };
+  if (kStage) prefetch(0);
   for (int i0 = 0; i0 < tn; i0 += THREADS) {
     const int i = i0 + tid;
     bool complex_task = false;
+    int32_t prio = 0, nd = 0, gid = -1;
+    int64_t exp_ns = 0, qb = 0, wb = 0;
+    uint32_t fl = 0;
+    if (kStage) {
+      cp_async_wait_all();
+      if (i < tn) {
+        prio = int32_t(st32[0 * THREADS + tid]); nd = int32_t(st32[1 * THREADS + tid]);
+        gid = int32_t(st32[2 * THREADS + tid]); fl = st32[3 * THREADS + tid];
+        exp_ns = st64[0 * THREADS + tid]; qb = st64[1 * THREADS + tid]; wb = st64[2 * THREADS + tid];
+      }
+      if (i0 + THREADS < tn) prefetch(i0 + THREADS);
+    } else if (i < tn) {
+      const int64_t t = base + i;
+      prio = T.priority[t]; nd = T.numdep[t]; gid = T.gid[t]; fl = T.flags[t];
+      exp_ns = T.expected[t]; qb = T.qbasis[t]; wb = T.wbasis[t];
+    }
     if (i < tn) {
       const int64_t t = base + i;
-      const int32_t prio = T.priority[t], nd = T.numdep[t], gid = T.gid[t];
-      const int64_t exp_ns = T.expected[t], qb = T.qbasis[t], wb = T.wbasis[t];
-      const uint32_t fl = T.flags[t];
       // GetDistroQueueInfo (scheduler.go:66-138)
       const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
       const bool counted = !cfg.includes_dependencies || dm;
       const bool over = counted && exp_ns > threshold;
-      const bool wait_over = counted && dm && since(now, wb) > threshold;
+      const bool wait_over = counted && dm && (sane_clock ? wb < wait_cutoff : since(now, wb) > threshold);
       const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
       c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += (fl & EVG_TF_OTHER_DISTRO) != 0;
       if (counted) s_exp += exp_ns;

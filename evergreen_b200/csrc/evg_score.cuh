@@ -91,6 +91,7 @@ EVG_HD int64_t wmul(int64_t a, int64_t b) { return int64_t(uint64_t(a) * uint64_
 
 // time.Since(t) with a frozen clock; saturates like time.Time.Sub.
 EVG_HD int64_t since(int64_t now, int64_t t) {
+  if ((now | t) >= 0) return now - t;  // both non-negative: cannot overflow (EVG_TIME_ZERO is negative)
   if (t == EVG_TIME_ZERO) return kI64Max;
   const int64_t d = wsub(now, t);
   // signed overflow of now - t: operands differ in sign and the result's sign differs from now's

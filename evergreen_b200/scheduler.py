@@ -45,7 +45,10 @@ class AllocatorError(Exception):
 
 
 class Engine:
-    """One evg_ctx: device buffers + stream.  Thread-compatible (one tick at a time)."""
+    """One evg_ctx: device buffers + stream.  Thread-compatible (one tick at a time).
+
+    Result arrays live in pinned host buffers owned by the engine and are REUSED by the next
+    call: copy what must outlive the next tick."""
 
     def __init__(self, device: int = 0, stream: Optional[int] = None):
         self.lib = L.load()
@@ -54,11 +57,42 @@ class Engine:
         self.ctx = h
         self._n_tasks = self._n_distros = self._n_groups = 0
         self._has_hosts = False
+        self._pinned = {}  # name -> (address, capacity in bytes): result buffers reused across ticks
 
     def close(self) -> None:
         if getattr(self, "ctx", None):
+            for addr, _ in self._pinned.values():
+                self.lib.evg_host_free(C.c_void_p(addr))
+            self._pinned = {}
             self.lib.evg_shutdown(self.ctx)
             self.ctx = None
+
+    def _out(self, name: str, shape, dtype) -> np.ndarray:
+        """A result array in pinned host memory (evg_host_alloc), cached by name and grown on demand.
+        The returned view is only valid until the next call that produces the same result."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        nbytes = max(n * dtype.itemsize, 1)
+        addr, cap = self._pinned.get(name, (0, 0))
+        if cap < nbytes:
+            if addr:
+                self.lib.evg_host_free(C.c_void_p(addr))
+            cap = nbytes + nbytes // 8
+            addr = self.lib.evg_host_alloc(cap)
+            if not addr:
+                raise L.EvgError(L.EVG_ERR_NOMEM, L.last_error())
+            self._pinned[name] = (addr, cap)
+        buf = (C.c_uint8 * nbytes).from_address(addr)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def _plan_output(self, T: int, D: int, G: int, breakdown: bool) -> S.PlanOutput:
+        info = self._out("info", D, L.QUEUE_INFO_DTYPE)
+        ginfo = self._out("group_info", G, L.GROUP_INFO_DTYPE)
+        return S.PlanOutput(self._out("order", T, np.int32), self._out("total_value", T, np.int64), info, ginfo,
+                            self._out("breakdown", (T, L.EVG_BD_N), np.int64) if breakdown else None)
+
+    def _alloc_output(self, D: int) -> S.AllocOutput:
+        return S.AllocOutput(self._out("result", D, L.ALLOC_RESULT_DTYPE), self._out("status", D, np.int32))
 
     def __del__(self):
         try:
@@ -83,16 +117,14 @@ class Engine:
 
     def download(self, want_breakdown: bool = False, want_alloc: Optional[bool] = None):
         T, D, G = self._n_tasks, self._n_distros, self._n_groups
-        po = S.PlanOutput(np.empty(T, np.int32), np.empty(T, np.int64), np.zeros(D, L.QUEUE_INFO_DTYPE),
-                          np.zeros(G, L.GROUP_INFO_DTYPE),
-                          np.empty((T, L.EVG_BD_N), np.int64) if want_breakdown else None)
+        po = self._plan_output(T, D, G, want_breakdown)
         ps = L.PlanOutStruct(L.ptr(po.order), L.ptr(po.total_value),
                              L.ptr(po.breakdown) if want_breakdown else None, L.ptr(po.info), L.ptr(po.group_info))
         ao = None
         if want_alloc is None:
             want_alloc = self._has_hosts
         if want_alloc:
-            ao = S.AllocOutput(np.zeros(D, L.ALLOC_RESULT_DTYPE), np.zeros(D, np.int32))
+            ao = self._alloc_output(D)
             as_ = L.AllocOutStruct(L.ptr(ao.result), L.ptr(ao.status))
             L.check(self.lib.evg_download(self.ctx, C.byref(ps), C.byref(as_)))
         else:
@@ -118,8 +150,7 @@ class Engine:
     # -- one-shot batch API (host buffers in, host buffers out) ---------------
     def plan_batch(self, tasks: S.TaskSoA, distros: S.DistroTable, now: int, breakdown: bool = False) -> S.PlanOutput:
         T, D, G = tasks.n_tasks, distros.n_distros, distros.n_groups
-        po = S.PlanOutput(np.empty(T, np.int32), np.empty(T, np.int64), np.zeros(D, L.QUEUE_INFO_DTYPE),
-                          np.zeros(G, L.GROUP_INFO_DTYPE), np.empty((T, L.EVG_BD_N), np.int64) if breakdown else None)
+        po = self._plan_output(T, D, G, breakdown)
         ps = L.PlanOutStruct(L.ptr(po.order), L.ptr(po.total_value), L.ptr(po.breakdown) if breakdown else None,
                              L.ptr(po.info), L.ptr(po.group_info))
         ts, ds = tasks.struct(), distros.struct()
@@ -131,9 +162,8 @@ class Engine:
     def plan_and_alloc_batch(self, tasks: S.TaskSoA, distros: S.DistroTable, hosts: S.HostSoA, now: int,
                              breakdown: bool = False):
         T, D, G = tasks.n_tasks, distros.n_distros, distros.n_groups
-        po = S.PlanOutput(np.empty(T, np.int32), np.empty(T, np.int64), np.zeros(D, L.QUEUE_INFO_DTYPE),
-                          np.zeros(G, L.GROUP_INFO_DTYPE), np.empty((T, L.EVG_BD_N), np.int64) if breakdown else None)
-        ao = S.AllocOutput(np.zeros(D, L.ALLOC_RESULT_DTYPE), np.zeros(D, np.int32))
+        po = self._plan_output(T, D, G, breakdown)
+        ao = self._alloc_output(D)
         ps = L.PlanOutStruct(L.ptr(po.order), L.ptr(po.total_value), L.ptr(po.breakdown) if breakdown else None,
                              L.ptr(po.info), L.ptr(po.group_info))
         as_ = L.AllocOutStruct(L.ptr(ao.result), L.ptr(ao.status))
@@ -146,7 +176,7 @@ class Engine:
 
     def alloc_batch(self, hosts: S.HostSoA, qinfo: np.ndarray, ginfo: np.ndarray, group_off: np.ndarray, now: int):
         D = int(qinfo.shape[0])
-        ao = S.AllocOutput(np.zeros(D, L.ALLOC_RESULT_DTYPE), np.zeros(D, np.int32))
+        ao = self._alloc_output(D)
         as_ = L.AllocOutStruct(L.ptr(ao.result), L.ptr(ao.status))
         hs = hosts.struct()
         qinfo = np.ascontiguousarray(qinfo, dtype=L.QUEUE_INFO_DTYPE)

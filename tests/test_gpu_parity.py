@@ -262,6 +262,16 @@ def test_edge_inputs(engine):
     parity.check_against_oracle(w, po, None)
 
 
+@pytest.mark.parametrize("now", [5, -(10 ** 18), 2 ** 62])
+def test_odd_clocks(engine, now):
+    """Clocks outside the usual range (before the threshold, negative, far future) take the literal
+    saturating time.Since path instead of the cutoff comparison."""
+    w = synth.make(np.array([700, 2000, 5000]), 17, tg_frac=0.1, unmet_dep_frac=0.03, includes_dependencies=True, n_hosts=30)
+    w.now = now
+    po, ao = run(engine, w)
+    parity.check_against_oracle(w, po, ao)
+
+
 def test_bad_arguments_are_errors(engine):
     w = synth.make(np.array([10]), 1)
     bad = copy.deepcopy(w)
@@ -280,7 +290,7 @@ def test_resident_rerun_is_idempotent(engine):
     w = synth.config(3, 0.02)
     engine.upload(w.tasks, w.distros, w.hosts)
     engine.run(w.now)
-    a_po, a_ao = engine.download()
+    a_po, a_ao = copy.deepcopy(engine.download())  # result buffers are reused by the next call
     engine.run(w.now)
     engine.run(w.now)
     b_po, b_ao = engine.download()
