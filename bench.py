@@ -197,14 +197,15 @@ def main():
     assert stream.cuda_stream != 0
     eng = scheduler.Engine(local_rank, stream.cuda_stream)
     # allocator results go straight into the all-gather send buffer
-    send = torch.zeros(shards.max_shard * edist.RESULT_BYTES, dtype=torch.uint8, device=dev)
+    gather = edist.ResultGather(shards, dev)
+    send = gather.send
     eng.bind_result_buffer(send.data_ptr(), shards.max_shard)
     eng.upload(w.tasks, w.distros, w.hosts)
 
     def step():
         eng.run(w.now)
         if world > 1:
-            return edist.all_gather_results(send, shards, rank)
+            return gather.gather()
         return send
 
     def barrier():
@@ -252,7 +253,7 @@ def main():
     for _ in range(args.e2e_steps):
         po, ao = eng.plan_and_alloc_batch(w.tasks, w.distros, w.hosts, w.now)
         if world > 1:
-            edist.all_gather_results(send, shards, rank)
+            gather.gather()
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

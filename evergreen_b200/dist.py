@@ -60,22 +60,37 @@ def lpt_partition(weights: Sequence[int], world: int) -> Shards:
     return Shards(world, owner, slot, members, load)
 
 
-def all_gather_results(local, shards: Shards, rank: int):
-    """One all-gather of the padded per-rank result vectors.
+class ResultGather:
+    """The per-tick collective: one all-gather of the padded per-rank result vectors.
 
-    `local` is a uint8 torch tensor [max_shard * 16] on the rank's device (the
-    buffer the allocator kernel wrote; rows past this rank's shard are padding).
-    Returns a uint8 tensor [D * 16] in GLOBAL distro order on the same device."""
-    import torch
-    import torch.distributed as dist
-    pad = shards.max_shard * RESULT_BYTES
-    assert local.dtype == torch.uint8 and local.numel() == pad
-    gathered = torch.empty(shards.world * pad, dtype=torch.uint8, device=local.device)
-    dist.all_gather_into_tensor(gathered, local)
-    # un-pad into global distro order
-    idx = torch.as_tensor(shards.owner * shards.max_shard + shards.slot, device=local.device)
-    rows = gathered.view(shards.world * shards.max_shard, RESULT_BYTES)
-    return rows.index_select(0, idx).reshape(-1)
+    `send` is a uint8 tensor [max_shard * 16] on the rank's device -- bind it with
+    Engine.bind_result_buffer so the allocator kernel writes into it directly (rows past
+    this rank's shard are padding).  gather() returns a uint8 tensor [D * 16] in GLOBAL
+    distro order on the same device; all buffers are allocated once."""
+
+    def __init__(self, shards: Shards, device):
+        import torch
+        self.shards = shards
+        self.pad = shards.max_shard * RESULT_BYTES
+        self.send = torch.zeros(max(self.pad, 1), dtype=torch.uint8, device=device)[:self.pad]
+        self.gathered = torch.empty(shards.world * self.pad, dtype=torch.uint8, device=device)
+        self.index = torch.as_tensor(shards.owner * shards.max_shard + shards.slot, device=device)
+
+    def gather(self):
+        import torch.distributed as dist
+        if self.shards.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.send)
+            rows = self.gathered.view(self.shards.world * self.shards.max_shard, RESULT_BYTES)
+        else:
+            rows = self.send.view(self.shards.max_shard, RESULT_BYTES)
+        return rows.index_select(0, self.index).reshape(-1)
+
+
+def all_gather_results(local, shards: Shards, rank: int):
+    """One-shot form of ResultGather (allocates; used by the CPU tests)."""
+    g = ResultGather(shards, local.device)
+    g.send.copy_(local)
+    return g.gather()
 
 
 def decode_results(buf) -> np.ndarray:
