@@ -109,6 +109,7 @@ SYMBOLS = {
     "evg_bind_result_buffer": (C.c_int, [_P, _P, C.c_int64]),
     "evg_last_launch_count": (C.c_int64, [_P]),
     "evg_last_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "evg_kernel_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
     "evg_plan_distro": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, C.c_uint32, _P]),
     "evg_alloc_distro": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P]),
 }

@@ -769,6 +769,10 @@ struct evg_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev_begin = nullptr, ev_sort0 = nullptr, ev_sort1 = nullptr, ev_end = nullptr;
+  // ring of event pairs around the on-chip planner launches: per-run kernel time without syncing inside a timed loop
+  static constexpr int kRing = 128;
+  cudaEvent_t ring0[kRing] = {}, ring1[kRing] = {};
+  int64_t runs = 0;
   // resident inputs
   bool have_tasks = false, have_hosts = false;
   int64_t T = 0, E = 0, G = 0, H = 0, U = 0, NT = 0;
@@ -1048,7 +1052,10 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
   // breakdown mode reads best_pair for every task: tasks emitted from their own single-task unit keep kInactive
   if (bd && c->any_complex) CK(cudaMemsetAsync(c->b_bestpair.p, 0xFF, sizeof(uint32_t) * size_t(T + 1), s));
   int rc;
+  const int slot = int(c->runs % evg_ctx::kRing);
+  if (c->timed) CK(cudaEventRecord(c->ring0[slot], s));
   if ((rc = launch_smem<1024, 12, 1>(c, dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now)) != EVG_OK) return rc;
+  if (c->timed) { CK(cudaEventRecord(c->ring1[slot], s)); c->runs++; }
   if ((rc = launch_smem<256, 16, 3>(c, dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now)) != EVG_OK) return rc;
   if ((rc = launch_smem<128, 8, 8>(c, dt, dd, w, c->b_listA.as<int32_t>(), c->nA, now)) != EVG_OK) return rc;
   if (c->timed) CK(cudaEventRecord(c->ev_sort1, s));
@@ -1103,6 +1110,7 @@ int evg_init(int device, void* stream, evg_ctx** out) {
   else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CK(cudaEventCreate(&c->ev_begin)); CK(cudaEventCreate(&c->ev_sort0));
   CK(cudaEventCreate(&c->ev_sort1)); CK(cudaEventCreate(&c->ev_end));
+  for (int k = 0; k < evg_ctx::kRing; k++) { CK(cudaEventCreate(&c->ring0[k])); CK(cudaEventCreate(&c->ring1[k])); }
   *out = c;
   return EVG_OK;
 }
@@ -1119,6 +1127,7 @@ void evg_shutdown(evg_ctx* c) {
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
                    &c->b_hstart, &c->b_hostoff, &c->b_acfg, &c->b_gs, &c->b_result, &c->b_status};
   for (DevBuf* b : all) b->release();
+  for (int k = 0; k < evg_ctx::kRing; k++) { if (c->ring0[k]) cudaEventDestroy(c->ring0[k]); if (c->ring1[k]) cudaEventDestroy(c->ring1[k]); }
   cudaEventDestroy(c->ev_begin); cudaEventDestroy(c->ev_sort0); cudaEventDestroy(c->ev_sort1); cudaEventDestroy(c->ev_end);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1195,6 +1204,18 @@ int evg_last_timing_ms(evg_ctx* c, float* total_ms, float* sort_ms) {
   CK(cudaEventSynchronize(c->ev_end));
   if (total_ms) CK(cudaEventElapsedTime(total_ms, c->ev_begin, c->ev_end));
   if (sort_ms) CK(cudaEventElapsedTime(sort_ms, c->ev_sort0, c->ev_sort1));
+  return EVG_OK;
+}
+
+int evg_kernel_timing_ms(evg_ctx* c, float* out_ms, int32_t n) {
+  if (!c || !out_ms || n < 0) return fail(EVG_ERR_INVALID, "evg_kernel_timing_ms: bad argument");
+  if (n > evg_ctx::kRing || n > c->runs) return fail(EVG_ERR_STATE, "only %lld timed runs recorded (ring of %d)", (long long)c->runs, evg_ctx::kRing);
+  CK(cudaSetDevice(c->device));
+  for (int32_t k = 0; k < n; k++) {
+    const int slot = int((c->runs - n + k) % evg_ctx::kRing);
+    CK(cudaEventSynchronize(c->ring1[slot]));
+    CK(cudaEventElapsedTime(out_ms + k, c->ring0[slot], c->ring1[slot]));
+  }
   return EVG_OK;
 }
 

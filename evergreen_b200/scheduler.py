@@ -147,6 +147,12 @@ class Engine:
         L.check(self.lib.evg_last_timing_ms(self.ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def kernel_timing_ms(self, n: int):
+        """Per-run device time of the dominant kernel (k_plan_smem<1024,12>) for the last n resident runs."""
+        buf = (C.c_float * max(n, 1))()
+        L.check(self.lib.evg_kernel_timing_ms(self.ctx, buf, int(n)))
+        return [buf[k] for k in range(n)]
+
     # -- one-shot batch API (host buffers in, host buffers out) ---------------
     def plan_batch(self, tasks: S.TaskSoA, distros: S.DistroTable, now: int, breakdown: bool = False) -> S.PlanOutput:
         T, D, G = tasks.n_tasks, distros.n_distros, distros.n_groups

@@ -292,6 +292,11 @@ int64_t evg_last_launch_count(evg_ctx* ctx);
  * during the last evg_run_resident (valid after a sync / download). */
 int evg_last_timing_ms(evg_ctx* ctx, float* total_ms, float* sort_ms);
 
+/* Device time in ms of the dominant kernel -- k_plan_smem<1024,12>, the on-chip planner
+ * of distros with 4097..12288 tasks -- for each of the last `n` evg_run_resident calls
+ * (n <= 128), from CUDA events recorded on the context stream around that launch. */
+int evg_kernel_timing_ms(evg_ctx* ctx, float* out_ms, int32_t n);
+
 /* ---- single-distro wrappers: the per-job drop-in ------------------------- */
 
 /* One distro: PrioritizeTasks for `d` (scheduler/scheduler.go:27). */
