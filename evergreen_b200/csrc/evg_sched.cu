@@ -672,13 +672,13 @@ __device__ int eval_group(const evg_alloc_cfg& c, const evg_group_info& info, in
 // bucket's updates, so every bucket's FP64 sum is accumulated in host order
 // while buckets proceed in parallel.  Groups are then evaluated 32 at a time;
 // the per-group results are integers, so the warp reduction is exact.
-__global__ void __launch_bounds__(128) k_alloc(DHosts H, int32_t n_distros, const int64_t* group_off,
+__global__ void __launch_bounds__(128) k_alloc(DHosts H, int32_t d_begin, int32_t n_distros, const int64_t* group_off,
                                                const evg_queue_info* qinfo, evg_group_info* ginfo, GroupScratch* gs,
                                                int64_t now, evg_alloc_result* result, int32_t* status) {
-  const int d = int((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+  const int d = d_begin + int((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
-  if (d >= n_distros) return;  // warp-uniform
+  if (d >= n_distros) return;  // warp-uniform (n_distros = end of the range)
   const evg_alloc_cfg c = H.cfg[d];
   const evg_queue_info qi = qinfo[d];
   const int64_t threshold = qi.max_duration_threshold;
@@ -785,6 +785,11 @@ struct evg_ctx {
   DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_cv, b_ca, b_crk, b_bestpair;
   DevBuf b_route, b_listA, b_listB, b_listC, b_unitv, b_unita, b_unitn, b_unitmask;
   int32_t nA = 0, nB = 0, nC = 0, n_general = 0;  // distros per on-chip class / general path
+  std::vector<int32_t> h_listA, h_listB, h_listC;  // host copies (ascending distro ids) for the pipelined one-shot call
+  std::vector<int64_t> h_taskoff, h_groupoff;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  static constexpr int kMaxChunks = 16;
+  cudaEvent_t ev_h[kMaxChunks] = {}, ev_c[kMaxChunks] = {};
   int general_complex = 0;
   DevBuf b_ks[2], b_kv[2], b_ix[2], b_bits, b_npass, b_sched, b_maxpass;
   DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist;
@@ -798,7 +803,7 @@ struct evg_ctx {
 
 namespace {
 
-int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt) {
+int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, bool copy_columns = true) {
   if (!t || !dt) return fail(EVG_ERR_INVALID, "null task table / distro table");
   const int64_t T = t->n_tasks, E = t->n_edges;
   const int32_t D = dt->n_distros;
@@ -854,19 +859,25 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt) 
     CK((buf).ensure(sizeof(type) * size_t((count) > 0 ? (count) : 1)));                               \
     if ((count) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(count), cudaMemcpyHostToDevice, s)); \
   } while (0)
-  UP(c->b_prio, t->priority, T, int32_t);
-  UP(c->b_exp, t->expected_ns, T, int64_t);
-  UP(c->b_qb, t->queue_basis_ns, T, int64_t);
-  UP(c->b_wb, t->wait_basis_ns, T, int64_t);
-  UP(c->b_nd, t->num_dependents, T, int32_t);
-  UP(c->b_tgo, t->task_group_order, T, int32_t);
-  UP(c->b_gid, t->group_id, T, int32_t);
-  UP(c->b_vid, t->version_id, T, int32_t);
-  UP(c->b_flags, t->flags, T, uint32_t);
+#define UPC(buf, ptr, count, type)                                                                    \
+  do {                                                                                                \
+    CK((buf).ensure(sizeof(type) * size_t((count) > 0 ? (count) : 1)));                               \
+    if (copy_columns && (count) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(count), cudaMemcpyHostToDevice, s)); \
+  } while (0)
+  UPC(c->b_prio, t->priority, T, int32_t);
+  UPC(c->b_exp, t->expected_ns, T, int64_t);
+  UPC(c->b_qb, t->queue_basis_ns, T, int64_t);
+  UPC(c->b_wb, t->wait_basis_ns, T, int64_t);
+  UPC(c->b_nd, t->num_dependents, T, int32_t);
+  UPC(c->b_tgo, t->task_group_order, T, int32_t);
+  UPC(c->b_gid, t->group_id, T, int32_t);
+  UPC(c->b_vid, t->version_id, T, int32_t);
+  UPC(c->b_flags, t->flags, T, uint32_t);
   if (E > 0) {
-    UP(c->b_depoff, t->dep_off, T + 1, int64_t);
-    UP(c->b_depidx, t->dep_idx, E, int32_t);
+    UPC(c->b_depoff, t->dep_off, T + 1, int64_t);
+    UPC(c->b_depidx, t->dep_idx, E, int32_t);
   }
+#undef UPC
   UP(c->b_taskoff, dt->task_off, D + 1, int64_t);
   UP(c->b_groupoff, dt->group_off, D + 1, int64_t);
   UP(c->b_cfg, dt->cfg, D, evg_distro_cfg);
@@ -917,6 +928,9 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt) 
   c->nA = int32_t(listA.size()); c->nB = int32_t(listB.size()); c->nC = int32_t(listC.size());
   c->n_general = n_general;
   c->general_complex = general_complex;
+  c->h_listA.swap(listA); c->h_listB.swap(listB); c->h_listC.swap(listC);
+  c->h_taskoff.assign(dt->task_off, dt->task_off + D + 1);
+  c->h_groupoff.assign(dt->group_off, dt->group_off + D + 1);
   c->have_tasks = true;
   c->have_hosts = false;
   return EVG_OK;
@@ -1001,7 +1015,7 @@ int run_alloc(evg_ctx* c, int64_t now) {
   if (c->ext_result && c->ext_capacity < c->Dn) return fail(EVG_ERR_INVALID, "bound result buffer holds %lld rows, need %d", (long long)c->ext_capacity, c->Dn);
   CK(c->b_gs.ensure(sizeof(GroupScratch) * size_t(c->G + 1)));
   CK(cudaMemsetAsync(c->b_gs.p, 0, sizeof(GroupScratch) * size_t(c->G + 1), c->stream));
-  LAUNCH(c, k_alloc, grid_for(int64_t(c->Dn) * 32, 128), 128, h, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
+  LAUNCH(c, k_alloc, grid_for(int64_t(c->Dn) * 32, 128), 128, h, 0, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
          c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>());
   CK(cudaGetLastError());
   return EVG_OK;
@@ -1129,6 +1143,9 @@ void evg_shutdown(evg_ctx* c) {
   for (DevBuf* b : all) b->release();
   for (int k = 0; k < evg_ctx::kRing; k++) { if (c->ring0[k]) cudaEventDestroy(c->ring0[k]); if (c->ring1[k]) cudaEventDestroy(c->ring1[k]); }
   cudaEventDestroy(c->ev_begin); cudaEventDestroy(c->ev_sort0); cudaEventDestroy(c->ev_sort1); cudaEventDestroy(c->ev_end);
+  for (int k = 0; k < evg_ctx::kMaxChunks; k++) { if (c->ev_h[k]) cudaEventDestroy(c->ev_h[k]); if (c->ev_c[k]) cudaEventDestroy(c->ev_c[k]); }
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1228,10 +1245,128 @@ int evg_plan_batch(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table
   return evg_download(c, out, nullptr);
 }
 
+// The one-shot call as a three-stage pipeline over chunks of whole distros: H2D of chunk k+1, kernels of chunk k
+// and D2H of chunk k-1 overlap on three streams, so the tick costs about max(H2D, D2H) instead of their sum.
+// Used when every distro is planned on-chip (no general-path distro) and no breakdown is requested.
+static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, const evg_host_soa* hosts,
+                                    const int64_t* host_off, const evg_alloc_cfg* acfg, int64_t now, evg_plan_out* po,
+                                    evg_alloc_out* ao) {
+  const int64_t T = c->T, E = c->E;
+  const int32_t D = c->Dn;
+  if (!c->s_h2d) {
+    CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < evg_ctx::kMaxChunks; k++) {
+      CK(cudaEventCreateWithFlags(&c->ev_h[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->ev_c[k], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t s = c->stream;
+  DTasks dtk = dtasks(c);
+  DDistros dd = ddistros(c);
+  DWork w = dwork(c);
+  DHosts h;
+  h.n = c->H; h.flags = c->b_hflags.as<uint32_t>(); h.gid = c->b_hgid.as<int32_t>();
+  h.expected = c->b_hexp.as<int64_t>(); h.stddev = c->b_hstd.as<int64_t>(); h.start = c->b_hstart.as<int64_t>();
+  h.host_off = c->b_hostoff.as<int64_t>(); h.cfg = c->b_acfg.as<evg_alloc_cfg>();
+  if (c->ext_result && c->ext_capacity < D) return fail(EVG_ERR_INVALID, "bound result buffer too small");
+  CK(c->b_gs.ensure(sizeof(GroupScratch) * size_t(c->G + 1)));
+  CK(cudaMemsetAsync(c->b_gs.p, 0, sizeof(GroupScratch) * size_t(c->G + 1), s));
+  CK(cudaMemsetAsync(c->b_ginfo.p, 0, sizeof(evg_group_info) * size_t(c->G + 1), s));
+  c->launches = 0;
+  c->timed = false;
+  // chunk boundaries: whole distros, about equal task counts
+  const int n_chunks = int(std::min<int64_t>(evg_ctx::kMaxChunks, std::max<int64_t>(1, T / (1 << 20))));
+  std::vector<int32_t> cut(size_t(n_chunks) + 1, D);
+  cut[0] = 0;
+  {
+    int32_t d = 0;
+    for (int k = 1; k < n_chunks; k++) {
+      const int64_t want = T * k / n_chunks;
+      while (d < D && c->h_taskoff[d] < want) d++;
+      cut[k] = d;
+    }
+  }
+  auto sub = [](const std::vector<int32_t>& v, int32_t d0, int32_t d1, int32_t* first) {
+    auto a = std::lower_bound(v.begin(), v.end(), d0), b = std::lower_bound(v.begin(), v.end(), d1);
+    *first = int32_t(a - v.begin());
+    return int32_t(b - a);
+  };
+#define H2D(buf, ptr, off, count, type)                                                                  \
+  if ((count) > 0) CK(cudaMemcpyAsync((buf).as<type>() + (off), (ptr) + (off), sizeof(type) * size_t(count), cudaMemcpyHostToDevice, c->s_h2d))
+#define D2H(dst, src, off, count, type)                                                                  \
+  if ((dst) && (count) > 0) CK(cudaMemcpyAsync((dst) + (off), (src) + (off), sizeof(type) * size_t(count), cudaMemcpyDeviceToHost, c->s_d2h))
+  int rc;
+  for (int k = 0; k < n_chunks; k++) {
+    const int32_t d0 = cut[k], d1 = cut[k + 1];
+    if (d1 <= d0) continue;
+    const int64_t t0 = c->h_taskoff[d0], n = c->h_taskoff[d1] - t0;
+    const int64_t g0 = c->h_groupoff[d0], ng = c->h_groupoff[d1] - g0;
+    H2D(c->b_prio, t->priority, t0, n, int32_t);
+    H2D(c->b_exp, t->expected_ns, t0, n, int64_t);
+    H2D(c->b_qb, t->queue_basis_ns, t0, n, int64_t);
+    H2D(c->b_wb, t->wait_basis_ns, t0, n, int64_t);
+    H2D(c->b_nd, t->num_dependents, t0, n, int32_t);
+    H2D(c->b_tgo, t->task_group_order, t0, n, int32_t);
+    H2D(c->b_gid, t->group_id, t0, n, int32_t);
+    H2D(c->b_vid, t->version_id, t0, n, int32_t);
+    H2D(c->b_flags, t->flags, t0, n, uint32_t);
+    if (E > 0) {
+      const int64_t e0 = t->dep_off[t0], ne = t->dep_off[t0 + n] - e0;
+      H2D(c->b_depoff, t->dep_off, t0, n + 1, int64_t);
+      H2D(c->b_depidx, t->dep_idx, e0, ne, int32_t);
+    }
+    CK(cudaEventRecord(c->ev_h[k], c->s_h2d));
+    CK(cudaStreamWaitEvent(s, c->ev_h[k], 0));
+    int32_t first, cnt;
+    cnt = sub(c->h_listC, d0, d1, &first);
+    if ((rc = launch_smem<1024, 12, 1>(c, dtk, dd, w, c->b_listC.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
+    cnt = sub(c->h_listB, d0, d1, &first);
+    if ((rc = launch_smem<256, 16, 3>(c, dtk, dd, w, c->b_listB.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
+    cnt = sub(c->h_listA, d0, d1, &first);
+    if ((rc = launch_smem<128, 8, 8>(c, dtk, dd, w, c->b_listA.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
+    LAUNCH(c, k_alloc, grid_for(int64_t(d1 - d0) * 32, 128), 128, h, d0, d1, c->b_groupoff.as<int64_t>(),
+           c->b_qinfo.as<evg_queue_info>(), c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now,
+           c->result_ptr(), c->b_status.as<int32_t>());
+    CK(cudaEventRecord(c->ev_c[k], s));
+    CK(cudaStreamWaitEvent(c->s_d2h, c->ev_c[k], 0));
+    if (po) {
+      D2H(po->order, c->b_order.as<int32_t>(), t0, n, int32_t);
+      D2H(po->total_value, c->b_tv.as<int64_t>(), t0, n, int64_t);
+      D2H(po->info, c->b_qinfo.as<evg_queue_info>(), d0, d1 - d0, evg_queue_info);
+      D2H(po->group_info, c->b_ginfo.as<evg_group_info>(), g0, ng, evg_group_info);
+    }
+    if (ao) {
+      D2H(ao->result, c->result_ptr(), d0, d1 - d0, evg_alloc_result);
+      D2H(ao->status, c->b_status.as<int32_t>(), d0, d1 - d0, int32_t);
+    }
+  }
+#undef H2D
+#undef D2H
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->s_d2h));
+  CK(cudaStreamSynchronize(s));
+  c->have_hosts = true;
+  return EVG_OK;
+}
+
 int evg_plan_and_alloc_batch(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* distros,
                              const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg, int64_t now_ns,
                              uint32_t opts, evg_plan_out* plan_out, evg_alloc_out* alloc_out) {
   if (!hosts || !acfg) return fail(EVG_ERR_INVALID, "evg_plan_and_alloc_batch needs hosts and allocator config");
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  if (!(opts & EVG_OPT_BREAKDOWN) && tasks && distros && tasks->n_tasks >= (int64_t(1) << 21)) {
+    // large tick: stage the small tables, then pipeline the columns chunk by chunk
+    CK(cudaSetDevice(c->device));
+    int rc0 = upload_tasks(c, tasks, distros, /*copy_columns=*/false);
+    if (rc0 != EVG_OK) return rc0;
+    if (c->n_general == 0) {
+      rc0 = upload_hosts(c, hosts, host_off, acfg, distros->n_distros);
+      if (rc0 != EVG_OK) return rc0;
+      CK(cudaStreamSynchronize(c->stream));
+      return plan_and_alloc_pipelined(c, tasks, distros, hosts, host_off, acfg, now_ns, plan_out, alloc_out);
+    }
+  }
   int rc = evg_upload(c, tasks, distros, hosts, host_off, acfg);
   if (rc != EVG_OK) return rc;
   rc = evg_run_resident(c, now_ns, opts);

@@ -299,6 +299,24 @@ def test_resident_rerun_is_idempotent(engine):
     assert engine.last_launch_count() > 0
 
 
+def test_pipelined_one_shot_equals_resident(engine):
+    """Ticks of >= 2^21 tasks take the chunked H2D / kernels / D2H pipeline inside evg_plan_and_alloc_batch;
+    its results must equal the upload -> run -> download path bit for bit."""
+    rng = synth.Rng(77)
+    sizes = rng.integers(330, 2000, 12000)
+    w = synth.make(sizes, 78, zipf_priority=True, tg_frac=0.1, unmet_dep_frac=0.02, met_dep_frac=0.01,
+                   custom_factor_frac=0.3, includes_dependencies=True, n_hosts=3000, providers=(0.7, 0.2, 0.1))
+    assert w.n_tasks >= 2 ** 21
+    engine.upload(w.tasks, w.distros, w.hosts)
+    engine.run(w.now)
+    a_po, a_ao = copy.deepcopy(engine.download())
+    b_po, b_ao = engine.plan_and_alloc_batch(w.tasks, w.distros, w.hosts, w.now)
+    for f in ("order", "total_value", "info", "group_info"):
+        assert np.array_equal(getattr(a_po, f), getattr(b_po, f)), f
+    assert np.array_equal(a_ao.result, b_ao.result) and np.array_equal(a_ao.status, b_ao.status)
+    parity.check_against_oracle(w, b_po, b_ao, distros=[0, 1, 2, 150, 329])
+
+
 # ---------------------------------------------------------------- full-size properties
 def test_c2_full_size_properties(engine):
     """BASELINE configs[1] at full size: 1000 distros x 10k tasks (1e7 tasks).  The oracle checks a
