@@ -29,6 +29,7 @@ struct PlanShared {
   uint32_t ub;
   unsigned long long vmax_enc, vmin_enc;   // encoded so that atomicMax / atomicMin work on unsigned
   int32_t n_displaced;
+  int32_t tg_fallback;
   unsigned int n_list;
   // queue-info block accumulators
   unsigned int c[10];
@@ -76,7 +77,7 @@ __device__ __forceinline__ void eval_pair(const DTasks& T, const DWork& W, const
 
 template <int THREADS, int ITEMS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
-k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int64_t now,
+k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int64_t now, int lists_needed,
             int32_t* __restrict__ order, int64_t* __restrict__ total_value) {
   constexpr int CAP = THREADS * ITEMS;
   constexpr int NW = THREADS / 32;
@@ -115,6 +116,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     S->vmin_enc = ~0ull;
     S->n_displaced = 0;
     S->n_list = 0;
+    S->tg_fallback = 0;
     for (int k = 0; k < 10; k++) S->c[k] = 0;
     for (int k = 0; k < 4; k++) S->s[k] = 0;
   }
@@ -286,29 +288,110 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     return cx ? k : -1;
   };
 
+  // Task-group-only distros (no GroupVersions, no in-queue dependency edges) take a list-free path: every
+  // multi-member unit is exactly one task group, so Unit.info is a handful of shared-memory atomics per member,
+  // and -- when TaskGroupOrder is unique inside each group, which is what a task group's order means -- a
+  // member's rank inside its unit is the number of smaller orders present (a 64-bit presence mask).
+  // Anything else (orders >= 64, duplicate orders, too many groups, breakdown mode) falls back to the unit lists.
+  constexpr int kGroupCap = (4 * CAP) / 52;
+  unsigned long long* gTiq = reinterpret_cast<unsigned long long*>(sIdx);  // the staging area is idle again
+  unsigned long long* gRt = gTiq + kGroupCap;
+  unsigned long long* gMask = gRt + kGroupCap;
+  long long* gV = reinterpret_cast<long long*>(gMask + kGroupCap);
+  int* gMaxP = reinterpret_cast<int*>(gV + kGroupCap);
+  int* gMaxD = gMaxP + kGroupCap;
+  unsigned int* gFlags = reinterpret_cast<unsigned int*>(gMaxD + kGroupCap);
+  unsigned int* gN = gFlags + kGroupCap;
+  unsigned int* gAnchor = gN + kGroupCap;
+  bool fast_tg = any && !gv && !has_edges && !lists_needed && int(ng) <= kGroupCap;
+
   if (any) {
-    // ---- phase 2b: task-group sums (scheduler.go:79-137) and unit membership links (planner.go:431-456) ----
+    // ---- phase 2b: task-group sums (scheduler.go:79-137) ----
+    if (fast_tg)
+      for (int g = tid; g < int(ng); g += THREADS) {
+        gTiq[g] = 0ull; gRt[g] = 0ull; gMask[g] = 0ull; gMaxP[g] = 0; gMaxD[g] = 0; gFlags[g] = 0u; gN[g] = 0u;
+        gAnchor[g] = kNoAnchor;
+      }
+    __syncthreads();
+    for (int k = tid; k < n_work; k += THREADS) {
+      const int i = work_item(k);
+      if (i < 0) continue;
+      const int64_t t = base + i;
+      const int32_t gid = T.gid[t];
+      if (gid < 0) continue;
+      const int64_t exp_ns = T.expected[t];
+      const uint32_t fl = T.flags[t];
+      const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
+      const bool counted = !cfg.includes_dependencies || dm;
+      const bool over = counted && exp_ns > threshold;
+      const bool wait_over = counted && dm && since(now, T.wbasis[t]) > threshold;
+      const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
+      evg_group_info* g = W.ginfo + D.group_off[d] + gid;
+      atomic_add64(&g->count, counted);
+      atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
+      atomic_add64(&g->count_duration_over_threshold, over);
+      atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
+      atomic_add64(&g->count_wait_over_threshold, wait_over);
+      atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
+      if (fast_tg) {  // Unit.info (planner.go:302-337) of the task-group unit, member by member
+        const int32_t tgo = T.tgo[t];
+        if (tgo < 0 || tgo >= 64) { S->tg_fallback = 1; continue; }
+        const int64_t qb = T.qbasis[t];
+        const uint32_t req = fl & EVG_TF_REQ_MASK;
+        uint32_t uf = 0;
+        if (req == EVG_TF_REQ_MERGE_QUEUE) uf |= UF_MERGE_QUEUE;
+        else if (req == EVG_TF_REQ_PATCH) uf |= UF_PATCH;
+        if (fl & EVG_TF_GENERATE) uf |= UF_GENERATE;
+        if (fl & EVG_TF_STEPBACK) uf |= UF_STEPBACK;
+        if (qb != EVG_TIME_ZERO) atomicAdd(&gTiq[gid], (unsigned long long)since(now, qb));
+        atomicAdd(&gRt[gid], (unsigned long long)exp_ns);
+        atomicMax(&gMaxP[gid], T.priority[t]);
+        atomicMax(&gMaxD[gid], T.numdep[t]);
+        if (uf) atomicOr(&gFlags[gid], uf);
+        atomicAdd(&gN[gid], 1u);
+        atomicMin(&gAnchor[gid], uint32_t(i));
+        atomicOr(&gMask[gid], 1ull << tgo);
+      }
+    }
+    __syncthreads();
+    if (fast_tg) {
+      // ---- phase 3 (list-free): score each task group's unit (planner.go:209-300) ----
+      for (int g = tid; g < int(ng); g += THREADS) {
+        if (gN[g] != uint32_t(__popcll(gMask[g]))) { S->tg_fallback = 1; continue; }  // duplicate TaskGroupOrder
+        UnitAcc a;
+        a.tiq = int64_t(gTiq[g]); a.rt = int64_t(gRt[g]); a.max_p = gMaxP[g]; a.max_d = gMaxD[g];
+        a.n = gN[g]; a.flags = gFlags[g];
+        gV[g] = a.n ? unit_value(a, cfg, nullptr) : 0;
+      }
+      __syncthreads();
+      fast_tg = S->tg_fallback == 0;
+    }
+    if (fast_tg) {
+      // ---- phase 4 (list-free): a task-group task is emitted from its group's unit, ranked by its order ----
+      for (int k = tid; k < n_work; k += THREADS) {
+        const int i = work_item(k);
+        if (i < 0) continue;
+        const int64_t t = base + i;
+        const int32_t gid = T.gid[t];
+        if (gid < 0) continue;
+        const uint32_t brk = __popcll(gMask[gid] & ((1ull << T.tgo[t]) - 1ull));
+        const uint32_t ba = gAnchor[gid];
+        sV[i] = gV[gid];
+        sA[i] = uint16_t(ba);
+        sRk[i] = uint16_t(brk);
+        if (!(ba == uint32_t(i) && brk == 0)) { atomicOr(&sDisp[i >> 5], 1u << (i & 31)); S->n_displaced = 1; }
+      }
+      __syncthreads();
+    }
+  }
+
+  if (any && !fast_tg) {
+    // ---- phase 2c: unit membership links (planner.go:431-456) ----
     for (int k = tid; k < n_work; k += THREADS) {
       const int i = work_item(k);
       if (i < 0) continue;
       const int64_t t = base + i;
       const int32_t gid = T.gid[t], vid = T.vid[t];
-      if (gid >= 0) {
-        const int64_t exp_ns = T.expected[t];
-        const uint32_t fl = T.flags[t];
-        const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
-        const bool counted = !cfg.includes_dependencies || dm;
-        const bool over = counted && exp_ns > threshold;
-        const bool wait_over = counted && dm && since(now, T.wbasis[t]) > threshold;
-        const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
-        evg_group_info* g = W.ginfo + D.group_off[d] + gid;
-        atomic_add64(&g->count, counted);
-        atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
-        atomic_add64(&g->count_duration_over_threshold, over);
-        atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
-        atomic_add64(&g->count_wait_over_threshold, wait_over);
-        atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
-      }
       const bool own_complex = gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31)));
       const uint32_t s_own = own_slot_local(gid, vid, uint32_t(i), ng, gv);
       const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
@@ -465,6 +548,10 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       const uint32_t a = sA[i];
       uint32_t pos = sE[a];
       const uint32_t myrk = sRk[i];
+      if (fast_tg) {  // every member of a task-group unit is emitted from it: the rank is the offset
+        sIdx[pos + myrk] = uint16_t(i);
+        continue;
+      }
       const uint32_t slot = W.pair_slot[W.best_pair[base + i]];
       if (W.unit_n[slot] <= 64) {
         pos += __popcll(W.unit_mask[slot] & ((1ull << myrk) - 1ull));

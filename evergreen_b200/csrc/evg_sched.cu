@@ -1022,11 +1022,12 @@ int run_alloc(evg_ctx* c, int64_t now) {
 }
 
 template <int THREADS, int ITEMS, int MIN_CTAS>
-int launch_smem(evg_ctx* c, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n, int64_t now) {
+int launch_smem(evg_ctx* c, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n, int64_t now,
+                int lists_needed = 0) {
   if (n <= 0) return EVG_OK;
   const size_t bytes = PlanSmem<THREADS, ITEMS>::kBytes;
   CK(cudaFuncSetAttribute(k_plan_smem<THREADS, ITEMS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
-  k_plan_smem<THREADS, ITEMS, MIN_CTAS><<<unsigned(n), THREADS, bytes, c->stream>>>(dt, dd, w, list, now,
+  k_plan_smem<THREADS, ITEMS, MIN_CTAS><<<unsigned(n), THREADS, bytes, c->stream>>>(dt, dd, w, list, now, lists_needed,
                                                                           c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
   c->launches++;
   return EVG_OK;
@@ -1068,10 +1069,10 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
   int rc;
   const int slot = int(c->runs % evg_ctx::kRing);
   if (c->timed) CK(cudaEventRecord(c->ring0[slot], s));
-  if ((rc = launch_smem<1024, 12, 1>(c, dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now)) != EVG_OK) return rc;
+  if ((rc = launch_smem<1024, 12, 1>(c, dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now, bd ? 1 : 0)) != EVG_OK) return rc;
   if (c->timed) { CK(cudaEventRecord(c->ring1[slot], s)); c->runs++; }
-  if ((rc = launch_smem<256, 16, 3>(c, dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now)) != EVG_OK) return rc;
-  if ((rc = launch_smem<128, 8, 8>(c, dt, dd, w, c->b_listA.as<int32_t>(), c->nA, now)) != EVG_OK) return rc;
+  if ((rc = launch_smem<256, 16, 3>(c, dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now, bd ? 1 : 0)) != EVG_OK) return rc;
+  if ((rc = launch_smem<128, 8, 8>(c, dt, dd, w, c->b_listA.as<int32_t>(), c->nA, now, bd ? 1 : 0)) != EVG_OK) return rc;
   if (c->timed) CK(cudaEventRecord(c->ev_sort1, s));
   if (general) {
     const int gc = c->general_complex;

@@ -173,6 +173,20 @@ def test_breakdown_parity(engine):
     assert np.array_equal(po.breakdown, ref["breakdown"])
 
 
+def test_task_group_order_fallbacks(engine):
+    """The list-free task-group path needs unique TaskGroupOrder < 64 inside each group; distros that break
+    that (duplicates, large or zero orders) must fall back to the unit lists and still match the oracle."""
+    w = synth.make(np.array([900, 3000, 9000, 9000, 500]), 55, tg_frac=0.2, zipf_priority=True, n_hosts=40)
+    toff = w.distros.task_off
+    t = w.tasks
+    t.task_group_order[toff[0]:toff[1]] = 0                       # all equal (the reference's TaskGroup KAT shape)
+    sel = np.arange(toff[1], toff[2])[::5]
+    t.task_group_order[sel] = 70                                  # beyond the presence mask
+    t.task_group_order[toff[2]:toff[3]] = np.minimum(t.task_group_order[toff[2]:toff[3]], 2)  # duplicates
+    po, ao = run(engine, w)
+    parity.check_against_oracle(w, po, ao)
+
+
 def test_route_boundaries(engine):
     """Distro sizes on both sides of every on-chip capacity class (1024 / 4096 / 12288 tasks) in one tick,
     so the three k_plan_smem variants and the general path all run in the same call."""
