@@ -615,32 +615,25 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     const uint16_t* ic = sIdx + cur * CAP;
     uint32_t* kn = sKey + (cur ^ 1) * CAP;
     uint16_t* in_ = sIdx + (cur ^ 1) * CAP;
-    uint16_t* wc = sWc + warp * 256;
+    uint32_t* wcAll = reinterpret_cast<uint32_t*>(sA);  // [NW][256]; anchor/rank arrays are dead after phase 7
+    uint32_t* wc = wcAll + warp * 256;
     for (int k = lane; k < 256; k += 32) wc[k] = 0;
     __syncwarp();
-    // histogram of this warp's segment; 4 chunks of 32 in flight so the loads / MATCH overlap
+    // histogram of this warp's segment: shared-memory atomics on the warp's private counters
+    // (MATCH.ANY here was the sort's bottleneck: one shared unit per SM, ~50 cycles per warp instruction)
     for (int s0 = seg0; s0 < seg1; s0 += 128) {
-      uint32_t dg[4];
-      unsigned peers[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int p = s0 + u * 32 + lane;
-        dg[u] = p < seg1 ? ((kc[p] >> shift) & 255u) : 0xFFFFu;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) peers[u] = __match_any_sync(full, dg[u]);
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if (dg[u] != 0xFFFFu && (peers[u] & lt) == 0) wc[dg[u]] += uint16_t(__popc(peers[u]));
-        __syncwarp();
+        if (p < seg1) atomicAdd(&wc[(kc[p] >> shift) & 255u], 1u);
       }
     }
     __syncthreads();
     for (int dgt = tid; dgt < 256; dgt += THREADS) {
       uint32_t run = 0;
       for (int w = 0; w < NW; w++) {
-        const uint32_t x = sWc[w * 256 + dgt];
-        sWc[w * 256 + dgt] = uint16_t(run);
+        const uint32_t x = wcAll[w * 256 + dgt];
+        wcAll[w * 256 + dgt] = run;
         run += x;
       }
       sTot[dgt] = run;
@@ -678,7 +671,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
         uint32_t off = 0;
         if (ok) off = wc[dg[u]];
         __syncwarp();
-        if (ok && r[u] == 0) wc[dg[u]] = uint16_t(off + __popc(peers[u]));
+        if (ok && r[u] == 0) wc[dg[u]] = off + __popc(peers[u]);
         __syncwarp();
         if (ok) {
           const uint32_t pos = sTot[dg[u]] + off + r[u];

@@ -331,6 +331,27 @@ def test_pipelined_one_shot_equals_resident(engine):
     parity.check_against_oracle(w, b_po, b_ao, distros=[0, 1, 2, 150, 329])
 
 
+# ---------------------------------------------------------------- full-size configs
+@pytest.mark.parametrize("k", [3, 4, 5])
+def test_configs_full_distro_counts(engine, k):
+    """BASELINE configs[2..4] at their full DISTRO counts (10k / 10k / 100k distros; the "N tasks" of configs[2]
+    and [3] read as the tick total), every distro compared bit-exactly with the oracle."""
+    w = synth.config(k, 1.0)
+    po, ao = run(engine, w)
+    parity.check_properties(w, po, ao)
+    parity.check_against_oracle(w, po, ao, threads=32)
+
+
+def test_config3_per_distro_reading_scaled(engine):
+    """configs[2] read per distro (100k tasks in ONE distro queue): 24 such distros take the general
+    (global-memory) path; oracle on all of them."""
+    w = synth.config(3, 0.0024, each=True)
+    assert w.distros.n_distros == 24 and w.n_tasks == 2_400_000
+    po, ao = run(engine, w)
+    parity.check_properties(w, po, ao)
+    parity.check_against_oracle(w, po, ao, threads=32)
+
+
 # ---------------------------------------------------------------- full-size properties
 def test_c2_full_size_properties(engine):
     """BASELINE configs[1] at full size: 1000 distros x 10k tasks (1e7 tasks).  The oracle checks a
