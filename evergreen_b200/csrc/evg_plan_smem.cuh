@@ -293,7 +293,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
   // and -- when TaskGroupOrder is unique inside each group, which is what a task group's order means -- a
   // member's rank inside its unit is the number of smaller orders present (a 64-bit presence mask).
   // Anything else (orders >= 64, duplicate orders, too many groups, breakdown mode) falls back to the unit lists.
-  constexpr int kGroupCap = (4 * CAP) / 52;
+  constexpr int kGroupCap = (4 * CAP) / 84;
   unsigned long long* gTiq = reinterpret_cast<unsigned long long*>(sIdx);  // the staging area is idle again
   unsigned long long* gRt = gTiq + kGroupCap;
   unsigned long long* gMask = gRt + kGroupCap;
@@ -303,7 +303,15 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
   unsigned int* gFlags = reinterpret_cast<unsigned int*>(gMaxD + kGroupCap);
   unsigned int* gN = gFlags + kGroupCap;
   unsigned int* gAnchor = gN + kGroupCap;
+  // TaskGroupInfo sums of the same groups (scheduler.go:79-137), written out once per group
+  unsigned long long* qExp = reinterpret_cast<unsigned long long*>(gAnchor + kGroupCap + (kGroupCap & 1));
+  unsigned long long* qDurOver = qExp + kGroupCap;
+  unsigned int* qCnt = reinterpret_cast<unsigned int*>(qDurOver + kGroupCap);
+  unsigned int* qOver = qCnt + kGroupCap;
+  unsigned int* qWait = qOver + kGroupCap;
+  unsigned int* qMq = qWait + kGroupCap;
   bool fast_tg = any && !gv && !has_edges && !lists_needed && int(ng) <= kGroupCap;
+  const bool smem_ginfo = fast_tg;  // stays true even if the rank shortcut later falls back
 
   if (any) {
     // ---- phase 2b: task-group sums (scheduler.go:79-137) ----
@@ -311,6 +319,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       for (int g = tid; g < int(ng); g += THREADS) {
         gTiq[g] = 0ull; gRt[g] = 0ull; gMask[g] = 0ull; gMaxP[g] = 0; gMaxD[g] = 0; gFlags[g] = 0u; gN[g] = 0u;
         gAnchor[g] = kNoAnchor;
+        qExp[g] = 0ull; qDurOver[g] = 0ull; qCnt[g] = 0u; qOver[g] = 0u; qWait[g] = 0u; qMq[g] = 0u;
       }
     __syncthreads();
     for (int k = tid; k < n_work; k += THREADS) {
@@ -326,13 +335,20 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       const bool over = counted && exp_ns > threshold;
       const bool wait_over = counted && dm && since(now, T.wbasis[t]) > threshold;
       const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
-      evg_group_info* g = W.ginfo + D.group_off[d] + gid;
-      atomic_add64(&g->count, counted);
-      atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
-      atomic_add64(&g->count_duration_over_threshold, over);
-      atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
-      atomic_add64(&g->count_wait_over_threshold, wait_over);
-      atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
+      if (smem_ginfo) {
+        if (counted) { atomicAdd(&qCnt[gid], 1u); atomicAdd(&qExp[gid], (unsigned long long)exp_ns); }
+        if (over) { atomicAdd(&qOver[gid], 1u); atomicAdd(&qDurOver[gid], (unsigned long long)exp_ns); }
+        if (wait_over) atomicAdd(&qWait[gid], 1u);
+        if (mq_dm) atomicAdd(&qMq[gid], 1u);
+      } else {
+        evg_group_info* g = W.ginfo + D.group_off[d] + gid;
+        atomic_add64(&g->count, counted);
+        atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
+        atomic_add64(&g->count_duration_over_threshold, over);
+        atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
+        atomic_add64(&g->count_wait_over_threshold, wait_over);
+        atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
+      }
       if (fast_tg) {  // Unit.info (planner.go:302-337) of the task-group unit, member by member
         const int32_t tgo = T.tgo[t];
         if (tgo < 0 || tgo >= 64) { S->tg_fallback = 1; continue; }
@@ -357,6 +373,13 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     if (fast_tg) {
       // ---- phase 3 (list-free): score each task group's unit (planner.go:209-300) ----
       for (int g = tid; g < int(ng); g += THREADS) {
+        evg_group_info* gi = W.ginfo + D.group_off[d] + g;  // one writer per row (max_hosts was set in phase 1)
+        gi->count = qCnt[g];
+        gi->expected_duration = int64_t(qExp[g]);
+        gi->count_duration_over_threshold = qOver[g];
+        gi->duration_over_threshold = int64_t(qDurOver[g]);
+        gi->count_wait_over_threshold = qWait[g];
+        gi->count_dep_filled_merge_queue_tasks = qMq[g];
         if (gN[g] != uint32_t(__popcll(gMask[g]))) { S->tg_fallback = 1; continue; }  // duplicate TaskGroupOrder
         UnitAcc a;
         a.tiq = int64_t(gTiq[g]); a.rt = int64_t(gRt[g]); a.max_p = gMaxP[g]; a.max_d = gMaxD[g];
@@ -629,26 +652,46 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       }
     }
     __syncthreads();
-    for (int dgt = tid; dgt < 256; dgt += THREADS) {
-      uint32_t run = 0;
-      for (int w = 0; w < NW; w++) {
-        const uint32_t x = wcAll[w * 256 + dgt];
-        wcAll[w * 256 + dgt] = run;
-        run += x;
-      }
-      sTot[dgt] = run;
+    // per-digit totals of each slice of warps, digit bases, then running offsets (base folded in)
+    constexpr int PARTS = THREADS >= 256 ? THREADS / 256 : 1;
+    constexpr int WPP = NW / PARTS;
+    uint32_t* sPart = reinterpret_cast<uint32_t*>(sWc);  // [PARTS][256]; the work list is dead by now
+    for (int x = tid; x < 256 * PARTS; x += THREADS) {
+      const int dgt = x & 255, part = x >> 8;
+      uint32_t sum = 0;
+#pragma unroll
+      for (int w = 0; w < WPP; w++) sum += wcAll[(part * WPP + w) * 256 + dgt];
+      sPart[part * 256 + dgt] = sum;
     }
     __syncthreads();
     if (warp == 0) {  // exclusive scan of the 256 digit totals
       uint32_t v[8], sum = 0;
 #pragma unroll
-      for (int k = 0; k < 8; k++) { v[k] = sTot[lane * 8 + k]; sum += v[k]; }
+      for (int k = 0; k < 8; k++) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int pp = 0; pp < PARTS; pp++) tot += sPart[pp * 256 + lane * 8 + k];
+        v[k] = tot;
+        sum += tot;
+      }
       uint32_t inc = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(full, inc, o); if (lane >= o) inc += x; }
       uint32_t run = inc - sum;
 #pragma unroll
       for (int k = 0; k < 8; k++) { sTot[lane * 8 + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    for (int x = tid; x < 256 * PARTS; x += THREADS) {
+      const int dgt = x & 255, part = x >> 8;
+      uint32_t run = sTot[dgt];
+      for (int pp = 0; pp < part; pp++) run += sPart[pp * 256 + dgt];
+#pragma unroll
+      for (int w = 0; w < WPP; w++) {
+        const uint32_t xx = wcAll[(part * WPP + w) * 256 + dgt];
+        wcAll[(part * WPP + w) * 256 + dgt] = run;
+        run += xx;
+      }
     }
     __syncthreads();
     for (int s0 = seg0; s0 < seg1; s0 += 64) {
@@ -669,12 +712,10 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       for (int u = 0; u < 2; u++) {  // chunks in order: stability
         const bool ok = dg[u] != 0xFFFFu;
         uint32_t off = 0;
-        if (ok) off = wc[dg[u]];
-        __syncwarp();
-        if (ok && r[u] == 0) wc[dg[u]] = off + __popc(peers[u]);
-        __syncwarp();
+        if (ok && r[u] == 0) off = atomicAdd(&wc[dg[u]], (uint32_t)__popc(peers[u]));
+        off = __shfl_sync(full, off, __ffs(peers[u]) - 1);
         if (ok) {
-          const uint32_t pos = sTot[dg[u]] + off + r[u];
+          const uint32_t pos = off + r[u];
           kn[pos] = kk[u];
           in_[pos] = ii[u];
         }
