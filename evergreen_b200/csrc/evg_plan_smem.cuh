@@ -34,6 +34,8 @@ struct PlanShared {
   // queue-info block accumulators
   unsigned int c[10];
   unsigned long long s[4];
+  unsigned int tgc[5];           // task-group tasks: n, counted, over, wait, merge-queue
+  unsigned long long tgs[2];     // task-group tasks: expected sum, over-threshold sum
 };
 
 // cp.async (LDGSTS): global -> shared without a register round trip
@@ -119,6 +121,8 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     S->tg_fallback = 0;
     for (int k = 0; k < 10; k++) S->c[k] = 0;
     for (int k = 0; k < 4; k++) S->s[k] = 0;
+    for (int k = 0; k < 5; k++) S->tgc[k] = 0;
+    S->tgs[0] = 0; S->tgs[1] = 0;
   }
   for (int i = tid; i < CAP / 32; i += THREADS) { sHasDep[i] = 0; sDisp[i] = 0; }
   __syncthreads();
@@ -155,8 +159,9 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
   // compacted into a work list so the list phases below run with full warps ----
   uint16_t* sList = sWc;                      // free until the sort
   constexpr int kListCap = NW * 256;
-  unsigned int c_dm = 0, c_mq = 0, c_over = 0, c_wait = 0, c_sec = 0, u_n = 0, u_cnt = 0, u_over = 0, u_wait = 0, u_mq = 0;
-  int64_t s_exp = 0, s_over = 0, s_uexp = 0, s_uover = 0;
+  // distro totals only; the "" group is totals minus the task-group tasks, which phase 2b sums over the work list
+  unsigned int c_dm = 0, c_mq = 0, c_over = 0, c_wait = 0, c_sec = 0, c_cnt = 0;
+  int64_t s_exp = 0, s_over = 0;
   const int64_t threshold = cfg.target_time_ns;
   const PlannerFactors pf = clamp_factors(cfg);
   // since(now, wb) > threshold  <=>  wb < now - threshold whenever 0 <= threshold <= now (no overflow on either
@@ -210,17 +215,11 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       const bool wait_over = counted && dm && (sane_clock ? wb < wait_cutoff : since(now, wb) > threshold);
       const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
       c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += (fl & EVG_TF_OTHER_DISTRO) != 0;
+      c_cnt += counted;
       if (counted) s_exp += exp_ns;
       if (over) s_over += exp_ns;
-      if (gid < 0) {
-        u_n += 1; u_cnt += counted; u_over += over; u_wait += wait_over; u_mq += mq_dm;
-        if (counted) s_uexp += exp_ns;
-        if (over) s_uover += exp_ns;
-      }
       const bool own_complex = any && (gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31))));
       complex_task = own_complex || (has_edges && T.dep_off[t + 1] > T.dep_off[t]);
-      sA[i] = uint16_t(i);
-      sRk[i] = 0;
       if (!own_complex) sV[i] = single_task_value(pf, now, prio, exp_ns, qb, nd, fl);  // unit == {this task}
     }
     if (any) {  // warp-aggregated append
@@ -236,45 +235,22 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       }
     }
   }
-  // fold the queue-info partials: warp shuffle, then shared atomics, then one writer
+  // fold the queue-info partials: warp shuffle, then shared atomics; the row is written after phase 2b
   {
-    unsigned int cs[10] = {c_dm, c_mq, c_over, c_wait, c_sec, u_n, u_cnt, u_over, u_wait, u_mq};
+    unsigned int cs[6] = {c_dm, c_mq, c_over, c_wait, c_sec, c_cnt};
 #pragma unroll
-    for (int k = 0; k < 10; k++) cs[k] = __reduce_add_sync(full, cs[k]);
-    int64_t ss[4] = {s_exp, s_over, s_uexp, s_uover};
+    for (int k = 0; k < 6; k++) cs[k] = __reduce_add_sync(full, cs[k]);
+    int64_t ss[2] = {s_exp, s_over};
 #pragma unroll
-    for (int k = 0; k < 4; k++) ss[k] = warp_sum64(ss[k]);
+    for (int k = 0; k < 2; k++) ss[k] = warp_sum64(ss[k]);
     if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < 10; k++) if (cs[k]) atomicAdd(&S->c[k], cs[k]);
+      for (int k = 0; k < 6; k++) if (cs[k]) atomicAdd(&S->c[k], cs[k]);
 #pragma unroll
-      for (int k = 0; k < 4; k++) if (ss[k]) atomicAdd(&S->s[k], (unsigned long long)ss[k]);
+      for (int k = 0; k < 2; k++) if (ss[k]) atomicAdd(&S->s[k], (unsigned long long)ss[k]);
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    evg_queue_info q;
-    q.length = tn;
-    q.length_with_dependencies_met = S->c[0];
-    q.count_dep_filled_merge_queue_tasks = S->c[1];
-    q.expected_duration = int64_t(S->s[0]);
-    q.max_duration_threshold = threshold;
-    q.count_duration_over_threshold = S->c[2];
-    q.duration_over_threshold = int64_t(S->s[1]);
-    q.count_wait_over_threshold = S->c[3];
-    q.secondary_queue = S->c[4] != 0;
-    q.has_ungrouped = S->c[5] != 0;
-    q.ungrouped.count = S->c[6];
-    q.ungrouped.count_free = 0;
-    q.ungrouped.count_required = 0;
-    q.ungrouped.max_hosts = 0;
-    q.ungrouped.expected_duration = int64_t(S->s[2]);
-    q.ungrouped.count_duration_over_threshold = S->c[7];
-    q.ungrouped.count_wait_over_threshold = S->c[8];
-    q.ungrouped.count_dep_filled_merge_queue_tasks = S->c[9];
-    q.ungrouped.duration_over_threshold = int64_t(S->s[3]);
-    W.qinfo[d] = q;
-  }
 
   // The list phases iterate the compacted work list (or, if it overflowed, every task with a filter).
   const int n_list = int(S->n_list);
@@ -322,6 +298,8 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
         qExp[g] = 0ull; qDurOver[g] = 0ull; qCnt[g] = 0u; qOver[g] = 0u; qWait[g] = 0u; qMq[g] = 0u;
       }
     __syncthreads();
+    unsigned int t_n = 0, t_cnt = 0, t_over = 0, t_wait = 0, t_mq = 0;
+    int64_t t_exp = 0, t_dover = 0;
     for (int k = tid; k < n_work; k += THREADS) {
       const int i = work_item(k);
       if (i < 0) continue;
@@ -335,6 +313,9 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       const bool over = counted && exp_ns > threshold;
       const bool wait_over = counted && dm && since(now, T.wbasis[t]) > threshold;
       const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
+      t_n += 1; t_cnt += counted; t_over += over; t_wait += wait_over; t_mq += mq_dm;
+      if (counted) t_exp += exp_ns;
+      if (over) t_dover += exp_ns;
       if (smem_ginfo) {
         if (counted) { atomicAdd(&qCnt[gid], 1u); atomicAdd(&qExp[gid], (unsigned long long)exp_ns); }
         if (over) { atomicAdd(&qOver[gid], 1u); atomicAdd(&qDurOver[gid], (unsigned long long)exp_ns); }
@@ -368,6 +349,11 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
         atomicMin(&gAnchor[gid], uint32_t(i));
         atomicOr(&gMask[gid], 1ull << tgo);
       }
+    }
+    if (t_n) {  // few threads carry task-group tasks: plain shared atomics
+      atomicAdd(&S->tgc[0], t_n); atomicAdd(&S->tgc[1], t_cnt); atomicAdd(&S->tgc[2], t_over);
+      atomicAdd(&S->tgc[3], t_wait); atomicAdd(&S->tgc[4], t_mq);
+      atomicAdd(&S->tgs[0], (unsigned long long)t_exp); atomicAdd(&S->tgs[1], (unsigned long long)t_dover);
     }
     __syncthreads();
     if (fast_tg) {
@@ -515,6 +501,30 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     __syncthreads();
   }
 
+  if (tid == 0) {  // DistroQueueInfo row (scheduler.go:144-158); "" group = totals - task-group tasks
+    evg_queue_info q;
+    q.length = tn;
+    q.length_with_dependencies_met = S->c[0];
+    q.count_dep_filled_merge_queue_tasks = S->c[1];
+    q.expected_duration = int64_t(S->s[0]);
+    q.max_duration_threshold = threshold;
+    q.count_duration_over_threshold = S->c[2];
+    q.duration_over_threshold = int64_t(S->s[1]);
+    q.count_wait_over_threshold = S->c[3];
+    q.secondary_queue = S->c[4] != 0;
+    q.has_ungrouped = (unsigned int)tn > S->tgc[0];
+    q.ungrouped.count = S->c[5] - S->tgc[1];
+    q.ungrouped.count_free = 0;
+    q.ungrouped.count_required = 0;
+    q.ungrouped.max_hosts = 0;
+    q.ungrouped.expected_duration = int64_t(S->s[0] - S->tgs[0]);
+    q.ungrouped.count_duration_over_threshold = S->c[2] - S->tgc[2];
+    q.ungrouped.count_wait_over_threshold = S->c[3] - S->tgc[3];
+    q.ungrouped.count_dep_filled_merge_queue_tasks = S->c[1] - S->tgc[4];
+    q.ungrouped.duration_over_threshold = int64_t(S->s[1] - S->tgs[1]);
+    W.qinfo[d] = q;
+  }
+
   // ---- phase 5: value range ----
   {
     unsigned long long mx = 0ull, mn = ~0ull;
@@ -537,7 +547,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     for (int i = tid; i < CAP / 2; i += THREADS) e32[i] = 0;
     __syncthreads();
     for (int i = tid; i < tn; i += THREADS) {
-      const uint32_t a = sA[i];
+      const uint32_t a = (sDisp[i >> 5] & (1u << (i & 31))) ? uint32_t(sA[i]) : uint32_t(i);  // anchor of a task emitted alone / first is itself
       atomicAdd(&e32[a >> 1], 1u << (16 * (a & 1)));
     }
     __syncthreads();
@@ -563,7 +573,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     for (int k = 0; k < ITEMS; k++) { sE[tid * ITEMS + k] = uint16_t(run); run += loc[k]; }
     __syncthreads();
     for (int i = tid; i < tn; i += THREADS)
-      if (!(sDisp[i >> 5] & (1u << (i & 31)))) sIdx[sE[sA[i]]] = uint16_t(i);  // rank 0 of its anchor
+      if (!(sDisp[i >> 5] & (1u << (i & 31)))) sIdx[sE[i]] = uint16_t(i);  // rank 0 of its own anchor
     for (int k = tid; k < n_work; k += THREADS) {
       const int i = work_item(k);
       if (i < 0 || !(sDisp[i >> 5] & (1u << (i & 31)))) continue;
