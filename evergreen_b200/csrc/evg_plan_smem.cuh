@@ -100,6 +100,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned full = 0xffffffffu;
 
+  if (*W.err) return;  // k_validate found an out-of-range id in this upload: plan nothing (uniform exit)
   // ---- phase 0: distro header ----
   if (tid == 0) {
     const int d = list[blockIdx.x];

@@ -1,18 +1,20 @@
 // evg_sched.cu -- libevgsched.so: CUDA kernels (sm_100a) + the C-ABI of
 // include/evg_sched.h.  See DESIGN.md for the data layout and the kernel list.
 //
-// General path (any distro size), one tick = all distros concatenated:
-//   k_mark_dependents   dependency edges -> "has in-queue dependents" byte     (planner.go:449-456)
-//   k_task              per task: queue-info reduction (scheduler.go:56-159),
-//                       unit membership links (planner.go:431-447), score of
-//                       single-task units (planner.go:209-337)
-//   k_unit              per (unit, member) pair: Unit.info reduction, score,
-//                       canonical tie data, rank inside the unit (planner.go:302-405)
-//   k_best              per task: first unit it is emitted from (planner.go:467-477)
-//   k_sort_*            per-distro segmented LSD radix sort (TaskPlan.Export, planner.go:462-481)
-//   k_emit              ranked queue + TotalValue (+ full breakdown on request)
-//   k_finalize_info     DistroQueueInfo / TaskGroupInfo scalars (scheduler.go:144-158)
-//   k_alloc             utilization host allocator (utilization_based_host_allocator.go:26-409)
+// Distros are routed by size on the host:
+//   <= 12288 tasks   k_plan_smem<THREADS,ITEMS> (evg_plan_smem.cuh): one CTA plans the distro on-chip
+//   larger           the general path below, any size up to 2^21-1 tasks:
+//     k_mark_dependents   dependency edges -> "has in-queue dependents" byte     (planner.go:449-456)
+//     k_task              per task: queue-info reduction (scheduler.go:56-159), unit membership
+//                         links (planner.go:431-447), score of single-task units (planner.go:209-337)
+//     k_unit              per (unit, member) pair: Unit.info reduction, score, anchor, rank in the unit
+//     k_best              per task: first unit it is emitted from (planner.go:467-477)
+//     k_sched/k_sort_*    per-distro segmented stable LSD radix sort over the key bytes that vary
+//     k_emit              ranked queue + TotalValue
+//     k_finalize_info     DistroQueueInfo / TaskGroupInfo scalars (scheduler.go:144-158)
+// Both:
+//   k_breakdown           the 13-field SortingValueBreakdown per ranked task (EVG_OPT_BREAKDOWN)
+//   k_alloc               utilization host allocator, one warp per distro (utilization_based_host_allocator.go:26-409)
 // No CPU fallback exists in this file: without a device every entry point fails.
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -81,6 +83,7 @@ constexpr int kChunks = kTile / 32;
 constexpr int kMaxPass = 16;       // 8 tie bytes + 8 value bytes
 // on-chip planner classes <THREADS, ITEMS>: capacity = THREADS*ITEMS tasks per distro
 constexpr int kCapA = 128 * 8, kCapB = 256 * 16, kCapC = 1024 * 12;
+constexpr int kCapW = 32;  // k_plan_warp: one warp per distro
 constexpr uint32_t kInactive = 0xFFFFFFFFu;  // next[]: pair not linked / head[]: empty list
 constexpr uint32_t kEnd = 0xFFFFFFFEu;       // next[]: end of list
 constexpr uint32_t kNoAnchor = 0xFFFFFFFFu;
@@ -128,6 +131,7 @@ struct DWork {
   uint32_t* edge_task;   // [E]
   uint8_t* edge_live;    // [E] on-chip path: 1 = edge pair linked (not a duplicate membership)
   const uint8_t* route;  // [D] 1 = distro planned by k_plan_smem (general kernels skip it)
+  int* err;              // [1] set by k_validate when a distro-local id is out of range; planners then do nothing
   int64_t* cand_v;       // [2T+E]
   uint32_t* cand_a;      // [2T+E]
   uint32_t* cand_rk;     // [2T+E]
@@ -247,13 +251,34 @@ __device__ __forceinline__ uint32_t pair_task(const DTasks& T, const DWork& W, u
 }
 
 #include "evg_plan_smem.cuh"
+#include "evg_plan_warp.cuh"
 
 // --------------------------------------------------------------------------
 // kernels (general path: any distro size)
 // --------------------------------------------------------------------------
 
+// Distro-local ids index device tables directly, so they are range-checked once per upload:
+// group_id in [-1, n_groups), version_id in [0, n_versions), dep_idx in [0, tasks of the distro).
+__global__ void __launch_bounds__(256) k_validate(DTasks T, DDistros D, DWork W, int64_t t_begin, int64_t t_end) {
+  const int64_t t = t_begin + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= t_end) return;
+  const int d = find_distro(D.task_off, 0, D.n - 1, t);
+  const int64_t tn = D.task_off[d + 1] - D.task_off[d];
+  const int64_t ng = D.group_off[d + 1] - D.group_off[d];
+  const int32_t gid = T.gid[t], vid = T.vid[t];
+  bool bad = gid < -1 || gid >= ng || vid < 0 || vid >= D.cfg[d].n_versions;
+  if (T.n_edges > 0) {
+    const int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
+    bad = bad || e1 < e0 || e0 < 0 || e1 > T.n_edges;
+    if (!bad)
+      for (int64_t e = e0; e < e1; e++) bad = bad || T.dep_idx[e] < 0 || T.dep_idx[e] >= tn;
+  }
+  if (bad) atomicOr(W.err, 1);
+}
+
 // planner.go:449-456 (pass 2): mark every task some in-queue task depends on.
 __global__ void k_mark_dependents(DTasks T, DDistros D, DWork W) {
+  if (*W.err) return;
   int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   int d = block_find_distro(D.task_off, D.n, t, T.n);
   if (d < 0 || W.route[d]) return;
@@ -265,6 +290,7 @@ __global__ void k_mark_dependents(DTasks T, DDistros D, DWork W) {
 // Per task: queue info (scheduler.go:56-159), unit links (planner.go:431-456),
 // and the score of units that are provably {this task} (planner.go:209-337).
 __global__ void __launch_bounds__(256) k_task(DTasks T, DDistros D, DWork W, int64_t now, int any_complex) {
+  if (*W.err) return;
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int d = block_find_distro(D.task_off, D.n, t, T.n);
   const bool valid = d >= 0 && !W.route[d];
@@ -406,7 +432,7 @@ __global__ void __launch_bounds__(256) k_task(DTasks T, DDistros D, DWork W, int
 // unit's score, its anchor and this member's rank inside the unit.
 __global__ void __launch_bounds__(256) k_unit(DTasks T, DDistros D, DWork W, int64_t now, int64_t n_pairs) {
   const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
+  if (p >= n_pairs || *W.err) return;
   // resolve the owning distro first: pairs of on-chip distros belong to k_plan_smem
   uint32_t t;
   if (p < T.n) t = uint32_t(p);
@@ -421,6 +447,7 @@ __global__ void __launch_bounds__(256) k_unit(DTasks T, DDistros D, DWork W, int
 // Per task: the unit it is emitted from = best of its memberships under the
 // canonical unit order (TaskPlan.Export first-occurrence rule, planner.go:467-477).
 __global__ void __launch_bounds__(256) k_best(DTasks T, DDistros D, DWork W) {
+  if (*W.err) return;
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int d = block_find_distro(D.task_off, D.n, t, T.n);
   const bool valid = d >= 0 && !W.route[d];
@@ -599,6 +626,7 @@ __global__ void __launch_bounds__(256) k_emit(DTasks T, DDistros D, DWork W, int
 // from (planner.go:472-476, model/task/task.go:3990-4038); both paths.
 __global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W, int64_t now, int any_complex,
                                                    const int32_t* order, int64_t* breakdown) {
+  if (*W.err) return;
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int d = block_find_distro(D.task_off, D.n, t, T.n);
   if (d < 0) return;
@@ -783,9 +811,10 @@ struct evg_ctx {
   DevBuf b_prio, b_exp, b_qb, b_wb, b_nd, b_tgo, b_gid, b_vid, b_flags, b_depoff, b_depidx;
   DevBuf b_taskoff, b_groupoff, b_cfg, b_gmax, b_unitbase;
   DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_cv, b_ca, b_crk, b_bestpair;
-  DevBuf b_route, b_listA, b_listB, b_listC, b_unitv, b_unita, b_unitn, b_unitmask;
-  int32_t nA = 0, nB = 0, nC = 0, n_general = 0;  // distros per on-chip class / general path
-  std::vector<int32_t> h_listA, h_listB, h_listC;  // host copies (ascending distro ids) for the pipelined one-shot call
+  DevBuf b_err;
+  DevBuf b_route, b_listW, b_listA, b_listB, b_listC, b_unitv, b_unita, b_unitn, b_unitmask;
+  int32_t nW = 0, nA = 0, nB = 0, nC = 0, n_general = 0;  // distros per on-chip class / general path
+  std::vector<int32_t> h_listW, h_listA, h_listB, h_listC;  // host copies (ascending distro ids) for the pipelined one-shot call
   std::vector<int64_t> h_taskoff, h_groupoff;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   static constexpr int kMaxChunks = 16;
@@ -803,6 +832,11 @@ struct evg_ctx {
 
 namespace {
 
+DTasks dtasks(const evg_ctx* c);
+DDistros ddistros(const evg_ctx* c);
+DWork dwork(const evg_ctx* c);
+inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1) / block); }
+
 int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, bool copy_columns = true) {
   if (!t || !dt) return fail(EVG_ERR_INVALID, "null task table / distro table");
   const int64_t T = t->n_tasks, E = t->n_edges;
@@ -817,7 +851,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   if (E > 0 && (!t->dep_off || !t->dep_idx)) return fail(EVG_ERR_INVALID, "n_edges > 0 but dep_off/dep_idx null");
   if (D == 0 && T != 0) return fail(EVG_ERR_INVALID, "tasks without distros");
   std::vector<int64_t> unit_base(size_t(D) + 1, 0), dtile_off(size_t(D) + 1, 0);
-  std::vector<int32_t> tile_distro, listA, listB, listC;
+  std::vector<int32_t> tile_distro, listW, listA, listB, listC;
   std::vector<int64_t> tile_start;
   std::vector<uint8_t> route(size_t(D) + 1, 0);
   int32_t n_general = 0;
@@ -835,7 +869,8 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
     unit_base[d + 1] = unit_base[d] + (gb - ga) + (cf.group_versions ? int64_t(cf.n_versions) : (b - a));
     // route: small distros are planned on-chip by k_plan_smem, the rest by the general path
     const int64_t n = b - a;
-    if (n <= kCapA) { listA.push_back(d); route[d] = 1; }
+    if (n <= kCapW) { listW.push_back(d); route[d] = 1; }
+    else if (n <= kCapA) { listA.push_back(d); route[d] = 1; }
     else if (n <= kCapB) { listB.push_back(d); route[d] = 1; }
     else if (n <= kCapC) { listC.push_back(d); route[d] = 1; }
     else {
@@ -887,6 +922,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   UP(c->b_tilestart, tile_start.data(), NT, int64_t);
   UP(c->b_dtileoff, dtile_off.data(), D + 1, int64_t);
   UP(c->b_route, route.data(), D + 1, uint8_t);
+  UP(c->b_listW, listW.data(), int64_t(listW.size()), int32_t);
   UP(c->b_listA, listA.data(), int64_t(listA.size()), int32_t);
   UP(c->b_listB, listB.data(), int64_t(listB.size()), int32_t);
   UP(c->b_listC, listC.data(), int64_t(listC.size()), int32_t);
@@ -925,14 +961,28 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   CK(c->b_tv.ensure(sizeof(int64_t) * size_t(T + 1)));
   c->T = T; c->E = E; c->G = G; c->U = U; c->NT = NT; c->Dn = D;
   c->any_complex = any_complex;
+  c->nW = int32_t(listW.size());
   c->nA = int32_t(listA.size()); c->nB = int32_t(listB.size()); c->nC = int32_t(listC.size());
   c->n_general = n_general;
   c->general_complex = general_complex;
+  CK(c->b_err.ensure(sizeof(int) * 4));
+  CK(cudaMemsetAsync(c->b_err.p, 0, sizeof(int) * 4, s));
+  c->h_listW.swap(listW);
   c->h_listA.swap(listA); c->h_listB.swap(listB); c->h_listC.swap(listC);
   c->h_taskoff.assign(dt->task_off, dt->task_off + D + 1);
   c->h_groupoff.assign(dt->group_off, dt->group_off + D + 1);
   c->have_tasks = true;
   c->have_hosts = false;
+  if (copy_columns && T > 0) {  // range-check the ids the kernels index with (the pipelined call checks chunk by chunk)
+    DTasks dtv = dtasks(c);
+    DDistros ddv = ddistros(c);
+    DWork wv = dwork(c);
+    k_validate<<<grid_for(T, 256), 256, 0, s>>>(dtv, ddv, wv, 0, T);
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (bad) { c->have_tasks = false; return fail(EVG_ERR_INVALID, "a group_id / version_id / dep_idx is out of range for its distro"); }
+  }
   return EVG_OK;
 }
 
@@ -982,6 +1032,7 @@ DWork dwork(const evg_ctx* c) {
   w.has_dep = c->b_hasdep.as<uint8_t>(); w.head = c->b_head.as<uint32_t>(); w.next = c->b_next.as<uint32_t>();
   w.pair_slot = c->b_pslot.as<uint32_t>(); w.edge_task = c->b_etask.as<uint32_t>();
   w.edge_live = c->b_elive.as<uint8_t>(); w.route = c->b_route.as<uint8_t>();
+  w.err = c->b_err.as<int>();
   w.unit_v = c->b_unitv.as<int64_t>(); w.unit_a = c->b_unita.as<uint32_t>(); w.unit_n = c->b_unitn.as<uint32_t>();
   w.unit_mask = c->b_unitmask.as<unsigned long long>();
   w.cand_v = c->b_cv.as<int64_t>(); w.cand_a = c->b_ca.as<uint32_t>();
@@ -996,8 +1047,6 @@ DWork dwork(const evg_ctx* c) {
   w.qinfo = c->b_qinfo.as<evg_queue_info>(); w.ginfo = c->b_ginfo.as<evg_group_info>();
   return w;
 }
-
-inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1) / block); }
 
 #define LAUNCH(c, kernel, grid, block, ...)                                  \
   do {                                                                       \
@@ -1029,6 +1078,18 @@ int launch_smem(evg_ctx* c, const DTasks& dt, const DDistros& dd, const DWork& w
   CK(cudaFuncSetAttribute(k_plan_smem<THREADS, ITEMS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
   k_plan_smem<THREADS, ITEMS, MIN_CTAS><<<unsigned(n), THREADS, bytes, c->stream>>>(dt, dd, w, list, now, lists_needed,
                                                                           c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
+  c->launches++;
+  return EVG_OK;
+}
+
+// Distros of at most 32 tasks: one warp each (k_plan_warp).  Breakdown mode needs the unit lists, so it
+// sends them through the smallest on-chip class instead.
+int launch_tiny(evg_ctx* c, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n, int64_t now,
+                int lists_needed) {
+  if (n <= 0) return EVG_OK;
+  if (lists_needed) return launch_smem<128, 8, 8>(c, dt, dd, w, list, n, now, 1);
+  k_plan_warp<<<grid_for(int64_t(n) * 32, 256), 256, 0, c->stream>>>(dt, dd, w, list, n, now, c->b_order.as<int32_t>(),
+                                                                  c->b_tv.as<int64_t>());
   c->launches++;
   return EVG_OK;
 }
@@ -1073,6 +1134,7 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
   if (c->timed) { CK(cudaEventRecord(c->ring1[slot], s)); c->runs++; }
   if ((rc = launch_smem<256, 16, 3>(c, dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now, bd ? 1 : 0)) != EVG_OK) return rc;
   if ((rc = launch_smem<128, 8, 8>(c, dt, dd, w, c->b_listA.as<int32_t>(), c->nA, now, bd ? 1 : 0)) != EVG_OK) return rc;
+  if ((rc = launch_tiny(c, dt, dd, w, c->b_listW.as<int32_t>(), c->nW, now, bd ? 1 : 0)) != EVG_OK) return rc;
   if (c->timed) CK(cudaEventRecord(c->ev_sort1, s));
   if (general) {
     const int gc = c->general_complex;
@@ -1136,7 +1198,7 @@ void evg_shutdown(evg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->b_prio, &c->b_exp, &c->b_qb, &c->b_wb, &c->b_nd, &c->b_tgo, &c->b_gid, &c->b_vid, &c->b_flags,
                    &c->b_depoff, &c->b_depidx, &c->b_taskoff, &c->b_groupoff, &c->b_cfg, &c->b_gmax, &c->b_unitbase,
-                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita, &c->b_unitn, &c->b_unitmask, &c->b_route, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_cv, &c->b_ca, &c->b_crk,
+                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita, &c->b_unitn, &c->b_unitmask, &c->b_err, &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_cv, &c->b_ca, &c->b_crk,
                    &c->b_bestpair, &c->b_ks[0], &c->b_ks[1], &c->b_kv[0], &c->b_kv[1], &c->b_ix[0], &c->b_ix[1], &c->b_bits,
                    &c->b_npass, &c->b_sched, &c->b_maxpass, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
@@ -1319,6 +1381,7 @@ static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg
     }
     CK(cudaEventRecord(c->ev_h[k], c->s_h2d));
     CK(cudaStreamWaitEvent(s, c->ev_h[k], 0));
+    k_validate<<<grid_for(n, 256), 256, 0, s>>>(dtk, dd, w, t0, t0 + n);
     int32_t first, cnt;
     cnt = sub(c->h_listC, d0, d1, &first);
     if ((rc = launch_smem<1024, 12, 1>(c, dtk, dd, w, c->b_listC.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
@@ -1326,6 +1389,8 @@ static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg
     if ((rc = launch_smem<256, 16, 3>(c, dtk, dd, w, c->b_listB.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
     cnt = sub(c->h_listA, d0, d1, &first);
     if ((rc = launch_smem<128, 8, 8>(c, dtk, dd, w, c->b_listA.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
+    cnt = sub(c->h_listW, d0, d1, &first);
+    if ((rc = launch_tiny(c, dtk, dd, w, c->b_listW.as<int32_t>() + first, cnt, now, 0)) != EVG_OK) return rc;
     LAUNCH(c, k_alloc, grid_for(int64_t(d1 - d0) * 32, 128), 128, h, d0, d1, c->b_groupoff.as<int64_t>(),
            c->b_qinfo.as<evg_queue_info>(), c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now,
            c->result_ptr(), c->b_status.as<int32_t>());
@@ -1345,8 +1410,11 @@ static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg
 #undef H2D
 #undef D2H
   CK(cudaGetLastError());
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(c->s_d2h));
   CK(cudaStreamSynchronize(s));
+  if (bad) { c->have_tasks = false; return fail(EVG_ERR_INVALID, "a group_id / version_id / dep_idx is out of range for its distro"); }
   c->have_hosts = true;
   return EVG_OK;
 }

@@ -286,6 +286,41 @@ def test_odd_clocks(engine, now):
     parity.check_against_oracle(w, po, ao)
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_tiny_distros_warp_path(engine, seed):
+    """Distros of 0..32 tasks are planned one warp each (k_plan_warp): task groups, GroupVersions, met and
+    unmet in-queue dependencies, custom factors, all mixed; plus the breakdown, which reroutes them on-chip."""
+    rng = synth.Rng(300 + seed)
+    sizes = rng.integers(3000, 0, 32)
+    w = synth.make(sizes, 9000 + seed, zipf_priority=True, unmet_dep_frac=0.08, met_dep_frac=0.05, tg_frac=0.3,
+                   group_versions_frac=0.4, custom_factor_frac=0.5, includes_dependencies=bool(seed & 1),
+                   n_hosts=2000, providers=(0.6, 0.2, 0.2))
+    po, ao = run(engine, w)
+    parity.check_against_oracle(w, po, ao)
+    parity.check_properties(w, po, ao)
+    order, tv = po.order.copy(), po.total_value.copy()
+    po2, _ = run(engine, w, breakdown=True)
+    assert np.array_equal(order, po2.order) and np.array_equal(tv, po2.total_value)
+    ref = parity.check_against_oracle(w, po2, None)
+    assert np.array_equal(po2.breakdown, ref["breakdown"])
+
+
+def test_out_of_range_ids_are_rejected(engine):
+    """Distro-local ids index device tables: the library range-checks them once per upload (k_validate)."""
+    for mutate in (lambda w: w.tasks.group_id.__setitem__(5, 10 ** 6),
+                   lambda w: w.tasks.version_id.__setitem__(7, 10 ** 6),
+                   lambda w: w.tasks.group_id.__setitem__(3, -5),
+                   lambda w: w.tasks.dep_idx.__setitem__(0, 10 ** 6)):
+        w = synth.make(np.array([200, 50, 3000]), 8, tg_frac=0.2, unmet_dep_frac=0.1, includes_dependencies=True)
+        mutate(w)
+        with pytest.raises(L.EvgError) as e:
+            engine.plan_batch(w.tasks, w.distros, w.now)
+        assert e.value.code == L.EVG_ERR_INVALID
+    w = synth.make(np.array([200, 50, 3000]), 8, tg_frac=0.2)
+    po, _ = run(engine, w)  # the context recovers
+    parity.check_against_oracle(w, po, None)
+
+
 def test_bad_arguments_are_errors(engine):
     w = synth.make(np.array([10]), 1)
     bad = copy.deepcopy(w)
