@@ -80,6 +80,18 @@ class HostSoAStruct(C.Structure):
                 ("expected_ns", C.c_void_p), ("std_ns", C.c_void_p), ("start_ns", C.c_void_p)]
 
 
+class DepsInStruct(C.Structure):
+    _fields_ = [("n_tasks", C.c_int64), ("n_deps", C.c_int64), ("dep_off", C.c_void_p), ("dep_kind", C.c_void_p),
+                ("dep_ref", C.c_void_p), ("dep_want", C.c_void_p), ("task_state", C.c_void_p), ("task_pre", C.c_void_p),
+                ("ext_state", C.c_void_p), ("n_ext", C.c_int64)]
+
+
+EVG_DEP_IN_QUEUE, EVG_DEP_EXTERNAL, EVG_DEP_MISSING = 0, 1, 2
+EVG_WANT_SUCCESS, EVG_WANT_FAILED, EVG_WANT_ANY, EVG_WANT_OTHER = 0, 1, 2, 3
+EVG_TS_BLOCKED = 0x4
+EVG_TP_OVERRIDE, EVG_TP_MET_TIME = 0x1, 0x2
+
+
 class AllocOutStruct(C.Structure):
     _fields_ = [("result", C.c_void_p), ("status", C.c_void_p)]
 
@@ -110,6 +122,7 @@ SYMBOLS = {
     "evg_last_launch_count": (C.c_int64, [_P]),
     "evg_last_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "evg_kernel_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
+    "evg_deps_met_batch": (C.c_int, [_P, _P, _P]),
     "evg_plan_distro": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, C.c_uint32, _P]),
     "evg_alloc_distro": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P]),
 }

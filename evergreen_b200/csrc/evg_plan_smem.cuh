@@ -351,10 +351,17 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
         atomicOr(&gMask[gid], 1ull << tgo);
       }
     }
-    if (t_n) {  // few threads carry task-group tasks: plain shared atomics
-      atomicAdd(&S->tgc[0], t_n); atomicAdd(&S->tgc[1], t_cnt); atomicAdd(&S->tgc[2], t_over);
-      atomicAdd(&S->tgc[3], t_wait); atomicAdd(&S->tgc[4], t_mq);
-      atomicAdd(&S->tgs[0], (unsigned long long)t_exp); atomicAdd(&S->tgs[1], (unsigned long long)t_dover);
+    // one shared atomic per warp and field: a 64-bit shared atomicAdd is a CAS spin loop, and the work list
+    // hands nearly every thread one task-group task, so per-thread adds would all fight over two addresses
+    if (__any_sync(full, t_n != 0)) {
+      t_n = __reduce_add_sync(full, t_n); t_cnt = __reduce_add_sync(full, t_cnt); t_over = __reduce_add_sync(full, t_over);
+      t_wait = __reduce_add_sync(full, t_wait); t_mq = __reduce_add_sync(full, t_mq);
+      t_exp = warp_sum64(t_exp); t_dover = warp_sum64(t_dover);
+      if (lane == 0) {
+        atomicAdd(&S->tgc[0], t_n); atomicAdd(&S->tgc[1], t_cnt); atomicAdd(&S->tgc[2], t_over);
+        atomicAdd(&S->tgc[3], t_wait); atomicAdd(&S->tgc[4], t_mq);
+        atomicAdd(&S->tgs[0], (unsigned long long)t_exp); atomicAdd(&S->tgs[1], (unsigned long long)t_dover);
+      }
     }
     __syncthreads();
     if (fast_tg) {

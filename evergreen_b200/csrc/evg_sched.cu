@@ -276,6 +276,50 @@ __global__ void __launch_bounds__(256) k_validate(DTasks T, DDistros D, DWork W,
   if (bad) atomicOr(W.err, 1);
 }
 
+// Task.DependenciesMet over direct dependencies (model/task/task.go:529-543,632-671).
+struct DDeps {
+  int64_t n_tasks;
+  const int64_t* dep_off;
+  const uint8_t* dep_kind;
+  const int32_t* dep_ref;
+  const uint8_t* dep_want;
+  const uint8_t* task_state;
+  const uint8_t* task_pre;
+  const uint8_t* ext_state;
+  int64_t n_ext;
+};
+__global__ void __launch_bounds__(256) k_deps_met(DDeps X, uint8_t* met, int* err) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= X.n_tasks) return;
+  const int64_t e0 = X.dep_off[t], e1 = X.dep_off[t + 1];
+  bool ok = true;
+  if (e1 > e0 && !(X.task_pre[t] & (EVG_TP_OVERRIDE | EVG_TP_MET_TIME))) {  // HasDependenciesMet task.go:3393
+    for (int64_t e = e0; e < e1 && ok; e++) {
+      const uint8_t kind = X.dep_kind[e];
+      const int32_t ref = X.dep_ref[e];
+      uint8_t st;
+      if (kind == EVG_DEP_IN_QUEUE) {
+        if (ref < 0 || ref >= X.n_tasks) { atomicOr(err, 1); ok = false; break; }
+        st = X.task_state[ref];
+      } else if (kind == EVG_DEP_EXTERNAL) {
+        if (ref < 0 || ref >= X.n_ext) { atomicOr(err, 1); ok = false; break; }
+        st = X.ext_state[ref];
+      } else {
+        ok = false;  // lookup error -> false (scheduler.go:161-168)
+        break;
+      }
+      const uint32_t status = st & EVG_TS_STATUS_MASK;
+      switch (X.dep_want[e]) {  // SatisfiesDependency task.go:529-543
+        case EVG_WANT_SUCCESS: ok = status == 0; break;
+        case EVG_WANT_FAILED: ok = status == 1; break;
+        case EVG_WANT_ANY: ok = status < 2 || (st & EVG_TS_BLOCKED); break;
+        default: ok = false;
+      }
+    }
+  }
+  met[t] = ok ? 1 : 0;
+}
+
 // planner.go:449-456 (pass 2): mark every task some in-queue task depends on.
 __global__ void k_mark_dependents(DTasks T, DDistros D, DWork W) {
   if (*W.err) return;
@@ -811,7 +855,7 @@ struct evg_ctx {
   DevBuf b_prio, b_exp, b_qb, b_wb, b_nd, b_tgo, b_gid, b_vid, b_flags, b_depoff, b_depidx;
   DevBuf b_taskoff, b_groupoff, b_cfg, b_gmax, b_unitbase;
   DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_cv, b_ca, b_crk, b_bestpair;
-  DevBuf b_err;
+  DevBuf b_err, b_dx0, b_dx1, b_dx2, b_dx3, b_dx4, b_dx5, b_dx6, b_dx7;
   DevBuf b_route, b_listW, b_listA, b_listB, b_listC, b_unitv, b_unita, b_unitn, b_unitmask;
   int32_t nW = 0, nA = 0, nB = 0, nC = 0, n_general = 0;  // distros per on-chip class / general path
   std::vector<int32_t> h_listW, h_listA, h_listB, h_listC;  // host copies (ascending distro ids) for the pipelined one-shot call
@@ -1198,7 +1242,7 @@ void evg_shutdown(evg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->b_prio, &c->b_exp, &c->b_qb, &c->b_wb, &c->b_nd, &c->b_tgo, &c->b_gid, &c->b_vid, &c->b_flags,
                    &c->b_depoff, &c->b_depidx, &c->b_taskoff, &c->b_groupoff, &c->b_cfg, &c->b_gmax, &c->b_unitbase,
-                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita, &c->b_unitn, &c->b_unitmask, &c->b_err, &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_cv, &c->b_ca, &c->b_crk,
+                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita, &c->b_unitn, &c->b_unitmask, &c->b_err, &c->b_dx0, &c->b_dx1, &c->b_dx2, &c->b_dx3, &c->b_dx4, &c->b_dx5, &c->b_dx6, &c->b_dx7, &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_cv, &c->b_ca, &c->b_crk,
                    &c->b_bestpair, &c->b_ks[0], &c->b_ks[1], &c->b_kv[0], &c->b_kv[1], &c->b_ix[0], &c->b_ix[1], &c->b_bits,
                    &c->b_npass, &c->b_sched, &c->b_maxpass, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
@@ -1472,6 +1516,48 @@ int evg_alloc_batch(evg_ctx* c, const evg_host_soa* hosts, const int64_t* host_o
   if (out->status && n_distros) CK(cudaMemcpyAsync(out->status, c->b_status.p, sizeof(int32_t) * size_t(n_distros), cudaMemcpyDeviceToHost, s));
   if (G > 0) CK(cudaMemcpyAsync(groups, c->b_ginfo.p, sizeof(evg_group_info) * size_t(G), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return EVG_OK;
+}
+
+int evg_deps_met_batch(evg_ctx* c, const evg_deps_in* in, uint8_t* met) {
+  if (!c || !in || (in->n_tasks > 0 && !met)) return fail(EVG_ERR_INVALID, "evg_deps_met_batch: null argument");
+  const int64_t T = in->n_tasks, E = in->n_deps, X = in->n_ext;
+  if (T < 0 || E < 0 || X < 0) return fail(EVG_ERR_INVALID, "negative sizes");
+  if (T == 0) return EVG_OK;
+  if (!in->dep_off || !in->task_state || !in->task_pre) return fail(EVG_ERR_INVALID, "null task arrays");
+  if (E > 0 && (!in->dep_kind || !in->dep_ref || !in->dep_want)) return fail(EVG_ERR_INVALID, "null dependency arrays");
+  if (X > 0 && !in->ext_state) return fail(EVG_ERR_INVALID, "null ext_state");
+  if (in->dep_off[0] != 0 || in->dep_off[T] != E) return fail(EVG_ERR_INVALID, "dep_off does not span n_deps");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+#define UPD(buf, ptr, count, type)                                                                                 \
+  do {                                                                                                             \
+    CK((buf).ensure(sizeof(type) * size_t((count) > 0 ? (count) : 1)));                                            \
+    if ((count) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(count), cudaMemcpyHostToDevice, s)); \
+  } while (0)
+  UPD(c->b_dx0, in->dep_off, T + 1, int64_t);
+  UPD(c->b_dx1, in->dep_kind, E, uint8_t);
+  UPD(c->b_dx2, in->dep_ref, E, int32_t);
+  UPD(c->b_dx3, in->dep_want, E, uint8_t);
+  UPD(c->b_dx4, in->task_state, T, uint8_t);
+  UPD(c->b_dx5, in->task_pre, T, uint8_t);
+  UPD(c->b_dx6, in->ext_state, X, uint8_t);
+#undef UPD
+  CK(c->b_dx7.ensure(size_t(T)));
+  CK(c->b_err.ensure(sizeof(int) * 4));
+  CK(cudaMemsetAsync(c->b_err.p, 0, sizeof(int) * 4, s));
+  DDeps d;
+  d.n_tasks = T; d.dep_off = c->b_dx0.as<int64_t>(); d.dep_kind = c->b_dx1.as<uint8_t>(); d.dep_ref = c->b_dx2.as<int32_t>();
+  d.dep_want = c->b_dx3.as<uint8_t>(); d.task_state = c->b_dx4.as<uint8_t>(); d.task_pre = c->b_dx5.as<uint8_t>();
+  d.ext_state = c->b_dx6.as<uint8_t>(); d.n_ext = X;
+  k_deps_met<<<grid_for(T, 256), 256, 0, s>>>(d, c->b_dx7.as<uint8_t>(), c->b_err.as<int>());
+  c->launches = 1;
+  CK(cudaGetLastError());
+  int bad = 0;
+  CK(cudaMemcpyAsync(met, c->b_dx7.p, size_t(T), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (bad) return fail(EVG_ERR_INVALID, "a dep_ref is out of range");
   return EVG_OK;
 }
 

@@ -180,6 +180,13 @@ class Engine:
         self._n_tasks, self._n_distros, self._n_groups, self._has_hosts = T, D, G, True
         return po, ao
 
+    def deps_met_batch(self, deps: "S.DepsTable") -> np.ndarray:
+        """Task.DependenciesMet for every task of the tick on the device (evg_deps_met_batch)."""
+        met = self._out("deps_met", deps.n_tasks, np.uint8)
+        st = deps.struct()
+        L.check(self.lib.evg_deps_met_batch(self.ctx, C.byref(st), L.ptr(met) if deps.n_tasks else None))
+        return met
+
     def alloc_batch(self, hosts: S.HostSoA, qinfo: np.ndarray, ginfo: np.ndarray, group_off: np.ndarray, now: int):
         D = int(qinfo.shape[0])
         ao = self._alloc_output(D)
@@ -289,6 +296,19 @@ def GetDistroQueueInfo(distro: M.Distro, tasks: List[M.Task], max_duration_thres
     po = eng.plan_batch(soa, table, now)
     info = _queue_info_from_rows(po.info[0], po.group_info, keys[0].group_names)
     return info
+
+
+def dependencies_met(batch: Sequence[Tuple[M.Distro, List[M.Task]]], *, engine: Optional[Engine] = None,
+                     dependency_db: Optional[Dict[str, M.Task]] = None) -> List[List[bool]]:
+    """Task.DependenciesMet (model/task/task.go:632-671) for every queued task, per distro: the predicate the
+    task finders filter on and the bit the planner takes as EVG_TF_DEPS_MET."""
+    eng = engine or default_engine()
+    met = eng.deps_met_batch(S.marshal_deps(batch, dependency_db))
+    out, a = [], 0
+    for _, tasks in batch:
+        out.append([bool(x) for x in met[a:a + len(tasks)]])
+        a += len(tasks)
+    return out
 
 
 def allocate_distros(datas: Sequence[M.HostAllocatorData], now: int, *, engine: Optional[Engine] = None):

@@ -369,3 +369,81 @@ def queue_info_rows(infos: Sequence[M.DistroQueueInfo]):
         goff.append(len(grows))
         names_all.append(names)
     return qrows, np.array(grows, dtype=L.GROUP_INFO_DTYPE).reshape(-1), np.array(goff, dtype=np.int64), names_all
+
+
+# ---------------------------------------------------------------------------
+# dependency filter tables (evg_deps_in)
+# ---------------------------------------------------------------------------
+
+def _task_state(t: M.Task) -> int:
+    st = 0 if t.status == M.TASK_SUCCEEDED else 1 if t.status == M.TASK_FAILED else 2
+    return st | (L.EVG_TS_BLOCKED if t.blocked() else 0)
+
+
+def _want(status: str) -> int:
+    if status in (M.TASK_SUCCEEDED, ""):
+        return L.EVG_WANT_SUCCESS
+    if status == M.TASK_FAILED:
+        return L.EVG_WANT_FAILED
+    if status == M.ALL_STATUSES:
+        return L.EVG_WANT_ANY
+    return L.EVG_WANT_OTHER
+
+
+@dataclass
+class DepsTable:
+    """evg_deps_in: every direct dependency of every task of the tick (all distros concatenated)."""
+    dep_off: np.ndarray
+    dep_kind: np.ndarray
+    dep_ref: np.ndarray
+    dep_want: np.ndarray
+    task_state: np.ndarray
+    task_pre: np.ndarray
+    ext_state: np.ndarray
+
+    @property
+    def n_tasks(self) -> int:
+        return int(self.task_state.shape[0])
+
+    def struct(self) -> L.DepsInStruct:
+        s = L.DepsInStruct()
+        s.n_tasks, s.n_deps, s.n_ext = self.n_tasks, int(self.dep_ref.shape[0]), int(self.ext_state.shape[0])
+        s.dep_off = L.ptr(self.dep_off)
+        for f in ("dep_kind", "dep_ref", "dep_want"):
+            setattr(s, f, L.ptr(getattr(self, f)) if s.n_deps else None)
+        s.task_state, s.task_pre = L.ptr(self.task_state), L.ptr(self.task_pre)
+        s.ext_state = L.ptr(self.ext_state) if s.n_ext else None
+        return s
+
+
+def marshal_deps(batch: Sequence[tuple], dependency_db: Optional[Dict[str, M.Task]] = None) -> DepsTable:
+    """[(Distro, [Task])] -> DepsTable.  A dependency resolves against the distro's own queue first (the
+    depCache of scheduler.go:61-64), then against `dependency_db` (the tasks collection), else it is MISSING."""
+    dep_off, kind, ref, want, tstate, pre, ext_state = [0], [], [], [], [], [], []
+    ext_index: Dict[str, int] = {}
+    db = dependency_db or {}
+    base = 0
+    for _, tasks in batch:
+        index = {t.id: i for i, t in enumerate(tasks)}
+        for t in tasks:
+            tstate.append(_task_state(t))
+            pre.append((L.EVG_TP_OVERRIDE if t.override_dependencies else 0) |
+                       (0 if M.is_zero_time(t.dependencies_met_time) else L.EVG_TP_MET_TIME))
+            for d in t.depends_on:
+                want.append(_want(d.status))
+                j = index.get(d.task_id)
+                if j is not None:
+                    kind.append(L.EVG_DEP_IN_QUEUE); ref.append(base + j)
+                elif d.task_id in db:
+                    k = ext_index.get(d.task_id)
+                    if k is None:
+                        k = ext_index[d.task_id] = len(ext_state)
+                        ext_state.append(_task_state(db[d.task_id]))
+                    kind.append(L.EVG_DEP_EXTERNAL); ref.append(k)
+                else:
+                    kind.append(L.EVG_DEP_MISSING); ref.append(0)
+            dep_off.append(len(ref))
+        base += len(tasks)
+    return DepsTable(np.array(dep_off, np.int64), np.array(kind, np.uint8), np.array(ref, np.int32),
+                     np.array(want, np.uint8), np.array(tstate, np.uint8), np.array(pre, np.uint8),
+                     np.array(ext_state, np.uint8))

@@ -297,6 +297,43 @@ int evg_last_timing_ms(evg_ctx* ctx, float* total_ms, float* sort_ms);
  * (n <= 128), from CUDA events recorded on the context stream around that launch. */
 int evg_kernel_timing_ms(evg_ctx* ctx, float* out_ms, int32_t n);
 
+/* ---- dependency filter (the next row after the planner/allocator path) ---- */
+
+/* evg_deps_in.dep_kind */
+#define EVG_DEP_IN_QUEUE 0  /* dep_ref = index (in this call's task table) of the dependency; its state is task_state[dep_ref] */
+#define EVG_DEP_EXTERNAL 1  /* dep_ref indexes ext_state[] (the dependency was fetched from the tasks collection) */
+#define EVG_DEP_MISSING 2   /* lookup failed: never met (checkDependenciesMet, scheduler/scheduler.go:161-168) */
+/* evg_deps_in.dep_want: Dependency.Status */
+#define EVG_WANT_SUCCESS 0  /* "success" or "" (model/task/task.go:533-534) */
+#define EVG_WANT_FAILED 1   /* "failed" */
+#define EVG_WANT_ANY 2      /* "*" AllStatuses: failed, succeeded or blocked (task.go:537-538) */
+#define EVG_WANT_OTHER 3    /* any other string: never satisfied */
+/* task_state / ext_state bits */
+#define EVG_TS_STATUS_MASK 0x3u /* 0 "success", 1 "failed", 2 anything else */
+#define EVG_TS_BLOCKED 0x4u     /* Task.Blocked() (task.go:3649-3660) */
+/* task_pre bits: Task.HasDependenciesMet short-circuits (task.go:3393-3395) */
+#define EVG_TP_OVERRIDE 0x1u    /* OverrideDependencies */
+#define EVG_TP_MET_TIME 0x2u    /* !utility.IsZeroTime(DependenciesMetTime) */
+
+/* All DIRECT dependencies of every task, CSR over tasks. */
+typedef struct {
+  int64_t n_tasks;
+  int64_t n_deps;
+  const int64_t* dep_off;   /* n_tasks + 1 */
+  const uint8_t* dep_kind;  /* EVG_DEP_* */
+  const int32_t* dep_ref;
+  const uint8_t* dep_want;  /* EVG_WANT_* */
+  const uint8_t* task_state;/* n_tasks, EVG_TS_* of the in-queue tasks themselves */
+  const uint8_t* task_pre;  /* n_tasks, EVG_TP_* */
+  const uint8_t* ext_state; /* n_ext, EVG_TS_* */
+  int64_t n_ext;
+} evg_deps_in;
+
+/* met[t] = Task.DependenciesMet(ctx, depCache) for every task (model/task/task.go:632-671 with
+ * SatisfiesDependency :529-543): the bit evg_task_soa.flags carries as EVG_TF_DEPS_MET and the predicate the
+ * task finders filter on (scheduler/task_finder.go:40-197).  Host pointers in and out. */
+int evg_deps_met_batch(evg_ctx* ctx, const evg_deps_in* in, uint8_t* met);
+
 /* ---- single-distro wrappers: the per-job drop-in ------------------------- */
 
 /* One distro: PrioritizeTasks for `d` (scheduler/scheduler.go:27). */

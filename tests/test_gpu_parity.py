@@ -321,6 +321,54 @@ def test_out_of_range_ids_are_rejected(engine):
     parity.check_against_oracle(w, po, None)
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_dependency_filter_parity(engine, seed):
+    """evg_deps_met_batch against the oracle's Task.DependenciesMet restatement and the host mirror."""
+    import random
+    from test_host_logic import random_tasks
+    rng = random.Random(40 + seed)
+    batch, db_all = [], {}
+    for d in range(6):
+        tasks, db = random_tasks(rng, rng.choice([0, 1, 7, 150, 900]))
+        for t in tasks:
+            t.id = f"d{d}-{t.id}"
+            for dep in t.depends_on:
+                if dep.task_id.startswith("t"):
+                    dep.task_id = f"d{d}-{dep.task_id}"
+        batch.append((M.Distro(id=f"d{d}"), tasks))
+        db_all.update(db)
+    got = S.dependencies_met(batch, engine=engine, dependency_db=db_all)
+    for (dist, tasks), g in zip(batch, got):
+        by_id = {t.id: t for t in tasks}
+        assert g == [soa.dependencies_met(t, by_id, db_all) for t in tasks]
+        assert g == O.deps_met(tasks, NOW, db_all).tolist()
+
+
+def test_dependency_filter_at_scale(engine):
+    """1e6 tasks with ~1.5e6 dependencies: device result vs a numpy restatement of the same table."""
+    rng = np.random.default_rng(5)
+    T = 1_000_000
+    n_dep = rng.integers(0, 4, T)
+    off = np.zeros(T + 1, np.int64); np.cumsum(n_dep, out=off[1:])
+    E = int(off[-1])
+    deps = soa.DepsTable(off, rng.integers(0, 3, E).astype(np.uint8), rng.integers(0, 5000, E).astype(np.int32),
+                         rng.integers(0, 4, E).astype(np.uint8), rng.integers(0, 8, T).astype(np.uint8) & 7,
+                         (rng.random(T) < 0.1).astype(np.uint8) | ((rng.random(T) < 0.1).astype(np.uint8) << 1),
+                         rng.integers(0, 8, 5000).astype(np.uint8))
+    deps.task_state &= 0x7
+    deps.task_state[(deps.task_state & 3) == 3] -= 1
+    deps.ext_state[(deps.ext_state & 3) == 3] -= 1
+    got = engine.deps_met_batch(deps).copy()
+    st = np.where(deps.dep_kind == 0, deps.task_state[deps.dep_ref], deps.ext_state[deps.dep_ref])
+    status, blocked = st & 3, (st & 4) != 0
+    sat = np.where(deps.dep_want == 0, status == 0, np.where(deps.dep_want == 1, status == 1,
+                   np.where(deps.dep_want == 2, (status < 2) | blocked, False)))
+    sat &= deps.dep_kind != 2
+    unsat = np.add.reduceat(np.concatenate([(~sat).astype(np.int64), [0]]), np.minimum(off[:-1], E))[:T] * (n_dep > 0)
+    want = (n_dep == 0) | (deps.task_pre != 0) | (unsat == 0)
+    assert np.array_equal(got.astype(bool), want)
+
+
 def test_bad_arguments_are_errors(engine):
     w = synth.make(np.array([10]), 1)
     bad = copy.deepcopy(w)
