@@ -45,7 +45,26 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4_s(uint32_t smem_addr, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8_s(uint32_t smem_addr, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+}
+// 64-bit add into shared memory as two native 32-bit atomics (low word, then high word plus the carry the
+// low word produced).  A 64-bit shared atomicAdd compiles to a compare-and-swap spin loop, which crawls when
+// the lanes of a warp hit the same task group; sums commute, so the split form ends at the same 64-bit value.
+__device__ __forceinline__ void smem_add64(unsigned long long* addr, unsigned long long v) {
+  unsigned int* p = reinterpret_cast<unsigned int*>(addr);
+  const unsigned int lo = (unsigned int)v;
+  unsigned int hi = (unsigned int)(v >> 32);
+  const unsigned int old = atomicAdd(p, lo);
+  hi += (old + lo < old) ? 1u : 0u;
+  if (hi) atomicAdd(p + 1, hi);
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_newest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // (A vote-based replacement for MATCH.ANY -- 9 ballots per chunk -- was measured and is slower:
 // 0.84 ms vs 0.78 ms per configs[1] tick.)
@@ -151,7 +170,15 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     if (!gv && has_edges)
       for (int i = tid; i < tn; i += THREADS)
         if (sHasDep[i >> 5] & (1u << (i & 31))) W.head[ub + ng + i] = kInactive;
-    for (uint32_t g = tid; g < ng; g += THREADS) W.ginfo[D.group_off[d] + g].max_hosts = D.gmax[D.group_off[d] + g];
+    // TaskGroupInfo rows start from zero (no host-side memset): the list-free path rewrites the sums in phase 3,
+    // the other paths accumulate into them with global atomics after the barrier below
+    for (uint32_t g = tid; g < ng; g += THREADS) {
+      evg_group_info z;
+      z.count = 0; z.count_free = 0; z.count_required = 0; z.max_hosts = D.gmax[D.group_off[d] + g];
+      z.expected_duration = 0; z.count_duration_over_threshold = 0; z.count_wait_over_threshold = 0;
+      z.count_dep_filled_merge_queue_tasks = 0; z.duration_over_threshold = 0;
+      W.ginfo[D.group_off[d] + g] = z;
+    }
     __syncthreads();
   }
 
@@ -169,39 +196,54 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
   // side; the Go zero time is INT64_MIN and so always "waits"); other clocks take the literal saturating path.
   const bool sane_clock = threshold >= 0 && now >= threshold;
   const int64_t wait_cutoff = wsub(now, threshold);
-  // The next iteration's seven columns are staged into the (still idle) index region with cp.async while this
-  // iteration computes: 4 x 4 B + 3 x 8 B per thread, each thread reads back only what it copied itself.
+  const bool fast_clock = now >= 0 && pf.nd_int != 0;  // single_task_value_fast's distro-wide preconditions
+  // The seven columns of the next TWO iterations are staged with cp.async while this one computes (4 x 4 B +
+  // 3 x 8 B per thread and stage; each thread reads back only what it copied itself).  One stage lives in the
+  // index region, the other in the anchor/rank region -- both idle until phase 3.  Two stages in flight because
+  // one is latency-bound: 40 KB per SM per DRAM round trip is ~4 TB/s across the chip.
   constexpr bool kStage = size_t(4) * CAP >= size_t(THREADS) * 40;
-  uint32_t* st32 = reinterpret_cast<uint32_t*>(sIdx);                 // [4][THREADS] priority, num_dependents, group_id, flags
-  int64_t* st64 = reinterpret_cast<int64_t*>(st32 + 4 * THREADS);    // [3][THREADS] expected, queue_basis, wait_basis
-  auto prefetch = [&](int i0) {
+  // per stage: [4][THREADS] priority, num_dependents, group_id, flags, then [3][THREADS] expected, queue_basis, wait_basis
+  auto stage32 = [&](int b) { return reinterpret_cast<uint32_t*>(b ? sA : sIdx); };
+  auto stage64 = [&](int b) { return reinterpret_cast<int64_t*>(stage32(b) + 4 * THREADS); };
+  const uint32_t st32_s0 = uint32_t(__cvta_generic_to_shared(stage32(0) + tid)), st32_s1 = uint32_t(__cvta_generic_to_shared(stage32(1) + tid));
+  const uint32_t st64_s0 = uint32_t(__cvta_generic_to_shared(stage64(0) + tid)), st64_s1 = uint32_t(__cvta_generic_to_shared(stage64(1) + tid));
+  auto prefetch = [&](int i0, int b) {  // always closes a copy group (possibly empty) so wait_group counts iterations
     const int i = i0 + tid;
     if (i < tn) {
       const int64_t t = base + i;
-      cp_async4(st32 + 0 * THREADS + tid, T.priority + t);
-      cp_async4(st32 + 1 * THREADS + tid, T.numdep + t);
-      cp_async4(st32 + 2 * THREADS + tid, T.gid + t);
-      cp_async4(st32 + 3 * THREADS + tid, T.flags + t);
-      cp_async8(st64 + 0 * THREADS + tid, T.expected + t);
-      cp_async8(st64 + 1 * THREADS + tid, T.qbasis + t);
-      cp_async8(st64 + 2 * THREADS + tid, T.wbasis + t);
+      const uint32_t a32 = b ? st32_s1 : st32_s0, a64 = b ? st64_s1 : st64_s0;
+      cp_async4_s(a32 + 0 * THREADS * 4, T.priority + t);
+      cp_async4_s(a32 + 1 * THREADS * 4, T.numdep + t);
+      cp_async4_s(a32 + 2 * THREADS * 4, T.gid + t);
+      cp_async4_s(a32 + 3 * THREADS * 4, T.flags + t);
+      cp_async8_s(a64 + 0 * THREADS * 8, T.expected + t);
+      cp_async8_s(a64 + 1 * THREADS * 8, T.qbasis + t);
+      cp_async8_s(a64 + 2 * THREADS * 8, T.wbasis + t);
     }
+    cp_async_commit();
   };
-  if (kStage) prefetch(0);
-  for (int i0 = 0; i0 < tn; i0 += THREADS) {
+#ifndef EVG_STAGES
+#define EVG_STAGES 2
+#endif
+  if (kStage) { prefetch(0, 0); if (EVG_STAGES == 2) prefetch(THREADS, 1); }
+  int stage = 0;
+  for (int i0 = 0; i0 < tn; i0 += THREADS, stage ^= (EVG_STAGES == 2 ? 1 : 0)) {
     const int i = i0 + tid;
-    bool complex_task = false;
+    bool complex_task = false, scores = false;
     int32_t prio = 0, nd = 0, gid = -1;
     int64_t exp_ns = 0, qb = 0, wb = 0;
     uint32_t fl = 0;
     if (kStage) {
-      cp_async_wait_all();
+      if (EVG_STAGES == 2) cp_async_wait_but_newest();  // this iteration's stage has landed; the next one may still be in flight
+      else cp_async_wait_all();
       if (i < tn) {
+        const uint32_t* st32 = stage32(stage);
+        const int64_t* st64 = stage64(stage);
         prio = int32_t(st32[0 * THREADS + tid]); nd = int32_t(st32[1 * THREADS + tid]);
         gid = int32_t(st32[2 * THREADS + tid]); fl = st32[3 * THREADS + tid];
         exp_ns = st64[0 * THREADS + tid]; qb = st64[1 * THREADS + tid]; wb = st64[2 * THREADS + tid];
       }
-      if (i0 + THREADS < tn) prefetch(i0 + THREADS);
+      prefetch(i0 + EVG_STAGES * THREADS, stage);  // refill the stage just consumed
     } else if (i < tn) {
       const int64_t t = base + i;
       prio = T.priority[t]; nd = T.numdep[t]; gid = T.gid[t]; fl = T.flags[t];
@@ -221,7 +263,15 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       if (over) s_over += exp_ns;
       const bool own_complex = any && (gid >= 0 || gv || (sHasDep[i >> 5] & (1u << (i & 31))));
       complex_task = own_complex || (has_edges && T.dep_off[t + 1] > T.dep_off[t]);
-      if (!own_complex) sV[i] = single_task_value(pf, now, prio, exp_ns, qb, nd, fl);  // unit == {this task}
+      scores = !own_complex;  // unit == {this task}
+    }
+    // every scoring lane inside the exact-integer domain (the production case): one straight-line evaluation,
+    // no data-dependent branch; otherwise each lane takes the literal path
+    if (fast_clock && __all_sync(full, !scores || score_fast_domain(now, exp_ns, qb))) {
+      const int64_t v = single_task_value_fast(pf, now, prio, exp_ns, qb, nd, fl);
+      if (scores) sV[i] = v;
+    } else if (scores) {
+      sV[i] = single_task_value(pf, now, prio, exp_ns, qb, nd, fl);
     }
     if (any) {  // warp-aggregated append
       const unsigned m = __ballot_sync(full, complex_task);
@@ -305,21 +355,25 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       const int i = work_item(k);
       if (i < 0) continue;
       const int64_t t = base + i;
+      // every column this phase needs, requested together: one L2 round trip instead of a chain of them
       const int32_t gid = T.gid[t];
-      if (gid < 0) continue;
-      const int64_t exp_ns = T.expected[t];
+      const int64_t exp_ns = T.expected[t], wb = T.wbasis[t];
       const uint32_t fl = T.flags[t];
+      int32_t tgo = 0, prio = 0, nd = 0;
+      int64_t qb = 0;
+      if (fast_tg) { tgo = T.tgo[t]; qb = T.qbasis[t]; prio = T.priority[t]; nd = T.numdep[t]; }  // CTA-uniform
+      if (gid < 0) continue;
       const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
       const bool counted = !cfg.includes_dependencies || dm;
       const bool over = counted && exp_ns > threshold;
-      const bool wait_over = counted && dm && since(now, T.wbasis[t]) > threshold;
+      const bool wait_over = counted && dm && since(now, wb) > threshold;
       const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
       t_n += 1; t_cnt += counted; t_over += over; t_wait += wait_over; t_mq += mq_dm;
       if (counted) t_exp += exp_ns;
       if (over) t_dover += exp_ns;
       if (smem_ginfo) {
-        if (counted) { atomicAdd(&qCnt[gid], 1u); atomicAdd(&qExp[gid], (unsigned long long)exp_ns); }
-        if (over) { atomicAdd(&qOver[gid], 1u); atomicAdd(&qDurOver[gid], (unsigned long long)exp_ns); }
+        if (counted) { atomicAdd(&qCnt[gid], 1u); smem_add64(&qExp[gid], (unsigned long long)exp_ns); }
+        if (over) { atomicAdd(&qOver[gid], 1u); smem_add64(&qDurOver[gid], (unsigned long long)exp_ns); }
         if (wait_over) atomicAdd(&qWait[gid], 1u);
         if (mq_dm) atomicAdd(&qMq[gid], 1u);
       } else {
@@ -332,23 +386,23 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
         atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
       }
       if (fast_tg) {  // Unit.info (planner.go:302-337) of the task-group unit, member by member
-        const int32_t tgo = T.tgo[t];
         if (tgo < 0 || tgo >= 64) { S->tg_fallback = 1; continue; }
-        const int64_t qb = T.qbasis[t];
+        // phase 4 ranks this task from (group, order) alone: park them in the task's still unused value slot
+        reinterpret_cast<uint32_t*>(&sV[i])[0] = uint32_t(gid) | (uint32_t(tgo) << 16);
         const uint32_t req = fl & EVG_TF_REQ_MASK;
         uint32_t uf = 0;
         if (req == EVG_TF_REQ_MERGE_QUEUE) uf |= UF_MERGE_QUEUE;
         else if (req == EVG_TF_REQ_PATCH) uf |= UF_PATCH;
         if (fl & EVG_TF_GENERATE) uf |= UF_GENERATE;
         if (fl & EVG_TF_STEPBACK) uf |= UF_STEPBACK;
-        if (qb != EVG_TIME_ZERO) atomicAdd(&gTiq[gid], (unsigned long long)since(now, qb));
-        atomicAdd(&gRt[gid], (unsigned long long)exp_ns);
-        atomicMax(&gMaxP[gid], T.priority[t]);
-        atomicMax(&gMaxD[gid], T.numdep[t]);
+        if (qb != EVG_TIME_ZERO) smem_add64(&gTiq[gid], (unsigned long long)since(now, qb));
+        smem_add64(&gRt[gid], (unsigned long long)exp_ns);
+        atomicMax(&gMaxP[gid], prio);
+        atomicMax(&gMaxD[gid], nd);
         if (uf) atomicOr(&gFlags[gid], uf);
         atomicAdd(&gN[gid], 1u);
         atomicMin(&gAnchor[gid], uint32_t(i));
-        atomicOr(&gMask[gid], 1ull << tgo);
+        atomicOr(reinterpret_cast<unsigned int*>(&gMask[gid]) + (tgo >> 5), 1u << (tgo & 31));  // 64-bit presence mask, word by word
       }
     }
     // one shared atomic per warp and field: a 64-bit shared atomicAdd is a CAS spin loop, and the work list
@@ -388,10 +442,10 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
       for (int k = tid; k < n_work; k += THREADS) {
         const int i = work_item(k);
         if (i < 0) continue;
-        const int64_t t = base + i;
-        const int32_t gid = T.gid[t];
-        if (gid < 0) continue;
-        const uint32_t brk = __popcll(gMask[gid] & ((1ull << T.tgo[t]) - 1ull));
+        // work items are exactly the task-group tasks here (no GroupVersions, no edges); phase 2b parked (group, order)
+        const uint32_t packed = reinterpret_cast<const uint32_t*>(&sV[i])[0];
+        const uint32_t gid = packed & 0xFFFFu;
+        const uint32_t brk = __popcll(gMask[gid] & ((1ull << (packed >> 16)) - 1ull));
         const uint32_t ba = gAnchor[gid];
         sV[i] = gV[gid];
         sA[i] = uint16_t(ba);

@@ -88,7 +88,14 @@ __global__ void __launch_bounds__(256) k_plan_warp(DTasks T, DDistros D, DWork W
       q.ungrouped.duration_over_threshold = s_uover;
       W.qinfo[d] = q;
     }
-    if (uint32_t(lane) < ng) W.ginfo[D.group_off[d] + lane].max_hosts = D.gmax[D.group_off[d] + lane];
+    for (uint32_t g = uint32_t(lane); g < ng; g += 32) {  // rows start from zero (no host-side memset)
+      evg_group_info z;
+      z.count = 0; z.count_free = 0; z.count_required = 0; z.max_hosts = D.gmax[D.group_off[d] + g];
+      z.expected_duration = 0; z.count_duration_over_threshold = 0; z.count_wait_over_threshold = 0;
+      z.count_dep_filled_merge_queue_tasks = 0; z.duration_over_threshold = 0;
+      W.ginfo[D.group_off[d] + g] = z;
+    }
+    __syncwarp();
     if (in_tg) {
       evg_group_info* g = W.ginfo + D.group_off[d] + gid;
       atomic_add64(&g->count, counted);
@@ -104,7 +111,13 @@ __global__ void __launch_bounds__(256) k_plan_warp(DTasks T, DDistros D, DWork W
   int64_t best_v = 0;
   uint32_t best_u = uint32_t(lane), rk = 0;
   if (!any) {
-    if (valid) best_v = single_task_value(clamp_factors(cfg), now, prio, exp_ns, qb, nd, fl);
+    const PlannerFactors pf = clamp_factors(cfg);
+    if (now >= 0 && pf.nd_int != 0 && __all_sync(full, !valid || score_fast_domain(now, exp_ns, qb))) {
+      const int64_t v = single_task_value_fast(pf, now, prio, exp_ns, qb, nd, fl);
+      if (valid) best_v = v;
+    } else if (valid) {
+      best_v = single_task_value(pf, now, prio, exp_ns, qb, nd, fl);
+    }
   } else {
     // key a task is filed under; invalid lanes get keys nobody shares
     const uint32_t s_own = valid ? own_slot_local(gid, vid, uint32_t(lane), ng, gv) : 0xF0000000u + uint32_t(lane);

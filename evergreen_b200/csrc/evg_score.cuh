@@ -214,6 +214,7 @@ EVG_HD int64_t unit_value(const UnitAcc& a, const evg_distro_cfg& c, int64_t* bd
 struct PlannerFactors {
   int64_t patch, patch_tiq, commit_queue, mainline_tiq, runtime, generate, stepback;
   double num_dependents;
+  int64_t nd_int;  // num_dependents as an integer when it is one (see single_task_value_fast), else 0
 };
 EVG_HD PlannerFactors clamp_factors(const evg_distro_cfg& c) {
   PlannerFactors f;
@@ -225,6 +226,8 @@ EVG_HD PlannerFactors clamp_factors(const evg_distro_cfg& c) {
   f.generate = factor(c.generate_task_factor);
   f.stepback = factor(c.stepback_task_factor);
   f.num_dependents = factor_d(c.num_dependents_factor);
+  // an integral factor below 2^20 times a count below 2^31 is exact in FP64, so int64(f * float64(n)) == f * n
+  f.nd_int = (f.num_dependents < 1048576.0 && f.num_dependents == i2d(d2i_trunc(f.num_dependents))) ? d2i_trunc(f.num_dependents) : 0;
   return f;
 }
 
@@ -250,6 +253,39 @@ EVG_HD int64_t single_task_value(const PlannerFactors& f, int64_t now, int32_t p
   }
   const int64_t r_deps = d2i_trunc(fmul64(f.num_dependents, i2d(num_dependents > 0 ? int64_t(num_dependents) : 0)));
   const int64_t r_rt = wmul(f.runtime, floor_minutes_over(expected_ns, 1));
+  const int64_t rank = wadd(wadd(wadd(1, term), r_deps), r_rt);
+  return wadd(wmul(prio, rank), 1);
+}
+
+// Straight-line form of single_task_value for the domain every production queue lives in:
+//   clock and queue basis non-negative, 0 <= time in queue < 2^15 minutes (22.7 days) or no basis at all,
+//   0 <= expected runtime < 2^15 minutes, integral NumDependentsFactor (f.nd_int != 0).
+// There Minutes()/Hours() are exact integer quotients (see floor_minutes_over / trunc_hours; whole hours of
+// d are whole minutes of d over 60), time.Since cannot saturate and the FP64 dependents term is an exact
+// product, so the value is the same integer -- without a data-dependent branch.  Callers test the domain for
+// a whole warp at once (score_fast_domain) and fall back to single_task_value otherwise;
+// tests/native/score_fastpath_check.cpp compares the two on random in-domain inputs.
+constexpr uint64_t kFastLimit = uint64_t(int64_t(1) << 15) * uint64_t(kMinute);
+EVG_HD bool score_fast_domain(int64_t now, int64_t expected_ns, int64_t queue_basis_ns) {  // requires now >= 0
+  const bool q_ok = queue_basis_ns == EVG_TIME_ZERO || (queue_basis_ns >= 0 && uint64_t(now - queue_basis_ns) < kFastLimit);
+  return q_ok && uint64_t(expected_ns) < kFastLimit;
+}
+EVG_HD int64_t single_task_value_fast(const PlannerFactors& f, int64_t now, int32_t priority, int64_t expected_ns,
+                                      int64_t queue_basis_ns, int32_t num_dependents, uint32_t tflags) {
+  const uint32_t req = tflags & EVG_TF_REQ_MASK;
+  const bool mq = req == EVG_TF_REQ_MERGE_QUEUE, pat = req == EVG_TF_REQ_PATCH;
+  const uint64_t tiq = queue_basis_ns == EVG_TIME_ZERO ? 0ull : uint64_t(now - queue_basis_ns);
+  int64_t prio = int64_t(1u + uint32_t(priority > 0 ? priority : 0));
+  prio = wmul(prio, (tflags & EVG_TF_GENERATE) ? f.generate : 1);
+  prio = wadd(prio, mq ? 200 : 0);
+  const uint64_t left = tiq < uint64_t(kWeek) ? uint64_t(kWeek) - tiq : 0ull;  // mainline: what is left of the first week
+  const uint32_t mins = uint32_t((pat ? tiq : left) / uint64_t(kMinute));
+  const uint32_t qty = pat ? mins : mins / 60u;  // patch: whole minutes waited; mainline: whole hours left
+  int64_t term = wmul(pat ? f.patch_tiq : f.mainline_tiq, int64_t(qty));
+  term = wadd(term, pat ? f.patch : ((tflags & EVG_TF_STEPBACK) ? f.stepback : 0));
+  if (mq) term = f.commit_queue;
+  const int64_t r_deps = wmul(f.nd_int, int64_t(uint32_t(num_dependents > 0 ? num_dependents : 0)));
+  const int64_t r_rt = wmul(f.runtime, int64_t(uint32_t(uint64_t(expected_ns) / uint64_t(kMinute))));
   const int64_t rank = wadd(wadd(wadd(1, term), r_deps), r_rt);
   return wadd(wmul(prio, rank), 1);
 }

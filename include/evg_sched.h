@@ -287,9 +287,10 @@ void* evg_device_result_ptr(evg_ctx* ctx);
 int evg_bind_result_buffer(evg_ctx* ctx, void* device_ptr, int64_t capacity);
 /* Number of kernel launches issued by the last evg_run_resident. */
 int64_t evg_last_launch_count(evg_ctx* ctx);
-/* Device time of the planner's dominant kernel (segmented sort) and of the
- * whole resident run in ms, measured with CUDA events on the context stream
- * during the last evg_run_resident (valid after a sync / download). */
+/* Device time in ms of the last evg_run_resident, from CUDA events on the context
+ * stream (valid after a sync / download): total_ms spans the whole tick; sort_ms is
+ * the general path's segmented radix sort when the tick had a distro above 12288
+ * tasks, otherwise the k_plan_smem<1024,12> launch (see evg_kernel_timing_ms). */
 int evg_last_timing_ms(evg_ctx* ctx, float* total_ms, float* sort_ms);
 
 /* Device time in ms of the dominant kernel -- k_plan_smem<1024,12>, the on-chip planner

@@ -8,7 +8,7 @@ using namespace evg;
 static int64_t ref_floor_minutes_over(int64_t d, int64_t n) { return int64_t(std::floor((double(d / kMinute) + double(d % kMinute) / (60.0 * 1e9)) / double(n))); }
 static int64_t ref_trunc_hours(int64_t d) { return int64_t(double(d / kHour) + double(d % kHour) / (3600.0 * 1e9)); }
 int main() {
-  uint64_t x = 88172645463325252ULL; long bad = 0; long n = 0;
+  uint64_t x = 88172645463325252ULL; long bad = 0; long n = 0; long fast_n = 0;
   auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
   for (int it = 0; it < 20000000; it++) {
     int64_t q = int64_t(rnd() % (uint64_t(1) << 15));
@@ -46,7 +46,7 @@ int main() {
     c.patch_factor = int64_t(rnd() % 120) - 10; c.patch_time_in_queue_factor = int64_t(rnd() % 120) - 10;
     c.commit_queue_factor = int64_t(rnd() % 120) - 10; c.mainline_time_in_queue_factor = int64_t(rnd() % 120) - 10;
     c.expected_runtime_factor = int64_t(rnd() % 120) - 10; c.generate_task_factor = int64_t(rnd() % 120) - 10;
-    c.stepback_task_factor = int64_t(rnd() % 120) - 10; c.num_dependents_factor = double(int64_t(rnd() % 1200) - 100) / 10.0;
+    c.stepback_task_factor = int64_t(rnd() % 120) - 10; c.num_dependents_factor = (rnd() % 4) ? double(int64_t(rnd() % 120) - 10) : double(int64_t(rnd() % 1200) - 100) / 10.0;
     c.target_time_ns = 0; c.group_versions = 0; c.includes_dependencies = 0; c.n_versions = 0; c._reserved = 0;
     const int64_t now = 1800000000000000000LL;
     int64_t qb;
@@ -56,9 +56,47 @@ int main() {
     const int64_t ex = (rnd() % 5 == 0) ? int64_t(rnd() % (1ULL << 58)) : int64_t(rnd() % (7200ULL * 1000000000ULL));
     const uint32_t fl = uint32_t(rnd() % 3) | (rnd() % 8 == 0 ? EVG_TF_GENERATE : 0) | (rnd() % 8 == 0 ? EVG_TF_STEPBACK : 0);
     UnitAcc a; acc_init(a); acc_add(a, now, prio, ex, qb, nd, -1, fl);
-    if (unit_value(a, c, nullptr) != single_task_value(clamp_factors(c), now, prio, ex, qb, nd, fl)) bad++;
+    const PlannerFactors pf = clamp_factors(c);
+    const int64_t want = unit_value(a, c, nullptr);
+    if (want != single_task_value(pf, now, prio, ex, qb, nd, fl)) bad++;
+    // the straight-line form, wherever its domain test admits the inputs
+    if (pf.nd_int != 0 && score_fast_domain(now, ex, qb)) {
+      fast_n++;
+      if (want != single_task_value_fast(pf, now, prio, ex, qb, nd, fl)) bad++;
+    }
     n++;
   }
-  printf("checked %ld, mismatches %ld\n", n, bad);
+  // the straight-line form at the edges of its domain (week boundary, limit - 1, zero basis, huge factors)
+  {
+    const int64_t now = 1800000000000000000LL;
+    const int64_t lim = int64_t(kFastLimit);
+    const int64_t tiqs[] = {0, 1, kMinute - 1, kMinute, kHour - 1, kHour, kWeek - kHour, kWeek - 1, kWeek, kWeek + 1, lim - 1};
+    const int64_t exps[] = {0, 1, kMinute - 1, kMinute, 90 * kMinute, lim - 1};
+    const int64_t facs[] = {0, 1, 7, 100, 2147483647LL, 9007199254740993LL, -5};
+    const double ndf[] = {0.0, 1.0, 2.0, 1048575.0, 1048576.0, 2.5, -1.0};
+    for (int64_t tq : tiqs) for (int64_t ex : exps) for (int64_t fc : facs) for (double nf : ndf) for (uint32_t fl = 0; fl < 3; fl++)
+      for (int extra = 0; extra < 4; extra++) for (int zero = 0; zero < 2; zero++) {
+        evg_distro_cfg c;
+        c.patch_factor = fc; c.patch_time_in_queue_factor = fc + 1; c.commit_queue_factor = fc; c.mainline_time_in_queue_factor = fc + 2;
+        c.expected_runtime_factor = fc; c.generate_task_factor = fc; c.stepback_task_factor = fc + 3; c.num_dependents_factor = nf;
+        c.target_time_ns = 0; c.group_versions = 0; c.includes_dependencies = 0; c.n_versions = 0; c._reserved = 0;
+        const uint32_t f2 = fl | ((extra & 1) ? EVG_TF_GENERATE : 0) | ((extra & 2) ? EVG_TF_STEPBACK : 0);
+        const int64_t qb = zero ? EVG_TIME_ZERO : now - tq;
+        const int32_t prio = int32_t(tq % 3 == 0 ? 2147483647 : 17), nd = int32_t(ex % 2 == 0 ? 2147483647 : 3);
+        UnitAcc a; acc_init(a); acc_add(a, now, prio, ex, qb, nd, -1, f2);
+        const PlannerFactors pf = clamp_factors(c);
+        if (unit_value(a, c, nullptr) != single_task_value(pf, now, prio, ex, qb, nd, f2)) bad++;
+        if (pf.nd_int != 0 && score_fast_domain(now, ex, qb)) {
+          fast_n++;
+          if (unit_value(a, c, nullptr) != single_task_value_fast(pf, now, prio, ex, qb, nd, f2)) bad++;
+        }
+        n++;
+      }
+    // outside the domain the test must say so
+    if (score_fast_domain(now, lim, 0 + now - 1) || score_fast_domain(now, 0, now - lim) || score_fast_domain(now, -1, now) ||
+        score_fast_domain(now, 0, now + 1) || score_fast_domain(now, 0, -5)) bad++;
+  }
+  if (fast_n < 1000000) bad++;  // the straight-line form must actually have been exercised
+  printf("checked %ld (%ld through the straight-line form), mismatches %ld\n", n, fast_n, bad);
   return bad != 0;
 }
