@@ -197,10 +197,9 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
   const bool sane_clock = threshold >= 0 && now >= threshold;
   const int64_t wait_cutoff = wsub(now, threshold);
   const bool fast_clock = now >= 0 && pf.nd_int != 0;  // single_task_value_fast's distro-wide preconditions
-  // The seven columns of the next TWO iterations are staged with cp.async while this one computes (4 x 4 B +
-  // 3 x 8 B per thread and stage; each thread reads back only what it copied itself).  One stage lives in the
-  // index region, the other in the anchor/rank region -- both idle until phase 3.  Two stages in flight because
-  // one is latency-bound: 40 KB per SM per DRAM round trip is ~4 TB/s across the chip.
+  // The seven columns of the next EVG_STAGES iterations are staged with cp.async while this one computes
+  // (4 x 4 B + 3 x 8 B per thread and stage; each thread reads back only what it copied itself).  Stage 0 lives
+  // in the index region, stage 1 in the anchor/rank region -- both idle until phase 3.
   constexpr bool kStage = size_t(4) * CAP >= size_t(THREADS) * 40;
   // per stage: [4][THREADS] priority, num_dependents, group_id, flags, then [3][THREADS] expected, queue_basis, wait_basis
   auto stage32 = [&](int b) { return reinterpret_cast<uint32_t*>(b ? sA : sIdx); };
@@ -223,7 +222,7 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
     cp_async_commit();
   };
 #ifndef EVG_STAGES
-#define EVG_STAGES 2
+#define EVG_STAGES 1  // measured on B200: two stages in flight 0.485 ms per configs[1] tick, one stage 0.476 ms (the loop is issue-bound)
 #endif
   if (kStage) { prefetch(0, 0); if (EVG_STAGES == 2) prefetch(THREADS, 1); }
   int stage = 0;
