@@ -83,6 +83,7 @@ constexpr int kChunks = kTile / 32;
 constexpr int kMaxPass = 16;       // 8 tie bytes + 8 value bytes
 // on-chip planner classes <THREADS, ITEMS>: capacity = THREADS*ITEMS tasks per distro
 constexpr int kCapA = 128 * 8, kCapB = 256 * 16, kCapC = 1024 * 12;
+constexpr int64_t kWideAllocGroups = 1024;  // k_alloc<128> (a block per distro) once some distro has more task groups
 constexpr int kCapW = 32;  // k_plan_warp: one warp per distro
 constexpr uint32_t kInactive = 0xFFFFFFFFu;  // next[]: pair not linked / head[]: empty list
 constexpr uint32_t kEnd = 0xFFFFFFFEu;       // next[]: end of list
@@ -218,10 +219,13 @@ __device__ __forceinline__ void note_key_bits(unsigned long long* bits, int d, b
   if (uniform) {
     uint64_t os = warp_or64(ks), as = warp_and64(ks), ov = warp_or64(kv), av = warp_and64(kv);
     if ((threadIdx.x & 31) == 0) {
-      atomicOr(bits + 4 * d + 0, os);
-      atomicAnd(bits + 4 * d + 1, as);
-      atomicOr(bits + 4 * d + 2, ov);
-      atomicAnd(bits + 4 * d + 3, av);
+      // or-words only gain bits and and-words only lose them, so an atomic that would change nothing (nearly
+      // all of them once a big distro's first warps have reported) is skipped after a plain L2 read
+      unsigned long long* b = bits + 4 * d;
+      if (os & ~__ldcg(b + 0)) atomicOr(b + 0, os);
+      if (~as & __ldcg(b + 1)) atomicAnd(b + 1, as);
+      if (ov & ~__ldcg(b + 2)) atomicOr(b + 2, ov);
+      if (~av & __ldcg(b + 3)) atomicAnd(b + 3, av);
     }
   } else if (valid) {
     atomicOr(bits + 4 * d + 0, ks);
@@ -341,6 +345,14 @@ __global__ void __launch_bounds__(256) k_task(DTasks T, DDistros D, DWork W, int
   const unsigned full = 0xffffffffu;
   const int d0 = __shfl_sync(full, d, 0);
   const bool uniform = __all_sync(full, d == d0) && valid;
+  // A block that lies inside one distro folds its eight warps in shared memory first: a million-task distro
+  // would otherwise send every warp's fourteen adds to the same DistroQueueInfo row (millions of L2 atomics
+  // on a handful of addresses).
+  __shared__ int s_first;
+  __shared__ long long s_fold[8][14];
+  if (threadIdx.x == 0) s_first = d;
+  __syncthreads();
+  const bool block_uniform = __syncthreads_and(valid && d == s_first) != 0;
 
   int32_t prio = 0, nd = 0, gid = -1, vid = 0;
   int64_t exp_ns = 0, qb = EVG_TIME_ZERO, wb = EVG_TIME_ZERO;
@@ -377,7 +389,15 @@ __global__ void __launch_bounds__(256) k_task(DTasks T, DDistros D, DWork W, int
       int64_t s_over = warp_sum64(over ? exp_ns : 0);
       int64_t s_uexp = warp_sum64(ung && counted ? exp_ns : 0);
       int64_t s_uover = warp_sum64(ung && over ? exp_ns : 0);
-      if ((threadIdx.x & 31) == 0) {
+      if (block_uniform) {
+        if ((threadIdx.x & 31) == 0) {
+          long long* f = s_fold[threadIdx.x >> 5];
+          f[0] = w0 & 63; f[1] = (w0 >> 6) & 63; f[2] = (w0 >> 12) & 63; f[3] = (w0 >> 18) & 63; f[4] = (w0 >> 24) & 63;
+          f[5] = s_exp; f[6] = s_over;
+          f[7] = w1 & 63; f[8] = (w1 >> 6) & 63; f[9] = (w1 >> 12) & 63; f[10] = (w1 >> 18) & 63; f[11] = (w1 >> 24) & 63;
+          f[12] = s_uexp; f[13] = s_uover;
+        }
+      } else if ((threadIdx.x & 31) == 0) {
         evg_queue_info* q = W.qinfo + d;
         atomic_add64(&q->length_with_dependencies_met, w0 & 63);
         atomic_add64(&q->count_dep_filled_merge_queue_tasks, (w0 >> 6) & 63);
@@ -413,6 +433,19 @@ __global__ void __launch_bounds__(256) k_task(DTasks T, DDistros D, DWork W, int
         atomic_add64(&q->ungrouped.duration_over_threshold, over ? exp_ns : 0);
       }
     }
+  }
+  if (block_uniform) {  // block-wide condition: every thread reaches the barrier
+    __syncthreads();
+    if (threadIdx.x < 14) {
+      // evg_queue_info as int64[19]: the field each folded slot belongs to
+      constexpr int kField[14] = {1, 2, 5, 7, 8, 3, 6, 9, 10, 15, 16, 17, 14, 18};
+      long long tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) tot += s_fold[w][threadIdx.x];
+      if (tot) atomic_add64(reinterpret_cast<int64_t*>(W.qinfo + d) + kField[threadIdx.x], tot);
+    }
+  }
+  if (valid) {
     if (gid >= 0) {
       evg_group_info* g = W.ginfo + D.group_off[d] + gid;
       atomic_add64(&g->count, counted);
@@ -579,28 +612,54 @@ __global__ void __launch_bounds__(256) k_sort_hist(int j, DDistros D, DWork W) {
   W.tile_hist[int64_t(tile) * 256 + threadIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(256) k_sort_scan(int j, DDistros D, DWork W) {
+// Offsets of every (tile, digit) counter of one general-path distro: exclusive over the tiles of a digit, then
+// over the digits.  A distro of a million tasks has ~500 tiles, so a thread per digit walking them one L2 round
+// trip at a time is a ~0.7 ms chain per pass; here four thread groups split the tiles and every thread keeps
+// eight independent loads in flight.
+__global__ void __launch_bounds__(1024) k_sort_scan(int j, const int32_t* __restrict__ general_list, DDistros D, DWork W) {
   if (j >= *W.maxpass) return;
-  const int d = blockIdx.x;
+  const int d = general_list[blockIdx.x];
   if (j >= W.npass[d]) return;
-  const int64_t t0 = W.dtile_off[d], t1 = W.dtile_off[d + 1];
-  uint32_t run = 0;
-  for (int64_t tile = t0; tile < t1; tile++) {
-    uint32_t x = W.tile_hist[tile * 256 + threadIdx.x];
-    W.tile_hist[tile * 256 + threadIdx.x] = run;
-    run += x;
+  const int dg = threadIdx.x & 255, grp = threadIdx.x >> 8;
+  const int64_t t0 = W.dtile_off[d], nt = W.dtile_off[d + 1] - t0;
+  const int64_t per = (nt + 3) / 4;
+  const int64_t a = t0 + (grp * per < nt ? grp * per : nt), b = t0 + ((grp + 1) * per < nt ? (grp + 1) * per : nt);
+  uint32_t* h = W.tile_hist + dg;
+  uint32_t sum = 0;
+  int64_t tile = a;
+  for (; tile + 8 <= b; tile += 8) {
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = h[(tile + k) * 256];
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += x[k];
   }
+  for (; tile < b; tile++) sum += h[tile * 256];
+  __shared__ uint32_t part[4][256];
   __shared__ uint32_t s[256];
-  s[threadIdx.x] = run;
+  part[grp][dg] = sum;
+  __syncthreads();
+  const uint32_t total = part[0][dg] + part[1][dg] + part[2][dg] + part[3][dg];
+  if (grp == 0) s[dg] = total;
   __syncthreads();
   for (int o = 1; o < 256; o <<= 1) {
-    uint32_t v = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+    uint32_t v = 0;
+    if (grp == 0 && dg >= o) v = s[dg - o];
     __syncthreads();
-    s[threadIdx.x] += v;
+    if (grp == 0) s[dg] += v;
     __syncthreads();
   }
-  const uint32_t basev = s[threadIdx.x] - run;
-  for (int64_t tile = t0; tile < t1; tile++) W.tile_hist[tile * 256 + threadIdx.x] += basev;
+  uint32_t run = s[dg] - total;  // digits before this one
+  for (int g = 0; g < grp; g++) run += part[g][dg];  // this digit in the tile groups before this one
+  tile = a;
+  for (; tile + 8 <= b; tile += 8) {
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = h[(tile + k) * 256];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { h[(tile + k) * 256] = run; run += x[k]; }
+  }
+  for (; tile < b; tile++) { const uint32_t x = h[tile * 256]; h[tile * 256] = run; run += x; }
 }
 
 __global__ void __launch_bounds__(256) k_sort_scatter(int j, DDistros D, DWork W) {
@@ -739,48 +798,64 @@ __device__ int eval_group(const evg_alloc_cfg& c, const evg_group_info& info, in
   return EVG_ALLOC_OK;
 }
 
-// One warp per distro.  Hosts are walked in index order by the whole warp; the
-// lane that owns a bucket (lane 0 for "", lane g%32 for group g) does that
-// bucket's updates, so every bucket's FP64 sum is accumulated in host order
-// while buckets proceed in parallel.  Groups are then evaluated 32 at a time;
-// the per-group results are integers, so the warp reduction is exact.
+// TPD threads per distro: a warp (four distros per block) when task groups are few, the whole 128-thread block
+// when some distro has thousands of them (a distro of a million tasks has tens of thousands).  The first warp
+// of the team walks the hosts in index order; the lane that owns a bucket (lane 0 for "", lane g%32 for group
+// g) does that bucket's updates, so every bucket's FP64 sum is accumulated in host order while buckets proceed
+// in parallel.  The team then evaluates the task groups; per-group results are integers, so the reduction is exact.
+template <int TPD>
 __global__ void __launch_bounds__(128) k_alloc(DHosts H, int32_t d_begin, int32_t n_distros, const int64_t* group_off,
                                                const evg_queue_info* qinfo, evg_group_info* ginfo, GroupScratch* gs,
                                                int64_t now, evg_alloc_result* result, int32_t* status) {
-  const int d = d_begin + int((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
+  constexpr int TEAMS = 128 / TPD, TW = TPD / 32;  // teams per block, warps per team
+  const int team = threadIdx.x / TPD, tt = threadIdx.x % TPD;
+  const int d = d_begin + int(blockIdx.x) * TEAMS + team;
+  const int lane = threadIdx.x & 31, warp = tt >> 5;
   const unsigned full = 0xffffffffu;
-  if (d >= n_distros) return;  // warp-uniform (n_distros = end of the range)
+  if (d >= n_distros) return;  // team-uniform (n_distros = end of the range); a team never shares a barrier with another
+  auto team_sync = [&]() { if (TPD == 128) __syncthreads(); else __syncwarp(); };
+  __shared__ long long sh_nfree[TEAMS], sh_uhosts[TEAMS], sh_ufree[TEAMS], sh_req[TEAMS][TW], sh_fre[TEAMS][TW];
+  __shared__ double sh_usoon[TEAMS];
+  __shared__ int sh_st[TEAMS][TW];
+  long long& s_nfree = sh_nfree[team]; long long& s_uhosts = sh_uhosts[team]; long long& s_ufree = sh_ufree[team];
+  double& s_usoon = sh_usoon[team];
+  long long* s_req = sh_req[team]; long long* s_fre = sh_fre[team];
+  int* s_st = sh_st[team];
   const evg_alloc_cfg c = H.cfg[d];
   const evg_queue_info qi = qinfo[d];
   const int64_t threshold = qi.max_duration_threshold;
   const int64_t h0 = H.host_off[d], h1 = H.host_off[d + 1];
   const int64_t g0 = group_off[d], g1 = group_off[d + 1];
   const int64_t n_existing = h1 - h0;
+  for (int64_t g = g0 + tt; g < g1; g += TPD) { gs[g].n_hosts = 0; gs[g].n_free = 0; gs[g].soon = 0.0; }
+  team_sync();
   // IsFree count (allocator.go:33-37), bucket sizes (groupByTaskGroup :223-260), soon-to-be-free sums (:324-394)
-  int64_t n_free_all = 0, u_hosts = 0, u_free = 0;
-  double u_soon = 0.0;
-  for (int64_t g = g0 + lane; g < g1; g += 32) { gs[g].n_hosts = 0; gs[g].n_free = 0; gs[g].soon = 0.0; }  // same lane owns the row below
-  for (int64_t h = h0; h < h1; h++) {
-    const uint32_t f = H.flags[h];
-    const int32_t g = H.gid[h];
-    const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
-    n_free_all += is_free;
-    const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
-    if (g == EVG_HG_NONE) {
-      if (lane == 0) {
-        u_hosts++;
-        u_free += is_free;
-        if (running) u_soon = fadd64(u_soon, soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction));
+  if (warp == 0) {
+    int64_t n_free_all = 0, u_hosts = 0, u_free = 0;
+    double u_soon = 0.0;
+    for (int64_t h = h0; h < h1; h++) {
+      const uint32_t f = H.flags[h];
+      const int32_t g = H.gid[h];
+      const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
+      n_free_all += is_free;
+      const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
+      if (g == EVG_HG_NONE) {
+        if (lane == 0) {
+          u_hosts++;
+          u_free += is_free;
+          if (running) u_soon = fadd64(u_soon, soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction));
+        }
+      } else if (g >= 0 && g < g1 - g0 && (g & 31) == lane) {
+        GroupScratch* s = gs + g0 + g;
+        s->n_hosts++;
+        s->n_free += is_free;
+        if (running) s->soon = fadd64(s->soon, soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction));
       }
-    } else if (g >= 0 && g < g1 - g0 && (g & 31) == lane) {
-      GroupScratch* s = gs + g0 + g;
-      s->n_hosts++;
-      s->n_free += is_free;
-      if (running) s->soon = fadd64(s->soon, soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction));
     }
+    if (lane == 0) { s_nfree = n_free_all; s_uhosts = u_hosts; s_ufree = u_free; s_usoon = u_soon; }
   }
-  __syncwarp();
+  team_sync();
+  const int64_t n_free_all = s_nfree;
   int32_t st = EVG_ALLOC_OK;
   int64_t n_new = 0, n_free_out = n_free_all;
   if (c.provider != EVG_PROVIDER_DOCKER && n_existing >= c.maximum_hosts) {
@@ -788,16 +863,16 @@ __global__ void __launch_bounds__(128) k_alloc(DHosts H, int32_t d_begin, int32_
   } else if (c.disabled) {
     n_new = int64_t(c.minimum_hosts) - n_existing;  // allocator.go:51-66
     if (n_new < 0) n_new = 0;
-  } else {
+  } else {  // team-uniform branch: c and the host count are per distro
     int64_t required = 0, free_approx = 0;
     // "" bucket exists when standalone tasks are queued or hosts are bucketed under ""
-    if (lane == 0 && (qi.has_ungrouped || u_hosts > 0)) {
+    if (tt == 0 && (qi.has_ungrouped || s_uhosts > 0)) {
       int64_t n, f;
-      st = eval_group(c, qi.ungrouped, threshold, c.maximum_hosts, u_hosts, u_free, u_soon, &n, &f);
+      st = eval_group(c, qi.ungrouped, threshold, c.maximum_hosts, s_uhosts, s_ufree, s_usoon, &n, &f);
       required += n;
       free_approx += f;
     }
-    for (int64_t g = g0 + lane; g < g1; g += 32) {
+    for (int64_t g = g0 + tt; g < g1; g += TPD) {
       evg_group_info* gi = ginfo + g;
       if (gi->count == 0) continue;  // allocator.go:84-86
       int64_t n, f;
@@ -808,10 +883,17 @@ __global__ void __launch_bounds__(128) k_alloc(DHosts H, int32_t d_begin, int32_
       gi->count_free = f;  // allocator.go:107-110
       gi->count_required = n;
     }
-    // a data error is distro-wide (fraction, parent) or the pool-size check of some group: any lane's error wins
+    // a data error is distro-wide (fraction, parent) or the pool-size check of some group: any thread's error wins
     st = __reduce_max_sync(full, st);
     required = warp_sum64(required);
     free_approx = warp_sum64(free_approx);
+    if (TW > 1) {
+      if (lane == 0) { s_st[warp] = st; s_req[warp] = required; s_fre[warp] = free_approx; }
+      team_sync();
+      st = s_st[0]; required = s_req[0]; free_approx = s_fre[0];
+#pragma unroll
+      for (int w = 1; w < TW; w++) { st = max(st, s_st[w]); required += s_req[w]; free_approx += s_fre[w]; }
+    }
     if (st == EVG_ALLOC_OK) {
       if (required + n_free_all > qi.length_with_dependencies_met) required = qi.length_with_dependencies_met - n_free_all;
       if (required < 0) required = 0;
@@ -824,7 +906,7 @@ __global__ void __launch_bounds__(128) k_alloc(DHosts H, int32_t d_begin, int32_
       n_free_out = n_free_all;
     }
   }
-  if (lane == 0) {
+  if (tt == 0) {
     int64_t deficit = wsub(qi.expected_duration, wmul(n_free_out, threshold));
     if (deficit < 0) deficit = 0;
     result[d].new_hosts = int32_t(n_new);
@@ -846,6 +928,7 @@ struct evg_ctx {
   static constexpr int kRing = 128;
   cudaEvent_t ring0[kRing] = {}, ring1[kRing] = {};
   int64_t runs = 0;
+  int64_t max_groups = 0;  // most task groups in any distro: picks the allocator's team width
   int sort_slot = -1;  // ring slot that stands in for the sort split when the tick had no general-path distro
   // resident inputs
   bool have_tasks = false, have_hosts = false;
@@ -858,7 +941,7 @@ struct evg_ctx {
   DevBuf b_taskoff, b_groupoff, b_cfg, b_gmax, b_unitbase;
   DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_cv, b_ca, b_crk, b_bestpair;
   DevBuf b_err, b_dx0, b_dx1, b_dx2, b_dx3, b_dx4, b_dx5, b_dx6, b_dx7;
-  DevBuf b_route, b_listW, b_listA, b_listB, b_listC, b_unitv, b_unita, b_unitn, b_unitmask;
+  DevBuf b_route, b_listW, b_listA, b_listB, b_listC, b_listG, b_unitv, b_unita, b_unitn, b_unitmask;
   int32_t nW = 0, nA = 0, nB = 0, nC = 0, n_general = 0;  // distros per on-chip class / general path
   std::vector<int32_t> h_listW, h_listA, h_listB, h_listC;  // host copies (ascending distro ids) for the pipelined one-shot call
   std::vector<int64_t> h_taskoff, h_groupoff;
@@ -897,7 +980,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   if (E > 0 && (!t->dep_off || !t->dep_idx)) return fail(EVG_ERR_INVALID, "n_edges > 0 but dep_off/dep_idx null");
   if (D == 0 && T != 0) return fail(EVG_ERR_INVALID, "tasks without distros");
   std::vector<int64_t> unit_base(size_t(D) + 1, 0), dtile_off(size_t(D) + 1, 0);
-  std::vector<int32_t> tile_distro, listW, listA, listB, listC;
+  std::vector<int32_t> tile_distro, listW, listA, listB, listC, listG;
   std::vector<int64_t> tile_start;
   std::vector<uint8_t> route(size_t(D) + 1, 0);
   int32_t n_general = 0;
@@ -921,6 +1004,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
     else if (n <= kCapC) { listC.push_back(d); route[d] = 1; }
     else {
       n_general++;
+      listG.push_back(d);
       const int64_t de = (E > 0) ? (t->dep_off[b] - t->dep_off[a]) : 0;
       if (gb > ga || cf.group_versions || de > 0) general_complex = 1;
       for (int64_t s = a; s < b; s += kTile) { tile_distro.push_back(d); tile_start.push_back(s); }
@@ -969,6 +1053,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   UP(c->b_dtileoff, dtile_off.data(), D + 1, int64_t);
   UP(c->b_route, route.data(), D + 1, uint8_t);
   UP(c->b_listW, listW.data(), int64_t(listW.size()), int32_t);
+  UP(c->b_listG, listG.data(), int64_t(listG.size()), int32_t);
   UP(c->b_listA, listA.data(), int64_t(listA.size()), int32_t);
   UP(c->b_listB, listB.data(), int64_t(listB.size()), int32_t);
   UP(c->b_listC, listC.data(), int64_t(listC.size()), int32_t);
@@ -1006,6 +1091,8 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   CK(c->b_order.ensure(sizeof(int32_t) * size_t(T + 1)));
   CK(c->b_tv.ensure(sizeof(int64_t) * size_t(T + 1)));
   c->T = T; c->E = E; c->G = G; c->U = U; c->NT = NT; c->Dn = D;
+  c->max_groups = 0;
+  for (int32_t d = 0; d < D; d++) c->max_groups = std::max(c->max_groups, dt->group_off[d + 1] - dt->group_off[d]);
   c->any_complex = any_complex;
   c->nW = int32_t(listW.size());
   c->nA = int32_t(listA.size()); c->nB = int32_t(listB.size()); c->nC = int32_t(listC.size());
@@ -1109,7 +1196,11 @@ int run_alloc(evg_ctx* c, int64_t now) {
   h.host_off = c->b_hostoff.as<int64_t>(); h.cfg = c->b_acfg.as<evg_alloc_cfg>();
   if (c->ext_result && c->ext_capacity < c->Dn) return fail(EVG_ERR_INVALID, "bound result buffer holds %lld rows, need %d", (long long)c->ext_capacity, c->Dn);
   CK(c->b_gs.ensure(sizeof(GroupScratch) * size_t(c->G + 1)));
-  LAUNCH(c, k_alloc, grid_for(int64_t(c->Dn) * 32, 128), 128, h, 0, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
+  if (c->max_groups > kWideAllocGroups)
+    LAUNCH(c, k_alloc<128>, unsigned(c->Dn), 128, h, 0, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
+           c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>());
+  else
+  LAUNCH(c, k_alloc<32>, grid_for(c->Dn, 4), 128, h, 0, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
          c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>());
   CK(cudaGetLastError());
   return EVG_OK;
@@ -1195,7 +1286,7 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
     if (c->timed) CK(cudaEventRecord(c->ev_sort0, s));  // the general path's segmented sort
     for (int j = 0; j < passes; j++) {
       LAUNCH(c, k_sort_hist, unsigned(c->NT), 256, j, dd, w);
-      LAUNCH(c, k_sort_scan, unsigned(D), 256, j, dd, w);
+      LAUNCH(c, k_sort_scan, unsigned(c->n_general), 1024, j, c->b_listG.as<int32_t>(), dd, w);
       LAUNCH(c, k_sort_scatter, unsigned(c->NT), 256, j, dd, w);
     }
     if (c->timed) CK(cudaEventRecord(c->ev_sort1, s));
@@ -1245,7 +1336,7 @@ void evg_shutdown(evg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->b_prio, &c->b_exp, &c->b_qb, &c->b_wb, &c->b_nd, &c->b_tgo, &c->b_gid, &c->b_vid, &c->b_flags,
                    &c->b_depoff, &c->b_depidx, &c->b_taskoff, &c->b_groupoff, &c->b_cfg, &c->b_gmax, &c->b_unitbase,
-                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita, &c->b_unitn, &c->b_unitmask, &c->b_err, &c->b_dx0, &c->b_dx1, &c->b_dx2, &c->b_dx3, &c->b_dx4, &c->b_dx5, &c->b_dx6, &c->b_dx7, &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_cv, &c->b_ca, &c->b_crk,
+                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita, &c->b_unitn, &c->b_unitmask, &c->b_err, &c->b_dx0, &c->b_dx1, &c->b_dx2, &c->b_dx3, &c->b_dx4, &c->b_dx5, &c->b_dx6, &c->b_dx7, &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_listG, &c->b_cv, &c->b_ca, &c->b_crk,
                    &c->b_bestpair, &c->b_ks[0], &c->b_ks[1], &c->b_kv[0], &c->b_kv[1], &c->b_ix[0], &c->b_ix[1], &c->b_bits,
                    &c->b_npass, &c->b_sched, &c->b_maxpass, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
@@ -1439,7 +1530,7 @@ static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg
     if ((rc = launch_smem<128, 8, 8>(c, dtk, dd, w, c->b_listA.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
     cnt = sub(c->h_listW, d0, d1, &first);
     if ((rc = launch_tiny(c, dtk, dd, w, c->b_listW.as<int32_t>() + first, cnt, now, 0)) != EVG_OK) return rc;
-    LAUNCH(c, k_alloc, grid_for(int64_t(d1 - d0) * 32, 128), 128, h, d0, d1, c->b_groupoff.as<int64_t>(),
+    LAUNCH(c, k_alloc<32>, grid_for(d1 - d0, 4), 128, h, d0, d1, c->b_groupoff.as<int64_t>(),
            c->b_qinfo.as<evg_queue_info>(), c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now,
            c->result_ptr(), c->b_status.as<int32_t>());
     CK(cudaEventRecord(c->ev_c[k], s));
@@ -1512,6 +1603,8 @@ int evg_alloc_batch(evg_ctx* c, const evg_host_soa* hosts, const int64_t* host_o
   if (G > 0) CK(cudaMemcpyAsync(c->b_ginfo.p, groups, sizeof(evg_group_info) * size_t(G), cudaMemcpyHostToDevice, s));
   c->Dn = n_distros;
   c->G = G;
+  c->max_groups = 0;
+  for (int32_t d = 0; d < n_distros; d++) c->max_groups = std::max(c->max_groups, group_off[d + 1] - group_off[d]);
   c->have_tasks = false;  // the resident planner inputs no longer match these tables
   c->launches = 0;
   rc = run_alloc(c, now_ns);

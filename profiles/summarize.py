@@ -18,20 +18,30 @@ def launches(path):
     ends = [i for i, (n, _) in enumerate(names) if n.startswith("k_alloc")]
     print(f"# ncu launch list ({len(names)} launches; `--metrics gpu__time_duration.sum --clock-control none`)\n")
     print("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n")
+    def table(seg, title):
+        agg = collections.OrderedDict()
+        for n, v in seg:
+            a = agg.setdefault(n, [0, 0.0])
+            a[0] += 1
+            a[1] += v
+        tot = sum(v for _, v in agg.values())
+        print(f"{title}\n")
+        print("| kernel | launches | time (us) | share |\n|---|---:|---:|---:|")
+        for n, (c, v) in agg.items():
+            print(f"| `{n}` | {c} | {v / 1e3:.1f} | {100 * v / tot:.1f}% |")
+        print(f"| **total** | {sum(c for c, _ in agg.values())} | {tot / 1e3:.1f} | 100% |\n")
     if len(ends) < 2:
-        seg = names
-    else:
-        seg = names[ends[-2] + 1: ends[-1] + 1]  # the last complete step
-    agg = collections.OrderedDict()
-    for n, v in seg:
-        a = agg.setdefault(n, [0, 0.0])
-        a[0] += 1
-        a[1] += v
-    tot = sum(v for _, v in agg.values())
-    print("| kernel | launches | time (us) | share |\n|---|---:|---:|---:|")
-    for n, (c, v) in agg.items():
-        print(f"| `{n}` | {c} | {v / 1e3:.1f} | {100 * v / tot:.1f}% |")
-    print(f"| **one tick** | {sum(c for c, _ in agg.values())} | {tot / 1e3:.1f} | 100% |")
+        table(names, "All launches:")
+        return
+    segs = [names[a + 1: b + 1] for a, b in zip(ends[:-1], ends[1:])]
+    # resident ticks (evg_run_resident: the bench's timed region) have no k_validate; the one-shot pipelined call
+    # (evg_plan_and_alloc_batch, the e2e leg) validates and plans chunk by chunk
+    resident = [s for s in segs if not any(n.startswith("k_validate") for n, _ in s)]
+    chunked = [s for s in segs if any(n.startswith("k_validate") for n, _ in s)]
+    if resident:
+        table(resident[-1], "One resident tick (the timed region of bench.py):")
+    if chunked:
+        table(chunked[-1], "One chunk of the pipelined one-shot call (bench.py e2e leg; H2D/D2H copies overlap on other streams):")
 
 
 def kernel(path):
