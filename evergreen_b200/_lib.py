@@ -92,6 +92,18 @@ EVG_TS_BLOCKED = 0x4
 EVG_TP_OVERRIDE, EVG_TP_MET_TIME = 0x1, 0x2
 
 
+class RunnableInStruct(C.Structure):
+    _fields_ = [("n_tasks", C.c_int64), ("n_distros", C.c_int32), ("n_projects", C.c_int32), ("task_off", C.c_void_p),
+                ("sched", C.c_void_p), ("project", C.c_void_p), ("project_flags", C.c_void_p), ("valid_off", C.c_void_p),
+                ("valid_idx", C.c_void_p), ("finder", C.c_void_p), ("deps", C.POINTER(DepsInStruct))]
+
+
+EVG_SQ_ACTIVATED, EVG_SQ_UNDISPATCHED, EVG_SQ_PRIORITY_OK, EVG_SQ_HOST_PLATFORM = 0x01, 0x02, 0x04, 0x08
+EVG_SQ_UNATTAINABLE, EVG_SQ_OVERRIDE_DEPS, EVG_SQ_GITHUB_PR, EVG_SQ_PATCH_REQUEST = 0x10, 0x20, 0x40, 0x80
+EVG_PF_ENABLED, EVG_PF_HIDDEN, EVG_PF_DISPATCHING_DISABLED, EVG_PF_PATCHING_DISABLED = 0x1, 0x2, 0x4, 0x8
+EVG_FINDER_NO_DEPS, EVG_FINDER_LEGACY, EVG_FINDER_ALTERNATE = 0, 1, 2
+
+
 class AllocOutStruct(C.Structure):
     _fields_ = [("result", C.c_void_p), ("status", C.c_void_p)]
 
@@ -123,6 +135,7 @@ SYMBOLS = {
     "evg_last_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "evg_kernel_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
     "evg_deps_met_batch": (C.c_int, [_P, _P, _P]),
+    "evg_find_runnable_batch": (C.c_int, [_P, _P, _P, _P]),
     "evg_plan_distro": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, C.c_uint32, _P]),
     "evg_alloc_distro": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P]),
 }

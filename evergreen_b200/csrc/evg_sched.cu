@@ -292,12 +292,15 @@ struct DDeps {
   const uint8_t* ext_state;
   int64_t n_ext;
 };
-__global__ void __launch_bounds__(256) k_deps_met(DDeps X, uint8_t* met, int* err) {
+// met[t] bit 0: Task.DependenciesMet (with the HasDependenciesMet short-circuit); with `both`, bit 1:
+// Task.AllDependenciesSatisfied (task.go:795-821: the same walk without the short-circuit).
+__global__ void __launch_bounds__(256) k_deps_met(DDeps X, uint8_t* met, int* err, int both) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= X.n_tasks) return;
   const int64_t e0 = X.dep_off[t], e1 = X.dep_off[t + 1];
   bool ok = true;
-  if (e1 > e0 && !(X.task_pre[t] & (EVG_TP_OVERRIDE | EVG_TP_MET_TIME))) {  // HasDependenciesMet task.go:3393
+  const bool shortcut = (X.task_pre[t] & (EVG_TP_OVERRIDE | EVG_TP_MET_TIME)) != 0;  // HasDependenciesMet task.go:3393
+  if (e1 > e0 && (both || !shortcut)) {
     for (int64_t e = e0; e < e1 && ok; e++) {
       const uint8_t kind = X.dep_kind[e];
       const int32_t ref = X.dep_ref[e];
@@ -321,7 +324,69 @@ __global__ void __launch_bounds__(256) k_deps_met(DDeps X, uint8_t* met, int* er
       }
     }
   }
-  met[t] = ok ? 1 : 0;
+  met[t] = uint8_t(((ok || shortcut) ? 1 : 0) | ((both && ok) ? 2 : 0));
+}
+
+// The task finders' filter (task_finder.go:40-197) with a stable per-distro compaction: one block per distro,
+// 256 tasks per step, ballot + warp totals for the positions.
+struct DRunnable {
+  int64_t n_tasks;
+  int32_t n_distros, n_projects;
+  const int64_t* task_off;
+  const uint8_t* sched;
+  const int32_t* project;
+  const uint8_t* project_flags;
+  const int64_t* valid_off;
+  const int32_t* valid_idx;
+  const uint8_t* finder;
+  const uint8_t* met;  // k_deps_met(both) output, or nullptr
+};
+__global__ void __launch_bounds__(256) k_runnable(DRunnable R, int32_t* __restrict__ out, int64_t* __restrict__ count, int* err) {
+  const int d = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
+  const int64_t base = R.task_off[d], end = R.task_off[d + 1];
+  const int64_t v0 = R.valid_off[d], v1 = R.valid_off[d + 1];
+  const uint32_t finder = R.finder[d];
+  __shared__ uint32_t s_warp[8];
+  int64_t running = 0;  // kept identically by every thread
+  for (int64_t c0 = base; c0 < end; c0 += 256) {
+    const int64_t t = c0 + threadIdx.x;
+    bool keep = false;
+    if (t < end) {
+      const uint32_t sq = R.sched[t];
+      // schedulableHostTasksQuery (model/task/db.go:671-689)
+      keep = (sq & EVG_SQ_ACTIVATED) && (sq & EVG_SQ_UNDISPATCHED) && (sq & EVG_SQ_PRIORITY_OK) && (sq & EVG_SQ_HOST_PLATFORM) &&
+             (!(sq & EVG_SQ_UNATTAINABLE) || (sq & EVG_SQ_OVERRIDE_DEPS));
+      const int32_t p = R.project[t];
+      if (p >= R.n_projects) { atomicOr(err, 1); keep = false; }
+      else if (p < 0) keep = false;  // "could not find project for task" (task_finder.go:57-67)
+      else if (keep) {
+        const uint32_t pf = R.project_flags[p];
+        // ProjectCanDispatchTask (model/project_ref.go:3441-3462)
+        if (!(pf & EVG_PF_ENABLED) && !((sq & EVG_SQ_GITHUB_PR) && (pf & EVG_PF_HIDDEN))) keep = false;
+        if (pf & EVG_PF_DISPATCHING_DISABLED) keep = false;
+        if ((sq & EVG_SQ_PATCH_REQUEST) && (pf & EVG_PF_PATCHING_DISABLED)) keep = false;
+        if (keep && v1 > v0) {  // len(d.ValidProjects) > 0 && !contains(ref.Id) (task_finder.go:74-84)
+          bool found = false;
+          for (int64_t k = v0; k < v1 && !found; k++) found = R.valid_idx[k] == p;
+          keep = found;
+        }
+        if (keep && finder != EVG_FINDER_NO_DEPS) keep = (R.met[t] & (finder == EVG_FINDER_LEGACY ? 1u : 2u)) != 0;
+      }
+    }
+    const unsigned m = __ballot_sync(full, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t x = s_warp[w]; total += x; if (w < warp) before += x; }
+    if (keep) out[base + running + before + __popc(m & ((1u << lane) - 1u))] = int32_t(t - base);
+    running += total;
+    __syncthreads();
+  }
+  for (int64_t i = base + running + threadIdx.x; i < end; i += 256) out[i] = -1;  // unused tail of the distro's slots
+  if (threadIdx.x == 0) count[d] = running;
 }
 
 // planner.go:449-456 (pass 2): mark every task some in-queue task depends on.
@@ -940,6 +1005,7 @@ struct evg_ctx {
   DevBuf b_prio, b_exp, b_qb, b_wb, b_nd, b_tgo, b_gid, b_vid, b_flags, b_depoff, b_depidx;
   DevBuf b_taskoff, b_groupoff, b_cfg, b_gmax, b_unitbase;
   DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_cv, b_ca, b_crk, b_bestpair;
+  DevBuf b_rn0, b_rn1, b_rn2, b_rn3, b_rn4, b_rn5, b_rn6, b_rn7;
   DevBuf b_err, b_dx0, b_dx1, b_dx2, b_dx3, b_dx4, b_dx5, b_dx6, b_dx7;
   DevBuf b_route, b_listW, b_listA, b_listB, b_listC, b_listG, b_unitv, b_unita, b_unitn, b_unitmask;
   int32_t nW = 0, nA = 0, nB = 0, nC = 0, n_general = 0;  // distros per on-chip class / general path
@@ -1336,7 +1402,7 @@ void evg_shutdown(evg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->b_prio, &c->b_exp, &c->b_qb, &c->b_wb, &c->b_nd, &c->b_tgo, &c->b_gid, &c->b_vid, &c->b_flags,
                    &c->b_depoff, &c->b_depidx, &c->b_taskoff, &c->b_groupoff, &c->b_cfg, &c->b_gmax, &c->b_unitbase,
-                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita, &c->b_unitn, &c->b_unitmask, &c->b_err, &c->b_dx0, &c->b_dx1, &c->b_dx2, &c->b_dx3, &c->b_dx4, &c->b_dx5, &c->b_dx6, &c->b_dx7, &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_listG, &c->b_cv, &c->b_ca, &c->b_crk,
+                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita, &c->b_unitn, &c->b_unitmask, &c->b_rn0, &c->b_rn1, &c->b_rn2, &c->b_rn3, &c->b_rn4, &c->b_rn5, &c->b_rn6, &c->b_rn7, &c->b_err, &c->b_dx0, &c->b_dx1, &c->b_dx2, &c->b_dx3, &c->b_dx4, &c->b_dx5, &c->b_dx6, &c->b_dx7, &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_listG, &c->b_cv, &c->b_ca, &c->b_crk,
                    &c->b_bestpair, &c->b_ks[0], &c->b_ks[1], &c->b_kv[0], &c->b_kv[1], &c->b_ix[0], &c->b_ix[1], &c->b_bits,
                    &c->b_npass, &c->b_sched, &c->b_maxpass, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
@@ -1616,8 +1682,8 @@ int evg_alloc_batch(evg_ctx* c, const evg_host_soa* hosts, const int64_t* host_o
   return EVG_OK;
 }
 
-int evg_deps_met_batch(evg_ctx* c, const evg_deps_in* in, uint8_t* met) {
-  if (!c || !in || (in->n_tasks > 0 && !met)) return fail(EVG_ERR_INVALID, "evg_deps_met_batch: null argument");
+// Stage an evg_deps_in table and run k_deps_met into b_dx7 (left on the device); `both` adds the no-short-circuit bit.
+static int deps_to_device(evg_ctx* c, const evg_deps_in* in, int both) {
   const int64_t T = in->n_tasks, E = in->n_deps, X = in->n_ext;
   if (T < 0 || E < 0 || X < 0) return fail(EVG_ERR_INVALID, "negative sizes");
   if (T == 0) return EVG_OK;
@@ -1625,7 +1691,6 @@ int evg_deps_met_batch(evg_ctx* c, const evg_deps_in* in, uint8_t* met) {
   if (E > 0 && (!in->dep_kind || !in->dep_ref || !in->dep_want)) return fail(EVG_ERR_INVALID, "null dependency arrays");
   if (X > 0 && !in->ext_state) return fail(EVG_ERR_INVALID, "null ext_state");
   if (in->dep_off[0] != 0 || in->dep_off[T] != E) return fail(EVG_ERR_INVALID, "dep_off does not span n_deps");
-  CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
 #define UPD(buf, ptr, count, type)                                                                                 \
   do {                                                                                                             \
@@ -1641,20 +1706,93 @@ int evg_deps_met_batch(evg_ctx* c, const evg_deps_in* in, uint8_t* met) {
   UPD(c->b_dx6, in->ext_state, X, uint8_t);
 #undef UPD
   CK(c->b_dx7.ensure(size_t(T)));
-  CK(c->b_err.ensure(sizeof(int) * 4));
-  CK(cudaMemsetAsync(c->b_err.p, 0, sizeof(int) * 4, s));
   DDeps d;
   d.n_tasks = T; d.dep_off = c->b_dx0.as<int64_t>(); d.dep_kind = c->b_dx1.as<uint8_t>(); d.dep_ref = c->b_dx2.as<int32_t>();
   d.dep_want = c->b_dx3.as<uint8_t>(); d.task_state = c->b_dx4.as<uint8_t>(); d.task_pre = c->b_dx5.as<uint8_t>();
   d.ext_state = c->b_dx6.as<uint8_t>(); d.n_ext = X;
-  k_deps_met<<<grid_for(T, 256), 256, 0, s>>>(d, c->b_dx7.as<uint8_t>(), c->b_err.as<int>());
-  c->launches = 1;
+  k_deps_met<<<grid_for(T, 256), 256, 0, s>>>(d, c->b_dx7.as<uint8_t>(), c->b_err.as<int>(), both);
+  c->launches++;
   CK(cudaGetLastError());
+  return EVG_OK;
+}
+
+int evg_deps_met_batch(evg_ctx* c, const evg_deps_in* in, uint8_t* met) {
+  if (!c || !in || (in->n_tasks > 0 && !met)) return fail(EVG_ERR_INVALID, "evg_deps_met_batch: null argument");
+  if (in->n_tasks == 0) return EVG_OK;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  CK(c->b_err.ensure(sizeof(int) * 4));
+  CK(cudaMemsetAsync(c->b_err.p, 0, sizeof(int) * 4, s));
+  c->launches = 0;
+  int rc = deps_to_device(c, in, 0);
+  if (rc != EVG_OK) return rc;
   int bad = 0;
-  CK(cudaMemcpyAsync(met, c->b_dx7.p, size_t(T), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(met, c->b_dx7.p, size_t(in->n_tasks), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (bad) return fail(EVG_ERR_INVALID, "a dep_ref is out of range");
+  return EVG_OK;
+}
+
+int evg_find_runnable_batch(evg_ctx* c, const evg_runnable_in* in, int32_t* runnable, int64_t* count) {
+  if (!c || !in) return fail(EVG_ERR_INVALID, "evg_find_runnable_batch: null argument");
+  const int64_t T = in->n_tasks;
+  const int32_t D = in->n_distros, P = in->n_projects;
+  if (T < 0 || D < 0 || P < 0) return fail(EVG_ERR_INVALID, "negative sizes");
+  if (D == 0) return T == 0 ? EVG_OK : fail(EVG_ERR_INVALID, "tasks without distros");
+  if (!count || (T > 0 && !runnable)) return fail(EVG_ERR_INVALID, "null output");
+  if (!in->task_off || !in->valid_off || !in->finder) return fail(EVG_ERR_INVALID, "null distro arrays");
+  if (T > 0 && (!in->sched || !in->project)) return fail(EVG_ERR_INVALID, "null task column");
+  if (P > 0 && !in->project_flags) return fail(EVG_ERR_INVALID, "null project_flags");
+  if (in->task_off[0] != 0 || in->task_off[D] != T || in->valid_off[0] != 0) return fail(EVG_ERR_INVALID, "offsets do not span the tables");
+  bool any_deps = false;
+  for (int32_t d = 0; d < D; d++) {
+    if (in->task_off[d + 1] < in->task_off[d] || in->valid_off[d + 1] < in->valid_off[d]) return fail(EVG_ERR_INVALID, "offsets of distro %d decrease", d);
+    if (in->finder[d] > EVG_FINDER_ALTERNATE) return fail(EVG_ERR_INVALID, "distro %d: unknown finder %d", d, int(in->finder[d]));
+    any_deps = any_deps || in->finder[d] != EVG_FINDER_NO_DEPS;
+  }
+  const int64_t V = in->valid_off[D];
+  if (V > 0 && !in->valid_idx) return fail(EVG_ERR_INVALID, "null valid_idx");
+  if (any_deps && T > 0 && (!in->deps || in->deps->n_tasks != T)) return fail(EVG_ERR_INVALID, "a finder checks dependencies but deps is null or of another size");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  CK(c->b_err.ensure(sizeof(int) * 4));
+  CK(cudaMemsetAsync(c->b_err.p, 0, sizeof(int) * 4, s));
+  c->launches = 0;
+  c->have_tasks = false;  // the scratch columns below are shared with nothing resident, but the order buffer is reused
+  if (any_deps && T > 0) {
+    int rc = deps_to_device(c, in->deps, 1);
+    if (rc != EVG_OK) return rc;
+  }
+#define UPR(buf, ptr, count, type)                                                                                 \
+  do {                                                                                                             \
+    CK((buf).ensure(sizeof(type) * size_t((count) > 0 ? (count) : 1)));                                            \
+    if ((count) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(count), cudaMemcpyHostToDevice, s)); \
+  } while (0)
+  UPR(c->b_rn0, in->task_off, D + 1, int64_t);
+  UPR(c->b_rn1, in->sched, T, uint8_t);
+  UPR(c->b_rn2, in->project, T, int32_t);
+  UPR(c->b_rn3, in->project_flags, P, uint8_t);
+  UPR(c->b_rn4, in->valid_off, D + 1, int64_t);
+  UPR(c->b_rn5, in->valid_idx, V, int32_t);
+  UPR(c->b_rn6, in->finder, D, uint8_t);
+#undef UPR
+  CK(c->b_order.ensure(sizeof(int32_t) * size_t(T + 1)));
+  CK(c->b_rn7.ensure(sizeof(int64_t) * size_t(D)));
+  DRunnable r;
+  r.n_tasks = T; r.n_distros = D; r.n_projects = P;
+  r.task_off = c->b_rn0.as<int64_t>(); r.sched = c->b_rn1.as<uint8_t>(); r.project = c->b_rn2.as<int32_t>();
+  r.project_flags = c->b_rn3.as<uint8_t>(); r.valid_off = c->b_rn4.as<int64_t>(); r.valid_idx = c->b_rn5.as<int32_t>();
+  r.finder = c->b_rn6.as<uint8_t>(); r.met = (any_deps && T > 0) ? c->b_dx7.as<uint8_t>() : nullptr;
+  k_runnable<<<unsigned(D), 256, 0, s>>>(r, c->b_order.as<int32_t>(), c->b_rn7.as<int64_t>(), c->b_err.as<int>());
+  c->launches++;
+  CK(cudaGetLastError());
+  int bad = 0;
+  if (T > 0) CK(cudaMemcpyAsync(runnable, c->b_order.p, sizeof(int32_t) * size_t(T), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(count, c->b_rn7.p, sizeof(int64_t) * size_t(D), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (bad) return fail(EVG_ERR_INVALID, "a project row or dep_ref is out of range");
   return EVG_OK;
 }
 

@@ -60,6 +60,7 @@ PROVIDER_MOCK = "mock"
 PROVIDER_SPAWNABLE = (PROVIDER_EC2_ONDEMAND, PROVIDER_EC2_FLEET, PROVIDER_MOCK, PROVIDER_DOCKER)  # globals.go:723-728
 # model/task_queue.go:216-219
 PERSISTED_QUEUE_CAP = 10000
+DISABLED_TASK_PRIORITY = -1  # globals.go:187
 
 
 def is_github_merge_queue_requester(r: str) -> bool:  # globals.go:1195-1197
@@ -115,6 +116,10 @@ class Task:
     start_time: int = ZERO_TIME
     distro_id: str = ""
     status: str = TASK_UNDISPATCHED
+    # what the task finders' base query reads (schedulableHostTasksQuery, model/task/db.go:671-689)
+    activated: bool = True
+    execution_platform: str = ""           # "" (field absent) or "host" pass ByExecutionPlatform(host), db.go:647-663
+    unattainable_dependency: bool = False  # the cached UnattainableDependency field
     expected_duration: int = 0
     expected_duration_std_dev: int = 0
     duration_prediction: CachedDurationValue = field(default_factory=CachedDurationValue)
@@ -177,6 +182,24 @@ class ContainerPool:  # config_containerpools.go:11-22
 
 
 @dataclass
+class ProjectRef:  # the fields ProjectCanDispatchTask reads (model/project_ref.go:3441-3462)
+    id: str = ""
+    enabled: bool = False
+    hidden: Optional[bool] = None
+    dispatching_disabled: Optional[bool] = None
+    patching_disabled: Optional[bool] = None
+
+    def can_dispatch_task(self, t: "Task") -> bool:
+        if not self.enabled and not (t.requester == GITHUB_PR_REQUESTER and bool(self.hidden)):
+            return False
+        if self.dispatching_disabled:
+            return False
+        if is_patch_requester(t.requester) and self.patching_disabled:
+            return False
+        return True
+
+
+@dataclass
 class Distro:
     id: str = ""
     provider: str = ""
@@ -186,6 +209,7 @@ class Distro:
     planner_settings: PlannerSettings = field(default_factory=PlannerSettings)
     host_allocator_settings: HostAllocatorSettings = field(default_factory=HostAllocatorSettings)
     dispatcher_settings: DispatcherSettings = field(default_factory=lambda: DispatcherSettings(version=""))
+    valid_projects: List[str] = field(default_factory=list)
 
     def max_duration_per_host(self) -> int:  # distro.go:422-432
         if self.container_pool != "":

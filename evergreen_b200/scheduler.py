@@ -187,6 +187,17 @@ class Engine:
         L.check(self.lib.evg_deps_met_batch(self.ctx, C.byref(st), L.ptr(met) if deps.n_tasks else None))
         return met
 
+    def find_runnable_batch(self, table: "S.RunnableTable"):
+        """The task finders' filter for every distro at once (evg_find_runnable_batch):
+        -> (runnable [n_tasks] distro-local indices compacted per distro, -1 padded; count [n_distros])."""
+        runnable = self._out("runnable", table.n_tasks, np.int32)
+        count = self._out("runnable_count", table.n_distros, np.int64)
+        st, keep = table.struct()
+        L.check(self.lib.evg_find_runnable_batch(self.ctx, C.byref(st), L.ptr(runnable) if table.n_tasks else None,
+                                                 L.ptr(count) if table.n_distros else None))
+        del keep
+        return runnable, count
+
     def alloc_batch(self, hosts: S.HostSoA, qinfo: np.ndarray, ginfo: np.ndarray, group_off: np.ndarray, now: int):
         D = int(qinfo.shape[0])
         ao = self._alloc_output(D)
@@ -309,6 +320,32 @@ def dependencies_met(batch: Sequence[Tuple[M.Distro, List[M.Task]]], *, engine: 
         out.append([bool(x) for x in met[a:a + len(tasks)]])
         a += len(tasks)
     return out
+
+
+def find_runnable_tasks(batch: Sequence[Tuple[M.Distro, List[M.Task]]], project_refs: Sequence[M.ProjectRef], *,
+                        finder: str = "legacy", dependency_db: Optional[Dict[str, M.Task]] = None,
+                        engine: Optional[Engine] = None) -> List[List[M.Task]]:
+    """LegacyFindRunnableTasks / AlternateTaskFinder / ParallelTaskFinder (scheduler/task_finder.go:40-317) for every
+    distro of the tick: `batch` holds each distro's candidates (the rows the tasks collection has for it), the result
+    the tasks each finder returns, in candidate order."""
+    eng = engine or default_engine()
+    table = S.marshal_runnable(batch, project_refs, finder, dependency_db)
+    runnable, count = eng.find_runnable_batch(table)
+    out = []
+    for i, (_, tasks) in enumerate(batch):
+        a = int(table.task_off[i])
+        out.append([tasks[int(j)] for j in runnable[a:a + int(count[i])]])
+    return out
+
+
+def LegacyFindRunnableTasks(d: M.Distro, candidates: List[M.Task], project_refs: Sequence[M.ProjectRef], **kw) -> List[M.Task]:
+    """scheduler/task_finder.go:40-106 for one distro."""
+    return find_runnable_tasks([(d, candidates)], project_refs, finder="legacy", **kw)[0]
+
+
+def AlternateTaskFinder(d: M.Distro, candidates: List[M.Task], project_refs: Sequence[M.ProjectRef], **kw) -> List[M.Task]:
+    """scheduler/task_finder.go:108-197 for one distro."""
+    return find_runnable_tasks([(d, candidates)], project_refs, finder="alternate", **kw)[0]
 
 
 def allocate_distros(datas: Sequence[M.HostAllocatorData], now: int, *, engine: Optional[Engine] = None):

@@ -12,6 +12,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
+import ctypes as C
+
 import numpy as np
 
 from . import _lib as L
@@ -447,3 +449,90 @@ def marshal_deps(batch: Sequence[tuple], dependency_db: Optional[Dict[str, M.Tas
     return DepsTable(np.array(dep_off, np.int64), np.array(kind, np.uint8), np.array(ref, np.int32),
                      np.array(want, np.uint8), np.array(tstate, np.uint8), np.array(pre, np.uint8),
                      np.array(ext_state, np.uint8))
+
+
+@dataclass
+class RunnableTable:
+    """evg_runnable_in: every candidate task of every distro, plus the project-ref cache and the per-distro rules."""
+    task_off: np.ndarray
+    sched: np.ndarray
+    project: np.ndarray
+    project_flags: np.ndarray
+    valid_off: np.ndarray
+    valid_idx: np.ndarray
+    finder: np.ndarray
+    deps: Optional[DepsTable]
+
+    @property
+    def n_tasks(self) -> int:
+        return int(self.sched.shape[0])
+
+    @property
+    def n_distros(self) -> int:
+        return int(self.finder.shape[0])
+
+    def struct(self):
+        """-> (RunnableInStruct, keepalive): the nested evg_deps_in must outlive the call."""
+        s = L.RunnableInStruct()
+        s.n_tasks, s.n_distros, s.n_projects = self.n_tasks, self.n_distros, int(self.project_flags.shape[0])
+        s.task_off, s.valid_off, s.finder = L.ptr(self.task_off), L.ptr(self.valid_off), L.ptr(self.finder)
+        s.sched = L.ptr(self.sched) if s.n_tasks else None
+        s.project = L.ptr(self.project) if s.n_tasks else None
+        s.project_flags = L.ptr(self.project_flags) if s.n_projects else None
+        s.valid_idx = L.ptr(self.valid_idx) if self.valid_idx.shape[0] else None
+        keep = None
+        if self.deps is not None:
+            keep = self.deps.struct()
+            s.deps = C.pointer(keep)
+        return s, keep
+
+
+def sched_bits(t: M.Task) -> int:
+    """The EVG_SQ_* byte of one task: the fields of schedulableHostTasksQuery (model/task/db.go:671-689) and the
+    requester classes ProjectCanDispatchTask looks at."""
+    b = 0
+    if t.activated:
+        b |= L.EVG_SQ_ACTIVATED
+    if t.status == M.TASK_UNDISPATCHED:
+        b |= L.EVG_SQ_UNDISPATCHED
+    if t.priority > M.DISABLED_TASK_PRIORITY:
+        b |= L.EVG_SQ_PRIORITY_OK
+    if t.execution_platform in ("", "host"):
+        b |= L.EVG_SQ_HOST_PLATFORM
+    if t.unattainable_dependency:
+        b |= L.EVG_SQ_UNATTAINABLE
+    if t.override_dependencies:
+        b |= L.EVG_SQ_OVERRIDE_DEPS
+    if t.requester == M.GITHUB_PR_REQUESTER:
+        b |= L.EVG_SQ_GITHUB_PR
+    if M.is_patch_requester(t.requester):
+        b |= L.EVG_SQ_PATCH_REQUEST
+    return b
+
+
+def project_bits(p: M.ProjectRef) -> int:
+    return ((L.EVG_PF_ENABLED if p.enabled else 0) | (L.EVG_PF_HIDDEN if p.hidden else 0) |
+            (L.EVG_PF_DISPATCHING_DISABLED if p.dispatching_disabled else 0) |
+            (L.EVG_PF_PATCHING_DISABLED if p.patching_disabled else 0))
+
+
+def marshal_runnable(batch: Sequence[tuple], project_refs: Sequence[M.ProjectRef], finder: str = "legacy",
+                     dependency_db: Optional[Dict[str, M.Task]] = None) -> RunnableTable:
+    """[(Distro, [candidate Task])] + the project-ref cache (getProjectRefCache, task_finder.go:46) -> RunnableTable.
+    `finder`: "legacy" (LegacyFindRunnableTasks) or "alternate" (AlternateTaskFinder / ParallelTaskFinder)."""
+    prow = {p.id: i for i, p in enumerate(project_refs)}
+    flavour = {"legacy": L.EVG_FINDER_LEGACY, "alternate": L.EVG_FINDER_ALTERNATE, "parallel": L.EVG_FINDER_ALTERNATE}[finder]
+    task_off, valid_off, valid_idx, fnd, sched, proj = [0], [0], [], [], [], []
+    for d, tasks in batch:
+        for t in tasks:
+            sched.append(sched_bits(t))
+            proj.append(prow.get(t.project, -1))
+        task_off.append(len(sched))
+        valid_idx.extend(prow.get(name, -1) for name in d.valid_projects)
+        valid_off.append(len(valid_idx))
+        fnd.append(L.EVG_FINDER_NO_DEPS
+                   if d.dispatcher_settings.version == M.DISPATCHER_VERSION_REVISED_WITH_DEPENDENCIES else flavour)
+    deps = marshal_deps(batch, dependency_db) if any(f != L.EVG_FINDER_NO_DEPS for f in fnd) else None
+    return RunnableTable(np.array(task_off, np.int64), np.array(sched, np.uint8), np.array(proj, np.int32),
+                         np.array([project_bits(p) for p in project_refs], np.uint8), np.array(valid_off, np.int64),
+                         np.array(valid_idx, np.int32), np.array(fnd, np.uint8), deps)

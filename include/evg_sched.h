@@ -335,6 +335,48 @@ typedef struct {
  * task finders filter on (scheduler/task_finder.go:40-197).  Host pointers in and out. */
 int evg_deps_met_batch(evg_ctx* ctx, const evg_deps_in* in, uint8_t* met);
 
+/* ---- runnable-task filter: the task finders ------------- */
+
+/* evg_runnable_in.sched: what schedulableHostTasksQuery (model/task/db.go:671-689) and ProjectCanDispatchTask read of a task */
+#define EVG_SQ_ACTIVATED 0x01u      /* Activated */
+#define EVG_SQ_UNDISPATCHED 0x02u   /* Status == "undispatched" */
+#define EVG_SQ_PRIORITY_OK 0x04u    /* Priority > DisabledTaskPriority (-1) */
+#define EVG_SQ_HOST_PLATFORM 0x08u  /* ByExecutionPlatform(host): field absent or "host" (db.go:647-663) */
+#define EVG_SQ_UNATTAINABLE 0x10u   /* UnattainableDependency */
+#define EVG_SQ_OVERRIDE_DEPS 0x20u  /* OverrideDependencies */
+#define EVG_SQ_GITHUB_PR 0x40u      /* Requester == "github_pull_request" */
+#define EVG_SQ_PATCH_REQUEST 0x80u  /* Task.IsPatchRequest() (model/task/task.go:545-547) */
+/* evg_runnable_in.project_flags: ProjectRef fields ProjectCanDispatchTask reads (model/project_ref.go:3441-3462) */
+#define EVG_PF_ENABLED 0x1u
+#define EVG_PF_HIDDEN 0x2u
+#define EVG_PF_DISPATCHING_DISABLED 0x4u
+#define EVG_PF_PATCHING_DISABLED 0x8u
+/* evg_runnable_in.finder, per distro */
+#define EVG_FINDER_NO_DEPS 0    /* DispatcherSettings.Version == "revised-with-dependencies": dependencies are not filtered (task_finder.go:85) */
+#define EVG_FINDER_LEGACY 1     /* LegacyFindRunnableTasks: Task.DependenciesMet, with the HasDependenciesMet short-circuit */
+#define EVG_FINDER_ALTERNATE 2  /* AlternateTaskFinder / ParallelTaskFinder: Task.AllDependenciesSatisfied (task.go:795-821), no short-circuit */
+
+/* Every candidate task of every distro (the rows task.FindHostSchedulable would be asked about), concatenated. */
+typedef struct {
+  int64_t n_tasks;
+  int32_t n_distros;
+  int32_t n_projects;
+  const int64_t* task_off;      /* n_distros + 1 */
+  const uint8_t* sched;         /* n_tasks, EVG_SQ_* */
+  const int32_t* project;       /* n_tasks: row of project_flags, or -1 when the project-ref cache has no such project */
+  const uint8_t* project_flags; /* n_projects, EVG_PF_* */
+  const int64_t* valid_off;     /* n_distros + 1: CSR of Distro.ValidProjects as project rows (-1 = a name no ref has) */
+  const int32_t* valid_idx;
+  const uint8_t* finder;        /* n_distros, EVG_FINDER_* */
+  const evg_deps_in* deps;      /* direct dependencies of the same n_tasks tasks; NULL when every finder is NO_DEPS */
+} evg_runnable_in;
+
+/* LegacyFindRunnableTasks / AlternateTaskFinder / ParallelTaskFinder (scheduler/task_finder.go:40-317) over all
+ * distros at once: runnable[task_off[d] .. task_off[d] + count[d]) holds the distro-local indices of the tasks
+ * the finder returns for distro d, in input order (the reference appends in query order); the rest of the
+ * distro's slots are -1.  Host pointers. */
+int evg_find_runnable_batch(evg_ctx* ctx, const evg_runnable_in* in, int32_t* runnable, int64_t* count);
+
 /* ---- single-distro wrappers: the per-job drop-in ------------------------- */
 
 /* One distro: PrioritizeTasks for `d` (scheduler/scheduler.go:27). */

@@ -250,6 +250,64 @@ def deps_met(tasks: Sequence[M.Task], now: int, dependency_db=None) -> np.ndarra
     return out[:len(tasks)].astype(bool)
 
 
+def _satisfies_dependency(t: M.Task, dep_task: M.Task) -> bool:
+    """Task.SatisfiesDependency, model/task/task.go:529-543."""
+    for dep in t.depends_on:
+        if dep.task_id == dep_task.id:
+            if dep.status in (M.TASK_SUCCEEDED, ""):
+                return dep_task.status == M.TASK_SUCCEEDED
+            if dep.status == M.TASK_FAILED:
+                return dep_task.status == M.TASK_FAILED
+            if dep.status == M.ALL_STATUSES:
+                return dep_task.status in (M.TASK_FAILED, M.TASK_SUCCEEDED) or dep_task.blocked()
+    return False
+
+
+def _deps_walk(t: M.Task, cache: Dict[str, M.Task], shortcut: bool) -> bool:
+    """Task.DependenciesMet (task.go:632-671, shortcut=True) / Task.AllDependenciesSatisfied (task.go:795-821,
+    shortcut=False) over a cache that already holds every task the collection has; a dependency the cache lacks
+    is the lookup error both callers turn into "skip this task" (task_finder.go:86-101,181-186)."""
+    if shortcut and t.has_dependencies_met():
+        return True
+    if not t.depends_on:
+        return True
+    deps = []
+    for dep in t.depends_on:
+        if dep.task_id not in cache:
+            return False
+        deps.append(cache[dep.task_id])
+    return all(_satisfies_dependency(t, d) for d in deps)
+
+
+def find_runnable(d: M.Distro, candidates: Sequence[M.Task], project_refs: Sequence[M.ProjectRef],
+                  dependency_db: Optional[Dict[str, M.Task]] = None, finder: str = "legacy") -> List[M.Task]:
+    """Restatement of LegacyFindRunnableTasks (scheduler/task_finder.go:40-106) and AlternateTaskFinder
+    (:108-197; ParallelTaskFinder :199-317 filters identically) for one distro.  `candidates` stands for the
+    tasks collection restricted to the distro: schedulableHostTasksQuery (model/task/db.go:671-689) is applied
+    here, as task.FindHostSchedulable would (model/task/task.go:3342-3350)."""
+    undispatched = [t for t in candidates
+                    if t.activated and t.status == M.TASK_UNDISPATCHED and t.priority > M.DISABLED_TASK_PRIORITY
+                    and t.execution_platform in ("", "host")
+                    and (not t.unattainable_dependency or t.override_dependencies)]
+    refs = {p.id: p for p in project_refs}
+    cache = dict(dependency_db or {})
+    cache.update({t.id: t for t in candidates})
+    out = []
+    for t in undispatched:
+        ref = refs.get(t.project)
+        if ref is None:  # "could not find project for task"
+            continue
+        if not ref.can_dispatch_task(t):  # model.ProjectCanDispatchTask, model/project_ref.go:3441-3462
+            continue
+        if d.valid_projects and ref.id not in d.valid_projects:
+            continue
+        if d.dispatcher_settings.version != M.DISPATCHER_VERSION_REVISED_WITH_DEPENDENCIES:
+            if not _deps_walk(t, cache, shortcut=(finder == "legacy")):
+                continue
+        out.append(t)
+    return out
+
+
 def hosts_struct(hosts: Sequence[M.Host], running: Dict[str, M.RunningTaskStats]):
     k = _Keep()
     h = Hosts()

@@ -369,6 +369,127 @@ def test_dependency_filter_at_scale(engine):
     assert np.array_equal(got.astype(bool), want)
 
 
+# ---------------------------------------------------------------- task finders
+FINDER = G.load("task_finder.json")
+
+
+def random_finder_batch(rng, n_distros):
+    """Candidates with every field the finders read randomised, plus project refs of every flag combination."""
+    from test_host_logic import random_tasks
+    refs = [M.ProjectRef(id=f"p{k}", enabled=bool(k & 1), hidden=bool(k & 2) or None, dispatching_disabled=bool(k & 4) or None,
+                         patching_disabled=bool(k & 8) or None) for k in range(16)]
+    batch, db_all = [], {}
+    for d in range(n_distros):
+        tasks, db = random_tasks(rng, rng.choice([0, 1, 40, 300, 700]))
+        for t in tasks:
+            t.id = f"d{d}-{t.id}"
+            for dep in t.depends_on:
+                if dep.task_id.startswith("t"):
+                    dep.task_id = f"d{d}-{dep.task_id}"
+            t.project = rng.choice([f"p{rng.randrange(16)}", f"p{rng.randrange(16)}", "p1", "p1", "nowhere"])
+            t.activated = rng.random() < 0.9
+            t.status = rng.choice(["undispatched"] * 8 + ["started", "success"])
+            t.execution_platform = rng.choice(["", "", "host", "container"])
+            t.unattainable_dependency = rng.random() < 0.1
+        dist = M.Distro(id=f"d{d}", valid_projects=rng.choice([[], [], ["p1"], ["p1", "p3", "ghost"], ["ghost"]]),
+                        dispatcher_settings=M.DispatcherSettings(version=rng.choice(["", "revised", "revised-with-dependencies"])))
+        batch.append((dist, tasks))
+        db_all.update(db)
+    return batch, refs, db_all
+
+
+@pytest.mark.parametrize("finder", ["legacy", "alternate"])
+@pytest.mark.parametrize("case", FINDER["cases"], ids=lambda c: c["name"])
+def test_task_finder_cases(engine, case, finder):
+    """What scheduler/task_finder_test.go asserts, through evg_find_runnable_batch."""
+    d, tasks, refs = G.finder_case(case)
+    got = [t.id for t in S.find_runnable_tasks([(d, tasks)], refs, finder=finder, engine=engine)[0]]
+    if "expect_len" in case:
+        assert len(got) == case["expect_len"]
+    if "expect_ids" in case:
+        assert sorted(got) == sorted(case["expect_ids"])
+    assert got == [t.id for t in O.find_runnable(d, tasks, refs, finder=finder)]  # same tasks, same order
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_task_finders_agree_on_fuzzy_tasks(engine, seed):
+    """TaskFinderComparisonSuite (task_finder_test.go:309-334) on its fuzzy generator: every finder returns the same ids."""
+    import random
+    tasks = G.random_finder_tasks(random.Random(seed))
+    refs = [M.ProjectRef(**r) for r in FINDER["cases"][-1]["project_refs"]]
+    a = [t.id for t in S.LegacyFindRunnableTasks(M.Distro(), tasks, refs, engine=engine)]
+    b = [t.id for t in S.AlternateTaskFinder(M.Distro(), tasks, refs, engine=engine)]
+    assert a == b == [t.id for t in O.find_runnable(M.Distro(), tasks, refs)]
+
+
+@pytest.mark.parametrize("finder", ["legacy", "alternate"])
+@pytest.mark.parametrize("seed", range(3))
+def test_task_finder_parity(engine, seed, finder):
+    import random
+    batch, refs, db = random_finder_batch(random.Random(70 + seed), 9)
+    got = S.find_runnable_tasks(batch, refs, finder=finder, dependency_db=db, engine=engine)
+    for (d, tasks), g in zip(batch, got):
+        assert [t.id for t in g] == [t.id for t in O.find_runnable(d, tasks, refs, db, finder)]
+
+
+def test_task_finder_at_scale(engine):
+    """2e6 candidates over 3000 distros: device result vs a numpy restatement of the same table (stable compaction)."""
+    rng = np.random.default_rng(9)
+    D, P = 3000, 64
+    sizes = rng.integers(0, 1400, D)
+    sizes[7] = 40_000
+    off = np.zeros(D + 1, np.int64); np.cumsum(sizes, out=off[1:])
+    T = int(off[-1])
+    sched = (rng.integers(0, 256, T) | 0x0F * (rng.random(T) < 0.85)).astype(np.uint8)
+    project = rng.integers(-1, P, T).astype(np.int32)
+    pflags = rng.integers(0, 16, P).astype(np.uint8) | np.uint8(1) * (rng.random(P) < 0.7).astype(np.uint8)
+    nvalid = np.where(rng.random(D) < 0.3, rng.integers(1, 6, D), 0)
+    voff = np.zeros(D + 1, np.int64); np.cumsum(nvalid, out=voff[1:])
+    vidx = rng.integers(-1, P, int(voff[-1])).astype(np.int32)
+    finder = rng.integers(0, 3, D).astype(np.uint8)
+    n_dep = rng.integers(0, 3, T)
+    doff = np.zeros(T + 1, np.int64); np.cumsum(n_dep, out=doff[1:])
+    E = int(doff[-1])
+    deps = soa.DepsTable(doff, rng.integers(0, 3, E).astype(np.uint8), rng.integers(0, 4000, E).astype(np.int32),
+                         rng.integers(0, 4, E).astype(np.uint8), rng.integers(0, 3, T).astype(np.uint8) | (4 * (rng.random(T) < 0.2)).astype(np.uint8),
+                         (rng.random(T) < 0.1).astype(np.uint8) | ((rng.random(T) < 0.1).astype(np.uint8) << 1),
+                         rng.integers(0, 3, 4000).astype(np.uint8))
+    table = soa.RunnableTable(off, sched, project, pflags, voff, vidx, finder, deps)
+    runnable, count = engine.find_runnable_batch(table)
+    runnable, count = runnable.copy(), count.copy()
+    # numpy restatement
+    st = np.where(deps.dep_kind == 0, deps.task_state[deps.dep_ref], deps.ext_state[deps.dep_ref])
+    status, blocked = st & 3, (st & 4) != 0
+    sat = np.where(deps.dep_want == 0, status == 0, np.where(deps.dep_want == 1, status == 1,
+                   np.where(deps.dep_want == 2, (status < 2) | blocked, False)))
+    sat &= deps.dep_kind != 2
+    unsat = np.add.reduceat(np.concatenate([(~sat).astype(np.int64), [0]]), np.minimum(doff[:-1], E))[:T] * (n_dep > 0)
+    walk_ok = unsat == 0
+    met_legacy = walk_ok | (deps.task_pre != 0)
+    dist_of = np.repeat(np.arange(D), sizes)
+    q = ((sched & 1) != 0) & ((sched & 2) != 0) & ((sched & 4) != 0) & ((sched & 8) != 0) & (((sched & 16) == 0) | ((sched & 32) != 0))
+    pf = pflags[np.maximum(project, 0)]
+    can = (((pf & 1) != 0) | (((sched & 64) != 0) & ((pf & 2) != 0))) & ((pf & 4) == 0) & ~(((sched & 128) != 0) & ((pf & 8) != 0))
+    keep = q & (project >= 0) & can
+    has_valid = nvalid[dist_of] > 0
+    in_valid = np.zeros(T, bool)
+    for d in np.nonzero(nvalid)[0]:
+        a, b = off[d], off[d + 1]
+        in_valid[a:b] = np.isin(project[a:b], vidx[voff[d]:voff[d + 1]])
+    keep &= ~has_valid | in_valid
+    f = finder[dist_of]
+    keep &= (f == 0) | ((f == 1) & met_legacy) | ((f == 2) & walk_ok)
+    assert np.array_equal(count, np.add.reduceat(np.concatenate([keep.astype(np.int64), [0]]), np.minimum(off[:-1], T))[:D] * (sizes > 0))
+    local = np.arange(T) - off[dist_of]
+    want = np.full(T, -1, np.int32)
+    pos = np.cumsum(keep) - keep  # exclusive, global
+    base_pos = pos[np.minimum(off[:-1], T - 1)]
+    dst = off[dist_of] + pos - base_pos[dist_of]
+    want[dst[keep]] = local[keep]
+    assert np.array_equal(runnable, want)
+    assert engine.last_launch_count() == 2  # k_deps_met + k_runnable
+
+
 def test_bad_arguments_are_errors(engine):
     w = synth.make(np.array([10]), 1)
     bad = copy.deepcopy(w)

@@ -159,3 +159,24 @@ def test_score_fast_paths_equal_the_fp64_formulas(tmp_path):
                            os.path.join(root, "tests", "native", "score_fastpath_check.cpp")])
     out = subprocess.check_output([str(exe)]).decode()
     assert "mismatches 0" in out, out
+
+
+def test_marshal_runnable_bits():
+    """soa.marshal_runnable: the byte columns of evg_runnable_in against the reference's field semantics."""
+    from evergreen_b200 import _lib as L
+    from evergreen_b200 import soa
+    refs = [M.ProjectRef(id="a", enabled=True), M.ProjectRef(id="b", hidden=True, patching_disabled=True)]
+    tasks = [M.Task(id="x", project="a", requester="github_pull_request", priority=-1, execution_platform="container"),
+             M.Task(id="y", project="zzz", activated=False, status="started", unattainable_dependency=True,
+                    override_dependencies=True, requester="gitter_request",
+                    depends_on=[M.Dependency("x", status="*")])]
+    d = M.Distro(id="d", valid_projects=["b", "ghost"])
+    t = soa.marshal_runnable([(d, tasks)], refs, "alternate")
+    assert t.sched.tolist() == [L.EVG_SQ_ACTIVATED | L.EVG_SQ_UNDISPATCHED | L.EVG_SQ_GITHUB_PR | L.EVG_SQ_PATCH_REQUEST,
+                                L.EVG_SQ_PRIORITY_OK | L.EVG_SQ_HOST_PLATFORM | L.EVG_SQ_UNATTAINABLE | L.EVG_SQ_OVERRIDE_DEPS]
+    assert t.project.tolist() == [0, -1] and t.project_flags.tolist() == [L.EVG_PF_ENABLED, L.EVG_PF_HIDDEN | L.EVG_PF_PATCHING_DISABLED]
+    assert t.valid_off.tolist() == [0, 2] and t.valid_idx.tolist() == [1, -1]
+    assert t.finder.tolist() == [L.EVG_FINDER_ALTERNATE] and t.deps is not None and t.deps.dep_kind.tolist() == [L.EVG_DEP_IN_QUEUE]
+    d2 = M.Distro(id="e", dispatcher_settings=M.DispatcherSettings(M.DISPATCHER_VERSION_REVISED_WITH_DEPENDENCIES))
+    t2 = soa.marshal_runnable([(d2, tasks)], refs, "legacy")
+    assert t2.finder.tolist() == [L.EVG_FINDER_NO_DEPS] and t2.deps is None

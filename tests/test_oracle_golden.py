@@ -182,3 +182,45 @@ def test_host_allocator_property_bounds():
                      host_allocator_settings=M.HostAllocatorSettings(maximum_hosts=1000, future_host_fraction=0.5))
         n, f, st = O.allocate(M.HostAllocatorData(d, hosts, qi, running_tasks=running), NOW)
         assert st == 0 and 0 <= n <= n_tasks and f >= 0
+
+
+# ---------------------------------------------------------------- task finders
+FINDER = G.load("task_finder.json")
+
+
+@pytest.mark.parametrize("finder", ["legacy", "alternate"])
+@pytest.mark.parametrize("case", FINDER["cases"], ids=lambda c: c["name"])
+def test_task_finder_cases(case, finder):
+    """What scheduler/task_finder_test.go asserts (every finder of the suite must satisfy it)."""
+    d, tasks, refs = G.finder_case(case)
+    got = [t.id for t in O.find_runnable(d, tasks, refs, finder=finder)]
+    if "expect_len" in case:
+        assert len(got) == case["expect_len"]
+    if "expect_ids" in case:
+        assert sorted(got) == sorted(case["expect_ids"])
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_task_finders_agree_on_fuzzy_tasks(seed):
+    """TaskFinderComparisonSuite.TestFindRunnableHostsIsIdentical (task_finder_test.go:309-334) on the fuzzy
+    generator: legacy and alternate finders return the same ids."""
+    import random
+    tasks = G.random_finder_tasks(random.Random(seed))
+    refs = [M.ProjectRef(**r) for r in FINDER["cases"][-1]["project_refs"]]
+    a = sorted(t.id for t in O.find_runnable(M.Distro(), tasks, refs, finder="legacy"))
+    b = sorted(t.id for t in O.find_runnable(M.Distro(), tasks, refs, finder="alternate"))
+    assert a == b
+    assert all(t.startswith("task") for t in a)
+
+
+def test_task_finders_differ_only_by_the_short_circuit():
+    """DependenciesMet trusts DependenciesMetTime / OverrideDependencies (task.go:3393-3395); AllDependenciesSatisfied
+    walks anyway (task.go:795-821)."""
+    dep = M.Task(id="dep", status="failed", activated=True, project="exists")
+    t = M.Task(id="t", activated=True, project="exists", dependencies_met_time=5,
+               depends_on=[M.Dependency(task_id="dep", status="success")])
+    refs = [M.ProjectRef(id="exists", enabled=True)]
+    assert [x.id for x in O.find_runnable(M.Distro(), [t, dep], refs, finder="legacy")] == ["t"]
+    assert [x.id for x in O.find_runnable(M.Distro(), [t, dep], refs, finder="alternate")] == []
+    d = M.Distro(dispatcher_settings=M.DispatcherSettings(version="revised-with-dependencies"))
+    assert [x.id for x in O.find_runnable(d, [t, dep], refs, finder="alternate")] == ["t"]
