@@ -4,6 +4,10 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import this module.  It converts reference-shaped
 inputs (evergreen_b200.model dataclasses, or the synthetic SoA tables turned
 back into strings) into the oracle's columnar-string structs.
+
+The task-finder restatement (find_runnable) is plain Python over the same dataclasses -- the
+finders are a per-task predicate, small enough for a loop; pinned by tests/golden/task_finder.json (the
+assertions of scheduler/task_finder_test.go).
 """
 from __future__ import annotations
 
