@@ -15,7 +15,7 @@ def launches(path):
     rows = list(csv.DictReader(lines))
     names = [(r["Kernel Name"].split("(")[0], float(r["Metric Value"].replace(",", ""))) for r in rows]
     # one step = from one k_plan_smem/k_init_bits launch sequence start to the next k_alloc (inclusive)
-    ends = [i for i, (n, _) in enumerate(names) if n.startswith("k_alloc")]
+    ends = [i for i, (n, _) in enumerate(names) if "k_alloc" in n]
     print(f"# ncu launch list ({len(names)} launches; `--metrics gpu__time_duration.sum --clock-control none`)\n")
     print("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n")
     def table(seg, title):
