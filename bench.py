@@ -108,6 +108,28 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_node(torch, local_rank: int):
+    """Run this rank on the CPUs next to its GPU (NVML's affinity mask for the device with the same PCI bus id), so
+    pinned host buffers are first-touched on the NUMA node the GPU's PCIe link hangs off.  Returns the previous
+    affinity set (to restore for the host-core baseline leg) or None when anything about it is unavailable."""
+    try:
+        import pynvml
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        n = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {i for i in range(n) if (int(mask[i // 64]) >> (i % 64)) & 1} & prev
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
 def cpu_baseline(w, n_distros: int, threads: int):
     """Time the oracle (C++ port of the reference algorithm) on a bounded sample: the first n distros."""
     from oracle import oracle as O
@@ -184,6 +206,7 @@ def main():
         return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    prev_affinity = bind_to_gpu_node(torch, local_rank)
     # NCCL / torchrun may write banners to fd 1; keep stdout clean for the single JSON line
     sys.stdout.flush()
     saved_stdout = os.dup(1)
@@ -295,7 +318,8 @@ def main():
             "decisions_per_s": D_total / step_s,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "tasks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": float(t.item()) * 1e3, "api": "Engine.plan_and_alloc_batch (evg_plan_and_alloc_batch), pinned host columns"},
+                    "ms_per_step": float(t.item()) * 1e3, "api": "Engine.plan_and_alloc_batch (evg_plan_and_alloc_batch), pinned host columns",
+                    "cpu_affinity": "GPU-local NUMA node" if prev_affinity else "unbound"},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
@@ -308,6 +332,8 @@ def main():
             "checksum_new_hosts": new_hosts_checksum,
         }
         if not args.no_cpu_baseline and world == 1:
+            if prev_affinity:
+                os.sched_setaffinity(0, prev_affinity)  # the baseline gets every host core back
             cb, _ = cpu_baseline(w, args.ref_sample, os.cpu_count() or 1)
             line["cpu_baseline"] = cb
         sys.stdout.flush()

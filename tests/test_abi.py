@@ -44,6 +44,8 @@ int main(void) {
          sizeof(evg_alloc_result), sizeof(evg_plan_out));
   printf("%zu %zu %zu %zu %zu\n", offsetof(evg_distro_cfg, num_dependents_factor), offsetof(evg_distro_cfg, n_versions),
          offsetof(evg_queue_info, ungrouped), offsetof(evg_alloc_cfg, provider), offsetof(evg_alloc_result, deficit_ns));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(evg_deps_in), offsetof(evg_deps_in, n_ext), sizeof(evg_runnable_in),
+         offsetof(evg_runnable_in, task_off), offsetof(evg_runnable_in, deps), sizeof(evg_alloc_out));
   return 0;
 }'''
     c = tmp_path / "t.c"
@@ -59,6 +61,9 @@ int main(void) {
     assert offs == [L.DISTRO_CFG_DTYPE.fields["num_dependents_factor"][1], L.DISTRO_CFG_DTYPE.fields["n_versions"][1],
                     L.QUEUE_INFO_DTYPE.fields["ungrouped"][1], L.ALLOC_CFG_DTYPE.fields["provider"][1],
                     L.ALLOC_RESULT_DTYPE.fields["deficit_ns"][1]]
+    more = [int(x) for x in out[2].split()]
+    assert more == [ctypes.sizeof(L.DepsInStruct), L.DepsInStruct.n_ext.offset, ctypes.sizeof(L.RunnableInStruct),
+                    L.RunnableInStruct.task_off.offset, L.RunnableInStruct.deps.offset, ctypes.sizeof(L.AllocOutStruct)]
 
 
 def test_no_cpu_fallback_without_a_device():
