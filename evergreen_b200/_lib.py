@@ -104,6 +104,16 @@ EVG_PF_ENABLED, EVG_PF_HIDDEN, EVG_PF_DISPATCHING_DISABLED, EVG_PF_PATCHING_DISA
 EVG_FINDER_NO_DEPS, EVG_FINDER_LEGACY, EVG_FINDER_ALTERNATE = 0, 1, 2
 
 
+class DurationRowsStruct(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_keys", C.c_int32), ("_reserved", C.c_int32), ("key", C.c_void_p),
+                ("time_taken_ns", C.c_void_p), ("start_ns", C.c_void_p), ("finish_ns", C.c_void_p), ("flags", C.c_void_p),
+                ("window_start_ns", C.c_int64), ("window_end_ns", C.c_int64)]
+
+
+EVG_DR_COMPLETED, EVG_DR_TIMED_OUT = 0x1, 0x2
+DURATION_STAT_DTYPE = np.dtype([("count", np.int64), ("mean_ns", np.float64), ("stddev_ns", np.float64)])
+
+
 class AllocOutStruct(C.Structure):
     _fields_ = [("result", C.c_void_p), ("status", C.c_void_p)]
 
@@ -136,6 +146,7 @@ SYMBOLS = {
     "evg_kernel_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
     "evg_deps_met_batch": (C.c_int, [_P, _P, _P]),
     "evg_find_runnable_batch": (C.c_int, [_P, _P, _P, _P]),
+    "evg_expected_durations_batch": (C.c_int, [_P, _P, _P]),
     "evg_plan_distro": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, C.c_uint32, _P]),
     "evg_alloc_distro": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P]),
 }

@@ -342,51 +342,140 @@ struct DRunnable {
   const uint8_t* met;  // k_deps_met(both) output, or nullptr
 };
 __global__ void __launch_bounds__(256) k_runnable(DRunnable R, int32_t* __restrict__ out, int64_t* __restrict__ count, int* err) {
+  constexpr int ITEMS = 4;  // candidates per thread and step: their loads are in flight together, one barrier pair per 1024
   const int d = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned full = 0xffffffffu;
   const int64_t base = R.task_off[d], end = R.task_off[d + 1];
   const int64_t v0 = R.valid_off[d], v1 = R.valid_off[d + 1];
   const uint32_t finder = R.finder[d];
-  __shared__ uint32_t s_warp[8];
+  const uint32_t met_bit = finder == EVG_FINDER_LEGACY ? 1u : 2u;
+  __shared__ uint32_t s_cnt[ITEMS * 8];  // survivors of (item j, warp w), in output order j-major
   int64_t running = 0;  // kept identically by every thread
-  for (int64_t c0 = base; c0 < end; c0 += 256) {
-    const int64_t t = c0 + threadIdx.x;
-    bool keep = false;
-    if (t < end) {
-      const uint32_t sq = R.sched[t];
+  for (int64_t c0 = base; c0 < end; c0 += 256 * ITEMS) {
+    uint32_t sq[ITEMS], mt[ITEMS];
+    int32_t pj[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const int64_t t = c0 + j * 256 + threadIdx.x;
+      const bool in = t < end;
+      sq[j] = in ? R.sched[t] : 0u;
+      pj[j] = in ? R.project[t] : -1;
+      mt[j] = (in && finder != EVG_FINDER_NO_DEPS) ? R.met[t] : 3u;
+    }
+    bool keep[ITEMS];
+    unsigned m[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const uint32_t q = sq[j];
       // schedulableHostTasksQuery (model/task/db.go:671-689)
-      keep = (sq & EVG_SQ_ACTIVATED) && (sq & EVG_SQ_UNDISPATCHED) && (sq & EVG_SQ_PRIORITY_OK) && (sq & EVG_SQ_HOST_PLATFORM) &&
-             (!(sq & EVG_SQ_UNATTAINABLE) || (sq & EVG_SQ_OVERRIDE_DEPS));
-      const int32_t p = R.project[t];
-      if (p >= R.n_projects) { atomicOr(err, 1); keep = false; }
-      else if (p < 0) keep = false;  // "could not find project for task" (task_finder.go:57-67)
-      else if (keep) {
+      bool k = (q & EVG_SQ_ACTIVATED) && (q & EVG_SQ_UNDISPATCHED) && (q & EVG_SQ_PRIORITY_OK) && (q & EVG_SQ_HOST_PLATFORM) &&
+               (!(q & EVG_SQ_UNATTAINABLE) || (q & EVG_SQ_OVERRIDE_DEPS));
+      const int32_t p = pj[j];
+      if (p >= R.n_projects) { atomicOr(err, 1); k = false; }
+      else if (p < 0) k = false;  // "could not find project for task" (task_finder.go:57-67)
+      else if (k) {
         const uint32_t pf = R.project_flags[p];
         // ProjectCanDispatchTask (model/project_ref.go:3441-3462)
-        if (!(pf & EVG_PF_ENABLED) && !((sq & EVG_SQ_GITHUB_PR) && (pf & EVG_PF_HIDDEN))) keep = false;
-        if (pf & EVG_PF_DISPATCHING_DISABLED) keep = false;
-        if ((sq & EVG_SQ_PATCH_REQUEST) && (pf & EVG_PF_PATCHING_DISABLED)) keep = false;
-        if (keep && v1 > v0) {  // len(d.ValidProjects) > 0 && !contains(ref.Id) (task_finder.go:74-84)
+        if (!(pf & EVG_PF_ENABLED) && !((q & EVG_SQ_GITHUB_PR) && (pf & EVG_PF_HIDDEN))) k = false;
+        if (pf & EVG_PF_DISPATCHING_DISABLED) k = false;
+        if ((q & EVG_SQ_PATCH_REQUEST) && (pf & EVG_PF_PATCHING_DISABLED)) k = false;
+        if (k && v1 > v0) {  // len(d.ValidProjects) > 0 && !contains(ref.Id) (task_finder.go:74-84)
           bool found = false;
-          for (int64_t k = v0; k < v1 && !found; k++) found = R.valid_idx[k] == p;
-          keep = found;
+          for (int64_t x = v0; x < v1 && !found; x++) found = R.valid_idx[x] == p;
+          k = found;
         }
-        if (keep && finder != EVG_FINDER_NO_DEPS) keep = (R.met[t] & (finder == EVG_FINDER_LEGACY ? 1u : 2u)) != 0;
+        if (k) k = (mt[j] & met_bit) != 0;  // the finder's dependency predicate (NO_DEPS reads 3: always met)
+      }
+      keep[j] = k;
+      m[j] = __ballot_sync(full, k);
+      if (lane == 0) s_cnt[j * 8 + warp] = __popc(m[j]);
+    }
+    __syncthreads();
+    uint32_t total = 0, before[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        if (w == warp) before[j] = total;
+        total += s_cnt[j * 8 + w];
       }
     }
-    const unsigned m = __ballot_sync(full, keep);
-    if (lane == 0) s_warp[warp] = __popc(m);
-    __syncthreads();
-    uint32_t before = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) { const uint32_t x = s_warp[w]; total += x; if (w < warp) before += x; }
-    if (keep) out[base + running + before + __popc(m & ((1u << lane) - 1u))] = int32_t(t - base);
+    for (int j = 0; j < ITEMS; j++)
+      if (keep[j]) out[base + running + before[j] + __popc(m[j] & ((1u << lane) - 1u))] = int32_t(c0 + j * 256 + threadIdx.x - base);
     running += total;
     __syncthreads();
   }
   for (int64_t i = base + running + threadIdx.x; i < end; i += 256) out[i] = -1;  // unused tail of the distro's slots
   if (threadIdx.x == 0) count[d] = running;
+}
+
+// Expected-duration statistics (model/task/expected_duration.go:36-96): the $match, then per key count / sum, then
+// the squared deviations from floor(mean) as an exact 128-bit integer, then one rounding per output.
+struct DDur {
+  int64_t n_rows;
+  int32_t n_keys;
+  const int32_t* key;
+  const int64_t* taken;
+  const int64_t* start;
+  const int64_t* finish;
+  const uint8_t* flags;
+  int64_t w0, w1;
+  unsigned long long* cnt;  // [n_keys]
+  unsigned long long* sum;  // [n_keys] two's complement
+  unsigned long long* sq_lo;
+  unsigned long long* sq_hi;
+};
+__device__ __forceinline__ bool dur_row_matches(const DDur& X, int64_t r) {
+  const uint32_t f = X.flags[r];
+  return (f & EVG_DR_COMPLETED) && !(f & EVG_DR_TIMED_OUT) && X.start[r] > X.w0 && X.finish[r] <= X.w1;
+}
+__global__ void __launch_bounds__(256) k_dur_sum(DDur X, int* err) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= X.n_rows) return;
+  const int32_t k = X.key[r];
+  if (k < 0 || k >= X.n_keys) { atomicOr(err, 1); return; }
+  if (!dur_row_matches(X, r)) return;
+  atomicAdd(X.cnt + k, 1ull);
+  atomicAdd(X.sum + k, (unsigned long long)X.taken[r]);
+}
+__global__ void __launch_bounds__(256) k_dur_dev(DDur X) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= X.n_rows) return;
+  const int32_t k = X.key[r];
+  if (k < 0 || k >= X.n_keys || !dur_row_matches(X, r)) return;
+  const int64_t n = int64_t(X.cnt[k]), s = int64_t(X.sum[k]);
+  int64_t m0 = s / n;
+  if ((s % n) < 0) m0 -= 1;  // floor
+  const int64_t dv = X.taken[r] - m0;
+  const unsigned long long a = dv < 0 ? (unsigned long long)(-dv) : (unsigned long long)dv;
+  const unsigned long long lo = a * a, hi = __umul64hi(a, a);
+  const unsigned long long old = atomicAdd(X.sq_lo + k, lo);
+  const unsigned long long carry = (old + lo < old) ? 1ull : 0ull;
+  if (hi + carry) atomicAdd(X.sq_hi + k, hi + carry);
+}
+__global__ void __launch_bounds__(256) k_dur_final(DDur X, evg_duration_stat* out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= X.n_keys) return;
+  evg_duration_stat st;
+  st.count = int64_t(X.cnt[k]);
+  st.mean_ns = 0.0;
+  st.stddev_ns = 0.0;
+  if (st.count > 0) {
+    const int64_t n = st.count, s = int64_t(X.sum[k]);
+    int64_t m0 = s / n, rem = s % n;
+    if (rem < 0) { m0 -= 1; rem += n; }
+    const double dn = __ll2double_rn(n);
+    st.mean_ns = __ddiv_rn(__ll2double_rn(s), dn);
+    // variance = S2/n - (rem/n)^2 with S2 = sum (x - floor(mean))^2 held exactly in 128 bits
+    const double s2 = __dadd_rn(__dmul_rn(__ull2double_rn(X.sq_hi[k]), 18446744073709551616.0), __ull2double_rn(X.sq_lo[k]));
+    const double fr = __ddiv_rn(__ll2double_rn(rem), dn);
+    double var = __dadd_rn(__ddiv_rn(s2, dn), -__dmul_rn(fr, fr));
+    if (var < 0.0) var = 0.0;
+    st.stddev_ns = __dsqrt_rn(var);
+  }
+  out[k] = st;
 }
 
 // planner.go:449-456 (pass 2): mark every task some in-queue task depends on.
@@ -1731,6 +1820,54 @@ int evg_deps_met_batch(evg_ctx* c, const evg_deps_in* in, uint8_t* met) {
   CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (bad) return fail(EVG_ERR_INVALID, "a dep_ref is out of range");
+  return EVG_OK;
+}
+
+int evg_expected_durations_batch(evg_ctx* c, const evg_duration_rows* in, evg_duration_stat* out) {
+  if (!c || !in) return fail(EVG_ERR_INVALID, "evg_expected_durations_batch: null argument");
+  const int64_t R = in->n_rows;
+  const int32_t K = in->n_keys;
+  if (R < 0 || K < 0) return fail(EVG_ERR_INVALID, "negative sizes");
+  if (K == 0) return R == 0 ? EVG_OK : fail(EVG_ERR_INVALID, "rows without keys");
+  if (!out) return fail(EVG_ERR_INVALID, "null output");
+  if (R > 0 && (!in->key || !in->time_taken_ns || !in->start_ns || !in->finish_ns || !in->flags)) return fail(EVG_ERR_INVALID, "null row column");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  c->launches = 0;
+  c->have_tasks = false;  // shares scratch buffers with the finder entry points
+#define UPX(buf, ptr, count, type)                                                                                 \
+  do {                                                                                                             \
+    CK((buf).ensure(sizeof(type) * size_t((count) > 0 ? (count) : 1)));                                            \
+    if ((count) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(count), cudaMemcpyHostToDevice, s)); \
+  } while (0)
+  UPX(c->b_rn0, in->key, R, int32_t);
+  UPX(c->b_rn1, in->time_taken_ns, R, int64_t);
+  UPX(c->b_rn2, in->start_ns, R, int64_t);
+  UPX(c->b_rn3, in->finish_ns, R, int64_t);
+  UPX(c->b_rn4, in->flags, R, uint8_t);
+#undef UPX
+  CK(c->b_rn5.ensure(sizeof(unsigned long long) * 4 * size_t(K)));
+  CK(c->b_rn6.ensure(sizeof(evg_duration_stat) * size_t(K)));
+  CK(c->b_err.ensure(sizeof(int) * 4));
+  CK(cudaMemsetAsync(c->b_err.p, 0, sizeof(int) * 4, s));
+  CK(cudaMemsetAsync(c->b_rn5.p, 0, sizeof(unsigned long long) * 4 * size_t(K), s));
+  DDur x;
+  x.n_rows = R; x.n_keys = K; x.key = c->b_rn0.as<int32_t>(); x.taken = c->b_rn1.as<int64_t>(); x.start = c->b_rn2.as<int64_t>();
+  x.finish = c->b_rn3.as<int64_t>(); x.flags = c->b_rn4.as<uint8_t>(); x.w0 = in->window_start_ns; x.w1 = in->window_end_ns;
+  x.cnt = c->b_rn5.as<unsigned long long>(); x.sum = x.cnt + K; x.sq_lo = x.sum + K; x.sq_hi = x.sq_lo + K;
+  if (R > 0) {
+    k_dur_sum<<<grid_for(R, 256), 256, 0, s>>>(x, c->b_err.as<int>());
+    k_dur_dev<<<grid_for(R, 256), 256, 0, s>>>(x);
+    c->launches += 2;
+  }
+  k_dur_final<<<grid_for(K, 256), 256, 0, s>>>(x, c->b_rn6.as<evg_duration_stat>());
+  c->launches++;
+  CK(cudaGetLastError());
+  int bad = 0;
+  CK(cudaMemcpyAsync(out, c->b_rn6.p, sizeof(evg_duration_stat) * size_t(K), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (bad) return fail(EVG_ERR_INVALID, "a key is out of range");
   return EVG_OK;
 }
 

@@ -37,6 +37,7 @@ TASK_UNDISPATCHED = "undispatched"
 TASK_SUCCEEDED = "success"
 TASK_FAILED = "failed"
 ALL_STATUSES = "*"  # model/task/task.go:491
+TASK_COMPLETED_STATUSES = (TASK_SUCCEEDED, TASK_FAILED)  # globals.go TaskCompletedStatuses
 # globals.go:264
 DISPATCHER_VERSION_REVISED_WITH_DEPENDENCIES = "revised-with-dependencies"
 # globals.go:267-268
@@ -116,6 +117,10 @@ class Task:
     start_time: int = ZERO_TIME
     distro_id: str = ""
     status: str = TASK_UNDISPATCHED
+    # finished-task history (expected_duration.go:36-55)
+    finish_time: int = ZERO_TIME
+    time_taken: int = 0
+    timed_out: bool = False  # Details.TimedOut
     # what the task finders' base query reads (schedulableHostTasksQuery, model/task/db.go:671-689)
     activated: bool = True
     execution_platform: str = ""           # "" (field absent) or "host" pass ByExecutionPlatform(host), db.go:647-663

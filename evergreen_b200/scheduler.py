@@ -198,6 +198,13 @@ class Engine:
         del keep
         return runnable, count
 
+    def expected_durations_batch(self, rows: "S.DurationRows") -> np.ndarray:
+        """{$avg, $stdDevPop} of TimeTaken per key (evg_expected_durations_batch) -> DURATION_STAT_DTYPE[n_keys]."""
+        out = self._out("duration_stats", rows.n_keys, L.DURATION_STAT_DTYPE)
+        st = rows.struct()
+        L.check(self.lib.evg_expected_durations_batch(self.ctx, C.byref(st), L.ptr(out) if rows.n_keys else None))
+        return out
+
     def alloc_batch(self, hosts: S.HostSoA, qinfo: np.ndarray, ginfo: np.ndarray, group_off: np.ndarray, now: int):
         D = int(qinfo.shape[0])
         ao = self._alloc_output(D)
@@ -346,6 +353,17 @@ def LegacyFindRunnableTasks(d: M.Distro, candidates: List[M.Task], project_refs:
 def AlternateTaskFinder(d: M.Distro, candidates: List[M.Task], project_refs: Sequence[M.ProjectRef], **kw) -> List[M.Task]:
     """scheduler/task_finder.go:108-197 for one distro."""
     return find_runnable_tasks([(d, candidates)], project_refs, finder="alternate", **kw)[0]
+
+
+def get_expected_durations_for_window(tasks: Sequence[M.Task], window_start: int, window_end: int, *,
+                                      engine: Optional[Engine] = None) -> Dict[tuple, Tuple[float, float]]:
+    """getExpectedDurationsForWindow (model/task/expected_duration.go:36-96) for every (project, build variant) at
+    once: {(project, build_variant, display_name): (exp_dur ns, std_dev ns)} over the finished tasks given; keys
+    whose rows all fail the $match are absent, as they are from the aggregation's result."""
+    eng = engine or default_engine()
+    rows, keys = S.marshal_durations(tasks, window_start, window_end)
+    stats = eng.expected_durations_batch(rows)
+    return {k: (float(stats["mean_ns"][i]), float(stats["stddev_ns"][i])) for i, k in enumerate(keys) if stats["count"][i] > 0}
 
 
 def allocate_distros(datas: Sequence[M.HostAllocatorData], now: int, *, engine: Optional[Engine] = None):

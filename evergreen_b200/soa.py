@@ -536,3 +536,45 @@ def marshal_runnable(batch: Sequence[tuple], project_refs: Sequence[M.ProjectRef
     return RunnableTable(np.array(task_off, np.int64), np.array(sched, np.uint8), np.array(proj, np.int32),
                          np.array([project_bits(p) for p in project_refs], np.uint8), np.array(valid_off, np.int64),
                          np.array(valid_idx, np.int32), np.array(fnd, np.uint8), deps)
+
+
+@dataclass
+class DurationRows:
+    """evg_duration_rows: finished tasks, the interned group-by key of each, and the aggregation window."""
+    key: np.ndarray
+    time_taken_ns: np.ndarray
+    start_ns: np.ndarray
+    finish_ns: np.ndarray
+    flags: np.ndarray
+    n_keys: int
+    window_start_ns: int
+    window_end_ns: int
+
+    @property
+    def n_rows(self) -> int:
+        return int(self.key.shape[0])
+
+    def struct(self) -> L.DurationRowsStruct:
+        s = L.DurationRowsStruct()
+        s.n_rows, s.n_keys, s._reserved = self.n_rows, int(self.n_keys), 0
+        for f in ("key", "time_taken_ns", "start_ns", "finish_ns", "flags"):
+            setattr(s, f, L.ptr(getattr(self, f)) if s.n_rows else None)
+        s.window_start_ns, s.window_end_ns = int(self.window_start_ns), int(self.window_end_ns)
+        return s
+
+
+def marshal_durations(tasks: Sequence[M.Task], window_start: int, window_end: int):
+    """Finished tasks -> (DurationRows, keys): keys[i] = (project, build_variant, display_name) of key row i, in
+    first-appearance order.  The $match of expected_duration.go:37-55 is evaluated on the device from the flags
+    and the two timestamps; here a row only says what the task document says."""
+    index: Dict[tuple, int] = {}
+    key, taken, start, finish, flags = [], [], [], [], []
+    for t in tasks:
+        k = (t.project, t.build_variant, t.display_name)
+        key.append(index.setdefault(k, len(index)))
+        taken.append(t.time_taken); start.append(t.start_time); finish.append(t.finish_time)
+        flags.append((L.EVG_DR_COMPLETED if t.status in M.TASK_COMPLETED_STATUSES else 0) |
+                     (L.EVG_DR_TIMED_OUT if t.timed_out else 0))
+    rows = DurationRows(np.array(key, np.int32), np.array(taken, np.int64), np.array(start, np.int64),
+                        np.array(finish, np.int64), np.array(flags, np.uint8), len(index), window_start, window_end)
+    return rows, list(index)

@@ -377,6 +377,40 @@ typedef struct {
  * distro's slots are -1.  Host pointers. */
 int evg_find_runnable_batch(evg_ctx* ctx, const evg_runnable_in* in, int32_t* runnable, int64_t* count);
 
+/* ---- expected-duration statistics ----------------------- */
+
+/* evg_duration_rows.flags */
+#define EVG_DR_COMPLETED 0x1u  /* Status in evergreen.TaskCompletedStatuses (expected_duration.go:41-43) */
+#define EVG_DR_TIMED_OUT 0x2u  /* Details.TimedOut == true (excluded, :44-46) */
+
+/* Finished tasks (one row each) of any number of (project, build variant) windows at once; `key` interns the
+ * group-by key -- (project, build variant, display name) -- so one call replaces one aggregation per pair. */
+typedef struct {
+  int64_t n_rows;
+  int32_t n_keys;
+  int32_t _reserved;
+  const int32_t* key;            /* n_rows: 0 .. n_keys-1 */
+  const int64_t* time_taken_ns;  /* n_rows: Task.TimeTaken */
+  const int64_t* start_ns;       /* n_rows: Task.StartTime (UnixNano) */
+  const int64_t* finish_ns;      /* n_rows: Task.FinishTime */
+  const uint8_t* flags;          /* n_rows: EVG_DR_* */
+  int64_t window_start_ns;       /* $match: StartTime > window_start && FinishTime <= window_end (:47-52) */
+  int64_t window_end_ns;
+} evg_duration_rows;
+
+/* One group of the $group stage (expected_duration.go:66-76): {$avg, $stdDevPop} of TimeTaken.  count == 0 means the
+ * aggregation returns no document for the key.  mean_ns = double(sum) / double(count); stddev_ns = sqrt(variance)
+ * with the variance accumulated EXACTLY in integers around floor(mean) and rounded once at the end (MongoDB's
+ * streaming Welford update differs from it in the last few ulps; the reference's own test allows 0.01 minutes). */
+typedef struct {
+  int64_t count;
+  double mean_ns;
+  double stddev_ns;
+} evg_duration_stat;
+
+/* getExpectedDurationsForWindow (model/task/expected_duration.go:36-96) for every key at once.  Host pointers. */
+int evg_expected_durations_batch(evg_ctx* ctx, const evg_duration_rows* in, evg_duration_stat* out);
+
 /* ---- single-distro wrappers: the per-job drop-in ------------------------- */
 
 /* One distro: PrioritizeTasks for `d` (scheduler/scheduler.go:27). */

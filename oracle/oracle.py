@@ -312,6 +312,36 @@ def find_runnable(d: M.Distro, candidates: Sequence[M.Task], project_refs: Seque
     return out
 
 
+def expected_durations_for_window(tasks: Sequence[M.Task], window_start: int, window_end: int):
+    """Restatement of getExpectedDurationsForWindow (model/task/expected_duration.go:36-96) over finished-task
+    documents: $match (completed status, not timed out, StartTime > start, FinishTime <= end), $group by display
+    name within (project, build variant) with $avg and $stdDevPop of TimeTaken.  Exact rational arithmetic, one
+    rounding per output -> {(project, bv, name): (count, mean, stddev)}; MongoDB's streaming doubles agree to ~1e-12."""
+    import math
+    from fractions import Fraction
+    groups: Dict[tuple, List[int]] = {}
+    for t in tasks:
+        if t.status not in M.TASK_COMPLETED_STATUSES or t.timed_out:
+            continue
+        if not (t.start_time > window_start and t.finish_time <= window_end):
+            continue
+        groups.setdefault((t.project, t.build_variant, t.display_name), []).append(t.time_taken)
+    out = {}
+    for k, xs in groups.items():
+        n, s = len(xs), sum(xs)
+        m0 = s // n  # floor
+        rem = s - n * m0
+        s2 = sum((x - m0) ** 2 for x in xs)
+        # the canonical roundings of include/evg_sched.h: double(s)/double(n); S2 as hi*2^64+lo, /n, minus (rem/n)^2
+        mean = float(s) / float(n)
+        s2f = float(s2 >> 64) * 18446744073709551616.0 + float(s2 & ((1 << 64) - 1))
+        fr = float(rem) / float(n)
+        var = max(s2f / float(n) - fr * fr, 0.0)
+        exact_std = math.sqrt(Fraction(n * sum(x * x for x in xs) - s * s, n * n))  # reference value, for the tolerance test
+        out[k] = (n, mean, math.sqrt(var), exact_std)
+    return out
+
+
 def hosts_struct(hosts: Sequence[M.Host], running: Dict[str, M.RunningTaskStats]):
     k = _Keep()
     h = Hosts()

@@ -490,6 +490,66 @@ def test_task_finder_at_scale(engine):
     assert engine.last_launch_count() == 2  # k_deps_met + k_runnable
 
 
+# ---------------------------------------------------------------- expected-duration statistics
+def test_expected_duration_kat(engine):
+    """model/task/expected_duration_test.go:14-69 through evg_expected_durations_batch."""
+    for case in G.load("expected_duration.json")["cases"]:
+        tasks = [G.make_task(t, 0, 0) for t in case["tasks"]]
+        got = S.get_expected_durations_for_window(tasks, case["window_start"], case["window_end"], engine=engine)
+        e = case["expect"]
+        mean, std = got[tuple(e["key"])]
+        assert len(got) == 1 and mean == e["mean_ns"] and abs(std - e["stddev_ns"]) <= e["stddev_delta_ns"]
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_expected_duration_parity(engine, seed):
+    """Random finished-task history: bit-equal to the oracle's canonical roundings, and within 1e-12 (relative) of the
+    exactly rounded population standard deviation."""
+    import random
+    rng = random.Random(90 + seed)
+    now = 1_800_000_000 * 10 ** 9
+    tasks = []
+    for i in range(4000):
+        taken = rng.choice([rng.randrange(10 ** 9, 4 * 3600 * 10 ** 9), rng.randrange(1, 10 ** 6), 7 * 10 ** 9])
+        tasks.append(M.Task(id=f"t{i}", project=f"p{rng.randrange(3)}", build_variant=f"bv{rng.randrange(4)}",
+                            display_name=f"n{rng.randrange(25)}", status=rng.choice(["success", "failed", "failed", "undispatched", "started"]),
+                            timed_out=rng.random() < 0.05, time_taken=taken,
+                            start_time=now - rng.randrange(0, 9 * 24 * 3600 * 10 ** 9), finish_time=now - rng.randrange(-10 ** 9, 10 ** 12)))
+    w0, w1 = now - 7 * 24 * 3600 * 10 ** 9, now
+    got = S.get_expected_durations_for_window(tasks, w0, w1, engine=engine)
+    want = O.expected_durations_for_window(tasks, w0, w1)
+    assert set(got) == set(want)
+    for k, (n, mean, std, exact) in want.items():
+        assert got[k] == (mean, std), k
+        assert abs(std - exact) <= 1e-12 * max(exact, 1.0) + 1e-3
+
+
+def test_expected_duration_at_scale(engine):
+    """8e6 rows over 200k keys against numpy (float64 two-pass): means equal, standard deviations within 1e-9 relative."""
+    rng = np.random.default_rng(3)
+    R, K = 8_000_000, 200_000
+    key = rng.integers(0, K, R).astype(np.int32)
+    taken = rng.integers(10 ** 9, 3 * 3600 * 10 ** 9, R)
+    flags = (rng.random(R) < 0.9).astype(np.uint8) | ((rng.random(R) < 0.05).astype(np.uint8) << 1)
+    now = 10 ** 18
+    start = now - rng.integers(0, 8 * 24 * 3600 * 10 ** 9, R)
+    finish = start + taken
+    rows = soa.DurationRows(key, taken, start, finish, flags, K, now - 7 * 24 * 3600 * 10 ** 9, now)
+    st = engine.expected_durations_batch(rows).copy()
+    ok = ((flags & 1) != 0) & ((flags & 2) == 0) & (start > rows.window_start_ns) & (finish <= rows.window_end_ns)
+    cnt = np.bincount(key[ok], minlength=K)
+    ssum = np.bincount(key[ok], weights=taken[ok].astype(np.float64), minlength=K)
+    assert np.array_equal(st["count"], cnt)
+    have = cnt > 0
+    mean = ssum[have] / cnt[have]
+    assert np.allclose(st["mean_ns"][have], mean, rtol=1e-12, atol=0)
+    dev = taken[ok].astype(np.float64) - (ssum / np.maximum(cnt, 1))[key[ok]]
+    var = np.bincount(key[ok], weights=dev * dev, minlength=K)[have] / cnt[have]
+    assert np.allclose(st["stddev_ns"][have], np.sqrt(var), rtol=1e-9, atol=1e-3)
+    assert not st["mean_ns"][~have].any() and not st["stddev_ns"][~have].any()
+    assert engine.last_launch_count() == 3
+
+
 def test_bad_arguments_are_errors(engine):
     w = synth.make(np.array([10]), 1)
     bad = copy.deepcopy(w)

@@ -224,3 +224,33 @@ def test_task_finders_differ_only_by_the_short_circuit():
     assert [x.id for x in O.find_runnable(M.Distro(), [t, dep], refs, finder="alternate")] == []
     d = M.Distro(dispatcher_settings=M.DispatcherSettings(version="revised-with-dependencies"))
     assert [x.id for x in O.find_runnable(d, [t, dep], refs, finder="alternate")] == ["t"]
+
+
+# ---------------------------------------------------------------- expected-duration statistics
+DURATION = G.load("expected_duration.json")
+
+
+def duration_case(case):
+    return [G.make_task(t, 0, 0) for t in case["tasks"]], case["window_start"], case["window_end"]
+
+
+@pytest.mark.parametrize("case", DURATION["cases"], ids=lambda c: c["name"])
+def test_expected_duration_kat(case):
+    tasks, w0, w1 = duration_case(case)
+    got = O.expected_durations_for_window(tasks, w0, w1)
+    e = case["expect"]
+    n, mean, std, _ = got[tuple(e["key"])]
+    assert len(got) == 1 and n == len(tasks)
+    assert mean == e["mean_ns"]                                   # EqualValues: exact
+    assert abs(std - e["stddev_ns"]) <= e["stddev_delta_ns"]      # InDelta(…, 0.01 minute)
+
+
+def test_expected_duration_match_stage():
+    """The $match of expected_duration.go:37-55: completed, not timed out, StartTime > start (strict), FinishTime <= end."""
+    MIN, now = 60 * 10 ** 9, 10 ** 18
+    base = dict(build_variant="bv", project="p", display_name="n", status="success", finish_time=now, start_time=now - MIN, time_taken=MIN)
+    rows = [M.Task(**base), M.Task(**dict(base, status="undispatched")), M.Task(**dict(base, timed_out=True)),
+            M.Task(**dict(base, start_time=now - 60 * MIN)), M.Task(**dict(base, finish_time=now + 1)),
+            M.Task(**dict(base, status="failed", time_taken=3 * MIN))]
+    got = O.expected_durations_for_window(rows, now - 60 * MIN, now)
+    assert got[("p", "bv", "n")][:3] == (2, 2.0 * MIN, 1.0 * MIN)
