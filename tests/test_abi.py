@@ -46,6 +46,8 @@ int main(void) {
          offsetof(evg_queue_info, ungrouped), offsetof(evg_alloc_cfg, provider), offsetof(evg_alloc_result, deficit_ns));
   printf("%zu %zu %zu %zu %zu %zu\n", sizeof(evg_deps_in), offsetof(evg_deps_in, n_ext), sizeof(evg_runnable_in),
          offsetof(evg_runnable_in, task_off), offsetof(evg_runnable_in, deps), sizeof(evg_alloc_out));
+  printf("%zu %zu %zu %zu\n", sizeof(evg_duration_rows), offsetof(evg_duration_rows, window_start_ns), sizeof(evg_duration_stat),
+         offsetof(evg_duration_stat, stddev_ns));
   return 0;
 }'''
     c = tmp_path / "t.c"
@@ -64,6 +66,9 @@ int main(void) {
     more = [int(x) for x in out[2].split()]
     assert more == [ctypes.sizeof(L.DepsInStruct), L.DepsInStruct.n_ext.offset, ctypes.sizeof(L.RunnableInStruct),
                     L.RunnableInStruct.task_off.offset, L.RunnableInStruct.deps.offset, ctypes.sizeof(L.AllocOutStruct)]
+    dur = [int(x) for x in out[3].split()]
+    assert dur == [ctypes.sizeof(L.DurationRowsStruct), L.DurationRowsStruct.window_start_ns.offset,
+                   L.DURATION_STAT_DTYPE.itemsize, L.DURATION_STAT_DTYPE.fields["stddev_ns"][1]]
 
 
 def test_no_cpu_fallback_without_a_device():
