@@ -82,7 +82,11 @@ constexpr int kTile = 2048;        // sort tile: 64 warp-chunks of 32
 constexpr int kChunks = kTile / 32;
 constexpr int kMaxPass = 16;       // 8 tie bytes + 8 value bytes
 // on-chip planner classes <THREADS, ITEMS>: capacity = THREADS*ITEMS tasks per distro
-constexpr int kCapA = 128 * 8, kCapB = 256 * 16, kCapC = 1024 * 12;
+#ifndef EVG_C_THREADS  // shape of the largest on-chip class (threads x tasks per thread = 12288 tasks in 218 KB)
+#define EVG_C_THREADS 1024
+#define EVG_C_ITEMS 12
+#endif
+constexpr int kCapA = 128 * 8, kCapB = 256 * 16, kCapC = EVG_C_THREADS * EVG_C_ITEMS;
 constexpr int64_t kWideAllocGroups = 1024;  // k_alloc<128> (a block per distro) once some distro has more task groups
 constexpr int kCapW = 32;  // k_plan_warp: one warp per distro
 constexpr uint32_t kInactive = 0xFFFFFFFFu;  // next[]: pair not linked / head[]: empty list
@@ -1421,7 +1425,7 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
   int rc;
   const int slot = int(c->runs % evg_ctx::kRing);
   if (c->timed) CK(cudaEventRecord(c->ring0[slot], s));
-  if ((rc = launch_smem<1024, 12, 1>(c, dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now, bd ? 1 : 0)) != EVG_OK) return rc;
+  if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now, bd ? 1 : 0)) != EVG_OK) return rc;
   if (c->timed) { CK(cudaEventRecord(c->ring1[slot], s)); c->runs++; }
   if (!general) c->sort_slot = slot;  // no general-path sort in this tick: the "dominant kernel" split is the ring pair
   if ((rc = launch_smem<256, 16, 3>(c, dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now, bd ? 1 : 0)) != EVG_OK) return rc;
@@ -1678,7 +1682,7 @@ static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg
     k_validate<<<grid_for(n, 256), 256, 0, s>>>(dtk, dd, w, t0, t0 + n);
     int32_t first, cnt;
     cnt = sub(c->h_listC, d0, d1, &first);
-    if ((rc = launch_smem<1024, 12, 1>(c, dtk, dd, w, c->b_listC.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, dtk, dd, w, c->b_listC.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
     cnt = sub(c->h_listB, d0, d1, &first);
     if ((rc = launch_smem<256, 16, 3>(c, dtk, dd, w, c->b_listB.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
     cnt = sub(c->h_listA, d0, d1, &first);
