@@ -2,6 +2,7 @@
 // include/evg_sched.h.  See DESIGN.md for the data layout and the kernel list.
 //
 // Distros are routed by size on the host:
+//   <= 32 tasks      k_plan_warp (evg_plan_warp.cuh): one warp plans the distro
 //   <= 12288 tasks   k_plan_smem<THREADS,ITEMS> (evg_plan_smem.cuh): one CTA plans the distro on-chip
 //   larger           the general path below, any size up to 2^21-1 tasks:
 //     k_mark_dependents   dependency edges -> "has in-queue dependents" byte     (planner.go:449-456)
@@ -14,7 +15,12 @@
 //     k_finalize_info     DistroQueueInfo / TaskGroupInfo scalars (scheduler.go:144-158)
 // Both:
 //   k_breakdown           the 13-field SortingValueBreakdown per ranked task (EVG_OPT_BREAKDOWN)
-//   k_alloc               utilization host allocator, one warp per distro (utilization_based_host_allocator.go:26-409)
+//   k_alloc<TPD>          utilization host allocator, a warp or a block per distro (utilization_based_host_allocator.go:26-409)
+//   k_validate            range check of the distro-local ids the planners index with
+// The rows either side of the path:
+//   k_deps_met            Task.DependenciesMet / AllDependenciesSatisfied (model/task/task.go:632-671,795-821)
+//   k_runnable            the task finders' filter + stable compaction (scheduler/task_finder.go:40-317)
+//   k_dur_sum/dev/final   expected-duration statistics (model/task/expected_duration.go:36-96)
 // No CPU fallback exists in this file: without a device every entry point fails.
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -719,8 +725,6 @@ __global__ void __launch_bounds__(256) k_best(DTasks T, DDistros D, DWork W) {
   }
   note_key_bits(W.bits, valid ? d : 0, valid, uniform, key_s, key_v);
 }
-
-// bits[]: or-words start at 0, and-words at all ones
 
 // bits[]: or-words start at 0, and-words at all ones
 __global__ void k_init_bits(unsigned long long* bits, int n) {
