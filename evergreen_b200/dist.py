@@ -86,6 +86,61 @@ class ResultGather:
         return rows.index_select(0, self.index).reshape(-1)
 
 
+class PipelinedGather:
+    """ResultGather with `depth` buffer sets and the collective on its own CUDA stream: tick k's all-gather (and
+    the reorder to global distro order) runs while tick k+1's planner already occupies the SMs -- the gather is
+    16 B per distro, all launch latency, and nothing in tick k+1 depends on it.
+
+    Per tick k:  before_tick(k, main)  -> bind send(k) as the allocator's result buffer -> run the tick on `main`
+                 -> launch(k, main).   drain(main) makes `main` wait for every gather still in flight
+    (call it before the closing timing event).  On CPU tensors (the gloo tests) everything is synchronous."""
+
+    def __init__(self, shards: Shards, device, depth: int = 2):
+        import torch
+        self.torch = torch
+        self.depth = depth
+        self.slots = [ResultGather(shards, device) for _ in range(depth)]
+        self.cuda = torch.device(device).type == "cuda"
+        self.out = [None] * depth
+        self.done = [None] * depth
+        if self.cuda:
+            self.comm = torch.cuda.Stream(device)
+            self.ready = [torch.cuda.Event() for _ in range(depth)]
+
+    def send(self, k: int):
+        return self.slots[k % self.depth].send
+
+    def before_tick(self, k: int, main) -> None:
+        """Tick k overwrites send(k): the gather that last read that buffer (tick k - depth) must be done."""
+        d = self.done[k % self.depth]
+        if self.cuda and d is not None:
+            main.wait_event(d)
+
+    def launch(self, k: int, main) -> None:
+        i = k % self.depth
+        if not self.cuda:
+            self.out[i] = self.slots[i].gather()
+            return
+        torch = self.torch
+        self.ready[i].record(main)
+        self.comm.wait_event(self.ready[i])
+        with torch.cuda.stream(self.comm):
+            self.out[i] = self.slots[i].gather()
+            done = torch.cuda.Event()
+            done.record(self.comm)
+        self.done[i] = done
+
+    def drain(self, main) -> None:
+        if self.cuda:
+            for d in self.done:
+                if d is not None:
+                    main.wait_event(d)
+
+    def result(self, k: int):
+        """Gathered rows of tick k, global distro order (valid once the stream that waits on drain() has caught up)."""
+        return self.out[k % self.depth]
+
+
 def all_gather_results(local, shards: Shards, rank: int):
     """One-shot form of ResultGather (allocates; used by the CPU tests)."""
     g = ResultGather(shards, local.device)

@@ -34,6 +34,16 @@ def _worker(rank, world, port, sizes, out_dir):
     send = torch.from_numpy(local.view(np.uint8).copy())
     got = edist.decode_results(edist.all_gather_results(send, shards, rank))
     np.save(os.path.join(out_dir, f"r{rank}.npy"), got)
+    # the double-buffered form used by bench.py: three ticks through two buffer sets
+    pg = edist.PipelinedGather(shards, torch.device("cpu"))
+    for k in range(3):
+        pg.before_tick(k, None)
+        buf = local.copy()
+        buf["new_hosts"][:len(mine)] += k
+        pg.send(k).copy_(torch.from_numpy(buf.view(np.uint8).copy()))
+        pg.launch(k, None)
+        assert np.array_equal(edist.decode_results(pg.result(k))["new_hosts"], np.arange(len(sizes)) * 3 + 1 + k)
+    pg.drain(None)
     dist.barrier()
     dist.destroy_process_group()
 
