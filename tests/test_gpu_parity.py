@@ -577,6 +577,72 @@ def test_resident_rerun_is_idempotent(engine):
     assert engine.last_launch_count() > 0
 
 
+def test_all_routes_in_one_tick(engine):
+    """One tick holding every planner route at once -- warp, the three on-chip classes at their boundaries, the
+    general path -- with task groups, GroupVersions, dependencies and hosts: each distro against the oracle."""
+    sizes = np.array([3, 31, 32, 33, 0, 900, 1024, 1025, 4000, 4096, 4097, 12288, 12289, 20000, 1, 7])
+    w = synth.make(sizes, 91, tg_frac=0.12, unmet_dep_frac=0.03, met_dep_frac=0.02, group_versions_frac=0.25,
+                   custom_factor_frac=0.4, zipf_priority=True, includes_dependencies=True, n_hosts=400,
+                   providers=(0.6, 0.2, 0.2))
+    po, ao = run(engine, w)
+    parity.check_properties(w, po, ao)
+    parity.check_against_oracle(w, po, ao)
+    po, _ = run(engine, w, breakdown=True)
+    parity.check_against_oracle(w, po, None)
+
+
+def test_resident_reruns_follow_the_clock(engine):
+    """Upload once, run at three different clocks (evg_run_resident): every run equals the oracle at that clock."""
+    w = synth.make(np.array([5000, 40, 13000, 700]), 92, tg_frac=0.1, met_dep_frac=0.02, n_hosts=60)
+    engine.upload(w.tasks, w.distros, w.hosts)
+    for now in (w.now, w.now + 3 * 3600 * 10 ** 9, w.now + 9 * 24 * 3600 * 10 ** 9):
+        engine.run(now)
+        po, ao = engine.download()
+        w2 = copy.copy(w)
+        w2.now = now
+        parity.check_against_oracle(w2, po, ao)
+
+
+def test_bound_result_buffer_receives_the_rows(engine):
+    """evg_bind_result_buffer: the allocator writes its rows into a caller-owned device buffer (the all-gather
+    send buffer) -- same bytes as the context-owned one."""
+    import torch
+    w = synth.config(3, 0.01)
+    po, ao = run(engine, w)
+    want = ao.result.copy()
+    D = w.distros.n_distros
+    buf = torch.zeros((D + 5) * 16, dtype=torch.uint8, device="cuda:0")
+    try:
+        engine.bind_result_buffer(buf.data_ptr(), D + 5)
+        po2, ao2 = run(engine, w)
+        got = np.frombuffer(buf.cpu().numpy().tobytes(), dtype=L.ALLOC_RESULT_DTYPE)
+        assert np.array_equal(got[:D], want) and not got[D:].view(np.uint8).any()
+        assert np.array_equal(ao2.result, want)  # the host copy comes from the bound buffer too
+        with pytest.raises(L.EvgError):
+            engine.bind_result_buffer(buf.data_ptr(), D - 1)
+            run(engine, w)
+    finally:
+        engine.bind_result_buffer(0, 0)
+    po3, ao3 = run(engine, w)
+    assert np.array_equal(ao3.result, want)
+
+
+def test_alloc_only_call_matches_the_fused_tick(engine):
+    """evg_alloc_batch on the queue infos a planner call returned (the reference's two-job topology) gives the same
+    decisions as the fused tick, including a distro with thousands of task groups (block-per-distro allocator)."""
+    w = synth.make(np.array([60000, 300, 5, 9000]), 93, tg_frac=0.15, n_hosts=500, providers=(0.7, 0.2, 0.1))
+    po, ao = run(engine, w)
+    want, want_status = ao.result.copy(), ao.status.copy()
+    qinfo, ginfo = po.info.copy(), po.group_info.copy()
+    ginfo["count_free"] = 0
+    ginfo["count_required"] = 0
+    assert int(np.diff(w.distros.group_off).max()) > 1024
+    ao2, g2 = engine.alloc_batch(w.hosts, qinfo, ginfo, w.distros.group_off, w.now)
+    assert np.array_equal(ao2.result, want) and np.array_equal(ao2.status, want_status)
+    assert np.array_equal(g2["count_required"], po.group_info["count_required"])
+    assert np.array_equal(g2["count_free"], po.group_info["count_free"])
+
+
 def test_pipelined_one_shot_equals_resident(engine):
     """Ticks of >= 2^21 tasks take the chunked H2D / kernels / D2H pipeline inside evg_plan_and_alloc_batch;
     its results must equal the upload -> run -> download path bit for bit."""
