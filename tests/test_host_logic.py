@@ -180,3 +180,61 @@ def test_marshal_runnable_bits():
     d2 = M.Distro(id="e", dispatcher_settings=M.DispatcherSettings(M.DISPATCHER_VERSION_REVISED_WITH_DEPENDENCIES))
     t2 = soa.marshal_runnable([(d2, tasks)], refs, "legacy")
     assert t2.finder.tolist() == [L.EVG_FINDER_NO_DEPS] and t2.deps is None
+
+
+def test_lpt_partition_properties():
+    """Whole distros, every distro exactly once, deterministic, and never worse than the classic LPT bound
+    (max load <= mean load + heaviest distro)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.integers(0, 2_000_000), min_size=0, max_size=300), st.integers(1, 8))
+    def prop(weights, world):
+        sh = edist.lpt_partition(weights, world)
+        w = np.asarray(weights, dtype=np.int64)
+        assert len(sh.members) == world
+        seen = np.concatenate(sh.members) if len(weights) else np.zeros(0, dtype=np.int64)
+        assert sorted(seen.tolist()) == list(range(len(weights)))
+        for r, m in enumerate(sh.members):
+            assert (sh.owner[m] == r).all() and (sh.slot[m] == np.arange(len(m))).all()
+            assert int(w[m].sum()) == int(sh.load[r])
+        if len(weights):
+            assert int(sh.load.max()) <= int(np.ceil(w.sum() / world)) + int(w.max())
+        again = edist.lpt_partition(weights, world)
+        assert np.array_equal(again.owner, sh.owner) and np.array_equal(again.slot, sh.slot)
+
+    prop()
+
+
+def test_queue_info_rows_round_trip():
+    """soa.queue_info_rows (DistroQueueInfo -> the 152 B / 72 B rows of the ABI) keeps every scalar and the slot
+    order of the named task groups; the "" group becomes the embedded `ungrouped` row."""
+    rng = random.Random(5)
+    infos = []
+    for d in range(6):
+        groups = [M.TaskGroupInfo(name=n, count=rng.randrange(50), max_hosts=rng.randrange(4), expected_duration=rng.randrange(10 ** 12),
+                                  count_duration_over_threshold=rng.randrange(5), count_wait_over_threshold=rng.randrange(5),
+                                  count_dep_filled_merge_queue_tasks=rng.randrange(3), duration_over_threshold=rng.randrange(10 ** 11))
+                  for n in rng.sample(["", "tg_a", "tg_b", "tg_c", "tg_d"], rng.randrange(0, 5))]
+        infos.append(M.DistroQueueInfo(length=rng.randrange(1000), length_with_dependencies_met=rng.randrange(900),
+                                       expected_duration=rng.randrange(10 ** 13), max_duration_threshold=30 * 60 * 10 ** 9,
+                                       count_duration_over_threshold=rng.randrange(9), duration_over_threshold=rng.randrange(10 ** 12),
+                                       count_wait_over_threshold=rng.randrange(9), count_dep_filled_merge_queue_tasks=rng.randrange(4),
+                                       task_group_infos=groups))
+    qrows, grows, goff, names = S.queue_info_rows(infos)
+    assert qrows.shape[0] == 6 and goff.tolist()[0] == 0 and int(goff[-1]) == grows.shape[0]
+    for d, qi in enumerate(infos):
+        named = [g for g in qi.task_group_infos if g.name != ""]
+        assert names[d] == [g.name for g in named]
+        assert int(qrows[d]["length"]) == qi.length and int(qrows[d]["expected_duration"]) == qi.expected_duration
+        assert int(qrows[d]["length_with_dependencies_met"]) == qi.length_with_dependencies_met
+        unnamed = [g for g in qi.task_group_infos if g.name == ""]
+        assert int(qrows[d]["has_ungrouped"]) == len(unnamed)
+        if unnamed:
+            assert int(qrows[d]["ungrouped"]["count"]) == unnamed[0].count
+            assert int(qrows[d]["ungrouped"]["expected_duration"]) == unnamed[0].expected_duration
+        for k, g in enumerate(named):
+            row = grows[int(goff[d]) + k]
+            for f in ("count", "max_hosts", "expected_duration", "count_duration_over_threshold", "count_wait_over_threshold",
+                      "count_dep_filled_merge_queue_tasks", "duration_over_threshold"):
+                assert int(row[f]) == getattr(g, f), (d, k, f)
