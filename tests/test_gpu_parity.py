@@ -344,6 +344,19 @@ def test_dependency_filter_parity(engine, seed):
         assert g == O.deps_met(tasks, NOW, db_all).tolist()
 
 
+@pytest.mark.parametrize("case", G.load("dependencies_met.json")["cases"], ids=lambda c: c["name"])
+def test_dependencies_met_cases(engine, case):
+    """TestDependenciesMet (model/task/task_test.go:249-434) through evg_deps_met_batch, and its
+    AllDependenciesSatisfied assertions through the alternate finder of evg_find_runnable_batch."""
+    t, db = G.deps_case(case)
+    if "met" in case:
+        assert S.dependencies_met([(M.Distro(id="d"), [t])], engine=engine, dependency_db=db) == [[case["met"]]]
+    if "all_satisfied" in case:
+        t.project = "p"
+        got = S.AlternateTaskFinder(M.Distro(id="d"), [t], [M.ProjectRef(id="p", enabled=True)], dependency_db=db, engine=engine)
+        assert [x.id for x in got] == (["t1"] if case["all_satisfied"] else [])
+
+
 def test_dependency_filter_at_scale(engine):
     """1e6 tasks with ~1.5e6 dependencies: device result vs a numpy restatement of the same table."""
     rng = np.random.default_rng(5)

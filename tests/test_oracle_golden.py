@@ -254,3 +254,26 @@ def test_expected_duration_match_stage():
             M.Task(**dict(base, status="failed", time_taken=3 * MIN))]
     got = O.expected_durations_for_window(rows, now - 60 * MIN, now)
     assert got[("p", "bv", "n")][:3] == (2, 2.0 * MIN, 1.0 * MIN)
+
+
+# ---------------------------------------------------------------- Task.DependenciesMet (model/task/task_test.go)
+DEPS = G.load("dependencies_met.json")
+
+
+@pytest.mark.parametrize("case", DEPS["cases"], ids=lambda c: c["name"])
+def test_dependencies_met_cases(case):
+    """TestDependenciesMet: the C++ oracle (evo_deps_met), the finder restatement's walk and the host mirror."""
+    from evergreen_b200 import soa
+    t, db = G.deps_case(case)
+    if "met" in case:
+        assert bool(O.deps_met([t], 0, db)[0]) == case["met"]
+        assert O._deps_walk(t, dict(db), shortcut=True) == case["met"]
+        assert soa.dependencies_met(t, {t.id: t}, db) == case["met"]
+    if "all_satisfied" in case:
+        assert O._deps_walk(t, dict(db), shortcut=False) == case["all_satisfied"]
+
+
+@pytest.mark.parametrize("case", DEPS["blocked"], ids=lambda c: c["name"])
+def test_blocked_cases(case):
+    t = M.Task(id="t1", depends_on=[M.Dependency(task_id="", unattainable=u) for u in case["unattainable"]])
+    assert t.blocked() == case["expect"]
