@@ -130,6 +130,37 @@ def bind_to_gpu_node(torch, local_rank: int):
         return None
 
 
+def usable_cores():
+    """Host cores this process may actually burn: the affinity mask capped by the cgroup CPU quota (the GPU boxes
+    show 128 logical CPUs under a 16-CPU quota; 128 runnable threads there only add throttling)."""
+    import math
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]  # cgroup v2
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())  # cgroup v1
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    if quota:
+        n = max(1, min(n, int(math.ceil(quota))))
+    return n, (os.cpu_count() or n), quota
+
+
+def cores_note():
+    n, logical, quota = usable_cores()
+    return f"{n} threads = usable host cores ({logical} logical CPUs" + (f", cgroup CPU quota {quota:g}" if quota else "") + ")"
+
+
 def cpu_baseline(w, n_distros: int, threads: int):
     """Time the oracle (C++ port of the reference algorithm) on a bounded sample: the first n distros."""
     from oracle import oracle as O
@@ -144,7 +175,8 @@ def cpu_baseline(w, n_distros: int, threads: int):
     dt = (time.perf_counter() - t0) / passes
     return {"value": n_tasks / dt, "unit": "tasks/s", "cores": threads, "kind": "port",
             "sample": f"first {len(sel)} distros ({n_tasks} tasks) of the workload, {passes} passes after one warm-up, "
-                      f"{dt:.2f} s each, oracle/evg_oracle.cpp (C++17 restatement of the Go path; no Go toolchain in the image)",
+                      f"{dt:.2f} s each, {cores_note()}; oracle/evg_oracle.cpp (C++17 restatement of the Go path; "
+                      f"no Go toolchain in the image)",
             "decisions_per_s": len(sel) / dt}, job
 
 
@@ -152,7 +184,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return 0
     w, _ = workload(0, 1, args.distros, args.tasks_per_distro)
-    threads = os.cpu_count() or 1
+    threads = usable_cores()[0]
     from oracle import oracle as O
     O.build()
     sel = list(range(min(args.ref_sample, w.distros.n_distros)))
@@ -173,7 +205,7 @@ def run_reference(args, rank, world):
                    "sample_distros": len(sel), "parallelism": f"{threads} host threads, one distro per work item"},
         "decisions_per_s": len(sel) / dt,
         "cpu_baseline": {"value": val, "unit": "tasks/s", "cores": threads, "kind": "port",
-                         "sample": f"each step = first {len(sel)} distros ({n_tasks} tasks) of the workload; "
+                         "sample": f"each step = first {len(sel)} distros ({n_tasks} tasks) of the workload; {cores_note()}; "
                                    "oracle/evg_oracle.cpp, C++17 restatement of the Go reference (Go toolchain absent)"},
         "e2e": {"value": val, "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -348,7 +380,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             if prev_affinity:
                 os.sched_setaffinity(0, prev_affinity)  # the baseline gets every host core back
-            cb, _ = cpu_baseline(w, args.ref_sample, os.cpu_count() or 1)
+            cb, _ = cpu_baseline(w, args.ref_sample, usable_cores()[0])
             line["cpu_baseline"] = cb
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
