@@ -1,21 +1,25 @@
 #!/usr/bin/env python3
-"""bench.py -- the scheduler hot path on synthetic ticks of BASELINE.json's shape.
+"""bench.py -- the scheduler hot path on synthetic ticks of BASELINE.json's shapes.
 
   python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
   python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU algorithm on the host cores)
 
-A "step" is one scheduler tick: tunable planner + DistroQueueInfo + utilization
-host allocator over every distro of the workload (configs[1]: 1k distros x 10k
-tasks each per GPU).  `value` = tasks ranked per second with the tick's inputs
-already resident in HBM; `e2e` = the same through the public API
-(Engine.plan_and_alloc_batch: pinned HOST buffers in, host buffers out, H2D and
-D2H inside the timed region).  N > 1: one process per GPU (torchrun), distros
-sharded whole by LPT, one NCCL all-gather of the per-distro result vector per
-step, max-over-ranks timing; weak scaling (each GPU owns its own 1k distros).
-
-The reference is Go and this image has no Go toolchain, so the reference arm
-times oracle/evg_oracle.cpp (a C++ restatement of the reference's algorithm,
-"port") on all host cores over a bounded sample of the same workload.
+A "step" is one scheduler tick: tunable planner + DistroQueueInfo + utilization host allocator over every distro of
+the workload.  Headline workload (per GPU): configs[2] read per distro -- distro queues of 100 000 tasks each, Zipf
+priorities, 5 % of tasks with an unmet dependency on another queued task (DispatcherSettings "revised-with-
+dependencies"), 10 % in task groups -- as many of the 10 000 distros as fit HBM next to the work buffers
+(--distros, default 4000 = 4e8 tasks, 24 GB of columns).  A block of --block distros comes from evergreen_b200.synth
+(splitmix64, the same generator the tests use) and is tiled on the device with a per-tile clock shift, so no two
+tiles are equal and nothing is re-read from L2.
+`value` = tasks ranked per second with the tick's inputs resident in HBM (evg_upload_device + evg_run_resident);
+`e2e`   = the same tick shape through the one-shot C-ABI call (evg_plan_and_alloc_batch: pinned HOST columns in, host
+          results out, H2D and D2H inside the timed region) on --e2e-distros distros;
+`shapes`= the other BASELINE configs through the resident tick in the same process, each with its own roofline
+          figures (configs[1] carries the on-chip planner's kernel-level numbers);
+`cpu_baseline` / --impl reference = oracle/evg_oracle.cpp (C++ restatement of the Go path, "port": the image has
+          no Go toolchain) on the usable host cores over the first --ref-sample distros of the same block.
+N > 1: one process per GPU (torchrun), distros sharded whole by LPT, one NCCL all-gather of the per-distro result
+vector per step on a second stream, max-over-ranks timing; weak scaling (each GPU owns --distros distros).
 """
 import argparse
 import json
@@ -40,17 +44,95 @@ def env_int(name, default):
         return default
 
 
-def workload(rank: int, world: int, distros_per_gpu: int, tasks_per_distro: int):
-    """configs[1] per GPU.  All N*distros_per_gpu distros form one tick; LPT assigns whole distros."""
-    from evergreen_b200 import dist, synth
-    D = world * distros_per_gpu
-    sizes = np.full(D, tasks_per_distro, dtype=np.int64)
-    shards = dist.lpt_partition(sizes, world)
-    mine = shards.members[rank]
-    w = synth.make(sizes[mine], synth.SEED_BASE + 2 + 1000 * rank,
-                   name=f"C2: {len(mine)} distros x {tasks_per_distro} tasks each (rank {rank}/{world})",
-                   n_hosts=5 * len(mine))
-    return w, shards
+HEADLINE = "configs[2] per-distro reading"
+
+
+def headline_block(rank: int, n_block: int, per: int):
+    """The generated block: n_block distros x `per` tasks in configs[2]'s mix (synth.config(3, each=True)'s arguments)."""
+    from evergreen_b200 import synth
+    return synth.make(np.full(n_block, per, dtype=np.int64), synth.SEED_BASE + 3 + 1000 * rank,
+                      name=f"C3 block: {n_block} distros x {per} tasks, Zipf priorities, 5% unmet deps",
+                      zipf_priority=True, unmet_dep_frac=0.05, met_dep_frac=0.02, includes_dependencies=True, n_hosts=2 * n_block)
+
+
+def tile_tables(w, reps: int):
+    """Distro / host tables of `reps` copies of block `w` (host arrays; the task columns are tiled by tile_host /
+    tile_device)."""
+    from evergreen_b200.soa import DistroTable, HostSoA
+    Db, Tb, Gb = w.distros.n_distros, w.n_tasks, w.distros.n_groups
+    task_off = np.concatenate([[0], (w.distros.task_off[1:][None, :] + Tb * np.arange(reps)[:, None]).ravel()]).astype(np.int64)
+    group_off = np.concatenate([[0], (w.distros.group_off[1:][None, :] + Gb * np.arange(reps)[:, None]).ravel()]).astype(np.int64)
+    distros = DistroTable(task_off, group_off, np.tile(w.distros.cfg, reps), np.tile(w.distros.group_max_hosts, reps)).normalize()
+    h = w.hosts
+    Hb = h.n_hosts
+    host_off = np.concatenate([[0], (h.host_off[1:][None, :] + Hb * np.arange(reps)[:, None]).ravel()]).astype(np.int64)
+    hosts = HostSoA(np.tile(h.flags, reps), np.tile(h.group_id, reps), np.tile(h.expected_ns, reps), np.tile(h.std_ns, reps),
+                    np.tile(h.start_ns, reps), host_off, np.tile(h.cfg, reps)).normalize()
+    assert distros.n_distros == Db * reps
+    return distros, hosts
+
+
+SHIFT_QB, SHIFT_EXP = 10 ** 9, 10 ** 6  # tile r: activated r seconds earlier, expected r ms longer
+
+
+def tile_host(w, reps: int):
+    """`reps` shifted copies of block `w` as a host Workload (the e2e leg's input)."""
+    from evergreen_b200 import synth
+    from evergreen_b200.soa import TaskSoA
+    t = w.tasks
+    r = np.repeat(np.arange(reps, dtype=np.int64), w.n_tasks)
+    cols = {name: np.tile(getattr(t, name), reps) for name, _ in t.COLUMNS}
+    cols["queue_basis_ns"] = cols["queue_basis_ns"] - r * SHIFT_QB
+    cols["expected_ns"] = cols["expected_ns"] + r * SHIFT_EXP
+    dep_off = dep_idx = None
+    if t.n_edges:
+        dep_off = np.concatenate([(t.dep_off[:-1][None, :] + t.n_edges * np.arange(reps)[:, None]).ravel(), [t.n_edges * reps]])
+        dep_idx = np.tile(t.dep_idx, reps)
+    tasks = TaskSoA(*[cols[name] for name, _ in t.COLUMNS], dep_off, dep_idx).normalize()
+    distros, hosts = tile_tables(w, reps)
+    return synth.Workload(f"{w.name} x{reps}", w.now, tasks, distros, hosts)
+
+
+def tile_device(torch, dev, w, reps: int):
+    """`reps` shifted copies of block `w`'s task columns in device memory (8 padding rows each, as evg_upload_device
+    asks).  Returns ({column: address}, tensors to keep alive, n_tasks, n_edges)."""
+    t = w.tasks
+    Tb, Eb = w.n_tasks, t.n_edges
+    keep, cols = [], {}
+    rr = torch.arange(reps, device=dev, dtype=torch.int64)[:, None]
+    for name, _ in t.COLUMNS:
+        a = getattr(t, name)
+        blk = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).to(dev)
+        big = torch.zeros(reps * Tb + 8, dtype=blk.dtype, device=dev)
+        v = big[: reps * Tb].view(reps, Tb)
+        v.copy_(blk[None, :])
+        if name == "queue_basis_ns":
+            v.sub_(rr * SHIFT_QB)
+        elif name == "expected_ns":
+            v.add_(rr * SHIFT_EXP)
+        keep.append(big)
+        cols[name] = big.data_ptr()
+        del blk
+    if Eb:
+        blk = torch.from_numpy(t.dep_off[:-1]).to(dev)
+        big = torch.zeros(reps * Tb + 1 + 8, dtype=torch.int64, device=dev)
+        v = big[: reps * Tb].view(reps, Tb)
+        v.copy_(blk[None, :])
+        v.add_(rr * Eb)
+        big[reps * Tb] = reps * Eb
+        keep.append(big)
+        cols["dep_off"] = big.data_ptr()
+        blk = torch.from_numpy(t.dep_idx).to(dev)
+        big = torch.zeros(reps * Eb + 8, dtype=torch.int32, device=dev)
+        big[: reps * Eb].view(reps, Eb).copy_(blk[None, :])
+        keep.append(big)
+        cols["dep_idx"] = big.data_ptr()
+    return cols, keep, reps * Tb, reps * Eb
+
+
+def alg_bytes(T, E, H, G, D):
+    """60*T + 4*E + 28*H + 96*G + 16*D (compulsory traffic only)."""
+    return 60 * T + 4 * E + 28 * H + 96 * G + 16 * D
 
 
 def load_peaks():
@@ -183,7 +265,7 @@ def cpu_baseline(w, n_distros: int, threads: int):
 def run_reference(args, rank, world):
     if rank != 0:
         return 0
-    w, _ = workload(0, 1, args.distros, args.tasks_per_distro)
+    w = headline_block(0, args.block, args.tasks_per_distro)
     threads = usable_cores()[0]
     from oracle import oracle as O
     O.build()
@@ -201,16 +283,69 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "tasks/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": w.name, "distros": w.distros.n_distros, "tasks_per_distro": args.tasks_per_distro,
-                   "sample_distros": len(sel), "parallelism": f"{threads} host threads, one distro per work item"},
+        "config": {"workload": f"{HEADLINE}: distro queues of {args.tasks_per_distro} tasks, Zipf priorities, 5% unmet deps; "
+                               f"each step plans the first {len(sel)} distros of the generated block ({n_tasks} tasks)",
+                   "tasks_per_distro": args.tasks_per_distro, "sample_distros": len(sel),
+                   "parallelism": f"{threads} host threads, one distro per work item"},
         "decisions_per_s": len(sel) / dt,
         "cpu_baseline": {"value": val, "unit": "tasks/s", "cores": threads, "kind": "port",
-                         "sample": f"each step = first {len(sel)} distros ({n_tasks} tasks) of the workload; {cores_note()}; "
+                         "sample": f"each step = first {len(sel)} distros ({n_tasks} tasks) of the workload's block; {cores_note()}; "
                                    "oracle/evg_oracle.cpp, C++17 restatement of the Go reference (Go toolchain absent)"},
         "e2e": {"value": val, "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def time_resident(torch, eng, now, steps, warmup, stream):
+    """ms per resident tick: `warmup` untimed ticks, then `steps` ticks between two events on the engine's stream."""
+    for _ in range(warmup):
+        eng.run(now)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        eng.run(now)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def measure_shapes(torch, eng, stream, peak, steps):
+    """The other BASELINE shapes through the resident tick (same process, same engine)."""
+    from evergreen_b200 import synth
+    out = []
+    specs = [
+        ("configs[1]: 1k distros x 10k tasks each, uniform expected durations", lambda: synth.config(2)),
+        ("configs[2] total reading: 10k distros, 100k tasks in total (Zipf, 5% unmet deps)", lambda: synth.config(3)),
+        ("configs[3] total reading: 10k distros, 1M tasks in total, 50k hosts", lambda: synth.config(4)),
+        ("configs[3] per-distro reading: 8 distros x 1M tasks each, 40 hosts", lambda: synth.config(4, 0.0008, each=True)),
+        ("configs[4]: 100k distros, power-law queue sizes 1..1M, mixed providers", lambda: synth.config(5)),
+    ]
+    for name, make in specs:
+        w = make()
+        eng.upload(w.tasks, w.distros, w.hosts)
+        ms = time_resident(torch, eng, w.now, steps, 3, stream)
+        b = w.algorithmic_bytes()
+        row = {"workload": name, "distros": w.distros.n_distros, "tasks": w.n_tasks, "ms_per_step": ms,
+               "value": w.n_tasks / (ms * 1e-3), "unit": "tasks/s", "decisions_per_s": w.distros.n_distros / (ms * 1e-3),
+               "gpu_launches_per_step": eng.last_launch_count(),
+               "roofline_whole_tick": {"achieved": b / (ms * 1e-3) / 1e9, "frac": b / (ms * 1e-3) / 1e9 / peak,
+                                       "algorithmic_bytes_per_step": int(b)}}
+        if name.startswith("configs[1]"):
+            try:
+                k = eng.kernel_timing_ms(min(steps, 128))
+                kb = 60 * w.tasks.n_tasks + 4 * w.tasks.n_edges + 96 * w.distros.n_groups
+                ks = float(np.mean(k)) * 1e-3
+                row["roofline_kernel"] = {"kernel": "k_plan_cta<512,10240,2> (on-chip planner: TMA-staged columns, u32 keys, "
+                                                    "two CTAs per SM)", "kernel_ms": ks * 1e3, "algorithmic_bytes_per_launch": int(kb),
+                                          "achieved": kb / ks / 1e9, "frac": kb / ks / 1e9 / peak,
+                                          "kernel_share_of_step": ks / (ms * 1e-3)}
+            except Exception as e:  # noqa: BLE001
+                row["roofline_kernel"] = {"error": str(e)}
+        out.append(row)
+        del w
+    return out
 
 
 def main():
@@ -219,13 +354,20 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--distros", type=int, default=1000, help="distros per GPU (configs[1]: 1000)")
-    ap.add_argument("--tasks-per-distro", type=int, default=10_000)
-    ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--ref-sample", type=int, default=300, help="distros per reference/cpu_baseline step")
+    ap.add_argument("--distros", type=int, default=4000, help="distros per GPU (configs[2] names 10000; see the docstring)")
+    ap.add_argument("--block", type=int, default=40, help="distros generated on the host; tiled on the device up to --distros")
+    ap.add_argument("--tasks-per-distro", type=int, default=100_000)
+    ap.add_argument("--e2e-distros", type=int, default=400)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--shape-steps", type=int, default=10)
+    ap.add_argument("--ref-sample", type=int, default=30, help="distros per reference/cpu_baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shapes", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.block = max(1, min(args.block, args.distros))
+    reps = max(1, args.distros // args.block)
+    args.distros = reps * args.block
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -250,9 +392,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    w, shards = workload(rank, world, args.distros, args.tasks_per_distro)
-    D_local = w.distros.n_distros
-    D_total = world * args.distros
+    blk = headline_block(rank, args.block, args.tasks_per_distro)
+    distros, hosts = tile_tables(blk, reps)
+    cols, keep, T, E = tile_device(torch, dev, blk, reps)
+    D_local = distros.n_distros
+    D_total = world * D_local
+    sizes = np.full(D_total, args.tasks_per_distro, dtype=np.int64)
+    shards = edist.lpt_partition(sizes, world)
     # a dedicated (non-default) stream: kernels, NCCL and the timing events all live on it
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
@@ -264,18 +410,20 @@ def main():
     gather = pg.slots[0]
     send = gather.send
     eng.bind_result_buffer(send.data_ptr(), shards.max_shard)
-    eng.upload(w.tasks, w.distros, w.hosts)
+    torch.cuda.synchronize()
+    eng.upload_device(cols, T, distros, hosts, n_edges=E)
+    now = blk.now
     tick = [0]
 
     def step():
         k = tick[0]
         tick[0] += 1
         if world == 1:
-            eng.run(w.now)
+            eng.run(now)
             return
         pg.before_tick(k, stream)
         eng.bind_result_buffer(pg.send(k).data_ptr(), shards.max_shard)
-        eng.run(w.now)
+        eng.run(now)
         pg.launch(k, stream)
 
     def barrier():
@@ -289,7 +437,6 @@ def main():
     launches_per_step = eng.last_launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sort_ms = total_ms = 0.0
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
@@ -298,32 +445,47 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    total_ms, sort_ms = eng.last_timing_ms()  # last step's own CUDA-event split (same stream)
-    kern_ms = eng.kernel_timing_ms(min(args.steps, 128))  # the dominant kernel, every timed step
+    try:
+        task_ms, sort_ms = eng.general_timing_ms()  # last step's own CUDA-event split (same stream)
+    except Exception:  # noqa: BLE001
+        task_ms = sort_ms = None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
-    tasks_total = world * args.distros * args.tasks_per_distro
+    tasks_total = world * T
     value = tasks_total / (ms_per_step * 1e-3)
+    po, ao = eng.download()
+    new_hosts_checksum = int(ao.result["new_hosts"].astype(np.int64).sum())
+    order_ok = bool((np.sort(po.order[: args.tasks_per_distro]) == np.arange(args.tasks_per_distro)).all())
+    H, G = hosts.n_hosts, distros.n_groups
+    del po, ao
+    # the device copy of the headline workload is no longer needed
+    eng.bind_result_buffer(send.data_ptr(), shards.max_shard)
+    del keep, cols
+    torch.cuda.empty_cache()
 
     # ---- end to end through the public API: host buffers in and out, every step ----
+    e2e_reps = max(1, min(args.e2e_distros, args.distros) // args.block)
+    we = tile_host(blk, e2e_reps)
+
     def pinned_like(a):
         v = a.view(np.int32) if a.dtype == np.uint32 else a  # torch pins signed views; same bytes
         p = torch.from_numpy(v).pin_memory().numpy()
         return p.view(a.dtype)
-    for name, _ in w.tasks.COLUMNS:
-        setattr(w.tasks, name, pinned_like(getattr(w.tasks, name)))
-    for name, _ in w.hosts.COLUMNS:
-        setattr(w.hosts, name, pinned_like(getattr(w.hosts, name)))
-    h2d = w.tasks.nbytes() + w.distros.nbytes() + w.hosts.nbytes()
-    eng.bind_result_buffer(send.data_ptr(), shards.max_shard)
-    po, ao = eng.plan_and_alloc_batch(w.tasks, w.distros, w.hosts, w.now)  # warm-up (buffers sized)
-    d2h = po.nbytes() + ao.nbytes()
+    for name, _ in we.tasks.COLUMNS:
+        setattr(we.tasks, name, pinned_like(getattr(we.tasks, name)))
+    if we.tasks.n_edges:
+        we.tasks.dep_off, we.tasks.dep_idx = pinned_like(we.tasks.dep_off), pinned_like(we.tasks.dep_idx)
+    for name, _ in we.hosts.COLUMNS:
+        setattr(we.hosts, name, pinned_like(getattr(we.hosts, name)))
+    h2d = we.tasks.nbytes() + we.distros.nbytes() + we.hosts.nbytes()
+    pe, ae = eng.plan_and_alloc_batch(we.tasks, we.distros, we.hosts, we.now)  # warm-up (buffers sized)
+    d2h = pe.nbytes() + ae.nbytes()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        po, ao = eng.plan_and_alloc_batch(w.tasks, w.distros, w.hosts, w.now)
+        pe, ae = eng.plan_and_alloc_batch(we.tasks, we.distros, we.hosts, we.now)
         if world > 1:
             gather.gather()
     barrier()
@@ -331,56 +493,55 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = tasks_total / float(t.item())
+    e2e_value = world * we.n_tasks / float(t.item())
     clocks = sampler.stop() if sampler else None  # sampled from before the timed loop to the end of the e2e loop
-    new_hosts_checksum = int(ao.result["new_hosts"].astype(np.int64).sum())
+    del we, pe, ae
 
     line = None
     if rank == 0:
         peak, peak_src = load_peaks()
-        alg_bytes = w.algorithmic_bytes()  # per GPU per step
         step_s = ms_per_step * 1e-3
-        # the dominant kernel is the on-chip planner: its algorithmic bytes are the task/edge/group terms
-        kern_bytes = 60 * w.tasks.n_tasks + 4 * w.tasks.n_edges + 96 * w.distros.n_groups
-        kern_s = float(np.mean(kern_ms)) * 1e-3
-        achieved = kern_bytes / kern_s / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per task from the committed ncu --set full capture
-        if os.path.exists(tpath):
-            try:
-                traffic = float(json.load(open(tpath))["dram_bytes_per_task"]) * w.tasks.n_tasks
-            except Exception:
-                traffic = None
+        ab = alg_bytes(T, E, H, G, D_local)  # per GPU per step
+        roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "whole_tick": {"achieved": ab / step_s / 1e9, "frac": ab / step_s / 1e9 / peak, "algorithmic_bytes_per_step": int(ab)}}
+        if task_ms:
+            kb = 48 * T + 4 * E  # the per-task pass reads every input column once; its outputs are scratch
+            roof.update({"kernel": "k_gtask (general path: 128-bit column loads, 32-bit scoring, queue-info fold, unit links), "
+                                   "CUDA events on its stream around the launch in the last timed step",
+                         "kernel_ms": task_ms, "algorithmic_bytes_per_launch": int(kb), "achieved": kb / (task_ms * 1e-3) / 1e9,
+                         "frac": kb / (task_ms * 1e-3) / 1e9 / peak, "kernel_share_of_step": task_ms / ms_per_step,
+                         "sort_ms": sort_ms, "sort_share_of_step": sort_ms / ms_per_step})
+        else:
+            roof.update({"achieved": roof["whole_tick"]["achieved"], "frac": roof["whole_tick"]["frac"], "kernel": "whole tick"})
         line = {
             "metric": METRIC, "value": value, "unit": "tasks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
-            "config": {"workload": f"configs[1]: {args.distros} distros x {args.tasks_per_distro} tasks each per GPU, "
-                                   "10% of tasks in task groups, 5 hosts per distro",
+            "config": {"workload": f"{HEADLINE}: {D_local} distros x {args.tasks_per_distro} tasks each per GPU (of configs[2]'s 10000: "
+                                   "what fits HBM next to the work buffers), Zipf priorities, 5% unmet + 2% met in-queue dependencies, "
+                                   f"10% of tasks in task groups, {H} hosts; a {args.block}-distro block from synth (splitmix64) tiled "
+                                   f"{reps}x on the device with a per-tile clock shift",
                        "distros_total": D_total, "tasks_total": tasks_total, "global_batch": tasks_total,
                        "parallelism": f"distro-sharded x{world} (LPT), 1 all-gather of 16 B/distro per step"
                                       + (", issued on a second stream under the next tick's planner (double-buffered)" if world > 1 else ""),
-                       "l2": "inputs (480 MB SoA per GPU) exceed the 126 MB L2; no flush needed"},
+                       "l2": f"inputs ({(48 * T + 8 * T + 4 * E) / 1e9:.1f} GB of columns per GPU) exceed the 126 MB L2; no flush needed"},
             "decisions_per_s": D_total / step_s,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "tasks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": float(t.item()) * 1e3, "api": "Engine.plan_and_alloc_batch (evg_plan_and_alloc_batch), pinned host columns",
+                    "ms_per_step": float(t.item()) * 1e3,
+                    "workload": f"the same shape on {e2e_reps * args.block} distros ({e2e_reps * args.block * args.tasks_per_distro} tasks) per GPU",
+                    "api": "Engine.plan_and_alloc_batch (evg_plan_and_alloc_batch), pinned host columns",
                     "cpu_affinity": "GPU-local NUMA node" if prev_affinity else "unbound"},
             "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_plan_smem<1024,12,1> (on-chip planner, one CTA per distro), CUDA events on the launching "
-                                   "stream around every launch of the timed region",
-                         "kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_launch": int(kern_bytes),
-                         "kernel_share_of_step": kern_s / step_s,
-                         "whole_tick": {"achieved": alg_bytes / step_s / 1e9, "frac": alg_bytes / step_s / 1e9 / peak,
-                                        "algorithmic_bytes_per_step": int(alg_bytes)}},
-            "checksum_new_hosts": new_hosts_checksum,
+            "roofline": roof,
+            "checksum_new_hosts": new_hosts_checksum, "first_distro_is_a_permutation": order_ok,
         }
+        if not args.no_shapes and world == 1:
+            line["shapes"] = measure_shapes(torch, eng, stream, peak, args.shape_steps)
         if not args.no_cpu_baseline and world == 1:
             if prev_affinity:
                 os.sched_setaffinity(0, prev_affinity)  # the baseline gets every host core back
-            cb, _ = cpu_baseline(w, args.ref_sample, usable_cores()[0])
+            cb, _ = cpu_baseline(blk, args.ref_sample, usable_cores()[0])
             line["cpu_baseline"] = cb
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

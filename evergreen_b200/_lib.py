@@ -137,6 +137,7 @@ SYMBOLS = {
     "evg_alloc_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P]),
     "evg_plan_and_alloc_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_uint32, _P, _P]),
     "evg_upload": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "evg_upload_device": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "evg_run_resident": (C.c_int, [_P, C.c_int64, C.c_uint32]),
     "evg_download": (C.c_int, [_P, _P, _P]),
     "evg_device_result_ptr": (_P, [_P]),
@@ -144,6 +145,7 @@ SYMBOLS = {
     "evg_last_launch_count": (C.c_int64, [_P]),
     "evg_last_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "evg_kernel_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
+    "evg_general_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "evg_deps_met_batch": (C.c_int, [_P, _P, _P]),
     "evg_find_runnable_batch": (C.c_int, [_P, _P, _P, _P]),
     "evg_expected_durations_batch": (C.c_int, [_P, _P, _P]),

@@ -1,0 +1,661 @@
+// evg_plan_general.cuh -- the general path: distros too large for one CTA (any size up to 2^21-1 tasks).
+//
+// Second generation.  The first one sorted a 64-bit value word plus a 42-bit tie word per task with a 16-pass
+// segmented LSD radix sort (20 B/task each way per pass).  This one:
+//   k_gtask        per 2048-task tile: 128-bit column loads, 32-bit scoring (single_task_value32) where the
+//                  distro allows it, queue-info sums folded per tile, TotalValue of single-task units, per-distro
+//                  value range; tasks of multi-member units are linked and compacted into a work list
+//   k_gcomplex     per work-list task: Unit.info / value / anchor of every unit it belongs to, first-occurrence choice
+//                  (planner.go:467-477), rank inside the chosen unit; anchor histogram e[]
+//   k_gsum/k_gscan/k_gplace(+_disp)
+//                  canonical pre-arrangement by COUNTING instead of sorting tie bytes: an exclusive scan of e[] over
+//                  the distro gives every anchor's run start; tasks are written to (key, index) buffers in
+//                  (anchor, rank-in-unit) order.  Distros without multi-member units skip the scan (identity).
+//   k_ghist/k_gdscan/k_gscatter
+//                  stable LSD radix sort on key = Vmax - V only: 32-bit keys, ceil(bits(Vmax-Vmin)/8) passes (3 for
+//                  a 20-bit range), 8 B/task each way per pass; a distro whose range exceeds 32 bits carries a
+//                  second key word and up to 8 passes (per-distro branch, same kernels)
+//   k_gemit        ranked queue + TotalValue
+// TotalValue per task is parked in the total_value OUTPUT buffer between k_gtask and k_gplace (no 8 B/task scratch).
+//
+// Reference: scheduler/planner.go:209-481, scheduler/scheduler.go:56-159.
+#pragma once
+
+constexpr int kGTile = 2048;  // tasks per tile; tiles start at multiples of 4 tasks (16-byte aligned vector loads)
+
+struct DGen {
+  // tiles of the general-path distros, in distro order
+  int64_t n_tiles;
+  const int32_t* tile_distro;  // [NT]
+  const int64_t* tile_start;   // [NT] first task slot of the tile: (base & ~3) + k*kGTile, may precede the distro by <= 3
+  const int64_t* dtile_off;    // [D+1]
+  unsigned long long* vmm;     // [D*2] ord(Vmax), ord(Vmin)
+  uint32_t* key_lo[2];         // [T] low word of Vmax - V, in sort position
+  uint32_t* key_hi[2];         // [T] high word (distros with a range above 32 bits only)
+  uint32_t* idx[2];            // [T] distro-local task index, in sort position
+  uint32_t* e;                 // [T] anchor histogram, then exclusive positions
+  uint32_t* tile_sum;          // [NT] sum of e over the tile, then the tile's exclusive offset inside its distro
+  uint32_t* tile_hist;         // [NT*256]
+  uint32_t* clist;             // work list: global task index of every task that touches a multi-member unit
+  unsigned int* ccount;        // [1]
+  uint32_t* tie_a;             // [T] anchor of the unit the task is emitted from (work-list tasks)
+  uint32_t* tie_r;             // [T] rank inside it
+  int32_t* maxpass;            // [1]
+  int64_t* tv;                 // [T] TotalValue by task (the output buffer, reused)
+};
+
+__device__ __forceinline__ int gen_bits(const DGen& G, int d) {  // significant bits of Vmax - Vmin
+  const unsigned long long r = G.vmm[2 * d] - G.vmm[2 * d + 1];
+  return r == 0 ? 0 : 64 - __clzll((long long)r);
+}
+__device__ __forceinline__ int gen_npass(int bits) { return (bits + 7) >> 3; }
+
+__global__ void k_ginit(DGen G, const int32_t* __restrict__ general_list, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) { *G.ccount = 0u; *G.maxpass = 0; }
+  if (k >= n) return;
+  const int d = general_list[k];
+  G.vmm[2 * d] = 0ull;
+  G.vmm[2 * d + 1] = ~0ull;
+}
+
+// planner.go:449-456 (pass 2): mark every task some in-queue task depends on (general-path distros only).
+__global__ void __launch_bounds__(256) k_gmark(DTasks T, DDistros D, DWork W, DGen G) {
+  if (*W.err) return;
+  const int tile = blockIdx.x;
+  const int d = G.tile_distro[tile];
+  const int64_t base = D.task_off[d], end = D.task_off[d + 1];
+  const int64_t lo = max(G.tile_start[tile], base), hi = min(G.tile_start[tile] + kGTile, end);
+  for (int64_t t = lo + threadIdx.x; t < hi; t += 256)
+    for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) W.has_dep[base + T.dep_idx[e]] = 1;
+}
+
+struct TileFold {  // queue-info partials of one tile (scheduler.go:66-138)
+  unsigned int c[10];
+  unsigned long long s[4];
+  unsigned long long vmax, vmin;
+};
+
+// Per tile: queue info, single-task scores, unit links.  256 threads x 8 tasks: thread q of group u owns the four
+// consecutive task slots tile_start + 4*(u*256 + q) .. +3, so every column is read with 128-bit loads.
+__global__ void __launch_bounds__(256) k_gtask(DTasks T, DDistros D, DWork W, DGen G, int64_t now, int any_complex) {
+  if (*W.err) return;
+  __shared__ TileFold F;
+  __shared__ evg_distro_cfg s_cfg;
+  const int tile = blockIdx.x;
+  const int d = G.tile_distro[tile];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned full = 0xffffffffu;
+  if (tid == 0) {
+    for (int k = 0; k < 10; k++) F.c[k] = 0;
+    for (int k = 0; k < 4; k++) F.s[k] = 0;
+    F.vmax = 0ull; F.vmin = ~0ull;
+    s_cfg = D.cfg[d];
+  }
+  __syncthreads();
+  const evg_distro_cfg& cfg = s_cfg;
+  const int64_t base = D.task_off[d], end = D.task_off[d + 1];
+  const int64_t ts = G.tile_start[tile];
+  const uint32_t ng = uint32_t(D.group_off[d + 1] - D.group_off[d]);
+  const uint32_t ub = uint32_t(D.unit_base[d]);
+  const bool gv = cfg.group_versions != 0;
+  const int64_t threshold = cfg.target_time_ns;
+  const PlannerFactors pf = clamp_factors(cfg);
+  const Factors32 f32 = factors32(pf, now);
+  const bool sane_clock = threshold >= 0 && now >= threshold;
+  const int64_t wait_cutoff = wsub(now, threshold);
+  const bool fast_clock = now >= 0 && pf.nd_int != 0;
+  const bool incl = cfg.includes_dependencies != 0;
+  const bool dcomplex = any_complex && (ng > 0 || gv || (T.n_edges > 0 && T.dep_off[end] > T.dep_off[base]));
+
+  unsigned int c_dm = 0, c_mq = 0, c_over = 0, c_wait = 0, c_sec = 0, c_ung = 0, c_ucnt = 0, c_uover = 0, c_uwait = 0, c_umq = 0;
+  int64_t s_exp = 0, s_over = 0, s_uexp = 0, s_uover = 0;
+  unsigned long long kmax = 0ull, kmin = ~0ull;
+
+#pragma unroll 1
+  for (int u = 0; u < 2; u++) {
+    const int64_t t4 = ts + 4 * int64_t(u * 256 + tid);  // multiple of 4: 16-byte aligned in every column
+    const bool live = t4 < end;  // the columns are readable 8 slots past the last task (upload pads them)
+    int4 prio4 = make_int4(0, 0, 0, 0), nd4 = prio4, gid4 = make_int4(-1, -1, -1, -1), vid4 = prio4;
+    uint4 fl4 = make_uint4(0, 0, 0, 0);
+    longlong2 ex01 = make_longlong2(0, 0), ex23 = ex01, qb01 = ex01, qb23 = ex01, wb01 = ex01, wb23 = ex01;
+    if (live) {
+      prio4 = *reinterpret_cast<const int4*>(T.priority + t4);
+      nd4 = *reinterpret_cast<const int4*>(T.numdep + t4);
+      gid4 = *reinterpret_cast<const int4*>(T.gid + t4);
+      fl4 = *reinterpret_cast<const uint4*>(T.flags + t4);
+      ex01 = *reinterpret_cast<const longlong2*>(T.expected + t4); ex23 = *reinterpret_cast<const longlong2*>(T.expected + t4 + 2);
+      qb01 = *reinterpret_cast<const longlong2*>(T.qbasis + t4); qb23 = *reinterpret_cast<const longlong2*>(T.qbasis + t4 + 2);
+      wb01 = *reinterpret_cast<const longlong2*>(T.wbasis + t4); wb23 = *reinterpret_cast<const longlong2*>(T.wbasis + t4 + 2);
+      if (gv) vid4 = *reinterpret_cast<const int4*>(T.vid + t4);
+    }
+    const int32_t prio_[4] = {prio4.x, prio4.y, prio4.z, prio4.w}, nd_[4] = {nd4.x, nd4.y, nd4.z, nd4.w};
+    const int32_t gid_[4] = {gid4.x, gid4.y, gid4.z, gid4.w}, vid_[4] = {vid4.x, vid4.y, vid4.z, vid4.w};
+    const uint32_t fl_[4] = {fl4.x, fl4.y, fl4.z, fl4.w};
+    const int64_t ex_[4] = {ex01.x, ex01.y, ex23.x, ex23.y}, qb_[4] = {qb01.x, qb01.y, qb23.x, qb23.y};
+    const int64_t wb_[4] = {wb01.x, wb01.y, wb23.x, wb23.y};
+    int64_t vout[4];
+    uint32_t eout[4];
+    bool wr_v[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const int64_t t = t4 + m;
+      const bool valid = live && t >= base && t < end;
+      const int32_t prio = prio_[m], nd = nd_[m], gid = gid_[m], vid = vid_[m];
+      const uint32_t fl = fl_[m];
+      const int64_t exp_ns = ex_[m], qb = qb_[m], wb = wb_[m];
+      bool scores = false, complex_task = false, own_complex = false;
+      if (valid) {
+        const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
+        const bool counted = !incl || dm;
+        const bool over = counted && exp_ns > threshold;
+        const bool wait_over = counted && dm && (sane_clock ? wb < wait_cutoff : since(now, wb) > threshold);
+        const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
+        const bool ung = gid < 0;
+        c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += (fl & EVG_TF_OTHER_DISTRO) != 0;
+        if (counted) s_exp += exp_ns;
+        if (over) s_over += exp_ns;
+        if (ung) {
+          c_ung += 1; c_ucnt += counted; c_uover += over; c_uwait += wait_over; c_umq += mq_dm;
+          if (counted) s_uexp += exp_ns;
+          if (over) s_uover += exp_ns;
+        } else {
+          evg_group_info* g = W.ginfo + D.group_off[d] + gid;
+          atomic_add64(&g->count, counted);
+          atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
+          atomic_add64(&g->count_duration_over_threshold, over);
+          atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
+          atomic_add64(&g->count_wait_over_threshold, wait_over);
+          atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
+        }
+        if (dcomplex) {
+          own_complex = gid >= 0 || gv || W.has_dep[t] != 0;
+          const uint32_t li = uint32_t(t - base);
+          const uint32_t s_own = own_slot_local(gid, vid, li, ng, gv);
+          const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
+          if (own_complex) link_pair(W, uint32_t(t), ub + s_own);
+          if (s_ver != kInactive) link_pair(W, uint32_t(T.n + t), ub + s_ver);  // planner.go:439
+          bool has_edges = false;
+          if (T.n_edges > 0) {
+            const int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
+            has_edges = e1 > e0;
+            for (int64_t e = e0; e < e1; e++) {
+              const uint32_t dl = uint32_t(T.dep_idx[e]);
+              const uint32_t sl = own_slot_local(T.gid[base + dl], T.vid[base + dl], dl, ng, gv);
+              bool dup = (sl == s_own) || (sl == s_ver);  // Unit.Add is keyed by task id (planner.go:131): join each unit once
+              for (int64_t f = e0; f < e && !dup; f++) {
+                const uint32_t fl2 = uint32_t(T.dep_idx[f]);
+                dup = own_slot_local(T.gid[base + fl2], T.vid[base + fl2], fl2, ng, gv) == sl;
+              }
+              W.edge_task[e] = uint32_t(t);
+              if (!dup) link_pair(W, uint32_t(2 * T.n + e), ub + sl);
+            }
+          }
+          complex_task = own_complex || has_edges;
+        }
+        scores = !own_complex;  // the unit filed under this task's own key is {this task}
+      }
+      uint64_t v = 0;
+      if (f32.ok && __all_sync(full, !scores || score32_domain(now, prio, nd, exp_ns, qb))) {
+        v = single_task_value32(f32, now, prio, exp_ns, qb, nd, fl);
+      } else if (fast_clock && __all_sync(full, !scores || score_fast_domain(now, exp_ns, qb))) {
+        v = uint64_t(single_task_value_fast(pf, now, prio, exp_ns, qb, nd, fl));
+      } else if (scores) {
+        v = uint64_t(single_task_value(pf, now, prio, exp_ns, qb, nd, fl));
+      }
+      vout[m] = int64_t(v);
+      wr_v[m] = scores;
+      eout[m] = (valid && !complex_task) ? 1u : 0u;
+      if (scores && !complex_task) {  // final: the task is emitted from its own unit
+        const unsigned long long k = ord_i64(int64_t(v));
+        kmax = max(kmax, k); kmin = min(kmin, k);
+      }
+      if (dcomplex) {  // warp-aggregated append to the work list
+        const unsigned mm = __ballot_sync(full, complex_task);
+        if (mm) {
+          unsigned int pos0 = 0;
+          if (lane == 0) pos0 = atomicAdd(G.ccount, (unsigned int)__popc(mm));
+          pos0 = __shfl_sync(full, pos0, 0);
+          if (complex_task) G.clist[pos0 + __popc(mm & ((1u << lane) - 1u))] = uint32_t(t);
+        }
+      }
+    }
+    // TotalValue of single-task units (also the own-unit candidate of a task that only joins other units by edges)
+    if (!live) {
+    } else if (t4 >= base && t4 + 3 < end && wr_v[0] && wr_v[1] && wr_v[2] && wr_v[3]) {
+      *reinterpret_cast<longlong2*>(G.tv + t4) = make_longlong2(vout[0], vout[1]);
+      *reinterpret_cast<longlong2*>(G.tv + t4 + 2) = make_longlong2(vout[2], vout[3]);
+    } else {
+#pragma unroll
+      for (int m = 0; m < 4; m++)
+        if (wr_v[m]) G.tv[t4 + m] = vout[m];
+    }
+    if (dcomplex && live) {
+      if (t4 >= base && t4 + 3 < end) *reinterpret_cast<uint4*>(G.e + t4) = make_uint4(eout[0], eout[1], eout[2], eout[3]);
+      else {
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+          if (t4 + m >= base && t4 + m < end) G.e[t4 + m] = eout[m];
+      }
+    }
+  }
+  // fold: warp, then block (shared atomics), then one set of global atomics per tile
+  {
+    unsigned int cs[10] = {c_dm, c_mq, c_over, c_wait, c_sec, c_ung, c_ucnt, c_uover, c_uwait, c_umq};
+#pragma unroll
+    for (int k = 0; k < 10; k++) cs[k] = __reduce_add_sync(full, cs[k]);
+    int64_t ss[4] = {s_exp, s_over, s_uexp, s_uover};
+#pragma unroll
+    for (int k = 0; k < 4; k++) ss[k] = warp_sum64(ss[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      kmax = max(kmax, __shfl_xor_sync(full, kmax, o));
+      kmin = min(kmin, __shfl_xor_sync(full, kmin, o));
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 10; k++) if (cs[k]) atomicAdd(&F.c[k], cs[k]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (ss[k]) atomicAdd(&F.s[k], (unsigned long long)ss[k]);
+      atomicMax(&F.vmax, kmax); atomicMin(&F.vmin, kmin);
+    }
+  }
+  __syncthreads();
+  if (tid < 16) {
+    evg_queue_info* q = W.qinfo + d;
+    switch (tid) {
+      case 0: atomic_add64(&q->length_with_dependencies_met, F.c[0]); break;
+      case 1: atomic_add64(&q->count_dep_filled_merge_queue_tasks, F.c[1]); break;
+      case 2: atomic_add64(&q->count_duration_over_threshold, F.c[2]); break;
+      case 3: atomic_add64(&q->count_wait_over_threshold, F.c[3]); break;
+      case 4: atomic_add64(&q->secondary_queue, F.c[4]); break;
+      case 5: atomic_add64(&q->has_ungrouped, F.c[5]); break;
+      case 6: atomic_add64(&q->ungrouped.count, F.c[6]); break;
+      case 7: atomic_add64(&q->ungrouped.count_duration_over_threshold, F.c[7]); break;
+      case 8: atomic_add64(&q->ungrouped.count_wait_over_threshold, F.c[8]); break;
+      case 9: atomic_add64(&q->ungrouped.count_dep_filled_merge_queue_tasks, F.c[9]); break;
+      case 10: atomic_add64(&q->expected_duration, int64_t(F.s[0])); break;
+      case 11: atomic_add64(&q->duration_over_threshold, int64_t(F.s[1])); break;
+      case 12: atomic_add64(&q->ungrouped.expected_duration, int64_t(F.s[2])); break;
+      case 13: atomic_add64(&q->ungrouped.duration_over_threshold, int64_t(F.s[3])); break;
+      case 14: if (F.vmax > __ldcg(G.vmm + 2 * d)) atomicMax(G.vmm + 2 * d, F.vmax); break;
+      case 15: if (F.vmin < __ldcg(G.vmm + 2 * d + 1)) atomicMin(G.vmm + 2 * d + 1, F.vmin); break;
+    }
+  }
+}
+
+// Per work-list task: every unit it belongs to is evaluated by walking the unit's member list (Unit.info, value, anchor
+// and this member's rank: eval_pair's arithmetic), then the first unit the task is emitted from is chosen
+// (TaskPlan.Export, planner.go:467-477).
+__global__ void __launch_bounds__(256) k_gcomplex(DTasks T, DDistros D, DWork W, DGen G, int64_t now) {
+  if (*W.err) return;
+  const unsigned int n = *G.ccount;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {  // the host cannot know n: fixed grid
+  const uint32_t t = G.clist[k];
+  const int d = find_distro(D.task_off, 0, D.n - 1, int64_t(t));
+  const evg_distro_cfg cfg = D.cfg[d];
+  const int64_t base = D.task_off[d];
+  const uint32_t li = uint32_t(int64_t(t) - base);
+  const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
+  const int64_t my_ex = T.expected[t];
+  bool have = false;
+  int64_t bv = 0;
+  uint32_t ba = 0, brk = 0, bp = kInactive, bslot = 0, bn = 0;
+  auto consider_pair = [&](uint32_t p) {
+    if (W.next[p] == kInactive) return;  // not linked (duplicate membership, or a key this task is not filed under)
+    const uint32_t slot = W.pair_slot[p];
+    UnitAcc a;
+    acc_init(a);
+    uint32_t anchor = kNoAnchor, rk = 0;
+    for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
+      const uint32_t tq = pair_task(T, W, q);
+      const uint32_t lq = uint32_t(int64_t(tq) - base);
+      const int32_t q_pr = T.priority[tq], q_nd = T.numdep[tq], q_tgo = T.tgo[tq];
+      const int64_t q_ex = T.expected[tq];
+      acc_add(a, now, q_pr, q_ex, T.qbasis[tq], q_nd, T.gid[tq], T.flags[tq]);
+      if (q < uint32_t(T.n)) anchor = min(anchor, lq);  // own-key pairs are the SetDistro members (planner.go:446)
+      if (in_unit_less(q_tgo, q_nd, q_pr, q_ex, lq, my_tgo, my_nd, my_pr, my_ex, li)) rk++;
+    }
+    if (anchor == kNoAnchor) return;  // the unit never got a distro -> not exported (planner.go:81-83)
+    const int64_t v = unit_value(a, cfg, nullptr);
+    if (!have || v > bv || (v == bv && anchor < ba)) { have = true; bv = v; ba = anchor; brk = rk; bp = p; bslot = slot; bn = uint32_t(a.n); }
+  };
+  if (W.next[t] == kInactive) { have = true; bv = G.tv[t]; ba = li; brk = 0; }  // its own single-task unit, scored by k_gtask
+  else consider_pair(t);
+  consider_pair(uint32_t(T.n + t));
+  if (T.n_edges > 0)
+    for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) consider_pair(uint32_t(2 * T.n + e));
+  G.tv[t] = bv;
+  G.tie_a[t] = ba;
+  G.tie_r[t] = brk;
+  W.best_pair[t] = bp;
+  if (bp != kInactive) {
+    W.unit_n[bslot] = bn;  // every member writes the same count
+    if (bn <= 64) atomicOr(&W.unit_mask[bslot], 1ull << brk);  // ranks emitted from the unit: k_gplace_disp counts below its own
+  }
+  const bool displaced = !(ba == li && brk == 0);
+  if (displaced) W.has_dep[t] |= 2;  // only this thread touches the byte now (k_gmark and k_gtask are done)
+  atomicAdd(G.e + base + ba, 1u);
+  const unsigned long long kk = ord_i64(bv);
+  if (kk > __ldcg(G.vmm + 2 * d)) atomicMax(G.vmm + 2 * d, kk);
+  if (kk < __ldcg(G.vmm + 2 * d + 1)) atomicMin(G.vmm + 2 * d + 1, kk);
+  }
+}
+
+// radix pass count of the tick (the host launches that many pass triples... it cannot know: it launches 8, the
+// kernels of passes beyond *maxpass exit at once)
+__global__ void k_gsched(DGen G, const int32_t* __restrict__ general_list, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int np = gen_npass(gen_bits(G, general_list[k]));
+  if (np > 0) atomicMax(G.maxpass, np);
+}
+
+// sum of e[] over each tile
+__global__ void __launch_bounds__(256) k_gsum(DDistros D, DGen G) {
+  const int tile = blockIdx.x;
+  const int d = G.tile_distro[tile];
+  const int64_t base = D.task_off[d], end = D.task_off[d + 1];
+  const int64_t lo = max(G.tile_start[tile], base), hi = min(G.tile_start[tile] + kGTile, end);
+  uint32_t sum = 0;
+  for (int64_t t = lo + threadIdx.x; t < hi; t += 256) sum += G.e[t];
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  __shared__ uint32_t sw[8];
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) G.tile_sum[tile] = sw[0] + sw[1] + sw[2] + sw[3] + sw[4] + sw[5] + sw[6] + sw[7];
+}
+
+// exclusive scan of the tile sums of one distro (<= 1025 tiles), one block per general-path distro
+__global__ void __launch_bounds__(1024) k_gscan(DGen G, const int32_t* __restrict__ general_list) {
+  const int d = general_list[blockIdx.x];
+  const int64_t t0 = G.dtile_off[d], nt = G.dtile_off[d + 1] - t0;
+  __shared__ uint32_t sw[32];
+  __shared__ uint32_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t c0 = 0; c0 < nt; c0 += 1024) {
+    const int64_t i = c0 + threadIdx.x;
+    const uint32_t v = i < nt ? G.tile_sum[t0 + i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) sw[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t w = sw[lane];
+      uint32_t winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += x; }
+      sw[lane] = winc - w;
+    }
+    __syncthreads();
+    const uint32_t ex = carry + sw[warp] + inc - v;
+    if (i < nt) G.tile_sum[t0 + i] = ex;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = ex + v;
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void gen_put(const DGen& G, int64_t base, uint32_t pos, unsigned long long vmax_ord, bool wide,
+                                        int64_t v, uint32_t li) {
+  const unsigned long long key = vmax_ord - ord_i64(v);
+  G.key_lo[0][base + pos] = uint32_t(key);
+  if (wide) G.key_hi[0][base + pos] = uint32_t(key >> 32);
+  G.idx[0][base + pos] = li;
+}
+
+// Per tile: exclusive scan of e[] (thread q owns 8 consecutive slots) on top of the tile's offset = the run start of
+// every anchor; tasks that keep their own anchor with rank 0 are written to their sort position.  use_e == 0 (no
+// multi-member unit in any general-path distro): positions are the input order.
+__global__ void __launch_bounds__(256) k_gplace(DDistros D, DWork W, DGen G, int use_e) {
+  const int tile = blockIdx.x;
+  const int d = G.tile_distro[tile];
+  const int64_t base = D.task_off[d], end = D.task_off[d + 1];
+  const int64_t ts = G.tile_start[tile];
+  const unsigned long long vmax_ord = G.vmm[2 * d];
+  const bool wide = gen_bits(G, d) > 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t t8 = ts + 8 * int64_t(tid);  // multiple of 4
+  const bool interior = t8 >= base && t8 + 7 < end;  // the common case: 128-bit loads
+  uint32_t ev[8];
+  uint32_t sum = 0;
+  if (use_e) {
+    if (interior) {
+      const uint4 a = *reinterpret_cast<const uint4*>(G.e + t8), b = *reinterpret_cast<const uint4*>(G.e + t8 + 4);
+      ev[0] = a.x; ev[1] = a.y; ev[2] = a.z; ev[3] = a.w; ev[4] = b.x; ev[5] = b.y; ev[6] = b.z; ev[7] = b.w;
+    } else {
+#pragma unroll
+      for (int m = 0; m < 8; m++) { const int64_t t = t8 + m; ev[m] = (t >= base && t < end) ? G.e[t] : 0u; }
+    }
+#pragma unroll
+    for (int m = 0; m < 8; m++) sum += ev[m];
+  }
+  uint32_t run = 0;
+  if (use_e) {
+    __shared__ uint32_t sw[8];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) sw[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) if (w < warp) before += sw[w];
+    run = G.tile_sum[tile] + before + inc - sum;
+  }
+  int64_t vv[8];
+  uint32_t dsp = 0;  // bit m: task t8+m leaves its own anchor's first slot (placed by k_gplace_disp)
+  if (interior) {
+#pragma unroll
+    for (int m = 0; m < 8; m += 2) {
+      const longlong2 x = *reinterpret_cast<const longlong2*>(G.tv + t8 + m);
+      vv[m] = x.x; vv[m + 1] = x.y;
+    }
+    if (use_e) {
+      const uint32_t h0 = *reinterpret_cast<const uint32_t*>(W.has_dep + t8), h1 = *reinterpret_cast<const uint32_t*>(W.has_dep + t8 + 4);
+#pragma unroll
+      for (int m = 0; m < 4; m++) dsp |= (((h0 >> (8 * m + 1)) & 1u) << m) | (((h1 >> (8 * m + 1)) & 1u) << (m + 4));
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+      const int64_t t = t8 + m;
+      const bool in = t >= base && t < end;
+      vv[m] = in ? G.tv[t] : 0;
+      if (use_e && in && (W.has_dep[t] & 2)) dsp |= 1u << m;
+    }
+  }
+  if (use_e) {
+    if (interior) {
+      uint32_t ps[8];
+#pragma unroll
+      for (int m = 0; m < 8; m++) { ps[m] = run; run += ev[m]; }
+      *reinterpret_cast<uint4*>(G.e + t8) = make_uint4(ps[0], ps[1], ps[2], ps[3]);
+      *reinterpret_cast<uint4*>(G.e + t8 + 4) = make_uint4(ps[4], ps[5], ps[6], ps[7]);
+#pragma unroll
+      for (int m = 0; m < 8; m++)
+        if (!((dsp >> m) & 1u)) gen_put(G, base, ps[m], vmax_ord, wide, vv[m], uint32_t(t8 + m - base));
+    } else {
+#pragma unroll
+      for (int m = 0; m < 8; m++) {
+        const int64_t t = t8 + m;
+        if (t >= base && t < end) {
+          G.e[t] = run;
+          if (!((dsp >> m) & 1u)) gen_put(G, base, run, vmax_ord, wide, vv[m], uint32_t(t - base));
+          run += ev[m];
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+      const int64_t t = t8 + m;
+      if (t >= base && t < end) gen_put(G, base, uint32_t(t - base), vmax_ord, wide, vv[m], uint32_t(t - base));
+    }
+  }
+}
+
+// Displaced work-list tasks: position = run start of the anchor + number of tasks emitted from the same unit with a smaller rank.
+__global__ void __launch_bounds__(256) k_gplace_disp(DTasks T, DDistros D, DWork W, DGen G) {
+  const unsigned int n = *G.ccount;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+  const uint32_t t = G.clist[k];
+  if (!(W.has_dep[t] & 2)) continue;
+  const int d = find_distro(D.task_off, 0, D.n - 1, int64_t(t));
+  const int64_t base = D.task_off[d];
+  const uint32_t a = G.tie_a[t], myrk = G.tie_r[t];
+  uint32_t pos = G.e[base + a];
+  const uint32_t slot = W.pair_slot[W.best_pair[t]];
+  if (W.unit_n[slot] <= 64) {
+    pos += __popcll(W.unit_mask[slot] & ((1ull << myrk) - 1ull));
+  } else {
+    for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
+      const uint32_t tq = pair_task(T, W, q);
+      if (W.best_pair[tq] != kInactive && W.pair_slot[W.best_pair[tq]] == slot && G.tie_r[tq] < myrk) pos++;
+    }
+  }
+  gen_put(G, base, pos, G.vmm[2 * d], gen_bits(G, d) > 32, G.tv[t], uint32_t(int64_t(t) - base));
+  }
+}
+
+__device__ __forceinline__ bool gen_tile(const DDistros& D, const DGen& G, int tile, int j, int* d_out, int64_t* seg, int64_t* lo,
+                                         int* cnt, bool* wide) {
+  const int d = G.tile_distro[tile];
+  const int bits = gen_bits(G, d);
+  if (j >= gen_npass(bits)) return false;
+  const int64_t base = D.task_off[d], end = D.task_off[d + 1];
+  const int64_t a = max(G.tile_start[tile], base), b = min(G.tile_start[tile] + kGTile, end);
+  *d_out = d; *seg = base; *lo = a; *cnt = int(b - a); *wide = bits > 32;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_ghist(int j, DDistros D, DGen G) {
+  if (j >= *G.maxpass) return;
+  int d, cnt; int64_t seg, lo; bool wide;
+  if (!gen_tile(D, G, blockIdx.x, j, &d, &seg, &lo, &cnt, &wide)) return;
+  const uint32_t* src = (j < 4 ? G.key_lo[j & 1] : G.key_hi[j & 1]) + lo;
+  const int shift = 8 * (j & 3);
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < cnt; i += 256) atomicAdd(&h[(src[i] >> shift) & 255u], 1u);
+  __syncthreads();
+  G.tile_hist[int64_t(blockIdx.x) * 256 + threadIdx.x] = h[threadIdx.x];
+}
+
+// Offsets of every (tile, digit) counter of one distro: exclusive over the tiles of a digit, then over the digits
+// (four thread groups split the tiles, eight independent loads in flight per thread).
+__global__ void __launch_bounds__(1024) k_gdscan(int j, const int32_t* __restrict__ general_list, DGen G) {
+  if (j >= *G.maxpass) return;
+  const int d = general_list[blockIdx.x];
+  if (j >= gen_npass(gen_bits(G, d))) return;
+  const int dg = threadIdx.x & 255, grp = threadIdx.x >> 8;
+  const int64_t t0 = G.dtile_off[d], nt = G.dtile_off[d + 1] - t0;
+  const int64_t per = (nt + 3) / 4;
+  const int64_t a = t0 + (grp * per < nt ? grp * per : nt), b = t0 + ((grp + 1) * per < nt ? (grp + 1) * per : nt);
+  uint32_t* h = G.tile_hist + dg;
+  uint32_t sum = 0;
+  int64_t tile = a;
+  for (; tile + 8 <= b; tile += 8) {
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = h[(tile + k) * 256];
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += x[k];
+  }
+  for (; tile < b; tile++) sum += h[tile * 256];
+  __shared__ uint32_t part[4][256];
+  __shared__ uint32_t s[256];
+  part[grp][dg] = sum;
+  __syncthreads();
+  const uint32_t total = part[0][dg] + part[1][dg] + part[2][dg] + part[3][dg];
+  if (grp == 0) s[dg] = total;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    uint32_t v = 0;
+    if (grp == 0 && dg >= o) v = s[dg - o];
+    __syncthreads();
+    if (grp == 0) s[dg] += v;
+    __syncthreads();
+  }
+  uint32_t run = s[dg] - total;
+  for (int g = 0; g < grp; g++) run += part[g][dg];
+  tile = a;
+  for (; tile + 8 <= b; tile += 8) {
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = h[(tile + k) * 256];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { h[(tile + k) * 256] = run; run += x[k]; }
+  }
+  for (; tile < b; tile++) { const uint32_t x = h[tile * 256]; h[tile * 256] = run; run += x; }
+}
+
+__global__ void __launch_bounds__(256) k_gscatter(int j, DDistros D, DGen G) {
+  if (j >= *G.maxpass) return;
+  int d, cnt; int64_t seg, lo; bool wide;
+  if (!gen_tile(D, G, blockIdx.x, j, &d, &seg, &lo, &cnt, &wide)) return;
+  const int sb = j & 1, db = sb ^ 1;
+  constexpr int kChunks = kGTile / 32;
+  __shared__ uint16_t ch[kChunks][256];
+  for (int i = threadIdx.x; i < kChunks * 256 / 2; i += 256) reinterpret_cast<uint32_t*>(&ch[0][0])[i] = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int shift = 8 * (j & 3);
+  uint32_t kl[8], kh[8], ix[8], dg[8], rk[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int c = warp * 8 + k;
+    const int i = c * 32 + lane;
+    const bool ok = i < cnt;
+    kl[k] = ok ? G.key_lo[sb][lo + i] : 0u;
+    kh[k] = (ok && wide) ? G.key_hi[sb][lo + i] : 0u;
+    ix[k] = ok ? G.idx[sb][lo + i] : 0u;
+    dg[k] = ok ? (((j < 4 ? kl[k] : kh[k]) >> shift) & 255u) : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, dg[k]);
+    rk[k] = __popc(peers & lt);
+    if (ok && rk[k] == 0) ch[c][dg[k]] = uint16_t(__popc(peers));
+  }
+  __syncthreads();
+  {
+    uint32_t run = 0;
+    for (int c = 0; c < kChunks; c++) {
+      const uint32_t x = ch[c][threadIdx.x];
+      ch[c][threadIdx.x] = uint16_t(run);
+      run += x;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    if (dg[k] < 256u) {
+      const int c = warp * 8 + k;
+      const int64_t pos = seg + G.tile_hist[int64_t(blockIdx.x) * 256 + dg[k]] + ch[c][dg[k]] + rk[k];
+      G.key_lo[db][pos] = kl[k];
+      if (wide) G.key_hi[db][pos] = kh[k];
+      G.idx[db][pos] = ix[k];
+    }
+  }
+}
+
+// Ranked queue out: order[] and TotalValue per rank (planner.go:467-477).
+__global__ void __launch_bounds__(256) k_gemit(DDistros D, DGen G, int32_t* __restrict__ order, int64_t* __restrict__ total_value) {
+  const int tile = blockIdx.x;
+  const int d = G.tile_distro[tile];
+  const int64_t base = D.task_off[d], end = D.task_off[d + 1];
+  const int64_t lo = max(G.tile_start[tile], base), hi = min(G.tile_start[tile] + kGTile, end);
+  const int bits = gen_bits(G, d);
+  const int fin = gen_npass(bits) & 1;
+  const bool wide = bits > 32;
+  const unsigned long long vmax_ord = G.vmm[2 * d];
+  for (int64_t p = lo + threadIdx.x; p < hi; p += 256) {
+    unsigned long long key = G.key_lo[fin][p];
+    if (wide) key |= (unsigned long long)G.key_hi[fin][p] << 32;
+    order[p] = int32_t(G.idx[fin][p]);
+    total_value[p] = unord_i64(vmax_ord - key);
+  }
+}

@@ -71,35 +71,10 @@ __device__ __forceinline__ void cp_async_wait_but_newest() { asm volatile("cp.as
 __device__ __forceinline__ unsigned long long ord_i64(int64_t v) { return uint64_t(v) ^ 0x8000000000000000ULL; }
 __device__ __forceinline__ int64_t unord_i64(unsigned long long k) { return int64_t(k ^ 0x8000000000000000ULL); }
 
-// Unit.info + value + this member's rank for one linked (unit, member) pair:
-// shared by the general path (k_unit) and the on-chip path.
-__device__ __forceinline__ void eval_pair(const DTasks& T, const DWork& W, const evg_distro_cfg& cfg, int64_t now,
-                                          uint32_t p, uint32_t t, int64_t base) {
-  const uint32_t slot = W.pair_slot[p];
-  const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
-  const int64_t my_ex = T.expected[t];
-  const uint32_t my_li = uint32_t(t - base);
-  UnitAcc a;
-  acc_init(a);
-  uint32_t anchor = kNoAnchor, rk = 0;
-  for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
-    const uint32_t tq = pair_task(T, W, q);
-    const uint32_t lq = uint32_t(tq - base);
-    const int32_t q_pr = T.priority[tq], q_nd = T.numdep[tq], q_tgo = T.tgo[tq];
-    const int64_t q_ex = T.expected[tq];
-    acc_add(a, now, q_pr, q_ex, T.qbasis[tq], q_nd, T.gid[tq], T.flags[tq]);
-    if (q < uint32_t(T.n)) anchor = min(anchor, lq);  // own-key pairs are the SetDistro members (planner.go:446)
-    if (in_unit_less(q_tgo, q_nd, q_pr, q_ex, lq, my_tgo, my_nd, my_pr, my_ex, my_li)) rk++;
-  }
-  W.cand_v[p] = unit_value(a, cfg, nullptr);
-  W.cand_a[p] = anchor;  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
-  W.cand_rk[p] = rk;
-}
-
 template <int THREADS, int ITEMS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
-k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int64_t now, int lists_needed,
-            int32_t* __restrict__ order, int64_t* __restrict__ total_value) {
+k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, const int32_t* __restrict__ list_count,
+            int64_t now, int lists_needed, int32_t* __restrict__ order, int64_t* __restrict__ total_value) {
   constexpr int CAP = THREADS * ITEMS;
   constexpr int NW = THREADS / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -120,6 +95,8 @@ k_plan_smem(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int
   const unsigned full = 0xffffffffu;
 
   if (*W.err) return;  // k_validate found an out-of-range id in this upload: plan nothing (uniform exit)
+  // list_count != nullptr: `list` was filled on the device (distros k_plan_cta handed back) and the grid is its capacity
+  if (list_count && int(blockIdx.x) >= *list_count) return;
   // ---- phase 0: distro header ----
   if (tid == 0) {
     const int d = list[blockIdx.x];

@@ -1,18 +1,19 @@
 // evg_sched.cu -- libevgsched.so: CUDA kernels (sm_100a) + the C-ABI of
 // include/evg_sched.h.  See DESIGN.md for the data layout and the kernel list.
 //
-// Distros are routed by size on the host:
+// Distros are routed by size and shape on the host:
 //   <= 32 tasks      k_plan_warp (evg_plan_warp.cuh): one warp plans the distro
-//   <= 12288 tasks   k_plan_smem<THREADS,ITEMS> (evg_plan_smem.cuh): one CTA plans the distro on-chip
-//   larger           the general path below, any size up to 2^21-1 tasks:
-//     k_mark_dependents   dependency edges -> "has in-queue dependents" byte     (planner.go:449-456)
-//     k_task              per task: queue-info reduction (scheduler.go:56-159), unit membership
-//                         links (planner.go:431-447), score of single-task units (planner.go:209-337)
-//     k_unit              per (unit, member) pair: Unit.info reduction, score, anchor, rank in the unit
-//     k_best              per task: first unit it is emitted from (planner.go:467-477)
-//     k_sched/k_sort_*    per-distro segmented stable LSD radix sort over the key bytes that vary
-//     k_emit              ranked queue + TotalValue
-//     k_finalize_info     DistroQueueInfo / TaskGroupInfo scalars (scheduler.go:144-158)
+//   <= 10240 tasks, no GroupVersions, no in-queue dependency edges
+//                    k_plan_cta<THREADS,CAP> (evg_plan_cta.cuh): one CTA plans the distro on-chip, several CTAs per
+//                    SM, TMA-staged columns, u32 keys; distros it cannot hold (values beyond 32 bits, ...) are
+//                    handed back ("punted") to k_plan_smem on the device
+//   <= 12288 tasks   k_plan_smem<THREADS,ITEMS> (evg_plan_smem.cuh): one CTA per distro, any unit structure
+//   larger           the general path (evg_plan_general.cuh), any size up to 2^21-1 tasks:
+//     k_gmark/k_gtask/k_gcomplex   dependents, per-task pass, multi-member units
+//     k_gsum/k_gscan/k_gplace*     canonical pre-arrangement by counting
+//     k_ghist/k_gdscan/k_gscatter  segmented stable LSD radix sort of 32-bit keys
+//     k_gemit                      ranked queue + TotalValue
+//     k_finalize_info              DistroQueueInfo / TaskGroupInfo scalars (scheduler.go:144-158)
 // Both:
 //   k_breakdown           the 13-field SortingValueBreakdown per ranked task (EVG_OPT_BREAKDOWN)
 //   k_alloc<TPD>          utilization host allocator, a warp or a block per distro (utilization_based_host_allocator.go:26-409)
@@ -29,6 +30,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -64,7 +66,13 @@ int fail(int code, const char* fmt, ...) {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool owned = true;  // false: p is caller-owned device memory (evg_upload_device)
+  void adopt(void* q) {
+    if (owned && p) cudaFree(p);
+    p = q; cap = 0; owned = false;
+  }
   cudaError_t ensure(size_t bytes) {
+    if (!owned) { p = nullptr; cap = 0; owned = true; }
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr;
@@ -76,17 +84,15 @@ struct DevBuf {
     return cudaSuccess;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     cap = 0;
+    owned = true;
   }
   template <class T>
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-constexpr int kTile = 2048;        // sort tile: 64 warp-chunks of 32
-constexpr int kChunks = kTile / 32;
-constexpr int kMaxPass = 16;       // 8 tie bytes + 8 value bytes
 // on-chip planner classes <THREADS, ITEMS>: capacity = THREADS*ITEMS tasks per distro
 #ifndef EVG_C_THREADS  // shape of the largest on-chip class (threads x tasks per thread = 12288 tasks in 218 KB)
 #define EVG_C_THREADS 1024
@@ -95,6 +101,10 @@ constexpr int kMaxPass = 16;       // 8 tie bytes + 8 value bytes
 constexpr int kCapA = 128 * 8, kCapB = 256 * 16, kCapC = EVG_C_THREADS * EVG_C_ITEMS;
 constexpr int64_t kWideAllocGroups = 1024;  // k_alloc<128> (a block per distro) once some distro has more task groups
 constexpr int kCapW = 32;  // k_plan_warp: one warp per distro
+// second-generation on-chip planner classes <THREADS, CAP, CTAs per SM> (evg_plan_cta.cuh)
+constexpr int kNT_A = 128, kNCapA = 1280, kNOccA = 8;
+constexpr int kNT_B = 256, kNCapB = 5120, kNOccB = 4;
+constexpr int kNT_C = 512, kNCapC = 10240, kNOccC = 2;
 constexpr uint32_t kInactive = 0xFFFFFFFFu;  // next[]: pair not linked / head[]: empty list
 constexpr uint32_t kEnd = 0xFFFFFFFEu;       // next[]: end of list
 constexpr uint32_t kNoAnchor = 0xFFFFFFFFu;
@@ -129,9 +139,7 @@ struct DDistros {
 };
 
 struct SortBuf {
-  uint64_t* key_s;
-  uint64_t* key_v;
-  uint32_t* idx;
+  uint64_t* key_v;  // [T] k_plan_smem: Vmax - V of a distro whose value range exceeds 32 bits
 };
 
 struct DWork {
@@ -143,23 +151,12 @@ struct DWork {
   uint8_t* edge_live;    // [E] on-chip path: 1 = edge pair linked (not a duplicate membership)
   const uint8_t* route;  // [D] 1 = distro planned by k_plan_smem (general kernels skip it)
   int* err;              // [1] set by k_validate when a distro-local id is out of range; planners then do nothing
-  int64_t* cand_v;       // [2T+E]
-  uint32_t* cand_a;      // [2T+E]
-  uint32_t* cand_rk;     // [2T+E]
   int64_t* unit_v;       // [unit slots] on-chip path: TotalValue of the unit
   uint32_t* unit_a;      // [unit slots] anchor
   uint32_t* unit_n;      // [unit slots] member count
   unsigned long long* unit_mask;  // [unit slots] ranks emitted from the unit (units of <= 64 members)
   uint32_t* best_pair;   // [T]
-  SortBuf buf[2];
-  unsigned long long* bits;  // [D*4]: orS, andS, orV, andV
-  int32_t* npass;        // [D]
-  uint8_t* sched;        // [D*16]
-  int32_t* maxpass;      // [1]
-  const int32_t* tile_distro;  // [NT]
-  const int64_t* tile_start;   // [NT]
-  const int64_t* dtile_off;    // [D+1]
-  uint32_t* tile_hist;   // [NT*256]
+  SortBuf buf[1];
   evg_queue_info* qinfo; // [D]
   evg_group_info* ginfo; // [G]
 };
@@ -223,28 +220,6 @@ __device__ __forceinline__ void atomic_add64(int64_t* p, int64_t v) {
   if (v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
 }
 
-// Record which key bits vary inside a distro (drives the radix pass schedule).
-__device__ __forceinline__ void note_key_bits(unsigned long long* bits, int d, bool valid, bool uniform, uint64_t ks,
-                                              uint64_t kv) {
-  if (uniform) {
-    uint64_t os = warp_or64(ks), as = warp_and64(ks), ov = warp_or64(kv), av = warp_and64(kv);
-    if ((threadIdx.x & 31) == 0) {
-      // or-words only gain bits and and-words only lose them, so an atomic that would change nothing (nearly
-      // all of them once a big distro's first warps have reported) is skipped after a plain L2 read
-      unsigned long long* b = bits + 4 * d;
-      if (os & ~__ldcg(b + 0)) atomicOr(b + 0, os);
-      if (~as & __ldcg(b + 1)) atomicAnd(b + 1, as);
-      if (ov & ~__ldcg(b + 2)) atomicOr(b + 2, ov);
-      if (~av & __ldcg(b + 3)) atomicAnd(b + 3, av);
-    }
-  } else if (valid) {
-    atomicOr(bits + 4 * d + 0, ks);
-    atomicAnd(bits + 4 * d + 1, ks);
-    atomicOr(bits + 4 * d + 2, kv);
-    atomicAnd(bits + 4 * d + 3, kv);
-  }
-}
-
 // unit slot (distro-local) a task is filed under by its id key (planner.go:434-445)
 __device__ __forceinline__ uint32_t own_slot_local(int32_t gid, int32_t vid, uint32_t local_idx, uint32_t n_groups,
                                                    bool group_versions) {
@@ -266,6 +241,8 @@ __device__ __forceinline__ uint32_t pair_task(const DTasks& T, const DWork& W, u
 
 #include "evg_plan_smem.cuh"
 #include "evg_plan_warp.cuh"
+#include "evg_plan_cta.cuh"
+#include "evg_plan_general.cuh"
 
 // --------------------------------------------------------------------------
 // kernels (general path: any distro size)
@@ -488,405 +465,6 @@ __global__ void __launch_bounds__(256) k_dur_final(DDur X, evg_duration_stat* ou
   out[k] = st;
 }
 
-// planner.go:449-456 (pass 2): mark every task some in-queue task depends on.
-__global__ void k_mark_dependents(DTasks T, DDistros D, DWork W) {
-  if (*W.err) return;
-  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  int d = block_find_distro(D.task_off, D.n, t, T.n);
-  if (d < 0 || W.route[d]) return;
-  int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
-  int64_t base = D.task_off[d];
-  for (int64_t e = e0; e < e1; e++) W.has_dep[base + T.dep_idx[e]] = 1;
-}
-
-// Per task: queue info (scheduler.go:56-159), unit links (planner.go:431-456),
-// and the score of units that are provably {this task} (planner.go:209-337).
-__global__ void __launch_bounds__(256) k_task(DTasks T, DDistros D, DWork W, int64_t now, int any_complex) {
-  if (*W.err) return;
-  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int d = block_find_distro(D.task_off, D.n, t, T.n);
-  const bool valid = d >= 0 && !W.route[d];
-  const unsigned full = 0xffffffffu;
-  const int d0 = __shfl_sync(full, d, 0);
-  const bool uniform = __all_sync(full, d == d0) && valid;
-  // A block that lies inside one distro folds its eight warps in shared memory first: a million-task distro
-  // would otherwise send every warp's fourteen adds to the same DistroQueueInfo row (millions of L2 atomics
-  // on a handful of addresses).
-  __shared__ int s_first;
-  __shared__ long long s_fold[8][14];
-  if (threadIdx.x == 0) s_first = d;
-  __syncthreads();
-  const bool block_uniform = __syncthreads_and(valid && d == s_first) != 0;
-
-  int32_t prio = 0, nd = 0, gid = -1, vid = 0;
-  int64_t exp_ns = 0, qb = EVG_TIME_ZERO, wb = EVG_TIME_ZERO;
-  uint32_t fl = 0;
-  evg_distro_cfg cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  int64_t base = 0;
-  if (valid) {
-    prio = T.priority[t]; exp_ns = T.expected[t]; qb = T.qbasis[t]; wb = T.wbasis[t];
-    nd = T.numdep[t]; gid = T.gid[t]; vid = T.vid[t]; fl = T.flags[t];
-    cfg = D.cfg[d];
-    base = D.task_off[d];
-  }
-
-  // ---- GetDistroQueueInfo contributions (scheduler.go:66-138) ----
-  const bool dm = valid && (fl & EVG_TF_DEPS_MET);
-  const bool counted = valid && (!cfg.includes_dependencies || dm);
-  const int64_t threshold = cfg.target_time_ns;
-  const bool over = counted && exp_ns > threshold;
-  const bool wait_over = counted && dm && since(now, wb) > threshold;
-  const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
-  const bool sec = valid && (fl & EVG_TF_OTHER_DISTRO);
-  const bool ung = valid && gid < 0;
-  if (valid) {
-    if (uniform) {
-      // five 6-bit counters per word (a warp adds at most 32 to each)
-      uint32_t w0 = uint32_t(dm) | (uint32_t(mq_dm) << 6) | (uint32_t(over) << 12) | (uint32_t(wait_over) << 18) |
-                    (uint32_t(sec) << 24);
-      uint32_t w1 = uint32_t(ung) | (uint32_t(ung && counted) << 6) | (uint32_t(ung && over) << 12) |
-                    (uint32_t(ung && wait_over) << 18) | (uint32_t(ung && mq_dm) << 24);
-      w0 = __reduce_add_sync(full, w0);
-      w1 = __reduce_add_sync(full, w1);
-      int64_t s_exp = warp_sum64(counted ? exp_ns : 0);
-      int64_t s_over = warp_sum64(over ? exp_ns : 0);
-      int64_t s_uexp = warp_sum64(ung && counted ? exp_ns : 0);
-      int64_t s_uover = warp_sum64(ung && over ? exp_ns : 0);
-      if (block_uniform) {
-        if ((threadIdx.x & 31) == 0) {
-          long long* f = s_fold[threadIdx.x >> 5];
-          f[0] = w0 & 63; f[1] = (w0 >> 6) & 63; f[2] = (w0 >> 12) & 63; f[3] = (w0 >> 18) & 63; f[4] = (w0 >> 24) & 63;
-          f[5] = s_exp; f[6] = s_over;
-          f[7] = w1 & 63; f[8] = (w1 >> 6) & 63; f[9] = (w1 >> 12) & 63; f[10] = (w1 >> 18) & 63; f[11] = (w1 >> 24) & 63;
-          f[12] = s_uexp; f[13] = s_uover;
-        }
-      } else if ((threadIdx.x & 31) == 0) {
-        evg_queue_info* q = W.qinfo + d;
-        atomic_add64(&q->length_with_dependencies_met, w0 & 63);
-        atomic_add64(&q->count_dep_filled_merge_queue_tasks, (w0 >> 6) & 63);
-        atomic_add64(&q->count_duration_over_threshold, (w0 >> 12) & 63);
-        atomic_add64(&q->count_wait_over_threshold, (w0 >> 18) & 63);
-        atomic_add64(&q->secondary_queue, (w0 >> 24) & 63);
-        atomic_add64(&q->expected_duration, s_exp);
-        atomic_add64(&q->duration_over_threshold, s_over);
-        atomic_add64(&q->has_ungrouped, w1 & 63);
-        atomic_add64(&q->ungrouped.count, (w1 >> 6) & 63);
-        atomic_add64(&q->ungrouped.count_duration_over_threshold, (w1 >> 12) & 63);
-        atomic_add64(&q->ungrouped.count_wait_over_threshold, (w1 >> 18) & 63);
-        atomic_add64(&q->ungrouped.count_dep_filled_merge_queue_tasks, (w1 >> 24) & 63);
-        atomic_add64(&q->ungrouped.expected_duration, s_uexp);
-        atomic_add64(&q->ungrouped.duration_over_threshold, s_uover);
-      }
-    } else {
-      evg_queue_info* q = W.qinfo + d;
-      atomic_add64(&q->length_with_dependencies_met, dm);
-      atomic_add64(&q->count_dep_filled_merge_queue_tasks, mq_dm);
-      atomic_add64(&q->count_duration_over_threshold, over);
-      atomic_add64(&q->count_wait_over_threshold, wait_over);
-      atomic_add64(&q->secondary_queue, sec);
-      atomic_add64(&q->expected_duration, counted ? exp_ns : 0);
-      atomic_add64(&q->duration_over_threshold, over ? exp_ns : 0);
-      if (ung) {
-        atomic_add64(&q->has_ungrouped, 1);
-        atomic_add64(&q->ungrouped.count, counted);
-        atomic_add64(&q->ungrouped.count_duration_over_threshold, over);
-        atomic_add64(&q->ungrouped.count_wait_over_threshold, wait_over);
-        atomic_add64(&q->ungrouped.count_dep_filled_merge_queue_tasks, mq_dm);
-        atomic_add64(&q->ungrouped.expected_duration, counted ? exp_ns : 0);
-        atomic_add64(&q->ungrouped.duration_over_threshold, over ? exp_ns : 0);
-      }
-    }
-  }
-  if (block_uniform) {  // block-wide condition: every thread reaches the barrier
-    __syncthreads();
-    if (threadIdx.x < 14) {
-      // evg_queue_info as int64[19]: the field each folded slot belongs to
-      constexpr int kField[14] = {1, 2, 5, 7, 8, 3, 6, 9, 10, 15, 16, 17, 14, 18};
-      long long tot = 0;
-#pragma unroll
-      for (int w = 0; w < 8; w++) tot += s_fold[w][threadIdx.x];
-      if (tot) atomic_add64(reinterpret_cast<int64_t*>(W.qinfo + d) + kField[threadIdx.x], tot);
-    }
-  }
-  if (valid) {
-    if (gid >= 0) {
-      evg_group_info* g = W.ginfo + D.group_off[d] + gid;
-      atomic_add64(&g->count, counted);
-      atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
-      atomic_add64(&g->count_duration_over_threshold, over);
-      atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
-      atomic_add64(&g->count_wait_over_threshold, wait_over);
-      atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
-    }
-  }
-
-  // ---- units ----
-  uint64_t key_s = 0, key_v = 0;
-  if (valid) {
-    const uint32_t li = uint32_t(t - base);
-    const bool gv = cfg.group_versions != 0;
-    const uint32_t ng = uint32_t(D.group_off[d + 1] - D.group_off[d]);
-    bool own_complex = false;
-    if (any_complex) {
-      own_complex = gid >= 0 || gv || W.has_dep[t] != 0;
-      const uint32_t ub = uint32_t(D.unit_base[d]);
-      const uint32_t s_own = own_slot_local(gid, vid, li, ng, gv);
-      const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
-      if (own_complex) link_pair(W, uint32_t(t), ub + s_own);
-      if (s_ver != kInactive) link_pair(W, uint32_t(T.n + t), ub + s_ver);  // planner.go:439
-      if (T.n_edges > 0) {
-        const int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
-        for (int64_t e = e0; e < e1; e++) {
-          const uint32_t dl = uint32_t(T.dep_idx[e]);
-          const uint32_t s = own_slot_local(T.gid[base + dl], T.vid[base + dl], dl, ng, gv);
-          // Unit.Add is keyed by task id (planner.go:131): join each unit once.
-          bool dup = (s == s_own) || (s == s_ver);
-          for (int64_t f = e0; f < e && !dup; f++) {
-            const uint32_t fl2 = uint32_t(T.dep_idx[f]);
-            dup = own_slot_local(T.gid[base + fl2], T.vid[base + fl2], fl2, ng, gv) == s;
-          }
-          W.edge_task[e] = uint32_t(t);
-          if (!dup) link_pair(W, uint32_t(2 * T.n + e), ub + s);
-        }
-      }
-    }
-    if (!own_complex) {
-      UnitAcc a;
-      acc_init(a);
-      acc_add(a, now, prio, exp_ns, qb, nd, gid, fl);
-      const int64_t v = unit_value(a, cfg, nullptr);
-      if (any_complex) W.cand_v[t] = v;  // read back by k_best
-      key_v = enc_value(v);
-      key_s = enc_tie(li, 0);
-    }
-    if (!any_complex) {
-      W.buf[0].key_s[t] = key_s;
-      W.buf[0].key_v[t] = key_v;
-      W.buf[0].idx[t] = li;
-    }
-  }
-  if (!any_complex) note_key_bits(W.bits, valid ? d : 0, valid, uniform, key_s, key_v);
-}
-
-// Per linked (unit, member) pair: Unit.info over the unit's member list, the
-// unit's score, its anchor and this member's rank inside the unit.
-__global__ void __launch_bounds__(256) k_unit(DTasks T, DDistros D, DWork W, int64_t now, int64_t n_pairs) {
-  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= n_pairs || *W.err) return;
-  // resolve the owning distro first: pairs of on-chip distros belong to k_plan_smem
-  uint32_t t;
-  if (p < T.n) t = uint32_t(p);
-  else if (p < 2 * T.n) t = uint32_t(p - T.n);
-  else t = W.edge_task[p - 2 * T.n];
-  const int d = find_distro(D.task_off, 0, D.n - 1, int64_t(t));
-  if (W.route[d]) return;
-  if (W.next[p] == kInactive) return;
-  eval_pair(T, W, D.cfg[d], now, uint32_t(p), t, D.task_off[d]);
-}
-
-// Per task: the unit it is emitted from = best of its memberships under the
-// canonical unit order (TaskPlan.Export first-occurrence rule, planner.go:467-477).
-__global__ void __launch_bounds__(256) k_best(DTasks T, DDistros D, DWork W) {
-  if (*W.err) return;
-  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int d = block_find_distro(D.task_off, D.n, t, T.n);
-  const bool valid = d >= 0 && !W.route[d];
-  const unsigned full = 0xffffffffu;
-  const int d0 = __shfl_sync(full, d, 0);
-  const bool uniform = __all_sync(full, d == d0) && valid;
-  uint64_t key_s = 0, key_v = 0;
-  if (valid) {
-    const uint32_t li = uint32_t(t - D.task_off[d]);
-    bool have = false;
-    int64_t bv = 0;
-    uint32_t ba = 0, brk = 0, bp = kInactive;
-    auto consider = [&](int64_t v, uint32_t a, uint32_t rk, uint32_t pair) {
-      if (a == kNoAnchor) return;
-      bool better = !have || v > bv || (v == bv && a < ba);
-      if (better) { have = true; bv = v; ba = a; brk = rk; bp = pair; }
-    };
-    if (W.next[t] == kInactive) consider(W.cand_v[t], li, 0, kInactive);  // single-task unit scored by k_task
-    else consider(W.cand_v[t], W.cand_a[t], W.cand_rk[t], uint32_t(t));
-    const int64_t pv = T.n + t;
-    if (W.next[pv] != kInactive) consider(W.cand_v[pv], W.cand_a[pv], W.cand_rk[pv], uint32_t(pv));
-    if (T.n_edges > 0) {
-      for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) {
-        const int64_t pe = 2 * T.n + e;
-        if (W.next[pe] != kInactive) consider(W.cand_v[pe], W.cand_a[pe], W.cand_rk[pe], uint32_t(pe));
-      }
-    }
-    key_v = enc_value(bv);
-    key_s = enc_tie(ba, brk);
-    W.best_pair[t] = bp;
-    W.buf[0].key_s[t] = key_s;
-    W.buf[0].key_v[t] = key_v;
-    W.buf[0].idx[t] = li;
-  }
-  note_key_bits(W.bits, valid ? d : 0, valid, uniform, key_s, key_v);
-}
-
-// bits[]: or-words start at 0, and-words at all ones
-__global__ void k_init_bits(unsigned long long* bits, int n) {
-  int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= n) return;
-  bits[4 * d + 0] = 0ull;
-  bits[4 * d + 1] = ~0ull;
-  bits[4 * d + 2] = 0ull;
-  bits[4 * d + 3] = ~0ull;
-}
-
-// Radix pass schedule per distro: the key bytes that actually vary.
-__global__ void k_sched(DDistros D, DWork W, int use_tie) {
-  int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D.n) return;
-  int n = 0;
-  if (!W.route[d] && D.task_off[d + 1] - D.task_off[d] > 1) {
-    uint64_t vs = W.bits[4 * d + 0] & ~W.bits[4 * d + 1];
-    uint64_t vv = W.bits[4 * d + 2] & ~W.bits[4 * d + 3];
-    if (use_tie)
-      for (int b = 0; b < 8; b++) if ((vs >> (8 * b)) & 0xff) W.sched[d * kMaxPass + n++] = uint8_t(b);
-    for (int b = 0; b < 8; b++) if ((vv >> (8 * b)) & 0xff) W.sched[d * kMaxPass + n++] = uint8_t(8 + b);
-  }
-  W.npass[d] = n;
-  if (n > 0) atomicMax(W.maxpass, n);
-}
-
-__device__ __forceinline__ uint32_t key_byte(uint64_t ks, uint64_t kv, int b) {
-  return uint32_t(((b < 8) ? (ks >> (8 * b)) : (kv >> (8 * (b - 8)))) & 0xffu);
-}
-
-__global__ void __launch_bounds__(256) k_sort_hist(int j, DDistros D, DWork W) {
-  if (j >= *W.maxpass) return;
-  const int tile = blockIdx.x;
-  const int d = W.tile_distro[tile];
-  if (j >= W.npass[d]) return;
-  const int b = W.sched[d * kMaxPass + j];
-  const SortBuf src = W.buf[j & 1];
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  const int64_t start = W.tile_start[tile];
-  const int64_t end = D.task_off[d + 1];
-  const int cnt = int((end - start) < int64_t(kTile) ? (end - start) : int64_t(kTile));
-  for (int i = threadIdx.x; i < cnt; i += 256) atomicAdd(&h[key_byte(src.key_s[start + i], src.key_v[start + i], b)], 1u);
-  __syncthreads();
-  W.tile_hist[int64_t(tile) * 256 + threadIdx.x] = h[threadIdx.x];
-}
-
-// Offsets of every (tile, digit) counter of one general-path distro: exclusive over the tiles of a digit, then
-// over the digits.  A distro of a million tasks has ~500 tiles, so a thread per digit walking them one L2 round
-// trip at a time is a ~0.7 ms chain per pass; here four thread groups split the tiles and every thread keeps
-// eight independent loads in flight.
-__global__ void __launch_bounds__(1024) k_sort_scan(int j, const int32_t* __restrict__ general_list, DDistros D, DWork W) {
-  if (j >= *W.maxpass) return;
-  const int d = general_list[blockIdx.x];
-  if (j >= W.npass[d]) return;
-  const int dg = threadIdx.x & 255, grp = threadIdx.x >> 8;
-  const int64_t t0 = W.dtile_off[d], nt = W.dtile_off[d + 1] - t0;
-  const int64_t per = (nt + 3) / 4;
-  const int64_t a = t0 + (grp * per < nt ? grp * per : nt), b = t0 + ((grp + 1) * per < nt ? (grp + 1) * per : nt);
-  uint32_t* h = W.tile_hist + dg;
-  uint32_t sum = 0;
-  int64_t tile = a;
-  for (; tile + 8 <= b; tile += 8) {
-    uint32_t x[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) x[k] = h[(tile + k) * 256];
-#pragma unroll
-    for (int k = 0; k < 8; k++) sum += x[k];
-  }
-  for (; tile < b; tile++) sum += h[tile * 256];
-  __shared__ uint32_t part[4][256];
-  __shared__ uint32_t s[256];
-  part[grp][dg] = sum;
-  __syncthreads();
-  const uint32_t total = part[0][dg] + part[1][dg] + part[2][dg] + part[3][dg];
-  if (grp == 0) s[dg] = total;
-  __syncthreads();
-  for (int o = 1; o < 256; o <<= 1) {
-    uint32_t v = 0;
-    if (grp == 0 && dg >= o) v = s[dg - o];
-    __syncthreads();
-    if (grp == 0) s[dg] += v;
-    __syncthreads();
-  }
-  uint32_t run = s[dg] - total;  // digits before this one
-  for (int g = 0; g < grp; g++) run += part[g][dg];  // this digit in the tile groups before this one
-  tile = a;
-  for (; tile + 8 <= b; tile += 8) {
-    uint32_t x[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) x[k] = h[(tile + k) * 256];
-#pragma unroll
-    for (int k = 0; k < 8; k++) { h[(tile + k) * 256] = run; run += x[k]; }
-  }
-  for (; tile < b; tile++) { const uint32_t x = h[tile * 256]; h[tile * 256] = run; run += x; }
-}
-
-__global__ void __launch_bounds__(256) k_sort_scatter(int j, DDistros D, DWork W) {
-  if (j >= *W.maxpass) return;
-  const int tile = blockIdx.x;
-  const int d = W.tile_distro[tile];
-  if (j >= W.npass[d]) return;
-  const int b = W.sched[d * kMaxPass + j];
-  const SortBuf src = W.buf[j & 1];
-  const SortBuf dst = W.buf[(j + 1) & 1];
-  __shared__ uint16_t ch[kChunks][256];
-  for (int i = threadIdx.x; i < kChunks * 256 / 2; i += 256) reinterpret_cast<uint32_t*>(&ch[0][0])[i] = 0;
-  __syncthreads();
-  const int64_t start = W.tile_start[tile];
-  const int64_t seg = D.task_off[d];
-  const int64_t rem = D.task_off[d + 1] - start;
-  const int cnt = int(rem < int64_t(kTile) ? rem : int64_t(kTile));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  uint64_t ks[8], kv[8];
-  uint32_t ix[8], dg[8], rk[8];
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const int c = warp * 8 + k;
-    const int i = c * 32 + lane;
-    const bool ok = i < cnt;
-    if (ok) { ks[k] = src.key_s[start + i]; kv[k] = src.key_v[start + i]; ix[k] = src.idx[start + i]; }
-    else { ks[k] = 0; kv[k] = 0; ix[k] = 0; }
-    dg[k] = ok ? key_byte(ks[k], kv[k], b) : 256u;
-    const unsigned peers = __match_any_sync(0xffffffffu, dg[k]);
-    rk[k] = __popc(peers & lt);
-    if (ok && rk[k] == 0) ch[c][dg[k]] = uint16_t(__popc(peers));
-  }
-  __syncthreads();
-  {
-    uint32_t run = 0;
-    for (int c = 0; c < kChunks; c++) {
-      uint32_t x = ch[c][threadIdx.x];
-      ch[c][threadIdx.x] = uint16_t(run);
-      run += x;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    if (dg[k] < 256u) {
-      const int c = warp * 8 + k;
-      const int64_t pos = seg + W.tile_hist[int64_t(tile) * 256 + dg[k]] + ch[c][dg[k]] + rk[k];
-      dst.key_s[pos] = ks[k];
-      dst.key_v[pos] = kv[k];
-      dst.idx[pos] = ix[k];
-    }
-  }
-}
-
-// Ranked queue out (general path): order[] and TotalValue per rank (planner.go:467-477).
-__global__ void __launch_bounds__(256) k_emit(DTasks T, DDistros D, DWork W, int32_t* order, int64_t* total_value) {
-  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int d = block_find_distro(D.task_off, D.n, t, T.n);
-  if (d < 0 || W.route[d]) return;
-  const SortBuf src = W.buf[W.npass[d] & 1];
-  order[t] = int32_t(src.idx[t]);
-  total_value[t] = dec_value(src.key_v[t]);
-}
-
 // The 13-field SortingValueBreakdown of the unit each ranked task was emitted
 // from (planner.go:472-476, model/task/task.go:3990-4038); both paths.
 __global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W, int64_t now, int any_complex,
@@ -1085,35 +663,47 @@ struct evg_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  cudaEvent_t ev_begin = nullptr, ev_sort0 = nullptr, ev_sort1 = nullptr, ev_end = nullptr;
-  // ring of event pairs around the on-chip planner launches: per-run kernel time without syncing inside a timed loop
+  // Entry points may be called from any OS thread (cgo runs a call on whatever M the goroutine sits on): every
+  // extern "C" function that takes a context holds this lock for its duration, so one context serialises its
+  // callers and several contexts (one per worker) run side by side on their own streams.
+  std::recursive_mutex mu;
+  cudaEvent_t ev_begin = nullptr, ev_sort0 = nullptr, ev_sort1 = nullptr, ev_end = nullptr, ev_gt0 = nullptr, ev_gt1 = nullptr;
+  bool general_timed = false;
+  // ring of event pairs around the dominant kernel of a tick: per-run kernel time without syncing inside a timed loop
   static constexpr int kRing = 128;
   cudaEvent_t ring0[kRing] = {}, ring1[kRing] = {};
   int64_t runs = 0;
   int64_t max_groups = 0;  // most task groups in any distro: picks the allocator's team width
-  int sort_slot = -1;  // ring slot that stands in for the sort split when the tick had no general-path distro
+  int sort_slot = -1;      // ring slot of the last run's dominant-kernel pair
+  // route streams: the size classes of one tick are independent until the allocator, so they run side by side
+  static constexpr int kAux = 6;
+  cudaStream_t s_aux[kAux] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
   // resident inputs
   bool have_tasks = false, have_hosts = false;
-  int64_t T = 0, E = 0, G = 0, H = 0, U = 0, NT = 0;
+  int64_t T = 0, E = 0, G = 0, H = 0, U = 0, NT = 0, t_pad = 0;
   int32_t Dn = 0;
   int any_complex = 0;
   int64_t launches = 0;
   bool timed = false;
+  bool adopted = false;  // task columns are caller-owned device memory (evg_upload_device)
   DevBuf b_prio, b_exp, b_qb, b_wb, b_nd, b_tgo, b_gid, b_vid, b_flags, b_depoff, b_depidx;
   DevBuf b_taskoff, b_groupoff, b_cfg, b_gmax, b_unitbase;
-  DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_cv, b_ca, b_crk, b_bestpair;
+  DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_ca, b_crk, b_bestpair;
   DevBuf b_rn0, b_rn1, b_rn2, b_rn3, b_rn4, b_rn5, b_rn6, b_rn7;
   DevBuf b_err, b_dx0, b_dx1, b_dx2, b_dx3, b_dx4, b_dx5, b_dx6, b_dx7;
-  DevBuf b_route, b_listW, b_listA, b_listB, b_listC, b_listG, b_unitv, b_unita, b_unitn, b_unitmask;
-  int32_t nW = 0, nA = 0, nB = 0, nC = 0, n_general = 0;  // distros per on-chip class / general path
-  std::vector<int32_t> h_listW, h_listA, h_listB, h_listC;  // host copies (ascending distro ids) for the pipelined one-shot call
+  DevBuf b_route, b_listW, b_listA, b_listB, b_listC, b_listG, b_listNA, b_listNB, b_listNC, b_unitv, b_unita, b_unitn, b_unitmask;
+  DevBuf b_punt, b_puntcnt;
+  int32_t nW = 0, nA = 0, nB = 0, nC = 0, nNA = 0, nNB = 0, nNC = 0, n_general = 0;  // distros per route
+  std::vector<int32_t> h_listW, h_listA, h_listB, h_listC, h_listNA, h_listNB, h_listNC;  // host copies (ascending distro ids)
   std::vector<int64_t> h_taskoff, h_groupoff;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   static constexpr int kMaxChunks = 16;
   cudaEvent_t ev_h[kMaxChunks] = {}, ev_c[kMaxChunks] = {};
   int general_complex = 0;
-  DevBuf b_ks[2], b_kv[2], b_ix[2], b_bits, b_npass, b_sched, b_maxpass;
-  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist;
+  int64_t Tgc = 0;  // tasks in general-path distros that can hold multi-member units (work-list capacity)
+  DevBuf b_kv, b_vmm, b_klo[2], b_khi[2], b_ix[2], b_e, b_tilesum, b_gmisc;
+  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist;
   DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
   DevBuf b_hflags, b_hgid, b_hexp, b_hstd, b_hstart, b_hostoff, b_acfg, b_gs, b_result, b_status;
   bool bd_valid = false;
@@ -1127,9 +717,17 @@ namespace {
 DTasks dtasks(const evg_ctx* c);
 DDistros ddistros(const evg_ctx* c);
 DWork dwork(const evg_ctx* c);
+DGen dgen(const evg_ctx* c);
 inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1) / block); }
 
-int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, bool copy_columns = true) {
+// Columns are padded so that 128-bit loads and TMA copies that start inside the table may run past its last row.
+constexpr int64_t kColPad = 8;
+
+// Route every distro of the tick, stage the small tables, size the work buffers.  Columns: copied from the host
+// (copy_columns), left for the pipelined call to copy chunk by chunk, or adopted from caller-owned device memory.
+// `edge_off` (D+1, host) is dep_off sampled at the distro boundaries; NULL when the host can read t->dep_off itself.
+int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, bool copy_columns = true, bool adopt = false,
+                 const int64_t* edge_off = nullptr) {
   if (!t || !dt) return fail(EVG_ERR_INVALID, "null task table / distro table");
   const int64_t T = t->n_tasks, E = t->n_edges;
   const int32_t D = dt->n_distros;
@@ -1143,34 +741,42 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   if (E > 0 && (!t->dep_off || !t->dep_idx)) return fail(EVG_ERR_INVALID, "n_edges > 0 but dep_off/dep_idx null");
   if (D == 0 && T != 0) return fail(EVG_ERR_INVALID, "tasks without distros");
   std::vector<int64_t> unit_base(size_t(D) + 1, 0), dtile_off(size_t(D) + 1, 0);
-  std::vector<int32_t> tile_distro, listW, listA, listB, listC, listG;
+  std::vector<int32_t> tile_distro, listW, listA, listB, listC, listG, listNA, listNB, listNC;
   std::vector<int64_t> tile_start;
   std::vector<uint8_t> route(size_t(D) + 1, 0);
   int32_t n_general = 0;
   int general_complex = 0;
   int any_complex = E > 0 ? 1 : 0;
+  int64_t Tgc = 0;
+  constexpr int kGA = PlanCta<kNT_A, kNCapA>::kGroupCap, kGB = PlanCta<kNT_B, kNCapB>::kGroupCap, kGC = PlanCta<kNT_C, kNCapC>::kGroupCap;
   for (int32_t d = 0; d < D; d++) {
     const int64_t a = dt->task_off[d], b = dt->task_off[d + 1];
     const int64_t ga = dt->group_off[d], gb = dt->group_off[d + 1];
     if (d == 0 && (a != 0 || ga != 0)) return fail(EVG_ERR_INVALID, "offsets must start at 0");
     if (b < a || gb < ga) return fail(EVG_ERR_INVALID, "offsets of distro %d decrease", d);
     if (b - a > kMaxTasksPerDistro) return fail(EVG_ERR_INVALID, "distro %d holds %lld tasks (max %lld)", d, (long long)(b - a), (long long)kMaxTasksPerDistro);
+    if (b > T) return fail(EVG_ERR_INVALID, "task_off of distro %d exceeds n_tasks", d);
     const evg_distro_cfg& cf = dt->cfg[d];
     if (cf.n_versions < 0) return fail(EVG_ERR_INVALID, "distro %d: negative n_versions", d);
     if (gb > ga || cf.group_versions) any_complex = 1;
     unit_base[d + 1] = unit_base[d] + (gb - ga) + (cf.group_versions ? int64_t(cf.n_versions) : (b - a));
-    // route: small distros are planned on-chip by k_plan_smem, the rest by the general path
-    const int64_t n = b - a;
+    const int64_t n = b - a, g = gb - ga;
+    const int64_t de = (E > 0) ? (edge_off ? edge_off[d + 1] - edge_off[d] : t->dep_off[b] - t->dep_off[a]) : 0;
+    // second-generation on-chip planner: task groups are the only multi-member units it knows
+    const bool narrow = !cf.group_versions && de == 0;
     if (n <= kCapW) { listW.push_back(d); route[d] = 1; }
+    else if (narrow && n <= kNCapA && g <= kGA) { listNA.push_back(d); route[d] = 1; }
+    else if (narrow && n <= kNCapB && g <= kGB) { listNB.push_back(d); route[d] = 1; }
+    else if (narrow && n <= kNCapC && g <= kGC) { listNC.push_back(d); route[d] = 1; }
     else if (n <= kCapA) { listA.push_back(d); route[d] = 1; }
     else if (n <= kCapB) { listB.push_back(d); route[d] = 1; }
     else if (n <= kCapC) { listC.push_back(d); route[d] = 1; }
     else {
       n_general++;
       listG.push_back(d);
-      const int64_t de = (E > 0) ? (t->dep_off[b] - t->dep_off[a]) : 0;
-      if (gb > ga || cf.group_versions || de > 0) general_complex = 1;
-      for (int64_t s = a; s < b; s += kTile) { tile_distro.push_back(d); tile_start.push_back(s); }
+      if (gb > ga || cf.group_versions || de > 0) { general_complex = 1; Tgc += n; }
+      const int64_t a0 = a & ~int64_t(3);  // tiles start 16-byte aligned in every column
+      for (int64_t s = a0; s < b; s += kGTile) { tile_distro.push_back(d); tile_start.push_back(s); }
     }
     dtile_off[d + 1] = int64_t(tile_distro.size());
   }
@@ -1189,8 +795,13 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   } while (0)
 #define UPC(buf, ptr, count, type)                                                                    \
   do {                                                                                                \
-    CK((buf).ensure(sizeof(type) * size_t((count) > 0 ? (count) : 1)));                               \
-    if (copy_columns && (count) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(count), cudaMemcpyHostToDevice, s)); \
+    if (adopt) {                                                                                      \
+      if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) return fail(EVG_ERR_INVALID, "device column %s is not 16-byte aligned", #ptr); \
+      (buf).adopt(const_cast<void*>(static_cast<const void*>(ptr)));                                  \
+    } else {                                                                                          \
+      CK((buf).ensure(sizeof(type) * size_t((count) + kColPad)));                                     \
+      if (copy_columns && (count) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(count), cudaMemcpyHostToDevice, s)); \
+    }                                                                                                 \
   } while (0)
   UPC(c->b_prio, t->priority, T, int32_t);
   UPC(c->b_exp, t->expected_ns, T, int64_t);
@@ -1220,11 +831,15 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   UP(c->b_listA, listA.data(), int64_t(listA.size()), int32_t);
   UP(c->b_listB, listB.data(), int64_t(listB.size()), int32_t);
   UP(c->b_listC, listC.data(), int64_t(listC.size()), int32_t);
+  UP(c->b_listNA, listNA.data(), int64_t(listNA.size()), int32_t);
+  UP(c->b_listNB, listNB.data(), int64_t(listNB.size()), int32_t);
+  UP(c->b_listNC, listNC.data(), int64_t(listNC.size()), int32_t);
   // the staging vectors above must outlive the async copies
   CK(cudaStreamSynchronize(s));
   // work buffers
+  const bool on_chip_cta = !(listA.empty() && listB.empty() && listC.empty() && listNA.empty() && listNB.empty() && listNC.empty());
   if (any_complex) {
-    CK(c->b_hasdep.ensure(size_t(T) + 1));
+    CK(c->b_hasdep.ensure(size_t(T) + 16));
     CK(c->b_head.ensure(sizeof(uint32_t) * size_t(U + 1)));
     CK(c->b_next.ensure(sizeof(uint32_t) * size_t(P + 1)));
     CK(c->b_pslot.ensure(sizeof(uint32_t) * size_t(P + 1)));
@@ -1234,42 +849,54 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
     CK(c->b_unita.ensure(sizeof(uint32_t) * size_t(U + 1)));
     CK(c->b_unitn.ensure(sizeof(uint32_t) * size_t(U + 1)));
     CK(c->b_unitmask.ensure(sizeof(uint64_t) * size_t(U + 1)));
-    CK(c->b_cv.ensure(sizeof(int64_t) * size_t(P + 1)));
-    CK(c->b_ca.ensure(sizeof(uint32_t) * size_t(P + 1)));
-    CK(c->b_crk.ensure(sizeof(uint32_t) * size_t(P + 1)));
     CK(c->b_bestpair.ensure(sizeof(uint32_t) * size_t(T + 1)));
   }
-  for (int k = 0; k < 2; k++) {
-    CK(c->b_ks[k].ensure(sizeof(uint64_t) * size_t(T + 1)));
-    CK(c->b_kv[k].ensure(sizeof(uint64_t) * size_t(T + 1)));
-    CK(c->b_ix[k].ensure(sizeof(uint32_t) * size_t(T + 1)));
+  if (on_chip_cta) CK(c->b_kv.ensure(sizeof(uint64_t) * size_t(T + 1)));  // k_plan_smem's scratch for value ranges above 32 bits
+  if (n_general > 0) {  // the general path's buffers exist only when a distro takes it
+    for (int k = 0; k < 2; k++) {
+      CK(c->b_klo[k].ensure(sizeof(uint32_t) * size_t(T + 1)));
+      CK(c->b_khi[k].ensure(sizeof(uint32_t) * size_t(T + 1)));
+      CK(c->b_ix[k].ensure(sizeof(uint32_t) * size_t(T + 1)));
+    }
+    CK(c->b_vmm.ensure(sizeof(uint64_t) * 2 * size_t(D + 1)));
+    CK(c->b_gmisc.ensure(64));
+    CK(c->b_tilesum.ensure(sizeof(uint32_t) * size_t(NT + 1)));
+    CK(c->b_tilehist.ensure(sizeof(uint32_t) * 256 * size_t(NT + 1)));
+    if (general_complex) {
+      CK(c->b_e.ensure(sizeof(uint32_t) * size_t(T + kColPad)));
+      CK(c->b_clist.ensure(sizeof(uint32_t) * size_t(Tgc + 1)));
+      CK(c->b_ca.ensure(sizeof(uint32_t) * size_t(T + 1)));
+      CK(c->b_crk.ensure(sizeof(uint32_t) * size_t(T + 1)));
+    }
   }
-  CK(c->b_bits.ensure(sizeof(uint64_t) * 4 * size_t(D + 1)));
-  CK(c->b_npass.ensure(sizeof(int32_t) * size_t(D + 1)));
-  CK(c->b_sched.ensure(size_t(kMaxPass) * size_t(D + 1)));
-  CK(c->b_maxpass.ensure(sizeof(int32_t) * 4));
-  CK(c->b_tilehist.ensure(sizeof(uint32_t) * 256 * size_t(NT + 1)));
+  CK(c->b_punt.ensure(sizeof(int32_t) * size_t(D + 1)));
+  CK(c->b_puntcnt.ensure(sizeof(int32_t) * (evg_ctx::kMaxChunks + 2)));
   CK(c->b_qinfo.ensure(sizeof(evg_queue_info) * size_t(D + 1)));
   CK(c->b_ginfo.ensure(sizeof(evg_group_info) * size_t(G + 1)));
   CK(c->b_order.ensure(sizeof(int32_t) * size_t(T + 1)));
-  CK(c->b_tv.ensure(sizeof(int64_t) * size_t(T + 1)));
+  CK(c->b_tv.ensure(sizeof(int64_t) * size_t(T + kColPad)));
   c->T = T; c->E = E; c->G = G; c->U = U; c->NT = NT; c->Dn = D;
+  c->t_pad = (T + 3) & ~int64_t(3);
+  c->adopted = adopt;
+  c->Tgc = Tgc;
   c->max_groups = 0;
   for (int32_t d = 0; d < D; d++) c->max_groups = std::max(c->max_groups, dt->group_off[d + 1] - dt->group_off[d]);
   c->any_complex = any_complex;
   c->nW = int32_t(listW.size());
   c->nA = int32_t(listA.size()); c->nB = int32_t(listB.size()); c->nC = int32_t(listC.size());
+  c->nNA = int32_t(listNA.size()); c->nNB = int32_t(listNB.size()); c->nNC = int32_t(listNC.size());
   c->n_general = n_general;
   c->general_complex = general_complex;
   CK(c->b_err.ensure(sizeof(int) * 4));
   CK(cudaMemsetAsync(c->b_err.p, 0, sizeof(int) * 4, s));
   c->h_listW.swap(listW);
   c->h_listA.swap(listA); c->h_listB.swap(listB); c->h_listC.swap(listC);
+  c->h_listNA.swap(listNA); c->h_listNB.swap(listNB); c->h_listNC.swap(listNC);
   c->h_taskoff.assign(dt->task_off, dt->task_off + D + 1);
   c->h_groupoff.assign(dt->group_off, dt->group_off + D + 1);
   c->have_tasks = true;
   c->have_hosts = false;
-  if (copy_columns && T > 0) {  // range-check the ids the kernels index with (the pipelined call checks chunk by chunk)
+  if ((copy_columns || adopt) && T > 0) {  // range-check the ids the kernels index with (the pipelined call checks chunk by chunk)
     DTasks dtv = dtasks(c);
     DDistros ddv = ddistros(c);
     DWork wv = dwork(c);
@@ -1283,10 +910,11 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
 }
 
 int upload_hosts(evg_ctx* c, const evg_host_soa* h, const int64_t* host_off, const evg_alloc_cfg* acfg, int32_t D) {
-  if (!h || !acfg) return fail(EVG_ERR_INVALID, "null host table / allocator config");
+  if (!h || (D > 0 && !acfg)) return fail(EVG_ERR_INVALID, "null host table / allocator config");
   const int64_t H = h->n_hosts;
   if (H < 0) return fail(EVG_ERR_INVALID, "negative n_hosts");
   if (D > 0 && !host_off) return fail(EVG_ERR_INVALID, "null host_off");
+  if (D == 0 && H != 0) return fail(EVG_ERR_INVALID, "hosts without distros");
   for (int32_t d = 0; d < D; d++)
     if (host_off[d + 1] < host_off[d] || (d == 0 && host_off[0] != 0)) return fail(EVG_ERR_INVALID, "bad host_off at distro %d", d);
   if (D > 0 && host_off[D] != H) return fail(EVG_ERR_INVALID, "host_off[n_distros] != n_hosts");
@@ -1297,7 +925,7 @@ int upload_hosts(evg_ctx* c, const evg_host_soa* h, const int64_t* host_off, con
   UP(c->b_hexp, h->expected_ns, H, int64_t);
   UP(c->b_hstd, h->std_ns, H, int64_t);
   UP(c->b_hstart, h->start_ns, H, int64_t);
-  UP(c->b_hostoff, host_off, D + 1, int64_t);
+  if (D > 0) UP(c->b_hostoff, host_off, D + 1, int64_t);
   UP(c->b_acfg, acfg, D, evg_alloc_cfg);
   CK(c->b_result.ensure(sizeof(evg_alloc_result) * size_t(D + 1)));
   CK(c->b_status.ensure(sizeof(int32_t) * size_t(D + 1)));
@@ -1331,70 +959,148 @@ DWork dwork(const evg_ctx* c) {
   w.err = c->b_err.as<int>();
   w.unit_v = c->b_unitv.as<int64_t>(); w.unit_a = c->b_unita.as<uint32_t>(); w.unit_n = c->b_unitn.as<uint32_t>();
   w.unit_mask = c->b_unitmask.as<unsigned long long>();
-  w.cand_v = c->b_cv.as<int64_t>(); w.cand_a = c->b_ca.as<uint32_t>();
-  w.cand_rk = c->b_crk.as<uint32_t>(); w.best_pair = c->b_bestpair.as<uint32_t>();
-  for (int k = 0; k < 2; k++) {
-    w.buf[k].key_s = c->b_ks[k].as<uint64_t>(); w.buf[k].key_v = c->b_kv[k].as<uint64_t>(); w.buf[k].idx = c->b_ix[k].as<uint32_t>();
-  }
-  w.bits = c->b_bits.as<unsigned long long>(); w.npass = c->b_npass.as<int32_t>(); w.sched = c->b_sched.as<uint8_t>();
-  w.maxpass = c->b_maxpass.as<int32_t>();
-  w.tile_distro = c->b_tiledistro.as<int32_t>(); w.tile_start = c->b_tilestart.as<int64_t>();
-  w.dtile_off = c->b_dtileoff.as<int64_t>(); w.tile_hist = c->b_tilehist.as<uint32_t>();
+  w.best_pair = c->b_bestpair.as<uint32_t>();
+  w.buf[0].key_v = c->b_kv.as<uint64_t>();
   w.qinfo = c->b_qinfo.as<evg_queue_info>(); w.ginfo = c->b_ginfo.as<evg_group_info>();
   return w;
 }
+DGen dgen(const evg_ctx* c) {
+  DGen g;
+  g.n_tiles = c->NT;
+  g.tile_distro = c->b_tiledistro.as<int32_t>(); g.tile_start = c->b_tilestart.as<int64_t>();
+  g.dtile_off = c->b_dtileoff.as<int64_t>();
+  g.vmm = c->b_vmm.as<unsigned long long>();
+  for (int k = 0; k < 2; k++) {
+    g.key_lo[k] = c->b_klo[k].as<uint32_t>(); g.key_hi[k] = c->b_khi[k].as<uint32_t>(); g.idx[k] = c->b_ix[k].as<uint32_t>();
+  }
+  g.e = c->b_e.as<uint32_t>(); g.tile_sum = c->b_tilesum.as<uint32_t>(); g.tile_hist = c->b_tilehist.as<uint32_t>();
+  g.clist = c->b_clist.as<uint32_t>();
+  g.ccount = c->b_gmisc.as<unsigned int>();
+  g.maxpass = c->b_gmisc.as<int32_t>() + 1;
+  g.tie_a = c->b_ca.as<uint32_t>(); g.tie_r = c->b_crk.as<uint32_t>();
+  g.tv = c->b_tv.as<int64_t>();
+  return g;
+}
 
-#define LAUNCH(c, kernel, grid, block, ...)                                  \
+#define LOCK(c) std::lock_guard<std::recursive_mutex> lock_((c)->mu)
+#define LAUNCH_ON(c, st, kernel, grid, block, ...)                           \
   do {                                                                       \
     if ((grid) > 0) {                                                        \
-      kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);              \
+      kernel<<<(grid), (block), 0, (st)>>>(__VA_ARGS__);                     \
       (c)->launches++;                                                       \
     }                                                                        \
   } while (0)
+#define LAUNCH(c, kernel, grid, block, ...) LAUNCH_ON(c, (c)->stream, kernel, grid, block, __VA_ARGS__)
 
-int run_alloc(evg_ctx* c, int64_t now) {
+int run_alloc_range(evg_ctx* c, int64_t now, int32_t d0, int32_t d1) {
   DHosts h;
   h.n = c->H; h.flags = c->b_hflags.as<uint32_t>(); h.gid = c->b_hgid.as<int32_t>();
   h.expected = c->b_hexp.as<int64_t>(); h.stddev = c->b_hstd.as<int64_t>(); h.start = c->b_hstart.as<int64_t>();
   h.host_off = c->b_hostoff.as<int64_t>(); h.cfg = c->b_acfg.as<evg_alloc_cfg>();
   if (c->ext_result && c->ext_capacity < c->Dn) return fail(EVG_ERR_INVALID, "bound result buffer holds %lld rows, need %d", (long long)c->ext_capacity, c->Dn);
   CK(c->b_gs.ensure(sizeof(GroupScratch) * size_t(c->G + 1)));
+  // a warp per distro (four per block) unless some distro has thousands of task groups, then a block per distro
   if (c->max_groups > kWideAllocGroups)
-    LAUNCH(c, k_alloc<128>, unsigned(c->Dn), 128, h, 0, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
+    LAUNCH(c, k_alloc<128>, unsigned(d1 - d0), 128, h, d0, d1, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
            c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>());
   else
-  LAUNCH(c, k_alloc<32>, grid_for(c->Dn, 4), 128, h, 0, c->Dn, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
-         c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>());
+    LAUNCH(c, k_alloc<32>, grid_for(d1 - d0, 4), 128, h, d0, d1, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
+           c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>());
   CK(cudaGetLastError());
   return EVG_OK;
 }
+int run_alloc(evg_ctx* c, int64_t now) { return run_alloc_range(c, now, 0, c->Dn); }
 
 template <int THREADS, int ITEMS, int MIN_CTAS>
-int launch_smem(evg_ctx* c, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n, int64_t now,
-                int lists_needed = 0) {
+int launch_smem(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n,
+                int64_t now, int lists_needed = 0, const int32_t* list_count = nullptr) {
   if (n <= 0) return EVG_OK;
   const size_t bytes = PlanSmem<THREADS, ITEMS>::kBytes;
   CK(cudaFuncSetAttribute(k_plan_smem<THREADS, ITEMS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
-  k_plan_smem<THREADS, ITEMS, MIN_CTAS><<<unsigned(n), THREADS, bytes, c->stream>>>(dt, dd, w, list, now, lists_needed,
+  k_plan_smem<THREADS, ITEMS, MIN_CTAS><<<unsigned(n), THREADS, bytes, st>>>(dt, dd, w, list, list_count, now, lists_needed,
                                                                           c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
+  c->launches++;
+  return EVG_OK;
+}
+
+// Second-generation on-chip planner for one class; distros it hands back land in punt_list[0 .. *punt_count).
+template <int THREADS, int CAP, int OCC>
+int launch_cta(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n,
+               int64_t now, int32_t* punt_list, int32_t* punt_count) {
+  if (n <= 0) return EVG_OK;
+  const size_t bytes = PlanCta<THREADS, CAP>::kBytes;
+  CK(cudaFuncSetAttribute(k_plan_cta<THREADS, CAP, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+  k_plan_cta<THREADS, CAP, OCC><<<unsigned(n), THREADS, bytes, st>>>(dt, dd, w, list, now, c->t_pad, c->b_order.as<int32_t>(),
+                                                                  c->b_tv.as<int64_t>(), punt_list, punt_count);
   c->launches++;
   return EVG_OK;
 }
 
 // Distros of at most 32 tasks: one warp each (k_plan_warp).  Breakdown mode needs the unit lists, so it
 // sends them through the smallest on-chip class instead.
-int launch_tiny(evg_ctx* c, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n, int64_t now,
-                int lists_needed) {
+int launch_tiny(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& dd, const DWork& w, const int32_t* list, int32_t n,
+                int64_t now, int lists_needed) {
   if (n <= 0) return EVG_OK;
-  if (lists_needed) return launch_smem<128, 8, 8>(c, dt, dd, w, list, n, now, 1);
-  k_plan_warp<<<grid_for(int64_t(n) * 32, 256), 256, 0, c->stream>>>(dt, dd, w, list, n, now, c->b_order.as<int32_t>(),
-                                                                  c->b_tv.as<int64_t>());
+  if (lists_needed) return launch_smem<128, 8, 8>(c, st, dt, dd, w, list, n, now, 1);
+  k_plan_warp<<<grid_for(int64_t(n) * 32, 256), 256, 0, st>>>(dt, dd, w, list, n, now, c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
   c->launches++;
   return EVG_OK;
 }
 
+// The general path of one tick on stream `st` (evg_plan_general.cuh).
+int run_general(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& dd, const DWork& w, int64_t now) {
+  const int64_t T = c->T, P = 2 * T + c->E;
+  const int32_t D = c->Dn;
+  const DGen g = dgen(c);
+  const int gc = c->general_complex;
+  const unsigned nt = unsigned(c->NT);
+  const int32_t* gl = c->b_listG.as<int32_t>();
+  CK(cudaMemsetAsync(c->b_qinfo.p, 0, sizeof(evg_queue_info) * size_t(D + 1), st));   // general distros accumulate with atomics;
+  CK(cudaMemsetAsync(c->b_ginfo.p, 0, sizeof(evg_group_info) * size_t(c->G + 1), st));  // on-chip planners write their own rows whole
+  if (gc) {
+    CK(cudaMemsetAsync(c->b_hasdep.p, 0, size_t(T) + 16, st));
+    CK(cudaMemsetAsync(c->b_head.p, 0xFF, sizeof(uint32_t) * size_t(c->U + 1), st));
+    CK(cudaMemsetAsync(c->b_next.p, 0xFF, sizeof(uint32_t) * size_t(P + 1), st));
+    CK(cudaMemsetAsync(c->b_unitmask.p, 0, sizeof(uint64_t) * size_t(c->U + 1), st));
+  }
+  LAUNCH_ON(c, st, k_ginit, grid_for(c->n_general, 256), 256, g, gl, c->n_general);
+  if (gc && c->E > 0) LAUNCH_ON(c, st, k_gmark, nt, 256, dt, dd, w, g);
+  if (c->timed) CK(cudaEventRecord(c->ev_gt0, st));
+  LAUNCH_ON(c, st, k_gtask, nt, 256, dt, dd, w, g, now, gc);
+  if (c->timed) { CK(cudaEventRecord(c->ev_gt1, st)); c->general_timed = true; }
+  const unsigned wl_grid = unsigned(std::min<int64_t>(std::max<int64_t>(1, (c->Tgc + 255) / 256), 148 * 16));
+  if (gc) LAUNCH_ON(c, st, k_gcomplex, wl_grid, 256, dt, dd, w, g, now);
+  LAUNCH_ON(c, st, k_gsched, grid_for(c->n_general, 128), 128, g, gl, c->n_general);
+  if (gc) {
+    LAUNCH_ON(c, st, k_gsum, nt, 256, dd, g);
+    LAUNCH_ON(c, st, k_gscan, unsigned(c->n_general), 1024, g, gl);
+  }
+  LAUNCH_ON(c, st, k_gplace, nt, 256, dd, w, g, gc);
+  if (gc) LAUNCH_ON(c, st, k_gplace_disp, wl_grid, 256, dt, dd, w, g);
+  if (c->timed) CK(cudaEventRecord(c->ev_sort0, st));  // the general path's segmented sort
+  for (int j = 0; j < 8; j++) {  // passes beyond the tick's longest key exit at once (*maxpass is device-side)
+    LAUNCH_ON(c, st, k_ghist, nt, 256, j, dd, g);
+    LAUNCH_ON(c, st, k_gdscan, unsigned(c->n_general), 1024, j, gl, g);
+    LAUNCH_ON(c, st, k_gscatter, nt, 256, j, dd, g);
+  }
+  if (c->timed) CK(cudaEventRecord(c->ev_sort1, st));
+  LAUNCH_ON(c, st, k_gemit, nt, 256, dd, g, c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
+  LAUNCH_ON(c, st, k_finalize_info, grid_for(std::max<int64_t>(D, c->G), 256), 256, dd, w, c->G);
+  return EVG_OK;
+}
+
+int ensure_aux_streams(evg_ctx* c) {
+  if (c->ev_fork) return EVG_OK;
+  for (int k = 0; k < evg_ctx::kAux; k++) {
+    CK(cudaStreamCreateWithFlags(&c->s_aux[k], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  return EVG_OK;
+}
+
 int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
-  const int64_t T = c->T, E = c->E, P = 2 * T + E;
+  const int64_t T = c->T;
   const int32_t D = c->Dn;
   cudaStream_t s = c->stream;
   DTasks dt = dtasks(c);
@@ -1407,54 +1113,65 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
     bd = c->b_bd.as<int64_t>();
     c->bd_valid = true;
   }
-  const bool general = c->n_general > 0;
-  if (general) CK(cudaMemsetAsync(c->b_qinfo.p, 0, sizeof(evg_queue_info) * size_t(D + 1), s));
-  if (general) CK(cudaMemsetAsync(c->b_ginfo.p, 0, sizeof(evg_group_info) * size_t(c->G + 1), s));  // on-chip planners zero their own rows
   c->sort_slot = -1;
   if (D == 0) {
     if (c->timed) { CK(cudaEventRecord(c->ev_sort0, s)); CK(cudaEventRecord(c->ev_sort1, s)); }
     return EVG_OK;
   }
-  if (general) {
-    CK(cudaMemsetAsync(c->b_maxpass.p, 0, sizeof(int32_t) * 4, s));
-    if (c->general_complex) {
-      CK(cudaMemsetAsync(c->b_hasdep.p, 0, size_t(T) + 1, s));
-      CK(cudaMemsetAsync(c->b_head.p, 0xFF, sizeof(uint32_t) * size_t(c->U + 1), s));
-      CK(cudaMemsetAsync(c->b_next.p, 0xFF, sizeof(uint32_t) * size_t(P + 1), s));
-    }
-  }
-  // on-chip planner: one CTA per distro, three capacity classes
+  const bool general = c->n_general > 0;
   // breakdown mode reads best_pair for every task: tasks emitted from their own single-task unit keep kInactive
   if (bd && c->any_complex) CK(cudaMemsetAsync(c->b_bestpair.p, 0xFF, sizeof(uint32_t) * size_t(T + 1), s));
+  const int32_t n_new = bd ? 0 : c->nNA + c->nNB + c->nNC;
+  if (n_new > 0) CK(cudaMemsetAsync(c->b_puntcnt.p, 0, sizeof(int32_t), s));
+  // Routes run side by side when the tick has more than one: fork the aux streams off the context stream here, join
+  // them before returning (the allocator and the caller's later work are ordered behind every planner kernel).
+  struct Route { int id; int64_t weight; };
+  const int64_t routes_present = (c->nW > 0) + (c->nA > 0) + (c->nB > 0) + (c->nC > 0) + (n_new > 0 || (bd && (c->nNA + c->nNB + c->nNC) > 0)) + (general ? 1 : 0);
+  const bool fork = routes_present > 1;
+  if (fork) {
+    int rc0 = ensure_aux_streams(c);
+    if (rc0 != EVG_OK) return rc0;
+    CK(cudaEventRecord(c->ev_fork, s));
+    for (int k = 0; k < evg_ctx::kAux; k++) CK(cudaStreamWaitEvent(c->s_aux[k], c->ev_fork, 0));
+  }
+  auto st = [&](int k) { return fork ? c->s_aux[k] : s; };
   int rc;
   const int slot = int(c->runs % evg_ctx::kRing);
-  if (c->timed) CK(cudaEventRecord(c->ring0[slot], s));
-  if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now, bd ? 1 : 0)) != EVG_OK) return rc;
-  if (c->timed) { CK(cudaEventRecord(c->ring1[slot], s)); c->runs++; }
-  if (!general) c->sort_slot = slot;  // no general-path sort in this tick: the "dominant kernel" split is the ring pair
-  if ((rc = launch_smem<256, 16, 3>(c, dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now, bd ? 1 : 0)) != EVG_OK) return rc;
-  if ((rc = launch_smem<128, 8, 8>(c, dt, dd, w, c->b_listA.as<int32_t>(), c->nA, now, bd ? 1 : 0)) != EVG_OK) return rc;
-  if ((rc = launch_tiny(c, dt, dd, w, c->b_listW.as<int32_t>(), c->nW, now, bd ? 1 : 0)) != EVG_OK) return rc;
-  if (general) {
-    const int gc = c->general_complex;
-    if (gc && E > 0) LAUNCH(c, k_mark_dependents, grid_for(T, 256), 256, dt, dd, w);
-    LAUNCH(c, k_init_bits, grid_for(D, 256), 256, w.bits, D);
-    LAUNCH(c, k_task, grid_for(T, 256), 256, dt, dd, w, now, gc);
-    if (gc) {
-      LAUNCH(c, k_unit, grid_for(P, 256), 256, dt, dd, w, now, P);
-      LAUNCH(c, k_best, grid_for(T, 256), 256, dt, dd, w);
+  // --- stream 0: the second-generation on-chip planner (the dominant kernel of configs[1]-like ticks), then the
+  //     distros it handed back
+  if (bd) {  // breakdown needs the unit lists: every on-chip distro goes through k_plan_smem (its largest class holds them all)
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, c->b_listNC.as<int32_t>(), c->nNC, now, 1)) != EVG_OK) return rc;
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, c->b_listNB.as<int32_t>(), c->nNB, now, 1)) != EVG_OK) return rc;
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, c->b_listNA.as<int32_t>(), c->nNA, now, 1)) != EVG_OK) return rc;
+  } else if (n_new > 0) {
+    int32_t* pl = c->b_punt.as<int32_t>();
+    int32_t* pc = c->b_puntcnt.as<int32_t>();
+    const bool time_it = c->timed && !general && c->nNC > 0;
+    if (time_it) CK(cudaEventRecord(c->ring0[slot], st(0)));
+    if ((rc = launch_cta<kNT_C, kNCapC, kNOccC>(c, st(0), dt, dd, w, c->b_listNC.as<int32_t>(), c->nNC, now, pl, pc)) != EVG_OK) return rc;
+    if (time_it) { CK(cudaEventRecord(c->ring1[slot], st(0))); c->runs++; c->sort_slot = slot; }
+    if ((rc = launch_cta<kNT_B, kNCapB, kNOccB>(c, st(0), dt, dd, w, c->b_listNB.as<int32_t>(), c->nNB, now, pl, pc)) != EVG_OK) return rc;
+    if ((rc = launch_cta<kNT_A, kNCapA, kNOccA>(c, st(0), dt, dd, w, c->b_listNA.as<int32_t>(), c->nNA, now, pl, pc)) != EVG_OK) return rc;
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, pl, n_new, now, 0, pc)) != EVG_OK) return rc;
+  }
+  // --- streams 1..3: first-generation classes (GroupVersions, in-queue dependency edges, very many task groups)
+  {
+    const bool time_it = c->timed && !general && c->sort_slot < 0 && c->nC > 0;
+    if (time_it) CK(cudaEventRecord(c->ring0[slot], st(1)));
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(1), dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now, bd ? 1 : 0)) != EVG_OK) return rc;
+    if (time_it) { CK(cudaEventRecord(c->ring1[slot], st(1))); c->runs++; c->sort_slot = slot; }
+  }
+  if ((rc = launch_smem<256, 16, 3>(c, st(2), dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now, bd ? 1 : 0)) != EVG_OK) return rc;
+  if ((rc = launch_smem<128, 8, 8>(c, st(3), dt, dd, w, c->b_listA.as<int32_t>(), c->nA, now, bd ? 1 : 0)) != EVG_OK) return rc;
+  // --- stream 4: one warp per tiny distro
+  if ((rc = launch_tiny(c, st(4), dt, dd, w, c->b_listW.as<int32_t>(), c->nW, now, bd ? 1 : 0)) != EVG_OK) return rc;
+  // --- stream 5: the general path
+  if (general && (rc = run_general(c, st(5), dt, dd, w, now)) != EVG_OK) return rc;
+  if (fork) {
+    for (int k = 0; k < evg_ctx::kAux; k++) {
+      CK(cudaEventRecord(c->ev_join[k], c->s_aux[k]));
+      CK(cudaStreamWaitEvent(s, c->ev_join[k], 0));
     }
-    LAUNCH(c, k_sched, grid_for(D, 128), 128, dd, w, gc);
-    const int passes = gc ? kMaxPass : 8;
-    if (c->timed) CK(cudaEventRecord(c->ev_sort0, s));  // the general path's segmented sort
-    for (int j = 0; j < passes; j++) {
-      LAUNCH(c, k_sort_hist, unsigned(c->NT), 256, j, dd, w);
-      LAUNCH(c, k_sort_scan, unsigned(c->n_general), 1024, j, c->b_listG.as<int32_t>(), dd, w);
-      LAUNCH(c, k_sort_scatter, unsigned(c->NT), 256, j, dd, w);
-    }
-    if (c->timed) CK(cudaEventRecord(c->ev_sort1, s));
-    LAUNCH(c, k_emit, grid_for(T, 256), 256, dt, dd, w, c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
-    LAUNCH(c, k_finalize_info, grid_for(std::max<int64_t>(D, c->G), 256), 256, dd, w, c->G);
   }
   if (bd) LAUNCH(c, k_breakdown, grid_for(T, 256), 256, dt, dd, w, now, c->any_complex, c->b_order.as<int32_t>(), bd);
   CK(cudaGetLastError());
@@ -1488,6 +1205,7 @@ int evg_init(int device, void* stream, evg_ctx** out) {
   else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CK(cudaEventCreate(&c->ev_begin)); CK(cudaEventCreate(&c->ev_sort0));
   CK(cudaEventCreate(&c->ev_sort1)); CK(cudaEventCreate(&c->ev_end));
+  CK(cudaEventCreate(&c->ev_gt0)); CK(cudaEventCreate(&c->ev_gt1));
   for (int k = 0; k < evg_ctx::kRing; k++) { CK(cudaEventCreate(&c->ring0[k])); CK(cudaEventCreate(&c->ring1[k])); }
   *out = c;
   return EVG_OK;
@@ -1499,17 +1217,24 @@ void evg_shutdown(evg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->b_prio, &c->b_exp, &c->b_qb, &c->b_wb, &c->b_nd, &c->b_tgo, &c->b_gid, &c->b_vid, &c->b_flags,
                    &c->b_depoff, &c->b_depidx, &c->b_taskoff, &c->b_groupoff, &c->b_cfg, &c->b_gmax, &c->b_unitbase,
-                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita, &c->b_unitn, &c->b_unitmask, &c->b_rn0, &c->b_rn1, &c->b_rn2, &c->b_rn3, &c->b_rn4, &c->b_rn5, &c->b_rn6, &c->b_rn7, &c->b_err, &c->b_dx0, &c->b_dx1, &c->b_dx2, &c->b_dx3, &c->b_dx4, &c->b_dx5, &c->b_dx6, &c->b_dx7, &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_listG, &c->b_cv, &c->b_ca, &c->b_crk,
-                   &c->b_bestpair, &c->b_ks[0], &c->b_ks[1], &c->b_kv[0], &c->b_kv[1], &c->b_ix[0], &c->b_ix[1], &c->b_bits,
-                   &c->b_npass, &c->b_sched, &c->b_maxpass, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
+                   &c->b_hasdep, &c->b_head, &c->b_next, &c->b_pslot, &c->b_etask, &c->b_elive, &c->b_unitv, &c->b_unita,
+                   &c->b_unitn, &c->b_unitmask, &c->b_rn0, &c->b_rn1, &c->b_rn2, &c->b_rn3, &c->b_rn4, &c->b_rn5, &c->b_rn6,
+                   &c->b_rn7, &c->b_err, &c->b_dx0, &c->b_dx1, &c->b_dx2, &c->b_dx3, &c->b_dx4, &c->b_dx5, &c->b_dx6, &c->b_dx7,
+                   &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_listG, &c->b_listNA, &c->b_listNB,
+                   &c->b_listNC, &c->b_punt, &c->b_puntcnt, &c->b_ca, &c->b_crk, &c->b_bestpair, &c->b_kv, &c->b_vmm,
+                   &c->b_klo[0], &c->b_klo[1], &c->b_khi[0], &c->b_khi[1], &c->b_ix[0], &c->b_ix[1], &c->b_e, &c->b_tilesum,
+                   &c->b_gmisc, &c->b_clist, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
                    &c->b_hstart, &c->b_hostoff, &c->b_acfg, &c->b_gs, &c->b_result, &c->b_status};
   for (DevBuf* b : all) b->release();
   for (int k = 0; k < evg_ctx::kRing; k++) { if (c->ring0[k]) cudaEventDestroy(c->ring0[k]); if (c->ring1[k]) cudaEventDestroy(c->ring1[k]); }
   cudaEventDestroy(c->ev_begin); cudaEventDestroy(c->ev_sort0); cudaEventDestroy(c->ev_sort1); cudaEventDestroy(c->ev_end);
+  cudaEventDestroy(c->ev_gt0); cudaEventDestroy(c->ev_gt1);
   for (int k = 0; k < evg_ctx::kMaxChunks; k++) { if (c->ev_h[k]) cudaEventDestroy(c->ev_h[k]); if (c->ev_c[k]) cudaEventDestroy(c->ev_c[k]); }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  for (int k = 0; k < evg_ctx::kAux; k++) { if (c->s_aux[k]) cudaStreamDestroy(c->s_aux[k]); if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1517,6 +1242,7 @@ void evg_shutdown(evg_ctx* c) {
 int evg_upload(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* distros, const evg_host_soa* hosts,
                const int64_t* host_off, const evg_alloc_cfg* acfg) {
   if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
   CK(cudaSetDevice(c->device));
   int rc = upload_tasks(c, tasks, distros);
   if (rc != EVG_OK) return rc;
@@ -1528,12 +1254,47 @@ int evg_upload(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* di
   return EVG_OK;
 }
 
+__global__ void k_gather_i64(const int64_t* __restrict__ src, const int64_t* __restrict__ at, int64_t* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[at[i]];
+}
+
+int evg_upload_device(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* distros, const evg_host_soa* hosts,
+                      const int64_t* host_off, const evg_alloc_cfg* acfg) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
+  if (!tasks || !distros) return fail(EVG_ERR_INVALID, "null task table / distro table");
+  CK(cudaSetDevice(c->device));
+  std::vector<int64_t> edge_off;
+  const int32_t D = distros->n_distros;
+  if (tasks->n_edges > 0 && D > 0) {  // dep_off is device memory: sample it at the distro boundaries for the routing
+    if (!tasks->dep_off || !distros->task_off) return fail(EVG_ERR_INVALID, "null dep_off / task_off");
+    edge_off.resize(size_t(D) + 1);
+    CK(c->b_rn0.ensure(sizeof(int64_t) * size_t(D + 1)));
+    CK(c->b_rn1.ensure(sizeof(int64_t) * size_t(D + 1)));
+    CK(cudaMemcpyAsync(c->b_rn0.p, distros->task_off, sizeof(int64_t) * size_t(D + 1), cudaMemcpyHostToDevice, c->stream));
+    k_gather_i64<<<grid_for(D + 1, 256), 256, 0, c->stream>>>(tasks->dep_off, c->b_rn0.as<int64_t>(), c->b_rn1.as<int64_t>(), D + 1);
+    CK(cudaMemcpyAsync(edge_off.data(), c->b_rn1.p, sizeof(int64_t) * size_t(D + 1), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  int rc = upload_tasks(c, tasks, distros, /*copy_columns=*/false, /*adopt=*/true, edge_off.empty() ? nullptr : edge_off.data());
+  if (rc != EVG_OK) return rc;
+  if (hosts) {
+    rc = upload_hosts(c, hosts, host_off, acfg, distros->n_distros);
+    if (rc != EVG_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return EVG_OK;
+}
+
 int evg_run_resident(evg_ctx* c, int64_t now_ns, uint32_t opts) {
   if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
   if (!c->have_tasks) return fail(EVG_ERR_STATE, "evg_run_resident before evg_upload");
   CK(cudaSetDevice(c->device));
   c->launches = 0;
   c->timed = true;
+  c->general_timed = false;
   CK(cudaEventRecord(c->ev_begin, c->stream));
   int rc = run_plan(c, now_ns, opts);
   if (rc != EVG_OK) return rc;
@@ -1547,6 +1308,7 @@ int evg_run_resident(evg_ctx* c, int64_t now_ns, uint32_t opts) {
 
 int evg_download(evg_ctx* c, evg_plan_out* po, evg_alloc_out* ao) {
   if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
   if (!c->have_tasks) return fail(EVG_ERR_STATE, "evg_download before evg_upload");
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
@@ -1572,6 +1334,7 @@ int evg_download(evg_ctx* c, evg_plan_out* po, evg_alloc_out* ao) {
 void* evg_device_result_ptr(evg_ctx* c) { return c ? (void*)c->result_ptr() : nullptr; }
 int evg_bind_result_buffer(evg_ctx* c, void* device_ptr, int64_t capacity) {
   if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
   if (device_ptr && capacity < 0) return fail(EVG_ERR_INVALID, "negative capacity");
   c->ext_result = reinterpret_cast<evg_alloc_result*>(device_ptr);
   c->ext_capacity = device_ptr ? capacity : 0;
@@ -1581,6 +1344,7 @@ int64_t evg_last_launch_count(evg_ctx* c) { return c ? c->launches : 0; }
 
 int evg_last_timing_ms(evg_ctx* c, float* total_ms, float* sort_ms) {
   if (!c || !c->timed) return fail(EVG_ERR_STATE, "no timed run");
+  LOCK(c);
   CK(cudaSetDevice(c->device));
   CK(cudaEventSynchronize(c->ev_end));
   if (total_ms) CK(cudaEventElapsedTime(total_ms, c->ev_begin, c->ev_end));
@@ -1591,8 +1355,20 @@ int evg_last_timing_ms(evg_ctx* c, float* total_ms, float* sort_ms) {
   return EVG_OK;
 }
 
+int evg_general_timing_ms(evg_ctx* c, float* task_pass_ms, float* sort_ms) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
+  if (!c->timed || !c->general_timed) return fail(EVG_ERR_STATE, "the last timed run had no general-path distro");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventSynchronize(c->ev_end));
+  if (task_pass_ms) CK(cudaEventElapsedTime(task_pass_ms, c->ev_gt0, c->ev_gt1));
+  if (sort_ms) CK(cudaEventElapsedTime(sort_ms, c->ev_sort0, c->ev_sort1));
+  return EVG_OK;
+}
+
 int evg_kernel_timing_ms(evg_ctx* c, float* out_ms, int32_t n) {
   if (!c || !out_ms || n < 0) return fail(EVG_ERR_INVALID, "evg_kernel_timing_ms: bad argument");
+  LOCK(c);
   if (n > evg_ctx::kRing || n > c->runs) return fail(EVG_ERR_STATE, "only %lld timed runs recorded (ring of %d)", (long long)c->runs, evg_ctx::kRing);
   CK(cudaSetDevice(c->device));
   for (int32_t k = 0; k < n; k++) {
@@ -1605,6 +1381,8 @@ int evg_kernel_timing_ms(evg_ctx* c, float* out_ms, int32_t n) {
 
 int evg_plan_batch(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* distros, int64_t now_ns, uint32_t opts,
                    evg_plan_out* out) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
   int rc = evg_upload(c, tasks, distros, nullptr, nullptr, nullptr);
   if (rc != EVG_OK) return rc;
   rc = evg_run_resident(c, now_ns, opts);
@@ -1640,6 +1418,8 @@ static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg
   CK(c->b_gs.ensure(sizeof(GroupScratch) * size_t(c->G + 1)));
   c->launches = 0;
   c->timed = false;
+  c->bd_valid = false;
+  CK(cudaMemsetAsync(c->b_puntcnt.p, 0, sizeof(int32_t) * (evg_ctx::kMaxChunks + 2), s));
   // chunk boundaries: whole distros, about equal task counts
   const int n_chunks = int(std::min<int64_t>(evg_ctx::kMaxChunks, std::max<int64_t>(1, T / (1 << 20))));
   std::vector<int32_t> cut(size_t(n_chunks) + 1, D);
@@ -1685,17 +1465,25 @@ static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg
     CK(cudaStreamWaitEvent(s, c->ev_h[k], 0));
     k_validate<<<grid_for(n, 256), 256, 0, s>>>(dtk, dd, w, t0, t0 + n);
     int32_t first, cnt;
+    {  // second-generation on-chip classes; the distros they hand back are replanned by k_plan_smem right behind them
+      int32_t fC, fB, fA;
+      const int32_t nC = sub(c->h_listNC, d0, d1, &fC), nB = sub(c->h_listNB, d0, d1, &fB), nA = sub(c->h_listNA, d0, d1, &fA);
+      int32_t* pl = c->b_punt.as<int32_t>() + d0;  // a chunk hands back at most its own d1 - d0 distros
+      int32_t* pc = c->b_puntcnt.as<int32_t>() + 1 + k;
+      if ((rc = launch_cta<kNT_C, kNCapC, kNOccC>(c, s, dtk, dd, w, c->b_listNC.as<int32_t>() + fC, nC, now, pl, pc)) != EVG_OK) return rc;
+      if ((rc = launch_cta<kNT_B, kNCapB, kNOccB>(c, s, dtk, dd, w, c->b_listNB.as<int32_t>() + fB, nB, now, pl, pc)) != EVG_OK) return rc;
+      if ((rc = launch_cta<kNT_A, kNCapA, kNOccA>(c, s, dtk, dd, w, c->b_listNA.as<int32_t>() + fA, nA, now, pl, pc)) != EVG_OK) return rc;
+      if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, s, dtk, dd, w, pl, nC + nB + nA, now, 0, pc)) != EVG_OK) return rc;
+    }
     cnt = sub(c->h_listC, d0, d1, &first);
-    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, dtk, dd, w, c->b_listC.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, s, dtk, dd, w, c->b_listC.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
     cnt = sub(c->h_listB, d0, d1, &first);
-    if ((rc = launch_smem<256, 16, 3>(c, dtk, dd, w, c->b_listB.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
+    if ((rc = launch_smem<256, 16, 3>(c, s, dtk, dd, w, c->b_listB.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
     cnt = sub(c->h_listA, d0, d1, &first);
-    if ((rc = launch_smem<128, 8, 8>(c, dtk, dd, w, c->b_listA.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
+    if ((rc = launch_smem<128, 8, 8>(c, s, dtk, dd, w, c->b_listA.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
     cnt = sub(c->h_listW, d0, d1, &first);
-    if ((rc = launch_tiny(c, dtk, dd, w, c->b_listW.as<int32_t>() + first, cnt, now, 0)) != EVG_OK) return rc;
-    LAUNCH(c, k_alloc<32>, grid_for(d1 - d0, 4), 128, h, d0, d1, c->b_groupoff.as<int64_t>(),
-           c->b_qinfo.as<evg_queue_info>(), c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now,
-           c->result_ptr(), c->b_status.as<int32_t>());
+    if ((rc = launch_tiny(c, s, dtk, dd, w, c->b_listW.as<int32_t>() + first, cnt, now, 0)) != EVG_OK) return rc;
+    if ((rc = run_alloc_range(c, now, d0, d1)) != EVG_OK) return rc;
     CK(cudaEventRecord(c->ev_c[k], s));
     CK(cudaStreamWaitEvent(c->s_d2h, c->ev_c[k], 0));
     if (po) {
@@ -1724,8 +1512,9 @@ static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg
 int evg_plan_and_alloc_batch(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* distros,
                              const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg, int64_t now_ns,
                              uint32_t opts, evg_plan_out* plan_out, evg_alloc_out* alloc_out) {
-  if (!hosts || !acfg) return fail(EVG_ERR_INVALID, "evg_plan_and_alloc_batch needs hosts and allocator config");
   if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
+  if (!hosts || (!acfg && distros && distros->n_distros > 0)) return fail(EVG_ERR_INVALID, "evg_plan_and_alloc_batch needs hosts and allocator config");
   if (!(opts & EVG_OPT_BREAKDOWN) && tasks && distros && tasks->n_tasks >= (int64_t(1) << 21)) {
     // large tick: stage the small tables, then pipeline the columns chunk by chunk
     CK(cudaSetDevice(c->device));
@@ -1749,6 +1538,7 @@ int evg_alloc_batch(evg_ctx* c, const evg_host_soa* hosts, const int64_t* host_o
                     const evg_queue_info* info, evg_group_info* groups, const int64_t* group_off, int32_t n_distros,
                     int64_t now_ns, evg_alloc_out* out) {
   if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
   if (n_distros < 0 || (n_distros > 0 && (!info || !group_off || !out))) return fail(EVG_ERR_INVALID, "evg_alloc_batch: null argument");
   CK(cudaSetDevice(c->device));
   const int64_t G = n_distros > 0 ? group_off[n_distros] : 0;
@@ -1815,6 +1605,7 @@ static int deps_to_device(evg_ctx* c, const evg_deps_in* in, int both) {
 
 int evg_deps_met_batch(evg_ctx* c, const evg_deps_in* in, uint8_t* met) {
   if (!c || !in || (in->n_tasks > 0 && !met)) return fail(EVG_ERR_INVALID, "evg_deps_met_batch: null argument");
+  LOCK(c);
   if (in->n_tasks == 0) return EVG_OK;
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
@@ -1833,6 +1624,7 @@ int evg_deps_met_batch(evg_ctx* c, const evg_deps_in* in, uint8_t* met) {
 
 int evg_expected_durations_batch(evg_ctx* c, const evg_duration_rows* in, evg_duration_stat* out) {
   if (!c || !in) return fail(EVG_ERR_INVALID, "evg_expected_durations_batch: null argument");
+  LOCK(c);
   const int64_t R = in->n_rows;
   const int32_t K = in->n_keys;
   if (R < 0 || K < 0) return fail(EVG_ERR_INVALID, "negative sizes");
@@ -1881,6 +1673,7 @@ int evg_expected_durations_batch(evg_ctx* c, const evg_duration_rows* in, evg_du
 
 int evg_find_runnable_batch(evg_ctx* c, const evg_runnable_in* in, int32_t* runnable, int64_t* count) {
   if (!c || !in) return fail(EVG_ERR_INVALID, "evg_find_runnable_batch: null argument");
+  LOCK(c);
   const int64_t T = in->n_tasks;
   const int32_t D = in->n_distros, P = in->n_projects;
   if (T < 0 || D < 0 || P < 0) return fail(EVG_ERR_INVALID, "negative sizes");

@@ -290,6 +290,51 @@ EVG_HD int64_t single_task_value_fast(const PlannerFactors& f, int64_t now, int3
   return wadd(wmul(prio, rank), 1);
 }
 
+// 32-bit form of single_task_value_fast: when, in addition to the straight-line domain, every planner factor is
+// below 2^14 (config_scheduler.go:132-159 validates them to 0..100) and the task's priority and NumDependents are
+// below 2^15, every intermediate fits 32 bits:
+//   prio = (1 + p) * gen + 200            < 2^15 * 2^14 + 200     < 2^30
+//   rank = 1 + f*qty + f + nd*d + rt*min  < 1 + 2^29 + 2^14 + 2^29 + 2^29 < 2^31
+// so TotalValue = prio * rank + 1 is ONE 32x32->64 multiply-add and cannot wrap.  Same integer as unit_value
+// (tests/native/score_fastpath_check.cpp compares them); everything else takes the 64-bit forms above.
+constexpr int64_t kFactor32Limit = int64_t(1) << 14;
+constexpr uint32_t kTask32Limit = 1u << 15;
+struct Factors32 {
+  uint32_t patch, patch_tiq, commit_queue, mainline_tiq, runtime, generate, stepback, nd;
+  uint32_t ok;  // distro-wide preconditions hold (clock non-negative, all factors small, integral NumDependentsFactor)
+};
+EVG_HD Factors32 factors32(const PlannerFactors& f, int64_t now) {
+  Factors32 g;
+  g.patch = uint32_t(f.patch); g.patch_tiq = uint32_t(f.patch_tiq); g.commit_queue = uint32_t(f.commit_queue);
+  g.mainline_tiq = uint32_t(f.mainline_tiq); g.runtime = uint32_t(f.runtime); g.generate = uint32_t(f.generate);
+  g.stepback = uint32_t(f.stepback); g.nd = uint32_t(f.nd_int);
+  g.ok = now >= 0 && f.nd_int != 0 && f.nd_int < kFactor32Limit && f.patch < kFactor32Limit && f.patch_tiq < kFactor32Limit &&
+         f.commit_queue < kFactor32Limit && f.mainline_tiq < kFactor32Limit && f.runtime < kFactor32Limit &&
+         f.generate < kFactor32Limit && f.stepback < kFactor32Limit;
+  return g;
+}
+// per-task part of the domain (requires Factors32::ok): score_fast_domain plus small priority / dependents
+EVG_HD bool score32_domain(int64_t now, int32_t priority, int32_t num_dependents, int64_t expected_ns, int64_t queue_basis_ns) {
+  return score_fast_domain(now, expected_ns, queue_basis_ns) && priority < int32_t(kTask32Limit) &&
+         num_dependents < int32_t(kTask32Limit);
+}
+EVG_HD uint64_t single_task_value32(const Factors32& f, int64_t now, int32_t priority, int64_t expected_ns,
+                                    int64_t queue_basis_ns, int32_t num_dependents, uint32_t tflags) {
+  const uint32_t req = tflags & EVG_TF_REQ_MASK;
+  const bool mq = req == EVG_TF_REQ_MERGE_QUEUE, pat = req == EVG_TF_REQ_PATCH;
+  const uint64_t tiq = queue_basis_ns == EVG_TIME_ZERO ? 0ull : uint64_t(now - queue_basis_ns);
+  const uint32_t p = 1u + uint32_t(priority > 0 ? priority : 0);
+  const uint32_t prio = p * ((tflags & EVG_TF_GENERATE) ? f.generate : 1u) + (mq ? 200u : 0u);
+  const uint64_t left = tiq < uint64_t(kWeek) ? uint64_t(kWeek) - tiq : 0ull;  // mainline: what is left of the first week
+  const uint32_t mins = uint32_t((pat ? tiq : left) / uint64_t(kMinute));
+  const uint32_t qty = pat ? mins : mins / 60u;  // patch: whole minutes waited; mainline: whole hours left
+  uint32_t term = (pat ? f.patch_tiq : f.mainline_tiq) * qty + (pat ? f.patch : ((tflags & EVG_TF_STEPBACK) ? f.stepback : 0u));
+  if (mq) term = f.commit_queue;
+  const uint32_t rank = 1u + term + f.nd * uint32_t(num_dependents > 0 ? num_dependents : 0) +
+                        f.runtime * uint32_t(uint64_t(expected_ns) / uint64_t(kMinute));
+  return uint64_t(prio) * uint64_t(rank) + 1ull;
+}
+
 // Sort-key encoding: ascending unsigned order of enc_value(v) == descending v.
 EVG_HD uint64_t enc_value(int64_t v) { return ~(uint64_t(v) ^ 0x8000000000000000ULL); }
 EVG_HD int64_t dec_value(uint64_t k) { return int64_t((~k) ^ 0x8000000000000000ULL); }

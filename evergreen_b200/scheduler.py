@@ -112,6 +112,23 @@ class Engine:
         self._n_tasks, self._n_distros, self._n_groups = tasks.n_tasks, distros.n_distros, distros.n_groups
         self._has_hosts = hosts is not None
 
+    def upload_device(self, cols: dict, n_tasks: int, distros: S.DistroTable, hosts: Optional[S.HostSoA] = None,
+                      n_edges: int = 0) -> None:
+        """evg_upload_device: the task columns already live in device memory.  `cols` maps the evg_task_soa column
+        names to device addresses (16-byte aligned, readable 8 rows past the end); nothing is copied, the caller
+        keeps the memory alive until the next upload."""
+        ts = L.TaskSoAStruct(int(n_tasks), int(n_edges), *[cols.get(name) for name, _ in S.TaskSoA.COLUMNS],
+                             cols.get("dep_off"), cols.get("dep_idx"))
+        ds = distros.struct()
+        if hosts is not None:
+            hs = hosts.struct()
+            L.check(self.lib.evg_upload_device(self.ctx, C.byref(ts), C.byref(ds), C.byref(hs), L.ptr(hosts.host_off),
+                                               L.ptr(hosts.cfg) if hosts.cfg.shape[0] else None))
+        else:
+            L.check(self.lib.evg_upload_device(self.ctx, C.byref(ts), C.byref(ds), None, None, None))
+        self._n_tasks, self._n_distros, self._n_groups = int(n_tasks), distros.n_distros, distros.n_groups
+        self._has_hosts = hosts is not None
+
     def run(self, now: int, opts: int = 0) -> None:
         L.check(self.lib.evg_run_resident(self.ctx, int(now), int(opts)))
 
@@ -146,6 +163,12 @@ class Engine:
         a, b = C.c_float(), C.c_float()
         L.check(self.lib.evg_last_timing_ms(self.ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def general_timing_ms(self) -> Tuple[float, float]:
+        """(k_gtask ms, segmented sort ms) of the last resident run; raises when it had no general-path distro."""
+        a, b = C.c_float(), C.c_float()
+        L.check(self.lib.evg_general_timing_ms(self.ctx, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
 
     def kernel_timing_ms(self, n: int):
         """Per-run device time of the dominant kernel (k_plan_smem<1024,12>) for the last n resident runs."""

@@ -273,6 +273,13 @@ int evg_plan_and_alloc_batch(evg_ctx* ctx, const evg_task_soa* tasks, const evg_
  * may be NULL for planner-only use). */
 int evg_upload(evg_ctx* ctx, const evg_task_soa* tasks, const evg_distro_table* distros,
                const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg);
+/* Like evg_upload, but the task columns already live in DEVICE memory (the finder's output, a generator kernel, a
+ * previous tick edited in place): `tasks` holds device pointers, which the context borrows until the next upload or
+ * evg_shutdown -- nothing is copied.  Every column must be 16-byte aligned and readable 8 elements past its last
+ * row (the kernels read whole 128-bit vectors / TMA tiles).  `distros`, `hosts`, `host_off`, `acfg` are host
+ * pointers as in evg_upload.  Replaces nothing in the reference (there the tasks are already in the process). */
+int evg_upload_device(evg_ctx* ctx, const evg_task_soa* device_tasks, const evg_distro_table* distros,
+                      const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg);
 /* Launch the fused path on the resident inputs; asynchronous on the context
  * stream.  Safe to call repeatedly (each call recomputes from the inputs). */
 int evg_run_resident(evg_ctx* ctx, int64_t now_ns, uint32_t opts);
@@ -293,10 +300,14 @@ int64_t evg_last_launch_count(evg_ctx* ctx);
  * tasks, otherwise the k_plan_smem<1024,12> launch (see evg_kernel_timing_ms). */
 int evg_last_timing_ms(evg_ctx* ctx, float* total_ms, float* sort_ms);
 
-/* Device time in ms of the dominant kernel -- k_plan_smem<1024,12>, the on-chip planner
- * of distros with 4097..12288 tasks -- for each of the last `n` evg_run_resident calls
- * (n <= 128), from CUDA events recorded on the context stream around that launch. */
+/* Device time in ms of the dominant kernel of on-chip ticks -- k_plan_cta<512,10240>, the on-chip planner of distros
+ * with 5121..10240 tasks (or k_plan_smem<1024,12> when the tick has none) -- for each of the last `n`
+ * evg_run_resident calls that launched it (n <= 128), from CUDA events recorded around that launch on its stream. */
 int evg_kernel_timing_ms(evg_ctx* ctx, float* out_ms, int32_t n);
+
+/* The general path's two big stages in the last evg_run_resident (ms, CUDA events on its stream): the per-task
+ * pass k_gtask (reads every input column once) and the segmented radix sort (all passes). */
+int evg_general_timing_ms(evg_ctx* ctx, float* task_pass_ms, float* sort_ms);
 
 /* ---- dependency filter (the next row after the planner/allocator path) ---- */
 

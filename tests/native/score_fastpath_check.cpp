@@ -3,12 +3,13 @@
 #include <initializer_list>
 #include <cstdlib>
 #include <cmath>
+#include <cstring>
 #include "evergreen_b200/csrc/evg_score.cuh"
 using namespace evg;
 static int64_t ref_floor_minutes_over(int64_t d, int64_t n) { return int64_t(std::floor((double(d / kMinute) + double(d % kMinute) / (60.0 * 1e9)) / double(n))); }
 static int64_t ref_trunc_hours(int64_t d) { return int64_t(double(d / kHour) + double(d % kHour) / (3600.0 * 1e9)); }
 int main() {
-  uint64_t x = 88172645463325252ULL; long bad = 0; long n = 0; long fast_n = 0;
+  uint64_t x = 88172645463325252ULL; long bad = 0; long n = 0; long fast_n = 0; long n32 = 0;
   auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
   for (int it = 0; it < 20000000; it++) {
     int64_t q = int64_t(rnd() % (uint64_t(1) << 15));
@@ -64,6 +65,11 @@ int main() {
       fast_n++;
       if (want != single_task_value_fast(pf, now, prio, ex, qb, nd, fl)) bad++;
     }
+    const Factors32 f32 = factors32(pf, now);
+    if (f32.ok && score32_domain(now, prio, nd, ex, qb)) {
+      n32++;
+      if (uint64_t(want) != single_task_value32(f32, now, prio, ex, qb, nd, fl)) bad++;
+    }
     n++;
   }
   // the straight-line form at the edges of its domain (week boundary, limit - 1, zero basis, huge factors)
@@ -90,6 +96,23 @@ int main() {
           fast_n++;
           if (unit_value(a, c, nullptr) != single_task_value_fast(pf, now, prio, ex, qb, nd, f2)) bad++;
         }
+        // the 32-bit form at the edges of ITS domain: factors up to 2^14 - 1, priority / dependents up to 2^15 - 1
+        for (int big = 0; big < 2; big++) {
+          evg_distro_cfg c2 = c;
+          if (big) {
+            c2.patch_factor = c2.patch_time_in_queue_factor = c2.commit_queue_factor = c2.mainline_time_in_queue_factor =
+                c2.expected_runtime_factor = c2.generate_task_factor = c2.stepback_task_factor = kFactor32Limit - 1;
+            c2.num_dependents_factor = double(kFactor32Limit - 1);
+          }
+          const int32_t p2 = big ? int32_t(kTask32Limit) - 1 : int32_t(tq % 5) - 1, d2 = big ? int32_t(kTask32Limit) - 1 : int32_t(ex % 7) - 1;
+          const PlannerFactors pf2 = clamp_factors(c2);
+          const Factors32 f32 = factors32(pf2, now);
+          if (f32.ok && score32_domain(now, p2, d2, ex, qb)) {
+            UnitAcc a2; acc_init(a2); acc_add(a2, now, p2, ex, qb, d2, -1, f2);
+            n32++;
+            if (uint64_t(unit_value(a2, c2, nullptr)) != single_task_value32(f32, now, p2, ex, qb, d2, f2)) bad++;
+          }
+        }
         n++;
       }
     // outside the domain the test must say so
@@ -97,6 +120,19 @@ int main() {
         score_fast_domain(now, 0, now + 1) || score_fast_domain(now, 0, -5)) bad++;
   }
   if (fast_n < 1000000) bad++;  // the straight-line form must actually have been exercised
-  printf("checked %ld (%ld through the straight-line form), mismatches %ld\n", n, fast_n, bad);
+  if (n32 < 500000) bad++;      // and so must the 32-bit form
+  {  // out of the 32-bit domain: big factor, big priority, big dependents, negative clock
+    evg_distro_cfg c; memset(&c, 0, sizeof(c));
+    c.patch_factor = kFactor32Limit;
+    if (factors32(clamp_factors(c), 5).ok) bad++;
+    c.patch_factor = 3; c.num_dependents_factor = 2.5;
+    if (factors32(clamp_factors(c), 5).ok) bad++;
+    c.num_dependents_factor = 0.0;
+    if (!factors32(clamp_factors(c), 5).ok || factors32(clamp_factors(c), -5).ok) bad++;
+    const int64_t now = 1800000000000000000LL;
+    if (score32_domain(now, int32_t(kTask32Limit), 0, 0, now) || score32_domain(now, 0, int32_t(kTask32Limit), 0, now) ||
+        !score32_domain(now, -7, -7, 0, now)) bad++;
+  }
+  printf("checked %ld (%ld through the straight-line form, %ld through the 32-bit form), mismatches %ld\n", n, fast_n, n32, bad);
   return bad != 0;
 }

@@ -703,3 +703,194 @@ def test_c2_full_size_properties(engine):
     po, ao = run(engine, w)
     parity.check_properties(w, po, ao)
     parity.check_against_oracle(w, po, ao, distros=[0, 1, 499, 998, 999])
+
+
+# ---------------------------------------------------------------- round 2: second-generation planners
+def test_cta_class_boundaries(engine):
+    """Sizes on both sides of every k_plan_cta class (1280 / 5120 / 10240 tasks) and of the k_plan_smem class above
+    it, with task groups only (the shape k_plan_cta plans) -- and the same sizes with in-queue dependencies, which
+    must be routed to k_plan_smem / the general path instead."""
+    sizes = np.array([33, 1279, 1280, 1281, 5119, 5120, 5121, 10239, 10240, 10241, 12288, 12289, 64, 0, 1])
+    w = synth.make(sizes, 201, zipf_priority=True, tg_frac=0.15, custom_factor_frac=0.4, n_hosts=150, providers=(0.7, 0.2, 0.1))
+    po, ao = run(engine, w)
+    parity.check_properties(w, po, ao)
+    parity.check_against_oracle(w, po, ao)
+    w = synth.make(sizes, 202, zipf_priority=True, tg_frac=0.15, met_dep_frac=0.02, unmet_dep_frac=0.02,
+                   includes_dependencies=True, n_hosts=150)
+    po, ao = run(engine, w)
+    parity.check_against_oracle(w, po, ao)
+
+
+def test_cta_misaligned_distro_starts(engine):
+    """TMA tiles start at multiples of four tasks; distros start anywhere.  Every start residue mod 4, first and
+    last distro of the table, sizes around one and two tiles of each class."""
+    sizes = np.array([1, 510, 513, 3, 127, 129, 2, 255, 257, 5, 1023, 1025, 6, 2049, 9999, 7, 10240])
+    w = synth.make(sizes, 203, tg_frac=0.1, zipf_priority=True, n_hosts=60)
+    assert len({int(x) % 4 for x in w.distros.task_off[:-1]}) == 4
+    po, ao = run(engine, w)
+    parity.check_properties(w, po, ao)
+    parity.check_against_oracle(w, po, ao)
+
+
+def test_cta_hands_back_what_it_cannot_hold(engine):
+    """Distros k_plan_cta starts and then hands back to k_plan_smem on the device: TotalValue beyond 32 bits,
+    TaskGroupOrder >= 64 or repeated inside a group, more task-group tasks than its work list holds -- next to
+    distros it keeps, in one tick."""
+    sizes = np.array([9000, 3000, 9000, 700, 4000, 9000, 2000])
+    w = synth.make(sizes, 204, tg_frac=0.12, zipf_priority=True, n_hosts=70)
+    toff, t = w.distros.task_off, w.tasks
+    w.distros.cfg["patch_time_in_queue_factor"][0] = 100      # distro 0: values beyond 2^32
+    w.distros.cfg["generate_task_factor"][0] = 100
+    w.distros.cfg["expected_runtime_factor"][0] = 100
+    t.priority[toff[0]:toff[1]:5] = 30000
+    t.flags[toff[0]:toff[1]:3] |= L.EVG_TF_GENERATE
+    t.task_group_order[np.arange(toff[1], toff[2])[::4]] = 70  # distro 1: order beyond the presence mask
+    t.task_group_order[toff[2]:toff[3]] = np.minimum(t.task_group_order[toff[2]:toff[3]], 2)  # distro 2: duplicates
+    w2 = synth.make(np.array([4000]), 205, tg_frac=0.6, zipf_priority=True)  # distro 4's shape: 60 % task-group tasks
+    po, ao = run(engine, w)
+    assert int(po.total_value[toff[0]:toff[1]].max()) > 2 ** 32
+    parity.check_against_oracle(w, po, ao)
+    po2, _ = run(engine, w2)
+    parity.check_against_oracle(w2, po2, None)
+
+
+def test_cta_digit_widths(engine):
+    """Value ranges from one value (no pass) through every pass count of the 10/9/8-bit digit classes."""
+    for seed, prio_step, factor in ((206, 0, 0), (207, 1, 0), (208, 50, 20), (209, 1000, 100)):
+        w = synth.make(np.array([10000, 5000, 1200, 300]), seed, tg_frac=0.05, custom_factor_frac=0.0)
+        if prio_step == 0:  # every task identical: a single TotalValue, ties broken by input order only
+            t = w.tasks
+            t.priority[:] = 0; t.expected_ns[:] = 600 * 10 ** 9; t.queue_basis_ns[:] = w.now; t.num_dependents[:] = 0
+            t.flags[:] = L.EVG_TF_DEPS_MET; t.group_id[:] = -1
+            w.distros.group_off[:] = 0
+            w.distros.group_max_hosts = w.distros.group_max_hosts[:0]
+        else:
+            w.tasks.priority[:] = (np.arange(w.n_tasks) % 7) * prio_step
+            for f in ("patch_time_in_queue_factor", "mainline_time_in_queue_factor", "expected_runtime_factor"):
+                w.distros.cfg[f] = factor
+        po, _ = run(engine, w)
+        parity.check_against_oracle(w, po, None)
+
+
+def test_one_million_task_distro(engine):
+    """A single queue of a million tasks (configs[3]'s per-distro reading) with task groups and in-queue
+    dependencies, bit-exact against the oracle: ~490 general-path tiles, the 2^21-1 index space half used."""
+    w = synth.make(np.array([1_000_000, 17]), 210, zipf_priority=True, tg_frac=0.1, unmet_dep_frac=0.03, met_dep_frac=0.01,
+                   includes_dependencies=True, n_hosts=300)
+    po, ao = run(engine, w)
+    parity.check_properties(w, po, ao)
+    parity.check_against_oracle(w, po, ao, threads=32)
+
+
+def test_general_path_shapes(engine):
+    """General-path distros of every kind in one tick: plain (identity pre-arrangement inside a tick that needs
+    e[] elsewhere), task groups, GroupVersions, dependency edges, a value range beyond 32 bits (two key words),
+    a single repeated value (no sort pass), start residues mod 4."""
+    sizes = np.array([13001, 1, 20003, 2, 15000, 3, 14001, 30000])
+    w = synth.make(sizes, 211, zipf_priority=True, tg_frac=0.1, unmet_dep_frac=0.03, met_dep_frac=0.02,
+                   group_versions_frac=0.0, includes_dependencies=True, n_hosts=100)
+    toff, t = w.distros.task_off, w.tasks
+    w.distros.cfg["group_versions"][2] = 1
+    for f in ("patch_time_in_queue_factor", "generate_task_factor", "expected_runtime_factor"):
+        w.distros.cfg[f][4] = 100
+    t.priority[toff[4]:toff[5]:7] = 100000
+    t.flags[toff[4]:toff[5]:3] |= L.EVG_TF_GENERATE
+    po, ao = run(engine, w)
+    assert int(po.total_value[toff[4]:toff[5]].max() - po.total_value[toff[4]:toff[5]].min()) > 2 ** 33
+    parity.check_properties(w, po, ao)
+    parity.check_against_oracle(w, po, ao)
+    # no multi-member unit anywhere: the scan-free placement
+    w = synth.make(np.array([40000, 13000]), 212, tg_frac=0.0, zipf_priority=True)
+    po, _ = run(engine, w)
+    parity.check_against_oracle(w, po, None)
+    t = w.tasks
+    t.priority[:] = 0; t.expected_ns[:] = 600 * 10 ** 9; t.queue_basis_ns[:] = w.now; t.num_dependents[:] = 0
+    t.flags[:] = L.EVG_TF_DEPS_MET
+    po, _ = run(engine, w)
+    assert np.array_equal(po.order[:40000], np.arange(40000))
+    parity.check_against_oracle(w, po, None)
+
+
+def test_config3_each_bigger_sample(engine):
+    """configs[2] per-distro reading at 100 distros x 100k tasks (1e7 tasks through the general path): invariants on
+    everything, the oracle on a sample."""
+    w = synth.config(3, 0.01, each=True)
+    assert w.n_tasks == 10_000_000
+    po, ao = run(engine, w)
+    parity.check_properties(w, po, ao)
+    parity.check_against_oracle(w, po, ao, distros=[0, 1, 50, 99], threads=32)
+
+
+def test_upload_device_equals_upload(engine):
+    """evg_upload_device: task columns that already live in device memory are planned in place."""
+    import torch
+    w = synth.make(np.array([9000, 40, 15000, 3, 700, 2000]), 213, zipf_priority=True, tg_frac=0.1, unmet_dep_frac=0.02,
+                   met_dep_frac=0.02, includes_dependencies=True, n_hosts=80)
+    po, ao = run(engine, w)
+    want = copy.deepcopy((po, ao))
+    keep, cols = [], {}
+    names = [n for n, _ in w.tasks.COLUMNS] + ["dep_off", "dep_idx"]
+    for name in names:
+        a = getattr(w.tasks, name)
+        pad = np.zeros(a.shape[0] + 8, dtype=a.dtype)
+        pad[:a.shape[0]] = a
+        v = pad.view(np.int32) if pad.dtype == np.uint32 else pad
+        tdev = torch.from_numpy(v).to("cuda:0")
+        keep.append(tdev)
+        cols[name] = tdev.data_ptr()
+    torch.cuda.synchronize()
+    engine.upload_device(cols, w.n_tasks, w.distros, w.hosts, n_edges=w.tasks.n_edges)
+    engine.run(w.now)
+    po2, ao2 = engine.download()
+    for f in ("order", "total_value", "info", "group_info"):
+        assert np.array_equal(getattr(want[0], f), getattr(po2, f)), f
+    assert np.array_equal(want[1].result, ao2.result)
+    engine.upload(w.tasks, w.distros, w.hosts)  # the context owns its columns again
+    engine.run(w.now)
+    po3, _ = engine.download()
+    assert np.array_equal(want[0].order, po3.order)
+    del keep
+
+
+def test_two_contexts_two_threads(engine):
+    """Entry points are called from arbitrary OS threads (cgo): two contexts planning different ticks at the same
+    time, and two threads sharing ONE context (serialised by its lock), all bit-equal to the single-threaded run."""
+    import threading
+    from evergreen_b200 import scheduler
+    ws = [synth.make(np.array([3000, 50, 14000, 900]), 220 + k, tg_frac=0.1, zipf_priority=True, met_dep_frac=0.02, n_hosts=50)
+          for k in range(2)]
+    want = []
+    for w in ws:
+        po, ao = engine.plan_and_alloc_batch(w.tasks, w.distros, w.hosts, w.now)
+        want.append((po.order.copy(), ao.result.copy()))
+    engines = [scheduler.Engine(0), scheduler.Engine(0)]
+    errs = []
+
+    def work(k, eng, reps):
+        try:
+            for _ in range(reps):
+                po, ao = eng.plan_and_alloc_batch(ws[k].tasks, ws[k].distros, ws[k].hosts, ws[k].now)
+                if not (np.array_equal(po.order, want[k][0]) and np.array_equal(ao.result, want[k][1])):
+                    errs.append(f"context {k}: results differ")
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=work, args=(k, engines[k], 5)) for k in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for e in engines:
+        e.close()
+    assert not errs, errs
+    # one context, two threads: raw C-ABI calls interleave, the lock keeps each call whole
+    lib = engine.lib
+    rcs = []
+
+    def resident(reps):
+        for _ in range(reps):
+            rcs.append(lib.evg_run_resident(engine.ctx, int(ws[0].now), 0))
+    engine.upload(ws[0].tasks, ws[0].distros, ws[0].hosts)
+    th = [threading.Thread(target=resident, args=(10,)) for _ in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert rcs == [0] * 20
+    po, ao = engine.download()
+    assert np.array_equal(po.order, want[0][0]) and np.array_equal(ao.result, want[0][1])
