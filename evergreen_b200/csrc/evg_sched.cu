@@ -492,16 +492,17 @@ __global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W
 }
 
 // scheduler.go:144-158: scalars of DistroQueueInfo / TaskGroupInfo that are not sums.
-__global__ void k_finalize_info(DDistros D, DWork W, int64_t n_groups_total) {
+__global__ void k_finalize_info(DDistros D, DWork W, int64_t g_begin, int64_t g_end) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < D.n) {
+  if (i < D.n && !W.route[i]) {  // on-chip planners write their rows whole (and may be doing so right now on another stream)
     evg_queue_info* q = W.qinfo + i;
     q->length = D.task_off[i + 1] - D.task_off[i];
     q->max_duration_threshold = D.cfg[i].target_time_ns;
     q->secondary_queue = q->secondary_queue != 0;
     q->has_ungrouped = q->has_ungrouped != 0;
   }
-  if (i < n_groups_total) W.ginfo[i].max_hosts = D.gmax[i];
+  // group rows between the first and the last general-path distro; an on-chip distro in between stores the same value
+  if (g_begin + i < g_end) W.ginfo[g_begin + i].max_hosts = D.gmax[g_begin + i];
 }
 
 // UtilizationBasedHostAllocator (utilization_based_host_allocator.go:26-130 and
@@ -702,6 +703,9 @@ struct evg_ctx {
   cudaEvent_t ev_h[kMaxChunks] = {}, ev_c[kMaxChunks] = {};
   int general_complex = 0;
   int64_t Tgc = 0;  // tasks in general-path distros that can hold multi-member units (work-list capacity)
+  // index ranges spanned by the general-path distros (first to last): what the general path's memsets cover
+  int32_t gr_d0 = 0, gr_d1 = 0;
+  int64_t gr_t0 = 0, gr_t1 = 0, gr_u0 = 0, gr_u1 = 0, gr_g0 = 0, gr_g1 = 0, gr_e0 = 0, gr_e1 = 0;
   DevBuf b_kv, b_vmm, b_klo[2], b_khi[2], b_ix[2], b_e, b_tilesum, b_gmisc;
   DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist;
   DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
@@ -887,6 +891,15 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   c->nNA = int32_t(listNA.size()); c->nNB = int32_t(listNB.size()); c->nNC = int32_t(listNC.size());
   c->n_general = n_general;
   c->general_complex = general_complex;
+  if (n_general > 0) {
+    const int32_t d0 = listG.front(), d1 = listG.back() + 1;
+    c->gr_d0 = d0; c->gr_d1 = d1;
+    c->gr_t0 = dt->task_off[d0]; c->gr_t1 = dt->task_off[d1];
+    c->gr_u0 = unit_base[d0]; c->gr_u1 = unit_base[d1];
+    c->gr_g0 = dt->group_off[d0]; c->gr_g1 = dt->group_off[d1];
+    c->gr_e0 = E > 0 ? (edge_off ? edge_off[d0] : t->dep_off[c->gr_t0]) : 0;
+    c->gr_e1 = E > 0 ? (edge_off ? edge_off[d1] : t->dep_off[c->gr_t1]) : 0;
+  }
   CK(c->b_err.ensure(sizeof(int) * 4));
   CK(cudaMemsetAsync(c->b_err.p, 0, sizeof(int) * 4, s));
   c->h_listW.swap(listW);
@@ -1047,22 +1060,33 @@ int launch_tiny(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& d
   return EVG_OK;
 }
 
+// Everything the general path accumulates into or links through starts from zero / "empty".  Runs on the context
+// stream BEFORE the routes fork: the ranges span from the first to the last general-path distro, and an on-chip
+// distro in between rewrites its own rows afterwards.
+int prepare_general(evg_ctx* c, cudaStream_t s) {
+  const int64_t T = c->T;
+  CK(cudaMemsetAsync(c->b_qinfo.as<evg_queue_info>() + c->gr_d0, 0, sizeof(evg_queue_info) * size_t(c->gr_d1 - c->gr_d0), s));
+  if (c->gr_g1 > c->gr_g0) CK(cudaMemsetAsync(c->b_ginfo.as<evg_group_info>() + c->gr_g0, 0, sizeof(evg_group_info) * size_t(c->gr_g1 - c->gr_g0), s));
+  if (c->general_complex) {
+    const size_t nt = size_t(c->gr_t1 - c->gr_t0);
+    CK(cudaMemsetAsync(c->b_hasdep.as<uint8_t>() + c->gr_t0, 0, nt, s));
+    CK(cudaMemsetAsync(c->b_head.as<uint32_t>() + c->gr_u0, 0xFF, sizeof(uint32_t) * size_t(c->gr_u1 - c->gr_u0), s));
+    CK(cudaMemsetAsync(c->b_unitmask.as<uint64_t>() + c->gr_u0, 0, sizeof(uint64_t) * size_t(c->gr_u1 - c->gr_u0), s));
+    CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + c->gr_t0, 0xFF, sizeof(uint32_t) * nt, s));          // own-key pairs
+    CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + T + c->gr_t0, 0xFF, sizeof(uint32_t) * nt, s));      // version pairs
+    if (c->gr_e1 > c->gr_e0)
+      CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + 2 * T + c->gr_e0, 0xFF, sizeof(uint32_t) * size_t(c->gr_e1 - c->gr_e0), s));  // edge pairs
+  }
+  return EVG_OK;
+}
+
 // The general path of one tick on stream `st` (evg_plan_general.cuh).
 int run_general(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& dd, const DWork& w, int64_t now) {
-  const int64_t T = c->T, P = 2 * T + c->E;
   const int32_t D = c->Dn;
   const DGen g = dgen(c);
   const int gc = c->general_complex;
   const unsigned nt = unsigned(c->NT);
   const int32_t* gl = c->b_listG.as<int32_t>();
-  CK(cudaMemsetAsync(c->b_qinfo.p, 0, sizeof(evg_queue_info) * size_t(D + 1), st));   // general distros accumulate with atomics;
-  CK(cudaMemsetAsync(c->b_ginfo.p, 0, sizeof(evg_group_info) * size_t(c->G + 1), st));  // on-chip planners write their own rows whole
-  if (gc) {
-    CK(cudaMemsetAsync(c->b_hasdep.p, 0, size_t(T) + 16, st));
-    CK(cudaMemsetAsync(c->b_head.p, 0xFF, sizeof(uint32_t) * size_t(c->U + 1), st));
-    CK(cudaMemsetAsync(c->b_next.p, 0xFF, sizeof(uint32_t) * size_t(P + 1), st));
-    CK(cudaMemsetAsync(c->b_unitmask.p, 0, sizeof(uint64_t) * size_t(c->U + 1), st));
-  }
   LAUNCH_ON(c, st, k_ginit, grid_for(c->n_general, 256), 256, g, gl, c->n_general);
   if (gc && c->E > 0) LAUNCH_ON(c, st, k_gmark, nt, 256, dt, dd, w, g);
   if (c->timed) CK(cudaEventRecord(c->ev_gt0, st));
@@ -1085,7 +1109,7 @@ int run_general(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& d
   }
   if (c->timed) CK(cudaEventRecord(c->ev_sort1, st));
   LAUNCH_ON(c, st, k_gemit, nt, 256, dd, g, c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
-  LAUNCH_ON(c, st, k_finalize_info, grid_for(std::max<int64_t>(D, c->G), 256), 256, dd, w, c->G);
+  LAUNCH_ON(c, st, k_finalize_info, grid_for(std::max<int64_t>(D, c->gr_g1 - c->gr_g0), 256), 256, dd, w, c->gr_g0, c->gr_g1);
   return EVG_OK;
 }
 
@@ -1123,6 +1147,7 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
   if (bd && c->any_complex) CK(cudaMemsetAsync(c->b_bestpair.p, 0xFF, sizeof(uint32_t) * size_t(T + 1), s));
   const int32_t n_new = bd ? 0 : c->nNA + c->nNB + c->nNC;
   if (n_new > 0) CK(cudaMemsetAsync(c->b_puntcnt.p, 0, sizeof(int32_t), s));
+  if (general) { int rcg = prepare_general(c, s); if (rcg != EVG_OK) return rcg; }
   // Routes run side by side when the tick has more than one: fork the aux streams off the context stream here, join
   // them before returning (the allocator and the caller's later work are ordered behind every planner kernel).
   struct Route { int id; int64_t weight; };
@@ -1410,10 +1435,6 @@ static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg
   DTasks dtk = dtasks(c);
   DDistros dd = ddistros(c);
   DWork w = dwork(c);
-  DHosts h;
-  h.n = c->H; h.flags = c->b_hflags.as<uint32_t>(); h.gid = c->b_hgid.as<int32_t>();
-  h.expected = c->b_hexp.as<int64_t>(); h.stddev = c->b_hstd.as<int64_t>(); h.start = c->b_hstart.as<int64_t>();
-  h.host_off = c->b_hostoff.as<int64_t>(); h.cfg = c->b_acfg.as<evg_alloc_cfg>();
   if (c->ext_result && c->ext_capacity < D) return fail(EVG_ERR_INVALID, "bound result buffer too small");
   CK(c->b_gs.ensure(sizeof(GroupScratch) * size_t(c->G + 1)));
   c->launches = 0;
