@@ -461,7 +461,6 @@ def main():
     H, G = hosts.n_hosts, distros.n_groups
     del po, ao
     # the device copy of the headline workload is no longer needed
-    eng.bind_result_buffer(send.data_ptr(), shards.max_shard)
     del keep, cols
     torch.cuda.empty_cache()
 
@@ -537,6 +536,7 @@ def main():
             "checksum_new_hosts": new_hosts_checksum, "first_distro_is_a_permutation": order_ok,
         }
         if not args.no_shapes and world == 1:
+            eng.bind_result_buffer(0, 0)  # the shapes have other distro counts: results go to the context's own buffer
             line["shapes"] = measure_shapes(torch, eng, stream, peak, args.shape_steps)
         if not args.no_cpu_baseline and world == 1:
             if prev_affinity:

@@ -114,6 +114,18 @@ EVG_DR_COMPLETED, EVG_DR_TIMED_OUT = 0x1, 0x2
 DURATION_STAT_DTYPE = np.dtype([("count", np.int64), ("mean_ns", np.float64), ("stddev_ns", np.float64)])
 
 
+class LegacySoAStruct(C.Structure):
+    _fields_ = [("n_tasks", C.c_int64), ("priority", C.c_void_p), ("ingest_ns", C.c_void_p), ("expected_ns", C.c_void_p),
+                ("num_dependents", C.c_void_p), ("revision_order", C.c_void_p), ("project_id", C.c_void_p),
+                ("tg_rank", C.c_void_p), ("tg_pair_id", C.c_void_p), ("task_group_order", C.c_void_p),
+                ("presort_rank", C.c_void_p), ("flags", C.c_void_p)]
+
+
+EVG_LF_REQ_SYSTEM, EVG_LF_REQ_PATCH, EVG_LF_REQ_OTHER, EVG_LF_GENERATE, EVG_LF_MERGE_QUEUE_VERSION = 0, 1, 2, 0x4, 0x8
+EVG_LEGACY_MODE_INGEST, EVG_LEGACY_MODE_REVISION, EVG_LEGACY_MODE_LITERAL = 0, 1, 2
+EVG_LEGACY_OK, EVG_LEGACY_NOT_DECOMPOSABLE = 0, 1
+
+
 class AllocOutStruct(C.Structure):
     _fields_ = [("result", C.c_void_p), ("status", C.c_void_p)]
 
@@ -149,6 +161,7 @@ SYMBOLS = {
     "evg_deps_met_batch": (C.c_int, [_P, _P, _P]),
     "evg_find_runnable_batch": (C.c_int, [_P, _P, _P, _P]),
     "evg_expected_durations_batch": (C.c_int, [_P, _P, _P]),
+    "evg_prioritize_legacy_batch": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "evg_plan_distro": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, C.c_uint32, _P]),
     "evg_alloc_distro": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P]),
 }

@@ -243,6 +243,7 @@ __device__ __forceinline__ uint32_t pair_task(const DTasks& T, const DWork& W, u
 #include "evg_plan_warp.cuh"
 #include "evg_plan_cta.cuh"
 #include "evg_plan_general.cuh"
+#include "evg_legacy.cuh"
 
 // --------------------------------------------------------------------------
 // kernels (general path: any distro size)
@@ -1752,6 +1753,91 @@ int evg_find_runnable_batch(evg_ctx* c, const evg_runnable_in* in, int32_t* runn
   CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (bad) return fail(EVG_ERR_INVALID, "a project row or dep_ref is out of range");
+  return EVG_OK;
+}
+
+int evg_prioritize_legacy_batch(evg_ctx* c, const evg_legacy_soa* in, const int64_t* task_off, const uint8_t* list_mode,
+                                int32_t n_distros, int32_t* order, int64_t* count, int32_t* status) {
+  if (!c || !in) return fail(EVG_ERR_INVALID, "evg_prioritize_legacy_batch: null argument");
+  LOCK(c);
+  const int64_t T = in->n_tasks;
+  const int32_t D = n_distros;
+  if (T < 0 || D < 0) return fail(EVG_ERR_INVALID, "negative sizes");
+  if (D == 0) return T == 0 ? EVG_OK : fail(EVG_ERR_INVALID, "tasks without distros");
+  if (!task_off || !list_mode || !count || !status || (T > 0 && !order)) return fail(EVG_ERR_INVALID, "null argument");
+  if (T > 0 && (!in->priority || !in->ingest_ns || !in->expected_ns || !in->num_dependents || !in->revision_order || !in->project_id ||
+                !in->tg_rank || !in->tg_pair_id || !in->task_group_order || !in->presort_rank || !in->flags))
+    return fail(EVG_ERR_INVALID, "null task column");
+  if (task_off[0] != 0 || task_off[D] != T) return fail(EVG_ERR_INVALID, "task_off does not span n_tasks");
+  int64_t max_n = 0;
+  for (int32_t d = 0; d < D; d++) {
+    if (task_off[d + 1] < task_off[d]) return fail(EVG_ERR_INVALID, "offsets of distro %d decrease", d);
+    max_n = std::max(max_n, task_off[d + 1] - task_off[d]);
+  }
+  for (int64_t k = 0; k < 3 * int64_t(D); k++)
+    if (list_mode[k] > EVG_LEGACY_MODE_LITERAL) return fail(EVG_ERR_INVALID, "unknown list mode %d", int(list_mode[k]));
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  c->launches = 0;
+  c->have_tasks = false;  // shares scratch buffers with the other entry points
+#define UPL(buf, ptr, count_, type)                                                                                \
+  do {                                                                                                             \
+    CK((buf).ensure(sizeof(type) * size_t((count_) > 0 ? (count_) : 1)));                                          \
+    if ((count_) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(count_), cudaMemcpyHostToDevice, s)); \
+  } while (0)
+  UPL(c->b_exp, in->priority, T, int64_t);
+  UPL(c->b_qb, in->ingest_ns, T, int64_t);
+  UPL(c->b_wb, in->expected_ns, T, int64_t);
+  UPL(c->b_nd, in->num_dependents, T, int32_t);
+  UPL(c->b_prio, in->revision_order, T, int32_t);
+  UPL(c->b_vid, in->project_id, T, int32_t);
+  UPL(c->b_gid, in->tg_rank, T, int32_t);
+  UPL(c->b_rn0, in->tg_pair_id, T, int32_t);
+  UPL(c->b_tgo, in->task_group_order, T, int32_t);
+  UPL(c->b_rn1, in->presort_rank, T, int32_t);
+  UPL(c->b_flags, in->flags, T, uint32_t);
+  UPL(c->b_rn2, list_mode, 3 * int64_t(D), uint8_t);
+  UPL(c->b_taskoff, task_off, D + 1, int64_t);
+#undef UPL
+  CK(c->b_order.ensure(sizeof(int32_t) * size_t(T + 1)));
+  CK(c->b_rn3.ensure(sizeof(int32_t) * size_t(T + 1)));
+  CK(c->b_rn4.ensure(sizeof(int32_t) * size_t(T + 1)));
+  CK(c->b_rn5.ensure(sizeof(unsigned int) * 4 * size_t(D)));
+  CK(c->b_rn6.ensure(sizeof(int64_t) * size_t(D)));
+  CK(c->b_status.ensure(sizeof(int32_t) * size_t(D + 1)));
+  CK(cudaMemsetAsync(c->b_rn5.p, 0, sizeof(unsigned int) * 4 * size_t(D), s));
+  DLegacy x;
+  x.n = T; x.priority = c->b_exp.as<int64_t>(); x.ingest = c->b_qb.as<int64_t>(); x.expected = c->b_wb.as<int64_t>();
+  x.numdep = c->b_nd.as<int32_t>(); x.revision = c->b_prio.as<int32_t>(); x.project = c->b_vid.as<int32_t>();
+  x.tg_rank = c->b_gid.as<int32_t>(); x.tg_pair = c->b_rn0.as<int32_t>(); x.tgo = c->b_tgo.as<int32_t>();
+  x.presort = c->b_rn1.as<int32_t>(); x.flags = c->b_flags.as<uint32_t>(); x.list_mode = c->b_rn2.as<uint8_t>();
+  x.task_off = c->b_taskoff.as<int64_t>(); x.n_distros = D;
+  int32_t* buf[2] = {c->b_rn3.as<int32_t>(), c->b_rn4.as<int32_t>()};
+  int cur = 0;
+  if (T > 0) {
+    LAUNCH(c, k_legacy_init, grid_for(T, 256), 256, x, buf[0], c->b_rn5.as<unsigned int>());
+    for (int64_t L = 1; L < max_n; L <<= 1) {
+      LAUNCH(c, k_legacy_merge_pass, grid_for(T, 256), 256, x, buf[cur], buf[cur ^ 1], L);
+      cur ^= 1;
+    }
+    LAUNCH(c, k_legacy_interleave, grid_for(T, 256), 256, x, buf[cur], c->b_rn5.as<unsigned int>(), c->b_order.as<int32_t>(),
+           c->b_rn6.as<int64_t>(), c->b_status.as<int32_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(order, c->b_order.p, sizeof(int32_t) * size_t(T), cudaMemcpyDeviceToHost, s));
+  }
+  // distros without tasks never reach k_legacy_interleave's q == 0 thread
+  std::vector<int64_t> cnt(size_t(D), 0);
+  std::vector<int32_t> st(size_t(D), EVG_LEGACY_OK);
+  if (T > 0) {
+    CK(cudaMemcpyAsync(cnt.data(), c->b_rn6.p, sizeof(int64_t) * size_t(D), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(st.data(), c->b_status.p, sizeof(int32_t) * size_t(D), cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  for (int32_t d = 0; d < D; d++) {
+    const bool empty = task_off[d + 1] == task_off[d];
+    count[d] = empty ? 0 : cnt[d];
+    status[d] = empty ? EVG_LEGACY_OK : st[d];
+  }
   return EVG_OK;
 }
 

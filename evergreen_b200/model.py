@@ -30,6 +30,12 @@ PATCH_VERSION_REQUESTER = "patch_request"
 GITHUB_PR_REQUESTER = "github_pull_request"
 REPOTRACKER_VERSION_REQUESTER = "gitter_request"
 GITHUB_MERGE_REQUESTER = "github_merge_request"
+GIT_TAG_REQUESTER = "git_tag_request"
+TRIGGER_REQUESTER = "trigger_request"
+AD_HOC_REQUESTER = "ad_hoc"
+# globals.go:766-772
+SYSTEM_VERSION_REQUESTER_TYPES = (REPOTRACKER_VERSION_REQUESTER, TRIGGER_REQUESTER, GIT_TAG_REQUESTER, AD_HOC_REQUESTER)
+MAX_TASK_PRIORITY = 100  # globals.go:185
 # globals.go:219
 STEPBACK_TASK_ACTIVATOR = "stepback"
 # globals.go:52-71
@@ -99,6 +105,8 @@ class Task:
     version: str = ""
     project: str = ""
     build_variant: str = ""
+    build_id: str = ""               # legacy prioritiser only (task_priority_cmp.go:149-174, setup_funcs.go:72-87)
+    revision_order_number: int = 0   # legacy prioritiser only (task_priority_cmp.go:75-84)
     display_name: str = ""
     task_group: str = ""
     task_group_max_hosts: int = 0

@@ -228,6 +228,17 @@ class Engine:
         L.check(self.lib.evg_expected_durations_batch(self.ctx, C.byref(st), L.ptr(out) if rows.n_keys else None))
         return out
 
+    def prioritize_legacy_batch(self, table: "S.LegacyTable"):
+        """evg_prioritize_legacy_batch: (order, count, status) of CmpBasedTaskPrioritizer over every distro of the table."""
+        T, D = table.n_tasks, table.n_distros
+        order = self._out("legacy_order", T, np.int32)
+        count = self._out("legacy_count", D, np.int64)
+        status = self._out("legacy_status", D, np.int32)
+        ts = table.struct()
+        L.check(self.lib.evg_prioritize_legacy_batch(self.ctx, C.byref(ts), L.ptr(table.task_off), L.ptr(table.list_mode), D,
+                                                     L.ptr(order) if T else None, L.ptr(count), L.ptr(status)))
+        return order, count, status
+
     def alloc_batch(self, hosts: S.HostSoA, qinfo: np.ndarray, ginfo: np.ndarray, group_off: np.ndarray, now: int):
         D = int(qinfo.shape[0])
         ao = self._alloc_output(D)
@@ -444,3 +455,42 @@ def plan_and_allocate(batch: Sequence[Tuple[M.Distro, List[M.Task], M.HostAlloca
         info = _queue_info_from_rows(po.info[i], po.group_info[ga:gb], keys[i].group_names)
         out.append((ranked, info, int(ao.result[i]["new_hosts"]), int(ao.result[i]["free_hosts"]), int(ao.status[i])))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class NotDecomposableError(Exception):
+    """The legacy comparator chain is not a strict weak order on some list of the distro (commit builds of several
+    projects in one list, zero and non-zero expected durations mixed): the reference's result then depends on the exact
+    steps of Go's sort.Stable, which this library does not reproduce.  The order it did compute is attached."""
+
+    def __init__(self, distro_id: str, tasks):
+        super().__init__(f"distro {distro_id!r}: the comparator chain is not a strict weak order on this queue")
+        self.tasks = tasks
+
+
+class CmpBasedTaskPrioritizer:
+    """scheduler.TaskPrioritizer (scheduler/task_prioritizer.go:20-25) implemented by the legacy comparator
+    prioritiser on the GPU.  PrioritizeTasks returns (tasks in run order, orderingLogic, error) like the reference;
+    orderingLogic -- the reference's map of per-comparison reason strings -- is always empty here."""
+
+    def __init__(self, runtime_id: str = "", engine: Optional[Engine] = None, now: Optional[int] = None):
+        self.runtime_id = runtime_id
+        self.engine = engine
+        self.now = now
+
+    def prioritize_batch(self, batch):
+        """(distro_id, tasks, versions) per distro -> list of (sorted tasks, status)."""
+        eng = self.engine or default_engine()
+        table = S.marshal_legacy(batch, self.now)
+        order, count, status = eng.prioritize_legacy_batch(table)
+        out = []
+        for d, (_, tasks, _) in enumerate(batch):
+            a = int(table.task_off[d])
+            out.append(([tasks[int(i)] for i in order[a:a + int(count[d])]], int(status[d])))
+        return out
+
+    def PrioritizeTasks(self, distro_id: str, tasks, versions=None):
+        (sorted_tasks, status), = self.prioritize_batch([(distro_id, list(tasks), versions)])
+        if status != L.EVG_LEGACY_OK:
+            return None, None, NotDecomposableError(distro_id, sorted_tasks)
+        return sorted_tasks, {}, None

@@ -578,3 +578,115 @@ def marshal_durations(tasks: Sequence[M.Task], window_start: int, window_end: in
     rows = DurationRows(np.array(key, np.int32), np.array(taken, np.int64), np.array(start, np.int64),
                         np.array(finish, np.int64), np.array(flags, np.uint8), len(index), window_start, window_end)
     return rows, list(index)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# legacy comparator prioritiser (scheduler/task_prioritizer.go, task_priority_cmp.go, setup_funcs.go:72-87)
+@dataclass
+class LegacyTable:
+    """evg_legacy_soa + task_off + list_mode for a batch of distros."""
+    priority: np.ndarray
+    ingest_ns: np.ndarray
+    expected_ns: np.ndarray
+    num_dependents: np.ndarray
+    revision_order: np.ndarray
+    project_id: np.ndarray
+    tg_rank: np.ndarray
+    tg_pair_id: np.ndarray
+    task_group_order: np.ndarray
+    presort_rank: np.ndarray
+    flags: np.ndarray
+    task_off: np.ndarray
+    list_mode: np.ndarray  # uint8 [3 * n_distros]: high priority, patch, repotracker
+
+    COLUMNS = (("priority", np.int64), ("ingest_ns", np.int64), ("expected_ns", np.int64), ("num_dependents", np.int32),
+               ("revision_order", np.int32), ("project_id", np.int32), ("tg_rank", np.int32), ("tg_pair_id", np.int32),
+               ("task_group_order", np.int32), ("presort_rank", np.int32), ("flags", np.uint32))
+
+    @property
+    def n_tasks(self) -> int:
+        return int(self.priority.shape[0])
+
+    @property
+    def n_distros(self) -> int:
+        return int(self.task_off.shape[0]) - 1
+
+    def struct(self) -> "L.LegacySoAStruct":
+        s = L.LegacySoAStruct()
+        s.n_tasks = self.n_tasks
+        for name, _ in self.COLUMNS:
+            setattr(s, name, L.ptr(getattr(self, name)))
+        return s
+
+
+def legacy_list_of(t: M.Task) -> int:
+    """splitTasksByRequester (task_prioritizer.go:214-247): 0 high priority, 1 patch, 2 repotracker, 3 dropped."""
+    if t.priority > M.MAX_TASK_PRIORITY:
+        return 0
+    if t.requester in M.SYSTEM_VERSION_REQUESTER_TYPES:
+        return 2
+    if M.is_patch_requester(t.requester):
+        return 1
+    return 3
+
+
+def legacy_list_mode(tasks: Sequence[M.Task], expected: Sequence[int]) -> int:
+    """Is the comparator chain a strict weak order on this list, and which byAge branch does it take
+    (task_priority_cmp.go:73-95)?  Only tasks outside task groups reach byAge / byRuntime."""
+    plain = [(t, e) for t, e in zip(tasks, expected) if t.task_group == ""]
+    if any(e == 0 for _, e in plain) and any(e != 0 for _, e in plain):
+        return L.EVG_LEGACY_MODE_LITERAL  # byRuntime ties a zero duration with everything (:109-111)
+    commit = [t for t, _ in plain if t.requester in M.SYSTEM_VERSION_REQUESTER_TYPES]
+    projects = [t.project for t in commit]
+    if len(set(projects)) == len(projects):
+        return L.EVG_LEGACY_MODE_INGEST      # no pair takes the revision-order branch
+    if len(commit) == len(plain) and len(set(projects)) == 1:
+        return L.EVG_LEGACY_MODE_REVISION    # every pair takes it
+    return L.EVG_LEGACY_MODE_LITERAL
+
+
+def marshal_legacy(batch: Sequence[tuple], now: Optional[int] = None) -> LegacyTable:
+    """batch: (distro_id, tasks, versions) per distro; `versions` maps a version id to its Requester (what byCommitQueue
+    reads of model.Version).  Resolves FetchExpectedDuration, interns the strings, decides each list's mode."""
+    cols = {name: [] for name, _ in LegacyTable.COLUMNS}
+    task_off, modes = [0], []
+    for _, tasks, versions in batch:
+        versions = versions or {}
+        expected = [M.fetch_expected_duration(t, now)[0] if now is not None else t.expected_duration for t in tasks]
+        fmt = [f"{t.build_id}-{t.task_group}" for t in tasks]
+        grouped = sorted({f for f, t in zip(fmt, tasks) if t.task_group != ""})
+        rank = {f: k for k, f in enumerate(grouped)}
+        pairs: Dict[tuple, int] = {}
+        by_fmt: Dict[str, set] = {}
+        for f, t in zip(fmt, tasks):
+            if t.task_group != "":
+                pairs.setdefault((t.task_group, t.build_id), len(pairs))
+                by_fmt.setdefault(f, set()).add((t.task_group, t.build_id))
+        collision = any(len(v) > 1 for v in by_fmt.values())
+        keys = sorted(range(len(tasks)), key=lambda k: f"{fmt[k]}-{tasks[k].id}", reverse=True)
+        presort = [0] * len(tasks)
+        for pos, k in enumerate(keys):
+            presort[k] = pos
+        projects: Dict[str, int] = {}
+        lists = [legacy_list_of(t) for t in tasks]
+        for k, t in enumerate(tasks):
+            if not -(2 ** 63) <= t.priority < 2 ** 63:
+                raise ValueError(f"task {t.id!r}: priority {t.priority} is outside int64")
+            rq = (L.EVG_LF_REQ_SYSTEM if t.requester in M.SYSTEM_VERSION_REQUESTER_TYPES else
+                  L.EVG_LF_REQ_PATCH if M.is_patch_requester(t.requester) else L.EVG_LF_REQ_OTHER)
+            fl = rq | (L.EVG_LF_GENERATE if t.generate_task else 0)
+            if versions.get(t.version, "") == M.GITHUB_MERGE_REQUESTER:
+                fl |= L.EVG_LF_MERGE_QUEUE_VERSION
+            cols["priority"].append(t.priority); cols["ingest_ns"].append(t.ingest_time); cols["expected_ns"].append(expected[k])
+            cols["num_dependents"].append(t.num_dependents); cols["revision_order"].append(t.revision_order_number)
+            cols["project_id"].append(projects.setdefault(t.project, len(projects)))
+            cols["tg_rank"].append(rank[fmt[k]] if t.task_group != "" else -1)
+            cols["tg_pair_id"].append(pairs[(t.task_group, t.build_id)] if t.task_group != "" else -1)
+            cols["task_group_order"].append(t.task_group_order); cols["presort_rank"].append(presort[k]); cols["flags"].append(fl)
+        for lst in (0, 1, 2):
+            sel = [k for k in range(len(tasks)) if lists[k] == lst]
+            m = legacy_list_mode([tasks[k] for k in sel], [expected[k] for k in sel])
+            modes.append(L.EVG_LEGACY_MODE_LITERAL if collision else m)
+        task_off.append(task_off[-1] + len(tasks))
+    return LegacyTable(**{name: np.array(cols[name], dtype=dt) for name, dt in LegacyTable.COLUMNS},
+                       task_off=np.array(task_off, dtype=np.int64), list_mode=np.array(modes, dtype=np.uint8))

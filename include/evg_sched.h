@@ -422,6 +422,50 @@ typedef struct {
 /* getExpectedDurationsForWindow (model/task/expected_duration.go:36-96) for every key at once.  Host pointers. */
 int evg_expected_durations_batch(evg_ctx* ctx, const evg_duration_rows* in, evg_duration_stat* out);
 
+/* ---- legacy comparator prioritiser ---------------------- */
+
+/* evg_legacy_soa.flags */
+#define EVG_LF_REQ_MASK 0x3u
+#define EVG_LF_REQ_SYSTEM 0u              /* Requester in evergreen.SystemVersionRequesterTypes (globals.go:766-772): repotracker list, "commit build" */
+#define EVG_LF_REQ_PATCH 1u               /* evergreen.IsPatchRequester (globals.go:1179-1185): patch list */
+#define EVG_LF_REQ_OTHER 2u               /* anything else: logged and dropped (task_prioritizer.go:232-240) */
+#define EVG_LF_GENERATE 0x4u              /* Task.GenerateTask */
+#define EVG_LF_MERGE_QUEUE_VERSION 0x8u   /* versions[Task.Version].Requester == github_merge_request (byCommitQueue) */
+/* byAge (task_priority_cmp.go:73-95) of one list, decided by the shim when it marshals the list */
+#define EVG_LEGACY_MODE_INGEST 0    /* no two commit builds of the list share a project: IngestTime ascending */
+#define EVG_LEGACY_MODE_REVISION 1  /* every non-group task is a commit build of ONE project: RevisionOrderNumber descending */
+#define EVG_LEGACY_MODE_LITERAL 2   /* neither (or zero and non-zero expected durations mixed, or two (TaskGroup, BuildId)
+                                       pairs format to one string): the chain is not a strict weak order on this list */
+/* per-distro status */
+#define EVG_LEGACY_OK 0
+#define EVG_LEGACY_NOT_DECOMPOSABLE 1 /* some list was EVG_LEGACY_MODE_LITERAL: the order is a stable sort by the literal
+                                         pairwise comparator, which need not be the one Go's sort.Stable produces */
+
+/* What CmpBasedTaskPrioritizer reads of []task.Task and map[string]model.Version, SoA over the concatenated distros
+ * (scheduler/task_prioritizer.go:80-278, task_priority_cmp.go:25-208, setup_funcs.go:72-87).  Strings are interned
+ * by the shim; ranks are per distro. */
+typedef struct {
+  int64_t n_tasks;
+  const int64_t* priority;         /* Task.Priority (int64: the > MaxTaskPriority split and byPriority) */
+  const int64_t* ingest_ns;        /* Task.IngestTime */
+  const int64_t* expected_ns;      /* Task.FetchExpectedDuration(ctx).Average */
+  const int32_t* num_dependents;
+  const int32_t* revision_order;   /* Task.RevisionOrderNumber */
+  const int32_t* project_id;       /* interned Task.Project */
+  const int32_t* tg_rank;          /* rank of "BuildId-TaskGroup" among the distro's distinct such strings, ascending byte order; -1 when TaskGroup == "" */
+  const int32_t* tg_pair_id;       /* dense id of the (TaskGroup, BuildId) pair; -1 when TaskGroup == "" */
+  const int32_t* task_group_order;
+  const int32_t* presort_rank;     /* position of "BuildId-TaskGroup-Id" in DESCENDING byte order inside the distro (groupTaskGroups) */
+  const uint32_t* flags;           /* EVG_LF_* */
+} evg_legacy_soa;
+
+/* CmpBasedTaskPrioritizer.PrioritizeTasks for every distro of the tick.  list_mode[3*d + {0,1,2}] is the
+ * EVG_LEGACY_MODE_* of distro d's high-priority / patch / repotracker list.  order[task_off[d] .. +count[d]) receives
+ * the distro-local indices of the prioritised tasks (dropped tasks leave -1 in the remaining slots).  Host pointers.
+ * Replaces: the TaskPrioritizer interface (scheduler/task_prioritizer.go:20-25) minus the orderingLogic reasons. */
+int evg_prioritize_legacy_batch(evg_ctx* ctx, const evg_legacy_soa* tasks, const int64_t* task_off, const uint8_t* list_mode,
+                                int32_t n_distros, int32_t* order, int64_t* count, int32_t* status);
+
 /* ---- single-distro wrappers: the per-job drop-in ------------------------- */
 
 /* One distro: PrioritizeTasks for `d` (scheduler/scheduler.go:27). */

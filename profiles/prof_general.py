@@ -1,15 +1,20 @@
-"""General-path shapes for the ncu launch list: `python profiles/prof_general.py 1m|100k`."""
+"""General-path shapes for ncu: `python profiles/prof_general.py c3|1m|plain [ticks]`
+c3: 48 distros x 100k tasks in configs[2]'s mix (Zipf, dependencies, task groups); 1m: 8 x 1M tasks; plain: no multi-member units."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from evergreen_b200 import scheduler, synth
-which = sys.argv[1] if len(sys.argv) > 1 else "1m"
-sizes = np.full(8, 1000000) if which == "1m" else np.full(48, 100000)
+which = sys.argv[1] if len(sys.argv) > 1 else "c3"
 eng = scheduler.Engine(0)
-w = synth.make(sizes, synth.SEED_BASE + 3, n_hosts=5 * len(sizes))
+if which == "c3":
+    w = synth.config(3, 0.0048, each=True)
+elif which == "1m":
+    w = synth.config(4, 0.0008, each=True)
+else:
+    w = synth.make(np.full(48, 100000), synth.SEED_BASE + 3, tg_frac=0.0, zipf_priority=True, n_hosts=96)
 eng.upload(w.tasks, w.distros, w.hosts)
-for _ in range(3):
+for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
     eng.run(w.now)
 po, ao = eng.download()
-print("ok", which, eng.last_timing_ms(), int(ao.result["new_hosts"].sum()))
+print("ok", which, w.n_tasks, eng.last_timing_ms(), eng.general_timing_ms(), eng.last_launch_count(), int(ao.result["new_hosts"].sum()))
