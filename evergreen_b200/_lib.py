@@ -53,6 +53,11 @@ ALLOC_CFG_DTYPE = np.dtype([
     ("maximum_hosts", "<i4"), ("round_up", "<i4"), ("waits_over_thresh_feedback", "<i4"), ("has_pool", "<i4"),
     ("pool_max_containers", "<i4"), ("parent_found", "<i4"), ("parent_maximum_hosts", "<i4")])
 ALLOC_RESULT_DTYPE = np.dtype([("new_hosts", "<i4"), ("free_hosts", "<i4"), ("deficit_ns", "<i8")])
+QUEUE_ITEM_DTYPE = np.dtype([("task", "<i4"), ("group_index", "<i4"), ("group_max_hosts", "<i4"), ("flags", "<u4"),
+                             ("priority", "<i8"), ("expected_ns", "<i8"), ("total_value", "<i8")])
+EVG_QI_DEPS_MET = 0x1
+EVG_PERSISTED_QUEUE_CAP = 10000
+assert QUEUE_ITEM_DTYPE.itemsize == 40
 assert DISTRO_CFG_DTYPE.itemsize == 88 and GROUP_INFO_DTYPE.itemsize == 72
 assert QUEUE_INFO_DTYPE.itemsize == 152 and ALLOC_CFG_DTYPE.itemsize == 48 and ALLOC_RESULT_DTYPE.itemsize == 16
 
@@ -152,6 +157,7 @@ SYMBOLS = {
     "evg_upload_device": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "evg_run_resident": (C.c_int, [_P, C.c_int64, C.c_uint32]),
     "evg_download": (C.c_int, [_P, _P, _P]),
+    "evg_download_queue": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int64]),
     "evg_device_result_ptr": (_P, [_P]),
     "evg_bind_result_buffer": (C.c_int, [_P, _P, C.c_int64]),
     "evg_last_launch_count": (C.c_int64, [_P]),
@@ -159,6 +165,8 @@ SYMBOLS = {
     "evg_kernel_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
     "evg_general_timing_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "evg_deps_met_batch": (C.c_int, [_P, _P, _P]),
+    "evg_upload_with_deps": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64]),
+    "evg_download_deps": (C.c_int, [_P, _P, _P]),
     "evg_find_runnable_batch": (C.c_int, [_P, _P, _P, _P]),
     "evg_expected_durations_batch": (C.c_int, [_P, _P, _P]),
     "evg_prioritize_legacy_batch": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P]),

@@ -282,7 +282,8 @@ struct DDeps {
 };
 // met[t] bit 0: Task.DependenciesMet (with the HasDependenciesMet short-circuit); with `both`, bit 1:
 // Task.AllDependenciesSatisfied (task.go:795-821: the same walk without the short-circuit).
-__global__ void __launch_bounds__(256) k_deps_met(DDeps X, uint8_t* met, int* err, int both) {
+__global__ void __launch_bounds__(256) k_deps_met(DDeps X, uint8_t* met, int* err, int both, const int64_t* __restrict__ dep_fin,
+                                                  int64_t now, int64_t* __restrict__ met_time) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= X.n_tasks) return;
   const int64_t e0 = X.dep_off[t], e1 = X.dep_off[t + 1];
@@ -313,6 +314,31 @@ __global__ void __launch_bounds__(256) k_deps_met(DDeps X, uint8_t* met, int* er
     }
   }
   met[t] = uint8_t(((ok || shortcut) ? 1 : 0) | ((both && ok) ? 2 : 0));
+  if (met_time) {
+    // a fresh evaluation that comes out met stamps DependenciesMetTime (setDependenciesMetTime, task.go:653,673-684):
+    // the latest non-zero FinishedAt of the dependencies (utility.IsZeroTime: Go's zero time or the Unix epoch), else now
+    int64_t stamp = EVG_TIME_ZERO;
+    if (ok && !shortcut && e1 > e0) {
+      if (dep_fin)
+        for (int64_t e = e0; e < e1; e++) {
+          const int64_t f = dep_fin[e];
+          if (f != EVG_TIME_ZERO && f != 0 && f > stamp) stamp = f;
+        }
+      if (stamp == EVG_TIME_ZERO || stamp == 0) stamp = now;
+    }
+    met_time[t] = stamp;
+  }
+}
+
+// The resident planner inputs take the device's own verdict: the EVG_TF_DEPS_MET bit of every task, and for freshly
+// stamped tasks the later of the wait basis the caller gave (ScheduledTime) and the stamp (scheduler.go:119-122).
+__global__ void __launch_bounds__(256) k_apply_deps(int64_t n, const uint8_t* __restrict__ met, const int64_t* __restrict__ met_time,
+                                                    uint32_t* __restrict__ flags, int64_t* __restrict__ wbasis) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  flags[t] = (flags[t] & ~EVG_TF_DEPS_MET) | ((met[t] & 1) ? EVG_TF_DEPS_MET : 0u);
+  const int64_t s = met_time[t];
+  if (s != EVG_TIME_ZERO && s > wbasis[t]) wbasis[t] = s;
 }
 
 // The task finders' filter (task_finder.go:40-197) with a stable per-distro compaction: one block per distro,
@@ -689,6 +715,7 @@ struct evg_ctx {
   int64_t launches = 0;
   bool timed = false;
   bool adopted = false;  // task columns are caller-owned device memory (evg_upload_device)
+  bool deps_resident = false;  // evg_upload_with_deps left the verdicts and stamps of this tick on the device
   DevBuf b_prio, b_exp, b_qb, b_wb, b_nd, b_tgo, b_gid, b_vid, b_flags, b_depoff, b_depidx;
   DevBuf b_taskoff, b_groupoff, b_cfg, b_gmax, b_unitbase;
   DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_ca, b_crk, b_bestpair;
@@ -883,6 +910,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   c->T = T; c->E = E; c->G = G; c->U = U; c->NT = NT; c->Dn = D;
   c->t_pad = (T + 3) & ~int64_t(3);
   c->adopted = adopt;
+  c->deps_resident = false;
   c->Tgc = Tgc;
   c->max_groups = 0;
   for (int32_t d = 0; d < D; d++) c->max_groups = std::max(c->max_groups, dt->group_off[d + 1] - dt->group_off[d]);
@@ -1357,6 +1385,54 @@ int evg_download(evg_ctx* c, evg_plan_out* po, evg_alloc_out* ao) {
   return EVG_OK;
 }
 
+// TaskQueueItem rows of the persisted head of every queue (task_queue_persister.go:14-42): one thread per output row.
+__global__ void __launch_bounds__(256) k_project_queue(DTasks T, DDistros D, const int64_t* __restrict__ item_off, int64_t n_items,
+                                                       const int32_t* __restrict__ order, const int64_t* __restrict__ total_value,
+                                                       evg_queue_item* __restrict__ items) {
+  const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= n_items) return;
+  const int d = find_distro(item_off, 0, D.n - 1, j);
+  const int64_t base = D.task_off[d];
+  const int64_t r = j - item_off[d];
+  const int32_t i = order[base + r];
+  const int64_t t = base + i;
+  const int32_t gid = T.gid[t];
+  evg_queue_item q;
+  q.task = i;
+  q.group_index = T.tgo[t];
+  q.group_max_hosts = gid >= 0 ? D.gmax[D.group_off[d] + gid] : 0;
+  q.flags = (T.flags[t] & EVG_TF_DEPS_MET) ? EVG_QI_DEPS_MET : 0u;
+  q.priority = T.priority[t];
+  q.expected_ns = T.expected[t];
+  q.total_value = total_value[base + r];
+  items[j] = q;
+}
+
+int evg_download_queue(evg_ctx* c, int32_t cap, int64_t* item_off, evg_queue_item* items, int64_t items_capacity) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
+  if (!c->have_tasks) return fail(EVG_ERR_STATE, "evg_download_queue before evg_upload");
+  if (cap < 0 || !item_off) return fail(EVG_ERR_INVALID, "evg_download_queue: bad argument");
+  if (cap == 0) cap = EVG_PERSISTED_QUEUE_CAP;
+  const int32_t D = c->Dn;
+  item_off[0] = 0;
+  for (int32_t d = 0; d < D; d++) item_off[d + 1] = item_off[d] + std::min<int64_t>(c->h_taskoff[d + 1] - c->h_taskoff[d], cap);
+  const int64_t n = item_off[D];
+  if (n > items_capacity || (n > 0 && !items)) return fail(EVG_ERR_INVALID, "evg_download_queue: %lld rows needed, %lld available", (long long)n, (long long)items_capacity);
+  if (n == 0) return EVG_OK;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  CK(c->b_rn0.ensure(sizeof(int64_t) * size_t(D + 1)));
+  CK(c->b_rn1.ensure(sizeof(evg_queue_item) * size_t(n)));
+  CK(cudaMemcpyAsync(c->b_rn0.p, item_off, sizeof(int64_t) * size_t(D + 1), cudaMemcpyHostToDevice, s));
+  k_project_queue<<<grid_for(n, 256), 256, 0, s>>>(dtasks(c), ddistros(c), c->b_rn0.as<int64_t>(), n, c->b_order.as<int32_t>(),
+                                                 c->b_tv.as<int64_t>(), c->b_rn1.as<evg_queue_item>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(items, c->b_rn1.p, sizeof(evg_queue_item) * size_t(n), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return EVG_OK;
+}
+
 void* evg_device_result_ptr(evg_ctx* c) { return c ? (void*)c->result_ptr() : nullptr; }
 int evg_bind_result_buffer(evg_ctx* c, void* device_ptr, int64_t capacity) {
   if (!c) return fail(EVG_ERR_INVALID, "null context");
@@ -1592,7 +1668,8 @@ int evg_alloc_batch(evg_ctx* c, const evg_host_soa* hosts, const int64_t* host_o
 }
 
 // Stage an evg_deps_in table and run k_deps_met into b_dx7 (left on the device); `both` adds the no-short-circuit bit.
-static int deps_to_device(evg_ctx* c, const evg_deps_in* in, int both) {
+static int deps_to_device(evg_ctx* c, const evg_deps_in* in, int both, const int64_t* dep_finished = nullptr, int64_t now = 0,
+                          bool want_stamp = false) {
   const int64_t T = in->n_tasks, E = in->n_deps, X = in->n_ext;
   if (T < 0 || E < 0 || X < 0) return fail(EVG_ERR_INVALID, "negative sizes");
   if (T == 0) return EVG_OK;
@@ -1615,11 +1692,22 @@ static int deps_to_device(evg_ctx* c, const evg_deps_in* in, int both) {
   UPD(c->b_dx6, in->ext_state, X, uint8_t);
 #undef UPD
   CK(c->b_dx7.ensure(size_t(T)));
+  int64_t* stamp = nullptr;
+  const int64_t* fin = nullptr;
+  if (want_stamp) {
+    CK(c->b_rn7.ensure(sizeof(int64_t) * size_t(T)));
+    stamp = c->b_rn7.as<int64_t>();
+    if (dep_finished && E > 0) {
+      CK(c->b_rn6.ensure(sizeof(int64_t) * size_t(E)));
+      CK(cudaMemcpyAsync(c->b_rn6.p, dep_finished, sizeof(int64_t) * size_t(E), cudaMemcpyHostToDevice, s));
+      fin = c->b_rn6.as<int64_t>();
+    }
+  }
   DDeps d;
   d.n_tasks = T; d.dep_off = c->b_dx0.as<int64_t>(); d.dep_kind = c->b_dx1.as<uint8_t>(); d.dep_ref = c->b_dx2.as<int32_t>();
   d.dep_want = c->b_dx3.as<uint8_t>(); d.task_state = c->b_dx4.as<uint8_t>(); d.task_pre = c->b_dx5.as<uint8_t>();
   d.ext_state = c->b_dx6.as<uint8_t>(); d.n_ext = X;
-  k_deps_met<<<grid_for(T, 256), 256, 0, s>>>(d, c->b_dx7.as<uint8_t>(), c->b_err.as<int>(), both);
+  k_deps_met<<<grid_for(T, 256), 256, 0, s>>>(d, c->b_dx7.as<uint8_t>(), c->b_err.as<int>(), both, fin, now, stamp);
   c->launches++;
   CK(cudaGetLastError());
   return EVG_OK;
@@ -1641,6 +1729,44 @@ int evg_deps_met_batch(evg_ctx* c, const evg_deps_in* in, uint8_t* met) {
   CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (bad) return fail(EVG_ERR_INVALID, "a dep_ref is out of range");
+  return EVG_OK;
+}
+
+int evg_upload_with_deps(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* distros, const evg_host_soa* hosts,
+                         const int64_t* host_off, const evg_alloc_cfg* acfg, const evg_deps_in* deps, const int64_t* dep_finished_ns,
+                         int64_t now_ns) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
+  if (!tasks || !deps) return fail(EVG_ERR_INVALID, "evg_upload_with_deps: null argument");
+  if (deps->n_tasks != tasks->n_tasks) return fail(EVG_ERR_INVALID, "deps covers %lld tasks, the task table %lld", (long long)deps->n_tasks, (long long)tasks->n_tasks);
+  int rc = evg_upload(c, tasks, distros, hosts, host_off, acfg);
+  if (rc != EVG_OK) return rc;
+  const int64_t T = tasks->n_tasks;
+  if (T == 0) return EVG_OK;
+  cudaStream_t s = c->stream;
+  rc = deps_to_device(c, deps, 0, dep_finished_ns, now_ns, /*want_stamp=*/true);
+  if (rc != EVG_OK) { c->have_tasks = false; return rc; }
+  k_apply_deps<<<grid_for(T, 256), 256, 0, s>>>(T, c->b_dx7.as<uint8_t>(), c->b_rn7.as<int64_t>(), c->b_flags.as<uint32_t>(), c->b_wb.as<int64_t>());
+  c->launches++;
+  int bad = 0;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (bad) { c->have_tasks = false; return fail(EVG_ERR_INVALID, "a dep_ref is out of range"); }
+  c->deps_resident = true;
+  return EVG_OK;
+}
+
+int evg_download_deps(evg_ctx* c, uint8_t* met, int64_t* met_time_ns) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
+  if (!c->have_tasks) return fail(EVG_ERR_STATE, "evg_download_deps before evg_upload_with_deps");
+  CK(cudaSetDevice(c->device));
+  if (c->T == 0) return EVG_OK;
+  if (!c->deps_resident) return fail(EVG_ERR_STATE, "the resident tick was not uploaded with evg_upload_with_deps");
+  if (met) CK(cudaMemcpyAsync(met, c->b_dx7.p, size_t(c->T), cudaMemcpyDeviceToHost, c->stream));
+  if (met_time_ns) CK(cudaMemcpyAsync(met_time_ns, c->b_rn7.p, sizeof(int64_t) * size_t(c->T), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return EVG_OK;
 }
 

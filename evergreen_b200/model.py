@@ -105,6 +105,7 @@ class Task:
     version: str = ""
     project: str = ""
     build_variant: str = ""
+    revision: str = ""               # TaskQueueItem.Revision (task_queue_persister.go:28)
     build_id: str = ""               # legacy prioritiser only (task_priority_cmp.go:149-174, setup_funcs.go:72-87)
     revision_order_number: int = 0   # legacy prioritiser only (task_priority_cmp.go:75-84)
     display_name: str = ""
@@ -283,6 +284,36 @@ class DistroQueueInfo:  # model/task_queue.go:49-75
     count_wait_over_threshold: int = 0
     task_group_infos: List[TaskGroupInfo] = field(default_factory=list)
     secondary_queue: bool = False
+
+
+@dataclass
+class TaskQueueItem:  # model/task_queue.go:131-153
+    id: str = ""
+    is_dispatched: bool = False
+    display_name: str = ""
+    group: str = ""
+    group_max_hosts: int = 0
+    group_index: int = 0
+    version: str = ""
+    build_variant: str = ""
+    revision_order_number: int = 0
+    requester: str = ""
+    revision: str = ""
+    project: str = ""
+    expected_duration: int = 0
+    priority: int = 0
+    sorting_value_breakdown: Optional["SortingValueBreakdown"] = None
+    dependencies: List[str] = field(default_factory=list)
+    dependencies_met: bool = False
+    activated_by: str = ""
+
+
+@dataclass
+class TaskQueue:  # model/task_queue.go:117-123
+    distro: str = ""
+    generated_at: int = ZERO_TIME
+    queue: List[TaskQueueItem] = field(default_factory=list)
+    distro_queue_info: Optional["DistroQueueInfo"] = None
 
 
 @dataclass

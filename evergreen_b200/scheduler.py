@@ -112,6 +112,30 @@ class Engine:
         self._n_tasks, self._n_distros, self._n_groups = tasks.n_tasks, distros.n_distros, distros.n_groups
         self._has_hosts = hosts is not None
 
+    def upload_with_deps(self, tasks: S.TaskSoA, distros: S.DistroTable, hosts: Optional[S.HostSoA], deps: "S.DepsTable",
+                         dep_finished: Optional[np.ndarray], now: int) -> None:
+        """evg_upload_with_deps: the device evaluates Task.DependenciesMet and writes the deps-met bit and the stamped
+        wait basis of the resident columns itself."""
+        ts, ds, dp = tasks.struct(), distros.struct(), deps.struct()
+        fin = None
+        if dep_finished is not None and dep_finished.shape[0]:
+            fin = np.ascontiguousarray(dep_finished, dtype=np.int64)
+        if hosts is not None:
+            hs = hosts.struct()
+            L.check(self.lib.evg_upload_with_deps(self.ctx, C.byref(ts), C.byref(ds), C.byref(hs), L.ptr(hosts.host_off),
+                                                  L.ptr(hosts.cfg) if hosts.cfg.shape[0] else None, C.byref(dp), L.ptr(fin), int(now)))
+        else:
+            L.check(self.lib.evg_upload_with_deps(self.ctx, C.byref(ts), C.byref(ds), None, None, None, C.byref(dp), L.ptr(fin), int(now)))
+        self._n_tasks, self._n_distros, self._n_groups = tasks.n_tasks, distros.n_distros, distros.n_groups
+        self._has_hosts = hosts is not None
+
+    def download_deps(self):
+        """(met, met_time): the device's Task.DependenciesMet verdicts and DependenciesMetTime stamps of the resident tick."""
+        met = self._out("deps_met", self._n_tasks, np.uint8)
+        stamp = self._out("deps_stamp", self._n_tasks, np.int64)
+        L.check(self.lib.evg_download_deps(self.ctx, L.ptr(met) if self._n_tasks else None, L.ptr(stamp) if self._n_tasks else None))
+        return met, stamp
+
     def upload_device(self, cols: dict, n_tasks: int, distros: S.DistroTable, hosts: Optional[S.HostSoA] = None,
                       n_edges: int = 0) -> None:
         """evg_upload_device: the task columns already live in device memory.  `cols` maps the evg_task_soa column
@@ -147,6 +171,17 @@ class Engine:
         else:
             L.check(self.lib.evg_download(self.ctx, C.byref(ps), None))
         return po, ao
+
+    def download_queue(self, cap: int = 0, task_off=None):
+        """evg_download_queue: (item_off, items) -- the TaskQueueItem rows of the first min(length, cap) ranks of every
+        distro (cap 0 = the reference's 10 000), projected on the device; only those rows cross PCIe."""
+        D = self._n_distros
+        item_off = self._out("queue_item_off", D + 1, np.int64)
+        cap_eff = cap or L.EVG_PERSISTED_QUEUE_CAP
+        n = self._n_tasks if task_off is None else int(np.minimum(np.diff(task_off), cap_eff).sum())
+        items = self._out("queue_items", max(n, 1), L.QUEUE_ITEM_DTYPE)
+        L.check(self.lib.evg_download_queue(self.ctx, int(cap), L.ptr(item_off), L.ptr(items), int(max(n, 1))))
+        return item_off, items[: int(item_off[D])]
 
     def bind_result_buffer(self, device_ptr: int, capacity_rows: int) -> None:
         """The allocator kernel writes evg_alloc_result rows straight into this device buffer
@@ -293,6 +328,20 @@ def _queue_info_from_rows(q, groups, names: Sequence[str]) -> M.DistroQueueInfo:
         secondary_queue=bool(q["secondary_queue"]))
 
 
+def _upload_with_device_deps(eng: Engine, batch, soa, table, hosts, now: int, dependency_db) -> None:
+    """Upload a marshalled tick and let the device evaluate Task.DependenciesMet (scheduler.go:161-168) for it; the
+    DependenciesMetTime stamps it made are written back on the Task objects, like tasks[i] = task (scheduler.go:137)."""
+    pairs = [(d, t) for d, t in ((b[0], b[1]) for b in batch)]
+    eng.upload_with_deps(soa, table, hosts, S.marshal_deps(pairs, dependency_db), S.marshal_dep_finished(pairs), now)
+    _, stamp = eng.download_deps()
+    k = 0
+    for _, tasks in pairs:
+        for t in tasks:
+            if int(stamp[k]) != M.ZERO_TIME:
+                t.dependencies_met_time = int(stamp[k])
+            k += 1
+
+
 def plan_distros(batch: Sequence[Tuple[M.Distro, List[M.Task]]], now: int, *, engine: Optional[Engine] = None,
                  dependency_db: Optional[Dict[str, M.Task]] = None, breakdown: bool = True,
                  secondary: bool = False):
@@ -301,7 +350,9 @@ def plan_distros(batch: Sequence[Tuple[M.Distro, List[M.Task]]], now: int, *, en
     DistroQueueInfo)."""
     eng = engine or default_engine()
     soa, table, keys = S.marshal_tasks(batch, now, dependency_db)
-    po = eng.plan_batch(soa, table, now, breakdown=breakdown)
+    _upload_with_device_deps(eng, batch, soa, table, None, now, dependency_db)
+    eng.run(now, L.EVG_OPT_BREAKDOWN if breakdown else 0)
+    po, _ = eng.download(want_breakdown=breakdown, want_alloc=False)
     out = []
     for d, (distro, tasks) in enumerate(batch):
         a, b = int(table.task_off[d]), int(table.task_off[d + 1])
@@ -318,6 +369,73 @@ def plan_distros(batch: Sequence[Tuple[M.Distro, List[M.Task]]], now: int, *, en
         info.secondary_queue = secondary  # scheduler.go:44
         out.append((ranked, info))
     return out
+
+
+def persist_task_queues(batch: Sequence[Tuple[M.Distro, List[M.Task]]], now: int, *, engine: Optional[Engine] = None,
+                        dependency_db: Optional[Dict[str, M.Task]] = None, cap: int = 0) -> List[M.TaskQueue]:
+    """Batched PersistTaskQueue minus the upsert (scheduler/task_queue_persister.go:14-42, TaskQueue.Save
+    model/task_queue.go:216-219): plan every distro, then build each distro's TaskQueue document from the
+    TaskQueueItem rows the device projected for the first min(length, 10 000) ranks -- only those rows are copied
+    back -- plus the strings of the shim's own Task objects.  Tasks are stamped like the reference leaves them
+    (ExpectedDuration scheduler.go:98, DependenciesMetTime task.go:653, ScheduledTime / DependenciesMetTime
+    task.go:1164-1195 at `now`)."""
+    eng = engine or default_engine()
+    soa, table, keys = S.marshal_tasks(batch, now, dependency_db)
+    _upload_with_device_deps(eng, batch, soa, table, None, now, dependency_db)
+    eng.run(now)
+    po, _ = eng.download(want_alloc=False)
+    item_off, items = eng.download_queue(cap, table.task_off)
+    out = []
+    for d, (distro, tasks) in enumerate(batch):
+        ga, gb = int(table.group_off[d]), int(table.group_off[d + 1])
+        info = _queue_info_from_rows(po.info[d], po.group_info[ga:gb], keys[d].group_names)
+        queue = []
+        for row in items[int(item_off[d]):int(item_off[d + 1])]:
+            t = tasks[int(row["task"])]
+            t.expected_duration = int(row["expected_ns"])
+            t.sorting_value_breakdown = M.SortingValueBreakdown(total_value=int(row["total_value"]))
+            queue.append(M.TaskQueueItem(
+                id=t.id, display_name=t.display_name, build_variant=t.build_variant,
+                revision_order_number=t.revision_order_number, requester=t.requester, revision=t.revision, project=t.project,
+                expected_duration=int(row["expected_ns"]), priority=int(row["priority"]),
+                sorting_value_breakdown=t.sorting_value_breakdown, group=t.task_group,
+                group_max_hosts=t.task_group_max_hosts, group_index=int(row["group_index"]), version=t.version,
+                activated_by=t.activated_by, dependencies=[dep.task_id for dep in t.depends_on],
+                dependencies_met=bool(int(row["flags"]) & L.EVG_QI_DEPS_MET)))
+        for t in tasks:  # SetTasksScheduledAndDepsMetTime (model/task/task.go:1164-1195), every prioritised task
+            if M.is_zero_time(t.scheduled_time):
+                t.scheduled_time = now
+            if t.has_dependencies_met() and M.is_zero_time(t.dependencies_met_time):
+                t.dependencies_met_time = now
+        out.append(M.TaskQueue(distro=distro.id, generated_at=now, queue=queue, distro_queue_info=info))
+    return out
+
+
+def PersistTaskQueue(distro: M.Distro, tasks: List[M.Task], *, now: int, engine: Optional[Engine] = None,
+                     dependency_db: Optional[Dict[str, M.Task]] = None) -> M.TaskQueue:
+    """scheduler.PersistTaskQueue for one distro; the caller upserts the returned document."""
+    return persist_task_queues([(distro, tasks)], now, engine=engine, dependency_db=dependency_db)[0]
+
+
+def PlanDistro(distro: M.Distro, find_tasks, *, now: int, engine: Optional[Engine] = None,
+               dependency_db: Optional[Dict[str, M.Task]] = None, existing_queue_length: int = 0):
+    """scheduler.PlanDistro (scheduler/wrapper.go:30-130) without its Mongo calls: a disabled distro is not planned
+    -- its persisted queue is cleared when it has one (wrapper.go:45-78; returns (None, True iff cleared)) --
+    otherwise the task finder runs and the queue is planned and projected (returns (TaskQueue, False)).
+    Unscheduling of stale tasks (underwaterUnschedule, wrapper.go:41) is a database update and stays with the caller."""
+    if distro.disabled:
+        return None, existing_queue_length > 0
+    tasks = list(find_tasks(distro))
+    return PersistTaskQueue(distro, tasks, now=now, engine=engine, dependency_db=dependency_db), False
+
+
+def hosts_to_request(distro: M.Distro, info: M.DistroQueueInfo, n_provisioning_hosts: int, allocate) -> Tuple[int, int]:
+    """The allocator call of hostAllocatorJob.Run (units/host_allocator.go:180-196): a single-task distro spawns one
+    host per queued task whose dependencies are met, minus the hosts already provisioning (:182-184); every other distro
+    asks the HostAllocator (`allocate()` -> (new_hosts, free_hosts))."""
+    if distro.single_task_distro:
+        return info.length_with_dependencies_met - n_provisioning_hosts, 0
+    return allocate()
 
 
 def PrioritizeTasks(d: M.Distro, tasks: List[M.Task], opts: Optional[TaskPlannerOptions] = None, *, now: int,
@@ -345,7 +463,9 @@ def GetDistroQueueInfo(distro: M.Distro, tasks: List[M.Task], max_duration_thres
                                      if opts.includes_dependencies else "")
     eng = engine or default_engine()
     soa, table, keys = S.marshal_tasks([(d, tasks)], now, dependency_db)
-    po = eng.plan_batch(soa, table, now)
+    _upload_with_device_deps(eng, [(d, tasks)], soa, table, None, now, dependency_db)
+    eng.run(now)
+    po, _ = eng.download(want_alloc=False)
     info = _queue_info_from_rows(po.info[0], po.group_info, keys[0].group_names)
     return info
 
@@ -446,7 +566,9 @@ def plan_and_allocate(batch: Sequence[Tuple[M.Distro, List[M.Task], M.HostAlloca
     eng = engine or default_engine()
     soa, table, keys = S.marshal_tasks([(d, t) for d, t, _ in batch], now, dependency_db)
     hosts = S.marshal_hosts([h for _, _, h in batch], [k.group_names for k in keys])
-    po, ao = eng.plan_and_alloc_batch(soa, table, hosts, now)
+    _upload_with_device_deps(eng, batch, soa, table, hosts, now, dependency_db)
+    eng.run(now)
+    po, ao = eng.download()
     out = []
     for i, (distro, tasks, _) in enumerate(batch):
         a, b = int(table.task_off[i]), int(table.task_off[i + 1])

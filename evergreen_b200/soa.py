@@ -196,10 +196,13 @@ def satisfies_dependency(dep: M.Dependency, dep_task: M.Task) -> bool:
     return False
 
 
-def dependencies_met(t: M.Task, in_queue: Dict[str, M.Task], db: Optional[Dict[str, M.Task]]) -> bool:
+def dependencies_met(t: M.Task, in_queue: Dict[str, M.Task], db: Optional[Dict[str, M.Task]],
+                     now: Optional[int] = None) -> bool:
     """Task.DependenciesMet (model/task/task.go:632-671) against the in-queue
     cache first, then `db` (the tasks collection lookup); a missing dependency
-    is the lookup error checkDependenciesMet turns into false (scheduler.go:161-168)."""
+    is the lookup error checkDependenciesMet turns into false (scheduler.go:161-168).
+    With `now`, a fresh evaluation that comes out met stamps DependenciesMetTime on the task like the reference
+    does (setDependenciesMetTime, task.go:653,673-684): the latest non-zero FinishedAt of its dependencies, else now."""
     if t.has_dependencies_met():
         return True
     for dep in t.depends_on:
@@ -210,6 +213,12 @@ def dependencies_met(t: M.Task, in_queue: Dict[str, M.Task], db: Optional[Dict[s
             return False
         if not satisfies_dependency(dep, dep_task):
             return False
+    if now is not None:
+        best = M.ZERO_TIME
+        for dep in t.depends_on:
+            if not M.is_zero_time(dep.finished_at) and dep.finished_at > best:
+                best = dep.finished_at
+        t.dependencies_met_time = now if M.is_zero_time(best) else best
     return True
 
 
@@ -221,12 +230,14 @@ class MarshalledDistro:
 
 
 def marshal_tasks(batch: Sequence[tuple], now: int, dependency_db: Optional[Dict[str, M.Task]] = None,
-                  duration_history: Optional[dict] = None):
+                  duration_history: Optional[dict] = None, resolve_deps: bool = False):
     """[(Distro, [Task])] -> (TaskSoA, DistroTable, [MarshalledDistro]).
 
-    Per task this resolves what the reference computes lazily on the path:
-    FetchExpectedDuration (PopulateCaches, setup_funcs.go:20-67) and
-    DependenciesMet (scheduler.go:161-168)."""
+    Per task this resolves FetchExpectedDuration (PopulateCaches, setup_funcs.go:20-67).  Task.DependenciesMet
+    (scheduler.go:161-168) is the DEVICE's job: the product path pairs these columns with marshal_deps() and
+    Engine.upload_with_deps(), which sets the EVG_TF_DEPS_MET bit and the stamped wait basis on the GPU.
+    resolve_deps=True evaluates it here instead (host restatement, kept for tests and for callers of the plain
+    one-shot entry points that want self-contained columns)."""
     cols = {name: [] for name, _ in TaskSoA.COLUMNS}
     dep_off, dep_idx = [0], []
     task_off, group_off, cfg_rows, gmax, keys = [0], [0], [], [], []
@@ -255,17 +266,24 @@ def marshal_tasks(batch: Sequence[tuple], now: int, dependency_db: Optional[Dict
                 vid = versions[t.version] = len(versions)
                 md.versions.append(t.version)
             qb = t.activated_time if t.activated_time != M.ZERO_TIME else t.ingest_time  # planner.go:318-322
-            wb = max(t.scheduled_time, t.dependencies_met_time)  # scheduler.go:119-122 (ZERO_TIME sorts first)
+            # checkDependenciesMet runs first (scheduler.go:82-98) and, on a fresh evaluation, stamps DependenciesMetTime
+            # on the task (task.go:653); the wait is measured after that (scheduler.go:119-123)
+            deps_met = dependencies_met(t, by_id, dependency_db, now) if resolve_deps else False
+            wb = max(t.scheduled_time, t.dependencies_met_time)  # ZERO_TIME sorts first
             fl = requester_class(t.requester)
             if t.generate_task:
                 fl |= L.EVG_TF_GENERATE
             if t.activated_by == M.STEPBACK_TASK_ACTIVATOR:
                 fl |= L.EVG_TF_STEPBACK
-            if dependencies_met(t, by_id, dependency_db):
+            if deps_met:
                 fl |= L.EVG_TF_DEPS_MET
             if t.distro_id != d.id:
                 fl |= L.EVG_TF_OTHER_DISTRO
-            cols["priority"].append(max(-2 ** 31, min(2 ** 31 - 1, t.priority)))
+            if not -2 ** 31 <= t.priority < 2 ** 31 or not -2 ** 31 <= t.num_dependents < 2 ** 31:
+                # evg_task_soa carries both as int32; Go's Task.Priority is an int64 whose valid range ends at
+                # evergreen.MaxTaskPriority (100, globals.go:185), so a value out here is a corrupt document
+                raise ValueError(f"task {t.id!r}: priority {t.priority} / num_dependents {t.num_dependents} outside int32")
+            cols["priority"].append(t.priority)
             cols["expected_ns"].append(avg)
             cols["queue_basis_ns"].append(qb)
             cols["wait_basis_ns"].append(wb)
@@ -416,6 +434,11 @@ class DepsTable:
         s.task_state, s.task_pre = L.ptr(self.task_state), L.ptr(self.task_pre)
         s.ext_state = L.ptr(self.ext_state) if s.n_ext else None
         return s
+
+
+def marshal_dep_finished(batch: Sequence[tuple]) -> np.ndarray:
+    """Dependency.FinishedAt of every dependency, in marshal_deps' order (what setDependenciesMetTime reads)."""
+    return np.array([d.finished_at for _, tasks in batch for t in tasks for d in t.depends_on], dtype=np.int64)
 
 
 def marshal_deps(batch: Sequence[tuple], dependency_db: Optional[Dict[str, M.Task]] = None) -> DepsTable:

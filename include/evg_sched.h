@@ -285,6 +285,32 @@ int evg_upload_device(evg_ctx* ctx, const evg_task_soa* device_tasks, const evg_
 int evg_run_resident(evg_ctx* ctx, int64_t now_ns, uint32_t opts);
 /* Wait for the stream and copy results out; either pointer may be NULL. */
 int evg_download(evg_ctx* ctx, evg_plan_out* plan_out, evg_alloc_out* alloc_out);
+/* ---- the persisted queue ---- */
+
+#define EVG_QI_DEPS_MET 0x1u /* TaskQueueItem.DependenciesMet = Task.HasDependenciesMet() after GetDistroQueueInfo
+                                stamped the task (scheduler.go:98,137; model/task/task.go:653,3393) */
+/* The numeric half of model.TaskQueueItem (model/task_queue.go:131-153) for one persisted rank; the string half
+ * (Id, DisplayName, BuildVariant, Requester, Revision, Project, Group, Version, ActivatedBy, Dependencies) is read by
+ * the shim from its own []task.Task at index `task`.  40 B. */
+typedef struct {
+  int32_t task;            /* distro-local index of the task at this rank */
+  int32_t group_index;     /* GroupIndex = Task.TaskGroupOrder */
+  int32_t group_max_hosts; /* GroupMaxHosts = Task.TaskGroupMaxHosts (0 outside task groups) */
+  uint32_t flags;          /* EVG_QI_* */
+  int64_t priority;        /* Priority */
+  int64_t expected_ns;     /* ExpectedDuration as GetDistroQueueInfo left it (scheduler.go:98) */
+  int64_t total_value;     /* SortingValueBreakdown.TotalValue of the unit the task was emitted from (planner.go:475) */
+} evg_queue_item;
+#define EVG_PERSISTED_QUEUE_CAP 10000 /* TaskQueue.Save keeps the first 10 000 items (model/task_queue.go:216-219) */
+
+/* After evg_run_resident: project the head of every distro's ranked queue -- the first min(length, cap) ranks, cap = 0
+ * meaning EVG_PERSISTED_QUEUE_CAP -- into TaskQueueItem rows on the device and copy only those to the host.
+ * item_off (n_distros + 1) receives the offsets of each distro's rows in `items`; `items_capacity` rows must be
+ * available (sum over distros of min(length, cap); -EVG_ERR_INVALID with the needed count in evg_last_error otherwise).
+ * Replaces: the TaskQueueItem projection and truncation of PersistTaskQueue / TaskQueue.Save
+ * (scheduler/task_queue_persister.go:14-42, model/task_queue.go:216-219).  The upsert stays with the caller. */
+int evg_download_queue(evg_ctx* ctx, int32_t cap, int64_t* item_off, evg_queue_item* items, int64_t items_capacity);
+
 /* Device pointer to the resident evg_alloc_result[n_distros] vector, the
  * send buffer of the per-distro all-gather. */
 void* evg_device_result_ptr(evg_ctx* ctx);
@@ -345,6 +371,22 @@ typedef struct {
  * SatisfiesDependency :529-543): the bit evg_task_soa.flags carries as EVG_TF_DEPS_MET and the predicate the
  * task finders filter on (scheduler/task_finder.go:40-197).  Host pointers in and out. */
 int evg_deps_met_batch(evg_ctx* ctx, const evg_deps_in* in, uint8_t* met);
+
+/* evg_upload with the dependency predicate evaluated ON THE DEVICE and wired into the planner's inputs: after the
+ * copy, Task.DependenciesMet runs for every task (same tables as evg_deps_met_batch, over the same n_tasks tasks) and
+ *   - the EVG_TF_DEPS_MET bit of the resident flags column is set from its verdict (the caller's bit is ignored);
+ *   - a task whose dependencies were evaluated afresh and found met is stamped like Task.setDependenciesMetTime does
+ *     (model/task/task.go:653,673-684): the latest non-zero dep_finished_ns[] (Dependency.FinishedAt, per dependency,
+ *     NULL = unknown) of its dependencies, else now_ns; its resident wait basis becomes the later of the caller's
+ *     wait_basis_ns (ScheduledTime) and that stamp (scheduler.go:119-122).
+ * Neither the bit nor the stamp visits the host; evg_download_deps returns them for the write-back the reference does
+ * (UpdateOne of DependenciesMetTime, task.go:659-666).
+ * Replaces: checkDependenciesMet inside GetDistroQueueInfo (scheduler/scheduler.go:82-98,161-168). */
+int evg_upload_with_deps(evg_ctx* ctx, const evg_task_soa* tasks, const evg_distro_table* distros,
+                         const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg,
+                         const evg_deps_in* deps, const int64_t* dep_finished_ns, int64_t now_ns);
+/* met[t] = Task.DependenciesMet; met_time_ns[t] = the stamp (EVG_TIME_ZERO when nothing was stamped).  Either may be NULL. */
+int evg_download_deps(evg_ctx* ctx, uint8_t* met, int64_t* met_time_ns);
 
 /* ---- runnable-task filter: the task finders ------------- */
 

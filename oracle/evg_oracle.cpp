@@ -287,6 +287,8 @@ PlanResult plan(const View& v, const evo_planner_settings& s, int64_t now) {
 }
 
 // ---- Task.DependenciesMet: model/task/task.go:529-543,632-671,3393-3395 ----
+// bit 0: Task.DependenciesMet; bit 1: the dependencies were evaluated afresh (no HasDependenciesMet short-circuit),
+// which is when the reference also runs setDependenciesMetTime on the task (task.go:653).
 std::vector<uint8_t> deps_met(const View& v) {
   const evo_tasks& t = *v.t;
   std::unordered_map<std::string_view, int64_t> cache;  // depCache scheduler.go:61-64
@@ -296,7 +298,7 @@ std::vector<uint8_t> deps_met(const View& v) {
     int64_t gi = v.g(i);
     int64_t e0 = t.dep_off ? t.dep_off[gi] : 0, e1 = t.dep_off ? t.dep_off[gi + 1] : 0;
     if (e1 == e0 || (t.override_dependencies && t.override_dependencies[gi]) ||
-        !util_is_zero_time(t.dependencies_met_time[gi])) {  // HasDependenciesMet task.go:3393
+        !util_is_zero_time(t.dependencies_met_time[gi])) {  // HasDependenciesMet task.go:3393: nothing is stamped
       met[i] = 1;
       continue;
     }
@@ -322,9 +324,22 @@ std::vector<uint8_t> deps_met(const View& v) {
       else if (want == "*") ok = dep_status == "failed" || dep_status == "success" || dep_blocked;
       else ok = false;
     }
-    met[i] = ok ? 1 : 0;
+    met[i] = ok ? 3 : 0;
   }
   return met;
+}
+
+// Task.setDependenciesMetTime (model/task/task.go:673-684): the latest non-zero FinishedAt of the dependencies, else now.
+int64_t fresh_dependencies_met_time(const View& v, int64_t i, int64_t now) {
+  const evo_tasks& t = *v.t;
+  const int64_t gi = v.g(i);
+  int64_t best = EVO_TIME_ZERO;  // utility.ZeroTime
+  if (t.dep_off && t.dep_finished_at)
+    for (int64_t e = t.dep_off[gi]; e < t.dep_off[gi + 1]; e++) {
+      const int64_t f = t.dep_finished_at[e];
+      if (!util_is_zero_time(f) && after(f, best)) best = f;
+    }
+  return util_is_zero_time(best) ? now : best;
 }
 
 int64_t target_time(const evo_planner_settings& s) {  // model/distro/distro.go:422-440
@@ -352,7 +367,7 @@ QueueInfo queue_info(const View& v, const int64_t* order, int64_t n_order, std::
     if (!sv(t.task_group, gi).empty()) name = task_group_string(v, i);
     int64_t duration = t.expected_ns[gi];
     if (sv(t.distro_id, gi) != distro_id) q.info.secondary_queue = 1;
-    bool dm = met[i] != 0;
+    bool dm = (met[i] & 1) != 0;
     bool counted = !includes_deps || dm;
     auto it = gmap.find(name);
     size_t gidx;
@@ -386,8 +401,11 @@ QueueInfo queue_info(const View& v, const int64_t* order, int64_t n_order, std::
         q.info.duration_over_threshold = wadd(q.info.duration_over_threshold, duration);
       }
       if (dm) {
+        // checkDependenciesMet ran on the loop's copy of the task first (scheduler.go:82-98): a fresh evaluation has
+        // already stamped DependenciesMetTime on it (task.go:653) when the wait is measured (scheduler.go:119-123)
+        const int64_t met_time = (met[i] & 2) ? fresh_dependencies_met_time(v, i, now) : t.dependencies_met_time[gi];
         int64_t start = t.scheduled_time[gi];
-        if (after(t.dependencies_met_time[gi], start)) start = t.dependencies_met_time[gi];
+        if (after(met_time, start)) start = met_time;
         int64_t wait = since(now, start);
         if (wait > threshold) { g.count_wait_over_threshold++; q.info.count_wait_over_threshold++; }
       }
@@ -572,7 +590,7 @@ int64_t evo_plan(const evo_tasks* t, const evo_planner_settings* s, int64_t now,
 void evo_deps_met(const evo_tasks* t, uint8_t* out_met) {
   View v{t, 0, t->n};
   std::vector<uint8_t> m = deps_met(v);
-  std::memcpy(out_met, m.data(), m.size());
+  for (size_t k = 0; k < m.size(); k++) out_met[k] = m[k] & 1;
 }
 
 int64_t evo_get_distro_queue_info(const evo_tasks* t, const int64_t* order, int64_t n_order, const char* distro_id,

@@ -60,6 +60,9 @@ typedef struct {
   const uint8_t* dep_found;
   evo_strcol dep_task_status;
   const uint8_t* dep_task_blocked;
+  /* Dependency.FinishedAt per dependency (model/task/task.go Dependency); NULL = all zero.  Read by
+   * setDependenciesMetTime (task.go:673-684) when DependenciesMet evaluates the dependencies afresh. */
+  const int64_t* dep_finished_at;
 } evo_tasks;
 
 /* distro.PlannerSettings (model/distro/distro.go:286-300) + the dispatcher bit */

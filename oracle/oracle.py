@@ -45,7 +45,7 @@ class Tasks(C.Structure):
                                   "generate_task", "override_dependencies", "blocked", "activated_time", "ingest_time",
                                   "scheduled_time", "dependencies_met_time", "expected_ns", "dep_off")] + [
         ("dep_task_id", StrCol), ("dep_status", StrCol), ("dep_found", C.c_void_p), ("dep_task_status", StrCol),
-        ("dep_task_blocked", C.c_void_p)]
+        ("dep_task_blocked", C.c_void_p), ("dep_finished_at", C.c_void_p)]
 
 
 class PlannerSettings(C.Structure):
@@ -161,12 +161,13 @@ def tasks_struct(tasks: Sequence[M.Task], now: int, dependency_db: Optional[Dict
     if expected is None:
         expected = [fetch_expected_duration(x, now)[0] for x in tasks]
     t.expected_ns = k.arr(expected, np.int64)
-    dep_off, ids, want, found, dstat, dblk = [0], [], [], [], [], []
+    dep_off, ids, want, found, dstat, dblk, dfin = [0], [], [], [], [], [], []
     db = dependency_db or {}
     for x in tasks:
         for d in x.depends_on:
             ids.append(d.task_id)
             want.append(d.status)
+            dfin.append(d.finished_at)
             dt = db.get(d.task_id)
             found.append(dt is not None)
             dstat.append(dt.status if dt else "")
@@ -178,6 +179,7 @@ def tasks_struct(tasks: Sequence[M.Task], now: int, dependency_db: Optional[Dict
     t.dep_found = k.arr(found, np.uint8)
     t.dep_task_status = k.strcol(dstat)
     t.dep_task_blocked = k.arr(dblk, np.uint8)
+    t.dep_finished_at = k.arr(dfin, np.int64)
     return t, k
 
 
@@ -501,6 +503,9 @@ class SoAJob:
                 found.append(0)
             dep_off.append(len(dep_ids))
         dep_cnt = np.diff(np.array(dep_off, dtype=np.int64))
+        # the SoA's deps-met bit and wait basis are already resolved: OverrideDependencies makes every met task with
+        # dependencies take the HasDependenciesMet short-circuit (task.go:3393), so the oracle does not re-stamp
+        # DependenciesMetTime (task.go:653) on them
         t.override_dependencies = k.arr(met & (dep_cnt > 0), np.uint8)
         t.blocked = k.arr(np.zeros(n), np.uint8)
         t.activated_time = k.arr(soa.queue_basis_ns[gidx], np.int64)
@@ -514,6 +519,7 @@ class SoAJob:
         t.dep_found = k.arr(np.zeros(len(dep_ids)), np.uint8)  # edges resolve in-queue; the extra one is missing
         t.dep_task_status = k.strcol([""] * len(dep_ids))
         t.dep_task_blocked = k.arr(np.zeros(len(dep_ids)), np.uint8)
+        t.dep_finished_at = None
         # settings
         self.ps = (PlannerSettings * max(len(sel), 1))()
         self.distro_ids = (C.c_char_p * max(len(sel), 1))()

@@ -894,3 +894,133 @@ def test_two_contexts_two_threads(engine):
     assert rcs == [0] * 20
     po, ao = engine.download()
     assert np.array_equal(po.order, want[0][0]) and np.array_equal(ao.result, want[0][1])
+
+
+def test_persisted_queue_projection(engine):
+    """evg_download_queue: TaskQueueItem rows of the first min(length, cap) ranks, projected on the
+    device -- equal to gathering the same fields on the host from the full download; the default cap is the
+    reference's 10 000 (TaskQueue.Save, model/task_queue.go:216-219)."""
+    w = synth.make(np.array([700, 0, 30, 15000, 12000, 3]), 230, zipf_priority=True, tg_frac=0.15, unmet_dep_frac=0.1,
+                   includes_dependencies=True, n_hosts=30)
+    engine.upload(w.tasks, w.distros, w.hosts)
+    engine.run(w.now)
+    po, _ = copy.deepcopy(engine.download())
+    toff, goff = w.distros.task_off, w.distros.group_off
+    for cap in (0, 50, 1):
+        item_off, items = engine.download_queue(cap, toff)
+        eff = cap or 10000
+        assert np.array_equal(np.diff(item_off), np.minimum(np.diff(toff), eff))
+        for d in range(w.distros.n_distros):
+            rows = items[int(item_off[d]):int(item_off[d + 1])]
+            n = rows.shape[0]
+            a = int(toff[d])
+            idx = po.order[a:a + n].astype(np.int64)
+            assert np.array_equal(rows["task"], po.order[a:a + n])
+            assert np.array_equal(rows["total_value"], po.total_value[a:a + n])
+            g = a + idx
+            assert np.array_equal(rows["priority"], w.tasks.priority[g]) and np.array_equal(rows["expected_ns"], w.tasks.expected_ns[g])
+            assert np.array_equal(rows["group_index"], w.tasks.task_group_order[g])
+            assert np.array_equal((rows["flags"] & L.EVG_QI_DEPS_MET) != 0, (w.tasks.flags[g] & L.EVG_TF_DEPS_MET) != 0)
+            gid = w.tasks.group_id[g]
+            want_max = np.where(gid >= 0, w.distros.group_max_hosts[np.clip(int(goff[d]) + gid, 0, None)], 0)
+            assert np.array_equal(rows["group_max_hosts"], want_max)
+    with pytest.raises(L.EvgError):
+        buf = np.zeros(3, dtype=L.QUEUE_ITEM_DTYPE)
+        off = np.zeros(w.distros.n_distros + 1, dtype=np.int64)
+        L.check(engine.lib.evg_download_queue(engine.ctx, 0, L.ptr(off), L.ptr(buf), 3))
+
+
+def test_persist_task_queue_mirror(engine):
+    """scheduler.PersistTaskQueue / PlanDistro mirrors: TaskQueue documents with the reference's item fields, a
+    12 000-task queue truncated to 10 000, a disabled distro cleared instead of planned, the single-task-distro bypass."""
+    rng = np.random.default_rng(3)
+    def tasks(n, tag):
+        return [M.Task(id=f"{tag}{k}", display_name=f"dn{k}", build_variant="bv", project="p", version=f"v{k % 7}",
+                       requester=M.PATCH_VERSION_REQUESTER if k % 3 else M.REPOTRACKER_VERSION_REQUESTER, revision=f"r{k % 5}",
+                       revision_order_number=k % 11, priority=int(rng.integers(0, 5)), num_dependents=int(rng.integers(0, 3)),
+                       activated_time=synth.NOW_NS - int(rng.integers(0, 10 ** 13)), distro_id=tag, activated_by="user",
+                       expected_duration=int(rng.integers(1, 60)) * M.MINUTE,
+                       depends_on=[M.Dependency("nowhere")] if k % 50 == 7 else []) for k in range(n)]
+    da, db = M.Distro(id="a"), M.Distro(id="b")
+    ta, tb = tasks(12000, "a"), tasks(40, "b")
+    qa, qb = S.persist_task_queues([(da, ta), (db, tb)], synth.NOW_NS, engine=engine)
+    assert len(qa.queue) == 10000 and len(qb.queue) == 40 and qa.distro == "a"
+    assert qa.distro_queue_info.length == 12000 and qb.distro_queue_info.length == 40
+    plan, info = S.PrioritizeTasks(db, tasks(40, "b"), now=synth.NOW_NS, engine=engine)
+    assert [i.id for i in qb.queue] == [t.id for t in plan]
+    by_id = {t.id: t for t in tb}
+    for it, t in zip(qb.queue, plan):
+        src = by_id[it.id]
+        assert (it.display_name, it.build_variant, it.requester, it.revision, it.project, it.version, it.activated_by) == \
+               (src.display_name, "bv", src.requester, src.revision, "p", src.version, "user")
+        assert it.revision_order_number == src.revision_order_number and it.priority == src.priority
+        assert it.expected_duration == src.expected_duration and it.dependencies == [d.task_id for d in src.depends_on]
+        assert it.dependencies_met == (not src.depends_on)
+        assert it.sorting_value_breakdown.total_value == t.sorting_value_breakdown.total_value
+    assert all(t.scheduled_time == synth.NOW_NS for t in tb)  # SetTasksScheduledAndDepsMetTime
+    assert all((t.dependencies_met_time == synth.NOW_NS) == (not t.depends_on) for t in tb)
+    # PlanDistro: disabled distro
+    q, cleared = S.PlanDistro(M.Distro(id="x", disabled=True), lambda d: 1 / 0, now=synth.NOW_NS, engine=engine, existing_queue_length=5)
+    assert q is None and cleared
+    q, cleared = S.PlanDistro(db, lambda d: tasks(40, "b"), now=synth.NOW_NS, engine=engine)
+    assert [i.id for i in q.queue] == [i.id for i in qb.queue] and not cleared
+    # units/host_allocator.go:182-184
+    assert S.hosts_to_request(M.Distro(id="s", single_task_distro=True), qb.distro_queue_info, 3, lambda: 1 / 0) == \
+           (qb.distro_queue_info.length_with_dependencies_met - 3, 0)
+    assert S.hosts_to_request(db, qb.distro_queue_info, 3, lambda: (7, 2)) == (7, 2)
+
+
+def test_device_side_dependency_wiring(engine):
+    """evg_upload_with_deps: the device evaluates Task.DependenciesMet and writes the EVG_TF_DEPS_MET bit and the
+    stamped wait basis of the resident columns itself -- equal to the host restatement (marshal_tasks
+    resolve_deps=True), on tasks, queue info and allocator decisions; the stamps come back for the write-back."""
+    import random
+    rng = random.Random(17)
+    NOWT = synth.NOW_NS
+    batch, db = [], {}
+    for di in range(4):
+        n = [60, 0, 400, 1500][di]
+        tasks = []
+        for i in range(n):
+            t = M.Task(id=f"d{di}t{i}", version=f"v{i % 5}", project="p", build_variant="bv", distro_id=f"d{di}",
+                       requester=rng.choice([M.PATCH_VERSION_REQUESTER, M.REPOTRACKER_VERSION_REQUESTER, M.GITHUB_MERGE_REQUESTER]),
+                       priority=rng.randrange(3), num_dependents=rng.randrange(3), expected_duration=rng.randrange(1, 90) * M.MINUTE,
+                       activated_time=NOWT - rng.randrange(10 ** 13), scheduled_time=rng.choice([M.ZERO_TIME, NOWT - rng.randrange(4 * M.HOUR)]),
+                       dependencies_met_time=rng.choice([M.ZERO_TIME, M.ZERO_TIME, NOWT - rng.randrange(3 * M.HOUR)]),
+                       override_dependencies=rng.random() < 0.05)
+            for _ in range(rng.choice([0, 0, 0, 1, 2])):
+                target = rng.choice([f"d{di}t{rng.randrange(n)}", f"ext{rng.randrange(8)}", "missing"])
+                t.depends_on.append(M.Dependency(target, status=rng.choice(["", "success", "failed", "*"]),
+                                                 finished_at=rng.choice([M.ZERO_TIME, 0, NOWT - rng.randrange(2 * M.HOUR)])))
+            tasks.append(t)
+        d = M.Distro(id=f"d{di}", dispatcher_settings=M.DispatcherSettings(M.DISPATCHER_VERSION_REVISED_WITH_DEPENDENCIES if di % 2 else ""))
+        batch.append((d, tasks))
+    for k in range(8):
+        db[f"ext{k}"] = M.Task(id=f"ext{k}", status=rng.choice([M.TASK_SUCCEEDED, M.TASK_FAILED, "started"]))
+    host_side = copy.deepcopy(batch)
+    soa_h, table_h, _ = soa.marshal_tasks(host_side, NOWT, db, resolve_deps=True)
+    po_h = copy.deepcopy(engine.plan_batch(soa_h, table_h, NOWT))
+    soa_d, table_d, _ = soa.marshal_tasks(batch, NOWT, db)
+    assert not (soa_d.flags & L.EVG_TF_DEPS_MET).any()
+    engine.upload_with_deps(soa_d, table_d, None, soa.marshal_deps(batch, db), soa.marshal_dep_finished(batch), NOWT)
+    engine.run(NOWT)
+    po_d, _ = engine.download(want_alloc=False)
+    for f in ("order", "total_value", "info", "group_info"):
+        assert np.array_equal(getattr(po_h, f), getattr(po_d, f)), f
+    met, stamp = engine.download_deps()
+    want_met = [(f & L.EVG_TF_DEPS_MET) != 0 for f in soa_h.flags.tolist()]
+    assert met.astype(bool).tolist() == want_met
+    flat_h = [t for _, ts in host_side for t in ts]
+    flat_d = [t for _, ts in batch for t in ts]
+    n_stamped = 0
+    for th, td, s in zip(flat_h, flat_d, stamp.tolist()):
+        if th.dependencies_met_time != td.dependencies_met_time:  # the host restatement stamped the task: so did the device
+            assert s == th.dependencies_met_time
+            n_stamped += 1
+        else:
+            assert s == M.ZERO_TIME
+    assert n_stamped > 20
+    # the reference-shaped mirrors take the same route and write the stamps back
+    plan, info = S.PrioritizeTasks(batch[2][0], batch[2][1], now=NOWT, engine=engine, dependency_db=db)
+    assert [t.dependencies_met_time for t in batch[2][1]] == [t.dependencies_met_time for t in host_side[2][1]]
+    assert info.length_with_dependencies_met == int(po_h.info[2]["length_with_dependencies_met"])

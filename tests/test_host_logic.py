@@ -238,3 +238,46 @@ def test_queue_info_rows_round_trip():
             for f in ("count", "max_hosts", "expected_duration", "count_duration_over_threshold", "count_wait_over_threshold",
                       "count_dep_filled_merge_queue_tasks", "duration_over_threshold"):
                 assert int(row[f]) == getattr(g, f), (d, k, f)
+
+
+def test_fresh_dependency_evaluation_stamps_the_met_time():
+    """GetDistroQueueInfo measures the wait AFTER checkDependenciesMet ran on the task (scheduler.go:82-123), and a fresh
+    evaluation that comes out met stamps DependenciesMetTime = latest non-zero dependency FinishedAt, else now
+    (Task.DependenciesMet -> setDependenciesMetTime, model/task/task.go:653,673-684).  So a task seen for the first
+    time with its dependencies met has waited since they finished -- not since it was scheduled."""
+    sched = NOW - 3 * M.HOUR
+    ext = {"e1": M.Task(id="e1", status=M.TASK_SUCCEEDED), "e2": M.Task(id="e2", status=M.TASK_SUCCEEDED)}
+
+    def mk():
+        return [
+            M.Task(id="a", distro_id="d", scheduled_time=sched),                                    # no dependencies: HasDependenciesMet short-circuit
+            M.Task(id="b", distro_id="d", scheduled_time=sched,
+                   depends_on=[M.Dependency("e1", finished_at=NOW - 50 * M.MINUTE), M.Dependency("e2", finished_at=NOW - 20 * M.MINUTE)]),
+            M.Task(id="c", distro_id="d", scheduled_time=sched, dependencies_met_time=NOW - 2 * M.HOUR),  # stamped on an earlier tick
+            M.Task(id="d", distro_id="d", scheduled_time=sched, depends_on=[M.Dependency("missing")]),     # unmet
+            M.Task(id="e", distro_id="d", scheduled_time=sched, depends_on=[M.Dependency("e1")]),           # met, FinishedAt unknown: now
+            M.Task(id="f", distro_id="d", scheduled_time=sched, override_dependencies=True,
+                   depends_on=[M.Dependency("missing", finished_at=NOW - M.MINUTE)]),                       # short-circuit: nothing stamped
+        ]
+    tasks = mk()
+    d = M.Distro(id="d")
+    soa, table, _ = S.marshal_tasks([(d, tasks)], NOW, ext, resolve_deps=True)
+    assert soa.wait_basis_ns.tolist() == [sched, NOW - 20 * M.MINUTE, NOW - 2 * M.HOUR, sched, NOW, sched]
+    assert [bool(f & L.EVG_TF_DEPS_MET) for f in soa.flags.tolist()] == [True, True, True, False, True, True]
+    # the marshaller wrote the stamp back on the task, like tasks[i] = task (scheduler.go:137) / the UpdateOne of task.go:659
+    assert [t.dependencies_met_time for t in tasks] == [M.ZERO_TIME, NOW - 20 * M.MINUTE, NOW - 2 * M.HOUR, M.ZERO_TIME, NOW, M.ZERO_TIME]
+    qi = O.queue_info("d", mk(), 30 * M.MINUTE, False, NOW, ext)
+    assert qi.count_wait_over_threshold == 3 and qi.length_with_dependencies_met == 5  # a and f (3 h since scheduled), c (2 h)
+    # the same queue through the SoA-level oracle job the GPU parity tests use
+    job = O.SoAJob(soa, table, None, None)
+    ref = job.run(NOW, 1)
+    assert int(ref["info"][0]["count_wait_over_threshold"]) == 3
+
+
+def test_out_of_range_priority_is_an_error_not_a_clamp():
+    d = M.Distro(id="d")
+    for bad in (2 ** 31, -2 ** 31 - 1, 2 ** 40):
+        with pytest.raises(ValueError):
+            S.marshal_tasks([(d, [M.Task(id="t", priority=bad)])], NOW)
+    soa, _, _ = S.marshal_tasks([(d, [M.Task(id="t", priority=2 ** 31 - 1), M.Task(id="u", priority=-2 ** 31)])], NOW)
+    assert soa.priority.tolist() == [2 ** 31 - 1, -2 ** 31]
