@@ -14,8 +14,11 @@
 // by a closed-form interleave.  Strings never reach the device: the shim interns "BuildId-TaskGroup" to its rank
 // among the distro's distinct such strings, the (TaskGroup, BuildId) pair to a dense id, the presort to a rank.
 // A list the host marks EVG_LEGACY_MODE_LITERAL (the chain is not transitive there: commit builds of several
-// projects, zero and non-zero expected durations mixed) is sorted with the literal pairwise comparator and the distro
-// is reported EVG_LEGACY_NOT_DECOMPOSABLE: a valid stable-sort outcome, not necessarily Go's.
+// projects, zero and non-zero expected durations mixed) has no order that every stable sort agrees on -- Go's result
+// depends on the exact steps of its insertion-sort / symMerge.  Such a list is sorted by the nearest transitive key
+// (byAge by IngestTime only, byRuntime on the raw durations) so that the output is still a permutation with task
+// groups, merge-queue tasks, priorities, dependents and generators where the reference puts them, and the distro is
+// reported EVG_LEGACY_NOT_DECOMPOSABLE.
 // The reference also returns an O(compares) map of reason strings (orderingLogic); it is not produced.
 #pragma once
 
@@ -69,16 +72,13 @@ __device__ bool legacy_less(const DLegacy& X, int d, int64_t a, int64_t b) {
   const bool ga = fa & EVG_LF_GENERATE, gb = fb & EVG_LF_GENERATE;  // byGenerateTasks :175-185
   if (ga != gb) return ga;
   // byAge :73-95
-  bool by_revision = mode == EVG_LEGACY_MODE_REVISION;
-  if (mode == EVG_LEGACY_MODE_LITERAL)
-    by_revision = (fa & EVG_LF_REQ_MASK) == EVG_LF_REQ_SYSTEM && (fb & EVG_LF_REQ_MASK) == EVG_LF_REQ_SYSTEM && X.project[a] == X.project[b];
-  if (by_revision) {
+  if (mode == EVG_LEGACY_MODE_REVISION) {
     if (X.revision[a] != X.revision[b]) return X.revision[a] > X.revision[b];
   } else {
     if (X.ingest[a] != X.ingest[b]) return X.ingest[a] < X.ingest[b];
   }
-  const int64_t ea = X.expected[a], eb = X.expected[b];  // byRuntime :104-123
-  if (ea != 0 && eb != 0 && ea != eb) return ea > eb;
+  const int64_t ea = X.expected[a], eb = X.expected[b];  // byRuntime :104-123 (a zero duration ties with everything: LITERAL lists)
+  if ((mode == EVG_LEGACY_MODE_LITERAL || (ea != 0 && eb != 0)) && ea != eb) return ea > eb;
   return X.presort[a] < X.presort[b];
 }
 

@@ -54,7 +54,8 @@ struct PlanCta {
   static constexpr size_t kOffScan = kOffDisp + size_t(CAP / 32) * 4;
   static constexpr size_t kOffBar = kOffScan + 32 * 4;
   static constexpr size_t kOffShared = kOffBar + 4 * 8;
-  static constexpr size_t kBytes = kOffShared + 160;
+  static constexpr size_t kOffNd = kOffShared + 160;   // u32[kNdTable]: int64(NumDependentsFactor * n)
+  static constexpr size_t kBytes = kOffNd + 4 * 64;
   static constexpr int kGroupCap = int(kMultiBytes / 84) > 65535 ? 65535 : int(kMultiBytes / 84);
   static_assert(CAP % THREADS == 0 && kItems % 2 == 0 && kItems <= 20, "blocked entries per thread: even, at most 20");
   static_assert(CAP / kWarps == 32 * kItems, "a warp's sort segment is kItems chunks of 32");
@@ -98,11 +99,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// the same on precomputed shared-window addresses: the task-pass loop issues them every tile
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// one lane's shared-memory add with the old value back (inline PTX: the compiler does not wrap it in its own warp aggregation)
+__device__ __forceinline__ uint32_t atom_add_shared(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
 // TMA, non-tensor form: one contiguous run global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// The 64-bit scorers, out of line: the task pass keeps only the 32-bit form in its loop body.  Called by whole warps.
+__device__ __noinline__ uint64_t score_slow(const PlannerFactors& pf, bool fast_clock, bool scores, int64_t now, int32_t prio,
+                                            int64_t exp_ns, int64_t qb, int32_t nd, uint32_t fl) {
+  if (fast_clock && __all_sync(0xffffffffu, !scores || score_fast_domain(now, exp_ns, qb)))
+    return uint64_t(single_task_value_fast(pf, now, prio, exp_ns, qb, nd, fl));
+  return scores ? uint64_t(single_task_value(pf, now, prio, exp_ns, qb, nd, fl)) : 0ull;
 }
 
 template <int THREADS, int CAP, int MIN_CTAS>
@@ -125,6 +147,7 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
   uint32_t* sScan = reinterpret_cast<uint32_t*>(smem_raw + L::kOffScan);    // [32] block-scan scratch
   uint64_t* sBar = reinterpret_cast<uint64_t*>(smem_raw + L::kOffBar);      // full[2], empty[2]
   CtaShared* S = reinterpret_cast<CtaShared*>(smem_raw + L::kOffShared);
+  uint32_t* sNd = reinterpret_cast<uint32_t*>(smem_raw + L::kOffNd);
   unsigned char* sStage = smem_raw + L::kOffIdx;                             // two stages of 40*THREADS bytes
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -193,19 +216,32 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
   const int64_t wait_cutoff = wsub(now, threshold);
   const bool fast_clock = now >= 0 && pf.nd_int != 0;
   const bool incl = cfg.includes_dependencies != 0;
+  // int64(NumDependentsFactor * n) for n < kNdTable: the 32-bit scorer then takes fractional factors too
+  if (tid < kNdTable) {
+    const int64_t e = nd_table_entry(pf, tid);
+    sNd[tid] = (e >= 0 && e < int64_t(kNdTermLimit)) ? uint32_t(e) : 0xFFFFFFFFu;
+  }
+  __syncthreads();
 
+  const uint32_t a_full0 = smem_u32(&sBar[0]), a_empty0 = smem_u32(&sBar[2]), a_nlist = smem_u32(&S->n_list);
+  const uint32_t* st32_0 = reinterpret_cast<const uint32_t*>(sStage) + tid;
+  const int64_t* st64_0 = reinterpret_cast<const int64_t*>(sStage + 16 * THREADS) + tid;
   for (int k = 0; k < n_tiles; k++) {
     const int s = k & 1;
     const uint32_t ph = uint32_t(k >> 1) & 1u;
-    mbar_wait(&sBar[s], ph);  // the tile's bytes have landed
+    mbar_wait_a(a_full0 + 8u * s, ph);  // the tile's bytes have landed
     const int i = k * THREADS + tid - off0;
     const bool valid = i >= 0 && i < tn;
-    const uint32_t* st32 = reinterpret_cast<const uint32_t*>(sStage + size_t(s) * L::kStageBytes);
-    const int64_t* st64 = reinterpret_cast<const int64_t*>(sStage + size_t(s) * L::kStageBytes + 16 * THREADS);
-    const int32_t prio = int32_t(st32[0 * THREADS + tid]), nd = int32_t(st32[1 * THREADS + tid]);
-    const int32_t gid = int32_t(st32[2 * THREADS + tid]);
-    const uint32_t fl = st32[3 * THREADS + tid];
-    const int64_t exp_ns = st64[0 * THREADS + tid], qb = st64[1 * THREADS + tid], wb = st64[2 * THREADS + tid];
+    const uint32_t* st32 = st32_0 + s * (L::kStageBytes / 4);
+    const int64_t* st64 = st64_0 + s * (L::kStageBytes / 8);
+    const int32_t prio = int32_t(st32[0 * THREADS]), nd = int32_t(st32[1 * THREADS]);
+    const int32_t gid = int32_t(st32[2 * THREADS]);
+    const uint32_t fl = st32[3 * THREADS];
+    const int64_t exp_ns = st64[0 * THREADS], qb = st64[1 * THREADS], wb = st64[2 * THREADS];
+    // Every field is in registers (the arrive is a release: it is ordered behind the loads above): the slot may be
+    // refilled while this tile is scored -- two tiles of prefetch distance instead of one.
+    mbar_arrive_a(a_empty0 + 8u * s);
+    if (tid == 0 && k + 2 < n_tiles) { mbar_wait_a(a_empty0 + 8u * s, ph); issue(k + 2); }
     bool complex_task = false, scores = false;
     if (valid) {
       // GetDistroQueueInfo (scheduler.go:66-138)
@@ -221,17 +257,13 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       complex_task = gid >= 0;  // a task-group task: its unit has other members (no GroupVersions, no edges here)
       scores = !complex_task;   // unit == {this task}
     }
-    uint64_t v = 0;
-    if (f32.ok && __all_sync(full, !scores || score32_domain(now, prio, nd, exp_ns, qb))) {
-      v = single_task_value32(f32, now, prio, exp_ns, qb, nd, fl);
-    } else if (fast_clock && __all_sync(full, !scores || score_fast_domain(now, exp_ns, qb))) {
-      v = uint64_t(single_task_value_fast(pf, now, prio, exp_ns, qb, nd, fl));
-    } else if (scores) {
-      v = uint64_t(single_task_value(pf, now, prio, exp_ns, qb, nd, fl));
-    }
-    // every field is in registers: the slot may be refilled
-    mbar_arrive(&sBar[2 + s]);
-    if (tid == 0 && k + 2 < n_tiles) { mbar_wait(&sBar[2 + s], ph); issue(k + 2); }
+    uint64_t v;
+    const uint32_t ndc = uint32_t(nd > 0 ? nd : 0);
+    const uint32_t nd_term = ndc < uint32_t(kNdTable) ? sNd[ndc] : ((f32.ok && ndc < kTask32Limit) ? f32.nd * ndc : 0xFFFFFFFFu);
+    if (f32.ok_base && __all_sync(full, !scores || (nd_term != 0xFFFFFFFFu && score32_domain_nd(now, prio, exp_ns, qb))))
+      v = single_task_value32_nd(f32, now, prio, exp_ns, qb, nd_term, fl);
+    else
+      v = score_slow(pf, fast_clock, scores, now, prio, exp_ns, qb, nd, fl);
     if (scores) {
       if (v >> 32) punt = true;  // does not fit the u32 key (negative values included): k_plan_smem plans this distro
       const uint32_t v32 = uint32_t(v);
@@ -242,7 +274,7 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       const unsigned m = __ballot_sync(full, complex_task);
       if (m) {
         unsigned int pos0 = 0;
-        if (lane == 0) pos0 = atomicAdd(&S->n_list, (unsigned int)__popc(m));
+        if (lane == 0) pos0 = atom_add_shared(a_nlist, (unsigned int)__popc(m));
         pos0 = __shfl_sync(full, pos0, 0);
         if (complex_task) {
           const unsigned int pos = pos0 + __popc(m & ((1u << lane) - 1u));
@@ -302,14 +334,20 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
     }
     unsigned int t_n = 0, t_cnt = 0, t_over = 0, t_wait = 0, t_mq = 0;
     int64_t t_exp = 0, t_dover = 0;
-    for (int k = tid; k < n_list; k += THREADS) {
-      const int i = int(sList[k]);
-      const int64_t t = base + i;
-      // every column this phase needs, requested together: one L2 round trip instead of a chain of them
-      const int32_t gid = T.gid[t];
-      const int64_t exp_ns = T.expected[t], wb = T.wbasis[t], qb = T.qbasis[t];
-      const uint32_t fl = T.flags[t];
-      const int32_t tgo = T.tgo[t], prio = T.priority[t], nd = T.numdep[t];
+    struct Member { int i; int32_t gid, tgo, prio, nd; uint32_t fl; int64_t exp_ns, wb, qb; };
+    auto fetch = [&](int k) {  // every column this phase needs, requested together: one L2 round trip, not a chain
+      Member m;
+      m.i = int(sList[k]);
+      const int64_t t = base + m.i;
+      m.gid = T.gid[t]; m.exp_ns = T.expected[t]; m.wb = T.wbasis[t]; m.qb = T.qbasis[t];
+      m.fl = T.flags[t]; m.tgo = T.tgo[t]; m.prio = T.priority[t]; m.nd = T.numdep[t];
+      return m;
+    };
+    auto member = [&](const Member& m) {
+      const int i = m.i;
+      const int32_t gid = m.gid, tgo = m.tgo, prio = m.prio, nd = m.nd;
+      const uint32_t fl = m.fl;
+      const int64_t exp_ns = m.exp_ns, wb = m.wb, qb = m.qb;
       const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
       const bool counted = !incl || dm;
       const bool over = counted && exp_ns > threshold;
@@ -322,7 +360,7 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       if (over) { atomicAdd(&qOver[gid], 1u); smem_add64(&qDurOver[gid], (unsigned long long)exp_ns); }
       if (wait_over) atomicAdd(&qWait[gid], 1u);
       if (mq_dm) atomicAdd(&qMq[gid], 1u);
-      if (tgo < 0 || tgo >= 64) { S->punt = 1; continue; }  // the presence-mask rank needs orders 0..63
+      if (tgo < 0 || tgo >= 64) { S->punt = 1; return; }  // the presence-mask rank needs orders 0..63
       sKey[i] = uint32_t(gid) | (uint32_t(tgo) << 16);  // parked for phase 4
       const uint32_t req = fl & EVG_TF_REQ_MASK;
       uint32_t uf = 0;
@@ -338,6 +376,13 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       atomicAdd(&gN[gid], 1u);
       atomicMin(&gAnchor[gid], uint32_t(i));
       atomicOr(reinterpret_cast<unsigned int*>(&gMask[gid]) + (tgo >> 5), 1u << (tgo & 31));
+    };
+    for (int k = tid; k < n_list; k += 2 * THREADS) {  // two members per trip: sixteen loads in flight
+      const bool two = k + THREADS < n_list;
+      const Member m0 = fetch(k);
+      const Member m1 = fetch(two ? k + THREADS : k);
+      member(m0);
+      if (two) member(m1);
     }
     if (__any_sync(full, t_n != 0)) {  // one shared atomic per warp and field
       t_n = __reduce_add_sync(full, t_n); t_cnt = __reduce_add_sync(full, t_cnt); t_over = __reduce_add_sync(full, t_over);
@@ -518,14 +563,29 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       __syncwarp();
       uint32_t ci[ITEMS / 2];  // task indices, two per register
       uint32_t cr[ITEMS];      // digit | warp-local rank << 10
+      // all the permutation loads first, then all the key gathers (independent shared-memory loads in flight together);
+      // only then the MATCH / atomic / shuffle chain, which must run chunk by chunk
+#pragma unroll
+      for (int j = 0; j < ITEMS; j += 2) {
+        const int p0 = seg0 + j * 32 + lane, p1 = p0 + 32;
+        const uint32_t i0 = (j * 32 < seg && p0 < seg1) ? uint32_t(sIdx[p0]) : 0u;
+        const uint32_t i1 = ((j + 1) * 32 < seg && p1 < seg1) ? uint32_t(sIdx[p1]) : 0u;
+        ci[j >> 1] = i0 | (i1 << 16);
+      }
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++) {
+        if (j * 32 < seg) {
+          const uint32_t i = (j & 1) ? (ci[j >> 1] >> 16) : (ci[j >> 1] & 0xFFFFu);
+          const bool ok = seg0 + j * 32 + lane < seg1;
+          const uint32_t key = vmax - sKey[i];
+          cr[j] = ok ? ((key >> shift) & mask) : 0x7FFFu;  // padding lanes match only each other
+        }
+      }
 #pragma unroll
       for (int j = 0; j < ITEMS; j++) {
         if (j * 32 < seg) {  // warp-uniform
-          const int p = seg0 + j * 32 + lane;
-          const bool ok = p < seg1;
-          const uint32_t i = ok ? uint32_t(sIdx[p]) : 0u;
-          const uint32_t key = vmax - sKey[i];
-          const uint32_t dg = ok ? ((key >> shift) & mask) : 0x7FFFu;  // padding lanes match only each other
+          const uint32_t dg = cr[j];
+          const bool ok = dg != 0x7FFFu;
           const unsigned peers = __match_any_sync(full, dg);
           const uint32_t r = __popc(peers & lt);
           uint32_t old = 0;
@@ -533,7 +593,6 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
           old = __shfl_sync(full, old, __ffs(peers) - 1);
           const uint32_t wr = ((old >> (16 * (dg & 1u))) & 0xFFFFu) + r;
           cr[j] = (dg & 0x3FFu) | (wr << 10);
-          if (j & 1) ci[j >> 1] |= i << 16; else ci[j >> 1] = i;
         }
       }
       __syncthreads();

@@ -5,8 +5,9 @@
 //   k_gtask        per 2048-task tile: 128-bit column loads, 32-bit scoring (single_task_value32) where the
 //                  distro allows it, queue-info sums folded per tile, TotalValue of single-task units, per-distro
 //                  value range; tasks of multi-member units are linked and compacted into a work list
-//   k_gcomplex     per work-list task: Unit.info / value / anchor of every unit it belongs to, first-occurrence choice
-//                  (planner.go:467-477), rank inside the chosen unit; anchor histogram e[]
+//   k_gunit/k_gbest  per work-list task: the member at the head of a unit's list computes Unit.info / value / anchor once;
+//                  then every task makes its first-occurrence choice (planner.go:467-477) and walks the chosen unit
+//                  for its rank; anchor histogram e[]
 //   k_gsum/k_gscan/k_gplace(+_disp)
 //                  canonical pre-arrangement by COUNTING instead of sorting tie bytes: an exclusive scan of e[] over
 //                  the distro gives every anchor's run start; tasks are written to (key, index) buffers in
@@ -78,7 +79,7 @@ struct TileFold {  // queue-info partials of one tile (scheduler.go:66-138)
 
 // Per tile: queue info, single-task scores, unit links.  256 threads x 8 tasks: thread q of group u owns the four
 // consecutive task slots tile_start + 4*(u*256 + q) .. +3, so every column is read with 128-bit loads.
-__global__ void __launch_bounds__(256) k_gtask(DTasks T, DDistros D, DWork W, DGen G, int64_t now, int any_complex) {
+__global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W, DGen G, int64_t now, int any_complex) {
   if (*W.err) return;
   __shared__ TileFold F;
   __shared__ evg_distro_cfg s_cfg;
@@ -129,6 +130,16 @@ __global__ void __launch_bounds__(256) k_gtask(DTasks T, DDistros D, DWork W, DG
       wb01 = *reinterpret_cast<const longlong2*>(T.wbasis + t4); wb23 = *reinterpret_cast<const longlong2*>(T.wbasis + t4 + 2);
       if (gv) vid4 = *reinterpret_cast<const int4*>(T.vid + t4);
     }
+    // dependency offsets of the four tasks (five consecutive entries) and their "has dependents" bytes, as vectors too
+    int64_t doff[5] = {0, 0, 0, 0, 0};
+    uint32_t hd4 = 0;
+    if (live && dcomplex) {
+      if (T.n_edges > 0) {
+        const longlong2 d01 = *reinterpret_cast<const longlong2*>(T.dep_off + t4), d23 = *reinterpret_cast<const longlong2*>(T.dep_off + t4 + 2);
+        doff[0] = d01.x; doff[1] = d01.y; doff[2] = d23.x; doff[3] = d23.y; doff[4] = T.dep_off[t4 + 4];
+      }
+      hd4 = *reinterpret_cast<const uint32_t*>(W.has_dep + t4);
+    }
     const int32_t prio_[4] = {prio4.x, prio4.y, prio4.z, prio4.w}, nd_[4] = {nd4.x, nd4.y, nd4.z, nd4.w};
     const int32_t gid_[4] = {gid4.x, gid4.y, gid4.z, gid4.w}, vid_[4] = {vid4.x, vid4.y, vid4.z, vid4.w};
     const uint32_t fl_[4] = {fl4.x, fl4.y, fl4.z, fl4.w};
@@ -169,7 +180,7 @@ __global__ void __launch_bounds__(256) k_gtask(DTasks T, DDistros D, DWork W, DG
           atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
         }
         if (dcomplex) {
-          own_complex = gid >= 0 || gv || W.has_dep[t] != 0;
+          own_complex = gid >= 0 || gv || ((hd4 >> (8 * m)) & 0xFFu) != 0;
           const uint32_t li = uint32_t(t - base);
           const uint32_t s_own = own_slot_local(gid, vid, li, ng, gv);
           const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
@@ -177,7 +188,7 @@ __global__ void __launch_bounds__(256) k_gtask(DTasks T, DDistros D, DWork W, DG
           if (s_ver != kInactive) link_pair(W, uint32_t(T.n + t), ub + s_ver);  // planner.go:439
           bool has_edges = false;
           if (T.n_edges > 0) {
-            const int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
+            const int64_t e0 = doff[m], e1 = doff[m + 1];
             has_edges = e1 > e0;
             for (int64_t e = e0; e < e1; e++) {
               const uint32_t dl = uint32_t(T.dep_idx[e]);
@@ -284,61 +295,87 @@ __global__ void __launch_bounds__(256) k_gtask(DTasks T, DDistros D, DWork W, DG
   }
 }
 
-// Per work-list task: every unit it belongs to is evaluated by walking the unit's member list (Unit.info, value, anchor
-// and this member's rank: eval_pair's arithmetic), then the first unit the task is emitted from is chosen
-// (TaskPlan.Export, planner.go:467-477).
-__global__ void __launch_bounds__(256) k_gcomplex(DTasks T, DDistros D, DWork W, DGen G, int64_t now) {
+// Multi-member units, in two passes over the work list (one thread per task, grid-stride):
+//   k_gunit   the pair at the HEAD of a unit's member list owns the unit: one walk for Unit.info (planner.go:302-337),
+//             its value (planner.go:209-300), its anchor and its member count
+//   k_gbest   per task: the first unit it is emitted from among its memberships (TaskPlan.Export, planner.go:467-477),
+//             then ONE walk of that unit for the task's rank inside it (TaskList.Less, planner.go:387-405)
+__global__ void __launch_bounds__(256, 4) k_gunit(DTasks T, DDistros D, DWork W, DGen G, int64_t now) {
   if (*W.err) return;
   const unsigned int n = *G.ccount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {  // the host cannot know n: fixed grid
-  const uint32_t t = G.clist[k];
-  const int d = find_distro(D.task_off, 0, D.n - 1, int64_t(t));
-  const evg_distro_cfg cfg = D.cfg[d];
-  const int64_t base = D.task_off[d];
-  const uint32_t li = uint32_t(int64_t(t) - base);
-  const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
-  const int64_t my_ex = T.expected[t];
-  bool have = false;
-  int64_t bv = 0;
-  uint32_t ba = 0, brk = 0, bp = kInactive, bslot = 0, bn = 0;
-  auto consider_pair = [&](uint32_t p) {
-    if (W.next[p] == kInactive) return;  // not linked (duplicate membership, or a key this task is not filed under)
-    const uint32_t slot = W.pair_slot[p];
-    UnitAcc a;
-    acc_init(a);
-    uint32_t anchor = kNoAnchor, rk = 0;
-    for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
-      const uint32_t tq = pair_task(T, W, q);
-      const uint32_t lq = uint32_t(int64_t(tq) - base);
-      const int32_t q_pr = T.priority[tq], q_nd = T.numdep[tq], q_tgo = T.tgo[tq];
-      const int64_t q_ex = T.expected[tq];
-      acc_add(a, now, q_pr, q_ex, T.qbasis[tq], q_nd, T.gid[tq], T.flags[tq]);
-      if (q < uint32_t(T.n)) anchor = min(anchor, lq);  // own-key pairs are the SetDistro members (planner.go:446)
-      if (in_unit_less(q_tgo, q_nd, q_pr, q_ex, lq, my_tgo, my_nd, my_pr, my_ex, li)) rk++;
-    }
-    if (anchor == kNoAnchor) return;  // the unit never got a distro -> not exported (planner.go:81-83)
-    const int64_t v = unit_value(a, cfg, nullptr);
-    if (!have || v > bv || (v == bv && anchor < ba)) { have = true; bv = v; ba = anchor; brk = rk; bp = p; bslot = slot; bn = uint32_t(a.n); }
-  };
-  if (W.next[t] == kInactive) { have = true; bv = G.tv[t]; ba = li; brk = 0; }  // its own single-task unit, scored by k_gtask
-  else consider_pair(t);
-  consider_pair(uint32_t(T.n + t));
-  if (T.n_edges > 0)
-    for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) consider_pair(uint32_t(2 * T.n + e));
-  G.tv[t] = bv;
-  G.tie_a[t] = ba;
-  G.tie_r[t] = brk;
-  W.best_pair[t] = bp;
-  if (bp != kInactive) {
-    W.unit_n[bslot] = bn;  // every member writes the same count
-    if (bn <= 64) atomicOr(&W.unit_mask[bslot], 1ull << brk);  // ranks emitted from the unit: k_gplace_disp counts below its own
+    const uint32_t t = G.clist[k];
+    int d = -1;
+    int64_t base = 0;
+    auto head_of = [&](uint32_t p) {
+      if (W.next[p] == kInactive) return;  // not linked
+      const uint32_t slot = W.pair_slot[p];
+      if (W.head[slot] != p) return;       // some other member owns the unit
+      if (d < 0) { d = find_distro(D.task_off, 0, D.n - 1, int64_t(t)); base = D.task_off[d]; }
+      UnitAcc a;
+      acc_init(a);
+      uint32_t anchor = kNoAnchor;
+      for (uint32_t q = p; q < kEnd; q = W.next[q]) {
+        const uint32_t tq = pair_task(T, W, q);
+        acc_add(a, now, T.priority[tq], T.expected[tq], T.qbasis[tq], T.numdep[tq], T.gid[tq], T.flags[tq]);
+        if (q < uint32_t(T.n)) anchor = min(anchor, uint32_t(int64_t(tq) - base));  // own-key pairs are the SetDistro members (planner.go:446)
+      }
+      W.unit_v[slot] = unit_value(a, D.cfg[d], nullptr);
+      W.unit_a[slot] = anchor;  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
+      W.unit_n[slot] = uint32_t(a.n);
+    };
+    head_of(t);
+    head_of(uint32_t(T.n + t));
+    if (T.n_edges > 0)
+      for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) head_of(uint32_t(2 * T.n + e));
   }
-  const bool displaced = !(ba == li && brk == 0);
-  if (displaced) W.has_dep[t] |= 2;  // only this thread touches the byte now (k_gmark and k_gtask are done)
-  atomicAdd(G.e + base + ba, 1u);
-  const unsigned long long kk = ord_i64(bv);
-  if (kk > __ldcg(G.vmm + 2 * d)) atomicMax(G.vmm + 2 * d, kk);
-  if (kk < __ldcg(G.vmm + 2 * d + 1)) atomicMin(G.vmm + 2 * d + 1, kk);
+}
+
+__global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W, DGen G) {
+  if (*W.err) return;
+  const unsigned int n = *G.ccount;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t t = G.clist[k];
+    const int d = find_distro(D.task_off, 0, D.n - 1, int64_t(t));
+    const int64_t base = D.task_off[d];
+    const uint32_t li = uint32_t(int64_t(t) - base);
+    bool have = false;
+    int64_t bv = 0;
+    uint32_t ba = 0, brk = 0, bp = kInactive, bslot = 0;
+    auto consider = [&](uint32_t p) {
+      if (W.next[p] == kInactive) return;  // not linked (duplicate membership, or a key this task is not filed under)
+      const uint32_t slot = W.pair_slot[p];
+      const uint32_t a = W.unit_a[slot];
+      if (a == kNoAnchor) return;
+      const int64_t v = W.unit_v[slot];
+      if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; bp = p; bslot = slot; }
+    };
+    if (W.next[t] == kInactive) { have = true; bv = G.tv[t]; ba = li; }  // its own single-task unit, scored by k_gtask
+    else consider(t);
+    consider(uint32_t(T.n + t));
+    if (T.n_edges > 0)
+      for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) consider(uint32_t(2 * T.n + e));
+    uint32_t bn = 1;
+    if (bp != kInactive) {  // rank among ALL members of the chosen unit
+      const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
+      const int64_t my_ex = T.expected[t];
+      for (uint32_t q = W.head[bslot]; q < kEnd; q = W.next[q]) {
+        const uint32_t tq = pair_task(T, W, q);
+        if (in_unit_less(T.tgo[tq], T.numdep[tq], T.priority[tq], T.expected[tq], uint32_t(int64_t(tq) - base), my_tgo, my_nd, my_pr, my_ex, li)) brk++;
+      }
+      bn = W.unit_n[bslot];
+      if (bn <= 64) atomicOr(&W.unit_mask[bslot], 1ull << brk);  // ranks emitted from the unit: k_gplace_disp counts below its own
+    }
+    G.tv[t] = bv;
+    G.tie_a[t] = ba;
+    G.tie_r[t] = brk;
+    W.best_pair[t] = bp;
+    const bool displaced = !(ba == li && brk == 0);
+    if (displaced) W.has_dep[t] |= 2;  // only this thread touches the byte now (k_gmark and k_gtask are done)
+    atomicAdd(G.e + base + ba, 1u);
+    const unsigned long long kk = ord_i64(bv);
+    if (kk > __ldcg(G.vmm + 2 * d)) atomicMax(G.vmm + 2 * d, kk);
+    if (kk < __ldcg(G.vmm + 2 * d + 1)) atomicMin(G.vmm + 2 * d + 1, kk);
   }
 }
 

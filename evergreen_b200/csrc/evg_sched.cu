@@ -9,7 +9,7 @@
 //                    handed back ("punted") to k_plan_smem on the device
 //   <= 12288 tasks   k_plan_smem<THREADS,ITEMS> (evg_plan_smem.cuh): one CTA per distro, any unit structure
 //   larger           the general path (evg_plan_general.cuh), any size up to 2^21-1 tasks:
-//     k_gmark/k_gtask/k_gcomplex   dependents, per-task pass, multi-member units
+//     k_gmark/k_gtask/k_gunit/k_gbest  dependents, per-task pass, multi-member units
 //     k_gsum/k_gscan/k_gplace*     canonical pre-arrangement by counting
 //     k_ghist/k_gdscan/k_gscatter  segmented stable LSD radix sort of 32-bit keys
 //     k_gemit                      ranked queue + TotalValue
@@ -1122,7 +1122,10 @@ int run_general(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& d
   LAUNCH_ON(c, st, k_gtask, nt, 256, dt, dd, w, g, now, gc);
   if (c->timed) { CK(cudaEventRecord(c->ev_gt1, st)); c->general_timed = true; }
   const unsigned wl_grid = unsigned(std::min<int64_t>(std::max<int64_t>(1, (c->Tgc + 255) / 256), 148 * 16));
-  if (gc) LAUNCH_ON(c, st, k_gcomplex, wl_grid, 256, dt, dd, w, g, now);
+  if (gc) {
+    LAUNCH_ON(c, st, k_gunit, wl_grid, 256, dt, dd, w, g, now);
+    LAUNCH_ON(c, st, k_gbest, wl_grid, 256, dt, dd, w, g);
+  }
   LAUNCH_ON(c, st, k_gsched, grid_for(c->n_general, 128), 128, g, gl, c->n_general);
   if (gc) {
     LAUNCH_ON(c, st, k_gsum, nt, 256, dd, g);

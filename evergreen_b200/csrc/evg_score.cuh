@@ -301,22 +301,48 @@ constexpr int64_t kFactor32Limit = int64_t(1) << 14;
 constexpr uint32_t kTask32Limit = 1u << 15;
 struct Factors32 {
   uint32_t patch, patch_tiq, commit_queue, mainline_tiq, runtime, generate, stepback, nd;
-  uint32_t ok;  // distro-wide preconditions hold (clock non-negative, all factors small, integral NumDependentsFactor)
+  uint32_t ok;       // distro-wide preconditions hold (clock non-negative, all factors small, integral NumDependentsFactor)
+  uint32_t ok_base;  // the same without the NumDependentsFactor condition: callers that tabulate int64(factor * n) for small n
 };
 EVG_HD Factors32 factors32(const PlannerFactors& f, int64_t now) {
   Factors32 g;
   g.patch = uint32_t(f.patch); g.patch_tiq = uint32_t(f.patch_tiq); g.commit_queue = uint32_t(f.commit_queue);
   g.mainline_tiq = uint32_t(f.mainline_tiq); g.runtime = uint32_t(f.runtime); g.generate = uint32_t(f.generate);
   g.stepback = uint32_t(f.stepback); g.nd = uint32_t(f.nd_int);
-  g.ok = now >= 0 && f.nd_int != 0 && f.nd_int < kFactor32Limit && f.patch < kFactor32Limit && f.patch_tiq < kFactor32Limit &&
-         f.commit_queue < kFactor32Limit && f.mainline_tiq < kFactor32Limit && f.runtime < kFactor32Limit &&
-         f.generate < kFactor32Limit && f.stepback < kFactor32Limit;
+  g.ok_base = now >= 0 && f.patch < kFactor32Limit && f.patch_tiq < kFactor32Limit &&
+              f.commit_queue < kFactor32Limit && f.mainline_tiq < kFactor32Limit && f.runtime < kFactor32Limit &&
+              f.generate < kFactor32Limit && f.stepback < kFactor32Limit;
+  g.ok = g.ok_base && f.nd_int != 0 && f.nd_int < kFactor32Limit;
   return g;
 }
 // per-task part of the domain (requires Factors32::ok): score_fast_domain plus small priority / dependents
 EVG_HD bool score32_domain(int64_t now, int32_t priority, int32_t num_dependents, int64_t expected_ns, int64_t queue_basis_ns) {
   return score_fast_domain(now, expected_ns, queue_basis_ns) && priority < int32_t(kTask32Limit) &&
          num_dependents < int32_t(kTask32Limit);
+}
+// NumDependentsFactor need not be integral for the 32-bit form: int64(factor * float64(n)) (planner.go:247) is tabulated
+// per distro for n < kNdTable (nearly every task) by nd_table_entry; entries must stay below 2^29 like the products above.
+constexpr int kNdTable = 64;
+constexpr uint32_t kNdTermLimit = 1u << 29;
+EVG_HD int64_t nd_table_entry(const PlannerFactors& f, int n) { return d2i_trunc(fmul64(f.num_dependents, i2d(n))); }
+// domain of single_task_value32_nd: everything score32_domain checks except NumDependents (the caller resolved its term)
+EVG_HD bool score32_domain_nd(int64_t now, int32_t priority, int64_t expected_ns, int64_t queue_basis_ns) {
+  return score_fast_domain(now, expected_ns, queue_basis_ns) && priority < int32_t(kTask32Limit);
+}
+EVG_HD uint64_t single_task_value32_nd(const Factors32& f, int64_t now, int32_t priority, int64_t expected_ns,
+                                       int64_t queue_basis_ns, uint32_t nd_term, uint32_t tflags) {
+  const uint32_t req = tflags & EVG_TF_REQ_MASK;
+  const bool mq = req == EVG_TF_REQ_MERGE_QUEUE, pat = req == EVG_TF_REQ_PATCH;
+  const uint64_t tiq = queue_basis_ns == EVG_TIME_ZERO ? 0ull : uint64_t(now - queue_basis_ns);
+  const uint32_t p = 1u + uint32_t(priority > 0 ? priority : 0);
+  const uint32_t prio = p * ((tflags & EVG_TF_GENERATE) ? f.generate : 1u) + (mq ? 200u : 0u);
+  const uint64_t left = tiq < uint64_t(kWeek) ? uint64_t(kWeek) - tiq : 0ull;
+  const uint32_t mins = uint32_t((pat ? tiq : left) / uint64_t(kMinute));
+  const uint32_t qty = pat ? mins : mins / 60u;
+  uint32_t term = (pat ? f.patch_tiq : f.mainline_tiq) * qty + (pat ? f.patch : ((tflags & EVG_TF_STEPBACK) ? f.stepback : 0u));
+  if (mq) term = f.commit_queue;
+  const uint32_t rank = 1u + term + nd_term + f.runtime * uint32_t(uint64_t(expected_ns) / uint64_t(kMinute));
+  return uint64_t(prio) * uint64_t(rank) + 1ull;
 }
 EVG_HD uint64_t single_task_value32(const Factors32& f, int64_t now, int32_t priority, int64_t expected_ns,
                                     int64_t queue_basis_ns, int32_t num_dependents, uint32_t tflags) {

@@ -480,8 +480,9 @@ int evg_expected_durations_batch(evg_ctx* ctx, const evg_duration_rows* in, evg_
                                        pairs format to one string): the chain is not a strict weak order on this list */
 /* per-distro status */
 #define EVG_LEGACY_OK 0
-#define EVG_LEGACY_NOT_DECOMPOSABLE 1 /* some list was EVG_LEGACY_MODE_LITERAL: the order is a stable sort by the literal
-                                         pairwise comparator, which need not be the one Go's sort.Stable produces */
+#define EVG_LEGACY_NOT_DECOMPOSABLE 1 /* some list was EVG_LEGACY_MODE_LITERAL: no order is common to all stable sorts there;
+                                         the list was sorted by the nearest transitive key (byAge by IngestTime only),
+                                         which need not be the order Go's sort.Stable produces */
 
 /* What CmpBasedTaskPrioritizer reads of []task.Task and map[string]model.Version, SoA over the concatenated distros
  * (scheduler/task_prioritizer.go:80-278, task_priority_cmp.go:25-208, setup_funcs.go:72-87).  Strings are interned

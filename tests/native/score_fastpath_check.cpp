@@ -9,7 +9,7 @@ using namespace evg;
 static int64_t ref_floor_minutes_over(int64_t d, int64_t n) { return int64_t(std::floor((double(d / kMinute) + double(d % kMinute) / (60.0 * 1e9)) / double(n))); }
 static int64_t ref_trunc_hours(int64_t d) { return int64_t(double(d / kHour) + double(d % kHour) / (3600.0 * 1e9)); }
 int main() {
-  uint64_t x = 88172645463325252ULL; long bad = 0; long n = 0; long fast_n = 0; long n32 = 0;
+  uint64_t x = 88172645463325252ULL; long bad = 0; long n = 0; long fast_n = 0; long n32 = 0; long n32t = 0;
   auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
   for (int it = 0; it < 20000000; it++) {
     int64_t q = int64_t(rnd() % (uint64_t(1) << 15));
@@ -70,6 +70,14 @@ int main() {
       n32++;
       if (uint64_t(want) != single_task_value32(f32, now, prio, ex, qb, nd, fl)) bad++;
     }
+    // the tabulated-NumDependents form admits fractional factors
+    if (f32.ok_base && score32_domain_nd(now, prio, ex, qb) && nd < kNdTable) {
+      const int64_t e = nd_table_entry(pf, nd > 0 ? nd : 0);
+      if (e >= 0 && e < int64_t(kNdTermLimit)) {
+        n32t++;
+        if (uint64_t(want) != single_task_value32_nd(f32, now, prio, ex, qb, uint32_t(e), fl)) bad++;
+      }
+    }
     n++;
   }
   // the straight-line form at the edges of its domain (week boundary, limit - 1, zero basis, huge factors)
@@ -120,7 +128,7 @@ int main() {
         score_fast_domain(now, 0, now + 1) || score_fast_domain(now, 0, -5)) bad++;
   }
   if (fast_n < 1000000) bad++;  // the straight-line form must actually have been exercised
-  if (n32 < 500000) bad++;      // and so must the 32-bit form
+  if (n32 < 500000 || n32t < 500000) bad++;      // and so must the 32-bit forms
   {  // out of the 32-bit domain: big factor, big priority, big dependents, negative clock
     evg_distro_cfg c; memset(&c, 0, sizeof(c));
     c.patch_factor = kFactor32Limit;

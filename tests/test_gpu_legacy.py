@@ -96,10 +96,13 @@ def random_queue(rnd, n, one_project=True, zero_runtimes=False):
         req = rnd.choice([M.REPOTRACKER_VERSION_REQUESTER, M.PATCH_VERSION_REQUESTER, M.GITHUB_PR_REQUESTER, M.TRIGGER_REQUESTER,
                           M.GITHUB_MERGE_REQUESTER, M.AD_HOC_REQUESTER, "nonsense" if rnd.random() < 0.05 else M.PATCH_VERSION_REQUESTER])
         tg = rnd.random() < 0.25
+        prio = rnd.choice([0, 0, 0, 1, 5, 50, 100, 101, 150, 2 ** 40])
+        if prio > M.MAX_TASK_PRIORITY and one_project and req in M.SYSTEM_VERSION_REQUESTER_TYPES:
+            req = M.PATCH_VERSION_REQUESTER  # keep the high-priority list free of commit builds: byAge stays on IngestTime there
         out.append(M.Task(id=f"task_{k:05d}_{rnd.randrange(10 ** 6)}", requester=req, project=rnd.choice(projects),
                           version=f"v{rnd.randrange(6)}", build_id=f"build_{rnd.randrange(5)}",
                           task_group=f"tg{rnd.randrange(3)}" if tg else "", task_group_order=rnd.randrange(1, 5) if tg else 0,
-                          priority=rnd.choice([0, 0, 0, 1, 5, 50, 100, 101, 150, 2 ** 40]), num_dependents=rnd.choice([0, 0, 1, 2, 7]),
+                          priority=prio, num_dependents=rnd.choice([0, 0, 1, 2, 7]),
                           generate_task=rnd.random() < 0.1, revision_order_number=rnd.randrange(50), ingest_time=NOW - rnd.randrange(20) * M.HOUR,
                           expected_duration=0 if zero_runtimes and rnd.random() < 0.3 else rnd.randrange(1, 8) * 10 * M.MINUTE))
     return out
