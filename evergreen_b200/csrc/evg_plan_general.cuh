@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
   if (*W.err) return;
   __shared__ TileFold F;
   __shared__ evg_distro_cfg s_cfg;
+  __shared__ uint32_t s_nd[kNdTable];  // int64(NumDependentsFactor * n), n < kNdTable: fractional factors stay on the 32-bit scorer
   const int tile = blockIdx.x;
   const int d = G.tile_distro[tile];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -107,6 +108,11 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
   const int64_t wait_cutoff = wsub(now, threshold);
   const bool fast_clock = now >= 0 && pf.nd_int != 0;
   const bool incl = cfg.includes_dependencies != 0;
+  if (tid < kNdTable) {
+    const int64_t e = nd_table_entry(pf, tid);
+    s_nd[tid] = (e >= 0 && e < int64_t(kNdTermLimit)) ? uint32_t(e) : 0xFFFFFFFFu;
+  }
+  __syncthreads();
   const bool dcomplex = any_complex && (ng > 0 || gv || (T.n_edges > 0 && T.dep_off[end] > T.dep_off[base]));
 
   unsigned int c_dm = 0, c_mq = 0, c_over = 0, c_wait = 0, c_sec = 0, c_ung = 0, c_ucnt = 0, c_uover = 0, c_uwait = 0, c_umq = 0;
@@ -207,8 +213,10 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
         scores = !own_complex;  // the unit filed under this task's own key is {this task}
       }
       uint64_t v = 0;
-      if (f32.ok && __all_sync(full, !scores || score32_domain(now, prio, nd, exp_ns, qb))) {
-        v = single_task_value32(f32, now, prio, exp_ns, qb, nd, fl);
+      const uint32_t ndc = uint32_t(nd > 0 ? nd : 0);
+      const uint32_t nd_term = ndc < uint32_t(kNdTable) ? s_nd[ndc] : ((f32.ok && ndc < kTask32Limit) ? f32.nd * ndc : 0xFFFFFFFFu);
+      if (f32.ok_base && __all_sync(full, !scores || (nd_term != 0xFFFFFFFFu && score32_domain_nd(now, prio, exp_ns, qb)))) {
+        v = single_task_value32_nd(f32, now, prio, exp_ns, qb, nd_term, fl);
       } else if (fast_clock && __all_sync(full, !scores || score_fast_domain(now, exp_ns, qb))) {
         v = uint64_t(single_task_value_fast(pf, now, prio, exp_ns, qb, nd, fl));
       } else if (scores) {
