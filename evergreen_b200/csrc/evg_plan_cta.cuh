@@ -33,8 +33,18 @@ struct CtaDigit {
   static constexpr int kBits = THREADS >= 512 ? 10 : (THREADS >= 256 ? 9 : 8);  // 2^bits == 2*THREADS: one u32 counter pair per thread in the scan
 };
 
+// Tasks per thread and tile of the task pass.  2: one 2*THREADS-task stage, refilled as soon as every thread has its two
+// tasks in registers -- per-tile overhead (barrier wait, refill, list append) amortised over two tasks and two
+// independent scoring chains per thread; 1: two THREADS-task stages.
+#ifndef EVG_CTA_TPT
+#define EVG_CTA_TPT 2
+#endif
+
 template <int THREADS, int CAP>
 struct PlanCta {
+  static constexpr int kTpt = EVG_CTA_TPT;
+  static constexpr int kTile = kTpt * THREADS;
+  static constexpr int kStages = kTpt == 1 ? 2 : 1;
   static constexpr int kWarps = THREADS / 32;
   static constexpr int kItems = CAP / THREADS;
   static constexpr int kDigitBits = CtaDigit<THREADS>::kBits;
@@ -42,9 +52,9 @@ struct PlanCta {
   static constexpr int kListCap = CAP / 5;
   static constexpr size_t kKeyBytes = size_t(4) * CAP;
   static constexpr size_t kIdxBytes = size_t(2) * CAP;
-  static constexpr size_t kStageBytes = size_t(40) * THREADS;
+  static constexpr size_t kStageBytes = size_t(40) * kTile;
   static constexpr size_t kCntNeed = size_t(kWarps) * kDigitWords * 4;
-  static constexpr size_t kMultiBytes = (kIdxBytes + kCntNeed) > 2 * kStageBytes ? (kIdxBytes + kCntNeed) : 2 * kStageBytes;  // idx + cnt, contiguous
+  static constexpr size_t kMultiBytes = (kIdxBytes + kCntNeed) > kStages * kStageBytes ? (kIdxBytes + kCntNeed) : kStages * kStageBytes;  // idx + cnt, contiguous
   static constexpr size_t kListBytes = size_t(6) * kListCap;
   static constexpr size_t kOffKey = 0;
   static constexpr size_t kOffIdx = kKeyBytes;
@@ -185,24 +195,25 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
   // Tile k holds tasks [a0 + k*THREADS, +THREADS) of the concatenated table, a0 = base rounded down to a multiple of
   // four tasks so that every copy starts 16-byte aligned; slot `tid` of a stage is this thread's task.
   const int64_t a0 = base - off0;
-  const int n_tiles = (off0 + tn + THREADS - 1) / THREADS;
+  constexpr int TPT = L::kTpt, TILE = L::kTile, NST = L::kStages;
+  const int n_tiles = (off0 + tn + TILE - 1) / TILE;
   auto issue = [&](int k) {  // thread 0 only
-    const int s = k & 1;
-    const int64_t start = a0 + int64_t(k) * THREADS;
+    const int s = k % NST;
+    const int64_t start = a0 + int64_t(k) * TILE;
     const int64_t left = t_pad - start;
-    const uint32_t cnt = uint32_t(left < int64_t(THREADS) ? left : int64_t(THREADS));  // multiple of 4, > 0
+    const uint32_t cnt = uint32_t(left < int64_t(TILE) ? left : int64_t(TILE));  // multiple of 4, > 0
     unsigned char* st = sStage + size_t(s) * L::kStageBytes;
     uint64_t* bar = &sBar[s];
     mbar_arrive_expect_tx(bar, cnt * 40u);
-    tma_load_1d(st + 0 * THREADS * 4, T.priority + start, cnt * 4u, bar);
-    tma_load_1d(st + 1 * THREADS * 4, T.numdep + start, cnt * 4u, bar);
-    tma_load_1d(st + 2 * THREADS * 4, T.gid + start, cnt * 4u, bar);
-    tma_load_1d(st + 3 * THREADS * 4, T.flags + start, cnt * 4u, bar);
-    tma_load_1d(st + 16 * THREADS + 0 * THREADS * 8, T.expected + start, cnt * 8u, bar);
-    tma_load_1d(st + 16 * THREADS + 1 * THREADS * 8, T.qbasis + start, cnt * 8u, bar);
-    tma_load_1d(st + 16 * THREADS + 2 * THREADS * 8, T.wbasis + start, cnt * 8u, bar);
+    tma_load_1d(st + 0 * TILE * 4, T.priority + start, cnt * 4u, bar);
+    tma_load_1d(st + 1 * TILE * 4, T.numdep + start, cnt * 4u, bar);
+    tma_load_1d(st + 2 * TILE * 4, T.gid + start, cnt * 4u, bar);
+    tma_load_1d(st + 3 * TILE * 4, T.flags + start, cnt * 4u, bar);
+    tma_load_1d(st + 16 * TILE + 0 * TILE * 8, T.expected + start, cnt * 8u, bar);
+    tma_load_1d(st + 16 * TILE + 1 * TILE * 8, T.qbasis + start, cnt * 8u, bar);
+    tma_load_1d(st + 16 * TILE + 2 * TILE * 8, T.wbasis + start, cnt * 8u, bar);
   };
-  if (tid == 0) { issue(0); if (n_tiles > 1) issue(1); }
+  if (tid == 0) { issue(0); if (NST > 1 && n_tiles > 1) issue(1); }
 
   unsigned int c_dm = 0, c_mq = 0, c_over = 0, c_wait = 0, c_sec = 0, c_cnt = 0;
   int64_t s_exp = 0, s_over = 0;
@@ -225,60 +236,80 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
 
   const uint32_t a_full0 = smem_u32(&sBar[0]), a_empty0 = smem_u32(&sBar[2]), a_nlist = smem_u32(&S->n_list);
   const uint32_t* st32_0 = reinterpret_cast<const uint32_t*>(sStage) + tid;
-  const int64_t* st64_0 = reinterpret_cast<const int64_t*>(sStage + 16 * THREADS) + tid;
+  const int64_t* st64_0 = reinterpret_cast<const int64_t*>(sStage + 16 * TILE) + tid;
   for (int k = 0; k < n_tiles; k++) {
-    const int s = k & 1;
-    const uint32_t ph = uint32_t(k >> 1) & 1u;
+    const int s = k % NST;
+    const uint32_t ph = uint32_t(k / NST) & 1u;
     mbar_wait_a(a_full0 + 8u * s, ph);  // the tile's bytes have landed
-    const int i = k * THREADS + tid - off0;
-    const bool valid = i >= 0 && i < tn;
     const uint32_t* st32 = st32_0 + s * (L::kStageBytes / 4);
     const int64_t* st64 = st64_0 + s * (L::kStageBytes / 8);
-    const int32_t prio = int32_t(st32[0 * THREADS]), nd = int32_t(st32[1 * THREADS]);
-    const int32_t gid = int32_t(st32[2 * THREADS]);
-    const uint32_t fl = st32[3 * THREADS];
-    const int64_t exp_ns = st64[0 * THREADS], qb = st64[1 * THREADS], wb = st64[2 * THREADS];
-    // Every field is in registers (the arrive is a release: it is ordered behind the loads above): the slot may be
-    // refilled while this tile is scored -- two tiles of prefetch distance instead of one.
+    int32_t prio[TPT], nd[TPT], gid[TPT];
+    uint32_t fl[TPT];
+    int64_t exp_ns[TPT], qb[TPT], wb[TPT];
+#pragma unroll
+    for (int u = 0; u < TPT; u++) {  // slot tid + u*THREADS of the tile is this thread's u-th task
+      prio[u] = int32_t(st32[0 * TILE + u * THREADS]); nd[u] = int32_t(st32[1 * TILE + u * THREADS]);
+      gid[u] = int32_t(st32[2 * TILE + u * THREADS]); fl[u] = st32[3 * TILE + u * THREADS];
+      exp_ns[u] = st64[0 * TILE + u * THREADS]; qb[u] = st64[1 * TILE + u * THREADS]; wb[u] = st64[2 * TILE + u * THREADS];
+    }
+    // Every field is in registers (the arrive is a release: it is ordered behind the loads above): the slot is refilled
+    // while this tile is scored.
     mbar_arrive_a(a_empty0 + 8u * s);
-    if (tid == 0 && k + 2 < n_tiles) { mbar_wait_a(a_empty0 + 8u * s, ph); issue(k + 2); }
-    bool complex_task = false, scores = false;
-    if (valid) {
-      // GetDistroQueueInfo (scheduler.go:66-138)
-      const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
-      const bool counted = !incl || dm;
-      const bool over = counted && exp_ns > threshold;
-      const bool wait_over = counted && dm && (sane_clock ? wb < wait_cutoff : since(now, wb) > threshold);
-      const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
-      c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += (fl & EVG_TF_OTHER_DISTRO) != 0;
-      c_cnt += counted;
-      if (counted) s_exp += exp_ns;
-      if (over) s_over += exp_ns;
-      complex_task = gid >= 0;  // a task-group task: its unit has other members (no GroupVersions, no edges here)
-      scores = !complex_task;   // unit == {this task}
+    if (tid == 0 && k + NST < n_tiles) { mbar_wait_a(a_empty0 + 8u * s, ph); issue(k + NST); }
+    int idx[TPT];
+    bool complex_task[TPT], scores[TPT];
+    uint32_t nd_term[TPT];
+    bool dom = true;
+#pragma unroll
+    for (int u = 0; u < TPT; u++) {
+      const int i = k * TILE + u * THREADS + tid - off0;
+      idx[u] = i;
+      const bool valid = i >= 0 && i < tn;
+      complex_task[u] = false; scores[u] = false;
+      if (valid) {
+        // GetDistroQueueInfo (scheduler.go:66-138)
+        const bool dm = (fl[u] & EVG_TF_DEPS_MET) != 0;
+        const bool counted = !incl || dm;
+        const bool over = counted && exp_ns[u] > threshold;
+        const bool wait_over = counted && dm && (sane_clock ? wb[u] < wait_cutoff : since(now, wb[u]) > threshold);
+        const bool mq_dm = dm && (fl[u] & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
+        c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += (fl[u] & EVG_TF_OTHER_DISTRO) != 0;
+        c_cnt += counted;
+        if (counted) s_exp += exp_ns[u];
+        if (over) s_over += exp_ns[u];
+        complex_task[u] = gid[u] >= 0;  // a task-group task: its unit has other members (no GroupVersions, no edges here)
+        scores[u] = !complex_task[u];   // unit == {this task}
+      }
+      const uint32_t ndc = uint32_t(nd[u] > 0 ? nd[u] : 0);
+      nd_term[u] = ndc < uint32_t(kNdTable) ? sNd[ndc] : ((f32.ok && ndc < kTask32Limit) ? f32.nd * ndc : 0xFFFFFFFFu);
+      dom = dom && (!scores[u] || (nd_term[u] != 0xFFFFFFFFu && score32_domain_nd(now, prio[u], exp_ns[u], qb[u])));
     }
-    uint64_t v;
-    const uint32_t ndc = uint32_t(nd > 0 ? nd : 0);
-    const uint32_t nd_term = ndc < uint32_t(kNdTable) ? sNd[ndc] : ((f32.ok && ndc < kTask32Limit) ? f32.nd * ndc : 0xFFFFFFFFu);
-    if (f32.ok_base && __all_sync(full, !scores || (nd_term != 0xFFFFFFFFu && score32_domain_nd(now, prio, exp_ns, qb))))
-      v = single_task_value32_nd(f32, now, prio, exp_ns, qb, nd_term, fl);
-    else
-      v = score_slow(pf, fast_clock, scores, now, prio, exp_ns, qb, nd, fl);
-    if (scores) {
-      if (v >> 32) punt = true;  // does not fit the u32 key (negative values included): k_plan_smem plans this distro
-      const uint32_t v32 = uint32_t(v);
-      sKey[i] = v32;
-      vmn = min(vmn, v32); vmx = max(vmx, v32);
+    uint64_t v[TPT];
+    if (f32.ok_base && __all_sync(full, dom)) {
+#pragma unroll
+      for (int u = 0; u < TPT; u++) v[u] = single_task_value32_nd(f32, now, prio[u], exp_ns[u], qb[u], nd_term[u], fl[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < TPT; u++) v[u] = score_slow(pf, fast_clock, scores[u], now, prio[u], exp_ns[u], qb[u], nd[u], fl[u]);
     }
-    if (any) {  // warp-aggregated append to the work list
-      const unsigned m = __ballot_sync(full, complex_task);
-      if (m) {
-        unsigned int pos0 = 0;
-        if (lane == 0) pos0 = atom_add_shared(a_nlist, (unsigned int)__popc(m));
-        pos0 = __shfl_sync(full, pos0, 0);
-        if (complex_task) {
-          const unsigned int pos = pos0 + __popc(m & ((1u << lane) - 1u));
-          if (pos < (unsigned)kListCap) sList[pos] = uint16_t(i);
+#pragma unroll
+    for (int u = 0; u < TPT; u++) {
+      if (scores[u]) {
+        if (v[u] >> 32) punt = true;  // does not fit the u32 key (negative values included): k_plan_smem plans this distro
+        const uint32_t v32 = uint32_t(v[u]);
+        sKey[idx[u]] = v32;
+        vmn = min(vmn, v32); vmx = max(vmx, v32);
+      }
+      if (any) {  // warp-aggregated append to the work list
+        const unsigned m = __ballot_sync(full, complex_task[u]);
+        if (m) {
+          unsigned int pos0 = 0;
+          if (lane == 0) pos0 = atom_add_shared(a_nlist, (unsigned int)__popc(m));
+          pos0 = __shfl_sync(full, pos0, 0);
+          if (complex_task[u]) {
+            const unsigned int pos = pos0 + __popc(m & ((1u << lane) - 1u));
+            if (pos < (unsigned)kListCap) sList[pos] = uint16_t(idx[u]);
+          }
         }
       }
     }
