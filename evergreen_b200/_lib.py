@@ -131,6 +131,11 @@ EVG_LEGACY_MODE_INGEST, EVG_LEGACY_MODE_REVISION, EVG_LEGACY_MODE_LITERAL = 0, 1
 EVG_LEGACY_OK, EVG_LEGACY_NOT_DECOMPOSABLE = 0, 1
 
 
+class DagInStruct(C.Structure):
+    _fields_ = [("n_items", C.c_int64), ("n_deps", C.c_int64), ("dep_off", C.c_void_p), ("dep_item", C.c_void_p),
+                ("group_id", C.c_void_p), ("group_index", C.c_void_p)]
+
+
 class AllocOutStruct(C.Structure):
     _fields_ = [("result", C.c_void_p), ("status", C.c_void_p)]
 
@@ -170,6 +175,7 @@ SYMBOLS = {
     "evg_find_runnable_batch": (C.c_int, [_P, _P, _P, _P]),
     "evg_expected_durations_batch": (C.c_int, [_P, _P, _P]),
     "evg_prioritize_legacy_batch": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P]),
+    "evg_dag_rebuild_batch": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "evg_plan_distro": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, C.c_uint32, _P]),
     "evg_alloc_distro": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P]),
 }

@@ -244,6 +244,7 @@ __device__ __forceinline__ uint32_t pair_task(const DTasks& T, const DWork& W, u
 #include "evg_plan_cta.cuh"
 #include "evg_plan_general.cuh"
 #include "evg_legacy.cuh"
+#include "evg_dag.cuh"
 
 // --------------------------------------------------------------------------
 // kernels (general path: any distro size)
@@ -1967,6 +1968,86 @@ int evg_prioritize_legacy_batch(evg_ctx* c, const evg_legacy_soa* in, const int6
     count[d] = empty ? 0 : cnt[d];
     status[d] = empty ? EVG_LEGACY_OK : st[d];
   }
+  return EVG_OK;
+}
+
+int evg_dag_rebuild_batch(evg_ctx* c, const evg_dag_in* in, const int64_t* item_off, const int64_t* group_off, int32_t n_distros,
+                          int32_t* sorted, int32_t* n_sorted, int32_t* n_cycles, int32_t* unit_items, int32_t* unit_off) {
+  if (!c || !in) return fail(EVG_ERR_INVALID, "evg_dag_rebuild_batch: null argument");
+  LOCK(c);
+  const int64_t N = in->n_items, E = in->n_deps;
+  const int32_t D = n_distros;
+  if (N < 0 || E < 0 || D < 0) return fail(EVG_ERR_INVALID, "negative sizes");
+  if (D == 0) return N == 0 ? EVG_OK : fail(EVG_ERR_INVALID, "items without distros");
+  if (!item_off || !group_off || !n_sorted || !n_cycles || !unit_off || (N > 0 && (!sorted || !unit_items))) return fail(EVG_ERR_INVALID, "null argument");
+  if (N > 0 && (!in->dep_off || !in->group_id || !in->group_index)) return fail(EVG_ERR_INVALID, "null item column");
+  if (E > 0 && !in->dep_item) return fail(EVG_ERR_INVALID, "null dep_item");
+  if (item_off[0] != 0 || item_off[D] != N || group_off[0] != 0) return fail(EVG_ERR_INVALID, "offsets do not span the tables");
+  if (N > 0 && (in->dep_off[0] != 0 || in->dep_off[N] != E)) return fail(EVG_ERR_INVALID, "dep_off does not span n_deps");
+  int64_t max_n = 0;
+  for (int32_t d = 0; d < D; d++) {
+    if (item_off[d + 1] < item_off[d] || group_off[d + 1] < group_off[d]) return fail(EVG_ERR_INVALID, "offsets of distro %d decrease", d);
+    max_n = std::max(max_n, item_off[d + 1] - item_off[d]);
+  }
+  if (max_n >= (int64_t(1) << 31) - 1) return fail(EVG_ERR_INVALID, "a queue exceeds 2^31 items");
+  const int64_t G = group_off[D];
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  c->launches = 0;
+  c->have_tasks = false;  // shares scratch buffers with the planner's resident inputs
+#define UPG(buf, ptr, count_, type)                                                                                \
+  do {                                                                                                             \
+    CK((buf).ensure(sizeof(type) * size_t((count_) > 0 ? (count_) : 1)));                                          \
+    if ((count_) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(count_), cudaMemcpyHostToDevice, s)); \
+  } while (0)
+  UPG(c->b_taskoff, item_off, D + 1, int64_t);
+  UPG(c->b_groupoff, group_off, D + 1, int64_t);
+  UPG(c->b_depoff, in->dep_off, N + 1, int64_t);
+  UPG(c->b_depidx, in->dep_item, E, int32_t);
+  UPG(c->b_gid, in->group_id, N, int32_t);
+  UPG(c->b_tgo, in->group_index, N, int32_t);
+#undef UPG
+  DevBuf* scratch[] = {&c->b_prio, &c->b_nd, &c->b_vid, &c->b_flags, &c->b_rn0, &c->b_rn1, &c->b_rn2, &c->b_rn3, &c->b_rn4};
+  for (DevBuf* b : scratch) CK(b->ensure(sizeof(int32_t) * size_t(N + D + 1)));
+  CK(c->b_rn5.ensure(sizeof(int32_t) * size_t(E + 1)));
+  CK(c->b_hasdep.ensure(size_t(N) + 16));
+  CK(c->b_order.ensure(sizeof(int32_t) * size_t(N + 1)));
+  CK(c->b_rn6.ensure(sizeof(int32_t) * 3 * size_t(D + 1)));
+  CK(c->b_rn7.ensure(sizeof(int32_t) * size_t(G + D + 1)));
+  DDag x;
+  x.n = N; x.n_deps = E; x.n_distros = D;
+  x.item_off = c->b_taskoff.as<int64_t>(); x.dep_off = c->b_depoff.as<int64_t>(); x.dep_item = c->b_depidx.as<int32_t>();
+  x.group_id = c->b_gid.as<int32_t>(); x.group_index = c->b_tgo.as<int32_t>();
+  x.succ_off = c->b_prio.as<int32_t>(); x.succ = c->b_rn5.as<int32_t>(); x.index = c->b_nd.as<int32_t>(); x.low = c->b_vid.as<int32_t>();
+  x.stack = c->b_flags.as<int32_t>(); x.cs_node = c->b_rn0.as<int32_t>(); x.cs_pos = c->b_rn1.as<int32_t>(); x.emit = c->b_rn2.as<int32_t>();
+  x.on_stack = c->b_hasdep.as<uint8_t>();
+  int32_t* d_nsorted = c->b_rn6.as<int32_t>();
+  int32_t* d_ncycles = d_nsorted + (D + 1);
+  int32_t* d_grouped = d_ncycles + (D + 1);
+  LAUNCH(c, k_dag_topo, grid_for(D, 64), 64, x, c->b_order.as<int32_t>(), d_nsorted, d_ncycles);
+  std::vector<int32_t> grouped(size_t(D), 0);
+  int32_t* buf[2] = {c->b_rn3.as<int32_t>(), c->b_rn4.as<int32_t>()};
+  int cur = 0;
+  if (N > 0) {
+    CK(cudaMemcpyAsync(sorted, c->b_order.p, sizeof(int32_t) * size_t(N), cudaMemcpyDeviceToHost, s));
+    // every item has a group or not: "no ungrouped item" leaves grouped[d] at the distro's length
+    for (int32_t d = 0; d < D; d++) grouped[size_t(d)] = int32_t(item_off[d + 1] - item_off[d]);
+    CK(cudaMemcpyAsync(d_grouped, grouped.data(), sizeof(int32_t) * size_t(D), cudaMemcpyHostToDevice, s));
+    LAUNCH(c, k_dag_group_init, grid_for(N, 256), 256, x, buf[0]);
+    for (int64_t L = 1; L < max_n; L <<= 1) {
+      LAUNCH(c, k_dag_group_pass, grid_for(N, 256), 256, x, buf[cur], buf[cur ^ 1], L);
+      cur ^= 1;
+    }
+    LAUNCH(c, k_dag_units, grid_for(N, 256), 256, x, buf[cur], c->b_groupoff.as<int64_t>(), c->b_rn7.as<int32_t>(), d_grouped);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(unit_items, buf[cur], sizeof(int32_t) * size_t(N), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(unit_off, c->b_rn7.p, sizeof(int32_t) * size_t(G + D), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(grouped.data(), d_grouped, sizeof(int32_t) * size_t(D), cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaMemcpyAsync(n_sorted, d_nsorted, sizeof(int32_t) * size_t(D), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(n_cycles, d_ncycles, sizeof(int32_t) * size_t(D), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int32_t d = 0; d < D; d++) unit_off[group_off[d + 1] + d] = grouped[size_t(d)];  // the closing entry of each distro
   return EVG_OK;
 }
 

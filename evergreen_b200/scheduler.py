@@ -274,6 +274,19 @@ class Engine:
                                                      L.ptr(order) if T else None, L.ptr(count), L.ptr(status)))
         return order, count, status
 
+    def dag_rebuild_batch(self, item_off, group_off, dep_off, dep_item, group_id, group_index):
+        """evg_dag_rebuild_batch -> (sorted, n_sorted, n_cycles, unit_items, unit_off)."""
+        D = int(item_off.shape[0]) - 1
+        N, E, G = int(item_off[-1]), int(dep_off[-1]) if dep_off.shape[0] else 0, int(group_off[-1])
+        st = L.DagInStruct(N, E, L.ptr(dep_off), L.ptr(dep_item) if E else None, L.ptr(group_id) if N else None,
+                           L.ptr(group_index) if N else None)
+        sorted_ = self._out("dag_sorted", max(N, 1), np.int32)
+        n_sorted, n_cycles = self._out("dag_nsorted", D, np.int32), self._out("dag_ncycles", D, np.int32)
+        unit_items, unit_off = self._out("dag_unit_items", max(N, 1), np.int32), self._out("dag_unit_off", G + D, np.int32)
+        L.check(self.lib.evg_dag_rebuild_batch(self.ctx, C.byref(st), L.ptr(item_off), L.ptr(group_off), D, L.ptr(sorted_) if N else None,
+                                               L.ptr(n_sorted), L.ptr(n_cycles), L.ptr(unit_items) if N else None, L.ptr(unit_off)))
+        return sorted_[:N], n_sorted, n_cycles, unit_items[:N], unit_off
+
     def alloc_batch(self, hosts: S.HostSoA, qinfo: np.ndarray, ginfo: np.ndarray, group_off: np.ndarray, now: int):
         D = int(qinfo.shape[0])
         ao = self._alloc_output(D)
@@ -616,3 +629,41 @@ class CmpBasedTaskPrioritizer:
         if status != L.EVG_LEGACY_OK:
             return None, None, NotDecomposableError(distro_id, sorted_tasks)
         return sorted_tasks, {}, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def rebuild_dag_dispatchers(queues: Sequence[M.TaskQueue], *, engine: Optional[Engine] = None):
+    """basicCachedDAGDispatcherImpl.rebuild for a batch of persisted queues (model/task_queue_service_dependency.go:
+    153-252).  Per queue: (sorted item ids with None for each dependency cycle's placeholder, number of cycles,
+    {composite group id: [item ids by GroupIndex]})."""
+    eng = engine or default_engine()
+    item_off, group_off, dep_off, dep_item, group_id, group_index, names = [0], [0], [0], [], [], [], []
+    for q in queues:
+        pos = {it.id: k for k, it in enumerate(q.queue)}
+        groups: Dict[str, int] = {}
+        for it in q.queue:
+            for dep in it.dependencies:
+                dep_item.append(pos.get(dep, -1))
+            dep_off.append(len(dep_item))
+            if it.group:
+                gid = f"{it.group}_{it.build_variant}_{it.project}_{it.version}"  # compositeGroupID
+                group_id.append(groups.setdefault(gid, len(groups)))
+            else:
+                group_id.append(-1)
+            group_index.append(it.group_index)
+        names.append(list(groups))
+        item_off.append(item_off[-1] + len(q.queue))
+        group_off.append(group_off[-1] + len(groups))
+    a = lambda x, t: np.ascontiguousarray(np.array(x, dtype=t))  # noqa: E731
+    io, go = a(item_off, np.int64), a(group_off, np.int64)
+    srt, n_sorted, n_cycles, unit_items, unit_off = eng.dag_rebuild_batch(io, go, a(dep_off, np.int64), a(dep_item, np.int32),
+                                                                            a(group_id, np.int32), a(group_index, np.int32))
+    out = []
+    for d, q in enumerate(queues):
+        b = int(io[d])
+        order = [None if int(i) < 0 else q.queue[int(i)].id for i in srt[b:b + int(n_sorted[d])]]
+        u = int(go[d]) + d
+        units = {name: [q.queue[int(i)].id for i in unit_items[b + int(unit_off[u + g]):b + int(unit_off[u + g + 1])]]
+                 for g, name in enumerate(names[d])}
+        out.append((order, int(n_cycles[d]), units))
+    return out

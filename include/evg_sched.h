@@ -509,6 +509,29 @@ typedef struct {
 int evg_prioritize_legacy_batch(evg_ctx* ctx, const evg_legacy_soa* tasks, const int64_t* task_off, const uint8_t* list_mode,
                                 int32_t n_distros, int32_t* order, int64_t* count, int32_t* status);
 
+/* ---- DAG dispatcher rebuild ------------------------------ */
+
+/* The persisted queues of a batch of distros, concatenated in queue order (item k of distro d has queueIndex k). */
+typedef struct {
+  int64_t n_items;
+  int64_t n_deps;
+  const int64_t* dep_off;      /* n_items + 1: CSR of TaskQueueItem.Dependencies */
+  const int32_t* dep_item;     /* n_deps: distro-local index of the item with that id, -1 when it is not in this queue */
+  const int32_t* group_id;     /* n_items: distro-local dense id of compositeGroupID(Group, BuildVariant, Project, Version), -1 when Group == "" */
+  const int32_t* group_index;  /* n_items: TaskQueueItem.GroupIndex */
+} evg_dag_in;
+
+/* basicCachedDAGDispatcherImpl.rebuild for every distro (model/task_queue_service_dependency.go:153-252).
+ * sorted[item_off[d] .. + n_sorted[d]) = d.sorted as distro-local item indices: topo.SortStabilized over the edges
+ *   dependency -> item with ties in queue order; -1 stands for the nil gonum leaves for a dependency cycle (one per
+ *   cyclic component, n_cycles[d] of them); the rest of the distro's slots are -2.
+ * unit_items[item_off[d] ..] = the items that have a group, bucketed by group id and stably sorted by GroupIndex inside
+ *   each bucket (d.taskGroups[...].tasks); group g of distro d is unit_items[item_off[d] + unit_off[u + g] ..
+ *   item_off[d] + unit_off[u + g + 1]) with u = group_off[d] + d (each distro has one closing entry).
+ * Host pointers.  group_off (n_distros + 1) counts the groups of each distro. */
+int evg_dag_rebuild_batch(evg_ctx* ctx, const evg_dag_in* in, const int64_t* item_off, const int64_t* group_off, int32_t n_distros,
+                          int32_t* sorted, int32_t* n_sorted, int32_t* n_cycles, int32_t* unit_items, int32_t* unit_off);
+
 /* ---- single-distro wrappers: the per-job drop-in ------------------------- */
 
 /* One distro: PrioritizeTasks for `d` (scheduler/scheduler.go:27). */

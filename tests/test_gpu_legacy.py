@@ -164,3 +164,44 @@ def test_large_queue_properties(engine):
     key = np.stack([-table.priority[pl], -table.num_dependents[pl].astype(np.int64), (~gen).astype(np.int64), table.ingest_ns[pl],
                     -table.expected_ns[pl], table.presort_rank[pl].astype(np.int64)], axis=1)
     assert (np.lexsort(key.T[::-1]) == np.arange(len(pl))).all()
+
+
+# ---------------------------------------------------------------- DAG dispatcher rebuild
+def _tq(items):
+    return M.TaskQueue(distro="d", queue=[M.TaskQueueItem(id=it["id"], group=it.get("group", ""), build_variant=it.get("build_variant", ""),
+                                                           project=it.get("project", ""), version=it.get("version", ""),
+                                                           group_index=it.get("group_index", 0), dependencies=list(it.get("dependencies", [])))
+                                          for it in items])
+
+
+def test_dag_rebuild_reference_order(engine):
+    from oracle import oracle_dag as OD
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "dag_dispatcher.json")))
+    (order, n_cycles, units), = S.rebuild_dag_dispatchers([_tq(g["items"])], engine=engine)
+    assert order == g["expected_order"] and n_cycles == 0
+    assert len(units) == g["n_task_groups"] and {len(v) for v in units.values()} == {g["group_size"]}
+    assert units == OD.rebuild(g["items"])[2]
+
+
+def test_dag_rebuild_random_batches_match_the_oracle(engine):
+    from oracle import oracle_dag as OD
+    rnd = random.Random(12)
+    batches = []
+    for n in (0, 1, 2, 50, 700, 3000, 10000):
+        items = []
+        for k in range(n):
+            deps = [str(rnd.randrange(n)) for _ in range(rnd.choice([0, 0, 0, 1, 2, 3]))]
+            if rnd.random() < 0.02:
+                deps.append("not-in-queue")
+            if deps and rnd.random() < 0.1:
+                deps.append(deps[0])  # a repeated dependency: parallel lines in the multigraph
+            grp = rnd.random() < 0.3
+            items.append({"id": str(k), "dependencies": deps, "group": f"g{rnd.randrange(6)}" if grp else "", "build_variant": f"bv{rnd.randrange(2)}",
+                          "project": "p", "version": f"v{rnd.randrange(3)}", "group_index": rnd.randrange(-2, 9)})
+        batches.append(items)
+    res = S.rebuild_dag_dispatchers([_tq(b) for b in batches], engine=engine)
+    for items, (order, n_cycles, units) in zip(batches, res):
+        want_order, want_cycles, want_units = OD.rebuild(items)
+        assert order == want_order and n_cycles == len(want_cycles)
+        assert units == want_units
+    assert any(n for _, n, _ in res)  # random edges in both directions do form cycles somewhere
