@@ -260,29 +260,34 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
     bool complex_task[TPT], scores[TPT];
     uint32_t nd_term[TPT];
     bool dom = true;
+    // Straight-line on purpose: & and | on bools instead of && and ||, selects instead of guarded adds -- the
+    // short-circuit forms compile to a branch (BSSY/BRA/BSYNC) per operator, which was a fifth of this loop.
 #pragma unroll
     for (int u = 0; u < TPT; u++) {
       const int i = k * TILE + u * THREADS + tid - off0;
       idx[u] = i;
-      const bool valid = i >= 0 && i < tn;
-      complex_task[u] = false; scores[u] = false;
-      if (valid) {
-        // GetDistroQueueInfo (scheduler.go:66-138)
-        const bool dm = (fl[u] & EVG_TF_DEPS_MET) != 0;
-        const bool counted = !incl || dm;
-        const bool over = counted && exp_ns[u] > threshold;
-        const bool wait_over = counted && dm && (sane_clock ? wb[u] < wait_cutoff : since(now, wb[u]) > threshold);
-        const bool mq_dm = dm && (fl[u] & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
-        c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += (fl[u] & EVG_TF_OTHER_DISTRO) != 0;
-        c_cnt += counted;
-        if (counted) s_exp += exp_ns[u];
-        if (over) s_over += exp_ns[u];
-        complex_task[u] = gid[u] >= 0;  // a task-group task: its unit has other members (no GroupVersions, no edges here)
-        scores[u] = !complex_task[u];   // unit == {this task}
-      }
+      const bool valid = (i >= 0) & (i < tn);
+      // GetDistroQueueInfo (scheduler.go:66-138)
+      const bool dm = valid & ((fl[u] & EVG_TF_DEPS_MET) != 0);
+      const bool counted = valid & (!incl | dm);
+      const bool over = counted & (exp_ns[u] > threshold);
+      const bool waited = sane_clock ? (wb[u] < wait_cutoff) : (since(now, wb[u]) > threshold);  // sane_clock is CTA-uniform
+      const bool wait_over = counted & dm & waited;
+      const bool mq_dm = dm & ((fl[u] & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE);
+      c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += valid & ((fl[u] & EVG_TF_OTHER_DISTRO) != 0);
+      c_cnt += counted;
+      s_exp += counted ? exp_ns[u] : 0;
+      s_over += over ? exp_ns[u] : 0;
+      complex_task[u] = valid & (gid[u] >= 0);  // a task-group task: its unit has other members (no GroupVersions, no edges here)
+      scores[u] = valid & (gid[u] < 0);         // unit == {this task}
+      // the 32-bit scorer's domain (score32_domain_nd + the tabulated NumDependents term), branch-free
       const uint32_t ndc = uint32_t(nd[u] > 0 ? nd[u] : 0);
-      nd_term[u] = ndc < uint32_t(kNdTable) ? sNd[ndc] : ((f32.ok && ndc < kTask32Limit) ? f32.nd * ndc : 0xFFFFFFFFu);
-      dom = dom && (!scores[u] || (nd_term[u] != 0xFFFFFFFFu && score32_domain_nd(now, prio[u], exp_ns[u], qb[u])));
+      const uint32_t tab = sNd[ndc < uint32_t(kNdTable) ? ndc : 0u];
+      const uint32_t mul = (f32.ok & (ndc < kTask32Limit)) ? f32.nd * ndc : 0xFFFFFFFFu;
+      nd_term[u] = ndc < uint32_t(kNdTable) ? tab : mul;
+      const bool q_ok = (qb[u] == EVG_TIME_ZERO) | ((qb[u] >= 0) & (uint64_t(now - qb[u]) < kFastLimit));
+      const bool in_dom = q_ok & (uint64_t(exp_ns[u]) < kFastLimit) & (prio[u] < int32_t(kTask32Limit)) & (nd_term[u] != 0xFFFFFFFFu);
+      dom = dom & (!scores[u] | in_dom);
     }
     uint64_t v[TPT];
     if (f32.ok_base && __all_sync(full, dom)) {
@@ -582,6 +587,7 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
     const int seg = ((tn + NW - 1) / NW + 31) & ~31;
     const int seg0 = warp * seg;
     const int seg1 = min(seg0 + seg, tn);
+    const bool full_seg = seg1 - seg0 == ITEMS * 32;  // warp-uniform: every lane of every chunk holds an element
     const unsigned lt = (1u << lane) - 1u;
     const int npass = (bits + MAXBITS - 1) / MAXBITS;
     const int wbase = npass ? bits / npass : 0, wrem = npass ? bits % npass : 0;
@@ -592,47 +598,46 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       const uint32_t nd = 1u << wbits, mask = nd - 1u;
       for (uint32_t x = lane; x < (nd + 1) / 2; x += 32) wc[x] = 0u;
       __syncwarp();
-      uint32_t ci[ITEMS / 2];  // task indices, two per register
-      uint32_t cr[ITEMS];      // digit | warp-local rank << 10
-      // all the permutation loads first, then all the key gathers (independent shared-memory loads in flight together);
-      // only then the MATCH / atomic / shuffle chain, which must run chunk by chunk
+      uint32_t ci[ITEMS];  // task index of the element at chunk j
+      uint32_t cr[ITEMS];  // its digit | warp-local rank << 10
+      // FULL: no per-element bounds (15 of 16 warps of a 10k-task distro); otherwise padding lanes carry digit 0x7FFF
+      // and match only each other.  All permutation loads first, then all key gathers (independent shared-memory
+      // loads in flight together), only then the MATCH / atomic / shuffle chain, which must run chunk by chunk.
+      auto rank = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-      for (int j = 0; j < ITEMS; j += 2) {
-        const int p0 = seg0 + j * 32 + lane, p1 = p0 + 32;
-        const uint32_t i0 = (j * 32 < seg && p0 < seg1) ? uint32_t(sIdx[p0]) : 0u;
-        const uint32_t i1 = ((j + 1) * 32 < seg && p1 < seg1) ? uint32_t(sIdx[p1]) : 0u;
-        ci[j >> 1] = i0 | (i1 << 16);
-      }
-#pragma unroll
-      for (int j = 0; j < ITEMS; j++) {
-        if (j * 32 < seg) {
-          const uint32_t i = (j & 1) ? (ci[j >> 1] >> 16) : (ci[j >> 1] & 0xFFFFu);
-          const bool ok = seg0 + j * 32 + lane < seg1;
-          const uint32_t key = vmax - sKey[i];
-          cr[j] = ok ? ((key >> shift) & mask) : 0x7FFFu;  // padding lanes match only each other
+        for (int j = 0; j < ITEMS; j++) {
+          const int p = seg0 + j * 32 + lane;
+          ci[j] = (FULL || p < seg1) ? uint32_t(sIdx[p]) : 0u;
         }
-      }
 #pragma unroll
-      for (int j = 0; j < ITEMS; j++) {
-        if (j * 32 < seg) {  // warp-uniform
-          const uint32_t dg = cr[j];
-          const bool ok = dg != 0x7FFFu;
-          const unsigned peers = __match_any_sync(full, dg);
-          const uint32_t r = __popc(peers & lt);
-          uint32_t old = 0;
-          if (ok && r == 0) old = atomicAdd(&wc[dg >> 1], uint32_t(__popc(peers)) << (16 * (dg & 1u)));
-          old = __shfl_sync(full, old, __ffs(peers) - 1);
-          const uint32_t wr = ((old >> (16 * (dg & 1u))) & 0xFFFFu) + r;
-          cr[j] = (dg & 0x3FFu) | (wr << 10);
+        for (int j = 0; j < ITEMS; j++) {
+          const uint32_t dg = ((vmax - sKey[ci[j]]) >> shift) & mask;
+          cr[j] = (FULL || seg0 + j * 32 + lane < seg1) ? dg : 0x7FFFu;
         }
-      }
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+          if (FULL || seg0 + j * 32 < seg1) {  // warp-uniform
+            const uint32_t dg = cr[j];
+            const unsigned peers = __match_any_sync(full, dg);
+            const uint32_t r = __popc(peers & lt);
+            const uint32_t sh = (dg & 1u) << 4;
+            uint32_t old = 0;
+            if (r == 0 && (FULL || dg != 0x7FFFu)) old = atomicAdd(&wc[dg >> 1], uint32_t(__popc(peers)) << sh);
+            old = __shfl_sync(full, old, __ffs(peers) - 1);
+            cr[j] = (dg & 0x3FFu) | ((((old >> sh) & 0xFFFFu) + r) << 10);
+          }
+        }
+      };
+      if (full_seg) rank(std::true_type{}); else rank(std::false_type{});
       __syncthreads();
       {  // block-wide scan: thread t owns digits 2t and 2t+1 (one u32 of every warp's row)
-        uint32_t x[NW];
         uint32_t tot = 0;
         const bool act = uint32_t(2 * tid) < nd;
+        if (act) {
 #pragma unroll
-        for (int w = 0; w < NW; w++) { x[w] = act ? sCnt[w * DW + tid] : 0u; tot += x[w]; }  // packed halves never carry: totals <= CAP
+          for (int w = 0; w < NW; w++) tot += sCnt[w * DW + tid];  // packed halves never carry: totals <= CAP
+        }
         const uint32_t t0 = tot & 0xFFFFu, t1 = tot >> 16;
         const uint32_t sum = t0 + t1;
         uint32_t inc = sum;
@@ -652,22 +657,22 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
         uint32_t run = ex | ((ex + t0) << 16);
         if (act) {
 #pragma unroll
-          for (int w = 0; w < NW; w++) { sCnt[w * DW + tid] = run; run += x[w]; }
+          for (int w = 0; w < NW; w++) { const uint32_t x = sCnt[w * DW + tid]; sCnt[w * DW + tid] = run; run += x; }
         }
       }
       __syncthreads();
+      auto scatter = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-      for (int j = 0; j < ITEMS; j++) {
-        if (j * 32 < seg) {
-          const int p = seg0 + j * 32 + lane;
-          if (p < seg1) {
+        for (int j = 0; j < ITEMS; j++) {
+          if (FULL || seg0 + j * 32 + lane < seg1) {
             const uint32_t dg = cr[j] & 0x3FFu, wr = cr[j] >> 10;
-            const uint32_t bs = (wc[dg >> 1] >> (16 * (dg & 1u))) & 0xFFFFu;
-            const uint32_t i = (j & 1) ? (ci[j >> 1] >> 16) : (ci[j >> 1] & 0xFFFFu);
-            sIdx[bs + wr] = uint16_t(i);
+            const uint32_t bs = (wc[dg >> 1] >> ((dg & 1u) << 4)) & 0xFFFFu;
+            sIdx[bs + wr] = uint16_t(ci[j]);
           }
         }
-      }
+      };
+      if (full_seg) scatter(std::true_type{}); else scatter(std::false_type{});
       __syncthreads();
       shift += wbits;
     }

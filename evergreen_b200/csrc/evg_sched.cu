@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <mutex>
 #include <string>
 #include <vector>

@@ -28,7 +28,8 @@ import numpy as np
 from evergreen_b200 import _lib as L
 lib = C.CDLL(sys.argv[1])
 for name, (res, args) in L.SYMBOLS.items():
-    fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
+    if hasattr(lib, name):
+        fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
 L._lib = lib
 from evergreen_b200 import scheduler, synth
 eng = scheduler.Engine(0)

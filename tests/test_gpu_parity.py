@@ -943,10 +943,11 @@ def test_persist_task_queue_mirror(engine):
                        depends_on=[M.Dependency("nowhere")] if k % 50 == 7 else []) for k in range(n)]
     da, db = M.Distro(id="a"), M.Distro(id="b")
     ta, tb = tasks(12000, "a"), tasks(40, "b")
+    tb_again, tb_third = copy.deepcopy(tb), copy.deepcopy(tb)
     qa, qb = S.persist_task_queues([(da, ta), (db, tb)], synth.NOW_NS, engine=engine)
     assert len(qa.queue) == 10000 and len(qb.queue) == 40 and qa.distro == "a"
     assert qa.distro_queue_info.length == 12000 and qb.distro_queue_info.length == 40
-    plan, info = S.PrioritizeTasks(db, tasks(40, "b"), now=synth.NOW_NS, engine=engine)
+    plan, info = S.PrioritizeTasks(db, tb_again, now=synth.NOW_NS, engine=engine)
     assert [i.id for i in qb.queue] == [t.id for t in plan]
     by_id = {t.id: t for t in tb}
     for it, t in zip(qb.queue, plan):
@@ -962,7 +963,7 @@ def test_persist_task_queue_mirror(engine):
     # PlanDistro: disabled distro
     q, cleared = S.PlanDistro(M.Distro(id="x", disabled=True), lambda d: 1 / 0, now=synth.NOW_NS, engine=engine, existing_queue_length=5)
     assert q is None and cleared
-    q, cleared = S.PlanDistro(db, lambda d: tasks(40, "b"), now=synth.NOW_NS, engine=engine)
+    q, cleared = S.PlanDistro(db, lambda d: tb_third, now=synth.NOW_NS, engine=engine)
     assert [i.id for i in q.queue] == [i.id for i in qb.queue] and not cleared
     # units/host_allocator.go:182-184
     assert S.hosts_to_request(M.Distro(id="s", single_task_distro=True), qb.distro_queue_info, 3, lambda: 1 / 0) == \
