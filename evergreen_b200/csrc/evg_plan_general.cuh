@@ -38,6 +38,7 @@ struct DGen {
   uint32_t* tile_sum;          // [NT] sum of e over the tile, then the tile's exclusive offset inside its distro
   uint32_t* tile_hist;         // [NT*256]
   uint32_t* clist;             // work list: global task index of every task that touches a multi-member unit
+  int32_t* clist_d;            // its distro
   unsigned int* ccount;        // [1]
   uint32_t* tie_a;             // [T] anchor of the unit the task is emitted from (work-list tasks)
   uint32_t* tie_r;             // [T] rank inside it
@@ -99,7 +100,6 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
   const int64_t base = D.task_off[d], end = D.task_off[d + 1];
   const int64_t ts = G.tile_start[tile];
   const uint32_t ng = uint32_t(D.group_off[d + 1] - D.group_off[d]);
-  const uint32_t ub = uint32_t(D.unit_base[d]);
   const bool gv = cfg.group_versions != 0;
   const int64_t threshold = cfg.target_time_ns;
   const PlannerFactors pf = clamp_factors(cfg);
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
   for (int u = 0; u < 2; u++) {
     const int64_t t4 = ts + 4 * int64_t(u * 256 + tid);  // multiple of 4: 16-byte aligned in every column
     const bool live = t4 < end;  // the columns are readable 8 slots past the last task (upload pads them)
-    int4 prio4 = make_int4(0, 0, 0, 0), nd4 = prio4, gid4 = make_int4(-1, -1, -1, -1), vid4 = prio4;
+    int4 prio4 = make_int4(0, 0, 0, 0), nd4 = prio4, gid4 = make_int4(-1, -1, -1, -1);
     uint4 fl4 = make_uint4(0, 0, 0, 0);
     longlong2 ex01 = make_longlong2(0, 0), ex23 = ex01, qb01 = ex01, qb23 = ex01, wb01 = ex01, wb23 = ex01;
     if (live) {
@@ -134,7 +134,6 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
       ex01 = *reinterpret_cast<const longlong2*>(T.expected + t4); ex23 = *reinterpret_cast<const longlong2*>(T.expected + t4 + 2);
       qb01 = *reinterpret_cast<const longlong2*>(T.qbasis + t4); qb23 = *reinterpret_cast<const longlong2*>(T.qbasis + t4 + 2);
       wb01 = *reinterpret_cast<const longlong2*>(T.wbasis + t4); wb23 = *reinterpret_cast<const longlong2*>(T.wbasis + t4 + 2);
-      if (gv) vid4 = *reinterpret_cast<const int4*>(T.vid + t4);
     }
     // dependency offsets of the four tasks (five consecutive entries) and their "has dependents" bytes, as vectors too
     int64_t doff[5] = {0, 0, 0, 0, 0};
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
       hd4 = *reinterpret_cast<const uint32_t*>(W.has_dep + t4);
     }
     const int32_t prio_[4] = {prio4.x, prio4.y, prio4.z, prio4.w}, nd_[4] = {nd4.x, nd4.y, nd4.z, nd4.w};
-    const int32_t gid_[4] = {gid4.x, gid4.y, gid4.z, gid4.w}, vid_[4] = {vid4.x, vid4.y, vid4.z, vid4.w};
+    const int32_t gid_[4] = {gid4.x, gid4.y, gid4.z, gid4.w};
     const uint32_t fl_[4] = {fl4.x, fl4.y, fl4.z, fl4.w};
     const int64_t ex_[4] = {ex01.x, ex01.y, ex23.x, ex23.y}, qb_[4] = {qb01.x, qb01.y, qb23.x, qb23.y};
     const int64_t wb_[4] = {wb01.x, wb01.y, wb23.x, wb23.y};
@@ -157,65 +156,37 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
 #pragma unroll
     for (int m = 0; m < 4; m++) {
       const int64_t t = t4 + m;
-      const bool valid = live && t >= base && t < end;
-      const int32_t prio = prio_[m], nd = nd_[m], gid = gid_[m], vid = vid_[m];
+      const bool valid = live & (t >= base) & (t < end);
+      const int32_t prio = prio_[m], nd = nd_[m], gid = gid_[m];
       const uint32_t fl = fl_[m];
       const int64_t exp_ns = ex_[m], qb = qb_[m], wb = wb_[m];
-      bool scores = false, complex_task = false, own_complex = false;
-      if (valid) {
-        const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
-        const bool counted = !incl || dm;
-        const bool over = counted && exp_ns > threshold;
-        const bool wait_over = counted && dm && (sane_clock ? wb < wait_cutoff : since(now, wb) > threshold);
-        const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
-        const bool ung = gid < 0;
-        c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += (fl & EVG_TF_OTHER_DISTRO) != 0;
-        if (counted) s_exp += exp_ns;
-        if (over) s_over += exp_ns;
-        if (ung) {
-          c_ung += 1; c_ucnt += counted; c_uover += over; c_uwait += wait_over; c_umq += mq_dm;
-          if (counted) s_uexp += exp_ns;
-          if (over) s_uover += exp_ns;
-        } else {
-          evg_group_info* g = W.ginfo + D.group_off[d] + gid;
-          atomic_add64(&g->count, counted);
-          atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
-          atomic_add64(&g->count_duration_over_threshold, over);
-          atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
-          atomic_add64(&g->count_wait_over_threshold, wait_over);
-          atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
-        }
-        if (dcomplex) {
-          own_complex = gid >= 0 || gv || ((hd4 >> (8 * m)) & 0xFFu) != 0;
-          const uint32_t li = uint32_t(t - base);
-          const uint32_t s_own = own_slot_local(gid, vid, li, ng, gv);
-          const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
-          if (own_complex) link_pair(W, uint32_t(t), ub + s_own);
-          if (s_ver != kInactive) link_pair(W, uint32_t(T.n + t), ub + s_ver);  // planner.go:439
-          bool has_edges = false;
-          if (T.n_edges > 0) {
-            const int64_t e0 = doff[m], e1 = doff[m + 1];
-            has_edges = e1 > e0;
-            for (int64_t e = e0; e < e1; e++) {
-              const uint32_t dl = uint32_t(T.dep_idx[e]);
-              const uint32_t sl = own_slot_local(T.gid[base + dl], T.vid[base + dl], dl, ng, gv);
-              bool dup = (sl == s_own) || (sl == s_ver);  // Unit.Add is keyed by task id (planner.go:131): join each unit once
-              for (int64_t f = e0; f < e && !dup; f++) {
-                const uint32_t fl2 = uint32_t(T.dep_idx[f]);
-                dup = own_slot_local(T.gid[base + fl2], T.vid[base + fl2], fl2, ng, gv) == sl;
-              }
-              W.edge_task[e] = uint32_t(t);
-              if (!dup) link_pair(W, uint32_t(2 * T.n + e), ub + sl);
-            }
-          }
-          complex_task = own_complex || has_edges;
-        }
-        scores = !own_complex;  // the unit filed under this task's own key is {this task}
-      }
+      // straight-line (bitwise bool operators, selects): the short-circuit forms cost a branch per operator
+      const bool dm = valid & ((fl & EVG_TF_DEPS_MET) != 0);
+      const bool counted = valid & (!incl | dm);
+      const bool over = counted & (exp_ns > threshold);
+      const bool waited = sane_clock ? (wb < wait_cutoff) : (since(now, wb) > threshold);  // sane_clock is block-uniform
+      const bool wait_over = counted & dm & waited;
+      const bool mq_dm = dm & ((fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE);
+      const bool ung = valid & (gid < 0);
+      c_dm += dm; c_mq += mq_dm; c_over += over; c_wait += wait_over; c_sec += valid & ((fl & EVG_TF_OTHER_DISTRO) != 0);
+      s_exp += counted ? exp_ns : 0;
+      s_over += over ? exp_ns : 0;
+      c_ung += ung; c_ucnt += ung & counted; c_uover += ung & over; c_uwait += ung & wait_over; c_umq += ung & mq_dm;
+      s_uexp += (ung & counted) ? exp_ns : 0;
+      s_uover += (ung & over) ? exp_ns : 0;
+      // membership links, dependency edges and the TaskGroupInfo sums of multi-member-unit tasks are k_glink's job:
+      // pointer chasing with a few active lanes per warp would stall this streaming pass
+      const bool own_complex = valid & dcomplex & ((gid >= 0) | gv | (((hd4 >> (8 * m)) & 0xFFu) != 0));
+      const bool complex_task = own_complex | (valid & dcomplex & (doff[m + 1] > doff[m]));
+      const bool scores = valid & !own_complex;  // the unit filed under this task's own key is {this task}
       uint64_t v = 0;
       const uint32_t ndc = uint32_t(nd > 0 ? nd : 0);
-      const uint32_t nd_term = ndc < uint32_t(kNdTable) ? s_nd[ndc] : ((f32.ok && ndc < kTask32Limit) ? f32.nd * ndc : 0xFFFFFFFFu);
-      if (f32.ok_base && __all_sync(full, !scores || (nd_term != 0xFFFFFFFFu && score32_domain_nd(now, prio, exp_ns, qb)))) {
+      const uint32_t tab = s_nd[ndc < uint32_t(kNdTable) ? ndc : 0u];
+      const uint32_t mul = (f32.ok & (ndc < kTask32Limit)) ? f32.nd * ndc : 0xFFFFFFFFu;
+      const uint32_t nd_term = ndc < uint32_t(kNdTable) ? tab : mul;
+      const bool q_ok = (qb == EVG_TIME_ZERO) | ((qb >= 0) & (uint64_t(now - qb) < kFastLimit));
+      const bool in_dom = q_ok & (uint64_t(exp_ns) < kFastLimit) & (prio < int32_t(kTask32Limit)) & (nd_term != 0xFFFFFFFFu);
+      if (f32.ok_base && __all_sync(full, !scores | in_dom)) {
         v = single_task_value32_nd(f32, now, prio, exp_ns, qb, nd_term, fl);
       } else if (fast_clock && __all_sync(full, !scores || score_fast_domain(now, exp_ns, qb))) {
         v = uint64_t(single_task_value_fast(pf, now, prio, exp_ns, qb, nd, fl));
@@ -235,7 +206,11 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
           unsigned int pos0 = 0;
           if (lane == 0) pos0 = atomicAdd(G.ccount, (unsigned int)__popc(mm));
           pos0 = __shfl_sync(full, pos0, 0);
-          if (complex_task) G.clist[pos0 + __popc(mm & ((1u << lane) - 1u))] = uint32_t(t);
+          if (complex_task) {
+            const unsigned int pos = pos0 + __popc(mm & ((1u << lane) - 1u));
+            G.clist[pos] = uint32_t(t);
+            G.clist_d[pos] = d;
+          }
         }
       }
     }
@@ -303,6 +278,60 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
   }
 }
 
+// Per work-list task: TaskGroupInfo sums of task-group tasks (scheduler.go:79-137), unit membership links
+// (planner.go:431-447) and the links of its in-queue dependencies (planner.go:449-456).  One thread per task, many
+// in flight: every step is a dependent L2 access.
+__global__ void __launch_bounds__(256, 4) k_glink(DTasks T, DDistros D, DWork W, DGen G, int64_t now) {
+  if (*W.err) return;
+  const unsigned int n = *G.ccount;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t t = G.clist[k];
+    const int d = G.clist_d[k];
+    const int64_t base = D.task_off[d];
+    const int32_t gid = T.gid[t], vid = T.vid[t];
+    const uint32_t ng = uint32_t(D.group_off[d + 1] - D.group_off[d]);
+    const uint32_t ub = uint32_t(D.unit_base[d]);
+    const evg_distro_cfg* cf = D.cfg + d;
+    const bool gv = cf->group_versions != 0;
+    if (gid >= 0) {
+      const uint32_t fl = T.flags[t];
+      const int64_t exp_ns = T.expected[t], threshold = cf->target_time_ns;
+      const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
+      const bool counted = !cf->includes_dependencies || dm;
+      const bool over = counted && exp_ns > threshold;
+      const bool wait_over = counted && dm && since(now, T.wbasis[t]) > threshold;
+      const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
+      evg_group_info* g = W.ginfo + D.group_off[d] + gid;
+      atomic_add64(&g->count, counted);
+      atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
+      atomic_add64(&g->count_duration_over_threshold, over);
+      atomic_add64(&g->duration_over_threshold, over ? exp_ns : 0);
+      atomic_add64(&g->count_wait_over_threshold, wait_over);
+      atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
+    }
+    const uint32_t li = uint32_t(int64_t(t) - base);
+    const bool own_complex = gid >= 0 || gv || (W.has_dep[t] & 1) != 0;
+    const uint32_t s_own = own_slot_local(gid, vid, li, ng, gv);
+    const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
+    if (own_complex) link_pair(W, t, ub + s_own);
+    if (s_ver != kInactive) link_pair(W, uint32_t(T.n + t), ub + s_ver);  // planner.go:439
+    if (T.n_edges > 0) {
+      const int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
+      for (int64_t e = e0; e < e1; e++) {
+        const uint32_t dl = uint32_t(T.dep_idx[e]);
+        const uint32_t sl = own_slot_local(T.gid[base + dl], T.vid[base + dl], dl, ng, gv);
+        bool dup = (sl == s_own) || (sl == s_ver);  // Unit.Add is keyed by task id (planner.go:131): join each unit once
+        for (int64_t f = e0; f < e && !dup; f++) {
+          const uint32_t fl2 = uint32_t(T.dep_idx[f]);
+          dup = own_slot_local(T.gid[base + fl2], T.vid[base + fl2], fl2, ng, gv) == sl;
+        }
+        W.edge_task[e] = t;
+        if (!dup) link_pair(W, uint32_t(2 * T.n + e), ub + sl);
+      }
+    }
+  }
+}
+
 // Multi-member units, in two passes over the work list (one thread per task, grid-stride):
 //   k_gunit   the pair at the HEAD of a unit's member list owns the unit: one walk for Unit.info (planner.go:302-337),
 //             its value (planner.go:209-300), its anchor and its member count
@@ -313,13 +342,12 @@ __global__ void __launch_bounds__(256, 4) k_gunit(DTasks T, DDistros D, DWork W,
   const unsigned int n = *G.ccount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {  // the host cannot know n: fixed grid
     const uint32_t t = G.clist[k];
-    int d = -1;
-    int64_t base = 0;
+    const int d = G.clist_d[k];
+    const int64_t base = D.task_off[d];
     auto head_of = [&](uint32_t p) {
       if (W.next[p] == kInactive) return;  // not linked
       const uint32_t slot = W.pair_slot[p];
       if (W.head[slot] != p) return;       // some other member owns the unit
-      if (d < 0) { d = find_distro(D.task_off, 0, D.n - 1, int64_t(t)); base = D.task_off[d]; }
       UnitAcc a;
       acc_init(a);
       uint32_t anchor = kNoAnchor;
@@ -344,7 +372,7 @@ __global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W,
   const unsigned int n = *G.ccount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const uint32_t t = G.clist[k];
-    const int d = find_distro(D.task_off, 0, D.n - 1, int64_t(t));
+    const int d = G.clist_d[k];
     const int64_t base = D.task_off[d];
     const uint32_t li = uint32_t(int64_t(t) - base);
     bool have = false;
@@ -549,7 +577,7 @@ __global__ void __launch_bounds__(256) k_gplace_disp(DTasks T, DDistros D, DWork
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
   const uint32_t t = G.clist[k];
   if (!(W.has_dep[t] & 2)) continue;
-  const int d = find_distro(D.task_off, 0, D.n - 1, int64_t(t));
+  const int d = G.clist_d[k];
   const int64_t base = D.task_off[d];
   const uint32_t a = G.tie_a[t], myrk = G.tie_r[t];
   uint32_t pos = G.e[base + a];

@@ -898,7 +898,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
     CK(c->b_tilehist.ensure(sizeof(uint32_t) * 256 * size_t(NT + 1)));
     if (general_complex) {
       CK(c->b_e.ensure(sizeof(uint32_t) * size_t(T + kColPad)));
-      CK(c->b_clist.ensure(sizeof(uint32_t) * size_t(Tgc + 1)));
+      CK(c->b_clist.ensure(sizeof(uint32_t) * 2 * size_t(Tgc + 1)));
       CK(c->b_ca.ensure(sizeof(uint32_t) * size_t(T + 1)));
       CK(c->b_crk.ensure(sizeof(uint32_t) * size_t(T + 1)));
     }
@@ -1019,6 +1019,7 @@ DGen dgen(const evg_ctx* c) {
   }
   g.e = c->b_e.as<uint32_t>(); g.tile_sum = c->b_tilesum.as<uint32_t>(); g.tile_hist = c->b_tilehist.as<uint32_t>();
   g.clist = c->b_clist.as<uint32_t>();
+  g.clist_d = c->b_clist.as<int32_t>() + (c->Tgc + 1);
   g.ccount = c->b_gmisc.as<unsigned int>();
   g.maxpass = c->b_gmisc.as<int32_t>() + 1;
   g.tie_a = c->b_ca.as<uint32_t>(); g.tie_r = c->b_crk.as<uint32_t>();
@@ -1125,6 +1126,7 @@ int run_general(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& d
   if (c->timed) { CK(cudaEventRecord(c->ev_gt1, st)); c->general_timed = true; }
   const unsigned wl_grid = unsigned(std::min<int64_t>(std::max<int64_t>(1, (c->Tgc + 255) / 256), 148 * 16));
   if (gc) {
+    LAUNCH_ON(c, st, k_glink, wl_grid, 256, dt, dd, w, g, now);
     LAUNCH_ON(c, st, k_gunit, wl_grid, 256, dt, dd, w, g, now);
     LAUNCH_ON(c, st, k_gbest, wl_grid, 256, dt, dd, w, g);
   }
