@@ -27,6 +27,7 @@ constexpr int kGTile = 2048;  // tasks per tile; tiles start at multiples of 4 t
 struct DGen {
   // tiles of the general-path distros, in distro order
   int64_t n_tiles;
+  int64_t tile0;               // first tile this launch covers (a chunk of the pipelined one-shot call); grids are relative to it
   const int32_t* tile_distro;  // [NT]
   const int64_t* tile_start;   // [NT] first task slot of the tile: (base & ~3) + k*kGTile, may precede the distro by <= 3
   const int64_t* dtile_off;    // [D+1]
@@ -64,7 +65,7 @@ __global__ void k_ginit(DGen G, const int32_t* __restrict__ general_list, int n)
 // planner.go:449-456 (pass 2): mark every task some in-queue task depends on (general-path distros only).
 __global__ void __launch_bounds__(256) k_gmark(DTasks T, DDistros D, DWork W, DGen G) {
   if (*W.err) return;
-  const int tile = blockIdx.x;
+  const int tile = int(blockIdx.x + G.tile0);
   const int d = G.tile_distro[tile];
   const int64_t base = D.task_off[d], end = D.task_off[d + 1];
   const int64_t lo = max(G.tile_start[tile], base), hi = min(G.tile_start[tile] + kGTile, end);
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
   __shared__ TileFold F;
   __shared__ evg_distro_cfg s_cfg;
   __shared__ uint32_t s_nd[kNdTable];  // int64(NumDependentsFactor * n), n < kNdTable: fractional factors stay on the 32-bit scorer
-  const int tile = blockIdx.x;
+  const int tile = int(blockIdx.x + G.tile0);
   const int d = G.tile_distro[tile];
   const int tid = threadIdx.x, lane = tid & 31;
   const unsigned full = 0xffffffffu;
@@ -426,7 +427,7 @@ __global__ void k_gsched(DGen G, const int32_t* __restrict__ general_list, int n
 
 // sum of e[] over each tile
 __global__ void __launch_bounds__(256) k_gsum(DDistros D, DGen G) {
-  const int tile = blockIdx.x;
+  const int tile = int(blockIdx.x + G.tile0);
   const int d = G.tile_distro[tile];
   const int64_t base = D.task_off[d], end = D.task_off[d + 1];
   const int64_t lo = max(G.tile_start[tile], base), hi = min(G.tile_start[tile] + kGTile, end);
@@ -484,7 +485,7 @@ __device__ __forceinline__ void gen_put(const DGen& G, int64_t base, uint32_t po
 // every anchor; tasks that keep their own anchor with rank 0 are written to their sort position.  use_e == 0 (no
 // multi-member unit in any general-path distro): positions are the input order.
 __global__ void __launch_bounds__(256) k_gplace(DDistros D, DWork W, DGen G, int use_e) {
-  const int tile = blockIdx.x;
+  const int tile = int(blockIdx.x + G.tile0);
   const int d = G.tile_distro[tile];
   const int64_t base = D.task_off[d], end = D.task_off[d + 1];
   const int64_t ts = G.tile_start[tile];
@@ -608,7 +609,8 @@ __device__ __forceinline__ bool gen_tile(const DDistros& D, const DGen& G, int t
 __global__ void __launch_bounds__(256) k_ghist(int j, DDistros D, DGen G) {
   if (j >= *G.maxpass) return;
   int d, cnt; int64_t seg, lo; bool wide;
-  if (!gen_tile(D, G, blockIdx.x, j, &d, &seg, &lo, &cnt, &wide)) return;
+  const int tile = int(blockIdx.x + G.tile0);
+  if (!gen_tile(D, G, tile, j, &d, &seg, &lo, &cnt, &wide)) return;
   const uint32_t* src = (j < 4 ? G.key_lo[j & 1] : G.key_hi[j & 1]) + lo;
   const int shift = 8 * (j & 3);
   __shared__ uint32_t h[256];
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(256) k_ghist(int j, DDistros D, DGen G) {
   __syncthreads();
   for (int i = threadIdx.x; i < cnt; i += 256) atomicAdd(&h[(src[i] >> shift) & 255u], 1u);
   __syncthreads();
-  G.tile_hist[int64_t(blockIdx.x) * 256 + threadIdx.x] = h[threadIdx.x];
+  G.tile_hist[int64_t(tile) * 256 + threadIdx.x] = h[threadIdx.x];
 }
 
 // Offsets of every (tile, digit) counter of one distro: exclusive over the tiles of a digit, then over the digits
@@ -670,7 +672,8 @@ __global__ void __launch_bounds__(1024) k_gdscan(int j, const int32_t* __restric
 __global__ void __launch_bounds__(256) k_gscatter(int j, DDistros D, DGen G) {
   if (j >= *G.maxpass) return;
   int d, cnt; int64_t seg, lo; bool wide;
-  if (!gen_tile(D, G, blockIdx.x, j, &d, &seg, &lo, &cnt, &wide)) return;
+  const int tile = int(blockIdx.x + G.tile0);
+  if (!gen_tile(D, G, tile, j, &d, &seg, &lo, &cnt, &wide)) return;
   const int sb = j & 1, db = sb ^ 1;
   constexpr int kChunks = kGTile / 32;
   __shared__ uint16_t ch[kChunks][256];
@@ -707,7 +710,7 @@ __global__ void __launch_bounds__(256) k_gscatter(int j, DDistros D, DGen G) {
   for (int k = 0; k < 8; k++) {
     if (dg[k] < 256u) {
       const int c = warp * 8 + k;
-      const int64_t pos = seg + G.tile_hist[int64_t(blockIdx.x) * 256 + dg[k]] + ch[c][dg[k]] + rk[k];
+      const int64_t pos = seg + G.tile_hist[int64_t(tile) * 256 + dg[k]] + ch[c][dg[k]] + rk[k];
       G.key_lo[db][pos] = kl[k];
       if (wide) G.key_hi[db][pos] = kh[k];
       G.idx[db][pos] = ix[k];
@@ -717,7 +720,7 @@ __global__ void __launch_bounds__(256) k_gscatter(int j, DDistros D, DGen G) {
 
 // Ranked queue out: order[] and TotalValue per rank (planner.go:467-477).
 __global__ void __launch_bounds__(256) k_gemit(DDistros D, DGen G, int32_t* __restrict__ order, int64_t* __restrict__ total_value) {
-  const int tile = blockIdx.x;
+  const int tile = int(blockIdx.x + G.tile0);
   const int d = G.tile_distro[tile];
   const int64_t base = D.task_off[d], end = D.task_off[d + 1];
   const int64_t lo = max(G.tile_start[tile], base), hi = min(G.tile_start[tile] + kGTile, end);

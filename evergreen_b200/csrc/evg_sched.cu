@@ -521,12 +521,13 @@ __global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W
 }
 
 // scheduler.go:144-158: scalars of DistroQueueInfo / TaskGroupInfo that are not sums.
-__global__ void k_finalize_info(DDistros D, DWork W, int64_t g_begin, int64_t g_end) {
+__global__ void k_finalize_info(DDistros D, DWork W, int32_t d_begin, int32_t d_end, int64_t g_begin, int64_t g_end) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < D.n && !W.route[i]) {  // on-chip planners write their rows whole (and may be doing so right now on another stream)
-    evg_queue_info* q = W.qinfo + i;
-    q->length = D.task_off[i + 1] - D.task_off[i];
-    q->max_duration_threshold = D.cfg[i].target_time_ns;
+  const int64_t di = d_begin + i;
+  if (di < d_end && !W.route[di]) {  // on-chip planners write their rows whole (and may be doing so right now on another stream)
+    evg_queue_info* q = W.qinfo + di;
+    q->length = D.task_off[di + 1] - D.task_off[di];
+    q->max_duration_threshold = D.cfg[di].target_time_ns;
     q->secondary_queue = q->secondary_queue != 0;
     q->has_ungrouped = q->has_ungrouped != 0;
   }
@@ -727,15 +728,13 @@ struct evg_ctx {
   DevBuf b_punt, b_puntcnt;
   int32_t nW = 0, nA = 0, nB = 0, nC = 0, nNA = 0, nNB = 0, nNC = 0, n_general = 0;  // distros per route
   std::vector<int32_t> h_listW, h_listA, h_listB, h_listC, h_listNA, h_listNB, h_listNC;  // host copies (ascending distro ids)
-  std::vector<int64_t> h_taskoff, h_groupoff;
+  std::vector<int64_t> h_taskoff, h_groupoff, h_unitbase, h_edgeoff, h_dtileoff;
+  std::vector<int32_t> h_listG;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   static constexpr int kMaxChunks = 16;
   cudaEvent_t ev_h[kMaxChunks] = {}, ev_c[kMaxChunks] = {};
   int general_complex = 0;
   int64_t Tgc = 0;  // tasks in general-path distros that can hold multi-member units (work-list capacity)
-  // index ranges spanned by the general-path distros (first to last): what the general path's memsets cover
-  int32_t gr_d0 = 0, gr_d1 = 0;
-  int64_t gr_t0 = 0, gr_t1 = 0, gr_u0 = 0, gr_u1 = 0, gr_g0 = 0, gr_g1 = 0, gr_e0 = 0, gr_e1 = 0;
   DevBuf b_kv, b_vmm, b_klo[2], b_khi[2], b_ix[2], b_e, b_tilesum, b_gmisc;
   DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist;
   DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
@@ -922,15 +921,6 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   c->nNA = int32_t(listNA.size()); c->nNB = int32_t(listNB.size()); c->nNC = int32_t(listNC.size());
   c->n_general = n_general;
   c->general_complex = general_complex;
-  if (n_general > 0) {
-    const int32_t d0 = listG.front(), d1 = listG.back() + 1;
-    c->gr_d0 = d0; c->gr_d1 = d1;
-    c->gr_t0 = dt->task_off[d0]; c->gr_t1 = dt->task_off[d1];
-    c->gr_u0 = unit_base[d0]; c->gr_u1 = unit_base[d1];
-    c->gr_g0 = dt->group_off[d0]; c->gr_g1 = dt->group_off[d1];
-    c->gr_e0 = E > 0 ? (edge_off ? edge_off[d0] : t->dep_off[c->gr_t0]) : 0;
-    c->gr_e1 = E > 0 ? (edge_off ? edge_off[d1] : t->dep_off[c->gr_t1]) : 0;
-  }
   CK(c->b_err.ensure(sizeof(int) * 4));
   CK(cudaMemsetAsync(c->b_err.p, 0, sizeof(int) * 4, s));
   c->h_listW.swap(listW);
@@ -938,6 +928,12 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   c->h_listNA.swap(listNA); c->h_listNB.swap(listNB); c->h_listNC.swap(listNC);
   c->h_taskoff.assign(dt->task_off, dt->task_off + D + 1);
   c->h_groupoff.assign(dt->group_off, dt->group_off + D + 1);
+  c->h_edgeoff.assign(size_t(D) + 1, 0);
+  if (E > 0)
+    for (int32_t d = 0; d <= D; d++) c->h_edgeoff[size_t(d)] = edge_off ? edge_off[d] : t->dep_off[dt->task_off[d]];
+  c->h_unitbase.swap(unit_base);
+  c->h_dtileoff.swap(dtile_off);
+  c->h_listG.swap(listG);
   c->have_tasks = true;
   c->have_hosts = false;
   if ((copy_columns || adopt) && T > 0) {  // range-check the ids the kernels index with (the pipelined call checks chunk by chunk)
@@ -1011,6 +1007,7 @@ DWork dwork(const evg_ctx* c) {
 DGen dgen(const evg_ctx* c) {
   DGen g;
   g.n_tiles = c->NT;
+  g.tile0 = 0;
   g.tile_distro = c->b_tiledistro.as<int32_t>(); g.tile_start = c->b_tilestart.as<int64_t>();
   g.dtile_off = c->b_dtileoff.as<int64_t>();
   g.vmm = c->b_vmm.as<unsigned long long>();
@@ -1092,34 +1089,39 @@ int launch_tiny(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& d
   return EVG_OK;
 }
 
-// Everything the general path accumulates into or links through starts from zero / "empty".  Runs on the context
-// stream BEFORE the routes fork: the ranges span from the first to the last general-path distro, and an on-chip
-// distro in between rewrites its own rows afterwards.
-int prepare_general(evg_ctx* c, cudaStream_t s) {
+// Everything the general path accumulates into or links through starts from zero / "empty", for the distros
+// [d0, d1) (first to last general-path distro of the tick, or of one chunk of the pipelined call).  On the resident
+// path this runs on the context stream BEFORE the routes fork: an on-chip distro inside the span rewrites its own rows
+// afterwards.
+int prepare_general(evg_ctx* c, cudaStream_t s, int32_t d0, int32_t d1) {
   const int64_t T = c->T;
-  CK(cudaMemsetAsync(c->b_qinfo.as<evg_queue_info>() + c->gr_d0, 0, sizeof(evg_queue_info) * size_t(c->gr_d1 - c->gr_d0), s));
-  if (c->gr_g1 > c->gr_g0) CK(cudaMemsetAsync(c->b_ginfo.as<evg_group_info>() + c->gr_g0, 0, sizeof(evg_group_info) * size_t(c->gr_g1 - c->gr_g0), s));
+  const int64_t t0 = c->h_taskoff[d0], t1 = c->h_taskoff[d1], u0 = c->h_unitbase[d0], u1 = c->h_unitbase[d1];
+  const int64_t g0 = c->h_groupoff[d0], g1 = c->h_groupoff[d1], e0 = c->h_edgeoff[d0], e1 = c->h_edgeoff[d1];
+  CK(cudaMemsetAsync(c->b_qinfo.as<evg_queue_info>() + d0, 0, sizeof(evg_queue_info) * size_t(d1 - d0), s));
+  if (g1 > g0) CK(cudaMemsetAsync(c->b_ginfo.as<evg_group_info>() + g0, 0, sizeof(evg_group_info) * size_t(g1 - g0), s));
   if (c->general_complex) {
-    const size_t nt = size_t(c->gr_t1 - c->gr_t0);
-    CK(cudaMemsetAsync(c->b_hasdep.as<uint8_t>() + c->gr_t0, 0, nt, s));
-    CK(cudaMemsetAsync(c->b_head.as<uint32_t>() + c->gr_u0, 0xFF, sizeof(uint32_t) * size_t(c->gr_u1 - c->gr_u0), s));
-    CK(cudaMemsetAsync(c->b_unitmask.as<uint64_t>() + c->gr_u0, 0, sizeof(uint64_t) * size_t(c->gr_u1 - c->gr_u0), s));
-    CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + c->gr_t0, 0xFF, sizeof(uint32_t) * nt, s));          // own-key pairs
-    CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + T + c->gr_t0, 0xFF, sizeof(uint32_t) * nt, s));      // version pairs
-    if (c->gr_e1 > c->gr_e0)
-      CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + 2 * T + c->gr_e0, 0xFF, sizeof(uint32_t) * size_t(c->gr_e1 - c->gr_e0), s));  // edge pairs
+    const size_t nt = size_t(t1 - t0);
+    CK(cudaMemsetAsync(c->b_hasdep.as<uint8_t>() + t0, 0, nt, s));
+    CK(cudaMemsetAsync(c->b_head.as<uint32_t>() + u0, 0xFF, sizeof(uint32_t) * size_t(u1 - u0), s));
+    CK(cudaMemsetAsync(c->b_unitmask.as<uint64_t>() + u0, 0, sizeof(uint64_t) * size_t(u1 - u0), s));
+    CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + t0, 0xFF, sizeof(uint32_t) * nt, s));          // own-key pairs
+    CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + T + t0, 0xFF, sizeof(uint32_t) * nt, s));      // version pairs
+    if (e1 > e0) CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + 2 * T + e0, 0xFF, sizeof(uint32_t) * size_t(e1 - e0), s));  // edge pairs
   }
   return EVG_OK;
 }
 
-// The general path of one tick on stream `st` (evg_plan_general.cuh).
-int run_general(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& dd, const DWork& w, int64_t now) {
-  const int32_t D = c->Dn;
-  const DGen g = dgen(c);
+// The general path on stream `st` for the general-path distros listG[gfirst .. gfirst + gcount) (evg_plan_general.cuh).
+int run_general(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& dd, const DWork& w, int64_t now, int32_t gfirst,
+                int32_t gcount) {
+  if (gcount <= 0) return EVG_OK;
+  DGen g = dgen(c);
   const int gc = c->general_complex;
-  const unsigned nt = unsigned(c->NT);
-  const int32_t* gl = c->b_listG.as<int32_t>();
-  LAUNCH_ON(c, st, k_ginit, grid_for(c->n_general, 256), 256, g, gl, c->n_general);
+  const int32_t d_first = c->h_listG[size_t(gfirst)], d_last = c->h_listG[size_t(gfirst + gcount - 1)];
+  g.tile0 = c->h_dtileoff[size_t(d_first)];
+  const unsigned nt = unsigned(c->h_dtileoff[size_t(d_last) + 1] - g.tile0);
+  const int32_t* gl = c->b_listG.as<int32_t>() + gfirst;
+  LAUNCH_ON(c, st, k_ginit, grid_for(gcount, 256), 256, g, gl, gcount);
   if (gc && c->E > 0) LAUNCH_ON(c, st, k_gmark, nt, 256, dt, dd, w, g);
   if (c->timed) CK(cudaEventRecord(c->ev_gt0, st));
   LAUNCH_ON(c, st, k_gtask, nt, 256, dt, dd, w, g, now, gc);
@@ -1130,22 +1132,23 @@ int run_general(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& d
     LAUNCH_ON(c, st, k_gunit, wl_grid, 256, dt, dd, w, g, now);
     LAUNCH_ON(c, st, k_gbest, wl_grid, 256, dt, dd, w, g);
   }
-  LAUNCH_ON(c, st, k_gsched, grid_for(c->n_general, 128), 128, g, gl, c->n_general);
+  LAUNCH_ON(c, st, k_gsched, grid_for(gcount, 128), 128, g, gl, gcount);
   if (gc) {
     LAUNCH_ON(c, st, k_gsum, nt, 256, dd, g);
-    LAUNCH_ON(c, st, k_gscan, unsigned(c->n_general), 1024, g, gl);
+    LAUNCH_ON(c, st, k_gscan, unsigned(gcount), 1024, g, gl);
   }
   LAUNCH_ON(c, st, k_gplace, nt, 256, dd, w, g, gc);
   if (gc) LAUNCH_ON(c, st, k_gplace_disp, wl_grid, 256, dt, dd, w, g);
   if (c->timed) CK(cudaEventRecord(c->ev_sort0, st));  // the general path's segmented sort
   for (int j = 0; j < 8; j++) {  // passes beyond the tick's longest key exit at once (*maxpass is device-side)
     LAUNCH_ON(c, st, k_ghist, nt, 256, j, dd, g);
-    LAUNCH_ON(c, st, k_gdscan, unsigned(c->n_general), 1024, j, gl, g);
+    LAUNCH_ON(c, st, k_gdscan, unsigned(gcount), 1024, j, gl, g);
     LAUNCH_ON(c, st, k_gscatter, nt, 256, j, dd, g);
   }
   if (c->timed) CK(cudaEventRecord(c->ev_sort1, st));
   LAUNCH_ON(c, st, k_gemit, nt, 256, dd, g, c->b_order.as<int32_t>(), c->b_tv.as<int64_t>());
-  LAUNCH_ON(c, st, k_finalize_info, grid_for(std::max<int64_t>(D, c->gr_g1 - c->gr_g0), 256), 256, dd, w, c->gr_g0, c->gr_g1);
+  const int64_t g0 = c->h_groupoff[size_t(d_first)], g1 = c->h_groupoff[size_t(d_last) + 1];
+  LAUNCH_ON(c, st, k_finalize_info, grid_for(std::max<int64_t>(d_last + 1 - d_first, g1 - g0), 256), 256, dd, w, d_first, d_last + 1, g0, g1);
   return EVG_OK;
 }
 
@@ -1183,7 +1186,7 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
   if (bd && c->any_complex) CK(cudaMemsetAsync(c->b_bestpair.p, 0xFF, sizeof(uint32_t) * size_t(T + 1), s));
   const int32_t n_new = bd ? 0 : c->nNA + c->nNB + c->nNC;
   if (n_new > 0) CK(cudaMemsetAsync(c->b_puntcnt.p, 0, sizeof(int32_t), s));
-  if (general) { int rcg = prepare_general(c, s); if (rcg != EVG_OK) return rcg; }
+  if (general) { int rcg = prepare_general(c, s, c->h_listG.front(), c->h_listG.back() + 1); if (rcg != EVG_OK) return rcg; }
   // Routes run side by side when the tick has more than one: fork the aux streams off the context stream here, join
   // them before returning (the allocator and the caller's later work are ordered behind every planner kernel).
   struct Route { int id; int64_t weight; };
@@ -1227,7 +1230,7 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
   // --- stream 4: one warp per tiny distro
   if ((rc = launch_tiny(c, st(4), dt, dd, w, c->b_listW.as<int32_t>(), c->nW, now, bd ? 1 : 0)) != EVG_OK) return rc;
   // --- stream 5: the general path
-  if (general && (rc = run_general(c, st(5), dt, dd, w, now)) != EVG_OK) return rc;
+  if (general && (rc = run_general(c, st(5), dt, dd, w, now, 0, c->n_general)) != EVG_OK) return rc;
   if (fork) {
     for (int k = 0; k < evg_ctx::kAux; k++) {
       CK(cudaEventRecord(c->ev_join[k], c->s_aux[k]));
@@ -1501,7 +1504,8 @@ int evg_plan_batch(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table
 
 // The one-shot call as a three-stage pipeline over chunks of whole distros: H2D of chunk k+1, kernels of chunk k
 // and D2H of chunk k-1 overlap on three streams, so the tick costs about max(H2D, D2H) instead of their sum.
-// Used when every distro is planned on-chip (no general-path distro) and no breakdown is requested.
+// Used for ticks of at least 2^21 tasks when no breakdown is requested; a chunk's general-path distros run through the
+// general path restricted to their tiles.
 static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, const evg_host_soa* hosts,
                                     const int64_t* host_off, const evg_alloc_cfg* acfg, int64_t now, evg_plan_out* po,
                                     evg_alloc_out* ao) {
@@ -1580,6 +1584,11 @@ static int plan_and_alloc_pipelined(evg_ctx* c, const evg_task_soa* t, const evg
       if ((rc = launch_cta<kNT_A, kNCapA, kNOccA>(c, s, dtk, dd, w, c->b_listNA.as<int32_t>() + fA, nA, now, pl, pc)) != EVG_OK) return rc;
       if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, s, dtk, dd, w, pl, nC + nB + nA, now, 0, pc)) != EVG_OK) return rc;
     }
+    cnt = sub(c->h_listG, d0, d1, &first);
+    if (cnt > 0) {  // the chunk's general-path distros: same kernels, restricted to their tiles
+      if ((rc = prepare_general(c, s, c->h_listG[size_t(first)], c->h_listG[size_t(first + cnt - 1)] + 1)) != EVG_OK) return rc;
+      if ((rc = run_general(c, s, dtk, dd, w, now, first, cnt)) != EVG_OK) return rc;
+    }
     cnt = sub(c->h_listC, d0, d1, &first);
     if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, s, dtk, dd, w, c->b_listC.as<int32_t>() + first, cnt, now)) != EVG_OK) return rc;
     cnt = sub(c->h_listB, d0, d1, &first);
@@ -1625,12 +1634,10 @@ int evg_plan_and_alloc_batch(evg_ctx* c, const evg_task_soa* tasks, const evg_di
     CK(cudaSetDevice(c->device));
     int rc0 = upload_tasks(c, tasks, distros, /*copy_columns=*/false);
     if (rc0 != EVG_OK) return rc0;
-    if (c->n_general == 0) {
-      rc0 = upload_hosts(c, hosts, host_off, acfg, distros->n_distros);
-      if (rc0 != EVG_OK) return rc0;
-      CK(cudaStreamSynchronize(c->stream));
-      return plan_and_alloc_pipelined(c, tasks, distros, hosts, host_off, acfg, now_ns, plan_out, alloc_out);
-    }
+    rc0 = upload_hosts(c, hosts, host_off, acfg, distros->n_distros);
+    if (rc0 != EVG_OK) return rc0;
+    CK(cudaStreamSynchronize(c->stream));
+    return plan_and_alloc_pipelined(c, tasks, distros, hosts, host_off, acfg, now_ns, plan_out, alloc_out);
   }
   int rc = evg_upload(c, tasks, distros, hosts, host_off, acfg);
   if (rc != EVG_OK) return rc;

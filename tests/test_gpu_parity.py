@@ -1025,3 +1025,21 @@ def test_device_side_dependency_wiring(engine):
     plan, info = S.PrioritizeTasks(batch[2][0], batch[2][1], now=NOWT, engine=engine, dependency_db=db)
     assert [t.dependencies_met_time for t in batch[2][1]] == [t.dependencies_met_time for t in host_side[2][1]]
     assert info.length_with_dependencies_met == int(po_h.info[2]["length_with_dependencies_met"])
+
+
+def test_pipelined_one_shot_with_general_path_distros(engine):
+    """The chunked one-shot call also carries general-path distros (each chunk runs the general path on its own
+    tiles): equal to upload -> run -> download, and to the oracle on a sample."""
+    sizes = np.array([60000, 900, 130000, 20, 250000, 13000, 5000, 400000, 70000, 33, 300000, 90000, 512, 450000, 200000, 180000])
+    w = synth.make(sizes, 240, zipf_priority=True, tg_frac=0.1, unmet_dep_frac=0.03, met_dep_frac=0.01, includes_dependencies=True,
+                   n_hosts=200, providers=(0.7, 0.2, 0.1))
+    assert w.n_tasks >= 2 ** 21
+    engine.upload(w.tasks, w.distros, w.hosts)
+    engine.run(w.now)
+    a_po, a_ao = copy.deepcopy(engine.download())
+    b_po, b_ao = engine.plan_and_alloc_batch(w.tasks, w.distros, w.hosts, w.now)
+    for f in ("order", "total_value", "info", "group_info"):
+        assert np.array_equal(getattr(a_po, f), getattr(b_po, f)), f
+    assert np.array_equal(a_ao.result, b_ao.result) and np.array_equal(a_ao.status, b_ao.status)
+    parity.check_properties(w, b_po, b_ao)
+    parity.check_against_oracle(w, b_po, b_ao, distros=[0, 1, 2, 3, 5, 8, 9], threads=16)
