@@ -75,6 +75,9 @@ class ResultGather:
         self.send = torch.zeros(max(self.pad, 1), dtype=torch.uint8, device=device)[:self.pad]
         self.gathered = torch.empty(shards.world * self.pad, dtype=torch.uint8, device=device)
         self.index = torch.as_tensor(shards.owner * shards.max_shard + shards.slot, device=device)
+        # the reordered result lives in a buffer of this slot, not in a fresh allocation per tick: a block freed back to
+        # the communication stream's pool could be rewritten by the next gather while another stream still reads it
+        self.result = torch.empty((int(self.index.shape[0]), RESULT_BYTES), dtype=torch.uint8, device=device)
 
     def gather(self):
         import torch.distributed as dist
@@ -83,7 +86,9 @@ class ResultGather:
             rows = self.gathered.view(self.shards.world * self.shards.max_shard, RESULT_BYTES)
         else:
             rows = self.send.view(self.shards.max_shard, RESULT_BYTES)
-        return rows.index_select(0, self.index).reshape(-1)
+        import torch
+        torch.index_select(rows, 0, self.index, out=self.result)
+        return self.result.reshape(-1)
 
 
 class PipelinedGather:
@@ -111,7 +116,9 @@ class PipelinedGather:
         return self.slots[k % self.depth].send
 
     def before_tick(self, k: int, main) -> None:
-        """Tick k overwrites send(k): the gather that last read that buffer (tick k - depth) must be done."""
+        """Tick k overwrites send(k) and, later, result(k): the gather that last used that slot (tick k - depth) must
+        be done before `main` goes on, and whatever `main` has queued so far (readers of that slot's result) must be done
+        before the communication stream rewrites it."""
         d = self.done[k % self.depth]
         if self.cuda and d is not None:
             main.wait_event(d)
@@ -122,7 +129,7 @@ class PipelinedGather:
             self.out[i] = self.slots[i].gather()
             return
         torch = self.torch
-        self.ready[i].record(main)
+        self.ready[i].record(main)  # orders the gather behind tick k's kernels AND behind every earlier reader of slot i on `main`
         self.comm.wait_event(self.ready[i])
         with torch.cuda.stream(self.comm):
             self.out[i] = self.slots[i].gather()

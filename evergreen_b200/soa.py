@@ -261,6 +261,11 @@ def marshal_tasks(batch: Sequence[tuple], now: int, dependency_db: Optional[Dict
                     gid = groups[name] = len(groups)
                     md.group_names.append(name)
                     gmax.append(t.task_group_max_hosts)
+                elif gmax[group_off[-1] + gid] != t.task_group_max_hosts:
+                    # TaskGroupInfo.MaxHosts is the value of the group's first task in PLAN order (scheduler.go:87-90);
+                    # a per-group table can only carry one value, so members must agree (they do: it is a project setting)
+                    raise ValueError(f"task group {name!r}: TaskGroupMaxHosts differs between members "
+                                     f"({gmax[group_off[-1] + gid]} vs {t.task_group_max_hosts} on {t.id!r})")
             vid = versions.get(t.version)
             if vid is None:
                 vid = versions[t.version] = len(versions)
