@@ -29,7 +29,10 @@ def random_tasks(rng, n, n_ext=5):
                    dependencies_met_time=rng.choice([M.ZERO_TIME, M.ZERO_TIME, 0, NOW - rng.randrange(10 ** 12)]),
                    override_dependencies=rng.random() < 0.1)
         if rng.random() < 0.3:
-            t.task_group, t.task_group_max_hosts, t.task_group_order = f"tg{rng.randrange(2)}", rng.randrange(1, 4), rng.randrange(5)
+            g = rng.randrange(2)
+            # TaskGroupMaxHosts is a property of the group (per build variant / version): uniform inside one TaskGroupString
+            t.task_group, t.task_group_order = f"tg{g}", rng.randrange(5)
+            t.task_group_max_hosts = 1 + (g + int(t.version[1:]) + int(t.build_variant[2:])) % 3
         for _ in range(rng.choice([0, 0, 1, 2])):
             target = rng.choice([f"t{rng.randrange(n)}", f"ext{rng.randrange(n_ext)}", "missing"])
             t.depends_on.append(M.Dependency(target, status=rng.choice(["", "success", "failed", "*"]),
@@ -281,3 +284,14 @@ def test_out_of_range_priority_is_an_error_not_a_clamp():
             S.marshal_tasks([(d, [M.Task(id="t", priority=bad)])], NOW)
     soa, _, _ = S.marshal_tasks([(d, [M.Task(id="t", priority=2 ** 31 - 1), M.Task(id="u", priority=-2 ** 31)])], NOW)
     assert soa.priority.tolist() == [2 ** 31 - 1, -2 ** 31]
+
+
+def test_task_group_max_hosts_must_agree_inside_a_group():
+    d = M.Distro(id="d")
+    a = M.Task(id="a", task_group="g", task_group_max_hosts=2, version="v", build_variant="bv", project="p")
+    b = M.Task(id="b", task_group="g", task_group_max_hosts=3, version="v", build_variant="bv", project="p")
+    with pytest.raises(ValueError):
+        S.marshal_tasks([(d, [a, b])], NOW)
+    b.task_group_max_hosts = 2
+    _, table, _ = S.marshal_tasks([(d, [a, b])], NOW)
+    assert table.group_max_hosts.tolist() == [2]
