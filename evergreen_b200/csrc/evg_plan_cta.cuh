@@ -23,7 +23,7 @@
 //   idx   2*CAP            u16 permutation                 | task pass: TMA stage 0 (+ start of stage 1)
 //   cnt   W*2^bits*2       u16 per-warp digit counters     | task pass: TMA stage 1; group phases: per-group
 //                                                          |   accumulators (with idx); pre-arrangement: e[] histogram
-//   list  6*CAP/5          u16 work list: task, anchor, rank
+//   list  6*CAP/4          u16 work list: task, anchor, rank (one stretch per warp)
 //
 // Reference: scheduler/planner.go:209-481, scheduler/scheduler.go:56-159.
 #pragma once
@@ -39,6 +39,14 @@ struct CtaDigit {
 #ifndef EVG_CTA_TPT
 #define EVG_CTA_TPT 2
 #endif
+// Tiles whose columns are pulled into L2 (cp.async.bulk.prefetch.L2) ahead of the one being staged; 0 = none.
+#ifndef EVG_CTA_PF
+#define EVG_CTA_PF 0
+#endif
+// ns a waiter may sleep inside mbarrier.try_wait before it re-polls; 0 = the default (short) suspend
+#ifndef EVG_CTA_WAITHINT
+#define EVG_CTA_WAITHINT 0
+#endif
 
 template <int THREADS, int CAP>
 struct PlanCta {
@@ -49,7 +57,7 @@ struct PlanCta {
   static constexpr int kItems = CAP / THREADS;
   static constexpr int kDigitBits = CtaDigit<THREADS>::kBits;
   static constexpr int kDigitWords = (1 << kDigitBits) / 2;  // u32 words per warp row of u16 counters
-  static constexpr int kListCap = CAP / 5;
+  static constexpr int kListCap = CAP / 4;  // task-group tasks a distro may hold here (each warp owns 1/kWarps of it)
   static constexpr size_t kKeyBytes = size_t(4) * CAP;
   static constexpr size_t kIdxBytes = size_t(2) * CAP;
   static constexpr size_t kStageBytes = size_t(40) * kTile;
@@ -76,7 +84,7 @@ struct PlanCta {
 struct CtaShared {
   int64_t base;
   int32_t tn, ng, d, off0;
-  uint32_t n_list;
+  uint32_t spare;
   int32_t punt, n_displaced;
   uint32_t vmin, vmax;
   unsigned int c[6];
@@ -112,9 +120,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // the same on precomputed shared-window addresses: the task-pass loop issues them every tile
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+#if EVG_CTA_WAITHINT > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity),
+      "r"(uint32_t(EVG_CTA_WAITHINT))
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity)
       : "memory");
+#endif
+}
+__device__ __forceinline__ void l2_prefetch_1d(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 // one lane's shared-memory add with the old value back (inline PTX: the compiler does not wrap it in its own warp aggregation)
 __device__ __forceinline__ uint32_t atom_add_shared(uint32_t addr, uint32_t v) {
@@ -172,7 +190,7 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
     S->tn = int32_t(D.task_off[d + 1] - D.task_off[d]);
     S->ng = int32_t(D.group_off[d + 1] - D.group_off[d]);
     S->off0 = int32_t(S->base & 3);
-    S->n_list = 0; S->punt = 0; S->n_displaced = 0;
+    S->punt = 0; S->n_displaced = 0;
     S->vmin = 0xFFFFFFFFu; S->vmax = 0u;
     for (int k = 0; k < 6; k++) S->c[k] = 0;
     for (int k = 0; k < 2; k++) S->s[k] = 0;
@@ -212,6 +230,16 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
     tma_load_1d(st + 16 * TILE + 0 * TILE * 8, T.expected + start, cnt * 8u, bar);
     tma_load_1d(st + 16 * TILE + 1 * TILE * 8, T.qbasis + start, cnt * 8u, bar);
     tma_load_1d(st + 16 * TILE + 2 * TILE * 8, T.wbasis + start, cnt * 8u, bar);
+#if EVG_CTA_PF > 0
+    if (k + EVG_CTA_PF < n_tiles) {  // a later tile's columns start their trip from HBM to L2 now
+      const int64_t ps = start + int64_t(EVG_CTA_PF) * TILE;
+      const int64_t pl = t_pad - ps;
+      const uint32_t pc = uint32_t(pl < int64_t(TILE) ? pl : int64_t(TILE));
+      l2_prefetch_1d(T.priority + ps, pc * 4u); l2_prefetch_1d(T.numdep + ps, pc * 4u); l2_prefetch_1d(T.gid + ps, pc * 4u);
+      l2_prefetch_1d(T.flags + ps, pc * 4u); l2_prefetch_1d(T.expected + ps, pc * 8u); l2_prefetch_1d(T.qbasis + ps, pc * 8u);
+      l2_prefetch_1d(T.wbasis + ps, pc * 8u);
+    }
+#endif
   };
   if (tid == 0) { issue(0); if (NST > 1 && n_tiles > 1) issue(1); }
 
@@ -234,7 +262,14 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
   }
   __syncthreads();
 
-  const uint32_t a_full0 = smem_u32(&sBar[0]), a_empty0 = smem_u32(&sBar[2]), a_nlist = smem_u32(&S->n_list);
+  const uint32_t a_full0 = smem_u32(&sBar[0]), a_empty0 = smem_u32(&sBar[2]);
+  const uint32_t opaque_zero = uint32_t(t_pad) & 3u;  // 0 at run time, unknown at compile time
+  // Work list of task-group tasks: warp w owns entries [w*kSeg, (w+1)*kSeg) through every later phase.  Tile slots are dealt
+  // to warps 32 tasks at a time, so the stretches fill evenly; one that overflows hands the distro to k_plan_smem.
+  constexpr int kSeg = kListCap / NW;
+  const int wl0 = warp * kSeg;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned int wl_n = 0;
   const uint32_t* st32_0 = reinterpret_cast<const uint32_t*>(sStage) + tid;
   const int64_t* st64_0 = reinterpret_cast<const int64_t*>(sStage + 16 * TILE) + tid;
   for (int k = 0; k < n_tiles; k++) {
@@ -252,10 +287,22 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       gid[u] = int32_t(st32[2 * TILE + u * THREADS]); fl[u] = st32[3 * TILE + u * THREADS];
       exp_ns[u] = st64[0 * TILE + u * THREADS]; qb[u] = st64[1 * TILE + u * THREADS]; wb[u] = st64[2 * TILE + u * THREADS];
     }
-    // Every field is in registers (the arrive is a release: it is ordered behind the loads above): the slot is refilled
-    // while this tile is scored.
-    mbar_arrive_a(a_empty0 + 8u * s);
+    // Release the slot as soon as every field IS in registers, so that it refills while this tile is scored.  "Is" needs
+    // care: LDS completes asynchronously and neither program order nor the arrive's release semantics hold the arrive
+    // back until the loads have actually read shared memory (measured: about one warp per 10^4 CTAs scored the NEXT
+    // tile's bytes).  So the arrive's address is made data-dependent on every loaded register -- an AND with a zero the
+    // compiler cannot prove (t_pad is a multiple of four) -- which waits on the loads' scoreboard and nothing else.
+#ifndef EVG_CTA_LATE_ARRIVE
+    {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int u = 0; u < TPT; u++)
+        acc ^= uint32_t(prio[u]) ^ uint32_t(nd[u]) ^ uint32_t(gid[u]) ^ fl[u] ^ uint32_t(uint64_t(exp_ns[u])) ^ uint32_t(uint64_t(exp_ns[u]) >> 32) ^
+               uint32_t(uint64_t(qb[u])) ^ uint32_t(uint64_t(qb[u]) >> 32) ^ uint32_t(uint64_t(wb[u])) ^ uint32_t(uint64_t(wb[u]) >> 32);
+      mbar_arrive_a(a_empty0 + 8u * s + (acc & opaque_zero));
+    }
     if (tid == 0 && k + NST < n_tiles) { mbar_wait_a(a_empty0 + 8u * s, ph); issue(k + NST); }
+#endif
     int idx[TPT];
     bool complex_task[TPT], scores[TPT];
     uint32_t nd_term[TPT];
@@ -285,9 +332,8 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       const uint32_t tab = sNd[ndc < uint32_t(kNdTable) ? ndc : 0u];
       const uint32_t mul = (f32.ok & (ndc < kTask32Limit)) ? f32.nd * ndc : 0xFFFFFFFFu;
       nd_term[u] = ndc < uint32_t(kNdTable) ? tab : mul;
-      const bool q_ok = (qb[u] == EVG_TIME_ZERO) | ((qb[u] >= 0) & (uint64_t(now - qb[u]) < kFastLimit));
-      const bool in_dom = q_ok & (uint64_t(exp_ns[u]) < kFastLimit) & (prio[u] < int32_t(kTask32Limit)) & (nd_term[u] != 0xFFFFFFFFu);
-      dom = dom & (!scores[u] | in_dom);
+      const uint32_t bad = score32_bad(now, prio[u], exp_ns[u], qb[u], nd_term[u]);  // the 32-bit scorer's domain, branch-free
+      dom = dom & (!scores[u] | (bad == 0u));
     }
     uint64_t v[TPT];
     if (f32.ok_base && __all_sync(full, dom)) {
@@ -305,19 +351,17 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
         sKey[idx[u]] = v32;
         vmn = min(vmn, v32); vmx = max(vmx, v32);
       }
-      if (any) {  // warp-aggregated append to the work list
+      if (any) {  // the warp's own stretch of the work list: no atomic, the count stays in a (warp-uniform) register
         const unsigned m = __ballot_sync(full, complex_task[u]);
-        if (m) {
-          unsigned int pos0 = 0;
-          if (lane == 0) pos0 = atom_add_shared(a_nlist, (unsigned int)__popc(m));
-          pos0 = __shfl_sync(full, pos0, 0);
-          if (complex_task[u]) {
-            const unsigned int pos = pos0 + __popc(m & ((1u << lane) - 1u));
-            if (pos < (unsigned)kListCap) sList[pos] = uint16_t(idx[u]);
-          }
-        }
+        const unsigned int pos = wl_n + __popc(m & lt_mask);
+        if (complex_task[u] && pos < (unsigned)kSeg) sList[wl0 + pos] = uint16_t(idx[u]);
+        wl_n += __popc(m);
       }
     }
+#ifdef EVG_CTA_LATE_ARRIVE
+    mbar_arrive_a(a_empty0 + 8u * s);
+    if (tid == 0 && k + NST < n_tiles) { mbar_wait_a(a_empty0 + 8u * s, ph); issue(k + NST); }
+#endif
   }
   // fold the queue-info partials: warp shuffle, then shared atomics
   {
@@ -333,11 +377,10 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
 #pragma unroll
       for (int k = 0; k < 2; k++) if (ss[k]) atomicAdd(&S->s[k], (unsigned long long)ss[k]);
     }
-    if (__any_sync(full, punt) && lane == 0) S->punt = 1;
+    if ((__any_sync(full, punt) || wl_n > (unsigned)kSeg) && lane == 0) S->punt = 1;  // a value outside u32, or more task-group tasks than the warp's stretch holds
   }
   __syncthreads();
-  const int n_list = int(S->n_list);
-  if (n_list > kListCap && tid == 0) S->punt = 1;  // more task-group tasks than the work list holds
+  const int wl_cnt = int(wl_n);
 
   // ---- task groups: per-group accumulators in the (now idle) staging area ----
   unsigned long long* gTiq = reinterpret_cast<unsigned long long*>(smem_raw + L::kOffIdx);
@@ -413,10 +456,10 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       atomicMin(&gAnchor[gid], uint32_t(i));
       atomicOr(reinterpret_cast<unsigned int*>(&gMask[gid]) + (tgo >> 5), 1u << (tgo & 31));
     };
-    for (int k = tid; k < n_list; k += 2 * THREADS) {  // two members per trip: sixteen loads in flight
-      const bool two = k + THREADS < n_list;
-      const Member m0 = fetch(k);
-      const Member m1 = fetch(two ? k + THREADS : k);
+    for (int k = lane; k < wl_cnt; k += 64) {  // two members per trip: sixteen loads in flight
+      const bool two = k + 32 < wl_cnt;
+      const Member m0 = fetch(wl0 + k);
+      const Member m1 = fetch(wl0 + (two ? k + 32 : k));
       member(m0);
       if (two) member(m1);
     }
@@ -457,7 +500,8 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       return;
     }
     // ---- phase 4: a task-group task is emitted from its group's unit, ranked by its order ----
-    for (int k = tid; k < n_list; k += THREADS) {
+    for (int kk = lane; kk < wl_cnt; kk += 32) {
+      const int k = wl0 + kk;
       const int i = int(sList[k]);
       const uint32_t packed = sKey[i];
       const uint32_t gid = packed & 0xFFFFu;
@@ -522,7 +566,8 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       e32[j >> 1] = lo | (hi << 16);
     }
     __syncthreads();
-    for (int k = tid; k < n_list; k += THREADS) {
+    for (int kk = lane; kk < wl_cnt; kk += 32) {
+      const int k = wl0 + kk;
       const int i = int(sList[k]);
       if (!((sDisp[i >> 5] >> (i & 31)) & 1u)) continue;
       const uint32_t a = sLA[k];
@@ -562,7 +607,8 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
       run = p1 + loc[k + 1];
     }
     __syncthreads();
-    for (int k = tid; k < n_list; k += THREADS) {
+    for (int kk = lane; kk < wl_cnt; kk += 32) {
+      const int k = wl0 + kk;
       const int i = int(sList[k]);
       if (!((sDisp[i >> 5] >> (i & 31)) & 1u)) continue;
       // every member of a task-group unit is emitted from it, so the rank inside the unit is the offset in the run
@@ -587,7 +633,11 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
     const int seg = ((tn + NW - 1) / NW + 31) & ~31;
     const int seg0 = warp * seg;
     const int seg1 = min(seg0 + seg, tn);
+#ifdef EVG_CTA_NOFULL
+    const bool full_seg = false;
+#else
     const bool full_seg = seg1 - seg0 == ITEMS * 32;  // warp-uniform: every lane of every chunk holds an element
+#endif
     const unsigned lt = (1u << lane) - 1u;
     const int npass = (bits + MAXBITS - 1) / MAXBITS;
     const int wbase = npass ? bits / npass : 0, wrem = npass ? bits % npass : 0;

@@ -22,6 +22,9 @@
 // Reference: scheduler/planner.go:209-481, scheduler/scheduler.go:56-159.
 #pragma once
 
+#ifndef EVG_GTASK_OCC
+#define EVG_GTASK_OCC 3
+#endif
 constexpr int kGTile = 2048;  // tasks per tile; tiles start at multiples of 4 tasks (16-byte aligned vector loads)
 
 struct DGen {
@@ -44,6 +47,8 @@ struct DGen {
   uint32_t* tie_a;             // [T] anchor of the unit the task is emitted from (work-list tasks)
   uint32_t* tie_r;             // [T] rank inside it
   int32_t* maxpass;            // [1]
+  struct URec* rec;            // unit table: the members of every multi-member unit, one contiguous run per unit
+  unsigned int* rcount;        // [1] records reserved
   int64_t* tv;                 // [T] TotalValue by task (the output buffer, reused)
 };
 
@@ -55,7 +60,7 @@ __device__ __forceinline__ int gen_npass(int bits) { return (bits + 7) >> 3; }
 
 __global__ void k_ginit(DGen G, const int32_t* __restrict__ general_list, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0) { *G.ccount = 0u; *G.maxpass = 0; }
+  if (k == 0) { *G.ccount = 0u; *G.maxpass = 0; *G.rcount = 0u; }
   if (k >= n) return;
   const int d = general_list[k];
   G.vmm[2 * d] = 0ull;
@@ -81,7 +86,7 @@ struct TileFold {  // queue-info partials of one tile (scheduler.go:66-138)
 
 // Per tile: queue info, single-task scores, unit links.  256 threads x 8 tasks: thread q of group u owns the four
 // consecutive task slots tile_start + 4*(u*256 + q) .. +3, so every column is read with 128-bit loads.
-__global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W, DGen G, int64_t now, int any_complex) {
+__global__ void __launch_bounds__(256, EVG_GTASK_OCC) k_gtask(DTasks T, DDistros D, DWork W, DGen G, int64_t now, int any_complex) {
   if (*W.err) return;
   __shared__ TileFold F;
   __shared__ evg_distro_cfg s_cfg;
@@ -119,6 +124,7 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
   unsigned int c_dm = 0, c_mq = 0, c_over = 0, c_wait = 0, c_sec = 0, c_ung = 0, c_ucnt = 0, c_uover = 0, c_uwait = 0, c_umq = 0;
   int64_t s_exp = 0, s_over = 0, s_uexp = 0, s_uover = 0;
   unsigned long long kmax = 0ull, kmin = ~0ull;
+  uint32_t cmask = 0;  // bit 4*u + m: task ts + 4*(u*256 + tid) + m goes on the work list
 
 #pragma unroll 1
   for (int u = 0; u < 2; u++) {
@@ -152,8 +158,9 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
     const int64_t ex_[4] = {ex01.x, ex01.y, ex23.x, ex23.y}, qb_[4] = {qb01.x, qb01.y, qb23.x, qb23.y};
     const int64_t wb_[4] = {wb01.x, wb01.y, wb23.x, wb23.y};
     int64_t vout[4];
-    uint32_t eout[4];
-    bool wr_v[4];
+    uint32_t eout[4], nd_term[4];
+    bool wr_v[4], solo[4];
+    bool dom = true;
 #pragma unroll
     for (int m = 0; m < 4; m++) {
       const int64_t t = t4 + m;
@@ -180,40 +187,28 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
       const bool own_complex = valid & dcomplex & ((gid >= 0) | gv | (((hd4 >> (8 * m)) & 0xFFu) != 0));
       const bool complex_task = own_complex | (valid & dcomplex & (doff[m + 1] > doff[m]));
       const bool scores = valid & !own_complex;  // the unit filed under this task's own key is {this task}
-      uint64_t v = 0;
       const uint32_t ndc = uint32_t(nd > 0 ? nd : 0);
       const uint32_t tab = s_nd[ndc < uint32_t(kNdTable) ? ndc : 0u];
       const uint32_t mul = (f32.ok & (ndc < kTask32Limit)) ? f32.nd * ndc : 0xFFFFFFFFu;
-      const uint32_t nd_term = ndc < uint32_t(kNdTable) ? tab : mul;
-      const bool q_ok = (qb == EVG_TIME_ZERO) | ((qb >= 0) & (uint64_t(now - qb) < kFastLimit));
-      const bool in_dom = q_ok & (uint64_t(exp_ns) < kFastLimit) & (prio < int32_t(kTask32Limit)) & (nd_term != 0xFFFFFFFFu);
-      if (f32.ok_base && __all_sync(full, !scores | in_dom)) {
-        v = single_task_value32_nd(f32, now, prio, exp_ns, qb, nd_term, fl);
-      } else if (fast_clock && __all_sync(full, !scores || score_fast_domain(now, exp_ns, qb))) {
-        v = uint64_t(single_task_value_fast(pf, now, prio, exp_ns, qb, nd, fl));
-      } else if (scores) {
-        v = uint64_t(single_task_value(pf, now, prio, exp_ns, qb, nd, fl));
-      }
-      vout[m] = int64_t(v);
+      nd_term[m] = ndc < uint32_t(kNdTable) ? tab : mul;
+      dom = dom & (!scores | (score32_bad(now, prio, exp_ns, qb, nd_term[m]) == 0u));
       wr_v[m] = scores;
-      eout[m] = (valid && !complex_task) ? 1u : 0u;
-      if (scores && !complex_task) {  // final: the task is emitted from its own unit
-        const unsigned long long k = ord_i64(int64_t(v));
-        kmax = max(kmax, k); kmin = min(kmin, k);
-      }
-      if (dcomplex) {  // warp-aggregated append to the work list
-        const unsigned mm = __ballot_sync(full, complex_task);
-        if (mm) {
-          unsigned int pos0 = 0;
-          if (lane == 0) pos0 = atomicAdd(G.ccount, (unsigned int)__popc(mm));
-          pos0 = __shfl_sync(full, pos0, 0);
-          if (complex_task) {
-            const unsigned int pos = pos0 + __popc(mm & ((1u << lane) - 1u));
-            G.clist[pos] = uint32_t(t);
-            G.clist_d[pos] = d;
-          }
-        }
-      }
+      solo[m] = scores & !complex_task;  // final: the task is emitted from its own unit
+      eout[m] = (valid & !complex_task) ? 1u : 0u;
+      cmask |= (complex_task ? 1u : 0u) << (4 * u + m);
+    }
+    if (f32.ok_base && __all_sync(full, dom)) {  // one warp vote per four tasks; the 64-bit scorers stay out of line
+#pragma unroll
+      for (int m = 0; m < 4; m++) vout[m] = int64_t(single_task_value32_nd(f32, now, prio_[m], ex_[m], qb_[m], nd_term[m], fl_[m]));
+    } else {
+#pragma unroll
+      for (int m = 0; m < 4; m++) vout[m] = int64_t(score_slow(pf, fast_clock, wr_v[m], now, prio_[m], ex_[m], qb_[m], nd_[m], fl_[m]));
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const unsigned long long k = ord_i64(vout[m]);
+      kmax = solo[m] ? max(kmax, k) : kmax;
+      kmin = solo[m] ? min(kmin, k) : kmin;
     }
     // TotalValue of single-task units (also the own-unit candidate of a task that only joins other units by edges)
     if (!live) {
@@ -231,6 +226,32 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
 #pragma unroll
         for (int m = 0; m < 4; m++)
           if (t4 + m >= base && t4 + m < end) G.e[t4 + m] = eout[m];
+      }
+    }
+  }
+  // Work list: ONE global atomic per tile (a block scan of the per-thread counts gives every entry its place) -- an
+  // atomic per warp and task slot serialised every tile of the tick on one L2 address.
+  if (dcomplex) {
+    __shared__ uint32_t s_wsum[8];
+    __shared__ uint32_t s_lbase;
+    const uint32_t mine = __popc(cmask);
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(full, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) s_wsum[tid >> 5] = inc;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t x = s_wsum[w]; before += w < (tid >> 5) ? x : 0u; total += x; }
+    if (total) {  // block-uniform
+      if (tid == 0) s_lbase = atomicAdd(G.ccount, total);
+      __syncthreads();
+      uint32_t pos = s_lbase + before + inc - mine;
+      for (uint32_t b = cmask; b; b &= b - 1u) {
+        const int bit = __ffs(b) - 1;
+        G.clist[pos] = uint32_t(ts + 4 * int64_t((bit >> 2) * 256 + tid) + (bit & 3));
+        G.clist_d[pos] = d;
+        pos++;
       }
     }
   }
@@ -279,22 +300,77 @@ __global__ void __launch_bounds__(256, 2) k_gtask(DTasks T, DDistros D, DWork W,
   }
 }
 
-// Per work-list task: TaskGroupInfo sums of task-group tasks (scheduler.go:79-137), unit membership links
-// (planner.go:431-447) and the links of its in-queue dependencies (planner.go:449-456).  One thread per task, many
-// in flight: every step is a dependent L2 access.
+// ---- multi-member units: the unit table ----
+// A membership ("pair": a task filed under a unit slot by its own key, by its version, or by one of its in-queue
+// dependencies' keys; planner.go:431-456) used to be a node of a linked list per slot, and every walk a chain of
+// dependent scattered loads through six task columns.  Now the members of a unit are one contiguous run of packed
+// 32-byte records:
+//   k_glink   per pair: k = atomicAdd(unit_n[slot], 1) -- its place in the run (any order: everything computed from a
+//             run is order-free); TaskGroupInfo sums of task-group tasks
+//   k_galloc  the pair that drew k == 0 reserves unit_n[slot] records: head[slot] = start of the run
+//   k_gfill   every pair writes its task's record at head[slot] + k
+//   k_gunit   the k == 0 pair folds the run into Unit.info (planner.go:302-337), value (planner.go:209-300), anchor
+//   k_gbest   per task: the first unit it is emitted from among its memberships (TaskPlan.Export, planner.go:467-477),
+//             then its rank inside it (TaskList.Less, planner.go:387-405) by one pass over the run
+// pair ids: own-key pair of task t = t, version pair = T.n + t, pair of dependency edge e = 2*T.n + e.
+struct __align__(16) URec {
+  int32_t prio, nd;
+  int64_t exp_ns, qb;
+  int32_t tgo;
+  uint32_t lif;  // bits 0..20 distro-local task index, 21 own-key pair, 22 group_id >= 0, 24..29 task flags
+};
+static_assert(sizeof(URec) == 32, "one L2 sector per member");
+constexpr uint32_t kRecOwn = 1u << 21, kRecGrouped = 1u << 22;
+__device__ __forceinline__ uint32_t rec_li(const URec& r) { return r.lif & 0x1FFFFFu; }
+__device__ __forceinline__ URec rec_load(const URec* p) {  // two 128-bit loads
+  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+  URec r;
+  r.prio = int32_t(a.x); r.nd = int32_t(a.y); r.exp_ns = int64_t((unsigned long long)a.z | ((unsigned long long)a.w << 32));
+  r.qb = int64_t((unsigned long long)b.x | ((unsigned long long)b.y << 32)); r.tgo = int32_t(b.z); r.lif = b.w;
+  return r;
+}
+__device__ __forceinline__ void rec_store(URec* p, const URec& r) {
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(uint32_t(r.prio), uint32_t(r.nd), uint32_t(uint64_t(r.exp_ns)), uint32_t(uint64_t(r.exp_ns) >> 32));
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(uint32_t(uint64_t(r.qb)), uint32_t(uint64_t(r.qb) >> 32), uint32_t(r.tgo), r.lif);
+}
+
+// what a work-list task is filed under (the same answers in every kernel below)
+struct WlTask {
+  uint32_t t; int d; int64_t base; uint32_t li, ub, ng; int32_t gid, vid; bool gv, own_complex; uint32_t s_own, s_ver;
+};
+__device__ __forceinline__ WlTask wl_task(const DTasks& T, const DDistros& D, const DWork& W, const DGen& G, unsigned int k) {
+  WlTask x;
+  x.t = G.clist[k]; x.d = G.clist_d[k];
+  x.base = D.task_off[x.d];
+  x.gid = T.gid[x.t]; x.vid = T.vid[x.t];
+  x.ng = uint32_t(D.group_off[x.d + 1] - D.group_off[x.d]);
+  x.ub = uint32_t(D.unit_base[x.d]);
+  x.gv = D.cfg[x.d].group_versions != 0;
+  x.li = uint32_t(int64_t(x.t) - x.base);
+  x.own_complex = x.gid >= 0 || x.gv || (W.has_dep[x.t] & 1) != 0;
+  x.s_own = own_slot_local(x.gid, x.vid, x.li, x.ng, x.gv);
+  x.s_ver = (x.gid >= 0 && x.gv) ? x.ng + uint32_t(x.vid) : kInactive;
+  return x;
+}
+// f(pair, slot) for every membership of the task (after k_glink: pair_slot / edge_live are final)
+template <typename F>
+__device__ __forceinline__ void wl_pairs(const DTasks& T, const DWork& W, const WlTask& x, F&& f) {
+  if (x.own_complex) f(x.t, x.ub + x.s_own);
+  if (x.s_ver != kInactive) f(uint32_t(T.n + x.t), x.ub + x.s_ver);
+  if (T.n_edges > 0)
+    for (int64_t e = T.dep_off[x.t]; e < T.dep_off[x.t + 1]; e++)
+      if (W.edge_live[e]) f(uint32_t(2 * T.n + e), W.pair_slot[2 * T.n + e]);
+}
+
 __global__ void __launch_bounds__(256, 4) k_glink(DTasks T, DDistros D, DWork W, DGen G, int64_t now) {
   if (*W.err) return;
   const unsigned int n = *G.ccount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const uint32_t t = G.clist[k];
-    const int d = G.clist_d[k];
-    const int64_t base = D.task_off[d];
-    const int32_t gid = T.gid[t], vid = T.vid[t];
-    const uint32_t ng = uint32_t(D.group_off[d + 1] - D.group_off[d]);
-    const uint32_t ub = uint32_t(D.unit_base[d]);
-    const evg_distro_cfg* cf = D.cfg + d;
-    const bool gv = cf->group_versions != 0;
-    if (gid >= 0) {
+    const WlTask x = wl_task(T, D, W, G, k);
+    const uint32_t t = x.t;
+    const int d = x.d;
+    if (x.gid >= 0) {
+      const evg_distro_cfg* cf = D.cfg + d;
       const uint32_t fl = T.flags[t];
       const int64_t exp_ns = T.expected[t], threshold = cf->target_time_ns;
       const bool dm = (fl & EVG_TF_DEPS_MET) != 0;
@@ -302,7 +378,7 @@ __global__ void __launch_bounds__(256, 4) k_glink(DTasks T, DDistros D, DWork W,
       const bool over = counted && exp_ns > threshold;
       const bool wait_over = counted && dm && since(now, T.wbasis[t]) > threshold;
       const bool mq_dm = dm && (fl & EVG_TF_REQ_MASK) == EVG_TF_REQ_MERGE_QUEUE;
-      evg_group_info* g = W.ginfo + D.group_off[d] + gid;
+      evg_group_info* g = W.ginfo + D.group_off[d] + x.gid;
       atomic_add64(&g->count, counted);
       atomic_add64(&g->expected_duration, counted ? exp_ns : 0);
       atomic_add64(&g->count_duration_over_threshold, over);
@@ -310,61 +386,81 @@ __global__ void __launch_bounds__(256, 4) k_glink(DTasks T, DDistros D, DWork W,
       atomic_add64(&g->count_wait_over_threshold, wait_over);
       atomic_add64(&g->count_dep_filled_merge_queue_tasks, mq_dm);
     }
-    const uint32_t li = uint32_t(int64_t(t) - base);
-    const bool own_complex = gid >= 0 || gv || (W.has_dep[t] & 1) != 0;
-    const uint32_t s_own = own_slot_local(gid, vid, li, ng, gv);
-    const uint32_t s_ver = (gid >= 0 && gv) ? ng + uint32_t(vid) : kInactive;
-    if (own_complex) link_pair(W, t, ub + s_own);
-    if (s_ver != kInactive) link_pair(W, uint32_t(T.n + t), ub + s_ver);  // planner.go:439
+    auto join = [&](uint32_t pair, uint32_t slot) {
+      W.pair_slot[pair] = slot;
+      W.next[pair] = atomicAdd(W.unit_n + slot, 1u);  // the pair's place in the unit's run
+    };
+    if (x.own_complex) join(t, x.ub + x.s_own);
+    if (x.s_ver != kInactive) join(uint32_t(T.n + t), x.ub + x.s_ver);  // planner.go:439
     if (T.n_edges > 0) {
       const int64_t e0 = T.dep_off[t], e1 = T.dep_off[t + 1];
       for (int64_t e = e0; e < e1; e++) {
         const uint32_t dl = uint32_t(T.dep_idx[e]);
-        const uint32_t sl = own_slot_local(T.gid[base + dl], T.vid[base + dl], dl, ng, gv);
-        bool dup = (sl == s_own) || (sl == s_ver);  // Unit.Add is keyed by task id (planner.go:131): join each unit once
+        const uint32_t sl = own_slot_local(T.gid[x.base + dl], T.vid[x.base + dl], dl, x.ng, x.gv);
+        bool dup = (sl == x.s_own) || (sl == x.s_ver);  // Unit.Add is keyed by task id (planner.go:131): join each unit once
         for (int64_t f = e0; f < e && !dup; f++) {
           const uint32_t fl2 = uint32_t(T.dep_idx[f]);
-          dup = own_slot_local(T.gid[base + fl2], T.vid[base + fl2], fl2, ng, gv) == sl;
+          dup = own_slot_local(T.gid[x.base + fl2], T.vid[x.base + fl2], fl2, x.ng, x.gv) == sl;
         }
         W.edge_task[e] = t;
-        if (!dup) link_pair(W, uint32_t(2 * T.n + e), ub + sl);
+        W.edge_live[e] = dup ? 0 : 1;
+        if (!dup) join(uint32_t(2 * T.n + e), x.ub + sl);
       }
     }
   }
 }
 
-// Multi-member units, in two passes over the work list (one thread per task, grid-stride):
-//   k_gunit   the pair at the HEAD of a unit's member list owns the unit: one walk for Unit.info (planner.go:302-337),
-//             its value (planner.go:209-300), its anchor and its member count
-//   k_gbest   per task: the first unit it is emitted from among its memberships (TaskPlan.Export, planner.go:467-477),
-//             then ONE walk of that unit for the task's rank inside it (TaskList.Less, planner.go:387-405)
+__global__ void __launch_bounds__(256, 4) k_galloc(DTasks T, DDistros D, DWork W, DGen G) {
+  if (*W.err) return;
+  const unsigned int n = *G.ccount;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const WlTask x = wl_task(T, D, W, G, k);
+    wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
+      if (W.next[pair] == 0u) W.head[slot] = atomicAdd(G.rcount, W.unit_n[slot]);
+    });
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) k_gfill(DTasks T, DDistros D, DWork W, DGen G) {
+  if (*W.err) return;
+  const unsigned int n = *G.ccount;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const WlTask x = wl_task(T, D, W, G, k);
+    URec r;
+    r.prio = T.priority[x.t]; r.nd = T.numdep[x.t]; r.exp_ns = T.expected[x.t]; r.qb = T.qbasis[x.t]; r.tgo = T.tgo[x.t];
+    r.lif = x.li | (x.gid >= 0 ? kRecGrouped : 0u) | ((T.flags[x.t] & 0x3Fu) << 24);
+    wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
+      URec q = r;
+      if (pair < uint32_t(T.n)) q.lif |= kRecOwn;  // own-key pairs are the SetDistro members (planner.go:446)
+      rec_store(G.rec + W.head[slot] + W.next[pair], q);
+    });
+  }
+}
+
+__device__ __forceinline__ void rec_acc(UnitAcc& a, int64_t now, const URec& r) {
+  acc_add(a, now, r.prio, r.exp_ns, r.qb, r.nd, (r.lif & kRecGrouped) ? 0 : -1, (r.lif >> 24) & 0x3Fu);
+}
+
 __global__ void __launch_bounds__(256, 4) k_gunit(DTasks T, DDistros D, DWork W, DGen G, int64_t now) {
   if (*W.err) return;
   const unsigned int n = *G.ccount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {  // the host cannot know n: fixed grid
-    const uint32_t t = G.clist[k];
-    const int d = G.clist_d[k];
-    const int64_t base = D.task_off[d];
-    auto head_of = [&](uint32_t p) {
-      if (W.next[p] == kInactive) return;  // not linked
-      const uint32_t slot = W.pair_slot[p];
-      if (W.head[slot] != p) return;       // some other member owns the unit
+    const WlTask x = wl_task(T, D, W, G, k);
+    wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
+      if (W.next[pair] != 0u) return;  // some other member owns the unit
+      const uint32_t cnt = W.unit_n[slot];
+      const URec* run = G.rec + W.head[slot];
       UnitAcc a;
       acc_init(a);
       uint32_t anchor = kNoAnchor;
-      for (uint32_t q = p; q < kEnd; q = W.next[q]) {
-        const uint32_t tq = pair_task(T, W, q);
-        acc_add(a, now, T.priority[tq], T.expected[tq], T.qbasis[tq], T.numdep[tq], T.gid[tq], T.flags[tq]);
-        if (q < uint32_t(T.n)) anchor = min(anchor, uint32_t(int64_t(tq) - base));  // own-key pairs are the SetDistro members (planner.go:446)
+      for (uint32_t i = 0; i < cnt; i++) {
+        const URec r = rec_load(run + i);
+        rec_acc(a, now, r);
+        if (r.lif & kRecOwn) anchor = min(anchor, rec_li(r));
       }
-      W.unit_v[slot] = unit_value(a, D.cfg[d], nullptr);
+      W.unit_v[slot] = unit_value(a, D.cfg[x.d], nullptr);
       W.unit_a[slot] = anchor;  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
-      W.unit_n[slot] = uint32_t(a.n);
-    };
-    head_of(t);
-    head_of(uint32_t(T.n + t));
-    if (T.n_edges > 0)
-      for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) head_of(uint32_t(2 * T.n + e));
+    });
   }
 }
 
@@ -372,35 +468,29 @@ __global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W,
   if (*W.err) return;
   const unsigned int n = *G.ccount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const uint32_t t = G.clist[k];
-    const int d = G.clist_d[k];
-    const int64_t base = D.task_off[d];
-    const uint32_t li = uint32_t(int64_t(t) - base);
+    const WlTask x = wl_task(T, D, W, G, k);
+    const uint32_t t = x.t, li = x.li;
+    const int d = x.d;
     bool have = false;
     int64_t bv = 0;
     uint32_t ba = 0, brk = 0, bp = kInactive, bslot = 0;
-    auto consider = [&](uint32_t p) {
-      if (W.next[p] == kInactive) return;  // not linked (duplicate membership, or a key this task is not filed under)
-      const uint32_t slot = W.pair_slot[p];
+    if (!x.own_complex) { have = true; bv = G.tv[t]; ba = li; }  // its own single-task unit, scored by k_gtask
+    wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
       const uint32_t a = W.unit_a[slot];
       if (a == kNoAnchor) return;
       const int64_t v = W.unit_v[slot];
-      if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; bp = p; bslot = slot; }
-    };
-    if (W.next[t] == kInactive) { have = true; bv = G.tv[t]; ba = li; }  // its own single-task unit, scored by k_gtask
-    else consider(t);
-    consider(uint32_t(T.n + t));
-    if (T.n_edges > 0)
-      for (int64_t e = T.dep_off[t]; e < T.dep_off[t + 1]; e++) consider(uint32_t(2 * T.n + e));
+      if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; bp = pair; bslot = slot; }
+    });
     uint32_t bn = 1;
     if (bp != kInactive) {  // rank among ALL members of the chosen unit
       const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
       const int64_t my_ex = T.expected[t];
-      for (uint32_t q = W.head[bslot]; q < kEnd; q = W.next[q]) {
-        const uint32_t tq = pair_task(T, W, q);
-        if (in_unit_less(T.tgo[tq], T.numdep[tq], T.priority[tq], T.expected[tq], uint32_t(int64_t(tq) - base), my_tgo, my_nd, my_pr, my_ex, li)) brk++;
-      }
       bn = W.unit_n[bslot];
+      const URec* run = G.rec + W.head[bslot];
+      for (uint32_t i = 0; i < bn; i++) {
+        const URec r = rec_load(run + i);
+        if (in_unit_less(r.tgo, r.nd, r.prio, r.exp_ns, rec_li(r), my_tgo, my_nd, my_pr, my_ex, li)) brk++;
+      }
       if (bn <= 64) atomicOr(&W.unit_mask[bslot], 1ull << brk);  // ranks emitted from the unit: k_gplace_disp counts below its own
     }
     G.tv[t] = bv;
@@ -409,7 +499,7 @@ __global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W,
     W.best_pair[t] = bp;
     const bool displaced = !(ba == li && brk == 0);
     if (displaced) W.has_dep[t] |= 2;  // only this thread touches the byte now (k_gmark and k_gtask are done)
-    atomicAdd(G.e + base + ba, 1u);
+    atomicAdd(G.e + x.base + ba, 1u);
     const unsigned long long kk = ord_i64(bv);
     if (kk > __ldcg(G.vmm + 2 * d)) atomicMax(G.vmm + 2 * d, kk);
     if (kk < __ldcg(G.vmm + 2 * d + 1)) atomicMin(G.vmm + 2 * d + 1, kk);
@@ -586,8 +676,10 @@ __global__ void __launch_bounds__(256) k_gplace_disp(DTasks T, DDistros D, DWork
   if (W.unit_n[slot] <= 64) {
     pos += __popcll(W.unit_mask[slot] & ((1ull << myrk) - 1ull));
   } else {
-    for (uint32_t q = W.head[slot]; q < kEnd; q = W.next[q]) {
-      const uint32_t tq = pair_task(T, W, q);
+    const URec* run = G.rec + W.head[slot];
+    const uint32_t cnt = W.unit_n[slot];
+    for (uint32_t i = 0; i < cnt; i++) {
+      const uint32_t tq = uint32_t(base + rec_li(rec_load(run + i)));
       if (W.best_pair[tq] != kInactive && W.pair_slot[W.best_pair[tq]] == slot && G.tie_r[tq] < myrk) pos++;
     }
   }
@@ -669,51 +761,63 @@ __global__ void __launch_bounds__(1024) k_gdscan(int j, const int32_t* __restric
   for (; tile < b; tile++) { const uint32_t x = h[tile * 256]; h[tile * 256] = run; run += x; }
 }
 
+// Warp w ranks chunks 8w .. 8w+7 of the tile in order (stability): one MATCH.ANY per chunk, the group's first lane adds
+// the group size to the warp's digit counter and gets back the count of equal digits in the warp's earlier chunks (as in
+// k_plan_cta).  Thread = digit then turns the 8 per-warp counters into bases on top of the tile's offset for the digit.
 __global__ void __launch_bounds__(256) k_gscatter(int j, DDistros D, DGen G) {
   if (j >= *G.maxpass) return;
   int d, cnt; int64_t seg, lo; bool wide;
   const int tile = int(blockIdx.x + G.tile0);
   if (!gen_tile(D, G, tile, j, &d, &seg, &lo, &cnt, &wide)) return;
   const int sb = j & 1, db = sb ^ 1;
-  constexpr int kChunks = kGTile / 32;
-  __shared__ uint16_t ch[kChunks][256];
-  for (int i = threadIdx.x; i < kChunks * 256 / 2; i += 256) reinterpret_cast<uint32_t*>(&ch[0][0])[i] = 0;
+  __shared__ uint32_t wcnt[8][256];
+#pragma unroll
+  for (int w = 0; w < 8; w++) wcnt[w][threadIdx.x] = 0u;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const int shift = 8 * (j & 3);
+  const uint32_t* src_lo = G.key_lo[sb] + lo;
+  const uint32_t* src_hi = G.key_hi[sb] + lo;
+  const uint32_t* src_ix = G.idx[sb] + lo;
   uint32_t kl[8], kh[8], ix[8], dg[8], rk[8];
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const int c = warp * 8 + k;
-    const int i = c * 32 + lane;
+  for (int k = 0; k < 8; k++) {  // all loads first
+    const int i = (warp * 8 + k) * 32 + lane;
     const bool ok = i < cnt;
-    kl[k] = ok ? G.key_lo[sb][lo + i] : 0u;
-    kh[k] = (ok && wide) ? G.key_hi[sb][lo + i] : 0u;
-    ix[k] = ok ? G.idx[sb][lo + i] : 0u;
+    kl[k] = ok ? src_lo[i] : 0u;
+    kh[k] = (ok && wide) ? src_hi[i] : 0u;
+    ix[k] = ok ? src_ix[i] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int i = (warp * 8 + k) * 32 + lane;
+    const bool ok = i < cnt;
     dg[k] = ok ? (((j < 4 ? kl[k] : kh[k]) >> shift) & 255u) : 256u;
     const unsigned peers = __match_any_sync(0xffffffffu, dg[k]);
-    rk[k] = __popc(peers & lt);
-    if (ok && rk[k] == 0) ch[c][dg[k]] = uint16_t(__popc(peers));
+    const uint32_t r = __popc(peers & lt);
+    uint32_t old = 0;
+    if (ok && r == 0) old = atomicAdd(&wcnt[warp][dg[k]], uint32_t(__popc(peers)));
+    old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+    rk[k] = old + r;
   }
   __syncthreads();
   {
-    uint32_t run = 0;
-    for (int c = 0; c < kChunks; c++) {
-      const uint32_t x = ch[c][threadIdx.x];
-      ch[c][threadIdx.x] = uint16_t(run);
-      run += x;
-    }
+    uint32_t run = G.tile_hist[int64_t(tile) * 256 + threadIdx.x];  // the tile's offset for this digit inside the distro
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t x = wcnt[w][threadIdx.x]; wcnt[w][threadIdx.x] = run; run += x; }
   }
   __syncthreads();
+  uint32_t* dst_lo = G.key_lo[db] + seg;
+  uint32_t* dst_hi = G.key_hi[db] + seg;
+  uint32_t* dst_ix = G.idx[db] + seg;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     if (dg[k] < 256u) {
-      const int c = warp * 8 + k;
-      const int64_t pos = seg + G.tile_hist[int64_t(tile) * 256 + dg[k]] + ch[c][dg[k]] + rk[k];
-      G.key_lo[db][pos] = kl[k];
-      if (wide) G.key_hi[db][pos] = kh[k];
-      G.idx[db][pos] = ix[k];
+      const uint32_t pos = wcnt[warp][dg[k]] + rk[k];
+      dst_lo[pos] = kl[k];
+      if (wide) dst_hi[pos] = kh[k];
+      dst_ix[pos] = ix[k];
     }
   }
 }

@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(256) k_dur_final(DDur X, evg_duration_stat* ou
 
 // The 13-field SortingValueBreakdown of the unit each ranked task was emitted
 // from (planner.go:472-476, model/task/task.go:3990-4038); both paths.
-__global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W, int64_t now, int any_complex,
+__global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W, const URec* rec, int64_t now, int any_complex,
                                                    const int32_t* order, int64_t* breakdown) {
   if (*W.err) return;
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -509,11 +509,16 @@ __global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W
   const uint32_t bp = any_complex ? W.best_pair[g] : kInactive;
   if (bp == kInactive) {
     acc_add(a, now, T.priority[g], T.expected[g], T.qbasis[g], T.numdep[g], T.gid[g], T.flags[g]);
-  } else {
+  } else if (W.route[d]) {  // on-chip planners leave member lists (breakdown mode only)
     for (uint32_t q = W.head[W.pair_slot[bp]]; q < kEnd; q = W.next[q]) {
       const uint32_t tq = pair_task(T, W, q);
       acc_add(a, now, T.priority[tq], T.expected[tq], T.qbasis[tq], T.numdep[tq], T.gid[tq], T.flags[tq]);
     }
+  } else {  // general path: the unit table
+    const uint32_t slot = W.pair_slot[bp];
+    const URec* run = rec + W.head[slot];
+    const uint32_t cnt = W.unit_n[slot];
+    for (uint32_t i = 0; i < cnt; i++) rec_acc(a, now, rec_load(run + i));
   }
   int64_t bd[EVG_BD_N];
   unit_value(a, D.cfg[d], bd);
@@ -736,7 +741,7 @@ struct evg_ctx {
   int general_complex = 0;
   int64_t Tgc = 0;  // tasks in general-path distros that can hold multi-member units (work-list capacity)
   DevBuf b_kv, b_vmm, b_klo[2], b_khi[2], b_ix[2], b_e, b_tilesum, b_gmisc;
-  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist;
+  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist, b_rec;
   DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
   DevBuf b_hflags, b_hgid, b_hexp, b_hstd, b_hstart, b_hostoff, b_acfg, b_gs, b_result, b_status;
   bool bd_valid = false;
@@ -780,7 +785,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   int32_t n_general = 0;
   int general_complex = 0;
   int any_complex = E > 0 ? 1 : 0;
-  int64_t Tgc = 0;
+  int64_t Tgc = 0, Prec = 0;
   constexpr int kGA = PlanCta<kNT_A, kNCapA>::kGroupCap, kGB = PlanCta<kNT_B, kNCapB>::kGroupCap, kGC = PlanCta<kNT_C, kNCapC>::kGroupCap;
   for (int32_t d = 0; d < D; d++) {
     const int64_t a = dt->task_off[d], b = dt->task_off[d + 1];
@@ -807,7 +812,11 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
     else {
       n_general++;
       listG.push_back(d);
-      if (gb > ga || cf.group_versions || de > 0) { general_complex = 1; Tgc += n; }
+      if (gb > ga || cf.group_versions || de > 0) {
+        general_complex = 1;
+        Tgc += n;
+        Prec += n + ((cf.group_versions && gb > ga) ? n : 0) + de;  // own-key, version and dependency memberships at most
+      }
       const int64_t a0 = a & ~int64_t(3);  // tiles start 16-byte aligned in every column
       for (int64_t s = a0; s < b; s += kGTile) { tile_distro.push_back(d); tile_start.push_back(s); }
     }
@@ -818,6 +827,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   if (G > 0 && !dt->group_max_hosts) return fail(EVG_ERR_INVALID, "null group_max_hosts");
   const int64_t U = unit_base[D];
   if (U >= int64_t(0xFFFFFFF0u)) return fail(EVG_ERR_INVALID, "unit slot space exceeds 32 bits");
+  if (Prec >= int64_t(0xFFFFFFF0u)) return fail(EVG_ERR_INVALID, "unit table exceeds 32 bits");
   const int64_t NT = int64_t(tile_distro.size());
   const int64_t P = 2 * T + E;
   cudaStream_t s = c->stream;
@@ -898,6 +908,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
     if (general_complex) {
       CK(c->b_e.ensure(sizeof(uint32_t) * size_t(T + kColPad)));
       CK(c->b_clist.ensure(sizeof(uint32_t) * 2 * size_t(Tgc + 1)));
+      CK(c->b_rec.ensure(sizeof(URec) * size_t(Prec + 1)));
       CK(c->b_ca.ensure(sizeof(uint32_t) * size_t(T + 1)));
       CK(c->b_crk.ensure(sizeof(uint32_t) * size_t(T + 1)));
     }
@@ -1019,6 +1030,8 @@ DGen dgen(const evg_ctx* c) {
   g.clist_d = c->b_clist.as<int32_t>() + (c->Tgc + 1);
   g.ccount = c->b_gmisc.as<unsigned int>();
   g.maxpass = c->b_gmisc.as<int32_t>() + 1;
+  g.rcount = c->b_gmisc.as<unsigned int>() + 2;
+  g.rec = c->b_rec.as<URec>();
   g.tie_a = c->b_ca.as<uint32_t>(); g.tie_r = c->b_crk.as<uint32_t>();
   g.tv = c->b_tv.as<int64_t>();
   return g;
@@ -1094,7 +1107,6 @@ int launch_tiny(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& d
 // path this runs on the context stream BEFORE the routes fork: an on-chip distro inside the span rewrites its own rows
 // afterwards.
 int prepare_general(evg_ctx* c, cudaStream_t s, int32_t d0, int32_t d1) {
-  const int64_t T = c->T;
   const int64_t t0 = c->h_taskoff[d0], t1 = c->h_taskoff[d1], u0 = c->h_unitbase[d0], u1 = c->h_unitbase[d1];
   const int64_t g0 = c->h_groupoff[d0], g1 = c->h_groupoff[d1], e0 = c->h_edgeoff[d0], e1 = c->h_edgeoff[d1];
   CK(cudaMemsetAsync(c->b_qinfo.as<evg_queue_info>() + d0, 0, sizeof(evg_queue_info) * size_t(d1 - d0), s));
@@ -1102,11 +1114,8 @@ int prepare_general(evg_ctx* c, cudaStream_t s, int32_t d0, int32_t d1) {
   if (c->general_complex) {
     const size_t nt = size_t(t1 - t0);
     CK(cudaMemsetAsync(c->b_hasdep.as<uint8_t>() + t0, 0, nt, s));
-    CK(cudaMemsetAsync(c->b_head.as<uint32_t>() + u0, 0xFF, sizeof(uint32_t) * size_t(u1 - u0), s));
+    CK(cudaMemsetAsync(c->b_unitn.as<uint32_t>() + u0, 0, sizeof(uint32_t) * size_t(u1 - u0), s));   // members drawn so far
     CK(cudaMemsetAsync(c->b_unitmask.as<uint64_t>() + u0, 0, sizeof(uint64_t) * size_t(u1 - u0), s));
-    CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + t0, 0xFF, sizeof(uint32_t) * nt, s));          // own-key pairs
-    CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + T + t0, 0xFF, sizeof(uint32_t) * nt, s));      // version pairs
-    if (e1 > e0) CK(cudaMemsetAsync(c->b_next.as<uint32_t>() + 2 * T + e0, 0xFF, sizeof(uint32_t) * size_t(e1 - e0), s));  // edge pairs
   }
   return EVG_OK;
 }
@@ -1129,6 +1138,8 @@ int run_general(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& d
   const unsigned wl_grid = unsigned(std::min<int64_t>(std::max<int64_t>(1, (c->Tgc + 255) / 256), 148 * 16));
   if (gc) {
     LAUNCH_ON(c, st, k_glink, wl_grid, 256, dt, dd, w, g, now);
+    LAUNCH_ON(c, st, k_galloc, wl_grid, 256, dt, dd, w, g);
+    LAUNCH_ON(c, st, k_gfill, wl_grid, 256, dt, dd, w, g);
     LAUNCH_ON(c, st, k_gunit, wl_grid, 256, dt, dd, w, g, now);
     LAUNCH_ON(c, st, k_gbest, wl_grid, 256, dt, dd, w, g);
   }
@@ -1237,7 +1248,7 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
       CK(cudaStreamWaitEvent(s, c->ev_join[k], 0));
     }
   }
-  if (bd) LAUNCH(c, k_breakdown, grid_for(T, 256), 256, dt, dd, w, now, c->any_complex, c->b_order.as<int32_t>(), bd);
+  if (bd) LAUNCH(c, k_breakdown, grid_for(T, 256), 256, dt, dd, w, c->b_rec.as<URec>(), now, c->any_complex, c->b_order.as<int32_t>(), bd);
   CK(cudaGetLastError());
   return EVG_OK;
 }
@@ -1287,7 +1298,7 @@ void evg_shutdown(evg_ctx* c) {
                    &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_listG, &c->b_listNA, &c->b_listNB,
                    &c->b_listNC, &c->b_punt, &c->b_puntcnt, &c->b_ca, &c->b_crk, &c->b_bestpair, &c->b_kv, &c->b_vmm,
                    &c->b_klo[0], &c->b_klo[1], &c->b_khi[0], &c->b_khi[1], &c->b_ix[0], &c->b_ix[1], &c->b_e, &c->b_tilesum,
-                   &c->b_gmisc, &c->b_clist, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
+                   &c->b_gmisc, &c->b_clist, &c->b_rec, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
                    &c->b_hstart, &c->b_hostoff, &c->b_acfg, &c->b_gs, &c->b_result, &c->b_status};
   for (DevBuf* b : all) b->release();

@@ -329,6 +329,14 @@ EVG_HD int64_t nd_table_entry(const PlannerFactors& f, int n) { return d2i_trunc
 EVG_HD bool score32_domain_nd(int64_t now, int32_t priority, int64_t expected_ns, int64_t queue_basis_ns) {
   return score_fast_domain(now, expected_ns, queue_basis_ns) && priority < int32_t(kTask32Limit);
 }
+// The kernels' form of that test, one OR of everything that must be small (nonzero = outside): time in queue and expected
+// duration below 2^50 ns (13 days, inside kFastLimit; with now >= 0 -- Factors32::ok_base -- a wrapped now - t below 2^50
+// is the exact difference, so a basis before 1970 needs no test of its own), priority below 2^15, the resolved
+// NumDependents term below 2^29 (kNdTermLimit; "not representable" is 0xFFFFFFFF).
+EVG_HD uint32_t score32_bad(int64_t now, int32_t priority, int64_t expected_ns, int64_t queue_basis_ns, uint32_t nd_term) {
+  const uint64_t tiq = queue_basis_ns == EVG_TIME_ZERO ? 0ull : uint64_t(now - queue_basis_ns);
+  return uint32_t((tiq | uint64_t(expected_ns)) >> 50) | (uint32_t(priority > 0 ? priority : 0) >> 15) | (nd_term >> 29);
+}
 EVG_HD uint64_t single_task_value32_nd(const Factors32& f, int64_t now, int32_t priority, int64_t expected_ns,
                                        int64_t queue_basis_ns, uint32_t nd_term, uint32_t tflags) {
   const uint32_t req = tflags & EVG_TF_REQ_MASK;

@@ -3,7 +3,15 @@ c3: 48 distros x 100k tasks in configs[2]'s mix (Zipf, dependencies, task groups
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
 import numpy as np
+from evergreen_b200 import _lib as L
+if len(sys.argv) > 3:  # another build of the library (profiles/ab_variants.py build ...)
+    lib = C.CDLL(sys.argv[3])
+    for name, (res, args) in L.SYMBOLS.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
+    L._lib = lib
 from evergreen_b200 import scheduler, synth
 which = sys.argv[1] if len(sys.argv) > 1 else "c3"
 eng = scheduler.Engine(0)
@@ -14,7 +22,11 @@ elif which == "1m":
 else:
     w = synth.make(np.full(48, 100000), synth.SEED_BASE + 3, tg_frac=0.0, zipf_priority=True, n_hosts=96)
 eng.upload(w.tasks, w.distros, w.hosts)
+ms = []
 for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
     eng.run(w.now)
+    ms.append(eng.last_timing_ms()[0])
 po, ao = eng.download()
-print("ok", which, w.n_tasks, eng.last_timing_ms(), eng.general_timing_ms(), eng.last_launch_count(), int(ao.result["new_hosts"].sum()))
+print("ok", which, os.path.basename(sys.argv[3]) if len(sys.argv) > 3 else "in-tree", w.n_tasks, "tick median %.4f ms min %.4f" % (float(np.median(ms)), float(min(ms))),
+      "tasks/s %.3e" % (w.n_tasks / (float(np.median(ms)) * 1e-3)), eng.general_timing_ms(), eng.last_launch_count(),
+      "checksum", int(ao.result["new_hosts"].sum()) + int(po.order[::997].sum()))

@@ -9,7 +9,7 @@ using namespace evg;
 static int64_t ref_floor_minutes_over(int64_t d, int64_t n) { return int64_t(std::floor((double(d / kMinute) + double(d % kMinute) / (60.0 * 1e9)) / double(n))); }
 static int64_t ref_trunc_hours(int64_t d) { return int64_t(double(d / kHour) + double(d % kHour) / (3600.0 * 1e9)); }
 int main() {
-  uint64_t x = 88172645463325252ULL; long bad = 0; long n = 0; long fast_n = 0; long n32 = 0; long n32t = 0;
+  uint64_t x = 88172645463325252ULL; long bad = 0; long n = 0; long fast_n = 0; long n32 = 0; long n32t = 0; long nbad0 = 0;
   auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
   for (int it = 0; it < 20000000; it++) {
     int64_t q = int64_t(rnd() % (uint64_t(1) << 15));
@@ -78,6 +78,23 @@ int main() {
         if (uint64_t(want) != single_task_value32_nd(f32, now, prio, ex, qb, uint32_t(e), fl)) bad++;
       }
     }
+    // the kernels' OR-form of the domain, also with a clock near the epoch and bases before it
+    {
+      const int64_t now2 = (it & 1) ? now : int64_t(rnd() % (1ULL << 52));
+      int64_t qb2 = qb;
+      if (it % 7 == 0) qb2 = now2 - int64_t(rnd() % (1ULL << 51)) + (int64_t(1) << 49);  // straddles 0 and the 2^50 limit
+      if (it % 11 == 0) qb2 = int64_t(rnd());
+      const Factors32 g32 = factors32(pf, now2);
+      if (g32.ok_base && nd < kNdTable) {
+        const int64_t e = nd_table_entry(pf, nd > 0 ? nd : 0);
+        const uint32_t term = (e >= 0 && e < int64_t(kNdTermLimit)) ? uint32_t(e) : 0xFFFFFFFFu;
+        if (score32_bad(now2, prio, ex, qb2, term) == 0u) {
+          nbad0++;
+          UnitAcc a2; acc_init(a2); acc_add(a2, now2, prio, ex, qb2, nd, -1, fl);
+          if (uint64_t(unit_value(a2, c, nullptr)) != single_task_value32_nd(g32, now2, prio, ex, qb2, term, fl)) bad++;
+        }
+      }
+    }
     n++;
   }
   // the straight-line form at the edges of its domain (week boundary, limit - 1, zero basis, huge factors)
@@ -128,7 +145,7 @@ int main() {
         score_fast_domain(now, 0, now + 1) || score_fast_domain(now, 0, -5)) bad++;
   }
   if (fast_n < 1000000) bad++;  // the straight-line form must actually have been exercised
-  if (n32 < 500000 || n32t < 500000) bad++;      // and so must the 32-bit forms
+  if (n32 < 500000 || n32t < 500000 || nbad0 < 500000) bad++;      // and so must the 32-bit forms
   {  // out of the 32-bit domain: big factor, big priority, big dependents, negative clock
     evg_distro_cfg c; memset(&c, 0, sizeof(c));
     c.patch_factor = kFactor32Limit;

@@ -705,6 +705,23 @@ def test_c2_full_size_properties(engine):
     parity.check_against_oracle(w, po, ao, distros=[0, 1, 499, 998, 999])
 
 
+def test_c2_full_size_every_distro_every_tick(engine):
+    """The same tick, ALL 1000 distros bit-exact against the oracle, eight resident ticks in a row.  A staging race in
+    k_plan_cta (a shared-memory slot refilled by TMA before a lagging warp's loads had read it) corrupted one warp's
+    tasks in roughly one CTA out of ten thousand: invisible to a handful of sampled distros or to a single tick."""
+    w = synth.config(2, 1.0)
+    job = O.SoAJob(w.tasks, w.distros, w.hosts, None)
+    ref = job.run(w.now, 32)
+    engine.upload(w.tasks, w.distros, w.hosts)
+    for tick in range(8):
+        engine.run(w.now)
+        po, ao = engine.download()
+        k = parity.first_diff(po.order, ref["order"])
+        assert k < 0, f"tick {tick}: order differs at table row {k} (distro {int(np.searchsorted(w.distros.task_off, k, side='right')) - 1})"
+        assert parity.first_diff(po.total_value, ref["total_value"]) < 0, f"tick {tick}: TotalValue differs"
+        assert np.array_equal(ao.result["new_hosts"], ref["new_hosts"]) and np.array_equal(ao.result["free_hosts"], ref["free_hosts"])
+
+
 # ---------------------------------------------------------------- round 2: second-generation planners
 def test_cta_class_boundaries(engine):
     """Sizes on both sides of every k_plan_cta class (1280 / 5120 / 10240 tasks) and of the k_plan_smem class above
