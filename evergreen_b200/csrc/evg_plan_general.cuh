@@ -44,11 +44,14 @@ struct DGen {
   uint32_t* clist;             // work list: global task index of every task that touches a multi-member unit
   int32_t* clist_d;            // its distro
   unsigned int* ccount;        // [1]
-  uint32_t* tie_a;             // [T] anchor of the unit the task is emitted from (work-list tasks)
-  uint32_t* tie_r;             // [T] rank inside it
+  uint4* tie;                  // [T] work-list tasks: x = anchor of the unit the task is emitted from, y = rank inside it,
+                               //     z = that unit's slot (kInactive: its own single-task unit)
+  struct UHdr* uh;             // [unit slots] header of every multi-member unit (one sector)
   int32_t* maxpass;            // [1]
   struct URec* rec;            // unit table: the members of every multi-member unit, one contiguous run per unit
   unsigned int* rcount;        // [1] records reserved
+  uint2* hlist;                // multi-member units of the tick: x = slot, y = distro (k_galloc lists them, k_gunit folds them)
+  unsigned int* hcount;        // [1]
   int64_t* tv;                 // [T] TotalValue by task (the output buffer, reused)
 };
 
@@ -60,7 +63,7 @@ __device__ __forceinline__ int gen_npass(int bits) { return (bits + 7) >> 3; }
 
 __global__ void k_ginit(DGen G, const int32_t* __restrict__ general_list, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0) { *G.ccount = 0u; *G.maxpass = 0; *G.rcount = 0u; }
+  if (k == 0) { *G.ccount = 0u; *G.maxpass = 0; *G.rcount = 0u; *G.hcount = 0u; }
   if (k >= n) return;
   const int d = general_list[k];
   G.vmm[2 * d] = 0ull;
@@ -320,6 +323,22 @@ struct __align__(16) URec {
   uint32_t lif;  // bits 0..20 distro-local task index, 21 own-key pair, 22 group_id >= 0, 24..29 task flags
 };
 static_assert(sizeof(URec) == 32, "one L2 sector per member");
+struct __align__(16) UHdr {  // what used to be five slot-indexed arrays (five sectors per visit)
+  int64_t v;                 // TotalValue (k_gunit)
+  uint32_t a;                // anchor; kNoAnchor: never exported
+  uint32_t n;                // members (k_glink counts them in)
+  uint32_t start;            // first record of the run (k_galloc)
+  uint32_t pad;
+  unsigned long long mask;   // ranks emitted from the unit (units of <= 64 members; k_gbest)
+};
+static_assert(sizeof(UHdr) == 32, "one L2 sector per unit");
+__device__ __forceinline__ UHdr uh_load(const UHdr* p) {
+  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+  UHdr h;
+  h.v = int64_t((unsigned long long)a.x | ((unsigned long long)a.y << 32)); h.a = a.z; h.n = a.w;
+  h.start = b.x; h.pad = b.y; h.mask = (unsigned long long)b.z | ((unsigned long long)b.w << 32);
+  return h;
+}
 constexpr uint32_t kRecOwn = 1u << 21, kRecGrouped = 1u << 22;
 __device__ __forceinline__ uint32_t rec_li(const URec& r) { return r.lif & 0x1FFFFFu; }
 __device__ __forceinline__ URec rec_load(const URec* p) {  // two 128-bit loads
@@ -388,7 +407,7 @@ __global__ void __launch_bounds__(256, 4) k_glink(DTasks T, DDistros D, DWork W,
     }
     auto join = [&](uint32_t pair, uint32_t slot) {
       W.pair_slot[pair] = slot;
-      W.next[pair] = atomicAdd(W.unit_n + slot, 1u);  // the pair's place in the unit's run
+      W.next[pair] = atomicAdd(&G.uh[slot].n, 1u);  // the pair's place in the unit's run
     };
     if (x.own_complex) join(t, x.ub + x.s_own);
     if (x.s_ver != kInactive) join(uint32_t(T.n + t), x.ub + x.s_ver);  // planner.go:439
@@ -410,14 +429,45 @@ __global__ void __launch_bounds__(256, 4) k_glink(DTasks T, DDistros D, DWork W,
   }
 }
 
+// Runs are reserved block by block: a block scan of the records its threads need, ONE atomic on the bump counter per
+// block and trip (an atomic per unit serialised ~10^5 units of a tick on one L2 address: 340 us of a 1.4 ms tick).
 __global__ void __launch_bounds__(256, 4) k_galloc(DTasks T, DDistros D, DWork W, DGen G) {
   if (*W.err) return;
+  __shared__ uint32_t s_wsum[8], s_wcnt[8];
+  __shared__ uint32_t s_base, s_hbase;
   const unsigned int n = *G.ccount;
-  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const WlTask x = wl_task(T, D, W, G, k);
-    wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
-      if (W.next[pair] == 0u) W.head[slot] = atomicAdd(G.rcount, W.unit_n[slot]);
-    });
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned int k0 = blockIdx.x * blockDim.x; k0 < n; k0 += gridDim.x * blockDim.x) {  // block-uniform trip count
+    const unsigned int k = k0 + threadIdx.x;
+    WlTask x;
+    uint32_t need = 0, heads = 0;  // records / units this thread's k == 0 pairs stand for
+    if (k < n) {
+      x = wl_task(T, D, W, G, k);
+      wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) { if (W.next[pair] == 0u) { need += G.uh[slot].n; heads++; } });
+    }
+    uint32_t inc = need, hinc = heads;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o), z = __shfl_up_sync(0xffffffffu, hinc, o);
+      if (lane >= o) { inc += y; hinc += z; }
+    }
+    if (lane == 31) { s_wsum[warp] = inc; s_wcnt[warp] = hinc; }
+    __syncthreads();
+    uint32_t before = 0, total = 0, hbefore = 0, htotal = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      const uint32_t y = s_wsum[w], z = s_wcnt[w];
+      before += w < warp ? y : 0u; total += y; hbefore += w < warp ? z : 0u; htotal += z;
+    }
+    if (threadIdx.x == 0 && htotal) { s_base = atomicAdd(G.rcount, total); s_hbase = atomicAdd(G.hcount, htotal); }
+    __syncthreads();
+    if (heads) {
+      uint32_t pos = s_base + before + inc - need, hp = s_hbase + hbefore + hinc - heads;
+      wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
+        if (W.next[pair] == 0u) { G.uh[slot].start = pos; pos += G.uh[slot].n; G.hlist[hp++] = make_uint2(slot, uint32_t(x.d)); }
+      });
+    }
+    __syncthreads();  // the shared scratch is rewritten by the next trip
   }
 }
 
@@ -432,7 +482,7 @@ __global__ void __launch_bounds__(256, 4) k_gfill(DTasks T, DDistros D, DWork W,
     wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
       URec q = r;
       if (pair < uint32_t(T.n)) q.lif |= kRecOwn;  // own-key pairs are the SetDistro members (planner.go:446)
-      rec_store(G.rec + W.head[slot] + W.next[pair], q);
+      rec_store(G.rec + G.uh[slot].start + W.next[pair], q);
     });
   }
 }
@@ -441,30 +491,29 @@ __device__ __forceinline__ void rec_acc(UnitAcc& a, int64_t now, const URec& r) 
   acc_add(a, now, r.prio, r.exp_ns, r.qb, r.nd, (r.lif & kRecGrouped) ? 0 : -1, (r.lif >> 24) & 0x3Fu);
 }
 
-__global__ void __launch_bounds__(256, 4) k_gunit(DTasks T, DDistros D, DWork W, DGen G, int64_t now) {
+// One thread per multi-member unit (dense warps: the unit list, not the work list).
+__global__ void __launch_bounds__(256, 4) k_gunit(DDistros D, DWork W, DGen G, int64_t now) {
   if (*W.err) return;
-  const unsigned int n = *G.ccount;
+  const unsigned int n = *G.hcount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {  // the host cannot know n: fixed grid
-    const WlTask x = wl_task(T, D, W, G, k);
-    wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
-      if (W.next[pair] != 0u) return;  // some other member owns the unit
-      const uint32_t cnt = W.unit_n[slot];
-      const URec* run = G.rec + W.head[slot];
-      UnitAcc a;
-      acc_init(a);
-      uint32_t anchor = kNoAnchor;
-      for (uint32_t i = 0; i < cnt; i++) {
-        const URec r = rec_load(run + i);
-        rec_acc(a, now, r);
-        if (r.lif & kRecOwn) anchor = min(anchor, rec_li(r));
-      }
-      W.unit_v[slot] = unit_value(a, D.cfg[x.d], nullptr);
-      W.unit_a[slot] = anchor;  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
-    });
+    const uint2 u = G.hlist[k];
+    UHdr* hp = G.uh + u.x;
+    const uint32_t cnt = hp->n;
+    const URec* run = G.rec + hp->start;
+    UnitAcc a;
+    acc_init(a);
+    uint32_t anchor = kNoAnchor;
+    for (uint32_t i = 0; i < cnt; i++) {
+      const URec r = rec_load(run + i);
+      rec_acc(a, now, r);
+      if (r.lif & kRecOwn) anchor = min(anchor, rec_li(r));
+    }
+    hp->v = unit_value(a, D.cfg[u.y], nullptr);
+    hp->a = anchor;  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
   }
 }
 
-__global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W, DGen G) {
+__global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W, DGen G, int want_best_pair) {
   if (*W.err) return;
   const unsigned int n = *G.ccount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -473,30 +522,26 @@ __global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W,
     const int d = x.d;
     bool have = false;
     int64_t bv = 0;
-    uint32_t ba = 0, brk = 0, bp = kInactive, bslot = 0;
+    uint32_t ba = 0, brk = 0, bp = kInactive, bslot = kInactive, bn = 1, bstart = 0;
     if (!x.own_complex) { have = true; bv = G.tv[t]; ba = li; }  // its own single-task unit, scored by k_gtask
     wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
-      const uint32_t a = W.unit_a[slot];
-      if (a == kNoAnchor) return;
-      const int64_t v = W.unit_v[slot];
-      if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; bp = pair; bslot = slot; }
+      const UHdr h = uh_load(G.uh + slot);  // value, anchor, size, run: one sector
+      if (h.a == kNoAnchor) return;
+      if (!have || h.v > bv || (h.v == bv && h.a < ba)) { have = true; bv = h.v; ba = h.a; bp = pair; bslot = slot; bn = h.n; bstart = h.start; }
     });
-    uint32_t bn = 1;
-    if (bp != kInactive) {  // rank among ALL members of the chosen unit
-      const int32_t my_tgo = T.tgo[t], my_nd = T.numdep[t], my_pr = T.priority[t];
-      const int64_t my_ex = T.expected[t];
-      bn = W.unit_n[bslot];
-      const URec* run = G.rec + W.head[bslot];
+    if (bp != kInactive) {  // rank among ALL members of the chosen unit; the task's own fields are its record in the run
+      const URec* run = G.rec + bstart;
+      URec me = rec_load(run);
+      for (uint32_t i = 1; i < bn && rec_li(me) != li; i++) me = rec_load(run + i);
       for (uint32_t i = 0; i < bn; i++) {
         const URec r = rec_load(run + i);
-        if (in_unit_less(r.tgo, r.nd, r.prio, r.exp_ns, rec_li(r), my_tgo, my_nd, my_pr, my_ex, li)) brk++;
+        if (in_unit_less(r.tgo, r.nd, r.prio, r.exp_ns, rec_li(r), me.tgo, me.nd, me.prio, me.exp_ns, li)) brk++;
       }
-      if (bn <= 64) atomicOr(&W.unit_mask[bslot], 1ull << brk);  // ranks emitted from the unit: k_gplace_disp counts below its own
+      if (bn <= 64) atomicOr(&G.uh[bslot].mask, 1ull << brk);  // ranks emitted from the unit: k_gplace_disp counts below its own
     }
     G.tv[t] = bv;
-    G.tie_a[t] = ba;
-    G.tie_r[t] = brk;
-    W.best_pair[t] = bp;
+    G.tie[t] = make_uint4(ba, brk, bslot, 0u);
+    if (want_best_pair) W.best_pair[t] = bp;  // k_breakdown's way back to the unit
     const bool displaced = !(ba == li && brk == 0);
     if (displaced) W.has_dep[t] |= 2;  // only this thread touches the byte now (k_gmark and k_gtask are done)
     atomicAdd(G.e + x.base + ba, 1u);
@@ -653,6 +698,22 @@ __global__ void __launch_bounds__(256) k_gplace(DDistros D, DWork W, DGen G, int
         }
       }
     }
+  } else if (interior) {  // identity placement: position base + (t - base) = t, and t8 is a multiple of four -> 128-bit stores
+    uint32_t kl[8], kh[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+      const unsigned long long key = vmax_ord - ord_i64(vv[m]);
+      kl[m] = uint32_t(key); kh[m] = uint32_t(key >> 32);
+    }
+    const uint32_t p0 = uint32_t(t8 - base);
+    *reinterpret_cast<uint4*>(G.key_lo[0] + t8) = make_uint4(kl[0], kl[1], kl[2], kl[3]);
+    *reinterpret_cast<uint4*>(G.key_lo[0] + t8 + 4) = make_uint4(kl[4], kl[5], kl[6], kl[7]);
+    *reinterpret_cast<uint4*>(G.idx[0] + t8) = make_uint4(p0, p0 + 1, p0 + 2, p0 + 3);
+    *reinterpret_cast<uint4*>(G.idx[0] + t8 + 4) = make_uint4(p0 + 4, p0 + 5, p0 + 6, p0 + 7);
+    if (wide) {
+      *reinterpret_cast<uint4*>(G.key_hi[0] + t8) = make_uint4(kh[0], kh[1], kh[2], kh[3]);
+      *reinterpret_cast<uint4*>(G.key_hi[0] + t8 + 4) = make_uint4(kh[4], kh[5], kh[6], kh[7]);
+    }
   } else {
 #pragma unroll
     for (int m = 0; m < 8; m++) {
@@ -670,17 +731,17 @@ __global__ void __launch_bounds__(256) k_gplace_disp(DTasks T, DDistros D, DWork
   if (!(W.has_dep[t] & 2)) continue;
   const int d = G.clist_d[k];
   const int64_t base = D.task_off[d];
-  const uint32_t a = G.tie_a[t], myrk = G.tie_r[t];
+  const uint4 tie = G.tie[t];
+  const uint32_t a = tie.x, myrk = tie.y, slot = tie.z;
   uint32_t pos = G.e[base + a];
-  const uint32_t slot = W.pair_slot[W.best_pair[t]];
-  if (W.unit_n[slot] <= 64) {
-    pos += __popcll(W.unit_mask[slot] & ((1ull << myrk) - 1ull));
+  const UHdr h = uh_load(G.uh + slot);
+  if (h.n <= 64) {
+    pos += __popcll(h.mask & ((1ull << myrk) - 1ull));
   } else {
-    const URec* run = G.rec + W.head[slot];
-    const uint32_t cnt = W.unit_n[slot];
-    for (uint32_t i = 0; i < cnt; i++) {
-      const uint32_t tq = uint32_t(base + rec_li(rec_load(run + i)));
-      if (W.best_pair[tq] != kInactive && W.pair_slot[W.best_pair[tq]] == slot && G.tie_r[tq] < myrk) pos++;
+    const URec* run = G.rec + h.start;
+    for (uint32_t i = 0; i < h.n; i++) {
+      const uint4 tq = G.tie[base + rec_li(rec_load(run + i))];
+      if (tq.z == slot && tq.y < myrk) pos++;
     }
   }
   gen_put(G, base, pos, G.vmm[2 * d], gen_bits(G, d) > 32, G.tv[t], uint32_t(int64_t(t) - base));
@@ -763,20 +824,26 @@ __global__ void __launch_bounds__(1024) k_gdscan(int j, const int32_t* __restric
 
 // Warp w ranks chunks 8w .. 8w+7 of the tile in order (stability): one MATCH.ANY per chunk, the group's first lane adds
 // the group size to the warp's digit counter and gets back the count of equal digits in the warp's earlier chunks (as in
-// k_plan_cta).  Thread = digit then turns the 8 per-warp counters into bases on top of the tile's offset for the digit.
+// k_plan_cta).  The tile is then sorted by digit IN SHARED MEMORY and written out in that order: consecutive threads
+// write consecutive addresses inside a digit's run, so a run costs its sectors once -- scattering straight from
+// registers put nearly every 4-byte store in a sector of its own (8.1 M sectors for 9.6 M stores, L2-write bound).
 __global__ void __launch_bounds__(256) k_gscatter(int j, DDistros D, DGen G) {
   if (j >= *G.maxpass) return;
   int d, cnt; int64_t seg, lo; bool wide;
   const int tile = int(blockIdx.x + G.tile0);
   if (!gen_tile(D, G, tile, j, &d, &seg, &lo, &cnt, &wide)) return;
   const int sb = j & 1, db = sb ^ 1;
-  __shared__ uint32_t wcnt[8][256];
+  __shared__ uint32_t wcnt[8][256];   // per-warp digit counters, then local positions
+  __shared__ uint32_t s_lo[kGTile], s_ix[kGTile], s_hi[kGTile];
+  __shared__ int32_t s_delta[256];    // digit -> (offset of the digit's run in the distro) - (its offset in the sorted tile)
+  __shared__ uint32_t s_wsum[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #pragma unroll
-  for (int w = 0; w < 8; w++) wcnt[w][threadIdx.x] = 0u;
+  for (int w = 0; w < 8; w++) wcnt[w][tid] = 0u;
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const int shift = 8 * (j & 3);
+  const bool use_hi = j >= 4;
   const uint32_t* src_lo = G.key_lo[sb] + lo;
   const uint32_t* src_hi = G.key_hi[sb] + lo;
   const uint32_t* src_ix = G.idx[sb] + lo;
@@ -793,7 +860,7 @@ __global__ void __launch_bounds__(256) k_gscatter(int j, DDistros D, DGen G) {
   for (int k = 0; k < 8; k++) {
     const int i = (warp * 8 + k) * 32 + lane;
     const bool ok = i < cnt;
-    dg[k] = ok ? (((j < 4 ? kl[k] : kh[k]) >> shift) & 255u) : 256u;
+    dg[k] = ok ? (((use_hi ? kh[k] : kl[k]) >> shift) & 255u) : 256u;
     const unsigned peers = __match_any_sync(0xffffffffu, dg[k]);
     const uint32_t r = __popc(peers & lt);
     uint32_t old = 0;
@@ -802,23 +869,45 @@ __global__ void __launch_bounds__(256) k_gscatter(int j, DDistros D, DGen G) {
     rk[k] = old + r;
   }
   __syncthreads();
-  {
-    uint32_t run = G.tile_hist[int64_t(tile) * 256 + threadIdx.x];  // the tile's offset for this digit inside the distro
+  {  // thread = digit: the eight warp counters become offsets inside the digit; the digit totals are scanned over the block
+    uint32_t x[8], tot = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) { const uint32_t x = wcnt[w][threadIdx.x]; wcnt[w][threadIdx.x] = run; run += x; }
+    for (int w = 0; w < 8; w++) { x[w] = wcnt[w][tid]; tot += x[w]; }
+    uint32_t inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) before += w < warp ? s_wsum[w] : 0u;
+    const uint32_t lbase = before + inc - tot;  // where digit `tid` starts in the sorted tile
+    s_delta[tid] = int32_t(G.tile_hist[int64_t(tile) * 256 + tid]) - int32_t(lbase);
+    uint32_t run = lbase;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { wcnt[w][tid] = run; run += x[w]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    if (dg[k] < 256u) {
+      const uint32_t lp = wcnt[warp][dg[k]] + rk[k];
+      s_lo[lp] = kl[k];
+      s_ix[lp] = ix[k];
+      if (wide) s_hi[lp] = kh[k];
+    }
   }
   __syncthreads();
   uint32_t* dst_lo = G.key_lo[db] + seg;
   uint32_t* dst_hi = G.key_hi[db] + seg;
   uint32_t* dst_ix = G.idx[db] + seg;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    if (dg[k] < 256u) {
-      const uint32_t pos = wcnt[warp][dg[k]] + rk[k];
-      dst_lo[pos] = kl[k];
-      if (wide) dst_hi[pos] = kh[k];
-      dst_ix[pos] = ix[k];
-    }
+  for (int i = tid; i < cnt; i += 256) {
+    const uint32_t a = s_lo[i], h = wide ? s_hi[i] : 0u;
+    const uint32_t dgt = ((use_hi ? h : a) >> shift) & 255u;
+    const int64_t pos = int64_t(s_delta[dgt]) + i;
+    dst_lo[pos] = a;
+    dst_ix[pos] = s_ix[i];
+    if (wide) dst_hi[pos] = h;
   }
 }
 

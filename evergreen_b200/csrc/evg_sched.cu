@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <type_traits>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -102,6 +103,7 @@ struct DevBuf {
 constexpr int kCapA = 128 * 8, kCapB = 256 * 16, kCapC = EVG_C_THREADS * EVG_C_ITEMS;
 constexpr int64_t kWideAllocGroups = 1024;  // k_alloc<128> (a block per distro) once some distro has more task groups
 constexpr int kCapW = 32;  // k_plan_warp: one warp per distro
+constexpr int64_t kSparseClass = 64;  // a k_plan_smem class of 1025+ task distros with fewer members than this goes to the general path
 // second-generation on-chip planner classes <THREADS, CAP, CTAs per SM> (evg_plan_cta.cuh)
 constexpr int kNT_A = 128, kNCapA = 1280, kNOccA = 8;
 constexpr int kNT_B = 256, kNCapB = 5120, kNOccB = 4;
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(256) k_dur_final(DDur X, evg_duration_stat* ou
 
 // The 13-field SortingValueBreakdown of the unit each ranked task was emitted
 // from (planner.go:472-476, model/task/task.go:3990-4038); both paths.
-__global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W, const URec* rec, int64_t now, int any_complex,
+__global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W, const URec* rec, const UHdr* uh, int64_t now, int any_complex,
                                                    const int32_t* order, int64_t* breakdown) {
   if (*W.err) return;
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -515,10 +517,9 @@ __global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W
       acc_add(a, now, T.priority[tq], T.expected[tq], T.qbasis[tq], T.numdep[tq], T.gid[tq], T.flags[tq]);
     }
   } else {  // general path: the unit table
-    const uint32_t slot = W.pair_slot[bp];
-    const URec* run = rec + W.head[slot];
-    const uint32_t cnt = W.unit_n[slot];
-    for (uint32_t i = 0; i < cnt; i++) rec_acc(a, now, rec_load(run + i));
+    const UHdr h = uh_load(uh + W.pair_slot[bp]);
+    const URec* run = rec + h.start;
+    for (uint32_t i = 0; i < h.n; i++) rec_acc(a, now, rec_load(run + i));
   }
   int64_t bd[EVG_BD_N];
   unit_value(a, D.cfg[d], bd);
@@ -741,7 +742,7 @@ struct evg_ctx {
   int general_complex = 0;
   int64_t Tgc = 0;  // tasks in general-path distros that can hold multi-member units (work-list capacity)
   DevBuf b_kv, b_vmm, b_klo[2], b_khi[2], b_ix[2], b_e, b_tilesum, b_gmisc;
-  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist, b_rec;
+  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist, b_rec, b_tie, b_uh, b_hlist;
   DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
   DevBuf b_hflags, b_hgid, b_hexp, b_hstd, b_hstart, b_hostoff, b_acfg, b_gs, b_result, b_status;
   bool bd_valid = false;
@@ -787,38 +788,67 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   int any_complex = E > 0 ? 1 : 0;
   int64_t Tgc = 0, Prec = 0;
   constexpr int kGA = PlanCta<kNT_A, kNCapA>::kGroupCap, kGB = PlanCta<kNT_B, kNCapB>::kGroupCap, kGC = PlanCta<kNT_C, kNCapC>::kGroupCap;
+  // Size class of distro d (no side effects): W warp, 1..3 k_plan_cta classes, 4..6 k_plan_smem classes, 7 general path.
+  auto classify = [&](int32_t d) -> int {
+    const int64_t a = dt->task_off[d], b = dt->task_off[d + 1];
+    const int64_t n = b - a, g = dt->group_off[d + 1] - dt->group_off[d];
+    const evg_distro_cfg& cf = dt->cfg[d];
+    const int64_t de = (E > 0) ? (edge_off ? edge_off[d + 1] - edge_off[d] : t->dep_off[b] - t->dep_off[a]) : 0;
+    const bool narrow = !cf.group_versions && de == 0;  // k_plan_cta: task groups are the only multi-member units it knows
+    if (n <= kCapW) return 0;
+    if (narrow && n <= kNCapA && g <= kGA) return 1;
+    if (narrow && n <= kNCapB && g <= kGB) return 2;
+    if (narrow && n <= kNCapC && g <= kGC) return 3;
+    if (n <= kCapA) return 4;
+    if (n <= kCapB) return 5;
+    if (n <= kCapC) return 6;
+    return 7;
+  };
+  // k_plan_smem walks the unit lists of GroupVersions / dependency distros with ONE CTA per distro: fine when a class
+  // has enough distros to fill the GPU, a millisecond-long tail when it has a handful (configs[4]: ~20 distros of 1-6k
+  // tasks held the whole tick).  The general path spreads every distro over all SMs, so sparse classes go there.
+  int64_t n_class[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int32_t d = 0; d < D; d++) {
+    const int64_t a = dt->task_off[d], b = dt->task_off[d + 1];
+    if (d == 0 && (a != 0 || dt->group_off[0] != 0)) return fail(EVG_ERR_INVALID, "offsets must start at 0");
+    if (b < a || dt->group_off[d + 1] < dt->group_off[d]) return fail(EVG_ERR_INVALID, "offsets of distro %d decrease", d);
+    if (b > T) return fail(EVG_ERR_INVALID, "task_off of distro %d exceeds n_tasks", d);
+    n_class[classify(d)]++;
+  }
+  const char* sparse_env = getenv("EVG_SPARSE_CLASS");  // tests set 0 to keep every class on its own kernel
+  const int64_t sparse = sparse_env ? atoll(sparse_env) : kSparseClass;
+  const bool sparse_b = n_class[5] > 0 && n_class[5] < sparse, sparse_c = n_class[6] > 0 && n_class[6] < sparse;
   for (int32_t d = 0; d < D; d++) {
     const int64_t a = dt->task_off[d], b = dt->task_off[d + 1];
     const int64_t ga = dt->group_off[d], gb = dt->group_off[d + 1];
-    if (d == 0 && (a != 0 || ga != 0)) return fail(EVG_ERR_INVALID, "offsets must start at 0");
-    if (b < a || gb < ga) return fail(EVG_ERR_INVALID, "offsets of distro %d decrease", d);
     if (b - a > kMaxTasksPerDistro) return fail(EVG_ERR_INVALID, "distro %d holds %lld tasks (max %lld)", d, (long long)(b - a), (long long)kMaxTasksPerDistro);
-    if (b > T) return fail(EVG_ERR_INVALID, "task_off of distro %d exceeds n_tasks", d);
     const evg_distro_cfg& cf = dt->cfg[d];
     if (cf.n_versions < 0) return fail(EVG_ERR_INVALID, "distro %d: negative n_versions", d);
     if (gb > ga || cf.group_versions) any_complex = 1;
     unit_base[d + 1] = unit_base[d] + (gb - ga) + (cf.group_versions ? int64_t(cf.n_versions) : (b - a));
-    const int64_t n = b - a, g = gb - ga;
+    const int64_t n = b - a;
     const int64_t de = (E > 0) ? (edge_off ? edge_off[d + 1] - edge_off[d] : t->dep_off[b] - t->dep_off[a]) : 0;
-    // second-generation on-chip planner: task groups are the only multi-member units it knows
-    const bool narrow = !cf.group_versions && de == 0;
-    if (n <= kCapW) { listW.push_back(d); route[d] = 1; }
-    else if (narrow && n <= kNCapA && g <= kGA) { listNA.push_back(d); route[d] = 1; }
-    else if (narrow && n <= kNCapB && g <= kGB) { listNB.push_back(d); route[d] = 1; }
-    else if (narrow && n <= kNCapC && g <= kGC) { listNC.push_back(d); route[d] = 1; }
-    else if (n <= kCapA) { listA.push_back(d); route[d] = 1; }
-    else if (n <= kCapB) { listB.push_back(d); route[d] = 1; }
-    else if (n <= kCapC) { listC.push_back(d); route[d] = 1; }
-    else {
-      n_general++;
-      listG.push_back(d);
-      if (gb > ga || cf.group_versions || de > 0) {
-        general_complex = 1;
-        Tgc += n;
-        Prec += n + ((cf.group_versions && gb > ga) ? n : 0) + de;  // own-key, version and dependency memberships at most
+    int cls = classify(d);
+    if ((cls == 5 && sparse_b) || (cls == 6 && sparse_c)) cls = 7;
+    switch (cls) {
+      case 0: listW.push_back(d); route[d] = 1; break;
+      case 1: listNA.push_back(d); route[d] = 1; break;
+      case 2: listNB.push_back(d); route[d] = 1; break;
+      case 3: listNC.push_back(d); route[d] = 1; break;
+      case 4: listA.push_back(d); route[d] = 1; break;
+      case 5: listB.push_back(d); route[d] = 1; break;
+      case 6: listC.push_back(d); route[d] = 1; break;
+      default: {
+        n_general++;
+        listG.push_back(d);
+        if (gb > ga || cf.group_versions || de > 0) {
+          general_complex = 1;
+          Tgc += n;
+          Prec += n + ((cf.group_versions && gb > ga) ? n : 0) + de;  // own-key, version and dependency memberships at most
+        }
+        const int64_t a0 = a & ~int64_t(3);  // tiles start 16-byte aligned in every column
+        for (int64_t s = a0; s < b; s += kGTile) { tile_distro.push_back(d); tile_start.push_back(s); }
       }
-      const int64_t a0 = a & ~int64_t(3);  // tiles start 16-byte aligned in every column
-      for (int64_t s = a0; s < b; s += kGTile) { tile_distro.push_back(d); tile_start.push_back(s); }
     }
     dtile_off[d + 1] = int64_t(tile_distro.size());
   }
@@ -909,8 +939,9 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
       CK(c->b_e.ensure(sizeof(uint32_t) * size_t(T + kColPad)));
       CK(c->b_clist.ensure(sizeof(uint32_t) * 2 * size_t(Tgc + 1)));
       CK(c->b_rec.ensure(sizeof(URec) * size_t(Prec + 1)));
-      CK(c->b_ca.ensure(sizeof(uint32_t) * size_t(T + 1)));
-      CK(c->b_crk.ensure(sizeof(uint32_t) * size_t(T + 1)));
+      CK(c->b_hlist.ensure(sizeof(uint2) * size_t(Prec + 1)));
+      CK(c->b_tie.ensure(sizeof(uint4) * size_t(T + 1)));
+      CK(c->b_uh.ensure(sizeof(UHdr) * size_t(U + 1)));
     }
   }
   CK(c->b_punt.ensure(sizeof(int32_t) * size_t(D + 1)));
@@ -1031,8 +1062,10 @@ DGen dgen(const evg_ctx* c) {
   g.ccount = c->b_gmisc.as<unsigned int>();
   g.maxpass = c->b_gmisc.as<int32_t>() + 1;
   g.rcount = c->b_gmisc.as<unsigned int>() + 2;
+  g.hcount = c->b_gmisc.as<unsigned int>() + 3;
+  g.hlist = c->b_hlist.as<uint2>();
   g.rec = c->b_rec.as<URec>();
-  g.tie_a = c->b_ca.as<uint32_t>(); g.tie_r = c->b_crk.as<uint32_t>();
+  g.tie = c->b_tie.as<uint4>(); g.uh = c->b_uh.as<UHdr>();
   g.tv = c->b_tv.as<int64_t>();
   return g;
 }
@@ -1114,8 +1147,7 @@ int prepare_general(evg_ctx* c, cudaStream_t s, int32_t d0, int32_t d1) {
   if (c->general_complex) {
     const size_t nt = size_t(t1 - t0);
     CK(cudaMemsetAsync(c->b_hasdep.as<uint8_t>() + t0, 0, nt, s));
-    CK(cudaMemsetAsync(c->b_unitn.as<uint32_t>() + u0, 0, sizeof(uint32_t) * size_t(u1 - u0), s));   // members drawn so far
-    CK(cudaMemsetAsync(c->b_unitmask.as<uint64_t>() + u0, 0, sizeof(uint64_t) * size_t(u1 - u0), s));
+    CK(cudaMemsetAsync(c->b_uh.as<UHdr>() + u0, 0, sizeof(UHdr) * size_t(u1 - u0), s));   // members drawn so far, rank masks
   }
   return EVG_OK;
 }
@@ -1140,8 +1172,8 @@ int run_general(evg_ctx* c, cudaStream_t st, const DTasks& dt, const DDistros& d
     LAUNCH_ON(c, st, k_glink, wl_grid, 256, dt, dd, w, g, now);
     LAUNCH_ON(c, st, k_galloc, wl_grid, 256, dt, dd, w, g);
     LAUNCH_ON(c, st, k_gfill, wl_grid, 256, dt, dd, w, g);
-    LAUNCH_ON(c, st, k_gunit, wl_grid, 256, dt, dd, w, g, now);
-    LAUNCH_ON(c, st, k_gbest, wl_grid, 256, dt, dd, w, g);
+    LAUNCH_ON(c, st, k_gunit, wl_grid, 256, dd, w, g, now);
+    LAUNCH_ON(c, st, k_gbest, wl_grid, 256, dt, dd, w, g, c->bd_valid ? 1 : 0);
   }
   LAUNCH_ON(c, st, k_gsched, grid_for(gcount, 128), 128, g, gl, gcount);
   if (gc) {
@@ -1248,7 +1280,7 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
       CK(cudaStreamWaitEvent(s, c->ev_join[k], 0));
     }
   }
-  if (bd) LAUNCH(c, k_breakdown, grid_for(T, 256), 256, dt, dd, w, c->b_rec.as<URec>(), now, c->any_complex, c->b_order.as<int32_t>(), bd);
+  if (bd) LAUNCH(c, k_breakdown, grid_for(T, 256), 256, dt, dd, w, c->b_rec.as<URec>(), c->b_uh.as<UHdr>(), now, c->any_complex, c->b_order.as<int32_t>(), bd);
   CK(cudaGetLastError());
   return EVG_OK;
 }
@@ -1298,7 +1330,7 @@ void evg_shutdown(evg_ctx* c) {
                    &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_listG, &c->b_listNA, &c->b_listNB,
                    &c->b_listNC, &c->b_punt, &c->b_puntcnt, &c->b_ca, &c->b_crk, &c->b_bestpair, &c->b_kv, &c->b_vmm,
                    &c->b_klo[0], &c->b_klo[1], &c->b_khi[0], &c->b_khi[1], &c->b_ix[0], &c->b_ix[1], &c->b_e, &c->b_tilesum,
-                   &c->b_gmisc, &c->b_clist, &c->b_rec, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
+                   &c->b_gmisc, &c->b_clist, &c->b_rec, &c->b_tie, &c->b_uh, &c->b_hlist, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
                    &c->b_hstart, &c->b_hostoff, &c->b_acfg, &c->b_gs, &c->b_result, &c->b_status};
   for (DevBuf* b : all) b->release();

@@ -19,6 +19,10 @@ if which == "c3":
     w = synth.config(3, 0.0048, each=True)
 elif which == "1m":
     w = synth.config(4, 0.0008, each=True)
+elif which == "c5":  # BASELINE configs[4]: 100k power-law distros, every route in one tick
+    w = synth.config(5)
+elif which == "c2":
+    w = synth.config(2)
 else:
     w = synth.make(np.full(48, 100000), synth.SEED_BASE + 3, tg_frac=0.0, zipf_priority=True, n_hosts=96)
 eng.upload(w.tasks, w.distros, w.hosts)

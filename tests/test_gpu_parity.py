@@ -738,6 +738,24 @@ def test_cta_class_boundaries(engine):
     parity.check_against_oracle(w, po, ao)
 
 
+def test_sparse_classes_on_their_own_kernels(engine, monkeypatch):
+    """A k_plan_smem class of 1025+ task distros that cannot fill the GPU is planned by the general path
+    (EVG_SPARSE_CLASS, default 64).  With the rule switched off every class runs on its own kernel: both
+    routings must give the oracle's answer on the same ticks."""
+    sizes = np.array([33, 1023, 1025, 4095, 4096, 4097, 10241, 12288, 12289, 700, 2500, 9000])
+    for seed, kw in ((211, dict(met_dep_frac=0.03, unmet_dep_frac=0.02, includes_dependencies=True)),
+                     (212, dict(group_versions_frac=1.0)), (213, dict(met_dep_frac=0.02, group_versions_frac=0.5))):
+        w = synth.make(sizes, seed, zipf_priority=True, tg_frac=0.15, n_hosts=80, **kw)
+        for rule in ("0", "64"):
+            monkeypatch.setenv("EVG_SPARSE_CLASS", rule)
+            po, ao = run(engine, w)
+            parity.check_against_oracle(w, po, ao)
+            pb, _ = run(engine, w, breakdown=True)
+            ref = parity.check_against_oracle(w, pb, None)
+            assert np.array_equal(pb.breakdown, ref["breakdown"])  # the general path's breakdown reads the unit table
+    monkeypatch.delenv("EVG_SPARSE_CLASS")
+
+
 def test_cta_misaligned_distro_starts(engine):
     """TMA tiles start at multiples of four tasks; distros start anywhere.  Every start residue mod 4, first and
     last distro of the table, sizes around one and two tiles of each class."""
