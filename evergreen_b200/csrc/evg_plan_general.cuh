@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256, EVG_GTASK_OCC) k_gtask(DTasks T, DDistros
     }
     // TotalValue of single-task units (also the own-unit candidate of a task that only joins other units by edges)
     if (!live) {
-    } else if (t4 >= base && t4 + 3 < end && wr_v[0] && wr_v[1] && wr_v[2] && wr_v[3]) {
+    } else if (t4 >= base && t4 + 3 < end) {  // whole sectors even when some of the four are multi-member-unit tasks: k_gbest rewrites theirs
       *reinterpret_cast<longlong2*>(G.tv + t4) = make_longlong2(vout[0], vout[1]);
       *reinterpret_cast<longlong2*>(G.tv + t4 + 2) = make_longlong2(vout[2], vout[3]);
     } else {
@@ -678,24 +678,50 @@ __global__ void __launch_bounds__(256) k_gplace(DDistros D, DWork W, DGen G, int
     }
   }
   if (use_e) {
-    if (interior) {
-      uint32_t ps[8];
+    // The tile's own-anchor tasks land in ONE contiguous stretch of the distro's segment, [tile_sum[tile], + sum of e over
+    // the tile), with holes where displaced tasks will be put by k_gplace_disp.  They are staged in shared memory and
+    // the stretch is written out whole (holes included: k_gplace_disp runs later and fills them): 4-byte stores
+    // straight from registers cost a sector each (8.6 M sectors for 1.2 M sectors of payload).
+    constexpr int kStage = 3072;
+    __shared__ uint32_t st_lo[kStage], st_ix[kStage], st_hi[kStage];
+    __shared__ uint32_t s_total;
+    const uint32_t p_tile = G.tile_sum[tile];
+    if (tid == 255) s_total = run + sum - p_tile;  // `run` is this thread's exclusive offset: the last thread knows the tile's total
+    uint32_t ps[8];
 #pragma unroll
-      for (int m = 0; m < 8; m++) { ps[m] = run; run += ev[m]; }
+    for (int m = 0; m < 8; m++) { ps[m] = run; run += ev[m]; }
+    if (interior) {
       *reinterpret_cast<uint4*>(G.e + t8) = make_uint4(ps[0], ps[1], ps[2], ps[3]);
       *reinterpret_cast<uint4*>(G.e + t8 + 4) = make_uint4(ps[4], ps[5], ps[6], ps[7]);
-#pragma unroll
-      for (int m = 0; m < 8; m++)
-        if (!((dsp >> m) & 1u)) gen_put(G, base, ps[m], vmax_ord, wide, vv[m], uint32_t(t8 + m - base));
     } else {
 #pragma unroll
-      for (int m = 0; m < 8; m++) {
-        const int64_t t = t8 + m;
-        if (t >= base && t < end) {
-          G.e[t] = run;
-          if (!((dsp >> m) & 1u)) gen_put(G, base, run, vmax_ord, wide, vv[m], uint32_t(t - base));
-          run += ev[m];
+      for (int m = 0; m < 8; m++) { const int64_t t = t8 + m; if (t >= base && t < end) G.e[t] = ps[m]; }
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    const bool staged = total <= uint32_t(kStage);  // block-uniform
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+      const int64_t t = t8 + m;
+      if (t >= base && t < end && !((dsp >> m) & 1u)) {
+        if (staged) {
+          const unsigned long long key = vmax_ord - ord_i64(vv[m]);
+          const uint32_t q = ps[m] - p_tile;
+          st_lo[q] = uint32_t(key); st_ix[q] = uint32_t(t - base);
+          if (wide) st_hi[q] = uint32_t(key >> 32);
+        } else {
+          gen_put(G, base, ps[m], vmax_ord, wide, vv[m], uint32_t(t - base));
         }
+      }
+    }
+    if (staged) {
+      __syncthreads();
+      uint32_t* dlo = G.key_lo[0] + base + p_tile;
+      uint32_t* dix = G.idx[0] + base + p_tile;
+      uint32_t* dhi = G.key_hi[0] + base + p_tile;
+      for (uint32_t q = tid; q < total; q += 256) {
+        dlo[q] = st_lo[q]; dix[q] = st_ix[q];
+        if (wide) dhi[q] = st_hi[q];
       }
     }
   } else if (interior) {  // identity placement: position base + (t - base) = t, and t8 is a multiple of four -> 128-bit stores
