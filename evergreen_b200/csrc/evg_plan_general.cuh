@@ -46,7 +46,6 @@ struct DGen {
   unsigned int* ccount;        // [1]
   uint4* tie;                  // [T] work-list tasks: x = anchor of the unit the task is emitted from, y = rank inside it,
                                //     z = that unit's slot (kInactive: its own single-task unit)
-  struct UHdr* uh;             // [unit slots] header of every multi-member unit (one sector)
   int32_t* maxpass;            // [1]
   struct URec* rec;            // unit table: the members of every multi-member unit, one contiguous run per unit
   unsigned int* rcount;        // [1] records reserved
@@ -323,22 +322,6 @@ struct __align__(16) URec {
   uint32_t lif;  // bits 0..20 distro-local task index, 21 own-key pair, 22 group_id >= 0, 24..29 task flags
 };
 static_assert(sizeof(URec) == 32, "one L2 sector per member");
-struct __align__(16) UHdr {  // what used to be five slot-indexed arrays (five sectors per visit)
-  int64_t v;                 // TotalValue (k_gunit)
-  uint32_t a;                // anchor; kNoAnchor: never exported
-  uint32_t n;                // members (k_glink counts them in)
-  uint32_t start;            // first record of the run (k_galloc)
-  uint32_t pad;
-  unsigned long long mask;   // ranks emitted from the unit (units of <= 64 members; k_gbest)
-};
-static_assert(sizeof(UHdr) == 32, "one L2 sector per unit");
-__device__ __forceinline__ UHdr uh_load(const UHdr* p) {
-  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
-  UHdr h;
-  h.v = int64_t((unsigned long long)a.x | ((unsigned long long)a.y << 32)); h.a = a.z; h.n = a.w;
-  h.start = b.x; h.pad = b.y; h.mask = (unsigned long long)b.z | ((unsigned long long)b.w << 32);
-  return h;
-}
 constexpr uint32_t kRecOwn = 1u << 21, kRecGrouped = 1u << 22;
 __device__ __forceinline__ uint32_t rec_li(const URec& r) { return r.lif & 0x1FFFFFu; }
 __device__ __forceinline__ URec rec_load(const URec* p) {  // two 128-bit loads
@@ -407,7 +390,7 @@ __global__ void __launch_bounds__(256, 4) k_glink(DTasks T, DDistros D, DWork W,
     }
     auto join = [&](uint32_t pair, uint32_t slot) {
       W.pair_slot[pair] = slot;
-      W.next[pair] = atomicAdd(&G.uh[slot].n, 1u);  // the pair's place in the unit's run
+      W.next[pair] = atomicAdd(W.unit_n + slot, 1u);  // the pair's place in the unit's run
     };
     if (x.own_complex) join(t, x.ub + x.s_own);
     if (x.s_ver != kInactive) join(uint32_t(T.n + t), x.ub + x.s_ver);  // planner.go:439
@@ -443,7 +426,7 @@ __global__ void __launch_bounds__(256, 4) k_galloc(DTasks T, DDistros D, DWork W
     uint32_t need = 0, heads = 0;  // records / units this thread's k == 0 pairs stand for
     if (k < n) {
       x = wl_task(T, D, W, G, k);
-      wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) { if (W.next[pair] == 0u) { need += G.uh[slot].n; heads++; } });
+      wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) { if (W.next[pair] == 0u) { need += W.unit_n[slot]; heads++; } });
     }
     uint32_t inc = need, hinc = heads;
 #pragma unroll
@@ -464,7 +447,7 @@ __global__ void __launch_bounds__(256, 4) k_galloc(DTasks T, DDistros D, DWork W
     if (heads) {
       uint32_t pos = s_base + before + inc - need, hp = s_hbase + hbefore + hinc - heads;
       wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
-        if (W.next[pair] == 0u) { G.uh[slot].start = pos; pos += G.uh[slot].n; G.hlist[hp++] = make_uint2(slot, uint32_t(x.d)); }
+        if (W.next[pair] == 0u) { W.head[slot] = pos; pos += W.unit_n[slot]; G.hlist[hp++] = make_uint2(slot, uint32_t(x.d)); }
       });
     }
     __syncthreads();  // the shared scratch is rewritten by the next trip
@@ -482,7 +465,7 @@ __global__ void __launch_bounds__(256, 4) k_gfill(DTasks T, DDistros D, DWork W,
     wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
       URec q = r;
       if (pair < uint32_t(T.n)) q.lif |= kRecOwn;  // own-key pairs are the SetDistro members (planner.go:446)
-      rec_store(G.rec + G.uh[slot].start + W.next[pair], q);
+      rec_store(G.rec + W.head[slot] + W.next[pair], q);
     });
   }
 }
@@ -497,9 +480,8 @@ __global__ void __launch_bounds__(256, 4) k_gunit(DDistros D, DWork W, DGen G, i
   const unsigned int n = *G.hcount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {  // the host cannot know n: fixed grid
     const uint2 u = G.hlist[k];
-    UHdr* hp = G.uh + u.x;
-    const uint32_t cnt = hp->n;
-    const URec* run = G.rec + hp->start;
+    const uint32_t cnt = W.unit_n[u.x];
+    const URec* run = G.rec + W.head[u.x];
     UnitAcc a;
     acc_init(a);
     uint32_t anchor = kNoAnchor;
@@ -508,8 +490,8 @@ __global__ void __launch_bounds__(256, 4) k_gunit(DDistros D, DWork W, DGen G, i
       rec_acc(a, now, r);
       if (r.lif & kRecOwn) anchor = min(anchor, rec_li(r));
     }
-    hp->v = unit_value(a, D.cfg[u.y], nullptr);
-    hp->a = anchor;  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
+    W.unit_v[u.x] = unit_value(a, D.cfg[u.y], nullptr);
+    W.unit_a[u.x] = anchor;  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
   }
 }
 
@@ -522,22 +504,24 @@ __global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W,
     const int d = x.d;
     bool have = false;
     int64_t bv = 0;
-    uint32_t ba = 0, brk = 0, bp = kInactive, bslot = kInactive, bn = 1, bstart = 0;
+    uint32_t ba = 0, brk = 0, bp = kInactive, bslot = kInactive, bn = 1;
     if (!x.own_complex) { have = true; bv = G.tv[t]; ba = li; }  // its own single-task unit, scored by k_gtask
     wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
-      const UHdr h = uh_load(G.uh + slot);  // value, anchor, size, run: one sector
-      if (h.a == kNoAnchor) return;
-      if (!have || h.v > bv || (h.v == bv && h.a < ba)) { have = true; bv = h.v; ba = h.a; bp = pair; bslot = slot; bn = h.n; bstart = h.start; }
+      const uint32_t a = W.unit_a[slot];
+      if (a == kNoAnchor) return;
+      const int64_t v = W.unit_v[slot];
+      if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; bp = pair; bslot = slot; }
     });
     if (bp != kInactive) {  // rank among ALL members of the chosen unit; the task's own fields are its record in the run
-      const URec* run = G.rec + bstart;
+      bn = W.unit_n[bslot];
+      const URec* run = G.rec + W.head[bslot];
       URec me = rec_load(run);
       for (uint32_t i = 1; i < bn && rec_li(me) != li; i++) me = rec_load(run + i);
       for (uint32_t i = 0; i < bn; i++) {
         const URec r = rec_load(run + i);
         if (in_unit_less(r.tgo, r.nd, r.prio, r.exp_ns, rec_li(r), me.tgo, me.nd, me.prio, me.exp_ns, li)) brk++;
       }
-      if (bn <= 64) atomicOr(&G.uh[bslot].mask, 1ull << brk);  // ranks emitted from the unit: k_gplace_disp counts below its own
+      if (bn <= 64) atomicOr(&W.unit_mask[bslot], 1ull << brk);  // ranks emitted from the unit: k_gplace_disp counts below its own
     }
     G.tv[t] = bv;
     G.tie[t] = make_uint4(ba, brk, bslot, 0u);
@@ -760,12 +744,12 @@ __global__ void __launch_bounds__(256) k_gplace_disp(DTasks T, DDistros D, DWork
   const uint4 tie = G.tie[t];
   const uint32_t a = tie.x, myrk = tie.y, slot = tie.z;
   uint32_t pos = G.e[base + a];
-  const UHdr h = uh_load(G.uh + slot);
-  if (h.n <= 64) {
-    pos += __popcll(h.mask & ((1ull << myrk) - 1ull));
+  const uint32_t cnt = W.unit_n[slot];
+  if (cnt <= 64) {
+    pos += __popcll(W.unit_mask[slot] & ((1ull << myrk) - 1ull));
   } else {
-    const URec* run = G.rec + h.start;
-    for (uint32_t i = 0; i < h.n; i++) {
+    const URec* run = G.rec + W.head[slot];
+    for (uint32_t i = 0; i < cnt; i++) {
       const uint4 tq = G.tie[base + rec_li(rec_load(run + i))];
       if (tq.z == slot && tq.y < myrk) pos++;
     }

@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(256) k_dur_final(DDur X, evg_duration_stat* ou
 
 // The 13-field SortingValueBreakdown of the unit each ranked task was emitted
 // from (planner.go:472-476, model/task/task.go:3990-4038); both paths.
-__global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W, const URec* rec, const UHdr* uh, int64_t now, int any_complex,
+__global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W, const URec* rec, int64_t now, int any_complex,
                                                    const int32_t* order, int64_t* breakdown) {
   if (*W.err) return;
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -517,9 +517,10 @@ __global__ void __launch_bounds__(256) k_breakdown(DTasks T, DDistros D, DWork W
       acc_add(a, now, T.priority[tq], T.expected[tq], T.qbasis[tq], T.numdep[tq], T.gid[tq], T.flags[tq]);
     }
   } else {  // general path: the unit table
-    const UHdr h = uh_load(uh + W.pair_slot[bp]);
-    const URec* run = rec + h.start;
-    for (uint32_t i = 0; i < h.n; i++) rec_acc(a, now, rec_load(run + i));
+    const uint32_t slot = W.pair_slot[bp];
+    const URec* run = rec + W.head[slot];
+    const uint32_t cnt = W.unit_n[slot];
+    for (uint32_t i = 0; i < cnt; i++) rec_acc(a, now, rec_load(run + i));
   }
   int64_t bd[EVG_BD_N];
   unit_value(a, D.cfg[d], bd);
@@ -742,7 +743,7 @@ struct evg_ctx {
   int general_complex = 0;
   int64_t Tgc = 0;  // tasks in general-path distros that can hold multi-member units (work-list capacity)
   DevBuf b_kv, b_vmm, b_klo[2], b_khi[2], b_ix[2], b_e, b_tilesum, b_gmisc;
-  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist, b_rec, b_tie, b_uh, b_hlist;
+  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist, b_rec, b_tie, b_hlist;
   DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
   DevBuf b_hflags, b_hgid, b_hexp, b_hstd, b_hstart, b_hostoff, b_acfg, b_gs, b_result, b_status;
   bool bd_valid = false;
@@ -941,7 +942,6 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
       CK(c->b_rec.ensure(sizeof(URec) * size_t(Prec + 1)));
       CK(c->b_hlist.ensure(sizeof(uint2) * size_t(Prec + 1)));
       CK(c->b_tie.ensure(sizeof(uint4) * size_t(T + 1)));
-      CK(c->b_uh.ensure(sizeof(UHdr) * size_t(U + 1)));
     }
   }
   CK(c->b_punt.ensure(sizeof(int32_t) * size_t(D + 1)));
@@ -1065,7 +1065,7 @@ DGen dgen(const evg_ctx* c) {
   g.hcount = c->b_gmisc.as<unsigned int>() + 3;
   g.hlist = c->b_hlist.as<uint2>();
   g.rec = c->b_rec.as<URec>();
-  g.tie = c->b_tie.as<uint4>(); g.uh = c->b_uh.as<UHdr>();
+  g.tie = c->b_tie.as<uint4>();
   g.tv = c->b_tv.as<int64_t>();
   return g;
 }
@@ -1147,7 +1147,8 @@ int prepare_general(evg_ctx* c, cudaStream_t s, int32_t d0, int32_t d1) {
   if (c->general_complex) {
     const size_t nt = size_t(t1 - t0);
     CK(cudaMemsetAsync(c->b_hasdep.as<uint8_t>() + t0, 0, nt, s));
-    CK(cudaMemsetAsync(c->b_uh.as<UHdr>() + u0, 0, sizeof(UHdr) * size_t(u1 - u0), s));   // members drawn so far, rank masks
+    CK(cudaMemsetAsync(c->b_unitn.as<uint32_t>() + u0, 0, sizeof(uint32_t) * size_t(u1 - u0), s));   // members drawn so far
+    CK(cudaMemsetAsync(c->b_unitmask.as<uint64_t>() + u0, 0, sizeof(uint64_t) * size_t(u1 - u0), s));
   }
   return EVG_OK;
 }
@@ -1280,7 +1281,7 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
       CK(cudaStreamWaitEvent(s, c->ev_join[k], 0));
     }
   }
-  if (bd) LAUNCH(c, k_breakdown, grid_for(T, 256), 256, dt, dd, w, c->b_rec.as<URec>(), c->b_uh.as<UHdr>(), now, c->any_complex, c->b_order.as<int32_t>(), bd);
+  if (bd) LAUNCH(c, k_breakdown, grid_for(T, 256), 256, dt, dd, w, c->b_rec.as<URec>(), now, c->any_complex, c->b_order.as<int32_t>(), bd);
   CK(cudaGetLastError());
   return EVG_OK;
 }
@@ -1330,7 +1331,7 @@ void evg_shutdown(evg_ctx* c) {
                    &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_listG, &c->b_listNA, &c->b_listNB,
                    &c->b_listNC, &c->b_punt, &c->b_puntcnt, &c->b_ca, &c->b_crk, &c->b_bestpair, &c->b_kv, &c->b_vmm,
                    &c->b_klo[0], &c->b_klo[1], &c->b_khi[0], &c->b_khi[1], &c->b_ix[0], &c->b_ix[1], &c->b_e, &c->b_tilesum,
-                   &c->b_gmisc, &c->b_clist, &c->b_rec, &c->b_tie, &c->b_uh, &c->b_hlist, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
+                   &c->b_gmisc, &c->b_clist, &c->b_rec, &c->b_tie, &c->b_hlist, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
                    &c->b_hstart, &c->b_hostoff, &c->b_acfg, &c->b_gs, &c->b_result, &c->b_status};
   for (DevBuf* b : all) b->release();
