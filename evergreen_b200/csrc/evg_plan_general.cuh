@@ -49,6 +49,8 @@ struct DGen {
   int32_t* maxpass;            // [1]
   struct URec* rec;            // unit table: the members of every multi-member unit, one contiguous run per unit
   unsigned int* rcount;        // [1] records reserved
+  uint4* usum;                 // [unit slots] what k_gbest asks of a candidate unit, in one 16-byte load: x|y<<32 = TotalValue, z = anchor
+                               //     (kNoAnchor: never exported), w = members
   uint2* hlist;                // multi-member units of the tick: x = slot, y = distro (k_galloc lists them, k_gunit folds them)
   unsigned int* hcount;        // [1]
   int64_t* tv;                 // [T] TotalValue by task (the output buffer, reused)
@@ -490,8 +492,8 @@ __global__ void __launch_bounds__(256, 4) k_gunit(DDistros D, DWork W, DGen G, i
       rec_acc(a, now, r);
       if (r.lif & kRecOwn) anchor = min(anchor, rec_li(r));
     }
-    W.unit_v[u.x] = unit_value(a, D.cfg[u.y], nullptr);
-    W.unit_a[u.x] = anchor;  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
+    const unsigned long long v = (unsigned long long)unit_value(a, D.cfg[u.y], nullptr);
+    G.usum[u.x] = make_uint4(uint32_t(v), uint32_t(v >> 32), anchor, cnt);  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
   }
 }
 
@@ -507,13 +509,13 @@ __global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W,
     uint32_t ba = 0, brk = 0, bp = kInactive, bslot = kInactive, bn = 1;
     if (!x.own_complex) { have = true; bv = G.tv[t]; ba = li; }  // its own single-task unit, scored by k_gtask
     wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
-      const uint32_t a = W.unit_a[slot];
+      const uint4 u = G.usum[slot];
+      const uint32_t a = u.z;
       if (a == kNoAnchor) return;
-      const int64_t v = W.unit_v[slot];
-      if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; bp = pair; bslot = slot; }
+      const int64_t v = int64_t((unsigned long long)u.x | ((unsigned long long)u.y << 32));
+      if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; bp = pair; bslot = slot; bn = u.w; }
     });
     if (bp != kInactive) {  // rank among ALL members of the chosen unit; the task's own fields are its record in the run
-      bn = W.unit_n[bslot];
       const URec* run = G.rec + W.head[bslot];
       URec me = rec_load(run);
       for (uint32_t i = 1; i < bn && rec_li(me) != li; i++) me = rec_load(run + i);
@@ -837,16 +839,11 @@ __global__ void __launch_bounds__(1024) k_gdscan(int j, const int32_t* __restric
 // k_plan_cta).  The tile is then sorted by digit IN SHARED MEMORY and written out in that order: consecutive threads
 // write consecutive addresses inside a digit's run, so a run costs its sectors once -- scattering straight from
 // registers put nearly every 4-byte store in a sector of its own (8.1 M sectors for 9.6 M stores, L2-write bound).
-__global__ void __launch_bounds__(256) k_gscatter(int j, DDistros D, DGen G) {
-  if (j >= *G.maxpass) return;
-  int d, cnt; int64_t seg, lo; bool wide;
-  const int tile = int(blockIdx.x + G.tile0);
-  if (!gen_tile(D, G, tile, j, &d, &seg, &lo, &cnt, &wide)) return;
+template <bool WIDE>
+__device__ __forceinline__ void gscatter_tile(int j, const DGen& G, int tile, int64_t seg, int64_t lo, int cnt, uint32_t (*wcnt)[256],
+                                              uint32_t* s_lo, uint32_t* s_ix, uint32_t* s_hi, int32_t* s_delta, uint32_t* s_wsum) {
+  constexpr bool wide = WIDE;
   const int sb = j & 1, db = sb ^ 1;
-  __shared__ uint32_t wcnt[8][256];   // per-warp digit counters, then local positions
-  __shared__ uint32_t s_lo[kGTile], s_ix[kGTile], s_hi[kGTile];
-  __shared__ int32_t s_delta[256];    // digit -> (offset of the digit's run in the distro) - (its offset in the sorted tile)
-  __shared__ uint32_t s_wsum[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int w = 0; w < 8; w++) wcnt[w][tid] = 0u;
@@ -919,6 +916,21 @@ __global__ void __launch_bounds__(256) k_gscatter(int j, DDistros D, DGen G) {
     dst_ix[pos] = s_ix[i];
     if (wide) dst_hi[pos] = h;
   }
+}
+
+// The key's high word travels only for distros whose value range exceeds 32 bits (a handful of registers and 8 KB of
+// shared memory the common case does not pay for).
+__global__ void __launch_bounds__(256, 4) k_gscatter(int j, DDistros D, DGen G) {
+  if (j >= *G.maxpass) return;
+  int d, cnt; int64_t seg, lo; bool wide;
+  const int tile = int(blockIdx.x + G.tile0);
+  if (!gen_tile(D, G, tile, j, &d, &seg, &lo, &cnt, &wide)) return;
+  __shared__ uint32_t wcnt[8][256];   // per-warp digit counters, then local positions
+  __shared__ uint32_t s_lo[kGTile], s_ix[kGTile], s_hi[kGTile];
+  __shared__ int32_t s_delta[256];    // digit -> (offset of the digit's run in the distro) - (its offset in the sorted tile)
+  __shared__ uint32_t s_wsum[8];
+  if (wide) gscatter_tile<true>(j, G, tile, seg, lo, cnt, wcnt, s_lo, s_ix, s_hi, s_delta, s_wsum);
+  else gscatter_tile<false>(j, G, tile, seg, lo, cnt, wcnt, s_lo, s_ix, s_hi, s_delta, s_wsum);
 }
 
 // Ranked queue out: order[] and TotalValue per rank (planner.go:467-477).

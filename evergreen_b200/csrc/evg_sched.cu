@@ -582,9 +582,9 @@ __device__ int eval_group(const evg_alloc_cfg& c, const evg_group_info& info, in
 // g) does that bucket's updates, so every bucket's FP64 sum is accumulated in host order while buckets proceed
 // in parallel.  The team then evaluates the task groups; per-group results are integers, so the reduction is exact.
 template <int TPD>
-__global__ void __launch_bounds__(128) k_alloc(DHosts H, int32_t d_begin, int32_t n_distros, const int64_t* group_off,
+__global__ void __launch_bounds__(128, TPD == 32 ? 8 : 4) k_alloc(DHosts H, int32_t d_begin, int32_t n_distros, const int64_t* group_off,
                                                const evg_queue_info* qinfo, evg_group_info* ginfo, GroupScratch* gs,
-                                               int64_t now, evg_alloc_result* result, int32_t* status) {
+                                               int64_t now, evg_alloc_result* result, int32_t* status, int skip_groupless) {
   constexpr int TEAMS = 128 / TPD, TW = TPD / 32;  // teams per block, warps per team
   const int team = threadIdx.x / TPD, tt = threadIdx.x % TPD;
   const int d = d_begin + int(blockIdx.x) * TEAMS + team;
@@ -599,11 +599,12 @@ __global__ void __launch_bounds__(128) k_alloc(DHosts H, int32_t d_begin, int32_
   double& s_usoon = sh_usoon[team];
   long long* s_req = sh_req[team]; long long* s_fre = sh_fre[team];
   int* s_st = sh_st[team];
+  const int64_t g0 = group_off[d], g1 = group_off[d + 1];
+  if (skip_groupless && g1 == g0) return;  // team-uniform: k_alloc_groupless plans it, one thread instead of a warp
   const evg_alloc_cfg c = H.cfg[d];
   const evg_queue_info qi = qinfo[d];
   const int64_t threshold = qi.max_duration_threshold;
   const int64_t h0 = H.host_off[d], h1 = H.host_off[d + 1];
-  const int64_t g0 = group_off[d], g1 = group_off[d + 1];
   const int64_t n_existing = h1 - h0;
   for (int64_t g = g0 + tt; g < g1; g += TPD) { gs[g].n_hosts = 0; gs[g].n_free = 0; gs[g].soon = 0.0; }
   team_sync();
@@ -694,6 +695,68 @@ __global__ void __launch_bounds__(128) k_alloc(DHosts H, int32_t d_begin, int32_
   }
 }
 
+// Distros without task groups -- nearly all of a tick with 10^5 small queues -- have one bucket (""): the whole
+// decision is a scalar chain over a handful of hosts, so ONE THREAD plans a distro (k_alloc<32> spent a warp, and its
+// 13 us latency chain, on each).  Same arithmetic in the same order as k_alloc: hosts in index order, FP64 sum of the
+// soon-to-be-free terms, eval_group on the "" bucket, the same tail.
+__global__ void __launch_bounds__(128) k_alloc_groupless(DHosts H, int32_t d_begin, int32_t n_distros, const int64_t* group_off,
+                                                         const evg_queue_info* qinfo, int64_t now, evg_alloc_result* result, int32_t* status) {
+  const int d = d_begin + int(blockIdx.x * blockDim.x + threadIdx.x);
+  if (d >= n_distros) return;
+  if (group_off[d + 1] != group_off[d]) return;  // k_alloc's
+  const evg_alloc_cfg c = H.cfg[d];
+  const evg_queue_info qi = qinfo[d];
+  const int64_t threshold = qi.max_duration_threshold;
+  const int64_t h0 = H.host_off[d], h1 = H.host_off[d + 1];
+  const int64_t n_existing = h1 - h0;
+  int64_t n_free_all = 0, u_hosts = 0, u_free = 0;
+  double u_soon = 0.0;
+  for (int64_t h = h0; h < h1; h++) {
+    const uint32_t f = H.flags[h];
+    const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
+    n_free_all += is_free;
+    if (H.gid[h] == EVG_HG_NONE) {  // a host bucketed under a group name the queue does not have joins no bucket (allocator.go:223-260)
+      const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
+      u_hosts++;
+      u_free += is_free;
+      if (running) u_soon = fadd64(u_soon, soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction));
+    }
+  }
+  int32_t st = EVG_ALLOC_OK;
+  int64_t n_new = 0, n_free_out = n_free_all;
+  if (c.provider != EVG_PROVIDER_DOCKER && n_existing >= c.maximum_hosts) {
+    n_new = 0;  // allocator.go:39-48
+  } else if (c.disabled) {
+    n_new = int64_t(c.minimum_hosts) - n_existing;  // allocator.go:51-66
+    if (n_new < 0) n_new = 0;
+  } else {
+    int64_t required = 0, free_approx = 0;
+    if (qi.has_ungrouped || u_hosts > 0) {
+      int64_t n, f;
+      st = eval_group(c, qi.ungrouped, threshold, c.maximum_hosts, u_hosts, u_free, u_soon, &n, &f);
+      required += n;
+      free_approx += f;
+    }
+    if (st == EVG_ALLOC_OK) {
+      if (required + n_free_all > qi.length_with_dependencies_met) required = qi.length_with_dependencies_met - n_free_all;
+      if (required < 0) required = 0;
+      int64_t topup = 0;
+      if (n_existing + required < c.minimum_hosts) topup = c.minimum_hosts - (n_existing + required);
+      n_new = required + topup;
+      n_free_out = free_approx;
+    } else {
+      n_new = 0;  // (0, len(freeHosts), err) allocator.go:99-101
+      n_free_out = n_free_all;
+    }
+  }
+  int64_t deficit = wsub(qi.expected_duration, wmul(n_free_out, threshold));
+  if (deficit < 0) deficit = 0;
+  result[d].new_hosts = int32_t(n_new);
+  result[d].free_hosts = int32_t(n_free_out);
+  result[d].deficit_ns = deficit;
+  status[d] = st;
+}
+
 // --------------------------------------------------------------------------
 // context
 // --------------------------------------------------------------------------
@@ -743,7 +806,7 @@ struct evg_ctx {
   int general_complex = 0;
   int64_t Tgc = 0;  // tasks in general-path distros that can hold multi-member units (work-list capacity)
   DevBuf b_kv, b_vmm, b_klo[2], b_khi[2], b_ix[2], b_e, b_tilesum, b_gmisc;
-  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist, b_rec, b_tie, b_hlist;
+  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist, b_rec, b_tie, b_hlist, b_usum;
   DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
   DevBuf b_hflags, b_hgid, b_hexp, b_hstd, b_hstart, b_hostoff, b_acfg, b_gs, b_result, b_status;
   bool bd_valid = false;
@@ -941,6 +1004,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
       CK(c->b_clist.ensure(sizeof(uint32_t) * 2 * size_t(Tgc + 1)));
       CK(c->b_rec.ensure(sizeof(URec) * size_t(Prec + 1)));
       CK(c->b_hlist.ensure(sizeof(uint2) * size_t(Prec + 1)));
+      CK(c->b_usum.ensure(sizeof(uint4) * size_t(U + 1)));
       CK(c->b_tie.ensure(sizeof(uint4) * size_t(T + 1)));
     }
   }
@@ -1064,6 +1128,7 @@ DGen dgen(const evg_ctx* c) {
   g.rcount = c->b_gmisc.as<unsigned int>() + 2;
   g.hcount = c->b_gmisc.as<unsigned int>() + 3;
   g.hlist = c->b_hlist.as<uint2>();
+  g.usum = c->b_usum.as<uint4>();
   g.rec = c->b_rec.as<URec>();
   g.tie = c->b_tie.as<uint4>();
   g.tv = c->b_tv.as<int64_t>();
@@ -1088,12 +1153,17 @@ int run_alloc_range(evg_ctx* c, int64_t now, int32_t d0, int32_t d1) {
   if (c->ext_result && c->ext_capacity < c->Dn) return fail(EVG_ERR_INVALID, "bound result buffer holds %lld rows, need %d", (long long)c->ext_capacity, c->Dn);
   CK(c->b_gs.ensure(sizeof(GroupScratch) * size_t(c->G + 1)));
   // a warp per distro (four per block) unless some distro has thousands of task groups, then a block per distro
+  // ... and a thread per distro for the distros that have no task groups, when there are enough distros for that to matter
+  const int split = (d1 - d0) >= 4096 ? 1 : 0;
   if (c->max_groups > kWideAllocGroups)
     LAUNCH(c, k_alloc<128>, unsigned(d1 - d0), 128, h, d0, d1, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
-           c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>());
+           c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>(), split);
   else
     LAUNCH(c, k_alloc<32>, grid_for(d1 - d0, 4), 128, h, d0, d1, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
-           c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>());
+           c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>(), split);
+  if (split)
+    LAUNCH(c, k_alloc_groupless, grid_for(d1 - d0, 128), 128, h, d0, d1, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(), now,
+           c->result_ptr(), c->b_status.as<int32_t>());
   CK(cudaGetLastError());
   return EVG_OK;
 }
@@ -1331,7 +1401,7 @@ void evg_shutdown(evg_ctx* c) {
                    &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_listG, &c->b_listNA, &c->b_listNB,
                    &c->b_listNC, &c->b_punt, &c->b_puntcnt, &c->b_ca, &c->b_crk, &c->b_bestpair, &c->b_kv, &c->b_vmm,
                    &c->b_klo[0], &c->b_klo[1], &c->b_khi[0], &c->b_khi[1], &c->b_ix[0], &c->b_ix[1], &c->b_e, &c->b_tilesum,
-                   &c->b_gmisc, &c->b_clist, &c->b_rec, &c->b_tie, &c->b_hlist, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
+                   &c->b_gmisc, &c->b_clist, &c->b_rec, &c->b_tie, &c->b_hlist, &c->b_usum, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
                    &c->b_hstart, &c->b_hostoff, &c->b_acfg, &c->b_gs, &c->b_result, &c->b_status};
   for (DevBuf* b : all) b->release();
