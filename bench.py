@@ -363,6 +363,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=30, help="distros per reference/cpu_baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shapes", action="store_true")
+    ap.add_argument("--no-delta", action="store_true", help="skip the resident-delta leg of the e2e object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.block = max(1, min(args.block, args.distros))
@@ -494,6 +495,38 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * we.n_tasks / float(t.item())
     clocks = sampler.stop() if sampler else None  # sampled from before the timed loop to the end of the e2e loop
+    # ---- the same table kept resident, a tick's worth of changes sent instead (evg_update_tasks + evg_download_queue):
+    #      5% of the rows get new priority / durations / dependency bits each step, the persisted slice (first 10 000
+    #      ranks of every distro, scheduler/task_queue_persister.go:14-55) comes back.  Reported NEXT TO the headline
+    #      e2e, never as it: the headline uploads every column every step.
+    delta = None
+    if world == 1 and not args.no_delta:
+        from evergreen_b200 import _lib as L
+        from evergreen_b200.soa import TaskSoA
+        rng = np.random.default_rng(11)
+        n_upd = max(1, we.n_tasks // 20)
+        upd = []
+        for _ in range(args.e2e_steps + 1):
+            rows = np.sort(rng.choice(we.n_tasks, size=n_upd, replace=False)).astype(np.int64)
+            vals = TaskSoA(**{name: getattr(we.tasks, name)[rows].copy() for name, _ in we.tasks.COLUMNS})
+            vals.priority = rng.integers(0, 101, n_upd).astype(np.int32)
+            vals.expected_ns = (vals.expected_ns + rng.integers(0, 10 ** 9, n_upd)).astype(np.int64)
+            vals.flags = (vals.flags | L.EVG_TF_DEPS_MET).astype(np.uint32)
+            upd.append((pinned_like(rows), TaskSoA(**{name: pinned_like(getattr(vals, name)) for name, _ in vals.COLUMNS})))
+        eng.upload(we.tasks, we.distros, we.hosts)
+        eng.update_tasks(*upd[0]); eng.run(we.now); off, items = eng.download_queue(task_off=we.distros.task_off)  # warm-up
+        d_bytes = int(items.nbytes + off.nbytes)
+        t0 = time.perf_counter()
+        for k in range(args.e2e_steps):
+            eng.update_tasks(*upd[k + 1])
+            eng.run(we.now)
+            off, items = eng.download_queue(task_off=we.distros.task_off)
+        dt_s = (time.perf_counter() - t0) / args.e2e_steps
+        delta = {"value": we.n_tasks / dt_s, "unit": "tasks/s", "ms_per_step": dt_s * 1e3, "changed_rows_per_step": int(n_upd),
+                 "h2d_bytes_per_step": int(48 * n_upd), "d2h_bytes_per_step": d_bytes,
+                 "api": "Engine.update_tasks (evg_update_tasks: 5% of the rows, 48 B each) + evg_run_resident + Engine.download_queue "
+                        "(evg_download_queue: 40 B x the first 10 000 ranks of every distro)"}
+        del upd, off, items
     del we, pe, ae
 
     line = None
@@ -505,7 +538,7 @@ def main():
                 "whole_tick": {"achieved": ab / step_s / 1e9, "frac": ab / step_s / 1e9 / peak, "algorithmic_bytes_per_step": int(ab)}}
         if task_ms:
             kb = 48 * T + 4 * E  # the per-task pass reads every input column once; its outputs are scratch
-            roof.update({"kernel": "k_gtask (general path: 128-bit column loads, 32-bit scoring, queue-info fold, unit links), "
+            roof.update({"kernel": "k_gtask (general path: 128-bit column loads, 32-bit scoring, queue-info fold, work-list append), "
                                    "CUDA events on its stream around the launch in the last timed step",
                          "kernel_ms": task_ms, "algorithmic_bytes_per_launch": int(kb), "achieved": kb / (task_ms * 1e-3) / 1e9,
                          "frac": kb / (task_ms * 1e-3) / 1e9 / peak, "kernel_share_of_step": task_ms / ms_per_step,
@@ -530,7 +563,8 @@ def main():
                     "ms_per_step": float(t.item()) * 1e3,
                     "workload": f"the same shape on {e2e_reps * args.block} distros ({e2e_reps * args.block * args.tasks_per_distro} tasks) per GPU",
                     "api": "Engine.plan_and_alloc_batch (evg_plan_and_alloc_batch), pinned host columns",
-                    "cpu_affinity": "GPU-local NUMA node" if prev_affinity else "unbound"},
+                    "cpu_affinity": "GPU-local NUMA node" if prev_affinity else "unbound",
+                    "resident_delta": delta},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roof,
             "checksum_new_hosts": new_hosts_checksum, "first_distro_is_a_permutation": order_ok,

@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(256, 4) k_gunit(DDistros D, DWork W, DGen G, i
     }
     const unsigned long long v = (unsigned long long)unit_value(a, D.cfg[u.y], nullptr);
     G.usum[u.x] = make_uint4(uint32_t(v), uint32_t(v >> 32), anchor, cnt);  // kNoAnchor: the unit never got a distro -> not exported (planner.go:81-83)
+    W.unit_mask[u.x] = 0ull;  // k_gbest ORs the emitted ranks in (cleared here, unit by unit, instead of a slot-wide memset)
   }
 }
 

@@ -103,6 +103,7 @@ struct DevBuf {
 constexpr int kCapA = 128 * 8, kCapB = 256 * 16, kCapC = EVG_C_THREADS * EVG_C_ITEMS;
 constexpr int64_t kWideAllocGroups = 1024;  // k_alloc<128> (a block per distro) once some distro has more task groups
 constexpr int kCapW = 32;  // k_plan_warp: one warp per distro
+constexpr int64_t kGrouplessHosts = 64;  // k_alloc_groupless walks a distro's hosts with one thread: only short walks
 constexpr int64_t kSparseClass = 64;  // a k_plan_smem class of 1025+ task distros with fewer members than this goes to the general path
 // second-generation on-chip planner classes <THREADS, CAP, CTAs per SM> (evg_plan_cta.cuh)
 constexpr int kNT_A = 128, kNCapA = 1280, kNOccA = 8;
@@ -600,11 +601,11 @@ __global__ void __launch_bounds__(128, TPD == 32 ? 8 : 4) k_alloc(DHosts H, int3
   long long* s_req = sh_req[team]; long long* s_fre = sh_fre[team];
   int* s_st = sh_st[team];
   const int64_t g0 = group_off[d], g1 = group_off[d + 1];
-  if (skip_groupless && g1 == g0) return;  // team-uniform: k_alloc_groupless plans it, one thread instead of a warp
+  const int64_t h0 = H.host_off[d], h1 = H.host_off[d + 1];
+  if (skip_groupless && g1 == g0 && h1 - h0 <= kGrouplessHosts) return;  // team-uniform: k_alloc_groupless plans it, one thread instead of a warp
   const evg_alloc_cfg c = H.cfg[d];
   const evg_queue_info qi = qinfo[d];
   const int64_t threshold = qi.max_duration_threshold;
-  const int64_t h0 = H.host_off[d], h1 = H.host_off[d + 1];
   const int64_t n_existing = h1 - h0;
   for (int64_t g = g0 + tt; g < g1; g += TPD) { gs[g].n_hosts = 0; gs[g].n_free = 0; gs[g].soon = 0.0; }
   team_sync();
@@ -612,23 +613,36 @@ __global__ void __launch_bounds__(128, TPD == 32 ? 8 : 4) k_alloc(DHosts H, int3
   if (warp == 0) {
     int64_t n_free_all = 0, u_hosts = 0, u_free = 0;
     double u_soon = 0.0;
-    for (int64_t h = h0; h < h1; h++) {
-      const uint32_t f = H.flags[h];
-      const int32_t g = H.gid[h];
-      const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
-      n_free_all += is_free;
-      const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
-      if (g == EVG_HG_NONE) {
-        if (lane == 0) {
-          u_hosts++;
-          u_free += is_free;
-          if (running) u_soon = fadd64(u_soon, soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction));
+    // 32 hosts per trip: lane L loads host hc + L (coalesced, one round trip for the chunk), then the chunk is replayed
+    // in host order through shuffles -- every bucket's FP64 sum still accumulates in index order.  (One load per host
+    // and lane made a 1291-host distro a 400 us serial chain: the whole tail of a 10^5-distro tick.)
+    for (int64_t hc = h0; hc < h1; hc += 32) {
+      const int64_t hm = hc + lane;
+      const bool in = hm < h1;
+      const uint32_t my_f = in ? H.flags[hm] : 0u;
+      const int32_t my_g = in ? H.gid[hm] : EVG_HG_NONE;
+      const bool my_run = in && (my_f & EVG_HF_RUNNING) && (my_f & EVG_HF_RT_FOUND);
+      const int64_t my_e = my_run ? H.expected[hm] : 0, my_s = my_run ? H.stddev[hm] : 0, my_t = my_run ? H.start[hm] : 0;
+      const int cnt = int(h1 - hc < 32 ? h1 - hc : 32);
+      for (int j = 0; j < cnt; j++) {
+        const uint32_t f = __shfl_sync(full, my_f, j);
+        const int32_t g = __shfl_sync(full, my_g, j);
+        const int64_t he = __shfl_sync(full, my_e, j), hs = __shfl_sync(full, my_s, j), ht = __shfl_sync(full, my_t, j);
+        const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
+        n_free_all += is_free;
+        const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
+        if (g == EVG_HG_NONE) {
+          if (lane == 0) {
+            u_hosts++;
+            u_free += is_free;
+            if (running) u_soon = fadd64(u_soon, soon_free_term(now, he, hs, ht, threshold, c.future_host_fraction));
+          }
+        } else if (g >= 0 && g < g1 - g0 && (g & 31) == lane) {
+          GroupScratch* s = gs + g0 + g;
+          s->n_hosts++;
+          s->n_free += is_free;
+          if (running) s->soon = fadd64(s->soon, soon_free_term(now, he, hs, ht, threshold, c.future_host_fraction));
         }
-      } else if (g >= 0 && g < g1 - g0 && (g & 31) == lane) {
-        GroupScratch* s = gs + g0 + g;
-        s->n_hosts++;
-        s->n_free += is_free;
-        if (running) s->soon = fadd64(s->soon, soon_free_term(now, H.expected[h], H.stddev[h], H.start[h], threshold, c.future_host_fraction));
       }
     }
     if (lane == 0) { s_nfree = n_free_all; s_uhosts = u_hosts; s_ufree = u_free; s_usoon = u_soon; }
@@ -703,11 +717,11 @@ __global__ void __launch_bounds__(128) k_alloc_groupless(DHosts H, int32_t d_beg
                                                          const evg_queue_info* qinfo, int64_t now, evg_alloc_result* result, int32_t* status) {
   const int d = d_begin + int(blockIdx.x * blockDim.x + threadIdx.x);
   if (d >= n_distros) return;
-  if (group_off[d + 1] != group_off[d]) return;  // k_alloc's
+  const int64_t h0 = H.host_off[d], h1 = H.host_off[d + 1];
+  if (group_off[d + 1] != group_off[d] || h1 - h0 > kGrouplessHosts) return;  // k_alloc's
   const evg_alloc_cfg c = H.cfg[d];
   const evg_queue_info qi = qinfo[d];
   const int64_t threshold = qi.max_duration_threshold;
-  const int64_t h0 = H.host_off[d], h1 = H.host_off[d + 1];
   const int64_t n_existing = h1 - h0;
   int64_t n_free_all = 0, u_hosts = 0, u_free = 0;
   double u_soon = 0.0;
@@ -798,6 +812,7 @@ struct evg_ctx {
   DevBuf b_punt, b_puntcnt;
   int32_t nW = 0, nA = 0, nB = 0, nC = 0, nNA = 0, nNB = 0, nNC = 0, n_general = 0;  // distros per route
   std::vector<int32_t> h_listW, h_listA, h_listB, h_listC, h_listNA, h_listNB, h_listNC;  // host copies (ascending distro ids)
+  DevBuf b_lptA, b_lptB, b_lptC, b_lptNA, b_lptNB, b_lptNC;  // the same lists, largest distro first: the resident tick's launch order
   std::vector<int64_t> h_taskoff, h_groupoff, h_unitbase, h_edgeoff, h_dtileoff;
   std::vector<int32_t> h_listG;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -806,7 +821,7 @@ struct evg_ctx {
   int general_complex = 0;
   int64_t Tgc = 0;  // tasks in general-path distros that can hold multi-member units (work-list capacity)
   DevBuf b_kv, b_vmm, b_klo[2], b_khi[2], b_ix[2], b_e, b_tilesum, b_gmisc;
-  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist, b_rec, b_tie, b_hlist, b_usum;
+  DevBuf b_tiledistro, b_tilestart, b_dtileoff, b_tilehist, b_clist, b_rec, b_tie, b_hlist, b_usum, b_upd;
   DevBuf b_qinfo, b_ginfo, b_order, b_tv, b_bd;
   DevBuf b_hflags, b_hgid, b_hexp, b_hstd, b_hstart, b_hostoff, b_acfg, b_gs, b_result, b_status;
   bool bd_valid = false;
@@ -971,6 +986,20 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   UP(c->b_listNA, listNA.data(), int64_t(listNA.size()), int32_t);
   UP(c->b_listNB, listNB.data(), int64_t(listNB.size()), int32_t);
   UP(c->b_listNC, listNC.data(), int64_t(listNC.size()), int32_t);
+  // One CTA per distro: with the largest first, the last (partial) wave of a launch holds the smallest distros and the
+  // tail is short (configs[4]: 1371 distros of 33..1024 tasks on 1184 CTA slots).  The ascending lists stay: the
+  // pipelined one-shot call cuts them by distro range.
+  std::vector<int32_t> lptA(listA), lptB(listB), lptC(listC), lptNA(listNA), lptNB(listNB), lptNC(listNC);
+  for (std::vector<int32_t>* v : {&lptA, &lptB, &lptC, &lptNA, &lptNB, &lptNC})
+    std::stable_sort(v->begin(), v->end(), [&](int32_t x, int32_t y) {
+      return dt->task_off[x + 1] - dt->task_off[x] > dt->task_off[y + 1] - dt->task_off[y];
+    });
+  UP(c->b_lptA, lptA.data(), int64_t(lptA.size()), int32_t);
+  UP(c->b_lptB, lptB.data(), int64_t(lptB.size()), int32_t);
+  UP(c->b_lptC, lptC.data(), int64_t(lptC.size()), int32_t);
+  UP(c->b_lptNA, lptNA.data(), int64_t(lptNA.size()), int32_t);
+  UP(c->b_lptNB, lptNB.data(), int64_t(lptNB.size()), int32_t);
+  UP(c->b_lptNC, lptNC.data(), int64_t(lptNC.size()), int32_t);
   // the staging vectors above must outlive the async copies
   CK(cudaStreamSynchronize(s));
   // work buffers
@@ -1218,7 +1247,6 @@ int prepare_general(evg_ctx* c, cudaStream_t s, int32_t d0, int32_t d1) {
     const size_t nt = size_t(t1 - t0);
     CK(cudaMemsetAsync(c->b_hasdep.as<uint8_t>() + t0, 0, nt, s));
     CK(cudaMemsetAsync(c->b_unitn.as<uint32_t>() + u0, 0, sizeof(uint32_t) * size_t(u1 - u0), s));   // members drawn so far
-    CK(cudaMemsetAsync(c->b_unitmask.as<uint64_t>() + u0, 0, sizeof(uint64_t) * size_t(u1 - u0), s));
   }
   return EVG_OK;
 }
@@ -1318,29 +1346,29 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
   // --- stream 0: the second-generation on-chip planner (the dominant kernel of configs[1]-like ticks), then the
   //     distros it handed back
   if (bd) {  // breakdown needs the unit lists: every on-chip distro goes through k_plan_smem (its largest class holds them all)
-    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, c->b_listNC.as<int32_t>(), c->nNC, now, 1)) != EVG_OK) return rc;
-    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, c->b_listNB.as<int32_t>(), c->nNB, now, 1)) != EVG_OK) return rc;
-    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, c->b_listNA.as<int32_t>(), c->nNA, now, 1)) != EVG_OK) return rc;
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, c->b_lptNC.as<int32_t>(), c->nNC, now, 1)) != EVG_OK) return rc;
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, c->b_lptNB.as<int32_t>(), c->nNB, now, 1)) != EVG_OK) return rc;
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, c->b_lptNA.as<int32_t>(), c->nNA, now, 1)) != EVG_OK) return rc;
   } else if (n_new > 0) {
     int32_t* pl = c->b_punt.as<int32_t>();
     int32_t* pc = c->b_puntcnt.as<int32_t>();
     const bool time_it = c->timed && !general && c->nNC > 0;
     if (time_it) CK(cudaEventRecord(c->ring0[slot], st(0)));
-    if ((rc = launch_cta<kNT_C, kNCapC, kNOccC>(c, st(0), dt, dd, w, c->b_listNC.as<int32_t>(), c->nNC, now, pl, pc)) != EVG_OK) return rc;
+    if ((rc = launch_cta<kNT_C, kNCapC, kNOccC>(c, st(0), dt, dd, w, c->b_lptNC.as<int32_t>(), c->nNC, now, pl, pc)) != EVG_OK) return rc;
     if (time_it) { CK(cudaEventRecord(c->ring1[slot], st(0))); c->runs++; c->sort_slot = slot; }
-    if ((rc = launch_cta<kNT_B, kNCapB, kNOccB>(c, st(0), dt, dd, w, c->b_listNB.as<int32_t>(), c->nNB, now, pl, pc)) != EVG_OK) return rc;
-    if ((rc = launch_cta<kNT_A, kNCapA, kNOccA>(c, st(0), dt, dd, w, c->b_listNA.as<int32_t>(), c->nNA, now, pl, pc)) != EVG_OK) return rc;
+    if ((rc = launch_cta<kNT_B, kNCapB, kNOccB>(c, st(0), dt, dd, w, c->b_lptNB.as<int32_t>(), c->nNB, now, pl, pc)) != EVG_OK) return rc;
+    if ((rc = launch_cta<kNT_A, kNCapA, kNOccA>(c, st(0), dt, dd, w, c->b_lptNA.as<int32_t>(), c->nNA, now, pl, pc)) != EVG_OK) return rc;
     if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, pl, n_new, now, 0, pc)) != EVG_OK) return rc;
   }
   // --- streams 1..3: first-generation classes (GroupVersions, in-queue dependency edges, very many task groups)
   {
     const bool time_it = c->timed && !general && c->sort_slot < 0 && c->nC > 0;
     if (time_it) CK(cudaEventRecord(c->ring0[slot], st(1)));
-    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(1), dt, dd, w, c->b_listC.as<int32_t>(), c->nC, now, bd ? 1 : 0)) != EVG_OK) return rc;
+    if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(1), dt, dd, w, c->b_lptC.as<int32_t>(), c->nC, now, bd ? 1 : 0)) != EVG_OK) return rc;
     if (time_it) { CK(cudaEventRecord(c->ring1[slot], st(1))); c->runs++; c->sort_slot = slot; }
   }
-  if ((rc = launch_smem<256, 16, 3>(c, st(2), dt, dd, w, c->b_listB.as<int32_t>(), c->nB, now, bd ? 1 : 0)) != EVG_OK) return rc;
-  if ((rc = launch_smem<128, 8, 8>(c, st(3), dt, dd, w, c->b_listA.as<int32_t>(), c->nA, now, bd ? 1 : 0)) != EVG_OK) return rc;
+  if ((rc = launch_smem<256, 16, 3>(c, st(2), dt, dd, w, c->b_lptB.as<int32_t>(), c->nB, now, bd ? 1 : 0)) != EVG_OK) return rc;
+  if ((rc = launch_smem<128, 8, 8>(c, st(3), dt, dd, w, c->b_lptA.as<int32_t>(), c->nA, now, bd ? 1 : 0)) != EVG_OK) return rc;
   // --- stream 4: one warp per tiny distro
   if ((rc = launch_tiny(c, st(4), dt, dd, w, c->b_listW.as<int32_t>(), c->nW, now, bd ? 1 : 0)) != EVG_OK) return rc;
   // --- stream 5: the general path
@@ -1399,9 +1427,9 @@ void evg_shutdown(evg_ctx* c) {
                    &c->b_unitn, &c->b_unitmask, &c->b_rn0, &c->b_rn1, &c->b_rn2, &c->b_rn3, &c->b_rn4, &c->b_rn5, &c->b_rn6,
                    &c->b_rn7, &c->b_err, &c->b_dx0, &c->b_dx1, &c->b_dx2, &c->b_dx3, &c->b_dx4, &c->b_dx5, &c->b_dx6, &c->b_dx7,
                    &c->b_route, &c->b_listW, &c->b_listA, &c->b_listB, &c->b_listC, &c->b_listG, &c->b_listNA, &c->b_listNB,
-                   &c->b_listNC, &c->b_punt, &c->b_puntcnt, &c->b_ca, &c->b_crk, &c->b_bestpair, &c->b_kv, &c->b_vmm,
+                   &c->b_listNC, &c->b_lptA, &c->b_lptB, &c->b_lptC, &c->b_lptNA, &c->b_lptNB, &c->b_lptNC, &c->b_punt, &c->b_puntcnt, &c->b_ca, &c->b_crk, &c->b_bestpair, &c->b_kv, &c->b_vmm,
                    &c->b_klo[0], &c->b_klo[1], &c->b_khi[0], &c->b_khi[1], &c->b_ix[0], &c->b_ix[1], &c->b_e, &c->b_tilesum,
-                   &c->b_gmisc, &c->b_clist, &c->b_rec, &c->b_tie, &c->b_hlist, &c->b_usum, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
+                   &c->b_gmisc, &c->b_clist, &c->b_rec, &c->b_tie, &c->b_hlist, &c->b_usum, &c->b_upd, &c->b_tiledistro, &c->b_tilestart, &c->b_dtileoff, &c->b_tilehist,
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
                    &c->b_hstart, &c->b_hostoff, &c->b_acfg, &c->b_gs, &c->b_result, &c->b_status};
   for (DevBuf* b : all) b->release();
@@ -1435,6 +1463,63 @@ int evg_upload(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* di
 __global__ void k_gather_i64(const int64_t* __restrict__ src, const int64_t* __restrict__ at, int64_t* __restrict__ out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = src[at[i]];
+}
+
+// evg_update_tasks: scatter changed rows into the resident columns.
+__global__ void __launch_bounds__(256) k_update_rows(int64_t n, const int64_t* __restrict__ rows, int64_t T, int32_t* priority, int32_t* numdep,
+                                                     int32_t* tgo, uint32_t* flags, int64_t* expected, int64_t* qbasis, int64_t* wbasis,
+                                                     const int32_t* v_priority, const int32_t* v_numdep, const int32_t* v_tgo,
+                                                     const uint32_t* v_flags, const int64_t* v_expected, const int64_t* v_qbasis,
+                                                     const int64_t* v_wbasis, int* bad) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t r = rows[i];
+  if (r < 0 || r >= T) { *bad = 1; return; }
+  priority[r] = v_priority[i]; numdep[r] = v_numdep[i]; tgo[r] = v_tgo[i]; flags[r] = v_flags[i];
+  expected[r] = v_expected[i]; qbasis[r] = v_qbasis[i]; wbasis[r] = v_wbasis[i];
+}
+
+int evg_update_tasks(evg_ctx* c, int64_t n_rows, const int64_t* rows, const evg_task_soa* v) {
+  if (!c) return fail(EVG_ERR_INVALID, "null context");
+  LOCK(c);
+  if (!c->have_tasks) return fail(EVG_ERR_STATE, "evg_update_tasks before evg_upload");
+  if (c->adopted) return fail(EVG_ERR_STATE, "the resident columns are borrowed (evg_upload_device): edit them in place instead");
+  if (n_rows < 0) return fail(EVG_ERR_INVALID, "negative row count");
+  if (n_rows == 0) return EVG_OK;
+  if (!rows || !v || v->n_tasks != n_rows || !v->priority || !v->num_dependents || !v->task_group_order || !v->flags || !v->expected_ns ||
+      !v->queue_basis_ns || !v->wait_basis_ns)
+    return fail(EVG_ERR_INVALID, "evg_update_tasks: rows and a %lld-row value table (priority, num_dependents, task_group_order, flags, "
+                                 "expected_ns, queue_basis_ns, wait_basis_ns) are required", (long long)n_rows);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const size_t n = size_t(n_rows);
+  // staging: rows (8) + three 8-byte and four 4-byte columns = 48 B per changed row
+  CK(c->b_upd.ensure(n * 48 + 64));
+  unsigned char* base = c->b_upd.as<unsigned char>();
+  int64_t* d_rows = reinterpret_cast<int64_t*>(base);
+  int64_t* d_exp = d_rows + n; int64_t* d_qb = d_exp + n; int64_t* d_wb = d_qb + n;
+  int32_t* d_prio = reinterpret_cast<int32_t*>(d_wb + n); int32_t* d_nd = d_prio + n; int32_t* d_tgo = d_nd + n;
+  uint32_t* d_fl = reinterpret_cast<uint32_t*>(d_tgo + n);
+  CK(cudaMemcpyAsync(d_rows, rows, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_exp, v->expected_ns, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_qb, v->queue_basis_ns, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_wb, v->wait_basis_ns, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_prio, v->priority, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_nd, v->num_dependents, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_tgo, v->task_group_order, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_fl, v->flags, n * 4, cudaMemcpyHostToDevice, s));
+  int* bad = reinterpret_cast<int*>(base + n * 48);
+  CK(cudaMemsetAsync(bad, 0, sizeof(int), s));
+  k_update_rows<<<grid_for(n_rows, 256), 256, 0, s>>>(n_rows, d_rows, c->T, c->b_prio.as<int32_t>(), c->b_nd.as<int32_t>(), c->b_tgo.as<int32_t>(),
+                                                      c->b_flags.as<uint32_t>(), c->b_exp.as<int64_t>(), c->b_qb.as<int64_t>(), c->b_wb.as<int64_t>(),
+                                                      d_prio, d_nd, d_tgo, d_fl, d_exp, d_qb, d_wb, bad);
+  CK(cudaGetLastError());
+  int h_bad = 0;
+  CK(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));  // the caller's staging arrays are free again
+  if (h_bad) return fail(EVG_ERR_INVALID, "evg_update_tasks: a row index is outside [0, n_tasks)");
+  c->deps_resident = false;  // flags / wait bases written by a device-side dependency evaluation may have been replaced
+  return EVG_OK;
 }
 
 int evg_upload_device(evg_ctx* c, const evg_task_soa* tasks, const evg_distro_table* distros, const evg_host_soa* hosts,

@@ -153,6 +153,16 @@ class Engine:
         self._n_tasks, self._n_distros, self._n_groups = int(n_tasks), distros.n_distros, distros.n_groups
         self._has_hosts = hosts is not None
 
+    def update_tasks(self, rows: np.ndarray, values: S.TaskSoA) -> None:
+        """evg_update_tasks: the per-task scalars of `rows` (task slots of the resident table) take the values of
+        `values`' rows; group / version / dependency structure stays.  48 B per changed row cross PCIe."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        values = values.normalize()
+        if values.n_tasks != rows.shape[0]:
+            raise ValueError("one value row per updated task slot")
+        vs = values.struct()
+        L.check(self.lib.evg_update_tasks(self.ctx, int(rows.shape[0]), L.ptr(rows), C.byref(vs)))
+
     def run(self, now: int, opts: int = 0) -> None:
         L.check(self.lib.evg_run_resident(self.ctx, int(now), int(opts)))
 

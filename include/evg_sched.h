@@ -273,6 +273,15 @@ int evg_plan_and_alloc_batch(evg_ctx* ctx, const evg_task_soa* tasks, const evg_
  * may be NULL for planner-only use). */
 int evg_upload(evg_ctx* ctx, const evg_task_soa* tasks, const evg_distro_table* distros,
                const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg);
+/* Tick-to-tick update of the resident task table: row rows[i] (a task slot of the last evg_upload, 0 <= rows[i] <
+ * n_tasks) gets priority, num_dependents, task_group_order, flags, expected_ns, queue_basis_ns and wait_basis_ns of row i
+ * of `values` (values->n_tasks == n_rows; its group / version / dependency columns are not read: a task keeps its
+ * distro, its task group, its version and its in-queue dependency edges -- a tick that adds or removes tasks uploads
+ * again).  48 bytes cross PCIe per changed row instead of the whole table.  Not available after evg_upload_device (the
+ * caller owns those columns and edits them in place).  Replaces nothing in the reference: there the scheduler re-reads
+ * every task document each tick (scheduler/task_finder.go:40-197). */
+int evg_update_tasks(evg_ctx* ctx, int64_t n_rows, const int64_t* rows, const evg_task_soa* values);
+
 /* Like evg_upload, but the task columns already live in DEVICE memory (the finder's output, a generator kernel, a
  * previous tick edited in place): `tasks` holds device pointers, which the context borrows until the next upload or
  * evg_shutdown -- nothing is copied.  Every column must be 16-byte aligned and readable 8 elements past its last

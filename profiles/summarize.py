@@ -98,5 +98,66 @@ def kernel(path):
         print(f"| {ln} | {100 * smp / max(ts, 1):.1f}% | {100 * ins / max(ti, 1):.1f}% | {tops} | `{s.replace('|', '/')}` |")
 
 
+def kernels(path):
+    """Every kernel of a multi-kernel capture, one row each."""
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    cols = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
+            ("lts__t_sectors_srcunit_tex_op_read.sum", "L2 read sectors"), ("lts__t_sectors_srcunit_tex_op_write.sum", "L2 write sectors"),
+            ("smsp__inst_executed.sum", "warp instr"), ("sm__inst_executed.avg.per_cycle_elapsed", "IPC/SM"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"), ("launch__registers_per_thread", "regs"),
+            ("launch__grid_size", "grid")]
+    ix = {h: i for i, h in enumerate(hdr)}
+    print(f"# ncu --set full --clock-control none: {len(rows) - 2} launches of `{path.split('/')[-1]}`\n")
+    print("| kernel | " + " | ".join(f"{t} ({units[ix[c]]})" if units[ix[c]] else t for c, t in cols if c in ix) + " |")
+    print("|---|" + "---:|" * sum(c in ix for c, _ in cols))
+    for r in rows[2:]:
+        def fmt(v):
+            try:
+                x = float(v.replace(",", ""))
+                return f"{x:.4g}" if abs(x) < 1e6 else f"{x:.4e}"
+            except ValueError:
+                return v
+        print(f"| `{r[ix['Kernel Name']].split('(')[0].replace('void ', '')}` | " + " | ".join(fmt(r[ix[c]]) for c, _ in cols if c in ix) + " |")
+
+
+def phases(path, units_per_launch="1"):
+    """One kernel: SASS sorted by address, cut at every BAR.SYNC; per phase the share of stall samples, thread
+    instructions per unit (task) and the top stall reasons.  `units_per_launch` = tasks the profiled launch processed."""
+    n_units = float(units_per_launch)
+    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(src.splitlines()))
+    hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
+    hdr = rows[hi]
+    ix = {h: i for i, h in enumerate(hdr)}
+    data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    data.sort(key=lambda r: int(r[ix["Address"]], 16))
+    stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    num = lambda x: float(x) if x not in ("", "-") else 0.0
+    ph, cur = [], []
+    for r in data:
+        cur.append(r)
+        if "BAR.SYNC" in r[ix["Source"]]:
+            ph.append(cur); cur = []
+    if cur:
+        ph.append(cur)
+    tot_s = sum(num(r[ix["# Samples"]]) for r in data)
+    tot_t = sum(num(r[ix["Thread Instructions Executed"]]) for r in data)
+    tot_w = sum(num(r[ix["Instructions Executed"]]) for r in data)
+    print(f"# {rows[0][1][:100] if len(rows[0]) > 1 else path}\n")
+    print(f"Stall samples {tot_s:.0f}; warp instructions {tot_w:.4g}; thread instructions per unit {tot_t / n_units:.1f} ({n_units:.0f} units per launch).\n")
+    print("Phases = stretches of SASS between consecutive `BAR.SYNC` (address order; out-of-line code such as spin loops lands in the last one).\n")
+    print("| phase | SASS | samples | thread instr / unit | top stalls |\n|---:|---:|---:|---:|---|")
+    for k, p in enumerate(ph):
+        sm = sum(num(r[ix["# Samples"]]) for r in p)
+        if sm < 0.005 * tot_s:
+            continue
+        ti = sum(num(r[ix["Thread Instructions Executed"]]) for r in p)
+        st = collections.Counter({n: sum(num(r[ix[n]]) for r in p) for n in stalls})
+        tops = ", ".join(f"{n[6:]} {100 * v / max(sm, 1):.0f}%" for n, v in st.most_common(4))
+        print(f"| {k} | {len(p)} | {100 * sm / tot_s:.1f}% | {ti / n_units:.1f} | {tops} |")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "kernels": kernels, "phases": phases}[sys.argv[1]](*sys.argv[2:])

@@ -887,6 +887,33 @@ def test_upload_device_equals_upload(engine):
     del keep
 
 
+def test_update_tasks_equals_a_fresh_upload(engine):
+    """evg_update_tasks: after scattering changed rows into the resident table (every route: tiny, on-chip, general),
+    the tick equals the tick of a fresh upload of the edited table and the oracle's; bad row indices are errors."""
+    sizes = np.array([20, 700, 3000, 9000, 14000, 1, 40000])
+    w = synth.make(sizes, 221, zipf_priority=True, tg_frac=0.12, met_dep_frac=0.02, unmet_dep_frac=0.03, includes_dependencies=True, n_hosts=50)
+    engine.upload(w.tasks, w.distros, w.hosts)
+    engine.run(w.now)
+    rng = np.random.default_rng(5)
+    t = w.tasks
+    for round_ in range(3):
+        rows = np.sort(rng.choice(t.n_tasks, size=t.n_tasks // 15, replace=False)).astype(np.int64)
+        vals = soa.TaskSoA(**{name: getattr(t, name)[rows].copy() for name, _ in t.COLUMNS})
+        vals.priority = rng.integers(0, 101, rows.shape[0]).astype(np.int32)
+        vals.expected_ns = (vals.expected_ns + rng.integers(0, 10 ** 10, rows.shape[0])).astype(np.int64)
+        vals.flags = (vals.flags | np.where(rng.uniform(size=rows.shape[0]) < 0.5, L.EVG_TF_DEPS_MET, 0)).astype(np.uint32)
+        vals.wait_basis_ns = (vals.wait_basis_ns - rng.integers(0, 10 ** 12, rows.shape[0])).astype(np.int64)
+        vals.num_dependents = rng.integers(0, 30, rows.shape[0]).astype(np.int32)
+        for name in ("priority", "expected_ns", "flags", "wait_basis_ns", "num_dependents", "queue_basis_ns", "task_group_order"):
+            getattr(t, name)[rows] = getattr(vals, name)
+        engine.update_tasks(rows, vals)
+        engine.run(w.now)
+        po, ao = engine.download()
+        parity.check_against_oracle(w, po, ao)  # w.tasks was edited in step: the oracle plans the same table
+    with pytest.raises(L.EvgError):
+        engine.update_tasks(np.array([t.n_tasks], dtype=np.int64), soa.TaskSoA(**{name: getattr(t, name)[:1].copy() for name, _ in t.COLUMNS}))
+
+
 def test_two_contexts_two_threads(engine):
     """Entry points are called from arbitrary OS threads (cgo): two contexts planning different ticks at the same
     time, and two threads sharing ONE context (serialised by its lock), all bit-equal to the single-threaded run."""
