@@ -607,43 +607,55 @@ __global__ void __launch_bounds__(128, TPD == 32 ? 8 : 4) k_alloc(DHosts H, int3
   const evg_queue_info qi = qinfo[d];
   const int64_t threshold = qi.max_duration_threshold;
   const int64_t n_existing = h1 - h0;
-  for (int64_t g = g0 + tt; g < g1; g += TPD) { gs[g].n_hosts = 0; gs[g].n_free = 0; gs[g].soon = 0.0; }
-  team_sync();
-  // IsFree count (allocator.go:33-37), bucket sizes (groupByTaskGroup :223-260), soon-to-be-free sums (:324-394)
+  // IsFree count (allocator.go:33-37), bucket sizes (groupByTaskGroup :223-260), soon-to-be-free sums (:324-394).
+  // The buckets of kCache task groups at a time live in SHARED memory while the hosts are walked (a distro with more
+  // groups walks its hosts once per stretch of kCache): a bucket update used to be a load-add-store on global scratch,
+  // an L2 round trip per host in a serial loop.
+  constexpr int kCache = TPD == 32 ? 128 : 512;
+  __shared__ GroupScratch sh_gs[TEAMS][kCache];
+  GroupScratch* sg = sh_gs[team];
   if (warp == 0) {
     int64_t n_free_all = 0, u_hosts = 0, u_free = 0;
     double u_soon = 0.0;
-    // 32 hosts per trip: lane L loads host hc + L (coalesced, one round trip for the chunk), then the chunk is replayed
-    // in host order through shuffles -- every bucket's FP64 sum still accumulates in index order.  (One load per host
-    // and lane made a 1291-host distro a 400 us serial chain: the whole tail of a 10^5-distro tick.)
-    for (int64_t hc = h0; hc < h1; hc += 32) {
-      const int64_t hm = hc + lane;
-      const bool in = hm < h1;
-      const uint32_t my_f = in ? H.flags[hm] : 0u;
-      const int32_t my_g = in ? H.gid[hm] : EVG_HG_NONE;
-      const bool my_run = in && (my_f & EVG_HF_RUNNING) && (my_f & EVG_HF_RT_FOUND);
-      const int64_t my_e = my_run ? H.expected[hm] : 0, my_s = my_run ? H.stddev[hm] : 0, my_t = my_run ? H.start[hm] : 0;
-      const int cnt = int(h1 - hc < 32 ? h1 - hc : 32);
-      for (int j = 0; j < cnt; j++) {
-        const uint32_t f = __shfl_sync(full, my_f, j);
-        const int32_t g = __shfl_sync(full, my_g, j);
-        const int64_t he = __shfl_sync(full, my_e, j), hs = __shfl_sync(full, my_s, j), ht = __shfl_sync(full, my_t, j);
-        const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
-        n_free_all += is_free;
-        const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
-        if (g == EVG_HG_NONE) {
-          if (lane == 0) {
-            u_hosts++;
-            u_free += is_free;
-            if (running) u_soon = fadd64(u_soon, soon_free_term(now, he, hs, ht, threshold, c.future_host_fraction));
+    const int64_t ng = g1 - g0;
+    for (int64_t gb = 0; gb == 0 || gb < ng; gb += kCache) {
+      const bool first = gb == 0;  // the "" bucket and the free count are taken on the first walk only
+      const int64_t ge = ng - gb < kCache ? ng - gb : kCache;  // groups of this stretch: [gb, gb + ge)
+      for (int64_t i = lane; i < ge; i += 32) { sg[i].n_hosts = 0; sg[i].n_free = 0; sg[i].soon = 0.0; }
+      __syncwarp();
+      // 32 hosts per trip: lane L loads host hc + L (coalesced, one round trip for the chunk), then the chunk is replayed
+      // in host order through shuffles -- every bucket's FP64 sum still accumulates in index order.
+      for (int64_t hc = h0; hc < h1; hc += 32) {
+        const int64_t hm = hc + lane;
+        const bool in = hm < h1;
+        const uint32_t my_f = in ? H.flags[hm] : 0u;
+        const int32_t my_g = in ? H.gid[hm] : EVG_HG_NONE;
+        const bool my_run = in && (my_f & EVG_HF_RUNNING) && (my_f & EVG_HF_RT_FOUND);
+        const int64_t my_e = my_run ? H.expected[hm] : 0, my_s = my_run ? H.stddev[hm] : 0, my_t = my_run ? H.start[hm] : 0;
+        const int cnt = int(h1 - hc < 32 ? h1 - hc : 32);
+        for (int j = 0; j < cnt; j++) {
+          const uint32_t f = __shfl_sync(full, my_f, j);
+          const int32_t g = __shfl_sync(full, my_g, j);
+          const int64_t he = __shfl_sync(full, my_e, j), hs = __shfl_sync(full, my_s, j), ht = __shfl_sync(full, my_t, j);
+          const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
+          const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
+          if (first) n_free_all += is_free;
+          if (g == EVG_HG_NONE) {
+            if (first && lane == 0) {
+              u_hosts++;
+              u_free += is_free;
+              if (running) u_soon = fadd64(u_soon, soon_free_term(now, he, hs, ht, threshold, c.future_host_fraction));
+            }
+          } else if (g >= gb && g < gb + ge && (g & 31) == lane) {
+            GroupScratch* s = sg + (g - gb);
+            s->n_hosts++;
+            s->n_free += is_free;
+            if (running) s->soon = fadd64(s->soon, soon_free_term(now, he, hs, ht, threshold, c.future_host_fraction));
           }
-        } else if (g >= 0 && g < g1 - g0 && (g & 31) == lane) {
-          GroupScratch* s = gs + g0 + g;
-          s->n_hosts++;
-          s->n_free += is_free;
-          if (running) s->soon = fadd64(s->soon, soon_free_term(now, he, hs, ht, threshold, c.future_host_fraction));
         }
       }
+      __syncwarp();
+      for (int64_t i = lane; i < ge; i += 32) gs[g0 + gb + i] = sg[i];
     }
     if (lane == 0) { s_nfree = n_free_all; s_uhosts = u_hosts; s_ufree = u_free; s_usoon = u_soon; }
   }
