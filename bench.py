@@ -145,6 +145,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_traffic(n_tasks: int):
+    """DRAM bytes of one launch of the roofline kernel: profiles/traffic.json holds dram__bytes_read + dram__bytes_write
+    per task from one `ncu --set full` capture of that kernel (named there); scaled to this run's task count."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        return {"bytes_per_launch": int(float(t["dram_bytes_per_task"]) * n_tasks), "bytes_per_task": float(t["dram_bytes_per_task"]),
+                "kernel": t.get("kernel"), "source": t.get("source")}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -543,6 +555,10 @@ def main():
                          "kernel_ms": task_ms, "algorithmic_bytes_per_launch": int(kb), "achieved": kb / (task_ms * 1e-3) / 1e9,
                          "frac": kb / (task_ms * 1e-3) / 1e9 / peak, "kernel_share_of_step": task_ms / ms_per_step,
                          "sort_ms": sort_ms, "sort_share_of_step": sort_ms / ms_per_step})
+            tr = load_traffic(T)
+            if tr and tr.get("kernel") == "k_gtask":
+                roof["traffic"] = tr["bytes_per_launch"]
+                roof["traffic_source"] = f"{tr['bytes_per_task']:.1f} B/task x {T} tasks; {tr['source']}"
         else:
             roof.update({"achieved": roof["whole_tick"]["achieved"], "frac": roof["whole_tick"]["frac"], "kernel": "whole tick"})
         line = {

@@ -665,17 +665,35 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
           const uint32_t dg = ((vmax - sKey[ci[j]]) >> shift) & mask;
           cr[j] = (FULL || seg0 + j * 32 + lane < seg1) ? dg : 0x7FFFu;
         }
+        // RB chunks per trip: their MATCHes, then their leader atomics (issued back to back -- one warp's shared-memory
+        // atomics execute in order, so chunk j+1's returned count includes chunk j's add), then their shuffles.  The
+        // returns are first needed by the shuffles, so RB atomic round trips overlap instead of queueing behind each other
+        // (the single-chunk form spent 14% of the kernel's stall samples waiting on that one dependent chain).
+#ifdef EVG_CTA_RB
+        constexpr int RB = EVG_CTA_RB;
+#else
+        constexpr int RB = (ITEMS % 4 == 0) ? 4 : 2;
+#endif
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) {
-          if (FULL || seg0 + j * 32 < seg1) {  // warp-uniform
-            const uint32_t dg = cr[j];
-            const unsigned peers = __match_any_sync(full, dg);
-            const uint32_t r = __popc(peers & lt);
-            const uint32_t sh = (dg & 1u) << 4;
-            uint32_t old = 0;
-            if (r == 0 && (FULL || dg != 0x7FFFu)) old = atomicAdd(&wc[dg >> 1], uint32_t(__popc(peers)) << sh);
-            old = __shfl_sync(full, old, __ffs(peers) - 1);
-            cr[j] = (dg & 0x3FFu) | ((((old >> sh) & 0xFFFFu) + r) << 10);
+        for (int j0 = 0; j0 < ITEMS; j0 += RB) {
+          unsigned peers[RB];
+          uint32_t old[RB];
+#pragma unroll
+          for (int b = 0; b < RB; b++) peers[b] = (FULL || seg0 + (j0 + b) * 32 < seg1) ? __match_any_sync(full, cr[j0 + b]) : 0u;
+#pragma unroll
+          for (int b = 0; b < RB; b++) {
+            const uint32_t dg = cr[j0 + b];
+            old[b] = 0;
+            if ((FULL || seg0 + (j0 + b) * 32 < seg1) && (peers[b] & lt) == 0u && (FULL || dg != 0x7FFFu))
+              old[b] = atomicAdd(&wc[dg >> 1], uint32_t(__popc(peers[b])) << ((dg & 1u) << 4));
+          }
+#pragma unroll
+          for (int b = 0; b < RB; b++) {
+            if (FULL || seg0 + (j0 + b) * 32 < seg1) {  // warp-uniform
+              const uint32_t dg = cr[j0 + b];
+              const uint32_t o = __shfl_sync(full, old[b], __ffs(peers[b]) - 1);
+              cr[j0 + b] = (dg & 0x3FFu) | ((((o >> ((dg & 1u) << 4)) & 0xFFFFu) + uint32_t(__popc(peers[b] & lt))) << 10);
+            }
           }
         }
       };

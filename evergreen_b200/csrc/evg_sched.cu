@@ -631,12 +631,14 @@ __global__ void __launch_bounds__(128, TPD == 32 ? 8 : 4) k_alloc(DHosts H, int3
         const uint32_t my_f = in ? H.flags[hm] : 0u;
         const int32_t my_g = in ? H.gid[hm] : EVG_HG_NONE;
         const bool my_run = in && (my_f & EVG_HF_RUNNING) && (my_f & EVG_HF_RT_FOUND);
-        const int64_t my_e = my_run ? H.expected[hm] : 0, my_s = my_run ? H.stddev[hm] : 0, my_t = my_run ? H.start[hm] : 0;
+        // every lane evaluates ITS host's soon-to-be-free term (allocator.go:357-378: an FP64 division and a dozen
+        // overflow-checked integer steps, independent of the bucket) -- the in-order replay below only adds it
+        const double my_term = my_run ? soon_free_term(now, H.expected[hm], H.stddev[hm], H.start[hm], threshold, c.future_host_fraction) : 0.0;
         const int cnt = int(h1 - hc < 32 ? h1 - hc : 32);
         for (int j = 0; j < cnt; j++) {
           const uint32_t f = __shfl_sync(full, my_f, j);
           const int32_t g = __shfl_sync(full, my_g, j);
-          const int64_t he = __shfl_sync(full, my_e, j), hs = __shfl_sync(full, my_s, j), ht = __shfl_sync(full, my_t, j);
+          const double term = __shfl_sync(full, my_term, j);
           const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
           const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
           if (first) n_free_all += is_free;
@@ -644,13 +646,13 @@ __global__ void __launch_bounds__(128, TPD == 32 ? 8 : 4) k_alloc(DHosts H, int3
             if (first && lane == 0) {
               u_hosts++;
               u_free += is_free;
-              if (running) u_soon = fadd64(u_soon, soon_free_term(now, he, hs, ht, threshold, c.future_host_fraction));
+              if (running) u_soon = fadd64(u_soon, term);
             }
           } else if (g >= gb && g < gb + ge && (g & 31) == lane) {
             GroupScratch* s = sg + (g - gb);
             s->n_hosts++;
             s->n_free += is_free;
-            if (running) s->soon = fadd64(s->soon, soon_free_term(now, he, hs, ht, threshold, c.future_host_fraction));
+            if (running) s->soon = fadd64(s->soon, term);
           }
         }
       }
