@@ -672,7 +672,7 @@ k_plan_cta(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list, int6
 #ifdef EVG_CTA_RB
         constexpr int RB = EVG_CTA_RB;
 #else
-        constexpr int RB = (ITEMS % 4 == 0) ? 4 : 2;
+        constexpr int RB = 1;  // measured on configs[1]: 1 chunk per trip 0.339 ms, 2 -> 0.354, 4 -> 0.357 (the extra live registers spill)
 #endif
 #pragma unroll
         for (int j0 = 0; j0 < ITEMS; j0 += RB) {

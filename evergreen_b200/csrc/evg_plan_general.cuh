@@ -864,18 +864,22 @@ __device__ __forceinline__ void gscatter_tile(int j, const DGen& G, int tile, in
     kh[k] = (ok && wide) ? src_hi[i] : 0u;
     ix[k] = ok ? src_ix[i] : 0u;
   }
+  // all eight MATCHes, then the eight leader atomics back to back (one warp's shared-memory atomics execute in issue
+  // order: chunk k+1's returned count includes chunk k's add), then the shuffles: the atomic round trips overlap
+  unsigned peers[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const int i = (warp * 8 + k) * 32 + lane;
-    const bool ok = i < cnt;
-    dg[k] = ok ? (((use_hi ? kh[k] : kl[k]) >> shift) & 255u) : 256u;
-    const unsigned peers = __match_any_sync(0xffffffffu, dg[k]);
-    const uint32_t r = __popc(peers & lt);
-    uint32_t old = 0;
-    if (ok && r == 0) old = atomicAdd(&wcnt[warp][dg[k]], uint32_t(__popc(peers)));
-    old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
-    rk[k] = old + r;
+    dg[k] = i < cnt ? (((use_hi ? kh[k] : kl[k]) >> shift) & 255u) : 256u;
+    peers[k] = __match_any_sync(0xffffffffu, dg[k]);
   }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    rk[k] = 0;
+    if (dg[k] < 256u && (peers[k] & lt) == 0u) rk[k] = atomicAdd(&wcnt[warp][dg[k]], uint32_t(__popc(peers[k])));
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) rk[k] = __shfl_sync(0xffffffffu, rk[k], __ffs(peers[k]) - 1) + uint32_t(__popc(peers[k] & lt));
   __syncthreads();
   {  // thread = digit: the eight warp counters become offsets inside the digit; the digit totals are scanned over the block
     uint32_t x[8], tot = 0;

@@ -104,6 +104,7 @@ constexpr int kCapA = 128 * 8, kCapB = 256 * 16, kCapC = EVG_C_THREADS * EVG_C_I
 constexpr int64_t kWideAllocGroups = 1024;  // k_alloc<128> (a block per distro) once some distro has more task groups
 constexpr int kCapW = 32;  // k_plan_warp: one warp per distro
 constexpr int64_t kGrouplessHosts = 64;  // k_alloc_groupless walks a distro's hosts with one thread: only short walks
+constexpr int64_t kBigUnitTasks = 128;  // GroupVersions distros above this size in k_plan_smem's smallest class count as a class of their own
 constexpr int64_t kSparseClass = 64;  // a k_plan_smem class of 1025+ task distros with fewer members than this goes to the general path
 // second-generation on-chip planner classes <THREADS, CAP, CTAs per SM> (evg_plan_cta.cuh)
 constexpr int kNT_A = 128, kNCapA = 1280, kNOccA = 8;
@@ -623,42 +624,44 @@ __global__ void __launch_bounds__(128, TPD == 32 ? 8 : 4) k_alloc(DHosts H, int3
       const int64_t ge = ng - gb < kCache ? ng - gb : kCache;  // groups of this stretch: [gb, gb + ge)
       for (int64_t i = lane; i < ge; i += 32) { sg[i].n_hosts = 0; sg[i].n_free = 0; sg[i].soon = 0.0; }
       __syncwarp();
-      // 32 hosts per trip: lane L loads host hc + L (coalesced, one round trip for the chunk), then the chunk is replayed
-      // in host order through shuffles -- every bucket's FP64 sum still accumulates in index order.
+      // 32 hosts per trip: lane L loads host hc + L (coalesced) and evaluates ITS host's soon-to-be-free term
+      // (allocator.go:357-378: an FP64 division and a dozen overflow-checked integer steps, independent of the bucket).
+      // Everything that is a COUNT is order-free and taken in parallel (lane-local counters, shared-memory atomics on the
+      // bucket); only the FP64 sums need host order, so only the RUNNING hosts of this stretch are replayed in index
+      // order through shuffles, the bucket's owner lane adding the term.
       for (int64_t hc = h0; hc < h1; hc += 32) {
         const int64_t hm = hc + lane;
         const bool in = hm < h1;
         const uint32_t my_f = in ? H.flags[hm] : 0u;
-        const int32_t my_g = in ? H.gid[hm] : EVG_HG_NONE;
+        const int32_t my_g = in ? H.gid[hm] : -2;
+        const bool my_free = in && !(my_f & EVG_HF_RUNNING) && !(my_f & EVG_HF_TEARDOWN);
         const bool my_run = in && (my_f & EVG_HF_RUNNING) && (my_f & EVG_HF_RT_FOUND);
-        // every lane evaluates ITS host's soon-to-be-free term (allocator.go:357-378: an FP64 division and a dozen
-        // overflow-checked integer steps, independent of the bucket) -- the in-order replay below only adds it
+        const bool my_none = in && my_g == EVG_HG_NONE;
+        const bool my_here = in && my_g >= gb && my_g < gb + ge;  // a bucket of this stretch
         const double my_term = my_run ? soon_free_term(now, H.expected[hm], H.stddev[hm], H.start[hm], threshold, c.future_host_fraction) : 0.0;
-        const int cnt = int(h1 - hc < 32 ? h1 - hc : 32);
-        for (int j = 0; j < cnt; j++) {
-          const uint32_t f = __shfl_sync(full, my_f, j);
+        if (first) {
+          n_free_all += my_free;
+          u_hosts += my_none;
+          u_free += my_none && my_free;
+        }
+        if (my_here) {
+          atomicAdd(&sg[my_g - gb].n_hosts, 1);
+          if (my_free) atomicAdd(&sg[my_g - gb].n_free, 1);
+        }
+        unsigned todo = __ballot_sync(full, my_run && (my_here || (first && my_none)));
+        while (todo) {  // warp-uniform
+          const int j = __ffs(todo) - 1;
+          todo &= todo - 1u;
           const int32_t g = __shfl_sync(full, my_g, j);
           const double term = __shfl_sync(full, my_term, j);
-          const bool is_free = !(f & EVG_HF_RUNNING) && !(f & EVG_HF_TEARDOWN);
-          const bool running = (f & EVG_HF_RUNNING) && (f & EVG_HF_RT_FOUND);
-          if (first) n_free_all += is_free;
-          if (g == EVG_HG_NONE) {
-            if (first && lane == 0) {
-              u_hosts++;
-              u_free += is_free;
-              if (running) u_soon = fadd64(u_soon, term);
-            }
-          } else if (g >= gb && g < gb + ge && (g & 31) == lane) {
-            GroupScratch* s = sg + (g - gb);
-            s->n_hosts++;
-            s->n_free += is_free;
-            if (running) s->soon = fadd64(s->soon, term);
-          }
+          if (g == EVG_HG_NONE) { if (lane == 0) u_soon = fadd64(u_soon, term); }
+          else if (((g - int32_t(gb)) & 31) == lane) sg[g - gb].soon = fadd64(sg[g - gb].soon, term);
         }
       }
       __syncwarp();
       for (int64_t i = lane; i < ge; i += 32) gs[g0 + gb + i] = sg[i];
     }
+    n_free_all = warp_sum64(n_free_all); u_hosts = warp_sum64(u_hosts); u_free = warp_sum64(u_free);  // lane-local counts
     if (lane == 0) { s_nfree = n_free_all; s_uhosts = u_hosts; s_ufree = u_free; s_usoon = u_soon; }
   }
   team_sync();
@@ -892,15 +895,16 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
     if (narrow && n <= kNCapA && g <= kGA) return 1;
     if (narrow && n <= kNCapB && g <= kGB) return 2;
     if (narrow && n <= kNCapC && g <= kGC) return 3;
-    if (n <= kCapA) return 4;
+    if (n <= kCapA) return (cf.group_versions && n > kBigUnitTasks) ? 8 : 4;  // 8: version units of dozens of tasks, walked member by member
     if (n <= kCapB) return 5;
     if (n <= kCapC) return 6;
     return 7;
   };
   // k_plan_smem walks the unit lists of GroupVersions / dependency distros with ONE CTA per distro: fine when a class
   // has enough distros to fill the GPU, a millisecond-long tail when it has a handful (configs[4]: ~20 distros of 1-6k
-  // tasks held the whole tick).  The general path spreads every distro over all SMs, so sparse classes go there.
-  int64_t n_class[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // tasks held the whole tick, then ~50 GroupVersions distros of 129-1024 tasks whose version units are walked member by
+  // member).  The general path spreads every distro over all SMs, so sparse classes go there.
+  int64_t n_class[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int32_t d = 0; d < D; d++) {
     const int64_t a = dt->task_off[d], b = dt->task_off[d + 1];
     if (d == 0 && (a != 0 || dt->group_off[0] != 0)) return fail(EVG_ERR_INVALID, "offsets must start at 0");
@@ -911,6 +915,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   const char* sparse_env = getenv("EVG_SPARSE_CLASS");  // tests set 0 to keep every class on its own kernel
   const int64_t sparse = sparse_env ? atoll(sparse_env) : kSparseClass;
   const bool sparse_b = n_class[5] > 0 && n_class[5] < sparse, sparse_c = n_class[6] > 0 && n_class[6] < sparse;
+  const bool sparse_v = n_class[8] > 0 && n_class[8] < sparse;
   for (int32_t d = 0; d < D; d++) {
     const int64_t a = dt->task_off[d], b = dt->task_off[d + 1];
     const int64_t ga = dt->group_off[d], gb = dt->group_off[d + 1];
@@ -923,6 +928,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
     const int64_t de = (E > 0) ? (edge_off ? edge_off[d + 1] - edge_off[d] : t->dep_off[b] - t->dep_off[a]) : 0;
     int cls = classify(d);
     if ((cls == 5 && sparse_b) || (cls == 6 && sparse_c)) cls = 7;
+    if (cls == 8) cls = sparse_v ? 7 : 4;
     switch (cls) {
       case 0: listW.push_back(d); route[d] = 1; break;
       case 1: listNA.push_back(d); route[d] = 1; break;
