@@ -584,15 +584,18 @@ __device__ int eval_group(const evg_alloc_cfg& c, const evg_group_info& info, in
 // g) does that bucket's updates, so every bucket's FP64 sum is accumulated in host order while buckets proceed
 // in parallel.  The team then evaluates the task groups; per-group results are integers, so the reduction is exact.
 template <int TPD>
-__global__ void __launch_bounds__(128, TPD == 32 ? 8 : 4) k_alloc(DHosts H, int32_t d_begin, int32_t n_distros, const int64_t* group_off,
+__global__ void __launch_bounds__(128, TPD == 32 ? 6 : 4) k_alloc(DHosts H, int32_t d_begin, int32_t n_distros, const int64_t* group_off,
                                                const evg_queue_info* qinfo, evg_group_info* ginfo, GroupScratch* gs,
-                                               int64_t now, evg_alloc_result* result, int32_t* status, int skip_groupless) {
+                                               int64_t now, evg_alloc_result* result, int32_t* status, int skip_groupless,
+                                               const int32_t* list, int32_t n_list) {
   constexpr int TEAMS = 128 / TPD, TW = TPD / 32;  // teams per block, warps per team
   const int team = threadIdx.x / TPD, tt = threadIdx.x % TPD;
-  const int d = d_begin + int(blockIdx.x) * TEAMS + team;
+  const int ti = int(blockIdx.x) * TEAMS + team;
+  if (list && ti >= n_list) return;  // team-uniform; a team never shares a barrier with another
+  const int d = list ? list[ti] : d_begin + ti;  // `list`: the distros k_alloc_groupless does not take (built at upload)
   const int lane = threadIdx.x & 31, warp = tt >> 5;
   const unsigned full = 0xffffffffu;
-  if (d >= n_distros) return;  // team-uniform (n_distros = end of the range); a team never shares a barrier with another
+  if (d >= n_distros) return;  // team-uniform (n_distros = end of the range)
   auto team_sync = [&]() { if (TPD == 128) __syncthreads(); else __syncwarp(); };
   __shared__ long long sh_nfree[TEAMS], sh_uhosts[TEAMS], sh_ufree[TEAMS], sh_req[TEAMS][TW], sh_fre[TEAMS][TW];
   __shared__ double sh_usoon[TEAMS];
@@ -829,6 +832,9 @@ struct evg_ctx {
   DevBuf b_punt, b_puntcnt;
   int32_t nW = 0, nA = 0, nB = 0, nC = 0, nNA = 0, nNB = 0, nNC = 0, n_general = 0;  // distros per route
   std::vector<int32_t> h_listW, h_listA, h_listB, h_listC, h_listNA, h_listNB, h_listNC;  // host copies (ascending distro ids)
+  DevBuf b_alist;            // distros k_alloc plans itself (task groups, or more than kGrouplessHosts hosts), listed by upload_hosts
+  int64_t n_alist = 0;
+  bool alist_valid = false;
   DevBuf b_lptA, b_lptB, b_lptC, b_lptNA, b_lptNB, b_lptNC;  // the same lists, largest distro first: the resident tick's launch order
   std::vector<int64_t> h_taskoff, h_groupoff, h_unitbase, h_edgeoff, h_dtileoff;
   std::vector<int32_t> h_listG;
@@ -1090,6 +1096,7 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
   c->h_dtileoff.swap(dtile_off);
   c->h_listG.swap(listG);
   c->have_tasks = true;
+  c->alist_valid = false;  // upload_hosts lists the allocator's distros against THIS table
   c->have_hosts = false;
   if ((copy_columns || adopt) && T > 0) {  // range-check the ids the kernels index with (the pipelined call checks chunk by chunk)
     DTasks dtv = dtasks(c);
@@ -1122,6 +1129,16 @@ int upload_hosts(evg_ctx* c, const evg_host_soa* h, const int64_t* host_off, con
   UP(c->b_hstart, h->start_ns, H, int64_t);
   if (D > 0) UP(c->b_hostoff, host_off, D + 1, int64_t);
   UP(c->b_acfg, acfg, D, evg_alloc_cfg);
+  c->alist_valid = false;
+  std::vector<int32_t> alist;
+  if (c->have_tasks && c->Dn == D && int64_t(c->h_groupoff.size()) == int64_t(D) + 1) {
+    for (int32_t d = 0; d < D; d++)
+      if (c->h_groupoff[d + 1] != c->h_groupoff[d] || host_off[d + 1] - host_off[d] > kGrouplessHosts) alist.push_back(d);
+    UP(c->b_alist, alist.data(), int64_t(alist.size()), int32_t);
+    CK(cudaStreamSynchronize(s));  // `alist` is a local
+    c->n_alist = int64_t(alist.size());
+    c->alist_valid = true;
+  }
   CK(c->b_result.ensure(sizeof(evg_alloc_result) * size_t(D + 1)));
   CK(c->b_status.ensure(sizeof(int32_t) * size_t(D + 1)));
   c->H = H;
@@ -1204,12 +1221,16 @@ int run_alloc_range(evg_ctx* c, int64_t now, int32_t d0, int32_t d1) {
   // a warp per distro (four per block) unless some distro has thousands of task groups, then a block per distro
   // ... and a thread per distro for the distros that have no task groups, when there are enough distros for that to matter
   const int split = (d1 - d0) >= 4096 ? 1 : 0;
+  // ... and only for the distros it has to take when the upload listed them (whole-table ranges)
+  const bool listed = split && c->alist_valid && d0 == 0 && d1 == c->Dn;
+  const int32_t* al = listed ? c->b_alist.as<int32_t>() : nullptr;
+  const int64_t teams = listed ? c->n_alist : int64_t(d1 - d0);
   if (c->max_groups > kWideAllocGroups)
-    LAUNCH(c, k_alloc<128>, unsigned(d1 - d0), 128, h, d0, d1, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
-           c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>(), split);
+    LAUNCH(c, k_alloc<128>, unsigned(teams), 128, h, d0, d1, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
+           c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>(), split, al, int32_t(c->n_alist));
   else
-    LAUNCH(c, k_alloc<32>, grid_for(d1 - d0, 4), 128, h, d0, d1, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
-           c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>(), split);
+    LAUNCH(c, k_alloc<32>, grid_for(teams, 4), 128, h, d0, d1, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(),
+           c->b_ginfo.as<evg_group_info>(), c->b_gs.as<GroupScratch>(), now, c->result_ptr(), c->b_status.as<int32_t>(), split, al, int32_t(c->n_alist));
   if (split)
     LAUNCH(c, k_alloc_groupless, grid_for(d1 - d0, 128), 128, h, d0, d1, c->b_groupoff.as<int64_t>(), c->b_qinfo.as<evg_queue_info>(), now,
            c->result_ptr(), c->b_status.as<int32_t>());
@@ -1874,6 +1895,7 @@ int evg_alloc_batch(evg_ctx* c, const evg_host_soa* hosts, const int64_t* host_o
   CK(cudaSetDevice(c->device));
   const int64_t G = n_distros > 0 ? group_off[n_distros] : 0;
   if (G > 0 && !groups) return fail(EVG_ERR_INVALID, "evg_alloc_batch: groups is null");
+  c->have_tasks = false;  // the resident planner inputs no longer match the tables of this call (and upload_hosts must not list distros from them)
   int rc = upload_hosts(c, hosts, host_off, cfg, n_distros);
   if (rc != EVG_OK) return rc;
   cudaStream_t s = c->stream;

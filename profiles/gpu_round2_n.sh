@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-tag=${1:-n}
+tag=${1:-o}
 timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?" > gpurun_out/env_$tag.txt
 : > gpurun_out/gen_$tag.txt
 for w in c5 c3 plain 1m c2; do timeout 300 python profiles/prof_general.py $w 20 >> gpurun_out/gen_$tag.txt 2>&1; done
