@@ -15,7 +15,8 @@ def launches(path):
     rows = list(csv.DictReader(lines))
     names = [(r["Kernel Name"].split("(")[0], float(r["Metric Value"].replace(",", ""))) for r in rows]
     # one step = from one k_plan_smem/k_init_bits launch sequence start to the next k_alloc (inclusive)
-    ends = [i for i, (n, _) in enumerate(names) if "k_alloc" in n]
+    # a tick ends with its last allocator kernel (k_alloc<..>, then k_alloc_groupless when the tick has one)
+    ends = [i for i, (n, _) in enumerate(names) if "k_alloc" in n and (i + 1 == len(names) or "k_alloc" not in names[i + 1][0])]
     print(f"# ncu launch list ({len(names)} launches; `--metrics gpu__time_duration.sum --clock-control none`)\n")
     print("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n")
     def table(seg, title):
