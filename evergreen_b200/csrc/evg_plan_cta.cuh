@@ -1,7 +1,7 @@
 // evg_plan_cta.cuh -- k_plan_cta<THREADS, CAP>: the on-chip planner, second generation.
 //
 // One CTA plans one distro of up to CAP tasks entirely on-chip, like k_plan_smem (evg_plan_smem.cuh), but sized so
-// that SEVERAL CTAs share an SM (2 x 512 threads for 10240-task distros, 4 x 256 for 5120, 8 x 128 for 1280): while
+// that SEVERAL CTAs share an SM (2 x 512 threads for 10240-task distros, 4 x 256 for 5120, 8 x 128 for 1280, 16 x 64 for 384): while
 // one distro sorts (shared-memory / MATCH bound) its neighbour scores tasks (ALU bound), and nobody idles at the
 // other's barriers.  What makes it fit:
 //   * TotalValue is kept as a u32 (4 B/task instead of 8).  Every production queue has values far below 2^32; a
@@ -30,7 +30,7 @@
 
 template <int THREADS>
 struct CtaDigit {
-  static constexpr int kBits = THREADS >= 512 ? 10 : (THREADS >= 256 ? 9 : 8);  // 2^bits == 2*THREADS: one u32 counter pair per thread in the scan
+  static constexpr int kBits = THREADS >= 512 ? 10 : (THREADS >= 256 ? 9 : (THREADS >= 128 ? 8 : 7));  // 2^bits == 2*THREADS: one u32 counter pair per thread in the scan
 };
 
 // Tasks per thread and tile of the task pass.  2: one 2*THREADS-task stage, refilled as soon as every thread has its two

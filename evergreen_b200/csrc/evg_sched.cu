@@ -108,6 +108,9 @@ constexpr int64_t kBigUnitTasks = 128;  // GroupVersions distros above this size
 constexpr int64_t kSparseClass = 64;  // a k_plan_smem class of 1025+ task distros with fewer members than this goes to the general path
 // second-generation on-chip planner classes <THREADS, CAP, CTAs per SM> (evg_plan_cta.cuh)
 constexpr int kNT_A = 128, kNCapA = 1280, kNOccA = 8;
+// the smallest k_plan_cta class: a launch list's distros of at most 384 tasks (and few task groups) take 64-thread CTAs,
+// sixteen per SM -- twice the distros in flight (configs[3] "total": 10 000 distros of 100 tasks)
+constexpr int kNT_S = 64, kNCapS = 384, kNOccS = 16;
 constexpr int kNT_B = 256, kNCapB = 5120, kNOccB = 4;
 constexpr int kNT_C = 512, kNCapC = 10240, kNOccC = 2;
 constexpr uint32_t kInactive = 0xFFFFFFFFu;  // next[]: pair not linked / head[]: empty list
@@ -831,6 +834,7 @@ struct evg_ctx {
   DevBuf b_route, b_listW, b_listA, b_listB, b_listC, b_listG, b_listNA, b_listNB, b_listNC, b_unitv, b_unita, b_unitn, b_unitmask;
   DevBuf b_punt, b_puntcnt;
   int32_t nW = 0, nA = 0, nB = 0, nC = 0, nNA = 0, nNB = 0, nNC = 0, n_general = 0;  // distros per route
+  int32_t nNA_big = 0;  // leading entries of the largest-first NA list that need the 128-thread instance
   std::vector<int32_t> h_listW, h_listA, h_listB, h_listC, h_listNA, h_listNB, h_listNC;  // host copies (ascending distro ids)
   DevBuf b_alist;            // distros k_alloc plans itself (task groups, or more than kGrouplessHosts hosts), listed by upload_hosts
   int64_t n_alist = 0;
@@ -1020,6 +1024,11 @@ int upload_tasks(evg_ctx* c, const evg_task_soa* t, const evg_distro_table* dt, 
     std::stable_sort(v->begin(), v->end(), [&](int32_t x, int32_t y) {
       return dt->task_off[x + 1] - dt->task_off[x] > dt->task_off[y + 1] - dt->task_off[y];
     });
+  // the tail of the smallest class that fits the 64-thread instance (size AND task groups) goes last, largest first
+  constexpr int kGS = PlanCta<kNT_S, kNCapS>::kGroupCap;
+  auto fits_s = [&](int32_t x) { return dt->task_off[x + 1] - dt->task_off[x] <= kNCapS && dt->group_off[x + 1] - dt->group_off[x] <= kGS; };
+  std::stable_partition(lptNA.begin(), lptNA.end(), [&](int32_t x) { return !fits_s(x); });
+  c->nNA_big = int32_t(std::count_if(lptNA.begin(), lptNA.end(), [&](int32_t x) { return !fits_s(x); }));
   UP(c->b_lptA, lptA.data(), int64_t(lptA.size()), int32_t);
   UP(c->b_lptB, lptB.data(), int64_t(lptB.size()), int32_t);
   UP(c->b_lptC, lptC.data(), int64_t(lptC.size()), int32_t);
@@ -1398,7 +1407,8 @@ int run_plan(evg_ctx* c, int64_t now, uint32_t opts) {
     if ((rc = launch_cta<kNT_C, kNCapC, kNOccC>(c, st(0), dt, dd, w, c->b_lptNC.as<int32_t>(), c->nNC, now, pl, pc)) != EVG_OK) return rc;
     if (time_it) { CK(cudaEventRecord(c->ring1[slot], st(0))); c->runs++; c->sort_slot = slot; }
     if ((rc = launch_cta<kNT_B, kNCapB, kNOccB>(c, st(0), dt, dd, w, c->b_lptNB.as<int32_t>(), c->nNB, now, pl, pc)) != EVG_OK) return rc;
-    if ((rc = launch_cta<kNT_A, kNCapA, kNOccA>(c, st(0), dt, dd, w, c->b_lptNA.as<int32_t>(), c->nNA, now, pl, pc)) != EVG_OK) return rc;
+    if ((rc = launch_cta<kNT_A, kNCapA, kNOccA>(c, st(0), dt, dd, w, c->b_lptNA.as<int32_t>(), c->nNA_big, now, pl, pc)) != EVG_OK) return rc;
+    if ((rc = launch_cta<kNT_S, kNCapS, kNOccS>(c, st(0), dt, dd, w, c->b_lptNA.as<int32_t>() + c->nNA_big, c->nNA - c->nNA_big, now, pl, pc)) != EVG_OK) return rc;
     if ((rc = launch_smem<EVG_C_THREADS, EVG_C_ITEMS, 1>(c, st(0), dt, dd, w, pl, n_new, now, 0, pc)) != EVG_OK) return rc;
   }
   // --- streams 1..3: first-generation classes (GroupVersions, in-queue dependency edges, very many task groups)

@@ -23,6 +23,10 @@ elif which == "c5":  # BASELINE configs[4]: 100k power-law distros, every route 
     w = synth.config(5)
 elif which == "c2":
     w = synth.config(2)
+elif which == "c4":  # BASELINE configs[3], total reading: 10k distros, 1M tasks, 50k hosts
+    w = synth.config(4)
+elif which == "c3t":  # BASELINE configs[2], total reading: 10k distros, 100k tasks
+    w = synth.config(3)
 else:
     w = synth.make(np.full(48, 100000), synth.SEED_BASE + 3, tg_frac=0.0, zipf_priority=True, n_hosts=96)
 eng.upload(w.tasks, w.distros, w.hosts)
