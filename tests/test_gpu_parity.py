@@ -724,10 +724,10 @@ def test_c2_full_size_every_distro_every_tick(engine):
 
 # ---------------------------------------------------------------- round 2: second-generation planners
 def test_cta_class_boundaries(engine):
-    """Sizes on both sides of every k_plan_cta class (1280 / 5120 / 10240 tasks) and of the k_plan_smem class above
+    """Sizes on both sides of every k_plan_cta class (384 / 1280 / 5120 / 10240 tasks) and of the k_plan_smem class above
     it, with task groups only (the shape k_plan_cta plans) -- and the same sizes with in-queue dependencies, which
     must be routed to k_plan_smem / the general path instead."""
-    sizes = np.array([33, 1279, 1280, 1281, 5119, 5120, 5121, 10239, 10240, 10241, 12288, 12289, 64, 0, 1])
+    sizes = np.array([33, 1279, 1280, 1281, 5119, 5120, 5121, 10239, 10240, 10241, 12288, 12289, 64, 0, 1, 383, 384, 385, 129])
     w = synth.make(sizes, 201, zipf_priority=True, tg_frac=0.15, custom_factor_frac=0.4, n_hosts=150, providers=(0.7, 0.2, 0.1))
     po, ao = run(engine, w)
     parity.check_properties(w, po, ao)
