@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-tag=${1:-p}
+tag=${1:-q}
 timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q --maxfail=40 > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?" > gpurun_out/env_$tag.txt
 : > gpurun_out/gen_$tag.txt
 for w in c4 c3t c5 c2; do timeout 300 python profiles/prof_general.py $w 20 >> gpurun_out/gen_$tag.txt 2>&1; done
