@@ -161,6 +161,7 @@ SYMBOLS = {
     "evg_upload": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "evg_upload_device": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "evg_update_tasks": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "evg_plan_from_finder": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P]),
     "evg_run_resident": (C.c_int, [_P, C.c_int64, C.c_uint32]),
     "evg_download": (C.c_int, [_P, _P, _P]),
     "evg_download_queue": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int64]),

@@ -830,6 +830,7 @@ struct evg_ctx {
   DevBuf b_taskoff, b_groupoff, b_cfg, b_gmax, b_unitbase;
   DevBuf b_hasdep, b_head, b_next, b_pslot, b_etask, b_elive, b_ca, b_crk, b_bestpair;
   DevBuf b_rn0, b_rn1, b_rn2, b_rn3, b_rn4, b_rn5, b_rn6, b_rn7;
+  DevBuf b_pf[36];  // evg_plan_from_finder: finder tables, candidate columns, compacted columns, edge scratch
   DevBuf b_err, b_dx0, b_dx1, b_dx2, b_dx3, b_dx4, b_dx5, b_dx6, b_dx7;
   DevBuf b_route, b_listW, b_listA, b_listB, b_listC, b_listG, b_listNA, b_listNB, b_listNC, b_unitv, b_unita, b_unitn, b_unitmask;
   DevBuf b_punt, b_puntcnt;
@@ -1493,6 +1494,8 @@ void evg_shutdown(evg_ctx* c) {
                    &c->b_qinfo, &c->b_ginfo, &c->b_order, &c->b_tv, &c->b_bd, &c->b_hflags, &c->b_hgid, &c->b_hexp, &c->b_hstd,
                    &c->b_hstart, &c->b_hostoff, &c->b_acfg, &c->b_gs, &c->b_result, &c->b_status};
   for (DevBuf* b : all) b->release();
+  for (DevBuf& b : c->b_pf) b.release();
+  c->b_alist.release();
   for (int k = 0; k < evg_ctx::kRing; k++) { if (c->ring0[k]) cudaEventDestroy(c->ring0[k]); if (c->ring1[k]) cudaEventDestroy(c->ring1[k]); }
   cudaEventDestroy(c->ev_begin); cudaEventDestroy(c->ev_sort0); cudaEventDestroy(c->ev_sort1); cudaEventDestroy(c->ev_end);
   cudaEventDestroy(c->ev_gt0); cudaEventDestroy(c->ev_gt1);
@@ -2154,6 +2157,281 @@ int evg_find_runnable_batch(evg_ctx* c, const evg_runnable_in* in, int32_t* runn
   CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (bad) return fail(EVG_ERR_INVALID, "a project row or dep_ref is out of range");
+  return EVG_OK;
+}
+
+// --------------------------------------------------------------------------
+// evg_plan_from_finder: finder -> dependency predicate -> compaction -> resident planner inputs, all on the device
+// --------------------------------------------------------------------------
+struct PfCols {  // nine planner columns, candidate table (src) and compacted table (dst)
+  const int32_t *priority, *numdep, *tgo, *gid, *vid;
+  const uint32_t* flags;
+  const int64_t *expected, *qbasis, *wbasis;
+  int32_t *o_priority, *o_numdep, *o_tgo, *o_gid, *o_vid;
+  uint32_t* o_flags;
+  int64_t *o_expected, *o_qbasis, *o_wbasis;
+};
+// One thread per KEPT task: its row of the candidate table moves to its place in the compacted table; the
+// EVG_TF_DEPS_MET bit and the stamped wait basis come from the device's own evaluation (k_deps_met), like
+// evg_upload_with_deps.  new_idx[candidate row] = distro-local index in the compacted queue (memset to -1 before).
+__global__ void __launch_bounds__(256) k_pf_gather(int64_t n_new, int32_t D, const int64_t* __restrict__ new_off, const int64_t* __restrict__ cand_off,
+                                                   const int32_t* __restrict__ kept, PfCols C, const uint8_t* __restrict__ met,
+                                                   const int64_t* __restrict__ met_time, int32_t* __restrict__ new_idx, int64_t* __restrict__ src_row) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int d = block_find_distro(new_off, D, i, n_new);
+  if (d < 0) return;
+  const int64_t k = i - new_off[d];
+  const int64_t src = cand_off[d] + kept[cand_off[d] + k];
+  C.o_priority[i] = C.priority[src]; C.o_numdep[i] = C.numdep[src]; C.o_tgo[i] = C.tgo[src]; C.o_gid[i] = C.gid[src]; C.o_vid[i] = C.vid[src];
+  C.o_expected[i] = C.expected[src]; C.o_qbasis[i] = C.qbasis[src];
+  C.o_flags[i] = (C.flags[src] & ~EVG_TF_DEPS_MET) | ((met[src] & 1) ? EVG_TF_DEPS_MET : 0u);
+  const int64_t wb = C.wbasis[src], st = met_time[src];
+  C.o_wbasis[i] = (st != EVG_TIME_ZERO && st > wb) ? st : wb;
+  new_idx[src] = int32_t(k);
+  src_row[i] = src;
+}
+// in-queue dependency edges that survive: both ends kept
+__global__ void __launch_bounds__(256) k_pf_edge_count(int64_t n_new, int32_t D, const int64_t* __restrict__ new_off, const int64_t* __restrict__ cand_off,
+                                                       const int64_t* __restrict__ src_row, const int64_t* __restrict__ dep_off,
+                                                       const int32_t* __restrict__ dep_idx, const int32_t* __restrict__ new_idx, int32_t* __restrict__ cnt) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int d = block_find_distro(new_off, D, i, n_new);
+  if (d < 0) return;
+  const int64_t src = src_row[i], cb = cand_off[d];
+  int32_t n = 0;
+  for (int64_t e = dep_off[src]; e < dep_off[src + 1]; e++) n += new_idx[cb + dep_idx[e]] >= 0;
+  cnt[i] = n;
+}
+__global__ void __launch_bounds__(256) k_pf_edge_write(int64_t n_new, int32_t D, const int64_t* __restrict__ new_off, const int64_t* __restrict__ cand_off,
+                                                       const int64_t* __restrict__ src_row, const int64_t* __restrict__ dep_off,
+                                                       const int32_t* __restrict__ dep_idx, const int32_t* __restrict__ new_idx,
+                                                       const int64_t* __restrict__ o_dep_off, int32_t* __restrict__ o_dep_idx) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int d = block_find_distro(new_off, D, i, n_new);
+  if (d < 0) return;
+  const int64_t src = src_row[i], cb = cand_off[d];
+  int64_t w = o_dep_off[i];
+  for (int64_t e = dep_off[src]; e < dep_off[src + 1]; e++) {
+    const int32_t j = new_idx[cb + dep_idx[e]];
+    if (j >= 0) o_dep_idx[w++] = j;
+  }
+}
+// exclusive scan of int32 counts into int64 offsets (n + 1 entries), three launches
+__global__ void __launch_bounds__(1024) k_scan_blocks(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out, int64_t* __restrict__ block_sum) {
+  __shared__ int64_t sw[32];
+  const int64_t i = int64_t(blockIdx.x) * 1024 + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t v = i < n ? in[i] : 0;
+  int64_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+  if (lane == 31) sw[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int64_t w = sw[lane];
+    int64_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += y; }
+    sw[lane] = winc - w;
+    if (lane == 31) block_sum[blockIdx.x] = winc;
+  }
+  __syncthreads();
+  if (i < n) out[i] = sw[warp] + inc - v;
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(int64_t* __restrict__ block_sum, int64_t nb) {  // one block
+  __shared__ int64_t sw[32];
+  __shared__ int64_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t c0 = 0; c0 < nb; c0 += 1024) {
+    const int64_t i = c0 + threadIdx.x;
+    const int64_t v = i < nb ? block_sum[i] : 0;
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) sw[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int64_t w = sw[lane];
+      int64_t winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += y; }
+      sw[lane] = winc - w;
+    }
+    __syncthreads();
+    const int64_t ex = carry + sw[warp] + inc - v;
+    if (i < nb) block_sum[i] = ex;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = ex + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) block_sum[nb] = carry;  // the grand total
+}
+__global__ void __launch_bounds__(1024) k_scan_add(int64_t* __restrict__ out, int64_t n, const int64_t* __restrict__ block_sum, int64_t nb) {
+  const int64_t i = int64_t(blockIdx.x) * 1024 + threadIdx.x;
+  if (i < n) out[i] += block_sum[blockIdx.x];
+  if (i == 0) out[n] = block_sum[nb];
+}
+
+int evg_plan_from_finder(evg_ctx* c, const evg_runnable_in* in, const evg_task_soa* cand, const evg_distro_table* distros,
+                         const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg, const int64_t* dep_finished_ns,
+                         int64_t now_ns, int32_t* runnable, int64_t* count) {
+  if (!c || !in || !cand || !distros) return fail(EVG_ERR_INVALID, "evg_plan_from_finder: null argument");
+  LOCK(c);
+  const int64_t T = in->n_tasks, E = cand->n_edges;
+  const int32_t D = in->n_distros, P = in->n_projects;
+  if (T < 0 || D < 0 || P < 0 || E < 0) return fail(EVG_ERR_INVALID, "negative sizes");
+  if (cand->n_tasks != T || distros->n_distros != D) return fail(EVG_ERR_INVALID, "the candidate table, the finder table and the distro table disagree on their sizes");
+  if (D == 0) return T == 0 ? evg_upload(c, cand, distros, hosts, host_off, acfg) : fail(EVG_ERR_INVALID, "tasks without distros");
+  if (!count) return fail(EVG_ERR_INVALID, "null count");
+  if (!in->task_off || !in->valid_off || !in->finder || !distros->task_off) return fail(EVG_ERR_INVALID, "null distro arrays");
+  if (T > 0 && (!in->sched || !in->project)) return fail(EVG_ERR_INVALID, "null task column");
+  if (P > 0 && !in->project_flags) return fail(EVG_ERR_INVALID, "null project_flags");
+  if (in->task_off[0] != 0 || in->task_off[D] != T || in->valid_off[0] != 0) return fail(EVG_ERR_INVALID, "offsets do not span the tables");
+  for (int32_t d = 0; d <= D; d++)
+    if (in->task_off[d] != distros->task_off[d]) return fail(EVG_ERR_INVALID, "the finder table and the distro table cut the candidates differently at distro %d", d);
+  for (int32_t d = 0; d < D; d++) {
+    if (in->task_off[d + 1] < in->task_off[d] || in->valid_off[d + 1] < in->valid_off[d]) return fail(EVG_ERR_INVALID, "offsets of distro %d decrease", d);
+    if (in->finder[d] > EVG_FINDER_ALTERNATE) return fail(EVG_ERR_INVALID, "distro %d: unknown finder %d", d, int(in->finder[d]));
+  }
+  const int64_t V = in->valid_off[D];
+  if (V > 0 && !in->valid_idx) return fail(EVG_ERR_INVALID, "null valid_idx");
+  if (T > 0 && (!in->deps || in->deps->n_tasks != T)) return fail(EVG_ERR_INVALID, "evg_plan_from_finder needs the candidates' dependency table (the planner's EVG_TF_DEPS_MET comes from it)");
+  if (T > 0 && (!cand->priority || !cand->expected_ns || !cand->queue_basis_ns || !cand->wait_basis_ns || !cand->num_dependents ||
+                !cand->task_group_order || !cand->group_id || !cand->version_id || !cand->flags))
+    return fail(EVG_ERR_INVALID, "null candidate column");
+  if (E > 0 && (!cand->dep_off || !cand->dep_idx)) return fail(EVG_ERR_INVALID, "null candidate dependency edges");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  CK(c->b_err.ensure(sizeof(int) * 4));
+  CK(cudaMemsetAsync(c->b_err.p, 0, sizeof(int) * 4, s));
+  c->launches = 0;
+  c->have_tasks = false;
+  if (T == 0) {
+    for (int32_t d = 0; d < D; d++) count[d] = 0;
+    return evg_upload(c, cand, distros, hosts, host_off, acfg);
+  }
+  // 1. Task.DependenciesMet / AllDependenciesSatisfied of every candidate, with the DependenciesMetTime stamps
+  int rc = deps_to_device(c, in->deps, 1, dep_finished_ns, now_ns, /*want_stamp=*/true);
+  if (rc != EVG_OK) return rc;
+  // 2. the finders (buffers of their own: deps_to_device holds b_rn6 / b_rn7)
+#define UPF(buf, ptr, cnt_, type)                                                                                  \
+  do {                                                                                                             \
+    CK((buf).ensure(sizeof(type) * size_t((cnt_) > 0 ? (cnt_) : 1)));                                              \
+    if ((cnt_) > 0) CK(cudaMemcpyAsync((buf).p, (ptr), sizeof(type) * size_t(cnt_), cudaMemcpyHostToDevice, s));   \
+  } while (0)
+  UPF(c->b_pf[0], in->task_off, D + 1, int64_t);
+  UPF(c->b_pf[1], in->sched, T, uint8_t);
+  UPF(c->b_pf[2], in->project, T, int32_t);
+  UPF(c->b_pf[3], in->project_flags, P, uint8_t);
+  UPF(c->b_pf[4], in->valid_off, D + 1, int64_t);
+  UPF(c->b_pf[5], in->valid_idx, V, int32_t);
+  UPF(c->b_pf[6], in->finder, D, uint8_t);
+  CK(c->b_pf[7].ensure(sizeof(int32_t) * size_t(T + 1)));  // kept lists
+  CK(c->b_pf[8].ensure(sizeof(int64_t) * size_t(D + 1)));  // counts
+  DRunnable r;
+  r.n_tasks = T; r.n_distros = D; r.n_projects = P;
+  r.task_off = c->b_pf[0].as<int64_t>(); r.sched = c->b_pf[1].as<uint8_t>(); r.project = c->b_pf[2].as<int32_t>();
+  r.project_flags = c->b_pf[3].as<uint8_t>(); r.valid_off = c->b_pf[4].as<int64_t>(); r.valid_idx = c->b_pf[5].as<int32_t>();
+  r.finder = c->b_pf[6].as<uint8_t>(); r.met = c->b_dx7.as<uint8_t>();
+  k_runnable<<<unsigned(D), 256, 0, s>>>(r, c->b_pf[7].as<int32_t>(), c->b_pf[8].as<int64_t>(), c->b_err.as<int>());
+  c->launches++;
+  CK(cudaGetLastError());
+  // 3. the only thing the host needs before the planner can be routed: how many tasks each distro kept
+  int bad = 0;
+  CK(cudaMemcpyAsync(count, c->b_pf[8].p, sizeof(int64_t) * size_t(D), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&bad, c->b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (runnable) CK(cudaMemcpyAsync(runnable, c->b_pf[7].p, sizeof(int32_t) * size_t(T), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (bad) return fail(EVG_ERR_INVALID, "a project row or dep_ref is out of range");
+  std::vector<int64_t> new_off(size_t(D) + 1, 0);
+  for (int32_t d = 0; d < D; d++) {
+    if (count[d] < 0 || count[d] > in->task_off[d + 1] - in->task_off[d]) return fail(EVG_ERR_CUDA, "finder count out of range");
+    new_off[size_t(d) + 1] = new_off[size_t(d)] + count[d];
+  }
+  const int64_t Tn = new_off[size_t(D)];
+  // 4. candidate columns to the device, compaction into the context's own buffers
+  UPF(c->b_pf[9], cand->priority, T, int32_t);
+  UPF(c->b_pf[10], cand->num_dependents, T, int32_t);
+  UPF(c->b_pf[11], cand->task_group_order, T, int32_t);
+  UPF(c->b_pf[12], cand->group_id, T, int32_t);
+  UPF(c->b_pf[13], cand->version_id, T, int32_t);
+  UPF(c->b_pf[14], cand->flags, T, uint32_t);
+  UPF(c->b_pf[15], cand->expected_ns, T, int64_t);
+  UPF(c->b_pf[16], cand->queue_basis_ns, T, int64_t);
+  UPF(c->b_pf[17], cand->wait_basis_ns, T, int64_t);
+  UPF(c->b_pf[18], new_off.data(), D + 1, int64_t);
+  const size_t np = size_t(Tn + kColPad);
+  for (int k = 19; k <= 23; k++) { CK(c->b_pf[k].ensure(sizeof(int32_t) * np)); CK(cudaMemsetAsync(c->b_pf[k].p, 0, sizeof(int32_t) * np, s)); }
+  CK(c->b_pf[24].ensure(sizeof(uint32_t) * np)); CK(cudaMemsetAsync(c->b_pf[24].p, 0, sizeof(uint32_t) * np, s));
+  for (int k = 25; k <= 27; k++) { CK(c->b_pf[k].ensure(sizeof(int64_t) * np)); CK(cudaMemsetAsync(c->b_pf[k].p, 0, sizeof(int64_t) * np, s)); }
+  CK(c->b_pf[28].ensure(sizeof(int32_t) * size_t(T + 1)));   // new_idx
+  CK(cudaMemsetAsync(c->b_pf[28].p, 0xFF, sizeof(int32_t) * size_t(T + 1), s));
+  CK(c->b_pf[29].ensure(sizeof(int64_t) * size_t(Tn + 1)));  // src_row
+  PfCols pc;
+  pc.priority = c->b_pf[9].as<int32_t>(); pc.numdep = c->b_pf[10].as<int32_t>(); pc.tgo = c->b_pf[11].as<int32_t>();
+  pc.gid = c->b_pf[12].as<int32_t>(); pc.vid = c->b_pf[13].as<int32_t>(); pc.flags = c->b_pf[14].as<uint32_t>();
+  pc.expected = c->b_pf[15].as<int64_t>(); pc.qbasis = c->b_pf[16].as<int64_t>(); pc.wbasis = c->b_pf[17].as<int64_t>();
+  pc.o_priority = c->b_pf[19].as<int32_t>(); pc.o_numdep = c->b_pf[20].as<int32_t>(); pc.o_tgo = c->b_pf[21].as<int32_t>();
+  pc.o_gid = c->b_pf[22].as<int32_t>(); pc.o_vid = c->b_pf[23].as<int32_t>(); pc.o_flags = c->b_pf[24].as<uint32_t>();
+  pc.o_expected = c->b_pf[25].as<int64_t>(); pc.o_qbasis = c->b_pf[26].as<int64_t>(); pc.o_wbasis = c->b_pf[27].as<int64_t>();
+  const int64_t* d_new_off = c->b_pf[18].as<int64_t>();
+  const int64_t* d_cand_off = c->b_pf[0].as<int64_t>();
+  if (Tn > 0) {
+    k_pf_gather<<<grid_for(Tn, 256), 256, 0, s>>>(Tn, D, d_new_off, d_cand_off, c->b_pf[7].as<int32_t>(), pc, c->b_dx7.as<uint8_t>(),
+                                                  c->b_rn7.as<int64_t>(), c->b_pf[28].as<int32_t>(), c->b_pf[29].as<int64_t>());
+    c->launches++;
+  }
+  // 5. in-queue dependency edges between kept tasks
+  int64_t En = 0;
+  std::vector<int64_t> edge_off;
+  if (E > 0 && Tn > 0) {
+    UPF(c->b_pf[30], cand->dep_off, T + 1, int64_t);
+    UPF(c->b_pf[31], cand->dep_idx, E, int32_t);
+    CK(c->b_pf[32].ensure(sizeof(int32_t) * size_t(Tn + 1)));                 // surviving edges per kept task
+    CK(c->b_pf[33].ensure(sizeof(int64_t) * size_t(Tn + 1 + kColPad)));       // new dep_off
+    const int64_t nb = (Tn + 1023) / 1024;
+    CK(c->b_pf[34].ensure(sizeof(int64_t) * size_t(nb + 1)));
+    k_pf_edge_count<<<grid_for(Tn, 256), 256, 0, s>>>(Tn, D, d_new_off, d_cand_off, c->b_pf[29].as<int64_t>(), c->b_pf[30].as<int64_t>(),
+                                                      c->b_pf[31].as<int32_t>(), c->b_pf[28].as<int32_t>(), c->b_pf[32].as<int32_t>());
+    k_scan_blocks<<<unsigned(nb), 1024, 0, s>>>(c->b_pf[32].as<int32_t>(), Tn, c->b_pf[33].as<int64_t>(), c->b_pf[34].as<int64_t>());
+    k_scan_sums<<<1, 1024, 0, s>>>(c->b_pf[34].as<int64_t>(), nb);
+    k_scan_add<<<unsigned(nb), 1024, 0, s>>>(c->b_pf[33].as<int64_t>(), Tn, c->b_pf[34].as<int64_t>(), nb);
+    c->launches += 4;
+    CK(cudaMemcpyAsync(&En, c->b_pf[33].as<int64_t>() + Tn, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    // dep_off sampled at the distro boundaries: what the routing needs of the edges
+    edge_off.resize(size_t(D) + 1);
+    CK(c->b_rn0.ensure(sizeof(int64_t) * size_t(D + 1)));
+    k_gather_i64<<<grid_for(D + 1, 256), 256, 0, s>>>(c->b_pf[33].as<int64_t>(), d_new_off, c->b_rn0.as<int64_t>(), D + 1);
+    CK(cudaMemcpyAsync(edge_off.data(), c->b_rn0.p, sizeof(int64_t) * size_t(D + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(c->b_pf[35].ensure(sizeof(int32_t) * size_t(En + 1)));
+    if (En > 0) {
+      k_pf_edge_write<<<grid_for(Tn, 256), 256, 0, s>>>(Tn, D, d_new_off, d_cand_off, c->b_pf[29].as<int64_t>(), c->b_pf[30].as<int64_t>(),
+                                                        c->b_pf[31].as<int32_t>(), c->b_pf[28].as<int32_t>(), c->b_pf[33].as<int64_t>(),
+                                                        c->b_pf[35].as<int32_t>());
+      c->launches++;
+    }
+  }
+#undef UPF
+  CK(cudaGetLastError());
+  // 6. the compacted table becomes the resident tick (columns stay where they are: context-owned device memory)
+  evg_task_soa ts;
+  memset(&ts, 0, sizeof(ts));
+  ts.n_tasks = Tn; ts.n_edges = En;
+  ts.priority = pc.o_priority; ts.num_dependents = pc.o_numdep; ts.task_group_order = pc.o_tgo; ts.group_id = pc.o_gid; ts.version_id = pc.o_vid;
+  ts.flags = pc.o_flags; ts.expected_ns = pc.o_expected; ts.queue_basis_ns = pc.o_qbasis; ts.wait_basis_ns = pc.o_wbasis;
+  if (En > 0) { ts.dep_off = c->b_pf[33].as<int64_t>(); ts.dep_idx = c->b_pf[35].as<int32_t>(); }
+  evg_distro_table dn = *distros;
+  dn.task_off = new_off.data();
+  rc = upload_tasks(c, &ts, &dn, /*copy_columns=*/false, /*adopt=*/true, (En > 0) ? edge_off.data() : nullptr);
+  if (rc != EVG_OK) return rc;
+  if (hosts) {
+    rc = upload_hosts(c, hosts, host_off, acfg, D);
+    if (rc != EVG_OK) return rc;
+  }
+  CK(cudaStreamSynchronize(s));
   return EVG_OK;
 }
 

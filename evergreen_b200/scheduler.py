@@ -266,6 +266,29 @@ class Engine:
         del keep
         return runnable, count
 
+    def plan_from_finder(self, table: "S.RunnableTable", candidates: S.TaskSoA, distros: S.DistroTable,
+                         hosts: Optional[S.HostSoA], dep_finished: Optional[np.ndarray], now: int):
+        """evg_plan_from_finder: finder -> dependency predicate -> compaction -> resident planner inputs on the device.
+        -> (runnable, count) as find_runnable_batch; the context then holds the tick of the KEPT tasks (run / download)."""
+        if table.deps is None:
+            raise ValueError("plan_from_finder needs the candidates' dependency table")
+        runnable = self._out("runnable", table.n_tasks, np.int32)
+        count = self._out("runnable_count", table.n_distros, np.int64)
+        st, keep = table.struct()
+        ts, ds = candidates.normalize().struct(), distros.struct()
+        fin = None if dep_finished is None else np.ascontiguousarray(dep_finished, dtype=np.int64)
+        hargs = (None, None, None)
+        if hosts is not None:
+            hs = hosts.struct()
+            hargs = (C.byref(hs), L.ptr(hosts.host_off), L.ptr(hosts.cfg) if hosts.cfg.shape[0] else None)
+        L.check(self.lib.evg_plan_from_finder(self.ctx, C.byref(st), C.byref(ts), C.byref(ds), *hargs,
+                                              L.ptr(fin) if fin is not None and fin.shape[0] else None, int(now),
+                                              L.ptr(runnable) if table.n_tasks else None, L.ptr(count) if table.n_distros else None))
+        del keep
+        self._n_tasks, self._n_distros, self._n_groups = int(count.sum()), distros.n_distros, distros.n_groups
+        self._has_hosts = hosts is not None
+        return runnable, count
+
     def expected_durations_batch(self, rows: "S.DurationRows") -> np.ndarray:
         """{$avg, $stdDevPop} of TimeTaken per key (evg_expected_durations_batch) -> DURATION_STAT_DTYPE[n_keys]."""
         out = self._out("duration_stats", rows.n_keys, L.DURATION_STAT_DTYPE)
@@ -519,6 +542,36 @@ def find_runnable_tasks(batch: Sequence[Tuple[M.Distro, List[M.Task]]], project_
     for i, (_, tasks) in enumerate(batch):
         a = int(table.task_off[i])
         out.append([tasks[int(j)] for j in runnable[a:a + int(count[i])]])
+    return out
+
+
+def plan_candidates(batch: Sequence[Tuple[M.Distro, List[M.Task]]], project_refs: Sequence[M.ProjectRef], now: int, *,
+                    finder: str = "legacy", dependency_db: Optional[Dict[str, M.Task]] = None,
+                    engine: Optional[Engine] = None):
+    """The finder -> checkDependenciesMet -> PrioritizeTasks hand-over of scheduler.PlanDistro (wrapper.go:60-118,
+    scheduler.go:56-168) without the host in the middle: `batch` holds every distro's CANDIDATES; the device filters them,
+    evaluates their dependencies, compacts the planner's columns and plans (evg_plan_from_finder).  Returns, per distro,
+    (ranked kept tasks with TotalValue stamped, DistroQueueInfo)."""
+    eng = engine or default_engine()
+    table = S.marshal_runnable(batch, project_refs, finder, dependency_db)
+    if table.deps is None:
+        table.deps = S.marshal_deps(batch, dependency_db)
+    soa, dtable, keys = S.marshal_tasks(batch, now, dependency_db)
+    runnable, count = eng.plan_from_finder(table, soa, dtable, None, S.marshal_dep_finished(batch), now)
+    eng.run(now)
+    po, _ = eng.download(want_alloc=False)
+    out, a_new = [], 0
+    for d, (_, tasks) in enumerate(batch):
+        a = int(table.task_off[d])
+        kept = [tasks[int(j)] for j in runnable[a:a + int(count[d])]]
+        ranked = []
+        for r in range(a_new, a_new + len(kept)):
+            t = kept[int(po.order[r])]
+            t.sorting_value_breakdown = M.SortingValueBreakdown(total_value=int(po.total_value[r]))
+            ranked.append(t)
+        a_new += len(kept)
+        ga, gb = int(dtable.group_off[d]), int(dtable.group_off[d + 1])
+        out.append((ranked, _queue_info_from_rows(po.info[d], po.group_info[ga:gb], keys[d].group_names)))
     return out
 
 

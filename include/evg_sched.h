@@ -439,6 +439,23 @@ typedef struct {
  * distro's slots are -1.  Host pointers. */
 int evg_find_runnable_batch(evg_ctx* ctx, const evg_runnable_in* in, int32_t* runnable, int64_t* count);
 
+/* The finder's output feeds the planner without leaving the device.  `in` describes every CANDIDATE task of every
+ * distro as for evg_find_runnable_batch (in->deps is required: the planner's EVG_TF_DEPS_MET bit comes from it);
+ * `candidates` holds the same rows' planner columns (flags without EVG_TF_DEPS_MET, wait_basis_ns = ScheduledTime,
+ * in-queue dependency edges between candidates as distro-local candidate indices); `distros` is the distro table over
+ * the candidates (task_off == in->task_off; group / version ids may name groups no kept task is in).  On the device:
+ * k_deps_met (both predicates, DependenciesMetTime stamps from dep_finished_ns, as evg_upload_with_deps) -> the finders
+ * -> a stable compaction of the nine planner columns (EVG_TF_DEPS_MET and the stamped wait basis applied on the way)
+ * -> the dependency edges whose two ends were kept, re-indexed.  The compacted table becomes the context's resident
+ * tick: call evg_run_resident / evg_download next; ranks refer to the compacted queues, and `runnable` (n_tasks, may be
+ * NULL) / `count` (n_distros) map them back exactly as evg_find_runnable_batch reports them.  The only values the host
+ * reads in between are the n_distros counts (the routing needs queue lengths).
+ * Replaces: the finder + checkDependenciesMet + PrioritizeTasks hand-over inside scheduler.PlanDistro
+ * (scheduler/wrapper.go:60-118, scheduler/scheduler.go:56-168), where the filtered []task.Task is rebuilt on the host. */
+int evg_plan_from_finder(evg_ctx* ctx, const evg_runnable_in* in, const evg_task_soa* candidates, const evg_distro_table* distros,
+                         const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg,
+                         const int64_t* dep_finished_ns, int64_t now_ns, int32_t* runnable, int64_t* count);
+
 /* ---- expected-duration statistics ----------------------- */
 
 /* evg_duration_rows.flags */

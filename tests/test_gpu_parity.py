@@ -887,6 +887,44 @@ def test_upload_device_equals_upload(engine):
     del keep
 
 
+@pytest.mark.parametrize("finder", ["legacy", "alternate"])
+def test_planner_consumes_the_finders_device_output(engine, finder):
+    """evg_plan_from_finder: candidates in, ranked queues out, with the finder's verdict, the dependency predicate and the
+    compaction of the planner's columns all on the device -- equal to the route through the host (find_runnable_tasks ->
+    the kept tasks marshalled again -> plan_distros) on ranked ids, TotalValue and every DistroQueueInfo field."""
+    import random
+    rng = random.Random(23)
+    NOWT = synth.NOW_NS
+    batch, refs, db = random_finder_batch(rng, 9)
+    big, db2 = __import__("test_host_logic").random_tasks(rng, 15000)  # a general-path queue among the small ones
+    for t in big:
+        t.id = "big-" + t.id
+        for dep in t.depends_on:
+            if dep.task_id.startswith("t"):
+                dep.task_id = "big-" + dep.task_id
+        t.project = "p1"
+    batch.append((M.Distro(id="big"), big)); db.update(db2)
+    # a candidate the finder drops is still a task document: the host route finds it in the database (task.go:632-671 reads
+    # missing dependencies from the collection), the device route sees it in the candidate table -- same status either way
+    db.update({t.id: t for _, ts in batch for t in ts})
+    host_side = copy.deepcopy(batch)
+    kept = S.find_runnable_tasks(host_side, refs, finder=finder, dependency_db=db, engine=engine)
+    want = S.plan_distros([(d, k) for (d, _), k in zip(host_side, kept)], NOWT, engine=engine, dependency_db=db, breakdown=False)
+    got = S.plan_candidates(copy.deepcopy(batch), refs, NOWT, finder=finder, dependency_db=db, engine=engine)
+    n_kept = 0
+    for (wr, wi), (gr, gi) in zip(want, got):
+        assert [t.id for t in gr] == [t.id for t in wr]
+        assert [t.sorting_value_breakdown.total_value for t in gr] == [t.sorting_value_breakdown.total_value for t in wr]
+        n_kept += len(wr)
+        for f in ("length", "length_with_dependencies_met", "count_dep_filled_merge_queue_tasks", "expected_duration",
+                  "max_duration_threshold", "count_duration_over_threshold", "duration_over_threshold", "count_wait_over_threshold"):
+            assert getattr(gi, f) == getattr(wi, f), f
+        live = lambda infos: sorted((g.name, g.count, g.expected_duration, g.count_duration_over_threshold, g.count_wait_over_threshold)  # noqa: E731
+                                    for g in infos if g.count or g.name == "")
+        assert live(gi.task_group_infos) == live(wi.task_group_infos)
+    assert 2000 < n_kept < sum(len(t) for _, t in batch)
+
+
 def test_update_tasks_equals_a_fresh_upload(engine):
     """evg_update_tasks: after scattering changed rows into the resident table (every route: tiny, on-chip, general),
     the tick equals the tick of a fresh upload of the edited table and the oracle's; bad row indices are errors."""
