@@ -925,6 +925,32 @@ def test_planner_consumes_the_finders_device_output(engine, finder):
     assert 2000 < n_kept < sum(len(t) for _, t in batch)
 
 
+def test_plan_from_finder_edges_of_the_input(engine):
+    """evg_plan_from_finder on empty and degenerate inputs: no candidates, distros whose candidates are all dropped,
+    a single kept task, candidates without any in-queue edge."""
+    NOWT = synth.NOW_NS
+    refs = [M.ProjectRef(id="p", enabled=True)]
+    def task(i, **kw):
+        return M.Task(id=f"t{i}", project="p", version="v", build_variant="bv", distro_id="d", activated=True, status="undispatched",
+                      requester=M.REPOTRACKER_VERSION_REQUESTER, priority=1 + i % 3, expected_duration=(1 + i % 7) * M.MINUTE,
+                      activated_time=NOWT - (1 + i) * M.MINUTE, scheduled_time=NOWT - M.HOUR, **kw)
+    # no candidates at all, one and three distros
+    for batch in ([(M.Distro(id="d"), [])], [(M.Distro(id=f"d{k}"), []) for k in range(3)]):
+        got = S.plan_candidates(batch, refs, NOWT, engine=engine)
+        assert [(len(r), i.length) for r, i in got] == [(0, 0)] * len(batch)
+    # everything dropped in one distro (inactive), one task kept in another, 40 kept without edges in a third
+    batch = [(M.Distro(id="a"), [task(i, ) for i in range(30)]), (M.Distro(id="b"), [task(0)]), (M.Distro(id="c"), [task(i) for i in range(40)])]
+    for t in batch[0][1]:
+        t.activated = False
+    want = S.plan_distros([(d, k) for (d, _), k in zip(batch, S.find_runnable_tasks(copy.deepcopy(batch), refs, engine=engine))],
+                          NOWT, engine=engine, breakdown=False)
+    got = S.plan_candidates(copy.deepcopy(batch), refs, NOWT, engine=engine)
+    assert [len(r) for r, _ in got] == [0, 1, 40]
+    for (wr, wi), (gr, gi) in zip(want, got):
+        assert [t.id for t in gr] == [t.id for t in wr]
+        assert (gi.length, gi.length_with_dependencies_met, gi.expected_duration) == (wi.length, wi.length_with_dependencies_met, wi.expected_duration)
+
+
 def test_update_tasks_equals_a_fresh_upload(engine):
     """evg_update_tasks: after scattering changed rows into the resident table (every route: tiny, on-chip, general),
     the tick equals the tick of a fresh upload of the edited table and the oracle's; bad row indices are errors."""
