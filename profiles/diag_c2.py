@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from evergreen_b200 import _lib as L  # noqa: E402
 
-cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+cfg = sys.argv[1] if len(sys.argv) > 1 else "2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 if len(sys.argv) > 3:
     lib = C.CDLL(sys.argv[3])
@@ -23,7 +23,16 @@ if len(sys.argv) > 3:
 from evergreen_b200 import scheduler, synth  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
-w = synth.config(cfg)
+if cfg == "c3":      # 48 distros x 100k tasks, configs[2]'s mix: the general path with every kind of unit
+    w = synth.config(3, 0.0048, each=True)
+elif cfg == "c5s":   # configs[4] scaled: every route in one tick
+    w = synth.config(5, 0.3)
+elif cfg == "mixed":
+    import numpy as _np
+    w = synth.make(_np.array([20, 300, 700, 3000, 9000, 14000, 1, 40000, 1100, 5000, 250, 12288, 12289, 90000]), 77, zipf_priority=True, tg_frac=0.12,
+                   met_dep_frac=0.02, unmet_dep_frac=0.03, group_versions_frac=0.3, includes_dependencies=True, n_hosts=120)
+else:
+    w = synth.config(int(cfg))
 job = O.SoAJob(w.tasks, w.distros, w.hosts, None)
 ref = job.run(w.now, 16)
 toff = w.distros.task_off
