@@ -360,6 +360,52 @@ def measure_shapes(torch, eng, stream, peak, steps):
     return out
 
 
+def measure_sharded_shapes(torch, dist, edist, eng, stream, dev, rank, world, steps):
+    """N > 1: fixed ticks (strong scaling) sharded by whole distros with LPT -- configs[3] (hosts on) and configs[4]
+    (power-law sizes, so the imbalance LPT leaves is visible).  Every rank plans its shard and all-gathers the allocator
+    results (16 B/distro); per tick the max over ranks counts.  Returns rows with the per-rank load."""
+    from evergreen_b200 import synth
+    out = []
+    for name, make in (("configs[3] total reading: 10k distros, 1M tasks, 50k hosts", lambda: synth.config(4)),
+                       ("configs[4]: 100k distros, power-law queue sizes, mixed providers", lambda: synth.config(5))):
+        w = make()
+        weight = np.diff(w.distros.task_off) + np.diff(w.hosts.host_off)
+        shards = edist.lpt_partition(weight, world)
+        mine = synth.take_distros(w, shards.members[rank])
+        gather = edist.ResultGather(shards, dev)
+        eng.bind_result_buffer(gather.send.data_ptr(), shards.max_shard)
+        eng.upload(mine.tasks, mine.distros, mine.hosts)
+        for _ in range(3):
+            eng.run(w.now); gather.gather()
+        dist.barrier(); torch.cuda.synchronize(dev)
+        e0, e1, g0, g1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        e0.record(stream)
+        for _ in range(steps):
+            eng.run(w.now)
+            gather.gather()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        g0.record(stream)
+        for _ in range(steps):
+            gather.gather()
+        g1.record(stream)
+        torch.cuda.synchronize(dev)
+        mine_ms = e0.elapsed_time(e1) / steps
+        t = torch.tensor([mine_ms, g0.elapsed_time(g1) / steps, float(mine.n_tasks), float(mine.distros.n_distros)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per = [[float(x) for x in a.tolist()] for a in allr]
+        ms = max(p[0] for p in per)
+        out.append({"workload": name, "scaling": "strong", "distros": w.distros.n_distros, "tasks": w.n_tasks, "ms_per_step": ms,
+                    "value": w.n_tasks / (ms * 1e-3), "unit": "tasks/s", "decisions_per_s": w.distros.n_distros / (ms * 1e-3),
+                    "all_gather_ms": max(p[1] for p in per),
+                    "per_rank": [{"rank": r, "ms_per_step": p[0], "tasks": int(p[2]), "distros": int(p[3]), "lpt_load": int(shards.load[r])}
+                                 for r, p in enumerate(per)]})
+        eng.bind_result_buffer(0, 0)
+        del w, mine, gather
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -541,6 +587,9 @@ def main():
         del upd, off, items
     del we, pe, ae
 
+    sharded = None
+    if world > 1 and not args.no_shapes:  # every rank takes part
+        sharded = measure_sharded_shapes(torch, dist, edist, eng, stream, dev, rank, world, args.shape_steps)
     line = None
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -588,6 +637,8 @@ def main():
         if not args.no_shapes and world == 1:
             eng.bind_result_buffer(0, 0)  # the shapes have other distro counts: results go to the context's own buffer
             line["shapes"] = measure_shapes(torch, eng, stream, peak, args.shape_steps)
+        if sharded is not None:
+            line["shapes"] = sharded
         if not args.no_cpu_baseline and world == 1:
             if prev_affinity:
                 os.sched_setaffinity(0, prev_affinity)  # the baseline gets every host core back

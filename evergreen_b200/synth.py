@@ -73,6 +73,42 @@ class Workload:
                 16 * self.distros.n_distros)
 
 
+def _ranges(off: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    """Concatenated index ranges [off[i], off[i+1]) for i in ids, in that order."""
+    lens = (off[ids + 1] - off[ids]).astype(np.int64)
+    if lens.sum() == 0:
+        return np.zeros(0, dtype=np.int64)
+    starts = np.repeat(off[ids], lens)
+    within = np.arange(int(lens.sum()), dtype=np.int64) - np.repeat(np.cumsum(lens) - lens, lens)
+    return starts + within
+
+
+def take_distros(w: Workload, ids) -> Workload:
+    """The sub-tick of the distros `ids` (in that order): what one rank of a distro-sharded job uploads.  Task groups,
+    versions and in-queue dependency edges are distro-local, so rows move as they are."""
+    ids = np.asarray(ids, dtype=np.int64)
+    t, d, h = w.tasks, w.distros, w.hosts
+    rows = _ranges(d.task_off, ids)
+    cols = {name: getattr(t, name)[rows] for name, _ in t.COLUMNS}
+    dep_off = dep_idx = None
+    if t.n_edges:
+        deg = (t.dep_off[rows + 1] - t.dep_off[rows]).astype(np.int64)
+        dep_off = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+        dep_idx = t.dep_idx[_ranges(t.dep_off, rows)] if deg.sum() else np.zeros(0, dtype=np.int32)
+    tasks = TaskSoA(**cols, dep_off=dep_off, dep_idx=dep_idx).normalize()
+    n = (d.task_off[ids + 1] - d.task_off[ids]).astype(np.int64)
+    g = (d.group_off[ids + 1] - d.group_off[ids]).astype(np.int64)
+    distros = DistroTable(np.concatenate([[0], np.cumsum(n)]).astype(np.int64), np.concatenate([[0], np.cumsum(g)]).astype(np.int64),
+                          d.cfg[ids], d.group_max_hosts[_ranges(d.group_off, ids)]).normalize()
+    hosts = None
+    if h is not None:
+        hr = _ranges(h.host_off, ids)
+        hn = (h.host_off[ids + 1] - h.host_off[ids]).astype(np.int64)
+        hosts = HostSoA(h.flags[hr], h.group_id[hr], h.expected_ns[hr], h.std_ns[hr], h.start_ns[hr],
+                        np.concatenate([[0], np.cumsum(hn)]).astype(np.int64), h.cfg[ids]).normalize()
+    return Workload(f"{w.name} [{len(ids)} of {d.n_distros} distros]", w.now, tasks, distros, hosts)
+
+
 def _zipf_priorities(rng: Rng, n: int, s: float = 1.1, kmax: int = 100) -> np.ndarray:
     ranks = np.arange(1, kmax + 2, dtype=np.float64)
     w = ranks ** (-s)

@@ -151,6 +151,22 @@ def test_synth_is_deterministic_and_well_formed():
     assert a.algorithmic_bytes() == 60 * t.n_tasks + 4 * t.n_edges + 28 * a.hosts.n_hosts + 96 * d.n_groups + 16 * d.n_distros
 
 
+def test_take_distros_is_the_same_tick_per_distro():
+    """synth.take_distros (what a rank of the sharded bench uploads): the oracle plans a distro of the sub-tick exactly as it
+    plans it inside the whole tick -- order, TotalValue, allocator decision."""
+    w = synth.make(np.array([50, 0, 300, 7, 1200, 90]), 5, zipf_priority=True, tg_frac=0.2, met_dep_frac=0.05, unmet_dep_frac=0.05,
+                   group_versions_frac=0.3, includes_dependencies=True, n_hosts=30)
+    ids = np.array([4, 0, 2, 5, 1])
+    s = synth.take_distros(w, ids)
+    ref = O.SoAJob(w.tasks, w.distros, w.hosts, None).run(w.now, 4)
+    sub = O.SoAJob(s.tasks, s.distros, s.hosts, None).run(s.now, 4)
+    for j, d in enumerate(ids):
+        a, b = int(w.distros.task_off[d]), int(w.distros.task_off[d + 1])
+        a2, b2 = int(s.distros.task_off[j]), int(s.distros.task_off[j + 1])
+        assert np.array_equal(ref["order"][a:b], sub["order"][a2:b2]) and np.array_equal(ref["total_value"][a:b], sub["total_value"][a2:b2])
+        assert (int(ref["new_hosts"][d]), int(ref["free_hosts"][d])) == (int(sub["new_hosts"][j]), int(sub["free_hosts"][j]))
+
+
 def test_score_fast_paths_equal_the_fp64_formulas(tmp_path):
     """evg_score.cuh replaces Duration.Minutes()/Hours() FP64 arithmetic by integer quotients on a proven
     range; brute-force the equivalence on the host (same header the kernels compile)."""
