@@ -507,19 +507,19 @@ __global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W,
     const int d = x.d;
     bool have = false;
     int64_t bv = 0;
-    uint32_t ba = 0, brk = 0, bp = kInactive, bslot = kInactive, bn = 1;
+    uint32_t ba = 0, brk = 0, bp = kInactive, bslot = kInactive, bn = 1, bkx = 0;
     if (!x.own_complex) { have = true; bv = G.tv[t]; ba = li; }  // its own single-task unit, scored by k_gtask
     wl_pairs(T, W, x, [&](uint32_t pair, uint32_t slot) {
       const uint4 u = G.usum[slot];
+      const uint32_t kx = W.next[pair];  // this task's place in that unit's run (requested together with the summary)
       const uint32_t a = u.z;
       if (a == kNoAnchor) return;
       const int64_t v = int64_t((unsigned long long)u.x | ((unsigned long long)u.y << 32));
-      if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; bp = pair; bslot = slot; bn = u.w; }
+      if (!have || v > bv || (v == bv && a < ba)) { have = true; bv = v; ba = a; bp = pair; bslot = slot; bn = u.w; bkx = kx; }
     });
     if (bp != kInactive) {  // rank among ALL members of the chosen unit; the task's own fields are its record in the run
       const URec* run = G.rec + W.head[bslot];
-      URec me = rec_load(run);
-      for (uint32_t i = 1; i < bn && rec_li(me) != li; i++) me = rec_load(run + i);
+      const URec me = rec_load(run + bkx);
       for (uint32_t i = 0; i < bn; i++) {
         const URec r = rec_load(run + i);
         if (in_unit_less(r.tgo, r.nd, r.prio, r.exp_ns, rec_li(r), me.tgo, me.nd, me.prio, me.exp_ns, li)) brk++;
@@ -532,9 +532,29 @@ __global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W,
     const bool displaced = !(ba == li && brk == 0);
     if (displaced) W.has_dep[t] |= 2;  // only this thread touches the byte now (k_gmark and k_gtask are done)
     atomicAdd(G.e + x.base + ba, 1u);
+    // The distro's value range.  The work list is in task order, so a warp nearly always sits inside one distro: its 32
+    // values are folded with shuffles and ONE lane looks at the distro's pair (every thread polling the same two L2 lines
+    // was a third of this kernel's stall samples).
     const unsigned long long kk = ord_i64(bv);
-    if (kk > __ldcg(G.vmm + 2 * d)) atomicMax(G.vmm + 2 * d, kk);
-    if (kk < __ldcg(G.vmm + 2 * d + 1)) atomicMin(G.vmm + 2 * d + 1, kk);
+    const unsigned act = __activemask();
+    const int d0 = __shfl_sync(act, d, __ffs(act) - 1);
+    if (__all_sync(act, d == d0)) {
+      unsigned long long hi = kk, lo = kk;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long h2 = __shfl_xor_sync(act, hi, o), l2 = __shfl_xor_sync(act, lo, o);
+        const bool other = (act >> ((threadIdx.x & 31) ^ o)) & 1u;  // an exited lane's register is not a value
+        hi = (other && h2 > hi) ? h2 : hi;
+        lo = (other && l2 < lo) ? l2 : lo;
+      }
+      if ((threadIdx.x & 31) == __ffs(act) - 1) {
+        if (hi > __ldcg(G.vmm + 2 * d)) atomicMax(G.vmm + 2 * d, hi);
+        if (lo < __ldcg(G.vmm + 2 * d + 1)) atomicMin(G.vmm + 2 * d + 1, lo);
+      }
+    } else {
+      if (kk > __ldcg(G.vmm + 2 * d)) atomicMax(G.vmm + 2 * d, kk);
+      if (kk < __ldcg(G.vmm + 2 * d + 1)) atomicMin(G.vmm + 2 * d + 1, kk);
+    }
   }
 }
 
