@@ -22,7 +22,10 @@ __device__ __forceinline__ int64_t shfl64(int64_t v, int src) {
   return int64_t((uint64_t(hi) << 32) | lo);
 }
 
-__global__ void __launch_bounds__(256) k_plan_warp(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list,
+#ifndef EVG_WARP_OCC
+#define EVG_WARP_OCC 4  // blocks of 8 distros per SM: 64 registers (16 B spilled); measured against 3 (79 registers): configs[2] total 61 -> 57 us, configs[4] 0.73 -> 0.69 ms
+#endif
+__global__ void __launch_bounds__(256, EVG_WARP_OCC) k_plan_warp(DTasks T, DDistros D, DWork W, const int32_t* __restrict__ list,
                                                    int n_list, int64_t now, int32_t* __restrict__ order,
                                                    int64_t* __restrict__ total_value) {
   if (*W.err) return;
