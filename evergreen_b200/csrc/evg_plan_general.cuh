@@ -22,6 +22,22 @@
 // Reference: scheduler/planner.go:209-481, scheduler/scheduler.go:56-159.
 #pragma once
 
+// minimum resident blocks of the work-list kernels (latency-bound: one thread per task or unit, scattered sectors)
+#ifndef EVG_OCC_GLINK
+#define EVG_OCC_GLINK 4
+#endif
+#ifndef EVG_OCC_GALLOC
+#define EVG_OCC_GALLOC 4
+#endif
+#ifndef EVG_OCC_GFILL
+#define EVG_OCC_GFILL 4
+#endif
+#ifndef EVG_OCC_GUNIT
+#define EVG_OCC_GUNIT 4
+#endif
+#ifndef EVG_OCC_GBEST
+#define EVG_OCC_GBEST 4
+#endif
 #ifndef EVG_GTASK_OCC
 #define EVG_GTASK_OCC 3
 #endif
@@ -366,7 +382,7 @@ __device__ __forceinline__ void wl_pairs(const DTasks& T, const DWork& W, const 
       if (W.edge_live[e]) f(uint32_t(2 * T.n + e), W.pair_slot[2 * T.n + e]);
 }
 
-__global__ void __launch_bounds__(256, 4) k_glink(DTasks T, DDistros D, DWork W, DGen G, int64_t now) {
+__global__ void __launch_bounds__(256, EVG_OCC_GLINK) k_glink(DTasks T, DDistros D, DWork W, DGen G, int64_t now) {
   if (*W.err) return;
   const unsigned int n = *G.ccount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -416,7 +432,7 @@ __global__ void __launch_bounds__(256, 4) k_glink(DTasks T, DDistros D, DWork W,
 
 // Runs are reserved block by block: a block scan of the records its threads need, ONE atomic on the bump counter per
 // block and trip (an atomic per unit serialised ~10^5 units of a tick on one L2 address: 340 us of a 1.4 ms tick).
-__global__ void __launch_bounds__(256, 4) k_galloc(DTasks T, DDistros D, DWork W, DGen G) {
+__global__ void __launch_bounds__(256, EVG_OCC_GALLOC) k_galloc(DTasks T, DDistros D, DWork W, DGen G) {
   if (*W.err) return;
   __shared__ uint32_t s_wsum[8], s_wcnt[8];
   __shared__ uint32_t s_base, s_hbase;
@@ -456,7 +472,7 @@ __global__ void __launch_bounds__(256, 4) k_galloc(DTasks T, DDistros D, DWork W
   }
 }
 
-__global__ void __launch_bounds__(256, 4) k_gfill(DTasks T, DDistros D, DWork W, DGen G) {
+__global__ void __launch_bounds__(256, EVG_OCC_GFILL) k_gfill(DTasks T, DDistros D, DWork W, DGen G) {
   if (*W.err) return;
   const unsigned int n = *G.ccount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -477,7 +493,7 @@ __device__ __forceinline__ void rec_acc(UnitAcc& a, int64_t now, const URec& r) 
 }
 
 // One thread per multi-member unit (dense warps: the unit list, not the work list).
-__global__ void __launch_bounds__(256, 4) k_gunit(DDistros D, DWork W, DGen G, int64_t now) {
+__global__ void __launch_bounds__(256, EVG_OCC_GUNIT) k_gunit(DDistros D, DWork W, DGen G, int64_t now) {
   if (*W.err) return;
   const unsigned int n = *G.hcount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {  // the host cannot know n: fixed grid
@@ -498,7 +514,7 @@ __global__ void __launch_bounds__(256, 4) k_gunit(DDistros D, DWork W, DGen G, i
   }
 }
 
-__global__ void __launch_bounds__(256, 4) k_gbest(DTasks T, DDistros D, DWork W, DGen G, int want_best_pair) {
+__global__ void __launch_bounds__(256, EVG_OCC_GBEST) k_gbest(DTasks T, DDistros D, DWork W, DGen G, int want_best_pair) {
   if (*W.err) return;
   const unsigned int n = *G.ccount;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
