@@ -639,6 +639,18 @@ def main():
             line["shapes"] = measure_shapes(torch, eng, stream, peak, args.shape_steps)
         if sharded is not None:
             line["shapes"] = sharded
+        if world == 1 and not args.no_delta:
+            # the string side of marshalling (group keys / versions / dependency ids -> dense ids), host C++ behind the
+            # ABI (evg_intern_columns); columns of Evergreen-shaped strings, 1e6 tasks in 100 distros
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "profiles"))
+                import intern_bench
+                ib = intern_bench.run(100, 10000, threads=(1, usable_cores()[0]))
+                line["e2e"]["host_interning"] = {"tasks_per_s": ib["runs"][-1]["tasks_per_s"], "threads": ib["runs"][-1]["threads"],
+                                                 "one_thread_tasks_per_s": ib["runs"][0]["tasks_per_s"], "string_bytes_per_task": ib["string_bytes"] / ib["tasks"],
+                                                 "api": "evg_intern_columns (host C++): task-group keys, versions, dependency ids of 1e6 tasks"}
+            except Exception as e:  # noqa: BLE001
+                line["e2e"]["host_interning"] = {"error": str(e)}
         if not args.no_cpu_baseline and world == 1:
             if prev_affinity:
                 os.sched_setaffinity(0, prev_affinity)  # the baseline gets every host core back

@@ -62,6 +62,21 @@ assert DISTRO_CFG_DTYPE.itemsize == 88 and GROUP_INFO_DTYPE.itemsize == 72
 assert QUEUE_INFO_DTYPE.itemsize == 152 and ALLOC_CFG_DTYPE.itemsize == 48 and ALLOC_RESULT_DTYPE.itemsize == 16
 
 
+class StrColStruct(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("off", C.c_void_p)]
+
+
+class StringColsStruct(C.Structure):
+    _fields_ = [("n_tasks", C.c_int64), ("n_distros", C.c_int32), ("task_off", C.c_void_p), ("id", StrColStruct),
+                ("version", StrColStruct), ("group_key", StrColStruct), ("group_max_hosts", C.c_void_p),
+                ("dep_off", C.c_void_p), ("dep_id", StrColStruct)]
+
+
+class InternOutStruct(C.Structure):
+    _fields_ = [("group_id", C.c_void_p), ("version_id", C.c_void_p), ("group_off", C.c_void_p), ("n_versions", C.c_void_p),
+                ("group_max_hosts", C.c_void_p), ("group_first", C.c_void_p), ("dep_off", C.c_void_p), ("dep_idx", C.c_void_p)]
+
+
 class TaskSoAStruct(C.Structure):
     _fields_ = [("n_tasks", C.c_int64), ("n_edges", C.c_int64),
                 ("priority", C.c_void_p), ("expected_ns", C.c_void_p), ("queue_basis_ns", C.c_void_p),
@@ -162,6 +177,7 @@ SYMBOLS = {
     "evg_upload_device": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "evg_update_tasks": (C.c_int, [_P, C.c_int64, _P, _P]),
     "evg_plan_from_finder": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P]),
+    "evg_intern_columns": (C.c_int, [_P, _P, C.c_int32]),
     "evg_run_resident": (C.c_int, [_P, C.c_int64, C.c_uint32]),
     "evg_download": (C.c_int, [_P, _P, _P]),
     "evg_download_queue": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int64]),

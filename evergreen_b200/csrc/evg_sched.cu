@@ -37,6 +37,7 @@
 #include <vector>
 
 #include "evg_score.cuh"
+#include "evg_intern.h"
 
 using namespace evg;
 
@@ -2432,6 +2433,91 @@ int evg_plan_from_finder(evg_ctx* c, const evg_runnable_in* in, const evg_task_s
     if (rc != EVG_OK) return rc;
   }
   CK(cudaStreamSynchronize(s));
+  return EVG_OK;
+}
+
+// --------------------------------------------------------------------------
+// evg_intern_columns: host-side string interning (evg_intern.h)
+// --------------------------------------------------------------------------
+int evg_intern_columns(const evg_string_cols* in, evg_intern_out* out, int32_t threads) {
+  using namespace evg_intern;
+  if (!in || !out) return fail(EVG_ERR_INVALID, "evg_intern_columns: null argument");
+  const int64_t T = in->n_tasks;
+  const int32_t D = in->n_distros;
+  if (T < 0 || D < 0) return fail(EVG_ERR_INVALID, "negative sizes");
+  if (!out->group_off || (D > 0 && (!in->task_off || !out->n_versions))) return fail(EVG_ERR_INVALID, "null distro arrays");
+  if (D == 0) { out->group_off[0] = 0; return T == 0 ? EVG_OK : fail(EVG_ERR_INVALID, "tasks without distros"); }
+  if (in->task_off[0] != 0 || in->task_off[D] != T) return fail(EVG_ERR_INVALID, "task_off does not span n_tasks");
+  if (T > 0 && (!in->id.off || !in->version.off || !in->group_key.off || !in->group_max_hosts || !in->dep_off || !out->group_id ||
+                !out->version_id || !out->group_max_hosts || !out->group_first || !out->dep_off))
+    return fail(EVG_ERR_INVALID, "null column");
+  const int64_t E = T > 0 ? in->dep_off[T] : 0;
+  if (E > 0 && (!in->dep_id.off || !out->dep_idx)) return fail(EVG_ERR_INVALID, "null dependency columns");
+  // per distro: groups found, surviving edges (phase 1 counts into per-distro scratch, phase 2 writes at the scanned offsets)
+  std::vector<int64_t> n_groups(size_t(D), 0), n_edges(size_t(D), 0);
+  std::vector<std::vector<int32_t>> grp_max_by_distro(static_cast<size_t>(D));
+  std::vector<std::vector<int64_t>> grp_first_by_distro(static_cast<size_t>(D));
+  std::vector<std::vector<int32_t>> edge_by_distro(static_cast<size_t>(D));
+  std::atomic<int32_t> next{0};
+  std::atomic<int64_t> bad_row{-1};
+  int nt = threads > 0 ? threads : int(std::thread::hardware_concurrency());
+  nt = std::max(1, std::min(nt, int(D)));
+  auto work = [&]() {
+    Table groups, versions, ids;
+    for (;;) {
+      const int32_t d = next.fetch_add(1);
+      if (d >= D) return;
+      const int64_t a = in->task_off[d], b = in->task_off[d + 1];
+      if (b < a) { bad_row.store(a); return; }
+      const int64_t n = b - a;
+      groups.reset(n); versions.reset(n); ids.reset(n);
+      int32_t ng = 0, nv = 0;
+      bool ins;
+      for (int64_t t = a; t < b; t++) {
+        ids.get_or_put(str_at(in->id.bytes, in->id.off, t), in->id.bytes, in->id.off, t, int32_t(t - a), &ins);  // a repeated id keeps its first index
+        const Str gk = str_at(in->group_key.bytes, in->group_key.off, t);
+        int32_t gid = -1;
+        if (gk.n > 0) {
+          gid = groups.get_or_put(gk, in->group_key.bytes, in->group_key.off, t, ng, &ins);
+          if (ins) { ng++; grp_max_by_distro[size_t(d)].push_back(in->group_max_hosts[t]); grp_first_by_distro[size_t(d)].push_back(t); }
+          else if (grp_max_by_distro[size_t(d)][size_t(gid)] != in->group_max_hosts[t]) { int64_t none = -1; bad_row.compare_exchange_strong(none, t); }
+        }
+        out->group_id[t] = gid;
+        const int32_t vid = versions.get_or_put(str_at(in->version.bytes, in->version.off, t), in->version.bytes, in->version.off, t, nv, &ins);
+        if (ins) nv++;
+        out->version_id[t] = vid;
+      }
+      out->n_versions[d] = nv;
+      n_groups[size_t(d)] = ng;
+      std::vector<int32_t>& ed = edge_by_distro[size_t(d)];
+      for (int64_t t = a; t < b; t++) {
+        int64_t kept = 0;
+        for (int64_t e = in->dep_off[t]; e < in->dep_off[t + 1]; e++) {
+          const int32_t j = ids.find(str_at(in->dep_id.bytes, in->dep_id.off, e), in->id.bytes, in->id.off);
+          if (j >= 0) { ed.push_back(j); kept++; }
+        }
+        out->dep_off[t + 1] = kept;  // counts for now; scanned below
+      }
+      n_edges[size_t(d)] = int64_t(ed.size());
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int k = 1; k < nt; k++) pool.emplace_back(work);
+  work();
+  for (std::thread& th : pool) th.join();
+  if (bad_row.load() >= 0) return fail(EVG_ERR_INVALID, "task group of row %lld: TaskGroupMaxHosts differs between members (or offsets decrease)", (long long)bad_row.load());
+  // offsets, then the per-distro pieces move to their places
+  out->group_off[0] = 0;
+  for (int32_t d = 0; d < D; d++) out->group_off[d + 1] = out->group_off[d] + n_groups[size_t(d)];
+  if (T > 0) {
+    out->dep_off[0] = 0;
+    for (int64_t t = 0; t < T; t++) out->dep_off[t + 1] += out->dep_off[t];
+  }
+  for (int32_t d = 0; d < D; d++) {
+    const int64_t g0 = out->group_off[d];
+    for (size_t k = 0; k < grp_max_by_distro[size_t(d)].size(); k++) { out->group_max_hosts[g0 + int64_t(k)] = grp_max_by_distro[size_t(d)][k]; out->group_first[g0 + int64_t(k)] = grp_first_by_distro[size_t(d)][k]; }
+    if (!edge_by_distro[size_t(d)].empty()) memcpy(out->dep_idx + out->dep_off[in->task_off[d]], edge_by_distro[size_t(d)].data(), sizeof(int32_t) * edge_by_distro[size_t(d)].size());
+  }
   return EVG_OK;
 }
 

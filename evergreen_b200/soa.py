@@ -313,6 +313,49 @@ def marshal_tasks(batch: Sequence[tuple], now: int, dependency_db: Optional[Dict
     return soa, table, keys
 
 
+def pack_strings(strings: Sequence[str]):
+    """[str] -> (uint8 bytes, int64 offsets[n+1]): an evg_str_col."""
+    enc = [x.encode() for x in strings]
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        np.cumsum([len(b) for b in enc], out=off[1:])
+    return np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if enc else np.zeros(0, np.uint8), off
+
+
+def intern_columns(batch: Sequence[tuple], threads: int = 0):
+    """evg_intern_columns over a tick: the string work of marshal_tasks (task-group keys and versions to dense ids in
+    first-appearance order, dependency ids to queue indices) in the library's C++ instead of Python dicts.
+    -> dict(group_id, version_id, group_off, n_versions, group_max_hosts, group_first, dep_off, dep_idx)."""
+    lib = L.load()
+    tasks = [t for _, ts in batch for t in ts]
+    T, D = len(tasks), len(batch)
+    task_off = np.zeros(D + 1, dtype=np.int64)
+    if D:
+        np.cumsum([len(ts) for _, ts in batch], out=task_off[1:])
+    idb, ido = pack_strings([t.id for t in tasks])
+    vb, vo = pack_strings([t.version for t in tasks])
+    gb, go = pack_strings([t.get_task_group_string() if t.task_group != "" else "" for t in tasks])
+    gmax = np.array([t.task_group_max_hosts for t in tasks], dtype=np.int32)
+    dep_off = np.zeros(T + 1, dtype=np.int64)
+    if T:
+        np.cumsum([len(t.depends_on) for t in tasks], out=dep_off[1:])
+    db, do = pack_strings([dep.task_id for t in tasks for dep in t.depends_on])
+    E = int(dep_off[-1])
+    out = dict(group_id=np.empty(T, np.int32), version_id=np.empty(T, np.int32), group_off=np.zeros(D + 1, np.int64),
+               n_versions=np.zeros(D, np.int32), group_max_hosts=np.empty(max(T, 1), np.int32), group_first=np.empty(max(T, 1), np.int64),
+               dep_off=np.zeros(T + 1, np.int64), dep_idx=np.empty(max(E, 1), np.int32))
+    col = lambda b, o: L.StrColStruct(L.ptr(b) if b.shape[0] else None, L.ptr(o))  # noqa: E731
+    ins = L.StringColsStruct(T, D, L.ptr(task_off), col(idb, ido), col(vb, vo), col(gb, go), L.ptr(gmax) if T else None,
+                             L.ptr(dep_off), col(db, do))
+    outs = L.InternOutStruct(*[L.ptr(out[k]) for k in ("group_id", "version_id", "group_off", "n_versions", "group_max_hosts",
+                                                       "group_first", "dep_off", "dep_idx")])
+    import ctypes as C
+    L.check(lib.evg_intern_columns(C.byref(ins), C.byref(outs), int(threads)))
+    G, En = int(out["group_off"][D]), int(out["dep_off"][T])
+    out["group_max_hosts"], out["group_first"], out["dep_idx"] = out["group_max_hosts"][:G], out["group_first"][:G], out["dep_idx"][:En]
+    return out
+
+
 def provider_class(provider: str) -> int:
     if provider == M.PROVIDER_DOCKER:
         return L.EVG_PROVIDER_DOCKER

@@ -456,6 +456,45 @@ int evg_plan_from_finder(evg_ctx* ctx, const evg_runnable_in* in, const evg_task
                          const evg_host_soa* hosts, const int64_t* host_off, const evg_alloc_cfg* acfg,
                          const int64_t* dep_finished_ns, int64_t now_ns, int32_t* runnable, int64_t* count);
 
+/* ---- host-side string interning for the marshaller ------------------------ */
+
+/* A column of n strings: bytes[off[i] .. off[i+1]) is string i (not NUL-terminated). */
+typedef struct {
+  const char* bytes;
+  const int64_t* off; /* n + 1 */
+} evg_str_col;
+
+/* The strings of a tick's tasks, concatenated distro by distro like evg_task_soa. */
+typedef struct {
+  int64_t n_tasks;
+  int32_t n_distros;
+  const int64_t* task_off;          /* n_distros + 1 */
+  evg_str_col id;                   /* Task.Id */
+  evg_str_col version;              /* Task.Version */
+  evg_str_col group_key;            /* Task.GetTaskGroupString() (model/task/task.go:417-419); "" when Task.TaskGroup == "" */
+  const int32_t* group_max_hosts;   /* Task.TaskGroupMaxHosts, n_tasks */
+  const int64_t* dep_off;           /* n_tasks + 1: CSR over Task.DependsOn */
+  evg_str_col dep_id;               /* Dependency.TaskId, dep_off[n_tasks] strings */
+} evg_string_cols;
+
+/* What the planner's columns need of those strings; every array is caller-allocated. */
+typedef struct {
+  int32_t* group_id;        /* n_tasks: dense per distro in first-appearance order, -1 without a task group */
+  int32_t* version_id;      /* n_tasks: dense per distro in first-appearance order */
+  int64_t* group_off;       /* n_distros + 1 */
+  int32_t* n_versions;      /* n_distros */
+  int32_t* group_max_hosts; /* capacity n_tasks: one per group slot, group_off[n_distros] used */
+  int64_t* group_first;     /* capacity n_tasks: row of each group's first member (its name is group_key there) */
+  int64_t* dep_off;         /* n_tasks + 1: in-queue dependency edges (planner.go:449-456) */
+  int32_t* dep_idx;         /* capacity dep_off_in[n_tasks]: distro-local index of the dependency; targets outside the queue are dropped */
+} evg_intern_out;
+
+/* String work of marshalling a tick (scheduler.PrioritizeTasks builds the same maps while it walks a queue:
+ * planner.go:431-456 files units under exactly these strings): group keys and versions to dense ids, dependency ids
+ * to queue indices, per distro, `threads` distros at a time (<= 0: hardware concurrency).  Host only: no context.
+ * EVG_ERR_INVALID when members of one task group disagree on TaskGroupMaxHosts (evg_last_error names the row). */
+int evg_intern_columns(const evg_string_cols* in, evg_intern_out* out, int32_t threads);
+
 /* ---- expected-duration statistics ----------------------- */
 
 /* evg_duration_rows.flags */

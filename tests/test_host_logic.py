@@ -151,6 +151,42 @@ def test_synth_is_deterministic_and_well_formed():
     assert a.algorithmic_bytes() == 60 * t.n_tasks + 4 * t.n_edges + 28 * a.hosts.n_hosts + 96 * d.n_groups + 16 * d.n_distros
 
 
+def test_intern_columns_equals_the_python_marshaller():
+    """evg_intern_columns (host C++ behind the ABI): group ids, version ids, group offsets, per-group MaxHosts, version
+    counts and the in-queue dependency CSR equal what soa.marshal_tasks builds with Python dicts -- for 1 and 5 threads,
+    with empty distros, repeated versions, dependencies outside the queue; mismatching TaskGroupMaxHosts is an error."""
+    rng = random.Random(11)
+    batch = []
+    for d, n in enumerate([0, 1, 40, 700, 0, 2500, 13]):
+        tasks, _ = random_tasks(rng, n)
+        for t in tasks:
+            t.id = f"d{d}-{t.id}"
+            for dep in t.depends_on:
+                if dep.task_id.startswith("t"):
+                    dep.task_id = f"d{d}-{dep.task_id}"
+        batch.append((M.Distro(id=f"d{d}"), tasks))
+    soa, table, keys = S.marshal_tasks(batch, 10 ** 18)
+    for threads in (1, 5):
+        got = S.intern_columns(batch, threads)
+        assert np.array_equal(got["group_id"], soa.group_id) and np.array_equal(got["version_id"], soa.version_id)
+        assert np.array_equal(got["group_off"], table.group_off) and np.array_equal(got["group_max_hosts"], table.group_max_hosts)
+        assert got["n_versions"].tolist() == [len(k.versions) for k in keys]
+        want_off = soa.dep_off if soa.dep_off is not None else np.zeros(soa.n_tasks + 1, np.int64)
+        assert np.array_equal(got["dep_off"], want_off)
+        if soa.dep_idx is not None:
+            assert np.array_equal(got["dep_idx"], soa.dep_idx)
+        flat = [t for _, ts in batch for t in ts]
+        assert [flat[int(r)].get_task_group_string() for r in got["group_first"]] == [n for k in keys for n in k.group_names]
+    assert int(got["dep_off"][-1]) > 50 and int(got["group_off"][-1]) > 20
+    grouped = [t for t in batch[5][1] if t.task_group != ""]
+    twin = [t for t in grouped if t.get_task_group_string() == grouped[0].get_task_group_string()]
+    assert len(twin) > 1
+    twin[-1].task_group_max_hosts += 1
+    with pytest.raises(L.EvgError):
+        S.intern_columns(batch, 3)
+    assert S.intern_columns([], 1)["group_off"].tolist() == [0]
+
+
 def test_take_distros_is_the_same_tick_per_distro():
     """synth.take_distros (what a rank of the sharded bench uploads): the oracle plans a distro of the sub-tick exactly as it
     plans it inside the whole tick -- order, TotalValue, allocator decision."""
