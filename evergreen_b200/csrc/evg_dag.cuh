@@ -8,7 +8,7 @@
 // topo.SortStabilized (gonum v0.17.0, not vendored; restated in oracle/oracle_dag.py) is Tarjan's algorithm over
 // nodes and successors taken in DESCENDING queueIndex, its emission order reversed: for a DAG, the reverse
 // post-order of that depth-first search.  A lexicographic DFS order is inherently sequential (the problem is
-// P-complete), and a persisted queue holds at most 10 000 items, so one THREAD walks one distro's graph -- successor
+// P-complete), and a persisted queue holds at most 10 000 items, so one THREAD (lane 0 of a warp of its own) walks one distro's graph -- successor
 // lists built by a counting pass, an explicit call stack, everything in that distro's slice of global scratch -- and
 // the batch's parallelism is across distros.  The task-group buckets are a segmented stable merge sort by
 // (group id, GroupIndex): one thread per item and pass.
@@ -35,8 +35,10 @@ struct DDag {
 
 __global__ void __launch_bounds__(64) k_dag_topo(DDag X, int32_t* __restrict__ sorted, int32_t* __restrict__ n_sorted,
                                                  int32_t* __restrict__ n_cycles) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= X.n_distros) return;
+  // one WARP per queue, its first lane walking: 32 walks in one warp diverge at every step and run one after the other
+  // (measured: 200 queues of 10 000 items 216 ms with a thread per queue)
+  const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (d >= X.n_distros || (threadIdx.x & 31) != 0) return;
   const int64_t base = X.item_off[d];
   const int n = int(X.item_off[d + 1] - base);
   const int64_t ebase = n > 0 ? X.dep_off[base] : 0;

@@ -2659,7 +2659,7 @@ int evg_dag_rebuild_batch(evg_ctx* c, const evg_dag_in* in, const int64_t* item_
   int32_t* d_nsorted = c->b_rn6.as<int32_t>();
   int32_t* d_ncycles = d_nsorted + (D + 1);
   int32_t* d_grouped = d_ncycles + (D + 1);
-  LAUNCH(c, k_dag_topo, grid_for(D, 64), 64, x, c->b_order.as<int32_t>(), d_nsorted, d_ncycles);
+  LAUNCH(c, k_dag_topo, grid_for(int64_t(D) * 32, 64), 64, x, c->b_order.as<int32_t>(), d_nsorted, d_ncycles);
   std::vector<int32_t> grouped(size_t(D), 0);
   int32_t* buf[2] = {c->b_rn3.as<int32_t>(), c->b_rn4.as<int32_t>()};
   int cur = 0;
